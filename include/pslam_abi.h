@@ -1,0 +1,108 @@
+/* pslam_abi.h — C ABI of the B200-native PlanarSLAM per-frame hot path (libpslam_b200.so).
+ *
+ * The reference (yanyan-li/PlanarSLAM) has no plugin/FFI layer: its seam is a set of C++ methods called
+ * from Frame / Tracking.  Each entry point below replaces one of those methods with plain
+ * pointers and sizes; include/pslam_adapter.hpp re-creates the reference's C++ signatures on top of it.
+ *
+ * Conventions: every function returns 0 on success or a negative pslam_status; nothing throws; the callee
+ * never allocates caller-visible memory (the caller passes capacities); a context is bound to one GPU and is
+ * used by one thread at a time (the reference calls ORB / LSD / PEAC from three threads: use one context
+ * per thread, they are re-entrant across contexts).  There is NO CPU fallback: creation fails with
+ * PSLAM_E_NO_DEVICE when no sm_100 device is present.
+ *
+ * "_dev" variants take device pointers and enqueue on the context's stream without synchronising
+ * (inputs already resident in HBM); the plain variants take host pointers, copy in, run, copy out and
+ * synchronise — that is the call a Frame-constructor replacement makes.
+ */
+#ifndef PSLAM_ABI_H_
+#define PSLAM_ABI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pslam_status {
+    PSLAM_OK = 0,
+    PSLAM_E_INVALID = -1,    /* bad argument (null pointer, size mismatch, unsupported parameter) */
+    PSLAM_E_NO_DEVICE = -2,  /* no CUDA device / not sm_100 */
+    PSLAM_E_CUDA = -3,       /* CUDA runtime error; see pslam_last_error() */
+    PSLAM_E_CAPACITY = -4,   /* an internal or caller capacity was exceeded (results truncated) */
+    PSLAM_E_NCCL = -5
+} pslam_status;
+
+/* Layout-compatible with cv::KeyPoint {Point2f pt; float size, angle, response; int octave, class_id}
+ * as filled by ORBextractor::operator() (src/ORBextractor.cc:1043-1105). 28 bytes. */
+typedef struct pslam_keypoint {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} pslam_keypoint;
+
+/* Parameters of the reference constructors / settings file that the hot path reads
+ * (ORBextractor ctor include/ORBextractor.h:51-52; Examples/RGB-D/TUM3.yaml:8-55). */
+typedef struct pslam_config {
+    int32_t device;        /* CUDA ordinal */
+    int32_t width, height; /* frame size, all frames of a context share it */
+    int32_t max_batch;     /* frames processed per batched call (>= 1) */
+    /* ORB */
+    int32_t nfeatures;     /* ORBextractor.nFeatures   (1000) */
+    float scale_factor;    /* ORBextractor.scaleFactor (1.2)  */
+    int32_t nlevels;       /* ORBextractor.nLevels     (8, max 8) */
+    int32_t ini_th_fast;   /* ORBextractor.iniThFAST   (20) */
+    int32_t min_th_fast;   /* ORBextractor.minThFAST   (7), must be <= ini_th_fast */
+    /* camera (Camera.fx .. DepthMapFactor); float like the reference's cv::Mat K (CV_32F) */
+    float fx, fy, cx, cy;
+    float depth_scale;     /* metres per depth unit = 1 / DepthMapFactor, as float (src/Tracking.cc) */
+} pslam_config;
+
+typedef struct pslam_ctx pslam_ctx;
+
+/* Fill cfg with the reference defaults for TUM3.yaml at the given size / batch. */
+void pslam_default_config(pslam_config* cfg, int width, int height, int max_batch);
+
+int pslam_create(const pslam_config* cfg, pslam_ctx** out);
+void pslam_destroy(pslam_ctx* ctx);
+const char* pslam_last_error(const pslam_ctx* ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t / CUstream as void*); NULL restores the context's own. */
+int pslam_set_stream(pslam_ctx* ctx, void* cuda_stream);
+int pslam_synchronize(pslam_ctx* ctx);
+/* Number of kernel launches this context has issued since creation (bench.py's gpu_launches claim). */
+int64_t pslam_launch_count(const pslam_ctx* ctx);
+
+/* ---- ORB extraction -------------------------------------------------------------------------------
+ * Replaces  void ORBextractor::operator()(InputArray image, InputArray mask, vector<KeyPoint>&, OutputArray desc)
+ *           include/ORBextractor.h:59-61, src/ORBextractor.cc:1043-1105   (mask is ignored there too).
+ * Scale tables replace the getters include/ORBextractor.h:63-83 (read by Frame.cc:65-71).
+ */
+int pslam_orb_get_scale_tables(const pslam_ctx* ctx, float* scale, float* inv_scale, float* sigma2,
+                               float* inv_sigma2, int32_t* features_per_level /* each nlevels long, may be NULL */);
+
+/* One frame, host buffers. gray: height rows of `stride` bytes. kps/desc: room for `cap` keypoints
+ * (desc is cap x 32 bytes).  *n receives the number found; if it exceeds cap the first cap are written and
+ * PSLAM_E_CAPACITY is returned.  pslam_orb_max_keypoints() is always enough. */
+int pslam_orb_extract(pslam_ctx* ctx, const uint8_t* gray, int stride, pslam_keypoint* kps, uint8_t* desc,
+                      int cap, int32_t* n);
+int pslam_orb_max_keypoints(const pslam_ctx* ctx);
+
+/* Batched: nframes <= max_batch images, each height x width, densely packed (frame stride = width*height).
+ * Outputs are [nframes][cap] keypoints, [nframes][cap][32] descriptor bytes, [nframes] counts. */
+int pslam_orb_extract_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, pslam_keypoint* kps,
+                            uint8_t* desc, int cap, int32_t* n);
+/* Same with device pointers; asynchronous on the context's stream. */
+int pslam_orb_extract_batch_dev(pslam_ctx* ctx, const uint8_t* d_gray, int nframes, pslam_keypoint* d_kps,
+                                uint8_t* d_desc, int cap, int32_t* d_n);
+
+/* Stage outputs of the most recent ORB call, for stage-by-stage parity tests (host buffers; synchronises).
+ * Level pixels are the borderless level (the reference's mvImagePyramid ROI, include/ORBextractor.h:85). */
+int pslam_orb_debug_level_size(const pslam_ctx* ctx, int level, int32_t* w, int32_t* h);
+int pslam_orb_debug_level_pixels(pslam_ctx* ctx, int frame, int level, uint8_t* out /* w*h */);
+int pslam_orb_debug_level_blurred(pslam_ctx* ctx, int frame, int level, uint8_t* out /* w*h */);
+/* FAST candidates of a level in the reference's order (cell-major, row-major inside a cell), as int32
+ * triples (x, y, score) relative to (16,16) like vToDistributeKeys (src/ORBextractor.cc:820-825). */
+int pslam_orb_debug_level_candidates(pslam_ctx* ctx, int frame, int level, int32_t* xys, int cap, int32_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSLAM_ABI_H_ */

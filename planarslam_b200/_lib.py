@@ -1,0 +1,112 @@
+"""ctypes binding of libpslam_b200.so (the C ABI in include/pslam_abi.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no sm_100 GPU is present the
+import / context creation fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpslam_b200.so")
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+assert KEYPOINT_DTYPE.itemsize == 28
+
+PSLAM_OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_NCCL = 0, -1, -2, -3, -4, -5
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32),
+                ("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("depth_scale", C.c_float)]
+
+
+class PslamError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pslam error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32p, i32p, u8p = C.c_void_p, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
+    L.pslam_default_config.argtypes = [C.POINTER(Config), i32, i32, i32]; L.pslam_default_config.restype = None
+    L.pslam_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.pslam_destroy.argtypes = [vp]; L.pslam_destroy.restype = None
+    L.pslam_last_error.argtypes = [vp]; L.pslam_last_error.restype = C.c_char_p
+    L.pslam_set_stream.argtypes = [vp, vp]
+    L.pslam_synchronize.argtypes = [vp]
+    L.pslam_launch_count.argtypes = [vp]; L.pslam_launch_count.restype = C.c_int64
+    L.pslam_orb_get_scale_tables.argtypes = [vp, f32p, f32p, f32p, f32p, i32p]
+    L.pslam_orb_max_keypoints.argtypes = [vp]
+    L.pslam_orb_extract.argtypes = [vp, u8p, i32, vp, vp, i32, i32p]
+    L.pslam_orb_extract_batch.argtypes = [vp, u8p, i32, vp, vp, i32, vp]
+    L.pslam_orb_extract_batch_dev.argtypes = [vp, vp, i32, vp, vp, i32, vp]
+    L.pslam_orb_debug_level_size.argtypes = [vp, i32, i32p, i32p]
+    L.pslam_orb_debug_level_pixels.argtypes = [vp, i32, i32, vp]
+    L.pslam_orb_debug_level_blurred.argtypes = [vp, i32, i32, vp]
+    L.pslam_orb_debug_level_candidates.argtypes = [vp, i32, i32, vp, i32, i32p]
+    _lib = L
+    return L
+
+
+class Context:
+    """Owns one pslam_ctx (one GPU, one stream)."""
+
+    def __init__(self, width: int, height: int, max_batch: int = 1, device: int = 0, **overrides):
+        L = lib()
+        cfg = Config()
+        L.pslam_default_config(C.byref(cfg), width, height, max_batch)
+        cfg.device = device
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError(f"unknown config field {k}")
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = L.pslam_create(C.byref(cfg), C.byref(h))
+        if rc != PSLAM_OK:
+            raise PslamError(rc, "pslam_create failed (no sm_100 GPU, or invalid configuration; see stderr)")
+        self.h = h
+        self.L = L
+
+    def check(self, rc: int, allow_capacity: bool = False) -> int:
+        if rc == PSLAM_OK or (allow_capacity and rc == E_CAPACITY):
+            return rc
+        raise PslamError(rc, self.L.pslam_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pslam_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self.check(self.L.pslam_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def synchronize(self):
+        self.check(self.L.pslam_synchronize(self.h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.pslam_launch_count(self.h))

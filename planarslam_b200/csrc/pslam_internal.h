@@ -1,0 +1,102 @@
+// Internal declarations shared by the translation units of libpslam_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/pslam_abi.h"
+
+#define PSLAM_MAX_LEVELS 8
+
+namespace pslam {
+
+// Geometry of one pyramid level and of its FAST cell grid (reference: src/ORBextractor.cc:771-806, :1107-1116).
+struct LevelGeom {
+    int w, h, pitch;          // pitch: bytes per row in the pyramid buffer (multiple of 16); level 0 lives in the input
+    int pyr_off;              // byte offset of the level inside one frame's pyramid buffer (level 0: unused)
+    int blur_off, blur_pitch; // the blurred copy of the level (all levels, incl. 0) inside one frame's blur buffer
+    int n_cols, n_rows;       // FAST cell grid
+    int w_cell, h_cell;
+    int max_bx, max_by;       // maxBorderX/Y (minBorder is 16)
+    int cell_base;            // index of this level's first cell among all cells of a frame
+    int slot_cap;             // candidate slots per cell
+    int slot_base;            // index of this level's first slot among all slots of a frame
+    int quota;                // mnFeaturesPerLevel
+    int kp_cap;               // quota + 3 (the quadtree can overshoot by at most 2)
+    int kp_base;              // first row of this level in the per-frame level-keypoint scratch
+    int cand_cap;             // capacity of the ordered candidate list fed to the quadtree
+    int cand_base;            // first entry of this level in the per-frame candidate scratch
+    int node_cap, node_base;  // quadtree node pool
+    int tabx_off, taby_off;   // offsets of this level's resize tables (x: w entries, y: h entries) in the table buffers
+    int n_ini; float h_x;     // quadtree roots (reference DistributeOctTree :543-545)
+    int work_base;            // first int of this level in the per-frame quadtree scratch
+    float scale;              // mvScaleFactor[level]
+    int patch_size;           // (int)(31 * scale)
+};
+
+struct OrbGeom {
+    int nlevels;
+    int width, height;
+    int total_cells, total_slots, total_kp, total_cand, total_nodes, total_work, total_tabx, total_taby;
+    int pyr_bytes;            // per frame, levels 1..n-1
+    LevelGeom lv[PSLAM_MAX_LEVELS];
+    int ini_th, min_th;
+    int umax[16];
+};
+
+}  // namespace pslam
+
+struct pslam_ctx {
+    pslam_config cfg;
+    pslam::OrbGeom geom;
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int64_t launches = 0;
+    std::string err;
+    int last_nframes = 0;
+
+    // device buffers (sized for cfg.max_batch frames)
+    uint8_t* d_gray = nullptr;        // staging copy of host input (host-pointer entry points)
+    const uint8_t* d_gray_cur = nullptr;  // input of the most recent call (staging or caller's device buffer)
+    uint8_t* d_pyr = nullptr;         // levels 1.. of every frame
+    uint8_t* d_blur = nullptr;        // blurred levels 0.. of every frame (same layout incl. level 0)
+    int blur_frame_bytes = 0;
+    int16_t* d_xofs = nullptr; int16_t* d_xa = nullptr;   // resize tables: source column, (alpha0, alpha1) pairs
+    int16_t* d_yofs = nullptr; int16_t* d_ya = nullptr;
+    uint32_t* d_slots = nullptr;      // per-cell candidate slots (packed x | y<<11 | score<<22)
+    int32_t* d_cell_cnt = nullptr;    // per-cell candidate counts
+    uint32_t* d_cand = nullptr;       // ordered candidates per (frame, level), ping-pong x2
+    int32_t* d_cand_cnt = nullptr;    // [frame][level]
+    int4* d_nodes = nullptr;          // quadtree node pool
+    int2* d_links = nullptr;
+    int32_t* d_work = nullptr;        // quadtree scratch (expandable lists, list-order array)
+    uint32_t* d_lvl_kp = nullptr;     // selected keypoints per (frame, level) in list order (packed)
+    int32_t* d_lvl_cnt = nullptr;     // [frame][level]
+    int32_t* d_status = nullptr;      // per-frame capacity flags
+    pslam_keypoint* d_kps = nullptr;  // outputs for host-pointer entry points
+    uint8_t* d_desc = nullptr;
+    int32_t* d_n = nullptr;
+    // pinned host staging
+    uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
+    int32_t* h_status = nullptr;
+};
+
+namespace pslam {
+int set_error(pslam_ctx* c, int code, const std::string& msg);
+int check_cuda(pslam_ctx* c, cudaError_t e, const char* what);
+// ORB pipeline (orb_pipeline.cu)
+int orb_build_geometry(pslam_ctx* c);
+int orb_alloc(pslam_ctx* c);
+void orb_free(pslam_ctx* c);
+int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint* d_kps, uint8_t* d_desc, int cap,
+                int32_t* d_n);
+}  // namespace pslam
+
+#define PSLAM_CUDA(c, call)                                                   \
+    do {                                                                      \
+        int _rc = pslam::check_cuda((c), (call), #call);                      \
+        if (_rc != PSLAM_OK) return _rc;                                      \
+    } while (0)

@@ -1,0 +1,101 @@
+"""ctypes access to the CPU oracle (oracle/_build/liboracle.so). Test infrastructure only."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                           ("octave", "<i4"), ("class_id", "<i4")])
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_PATH):
+            subprocess.run(["make"], cwd=os.path.join(ROOT, "oracle"), check=True, stdout=subprocess.DEVNULL)
+        L = C.CDLL(_PATH)
+        vp, i = C.c_void_p, C.c_int
+        L.orc_orb_create.restype = vp
+        L.orc_orb_create.argtypes = [i, C.c_float, i, i, i]
+        L.orc_orb_destroy.argtypes = [vp]
+        L.orc_orb_extract.argtypes = [vp, vp, i, i, i, vp, vp, i]
+        L.orc_orb_level_size.argtypes = [vp, i, C.POINTER(i), C.POINTER(i)]
+        L.orc_orb_level_pixels.argtypes = [vp, i, vp]
+        L.orc_orb_level_candidates.argtypes = [vp, i, vp, i]
+        L.orc_orb_level_keypoints.argtypes = [vp, i, vp, i]
+        L.orc_orb_tables.argtypes = [vp] + [vp] * 6
+        L.orc_orb_describe.argtypes = [vp, vp, i, i, C.c_float, C.c_float, C.c_float, vp]
+        L.orc_orb_ic_angle.argtypes = [vp, vp, i, i, i, i]
+        L.orc_orb_ic_angle.restype = C.c_float
+        L.orc_resize_linear_u8.argtypes = [vp, i, i, i, vp, i, i]
+        L.orc_border_reflect101.argtypes = [vp, i, i, i, vp, i]
+        L.orc_gaussian_blur_7x7_s2.argtypes = [vp, i, i, i, vp]
+        L.orc_fast_detect.argtypes = [vp, i, i, i, i, vp, i]
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_cv_round.argtypes = [C.c_double]
+        _lib = L
+    return _lib
+
+
+class OrbOracle:
+    def __init__(self, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.h = self.L.orc_orb_create(nfeatures, scale, nlevels, ini_th, min_th)
+        self.nlevels = nlevels
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_orb_destroy(self.h)
+            self.h = None
+
+    def extract(self, gray: np.ndarray):
+        gray = np.ascontiguousarray(gray)
+        h, w = gray.shape
+        cap = 8192
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_orb_extract(self.h, gray.ctypes.data, w, h, w, kps.ctypes.data, desc.ctypes.data, cap)
+        assert n <= cap
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l: int) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        assert self.L.orc_orb_level_size(self.h, l, C.byref(w), C.byref(h)) == 0
+        out = np.zeros((h.value, w.value), np.uint8)
+        self.L.orc_orb_level_pixels(self.h, l, out.ctypes.data)
+        return out
+
+    def candidates(self, l: int) -> np.ndarray:
+        buf = np.zeros((200000, 3), np.int32)
+        n = self.L.orc_orb_level_candidates(self.h, l, buf.ctypes.data, 200000)
+        return buf[:n].copy()
+
+    def level_keypoints(self, l: int) -> np.ndarray:
+        buf = np.zeros(8192, KEYPOINT_DTYPE)
+        n = self.L.orc_orb_level_keypoints(self.h, l, buf.ctypes.data, 8192)
+        return buf[:n].copy()
+
+    def tables(self):
+        f = [np.zeros(self.nlevels, np.float32) for _ in range(4)]
+        q = np.zeros(self.nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.orc_orb_tables(self.h, *[a.ctypes.data for a in f], q.ctypes.data, um.ctypes.data)
+        return f + [q, um]
+
+
+def orb_extract(gray, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7):
+    return OrbOracle(nfeatures, scale, nlevels, ini_th, min_th).extract(gray)
+
+
+def blur(gray: np.ndarray) -> np.ndarray:
+    gray = np.ascontiguousarray(gray)
+    out = np.empty_like(gray)
+    lib().orc_gaussian_blur_7x7_s2(gray.ctypes.data, gray.shape[1], gray.shape[0], gray.shape[1], out.ctypes.data)
+    return out
