@@ -72,23 +72,30 @@ __device__ __forceinline__ int fast_score(const uint8_t (*win)[FAST_WIN_MAX + 4]
         const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
         if (nb < 2 && nd < 2) return 0;
     }
-    int d[16];
-    d[0] = v - p0;              d[1] = v - win[y + 3][x + 1];  d[2] = v - win[y + 2][x + 2];  d[3] = v - win[y + 1][x + 3];
-    d[4] = v - p4;              d[5] = v - win[y - 1][x + 3];  d[6] = v - win[y - 2][x + 2];  d[7] = v - win[y - 3][x + 1];
-    d[8] = v - p8;              d[9] = v - win[y - 3][x - 1];  d[10] = v - win[y - 2][x - 2]; d[11] = v - win[y - 1][x - 3];
-    d[12] = v - p12;            d[13] = v - win[y + 1][x - 3]; d[14] = v - win[y + 2][x - 2]; d[15] = v - win[y + 3][x - 1];
-    int mn[16], mx[16];
+    // d = centre - circle (dark arcs), e = circle - centre (bright arcs).  Both polarities use min-chains only:
+    // nvcc 12.9 / sm_100a miscompiles max(x, -y) when it is folded into a 3-input VIMNMX (observed on B200:
+    // max(0, max(-4, -203)) evaluated to 203), so no negation may appear inside a min/max operand here.
+    int d[16], e[16];
+    const int c1 = win[y + 3][x + 1], c2 = win[y + 2][x + 2], c3 = win[y + 1][x + 3], c5 = win[y - 1][x + 3];
+    const int c6 = win[y - 2][x + 2], c7 = win[y - 3][x + 1], c9 = win[y - 3][x - 1], c10 = win[y - 2][x - 2];
+    const int c11 = win[y - 1][x - 3], c13 = win[y + 1][x - 3], c14 = win[y + 2][x - 2], c15 = win[y + 3][x - 1];
+    d[0] = v - p0;   d[1] = v - c1;   d[2] = v - c2;   d[3] = v - c3;   d[4] = v - p4;   d[5] = v - c5;   d[6] = v - c6;   d[7] = v - c7;
+    d[8] = v - p8;   d[9] = v - c9;   d[10] = v - c10; d[11] = v - c11; d[12] = v - p12; d[13] = v - c13; d[14] = v - c14; d[15] = v - c15;
+    e[0] = p0 - v;   e[1] = c1 - v;   e[2] = c2 - v;   e[3] = c3 - v;   e[4] = p4 - v;   e[5] = c5 - v;   e[6] = c6 - v;   e[7] = c7 - v;
+    e[8] = p8 - v;   e[9] = c9 - v;   e[10] = c10 - v; e[11] = c11 - v; e[12] = p12 - v; e[13] = c13 - v; e[14] = c14 - v; e[15] = c15 - v;
+    int d2[16], e2[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { mn[i] = min(d[i], d[(i + 1) & 15]); mx[i] = max(d[i], d[(i + 1) & 15]); }       // 2
-    int mn4[16], mx4[16];
+    for (int i = 0; i < 16; ++i) { d2[i] = min(d[i], d[(i + 1) & 15]); e2[i] = min(e[i], e[(i + 1) & 15]); }           // arcs of 2
+    int d4[16], e4[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { mn4[i] = min(mn[i], mn[(i + 2) & 15]); mx4[i] = max(mx[i], mx[(i + 2) & 15]); } // 4
+    for (int i = 0; i < 16; ++i) { d4[i] = min(d2[i], d2[(i + 2) & 15]); e4[i] = min(e2[i], e2[(i + 2) & 15]); }       // arcs of 4
     int best = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int m8 = min(mn4[i], mn4[(i + 4) & 15]), M8 = max(mx4[i], mx4[(i + 4) & 15]);                       // 8
-        const int m9 = min(m8, d[(i + 8) & 15]), M9 = max(M8, d[(i + 8) & 15]);                                    // 9
-        best = max(best, max(m9, -M9));
+        const int d9 = min(min(d4[i], d4[(i + 4) & 15]), d[(i + 8) & 15]);                                            // arcs of 9
+        const int e9 = min(min(e4[i], e4[(i + 4) & 15]), e[(i + 8) & 15]);
+        best = max(best, d9);
+        best = max(best, e9);
     }
     const int s = best - 1;
     return s >= min_th ? s : 0;

@@ -68,7 +68,7 @@ int orb_build_geometry(pslam_ctx* c) {
         v.quota = c->quota[l];
         v.kp_cap = v.quota + 3;
         v.kp_base = kp; kp += v.kp_cap;
-        v.cand_cap = std::min(v.n_cols * v.n_rows * v.slot_cap, std::max(8192, 40 * v.quota));
+        v.cand_cap = v.n_cols * v.n_rows * v.slot_cap;                    // every slot can be filled (noise images)
         v.cand_base = cand; cand += v.cand_cap;
         v.node_cap = 24 * v.kp_cap + 64;
         v.node_base = nodes; nodes += v.node_cap;

@@ -48,7 +48,7 @@ def camera_pose(frame: int, n_frames: int = 64) -> tuple[np.ndarray, np.ndarray]
     """World-from-camera rotation R_wc (3x3) and camera centre t_wc for a smooth path."""
     s = frame / max(n_frames, 1)
     yaw = 0.25 * np.sin(2 * np.pi * s) + 0.35
-    pitch = 0.12 * np.cos(2 * np.pi * s) + 0.18
+    pitch = -(0.10 * np.cos(2 * np.pi * s) + 0.30)
     roll = 0.05 * np.sin(4 * np.pi * s)
     cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
     Ry = np.array([[cy, 0, -sy], [0, 1, 0], [sy, 0, cy]])
@@ -105,7 +105,17 @@ def render_frame(seed: int, frame: int = 0, width: int = 640, height: int = 480,
         zn = z + rng.normal(0.0, 1.0, z.shape) * sigma
     d16 = np.clip(np.rint(zn * DEPTH_FACTOR), 0, 65535).astype(np.uint16)
     if hole_frac > 0:
-        d16[rng.random(z.shape) < hole_frac] = 0
+        # Kinect-like dropouts are clustered (specular spots, occlusion shadows), not i.i.d. pixels: paint random
+        # discs until about hole_frac of the image is invalid.  (PEAC's INIT_STRICT rejects any 10x10 block that
+        # contains a single zero, so i.i.d. holes at 2 % would wipe out 87 % of the blocks.)
+        yy, xx = np.mgrid[0:height, 0:width]
+        target = hole_frac * width * height
+        covered = 0.0
+        while covered < target:
+            hx, hy = rng.uniform(0, width), rng.uniform(0, height)
+            hr = rng.uniform(2.0, 9.0) * width / 640.0
+            d16[(xx - hx) ** 2 + (yy - hy) ** 2 < hr * hr] = 0
+            covered += np.pi * hr * hr
     d16[z <= 0] = 0
     return gray8, d16, z.astype(np.float32), (R, t)
 
