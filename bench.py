@@ -1,0 +1,290 @@
+#!/usr/bin/env python3
+"""bench.py — RGB-D frames/s of the PlanarSLAM per-frame hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch of synthetic 640x480 RGB-D frames (seeded "room corner"
+sequence, planarslam_b200/synth.py).  Frames are independent units, so ranks shard them with no data-path
+collective (weak scaling: every rank processes FRAMES_PER_STEP frames per step).
+
+Prints ONE JSON line on rank 0 (see DESIGN.md §measurement for every field):
+  value      frames/s, inputs already resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e        frames/s through the host-pointer C-ABI call (pinned H2D of the frames + D2H of keypoints,
+             descriptors, plane labels inside the timed region)
+  roofline   dominant kernel: algorithmic bytes per launch / its mean launch time (event-bracketed, measured live
+             in a separate pass of the same workload) vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (a restatement of the reference, NOT the original binary) timed on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H = 640, 480
+SUB_BATCH = 64            # frames per library call (context max_batch)
+SUBS_PER_STEP = 4         # library calls per step -> 256 frames = 236 MB of gray+depth input, larger than the 126 MB L2
+FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
+DISTINCT_FRAMES = 16      # rendered once (CPU, ~0.4 s each) and tiled with a per-copy intensity offset
+
+# Algorithmic bytes per 640x480 frame of each kernel family (restated in DESIGN.md §kernels)
+ALGO_BYTES = {
+    "orb_resize_level": 926546 + 850812,      # read levels 0-6 once, write levels 1-7 (borderless)
+    "orb_fast_cells": 950532 + 30000 * 4,     # read every level once, write <= 30k packed candidates
+    "orb_blur_level": 2 * 950532,             # read + write every level once
+    "orb_quadtree": 30000 * 4 * 2,
+    "orb_orient_describe": 1000 * (709 + 512 + 60),
+}
+
+
+def _peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def make_frames(n_distinct=DISTINCT_FRAMES):
+    from planarslam_b200 import synth
+    g, d = synth.render_sequence(seed=2, n=n_distinct, width=W, height=H)
+    return g, d
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while the timed region runs (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_oracle_fps(gray, depth, seconds=12.0, threads=1):
+    """Frames/s of the CPU oracle (oracle/, a restatement of the reference compiled -O2, scalar) on `threads`
+    host threads over a bounded sample of the same frames."""
+    import oracle_lib
+    from concurrent.futures import ThreadPoolExecutor
+    oracle_lib.lib()
+    n = len(gray)
+
+    def work(i):
+        oracle_lib.orb_extract(gray[i % n])      # ctypes releases the GIL inside the C call
+        return 1
+
+    work(0)                                      # warm
+    t0 = time.perf_counter()
+    done = 0
+    with ThreadPoolExecutor(threads) as ex:
+        while time.perf_counter() - t0 < seconds:
+            done += sum(ex.map(work, range(done, done + threads)))
+    dt = time.perf_counter() - t0
+    return done / dt, done
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path cannot be built here (OpenCV/Eigen/PCL absent),
+    so this arm times the oracle port on all host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    gray, depth = make_frames(4)
+    cores = os.cpu_count() or 1
+    vals = []
+    for _ in range(max(args.warmup, 0) + max(args.steps, 1)):
+        fps, n = cpu_oracle_fps(gray, depth, seconds=6.0, threads=cores)
+        vals.append(fps)
+    v = float(np.mean(vals[max(args.warmup, 0):]))
+    line = {"impl": "reference", "metric": "rgbd_frames_per_sec_640x480", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * FRAMES_PER_STEP / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+            "config": workload_config(),
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"oracle ORB stage on {len(gray)} frames looped for 6 s per step, {cores} threads"},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config():
+    return {"workload": "640x480 synthetic RGB-D sequence, ORB front end (1000 feats, 8 levels) [stages built so far: orb]",
+            "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "l2": "inputs_larger_than_l2",
+            "stages": ["orb"]}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from planarslam_b200._lib import Context, KEYPOINT_DTYPE
+
+    gray, depth = make_frames()
+    reps = FRAMES_PER_STEP // DISTINCT_FRAMES
+    gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * r, 0, 255).astype(np.uint8) for r in range(reps)])
+    dev = torch.device("cuda", local_rank)
+    ctx = Context(W, H, SUB_BATCH, device=local_rank)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    cap = ctx.L.pslam_orb_max_keypoints(ctx.h)
+
+    d_gray = torch.from_numpy(gray_step).to(dev)                       # [FRAMES_PER_STEP, H, W] resident in HBM
+    d_kps = torch.empty((FRAMES_PER_STEP, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((FRAMES_PER_STEP, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.empty(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
+    h_gray = torch.from_numpy(gray_step).pin_memory()
+    h_kps = np.zeros((SUB_BATCH, cap), KEYPOINT_DTYPE)
+    h_desc = np.zeros((SUB_BATCH, cap, 32), np.uint8)
+    h_n = np.zeros(SUB_BATCH, np.int32)
+
+    def step_dev():
+        for s in range(SUBS_PER_STEP):
+            o = s * SUB_BATCH
+            ctx.check(ctx.L.pslam_orb_extract_batch_dev(ctx.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps[o].data_ptr(), d_desc[o].data_ptr(),
+                                                        cap, d_n[o:].data_ptr()))
+
+    def step_e2e():
+        for s in range(SUBS_PER_STEP):
+            o = s * SUB_BATCH
+            ctx.check(ctx.L.pslam_orb_extract_batch(ctx.h, h_gray[o].data_ptr(), SUB_BATCH, h_kps.ctypes.data, h_desc.ctypes.data, cap,
+                                                    h_n.ctypes.data))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    launches = ctx.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    n_found = int(d_n.sum().item())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * FRAMES_PER_STEP * args.steps / (ms_max / 1e3)
+
+    # ---- end to end through the host-pointer ABI ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, args.steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
+    h2d = FRAMES_PER_STEP * W * H
+    d2h = FRAMES_PER_STEP * (cap * 60 + 8)
+
+    # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
+    ctx.profile(True)
+    step_dev()
+    rep = ctx.profile_report()
+    ctx.profile(False)
+    peak, peak_kind = _peaks()
+    per_kernel = {}
+    for name, (n, tot_ms) in rep.items():
+        launches_per_frame_batch = n / SUBS_PER_STEP
+        bytes_per_launch = ALGO_BYTES.get(name, 0) * SUB_BATCH / max(launches_per_frame_batch, 1)
+        per_kernel[name] = {"launches": n, "ms_total": round(tot_ms, 4), "share": None,
+                            "achieved_gbs": round(bytes_per_launch / (tot_ms / n * 1e-3) / 1e9, 2)}
+    tot = sum(v["ms_total"] for v in per_kernel.values()) or 1.0
+    for v in per_kernel.values():
+        v["share"] = round(v["ms_total"] / tot, 4)
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_total"])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 5), "traffic": None, "peak_kind": peak_kind,
+                "per_kernel": per_kernel}
+
+    if rank == 0:
+        cpu_fps, cpu_n = cpu_oracle_fps(gray, depth, seconds=12.0, threads=1)
+        line = {"metric": "rgbd_frames_per_sec_640x480", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(),
+                "clocks": sampler.summary(), "gpu_launches": int(launches),
+                "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                                 "sample": f"oracle (restatement of the reference, -O2, scalar) ORB stage, {cpu_n} frames in ~12 s"},
+                "keypoints_per_frame": n_found / FRAMES_PER_STEP}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,12 @@ int pslam_synchronize(pslam_ctx* ctx);
 /* Number of kernel launches this context has issued since creation (bench.py's gpu_launches claim). */
 int64_t pslam_launch_count(const pslam_ctx* ctx);
 
+/* Per-kernel timing for the roofline report: when enabled every kernel launch is bracketed by a CUDA event pair
+ * on the launching stream (do not enable inside a timed throughput region).  pslam_profile_report() synchronises
+ * and writes one line per kernel name: "<name> <launches> <total_ms>\n". Enabling again clears the records. */
+int pslam_profile_enable(pslam_ctx* ctx, int on);
+int pslam_profile_report(pslam_ctx* ctx, char* buf, int cap);
+
 /* ---- ORB extraction -------------------------------------------------------------------------------
  * Replaces  void ORBextractor::operator()(InputArray image, InputArray mask, vector<KeyPoint>&, OutputArray desc)
  *           include/ORBextractor.h:59-61, src/ORBextractor.cc:1043-1105   (mask is ignored there too).
@@ -101,6 +107,42 @@ int pslam_orb_debug_level_blurred(pslam_ctx* ctx, int frame, int level, uint8_t*
 /* FAST candidates of a level in the reference's order (cell-major, row-major inside a cell), as int32
  * triples (x, y, score) relative to (16,16) like vToDistributeKeys (src/ORBextractor.cc:820-825). */
 int pslam_orb_debug_level_candidates(pslam_ctx* ctx, int frame, int level, int32_t* xys, int cap, int32_t* n);
+
+/* ---- PEAC plane extraction ------------------------------------------------------------------------
+ * Replaces  bool PlaneDetection::readDepthImage(cv::Mat depth16U, cv::Mat& K, float kScaleFactor)   src/PlaneExtractor.cpp:26-57
+ *           void PlaneDetection::runPlaneDetection(int H, int W)                                     src/PlaneExtractor.cpp:59-65
+ * and the public results Frame::ComputePlanes reads (src/Frame.cc:652-672): plane_num_, plane_vertices_
+ * (member_idx / member_off), plane_filter.extractedPlanes[i]->{normal, center, N, mse} (pslam_plane), membershipImg (labels).
+ * Camera intrinsics and the depth scale come from pslam_config (fx, fy, cx, cy, depth_scale).
+ * The organised cloud is never materialised: x = (j - cx) z / fx etc. are recomputed in double where needed. */
+typedef struct pslam_plane {
+    double normal[3];   /* unit normal pointing towards the camera (n . c <= 0) */
+    double center[3];   /* centre of mass; plane coefficients are (n, -n . c) as in src/Frame.cc:664-672 */
+    double mse, curvature;
+    int32_t N, rid;     /* supporting points before refinement; root block id */
+} pslam_plane;
+
+int pslam_peac_max_planes(const pslam_ctx* ctx);
+
+/* nframes depth images, each height x width uint16, densely packed.  Outputs per frame:
+ *   labels     [height*width] int32: final plane index, or a negative value for unlabelled pixels (the raw
+ *              region-growing trail counters -1..-6 of the reference's membershipImg)
+ *   planes     [pslam_peac_max_planes()] records, the first nplanes[f] valid, sorted by N descending
+ *   member_idx [height*width] pixel indices grouped by plane, ascending inside a plane (plane_vertices_)
+ *   member_off [pslam_peac_max_planes()+1] start offsets into member_idx; member_off[nplanes] = total
+ * member_idx / member_off may be NULL in the host variant. */
+int pslam_peac_run_batch(pslam_ctx* ctx, const uint16_t* depth, int nframes, int32_t* labels, pslam_plane* planes,
+                         int32_t* nplanes, int32_t* member_idx, int32_t* member_off);
+/* Device pointers (all required); asynchronous on the context's stream. */
+int pslam_peac_run_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes,
+                             int32_t* d_nplanes, int32_t* d_member_idx, int32_t* d_member_off);
+
+/* Stage outputs of the most recent PEAC call (host buffers; synchronises): per 10x10 block the nine running sums
+ * (sx sy sz sxx syy szz sxy syz sxz), {center[3], normal[3], mse, curvature}, point count and the "node kept" flag;
+ * the eroded block -> coarse plane map and the number of coarse planes before the last merge. */
+int pslam_peac_debug_blocks(pslam_ctx* ctx, int frame, double* st9, double* geo8, int32_t* n, uint8_t* valid);
+int pslam_peac_debug_coarse(pslam_ctx* ctx, int frame, int32_t* blk_map, int32_t* n_coarse);
+int pslam_peac_num_blocks(const pslam_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,9 @@ KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle"
                            ("octave", "<i4"), ("class_id", "<i4")])
 assert KEYPOINT_DTYPE.itemsize == 28
 
+PLANE_DTYPE = np.dtype([("normal", "<f8", 3), ("center", "<f8", 3), ("mse", "<f8"), ("curvature", "<f8"), ("N", "<i4"), ("rid", "<i4")])
+assert PLANE_DTYPE.itemsize == 72
+
 PSLAM_OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_NCCL = 0, -1, -2, -3, -4, -5
 
 
@@ -52,6 +55,8 @@ def lib() -> C.CDLL:
     L.pslam_set_stream.argtypes = [vp, vp]
     L.pslam_synchronize.argtypes = [vp]
     L.pslam_launch_count.argtypes = [vp]; L.pslam_launch_count.restype = C.c_int64
+    L.pslam_profile_enable.argtypes = [vp, i32]
+    L.pslam_profile_report.argtypes = [vp, C.c_char_p, i32]
     L.pslam_orb_get_scale_tables.argtypes = [vp, f32p, f32p, f32p, f32p, i32p]
     L.pslam_orb_max_keypoints.argtypes = [vp]
     L.pslam_orb_extract.argtypes = [vp, u8p, i32, vp, vp, i32, i32p]
@@ -61,6 +66,12 @@ def lib() -> C.CDLL:
     L.pslam_orb_debug_level_pixels.argtypes = [vp, i32, i32, vp]
     L.pslam_orb_debug_level_blurred.argtypes = [vp, i32, i32, vp]
     L.pslam_orb_debug_level_candidates.argtypes = [vp, i32, i32, vp, i32, i32p]
+    L.pslam_peac_max_planes.argtypes = [vp]
+    L.pslam_peac_num_blocks.argtypes = [vp]
+    L.pslam_peac_run_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.pslam_peac_run_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.pslam_peac_debug_blocks.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.pslam_peac_debug_coarse.argtypes = [vp, i32, vp, i32p]
     _lib = L
     return L
 
@@ -106,6 +117,19 @@ class Context:
 
     def synchronize(self):
         self.check(self.L.pslam_synchronize(self.h))
+
+    def profile(self, on: bool):
+        self.check(self.L.pslam_profile_enable(self.h, 1 if on else 0))
+
+    def profile_report(self) -> dict:
+        """{kernel name: (launches, total_ms)} since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.L.pslam_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, n, ms = line.split()
+            out[name] = (int(n), float(ms))
+        return out
 
     @property
     def launch_count(self) -> int:

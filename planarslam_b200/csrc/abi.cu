@@ -56,9 +56,11 @@ int pslam_create(const pslam_config* cfg, pslam_ctx** out) {
     c->cfg = *cfg;
     int rc = check_cuda(c, cudaSetDevice(cfg->device), "cudaSetDevice");
     if (rc == PSLAM_OK) rc = orb_build_geometry(c);
+    if (rc == PSLAM_OK) rc = peac_build_geometry(c);
     if (rc == PSLAM_OK) rc = check_cuda(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     c->stream = c->own_stream;
     if (rc == PSLAM_OK) rc = orb_alloc(c);
+    if (rc == PSLAM_OK) rc = peac_alloc(c);
     if (rc != PSLAM_OK) {
         std::fprintf(stderr, "pslam_create failed: %s\n", c->err.c_str());
         pslam_destroy(c);
@@ -73,6 +75,7 @@ void pslam_destroy(pslam_ctx* c) {
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
     orb_free(c);
+    peac_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -92,6 +95,33 @@ int pslam_synchronize(pslam_ctx* c) {
 }
 
 int64_t pslam_launch_count(const pslam_ctx* c) { return c ? c->launches : 0; }
+
+int pslam_profile_enable(pslam_ctx* c, int on) {
+    if (!c) return PSLAM_E_INVALID;
+    for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->prof.clear();
+    c->profile = on != 0;
+    return PSLAM_OK;
+}
+
+int pslam_profile_report(pslam_ctx* c, char* buf, int cap) {
+    if (!c || !buf || cap < 2) return PSLAM_E_INVALID;
+    PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
+    struct Acc { const char* name; int n; double ms; };
+    std::vector<Acc> acc;
+    for (auto& r : c->prof) {
+        float ms = 0.f;
+        PSLAM_CUDA(c, cudaEventElapsedTime(&ms, r.a, r.b));
+        bool found = false;
+        for (auto& a : acc) if (!std::strcmp(a.name, r.name)) { a.n++; a.ms += ms; found = true; break; }
+        if (!found) acc.push_back({r.name, 1, ms});
+    }
+    std::string out;
+    for (auto& a : acc) { char line[160]; std::snprintf(line, sizeof line, "%s %d %.6f\n", a.name, a.n, a.ms); out += line; }
+    if ((int)out.size() + 1 > cap) return set_error(c, PSLAM_E_CAPACITY, "profile report buffer too small");
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return PSLAM_OK;
+}
 
 int pslam_orb_get_scale_tables(const pslam_ctx* c, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int32_t* fpl) {
     if (!c) return PSLAM_E_INVALID;

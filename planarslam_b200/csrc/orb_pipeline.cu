@@ -175,31 +175,27 @@ int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint
         const uint8_t* src = (l == 1) ? d_gray : c->d_pyr + s.pyr_off;
         const size_t sfs = (l == 1) ? frame_px : (size_t)g.pyr_bytes;
         dim3 grid((d.w + 127) / 128, (d.h + 7) / 8, nframes), block(32, 8);
-        k_resize_level<<<grid, block, 0, st>>>(src, sfs, s.pitch, s.w, s.h, c->d_pyr + d.pyr_off, (size_t)g.pyr_bytes, d.pitch, d.w, d.h,
-                                               c->d_xofs + d.tabx_off, c->d_xa + 2 * d.tabx_off, c->d_yofs + d.taby_off,
-                                               c->d_ya + 2 * d.taby_off);
-        ++c->launches;
+        PSLAM_LAUNCH(c, "orb_resize_level", k_resize_level<<<grid, block, 0, st>>>(src, sfs, s.pitch, s.w, s.h, c->d_pyr + d.pyr_off,
+                     (size_t)g.pyr_bytes, d.pitch, d.w, d.h, c->d_xofs + d.tabx_off, c->d_xa + 2 * d.tabx_off, c->d_yofs + d.taby_off,
+                     c->d_ya + 2 * d.taby_off));
     }
     // K2: FAST per cell, all levels and frames in one launch
-    k_fast_cells<<<dim3(g.total_cells, nframes), 128, 0, st>>>(d_gray, c->d_pyr, g, c->d_slots, c->d_cell_cnt, c->d_status);
-    ++c->launches;
+    PSLAM_LAUNCH(c, "orb_fast_cells", k_fast_cells<<<dim3(g.total_cells, nframes), 128, 0, st>>>(d_gray, c->d_pyr, g, c->d_slots, c->d_cell_cnt, c->d_status));
     // K3: quadtree, one warp per (level, frame)
-    k_quadtree<<<dim3(g.nlevels, nframes), 32, 0, st>>>(g, c->d_slots, c->d_cell_cnt, c->d_cand, c->d_cand_cnt, c->d_nodes, c->d_links,
-                                                        c->d_work, c->d_lvl_kp, c->d_lvl_cnt, c->d_status);
-    ++c->launches;
+    PSLAM_LAUNCH(c, "orb_quadtree", k_quadtree<<<dim3(g.nlevels, nframes), 32, 0, st>>>(g, c->d_slots, c->d_cell_cnt, c->d_cand, c->d_cand_cnt,
+                 c->d_nodes, c->d_links, c->d_work, c->d_lvl_kp, c->d_lvl_cnt, c->d_status));
     // K4a: blur every level
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& v = g.lv[l];
         const uint8_t* src = (l == 0) ? d_gray : c->d_pyr + v.pyr_off;
         const size_t sfs = (l == 0) ? frame_px : (size_t)g.pyr_bytes;
         dim3 grid((v.w + 63) / 64, (v.h + 15) / 16, nframes);
-        k_blur_level<<<grid, 256, 0, st>>>(src, sfs, v.pitch, c->d_blur + v.blur_off, (size_t)c->blur_frame_bytes, v.blur_pitch, v.w, v.h);
-        ++c->launches;
+        PSLAM_LAUNCH(c, "orb_blur_level", k_blur_level<<<grid, 256, 0, st>>>(src, sfs, v.pitch, c->d_blur + v.blur_off,
+                     (size_t)c->blur_frame_bytes, v.blur_pitch, v.w, v.h));
     }
     // K4b: orientation + descriptors + output records
-    k_orient_describe<<<dim3((g.total_kp + 7) / 8, nframes), 256, 0, st>>>(g, d_gray, c->d_pyr, c->d_blur, c->blur_frame_bytes, c->d_lvl_kp,
-                                                                          c->d_lvl_cnt, d_kps, d_desc, d_n, cap, c->d_status);
-    ++c->launches;
+    PSLAM_LAUNCH(c, "orb_orient_describe", k_orient_describe<<<dim3((g.total_kp + 7) / 8, nframes), 256, 0, st>>>(g, d_gray, c->d_pyr, c->d_blur,
+                 c->blur_frame_bytes, c->d_lvl_kp, c->d_lvl_cnt, d_kps, d_desc, d_n, cap, c->d_status));
     PSLAM_CUDA(c, cudaGetLastError());
     return PSLAM_OK;
 }

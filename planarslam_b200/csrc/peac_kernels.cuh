@@ -1,0 +1,739 @@
+// PEAC plane extraction kernels for sm_100a (batched over frames).
+//
+// Reference semantics (file:line under /root/reference): PlaneDetection::readDepthImage src/PlaneExtractor.cpp:26-57,
+// ImagePointCloud::get include/PlaneExtractor.h:25-33, ahc::PlaneSeg ctor include/peac/AHCPlaneSeg.hpp:211-285,
+// Stats::compute :125-156, PlaneFitter::initGraph include/peac/AHCPlaneFitter.hpp:786-972, ahCluster :983-1189,
+// mergeNbsFrom AHCPlaneSeg.hpp:379-410, findBlockMembership AHCPlaneFitter.hpp:485-587, floodFill :428-476,
+// refineDetails :299-379, DisjointSet include/peac/DisjointSet.hpp:64-92.
+// Compiled with --fmad=false: every double operation rounds like the unfused CPU oracle.
+//
+// Work decomposition:
+//   k_peac_blocks   one thread per 10x10 block: validity, the nine running sums in row-major order, PCA
+//   k_peac_cluster  one warp per frame: graph edges, agglomerative clustering (serial pops, the neighbours of the
+//                   popped node are evaluated in parallel by the 32 lanes), plane list, eroded block map
+//   k_peac_seed     one CTA per frame: label image / distance map initialisation, region-growing seed queue
+//   k_peac_flood    one warp per frame: the FIFO region growing, 8 queue items x 4 neighbours per step with an
+//                   exact-order fallback whenever two lanes touch the same pixel
+//   k_peac_final    one CTA per frame: last merge over the coarse planes, relabel, per-plane pixel index lists
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+
+#include "pslam_internal.h"
+
+namespace pslam {
+
+#define PEAC_MAX_PLANES 128          // >= H*W / minSupport for 640x480 (102); checked at context creation
+#define PEAC_PL_WORDS (PEAC_MAX_PLANES / 32)
+
+// ---------------------------------------------------------------------------------------------------------
+// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (only + - * / sqrt: bit-identical to oracle/peac.cc)
+__device__ __forceinline__ void eig33sym_jacobi(const double K[3][3], double s[3], double V[3][3]) {
+    double a[3][3], d[3], b[3], z[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { a[i][j] = K[i][j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
+        d[i] = b[i] = a[i][i];
+        z[i] = 0.0;
+    }
+    for (int sweep = 0; sweep < 50; ++sweep) {
+        const double sm = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (sm == 0.0) break;
+        const double tresh = (sweep < 3) ? 0.2 * sm / 9.0 : 0.0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                const double g = 100.0 * fabs(a[p][q]);
+                if (sweep > 3 && fabs(d[p]) + g == fabs(d[p]) && fabs(d[q]) + g == fabs(d[q])) {
+                    a[p][q] = 0.0;
+                } else if (fabs(a[p][q]) > tresh) {
+                    double h = d[q] - d[p], t;
+                    if (fabs(h) + g == fabs(h)) {
+                        t = a[p][q] / h;
+                    } else {
+                        const double theta = 0.5 * h / a[p][q];
+                        t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+                        if (theta < 0.0) t = -t;
+                    }
+                    const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c, tau = sn / (1.0 + c);
+                    h = t * a[p][q];
+                    z[p] -= h; z[q] += h; d[p] -= h; d[q] += h;
+                    a[p][q] = 0.0;
+#define PEAC_ROT(i, j, k, l) { const double gg = a[i][j], hh = a[k][l]; a[i][j] = gg - sn * (hh + gg * tau); a[k][l] = hh + sn * (gg - hh * tau); }
+                    // for a 3x3 the rotation touches exactly one off-diagonal pair besides (p,q)
+                    if (p == 0 && q == 1) { PEAC_ROT(0, 2, 1, 2) }
+                    else if (p == 0 && q == 2) { PEAC_ROT(0, 1, 1, 2) }
+                    else { PEAC_ROT(0, 1, 0, 2) }
+#undef PEAC_ROT
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const double gg = V[j][p], hh = V[j][q];
+                        V[j][p] = gg - sn * (hh + gg * tau);
+                        V[j][q] = hh + sn * (gg - hh * tau);
+                    }
+                }
+            }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { b[i] += z[i]; d[i] = b[i]; z[i] = 0.0; }
+    }
+    int o0 = 0, o1 = 1, o2 = 2;
+    if (d[o1] < d[o0]) { const int t = o0; o0 = o1; o1 = t; }
+    if (d[o2] < d[o0]) { const int t = o0; o0 = o2; o2 = t; }
+    if (d[o2] < d[o1]) { const int t = o1; o1 = o2; o2 = t; }
+    double Vc[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Vc[i][j] = V[i][j];
+    const int ord[3] = {o0, o1, o2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s[k] = d[ord[k]];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) V[i][k] = Vc[i][ord[k]];
+    }
+}
+
+// Stats::compute (AHCPlaneSeg.hpp:125-156): geo = {center[3], normal[3], mse, curvature}
+__device__ __forceinline__ void peac_stats_compute(const double st[9], int N, double geo[8]) {
+    const double sc = 1.0 / N;
+    const double sx = st[0], sy = st[1], sz = st[2];
+    geo[0] = sx * sc; geo[1] = sy * sc; geo[2] = sz * sc;
+    double K[3][3];
+    K[0][0] = st[3] - sx * sx * sc; K[0][1] = st[6] - sx * sy * sc; K[0][2] = st[8] - sx * sz * sc;
+    K[1][1] = st[4] - sy * sy * sc; K[1][2] = st[7] - sy * sz * sc; K[2][2] = st[5] - sz * sz * sc;
+    K[1][0] = K[0][1]; K[2][0] = K[0][2]; K[2][1] = K[1][2];
+    double sv[3], V[3][3];
+    eig33sym_jacobi(K, sv, V);
+    if (V[0][0] * geo[0] + V[1][0] * geo[1] + V[2][0] * geo[2] <= 0) { geo[3] = V[0][0]; geo[4] = V[1][0]; geo[5] = V[2][0]; }
+    else { geo[3] = -V[0][0]; geo[4] = -V[1][0]; geo[5] = -V[2][0]; }
+    geo[6] = sv[0] * sc;
+    geo[7] = sv[0] / (sv[0] + sv[1] + sv[2]);
+}
+
+__device__ __forceinline__ double peac_t_mse(const PeacGeom& g, double tol, double z) { const double v = g.depth_sigma * z * z + tol; return v * v; }
+__device__ __forceinline__ double peac_t_ang_init(const PeacGeom& g, double z) {
+    if (z <= g.z_near) return g.t_ang_init_near;               // the only branch reachable with metre-valued clouds
+    const double cz = fmin(z, g.z_far);
+    const double factor = (g.angle_far - g.angle_near) / (g.z_far - g.z_near);
+    return cos(factor * cz + g.angle_near - factor * g.z_near);
+}
+__device__ __forceinline__ double peac_sim(const double* ga, const double* gb) {
+    return fabs(ga[3] * gb[3] + ga[4] * gb[4] + ga[5] * gb[5]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K-P1: per-block statistics. grid (ceil(nblk/128), frames), block 128.
+__global__ void __launch_bounds__(128) k_peac_blocks(PeacGeom g, const uint16_t* __restrict__ depth, double* __restrict__ blk_st,
+                                                     double* __restrict__ blk_geo, int32_t* __restrict__ blk_n, uint8_t* __restrict__ blk_valid) {
+    const int b = blockIdx.x * 128 + threadIdx.x, frame = blockIdx.y;
+    if (b >= g.nblk) return;
+    const int bi = b / g.nbw, bj = b - bi * g.nbw;
+    const uint16_t* D = depth + (size_t)frame * g.w * g.h;
+    const double scale = (double)g.scale, fx = (double)g.fx, fy = (double)g.fy, cx = (double)g.cx, cy = (double)g.cy;
+    double st[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int n = 0;
+    bool valid = true;
+    for (int i = bi * g.win, ic = 0; ic < g.win && i < g.h && valid; ++i, ++ic)
+        for (int j = bj * g.win, jc = 0; jc < g.win && j < g.w; ++j, ++jc) {
+            const int dv = D[(size_t)i * g.w + j];
+            if (dv == 0) { valid = false; break; }
+            const double z = (double)dv * scale;
+            const double tdz = g.depth_alpha * fabs(z) + g.depth_change_tol;
+            if (j + 1 < g.w) { const int dn = D[(size_t)i * g.w + j + 1]; if (dn != 0 && fabs(z - (double)dn * scale) > tdz) { valid = false; break; } }
+            if (i + 1 < g.h) { const int dn = D[(size_t)(i + 1) * g.w + j]; if (dn != 0 && fabs(z - (double)dn * scale) > tdz) { valid = false; break; } }
+            const double x = ((double)j - cx) * z / fx, y = ((double)i - cy) * z / fy;
+            st[0] += x; st[1] += y; st[2] += z;
+            st[3] += x * x; st[4] += y * y; st[5] += z * z;
+            st[6] += x * y; st[7] += y * z; st[8] += x * z;
+            ++n;
+        }
+    double geo[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool keep = false;
+    if (!valid) { n = 0; for (int k = 0; k < 9; ++k) st[k] = 0; }
+    if (n >= 4) {
+        peac_stats_compute(st, n, geo);
+        keep = valid && geo[6] < peac_t_mse(g, g.std_tol_init, geo[2]);
+    } else {
+        geo[6] = geo[7] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    const size_t o = (size_t)frame * g.nblk + b;
+    for (int k = 0; k < 9; ++k) blk_st[o * 9 + k] = st[k];
+    for (int k = 0; k < 8; ++k) blk_geo[o * 8 + k] = geo[k];
+    blk_n[o] = n;
+    blk_valid[o] = keep ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Agglomerative clustering shared by the coarse pass (nodes = blocks) and the last merge (nodes = coarse planes).
+struct AhcState {
+    int nslots;              // node slots (a merged node reuses the slot of the popped parent)
+    int words;               // adjacency bitset words per row
+    double* st;              // [nslots][9]
+    double* geo;             // [nslots][8]
+    int32_t* N;              // [nslots]
+    int32_t* rid;            // [nslots]
+    int32_t* cid;            // [nslots] creation order (canonical neighbour order)
+    uint8_t* alive;          // [nslots] still in the graph
+    uint32_t* adj;           // [nslots][words]
+    int32_t* heap;           // [nslots]
+    int32_t* nb_list;        // [nslots] scratch
+    int32_t* ds_parent;      // disjoint set over initial blocks
+    int32_t* ds_size;
+};
+
+__device__ __forceinline__ int ds_find(int32_t* parent, int x) {
+    int r = x;
+    while (parent[r] != r) r = parent[r];
+    while (parent[x] != r) { const int nx = parent[x]; parent[x] = r; x = nx; }
+    return r;
+}
+__device__ __forceinline__ void ds_union(int32_t* parent, int32_t* size, int x, int y) {
+    const int xr = ds_find(parent, x), yr = ds_find(parent, y);
+    if (xr == yr) return;
+    if (size[xr] < size[yr]) { parent[xr] = yr; size[yr] += size[xr]; }
+    else { parent[yr] = xr; size[xr] += size[yr]; }
+}
+
+// libstdc++ binary-heap algorithms (std::priority_queue<.., PlaneSegMinMSECmp>): comp(a,b) = mse[b] < mse[a]
+__device__ __forceinline__ bool heap_comp(const double* geo, int a, int b) { return geo[b * 8 + 6] < geo[a * 8 + 6]; }
+__device__ __forceinline__ void heap_sift_up(int32_t* h, const double* geo, int hole, int top, int value) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && heap_comp(geo, h[parent], value)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
+    h[hole] = value;
+}
+__device__ __forceinline__ void heap_push(int32_t* h, int& len, const double* geo, int id) { h[len] = id; ++len; heap_sift_up(h, geo, len - 1, 0, id); }
+__device__ __forceinline__ int heap_pop(int32_t* h, int& len, const double* geo) {
+    const int top = h[0], value = h[len - 1];
+    --len;
+    if (len > 0) {
+        int hole = 0, child = 0;
+        while (child < (len - 1) / 2) {
+            child = 2 * (child + 1);
+            if (heap_comp(geo, h[child], h[child - 1])) --child;
+            h[hole] = h[child]; hole = child;
+        }
+        if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); h[hole] = h[child - 1]; hole = child - 1; }
+        heap_sift_up(h, geo, hole, 0, value);
+    }
+    return top;
+}
+
+// One warp. heap_len: current heap size (entries already pushed in the reference's order). next_cid: next creation id.
+// Extracted slots are appended to ex[] (at most PEAC_MAX_PLANES) and finally stable-sorted by N descending.
+__device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_cid, int32_t* ex, int& n_ex, bool& overflow) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t full = 0xffffffffu;
+    int step = 0;
+    while (heap_len > 0 && step <= g.max_step) {
+        int p = 0;
+        if (lane == 0) p = heap_pop(S.heap, heap_len, S.geo);
+        p = __shfl_sync(full, p, 0);
+        heap_len = __shfl_sync(full, heap_len, 0);
+        if (!S.alive[p]) continue;
+        // ---- neighbours of p (set bits of its adjacency row), compacted in slot order ----
+        int cnt = 0;
+        for (int w0 = 0; w0 < S.words; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t bits = (w < S.words) ? S.adj[(size_t)p * S.words + w] : 0u;
+            const int c = __popc(bits);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, inc, o); if (lane >= o) inc += t; }
+            int pos = cnt + inc - c;
+            while (bits) { const int bpos = __ffs(bits) - 1; bits &= bits - 1; S.nb_list[pos++] = w * 32 + bpos; }
+            cnt += __shfl_sync(full, inc, 31);
+        }
+        __syncwarp();
+        // ---- every lane tries the merges lane, lane+32, ... and keeps its best (mse, then creation id) ----
+        const double* gp = S.geo + (size_t)p * 8;
+        const double* sp = S.st + (size_t)p * 9;
+        const int Np = S.N[p];
+        double best_mse = 0.0;
+        int best_nb = -1, best_cid = 0x7fffffff;
+        for (int i = lane; i < cnt; i += 32) {
+            const int q = S.nb_list[i];
+            const double* gq = S.geo + (size_t)q * 8;
+            if (peac_sim(gp, gq) < g.sim_merge) continue;
+            double st[9], geo[8];
+            const double* sq = S.st + (size_t)q * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st[k] = sp[k] + sq[k];
+            peac_stats_compute(st, Np + S.N[q], geo);
+            const int cq = S.cid[q];
+            if (best_nb < 0 || geo[6] < best_mse || (geo[6] == best_mse && cq < best_cid)) { best_mse = geo[6]; best_nb = q; best_cid = cq; }
+        }
+        // warp argmin over (mse, cid); lanes without a candidate carry best_nb = -1
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double om = __shfl_xor_sync(full, best_mse, o);
+            const int onb = __shfl_xor_sync(full, best_nb, o), oc = __shfl_xor_sync(full, best_cid, o);
+            if (onb >= 0 && (best_nb < 0 || om < best_mse || (om == best_mse && oc < best_cid))) { best_mse = om; best_nb = onb; best_cid = oc; }
+        }
+        // (The reference's tie rule `cand.N < merge.mse` (AHCPlaneFitter.hpp:1045) can only fire when two merges have
+        //  bit-identical mse AND mse exceeds the point count; with metre-valued clouds mse << 1, so the first
+        //  candidate in canonical order wins a tie, which is what the (mse, cid) order above implements.)
+        bool merged = false;
+        if (best_nb >= 0) {
+            const int nb = best_nb;
+            double st[9], geo[8];
+            const double* sq = S.st + (size_t)nb * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) st[k] = sp[k] + sq[k];
+            const int Nc = Np + S.N[nb];
+            peac_stats_compute(st, Nc, geo);
+            if (geo[6] < peac_t_mse(g, g.std_tol_merge, geo[2])) {
+                merged = true;
+                // mergeNbsFrom: union in the disjoint set, new neighbour set = nbs(p) | nbs(nb) - {p, nb}
+                const int rid_c = Np >= S.N[nb] ? S.rid[p] : S.rid[nb];
+                if (lane == 0) ds_union(S.ds_parent, S.ds_size, S.rid[p], S.rid[nb]);
+                // every neighbour q of nb: forget nb, learn p (the merged node lives in p's slot)
+                for (int w = lane; w < S.words; w += 32) {
+                    uint32_t bits = S.adj[(size_t)nb * S.words + w];
+                    while (bits) {
+                        const int q = w * 32 + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if (q == p) continue;
+                        atomicAnd(&S.adj[(size_t)q * S.words + (nb >> 5)], ~(1u << (nb & 31)));
+                        atomicOr(&S.adj[(size_t)q * S.words + (p >> 5)], 1u << (p & 31));
+                    }
+                }
+                __syncwarp();
+                for (int w = lane; w < S.words; w += 32) {
+                    uint32_t u = S.adj[(size_t)p * S.words + w] | S.adj[(size_t)nb * S.words + w];
+                    if (w == (p >> 5)) u &= ~(1u << (p & 31));
+                    if (w == (nb >> 5)) u &= ~(1u << (nb & 31));
+                    S.adj[(size_t)p * S.words + w] = u;
+                    S.adj[(size_t)nb * S.words + w] = 0u;
+                }
+                if (lane < 9) S.st[(size_t)p * 9 + lane] = st[lane];
+                if (lane < 8) S.geo[(size_t)p * 8 + lane] = geo[lane];
+                if (lane == 0) { S.N[p] = Nc; S.rid[p] = rid_c; S.cid[p] = next_cid; S.alive[nb] = 0; }
+                ++next_cid;
+                __syncwarp();
+                if (lane == 0) heap_push(S.heap, heap_len, S.geo, p);
+                heap_len = __shfl_sync(full, heap_len, 0);
+            }
+        }
+        if (!merged) {
+            if (Np >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex] = p; ++n_ex; } else overflow = true; }
+            // disconnectAllNbs(p)
+            for (int w = lane; w < S.words; w += 32) {
+                uint32_t bits = S.adj[(size_t)p * S.words + w];
+                while (bits) { const int q = w * 32 + __ffs(bits) - 1; bits &= bits - 1; atomicAnd(&S.adj[(size_t)q * S.words + (p >> 5)], ~(1u << (p & 31))); }
+                S.adj[(size_t)p * S.words + w] = 0u;
+            }
+            if (lane == 0) S.alive[p] = 0;
+        }
+        __syncwarp();
+        ++step;
+    }
+    // (maxStep is never reached in practice; the reference then just drains the queue, :1168-1175)
+    while (heap_len > 0) {
+        int p = 0;
+        if (lane == 0) p = heap_pop(S.heap, heap_len, S.geo);
+        p = __shfl_sync(full, p, 0);
+        heap_len = __shfl_sync(full, heap_len, 0);
+        if (S.alive[p] && S.N[p] >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex] = p; ++n_ex; } else overflow = true; }
+    }
+    __syncwarp();
+    if (lane == 0)      // stable insertion sort by N descending (std::sort on <= 16 elements is exactly this)
+        for (int i = 1; i < n_ex; ++i) {
+            const int v = ex[i];
+            int j = i - 1;
+            while (j >= 0 && S.N[ex[j]] < S.N[v]) { ex[j + 1] = ex[j]; --j; }
+            ex[j + 1] = v;
+        }
+    __syncwarp();
+}
+
+// Per-frame plane record written by the cluster / final kernels (also what the ABI returns)
+struct PeacPlaneRec {
+    double normal[3], center[3], mse, curvature;
+    double st[9];
+    int32_t N, rid, cid, valid;
+};
+
+// K-P2: graph edges + coarse clustering + eroded block map. grid (frames), block 32.
+__global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* __restrict__ blk_st, const double* __restrict__ blk_geo,
+                                                     const int32_t* __restrict__ blk_n, const uint8_t* __restrict__ blk_valid,
+                                                     double* node_st, double* node_geo, int32_t* node_n, int32_t* node_rid, int32_t* node_cid,
+                                                     uint8_t* node_alive, uint32_t* adj, int32_t* heap, int32_t* nb_list, int32_t* ds_parent,
+                                                     int32_t* ds_size, PeacPlaneRec* planes, int32_t* n_planes, int32_t* blk_map,
+                                                     int32_t* next_cid_out, int32_t* status) {
+    const int frame = blockIdx.x, lane = threadIdx.x;
+    const size_t fo = (size_t)frame * g.nblk;
+    AhcState S;
+    S.nslots = g.nblk; S.words = g.adj_words;
+    S.st = node_st + fo * 9; S.geo = node_geo + fo * 8; S.N = node_n + fo; S.rid = node_rid + fo; S.cid = node_cid + fo;
+    S.alive = node_alive + fo; S.adj = adj + fo * g.adj_words; S.heap = heap + fo; S.nb_list = nb_list + fo;
+    S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
+    const uint8_t* valid = blk_valid + fo;
+    // node slots = blocks
+    for (int b = lane; b < g.nblk; b += 32) {
+        for (int k = 0; k < 9; ++k) S.st[(size_t)b * 9 + k] = blk_st[(fo + b) * 9 + k];
+        for (int k = 0; k < 8; ++k) S.geo[(size_t)b * 8 + k] = blk_geo[(fo + b) * 8 + k];
+        S.N[b] = blk_n[fo + b]; S.rid[b] = b; S.cid[b] = b; S.alive[b] = valid[b];
+        S.ds_parent[b] = b; S.ds_size[b] = 1;
+    }
+    __syncwarp();
+    auto connect = [&](int a, int b) {
+        atomicOr(&S.adj[(size_t)a * S.words + (b >> 5)], 1u << (b & 31));
+        atomicOr(&S.adj[(size_t)b * S.words + (a >> 5)], 1u << (a & 31));
+    };
+    const int Nh = g.nbh, Nw = g.nbw;
+    // row pass (AHCPlaneFitter.hpp:896-924): rows are independent, the walk along a row is sequential
+    for (int i = lane; i < Nh; i += 32)
+        for (int j = 1; j < Nw; j += 2) {
+            const int c = i * Nw + j;
+            if (!valid[c - 1]) { --j; continue; }
+            if (!valid[c]) continue;
+            if (j < Nw - 1 && !valid[c + 1]) { ++j; continue; }
+            const double th = peac_t_ang_init(g, S.geo[(size_t)c * 8 + 2]);
+            if ((j < Nw - 1 && peac_sim(S.geo + (size_t)(c - 1) * 8, S.geo + (size_t)(c + 1) * 8) >= th) ||
+                (j == Nw - 1 && peac_sim(S.geo + (size_t)c * 8, S.geo + (size_t)(c - 1) * 8) >= th)) {
+                connect(c, c - 1);
+                if (j < Nw - 1) connect(c, c + 1);
+            } else {
+                --j;
+            }
+        }
+    // column pass (:926-954)
+    for (int j = lane; j < Nw; j += 32)
+        for (int i = 1; i < Nh; i += 2) {
+            const int c = i * Nw + j;
+            if (!valid[c - Nw]) { --i; continue; }
+            if (!valid[c]) continue;
+            if (i < Nh - 1 && !valid[c + Nw]) { ++i; continue; }
+            const double th = peac_t_ang_init(g, S.geo[(size_t)c * 8 + 2]);
+            if ((i < Nh - 1 && peac_sim(S.geo + (size_t)(c - Nw) * 8, S.geo + (size_t)(c + Nw) * 8) >= th) ||
+                (i == Nh - 1 && peac_sim(S.geo + (size_t)c * 8, S.geo + (size_t)(c - Nw) * 8) >= th)) {
+                connect(c, c - Nw);
+                if (i < Nh - 1) connect(c, c + Nw);
+            } else {
+                --i;
+            }
+        }
+    __syncwarp();
+    // initial heap: valid blocks pushed in block order (:810-811)
+    int heap_len = 0;
+    if (lane == 0)
+        for (int b = 0; b < g.nblk; ++b) if (valid[b]) heap_push(S.heap, heap_len, S.geo, b);
+    heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
+    __syncwarp();
+
+    __shared__ int32_t ex[PEAC_MAX_PLANES];
+    int n_ex = 0, next_cid = g.nblk;
+    bool overflow = false;
+    ahc_run(g, S, heap_len, next_cid, ex, n_ex, overflow);
+    if (overflow && lane == 0) atomicOr(status + frame, 16);
+
+    PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
+    for (int i = lane; i < n_ex; i += 32) {
+        const int s = ex[i];
+        PeacPlaneRec r;
+        for (int k = 0; k < 3; ++k) { r.center[k] = S.geo[(size_t)s * 8 + k]; r.normal[k] = S.geo[(size_t)s * 8 + 3 + k]; }
+        r.mse = S.geo[(size_t)s * 8 + 6]; r.curvature = S.geo[(size_t)s * 8 + 7];
+        for (int k = 0; k < 9; ++k) r.st[k] = S.st[(size_t)s * 9 + k];
+        r.N = S.N[s]; r.rid = S.rid[s]; r.cid = S.cid[s]; r.valid = 0;
+        P[i] = r;
+    }
+    __syncwarp();
+    // findBlockMembership (:485-531): a block keeps its plane only if all its 4-neighbours are in the same set
+    int32_t* bm = blk_map + fo;
+    const int PP = g.win * g.win;
+    for (int b = lane; b < g.nblk; b += 32) {
+        const int i = b / Nw, j = b - i * Nw;
+        const int setid = ds_find(S.ds_parent, b);      // lanes touch disjoint chains only through benign idempotent compression
+        int plid = -1;
+        if (S.ds_size[setid] * PP >= g.min_support) {
+            bool same = true;
+            if (j > 0 && ds_find(S.ds_parent, b - 1) != setid) same = false;
+            if (same && j < Nw - 1 && ds_find(S.ds_parent, b + 1) != setid) same = false;
+            if (same && i > 0 && ds_find(S.ds_parent, b - Nw) != setid) same = false;
+            if (same && i < Nh - 1 && ds_find(S.ds_parent, b + Nw) != setid) same = false;
+            if (same) {
+                plid = 0;                                   // std::map::operator[] default when the root is unknown
+                for (int k = 0; k < n_ex; ++k) if (P[k].rid == setid) { plid = k; break; }
+                P[plid].valid = 1;
+            }
+        }
+        bm[b] = plid;
+    }
+    if (lane == 0) { n_planes[frame] = n_ex; next_cid_out[frame] = next_cid; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K-P3: labels = -1 / plane id of kept blocks, distance map = FLT_MAX, seed queue in block-scan order (:532-575).
+// queue entry: pixel index | plane id << 24.  grid (frames), block 256.
+__device__ __forceinline__ int peac_seed_count(const PeacGeom& g, const int32_t* bm, int b) {
+    const int i = b / g.nbw, j = b - i * g.nbw, W = g.win;
+    int n = 0;
+    if (bm[b] < 0) {
+        if (i > 0 && bm[b - g.nbw] >= 0) n += W - 1;
+        if (j > 0 && bm[b - 1] >= 0) n += W - 1;
+    } else {
+        if (i > 0 && bm[b - g.nbw] != bm[b]) n += W - 1;
+        if (j > 0 && bm[b - 1] != bm[b]) n += W - 1;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(256) k_peac_seed(PeacGeom g, const int32_t* __restrict__ blk_map, int32_t* __restrict__ labels,
+                                                   float* __restrict__ dist, uint32_t* __restrict__ queue, int32_t* __restrict__ q_len) {
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    const int32_t* bm = blk_map + (size_t)frame * g.nblk;
+    int32_t* lab = labels + (size_t)frame * g.w * g.h;
+    float* dm = dist + (size_t)frame * g.w * g.h;
+    uint32_t* q = queue + (size_t)frame * g.queue_cap;
+    const int npx = g.w * g.h;
+    for (int p = tid; p < npx; p += 256) {
+        const int y = p / g.w, x = p - y * g.w;
+        const int by = y / g.win, bx = x / g.win;
+        lab[p] = (by < g.nbh && bx < g.nbw) ? (bm[by * g.nbw + bx] >= 0 ? bm[by * g.nbw + bx] : -1) : -1;
+        dm[p] = FLT_MAX;
+    }
+    // exclusive scan of per-block seed counts: each thread owns a contiguous run of blocks
+    __shared__ int s_part[256];
+    const int per = (g.nblk + 255) / 256;
+    const int b0 = tid * per, b1 = min(g.nblk, b0 + per);
+    int mine = 0;
+    for (int b = b0; b < b1; ++b) mine += peac_seed_count(g, bm, b);
+    s_part[tid] = mine;
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int t = 0; t < 256; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; } q_len[frame] = run; }
+    __syncthreads();
+    int pos = s_part[tid];
+    const int W = g.win, iw = g.w;
+    for (int b = b0; b < b1; ++b) {
+        const int i = b / g.nbw, j = b - i * g.nbw;
+        if (bm[b] < 0) {
+            if (i > 0 && bm[b - g.nbw] >= 0) { const int s0 = (i * W - 1) * iw + j * W; const uint32_t pl = (uint32_t)bm[b - g.nbw] << 24; for (int k = 1; k < W; ++k) q[pos++] = (uint32_t)(s0 + k) | pl; }
+            if (j > 0 && bm[b - 1] >= 0) { const int s0 = (i * W) * iw + j * W - 1; const uint32_t pl = (uint32_t)bm[b - 1] << 24; for (int k = 0; k < W - 1; ++k) q[pos++] = (uint32_t)(s0 + k * iw) | pl; }
+        } else {
+            const uint32_t pl = (uint32_t)bm[b] << 24;
+            if (i > 0 && bm[b - g.nbw] != bm[b]) { const int s0 = (i * W) * iw + j * W; for (int k = 0; k < W - 1; ++k) q[pos++] = (uint32_t)(s0 + k) | pl; }
+            if (j > 0 && bm[b - 1] != bm[b]) { const int s0 = (i * W) * iw + j * W; for (int k = 1; k < W; ++k) q[pos++] = (uint32_t)(s0 + k * iw) | pl; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K-P4: region growing (floodFill :428-476). One warp per frame; lane = (queue item % 8) * 4 + neighbour.
+// All 32 (item, neighbour) touches of a group run in parallel unless two lanes address the same pixel and at
+// least one of them would change it; such a group is replayed lane by lane in queue order (exact FIFO semantics).
+__global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* __restrict__ depth, const int32_t* __restrict__ blk_map,
+                                                   const PeacPlaneRec* __restrict__ planes, int32_t* __restrict__ labels, float* __restrict__ dist,
+                                                   uint32_t* __restrict__ queue, int32_t* __restrict__ q_len, uint32_t* __restrict__ pl_adj,
+                                                   int32_t* __restrict__ status) {
+    const int frame = blockIdx.x, lane = threadIdx.x;
+    const uint32_t full = 0xffffffffu;
+    const uint16_t* D = depth + (size_t)frame * g.w * g.h;
+    const int32_t* bm = blk_map + (size_t)frame * g.nblk;
+    const PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
+    int32_t* lab = labels + (size_t)frame * g.w * g.h;
+    float* dm = dist + (size_t)frame * g.w * g.h;
+    uint32_t* q = queue + (size_t)frame * g.queue_cap;
+    uint32_t* padj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
+    int tail = q_len[frame];
+    const double scale = (double)g.scale, fx = (double)g.fx, fy = (double)g.fy, cx = (double)g.cx, cy = (double)g.cy;
+    const int item_in_group = lane >> 2, nbr = lane & 3;
+    bool overflow = false;
+
+    for (int head = 0; head < tail; head += 8) {
+        const int k = head + item_in_group;
+        bool have = k < tail;
+        int c = -1, plid = 0;
+        if (have) {
+            const uint32_t e = q[k];
+            const int s = e & 0xffffff;
+            plid = e >> 24;
+            const int sy = s / g.w, sx = s - sy * g.w;
+            // neighbour order of getValid4Neighbor (:393-405): left, right, up, down, skipping the ones outside
+            int cand[4], nn = 0;
+            if (sx > 0) cand[nn++] = s - 1;
+            if (sx < g.w - 1) cand[nn++] = s + 1;
+            if (sy > 0) cand[nn++] = s - g.w;
+            if (sy < g.h - 1) cand[nn++] = s + g.w;
+            if (nbr < nn) c = cand[nbr]; else have = false;
+        }
+        // a touch is "inert" when the reference skips it before reading the point (:445-450 for the state seen now)
+        auto inert_now = [&](int cc, int pl) -> bool {
+            const int tr = lab[cc];
+            if (tr <= -6) return true;
+            if (tr >= 0 && tr == pl) return true;
+            const int cy_ = cc / g.w, cx_ = cc - cy_ * g.w;
+            const int by = cy_ / g.win, bx = cx_ / g.win;
+            return by < g.nbh && bx < g.nbw && bm[by * g.nbw + bx] >= 0;
+        };
+        // full reference semantics for one touch; returns true when the pixel is pushed
+        auto touch = [&](int cc, int pl) -> bool {
+            int tr = lab[cc];
+            if (tr <= -6) return false;
+            if (tr >= 0 && tr == pl) return false;
+            const int cy_ = cc / g.w, cx_ = cc - cy_ * g.w;
+            const int by = cy_ / g.win, bx = cx_ / g.win;
+            if (by < g.nbh && bx < g.nbw && bm[by * g.nbw + bx] >= 0) return false;
+            const PeacPlaneRec& pr = P[pl];
+            const int dv = D[cc];
+            bool ok = false;
+            float cdist = -1.f;
+            if (dv != 0) {
+                const double z = (double)dv * scale;
+                const double x = ((double)cx_ - cx) * z / fx, y = ((double)cy_ - cy) * z / fy;
+                const double sd = pr.normal[0] * (x - pr.center[0]) + pr.normal[1] * (y - pr.center[1]) + pr.normal[2] * (z - pr.center[2]);
+                cdist = (float)fabs(sd);
+                ok = (double)cdist * (double)cdist < 9 * pr.mse + 1e-5;
+            }
+            bool pushed = false;
+            if (ok) {
+                if (tr >= 0) {
+                    const PeacPlaneRec& other = P[tr];
+                    const double sim = fabs(pr.normal[0] * other.normal[0] + pr.normal[1] * other.normal[1] + pr.normal[2] * other.normal[2]);
+                    if (sim >= g.sim_refine) {
+                        atomicOr(&padj[tr * PEAC_PL_WORDS + (pl >> 5)], 1u << (pl & 31));
+                        atomicOr(&padj[pl * PEAC_PL_WORDS + (tr >> 5)], 1u << (tr & 31));
+                    }
+                }
+                if (cdist < dm[cc]) { lab[cc] = pl; dm[cc] = cdist; pushed = true; }
+                else if (tr < 0) lab[cc] = tr - 1;
+            } else if (tr < 0) lab[cc] = tr - 1;
+            return pushed;
+        };
+
+        const bool active = have && !inert_now(c, plid);
+        // conflict: two lanes of the group address the same pixel and at least one of them is active
+        const uint32_t peers = __match_any_sync(full, have ? c : -1 - lane);
+        const uint32_t act_mask = __ballot_sync(full, active);
+        const bool conflict = have && (__popc(peers) > 1) && (peers & act_mask);
+        bool pushed = false;
+        if (!__any_sync(full, conflict)) {
+            if (active) pushed = touch(c, plid);
+            __syncwarp();
+        } else {
+            for (int l = 0; l < 32; ++l) {
+                if (lane == l && have) pushed = touch(c, plid);
+                __syncwarp();
+            }
+        }
+        const uint32_t pm = __ballot_sync(full, pushed);
+        if (pushed) {
+            const int pos = tail + __popc(pm & ((1u << lane) - 1));
+            if (pos < g.queue_cap) q[pos] = (uint32_t)c | ((uint32_t)plid << 24); else overflow = true;
+        }
+        tail = min(tail + __popc(pm), g.queue_cap);
+        __syncwarp();
+    }
+    if (__any_sync(full, overflow) && lane == 0) atomicOr(status + frame, 32);
+    if (lane == 0) q_len[frame] = tail;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K-P5: last merge over the coarse planes (warp 0), then relabel and build the per-plane pixel lists.
+// grid (frames), block 256.
+__global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __restrict__ planes, const int32_t* __restrict__ n_planes,
+                                                    const int32_t* __restrict__ next_cid_in, uint32_t* __restrict__ pl_adj,
+                                                    int32_t* ds_parent, int32_t* ds_size, int32_t* __restrict__ labels,
+                                                    PeacPlaneRec* __restrict__ out_planes, pslam_plane* __restrict__ abi_planes, int32_t* __restrict__ out_n, int32_t* __restrict__ member_idx,
+                                                    int32_t* __restrict__ member_off, int32_t* __restrict__ scratch, int32_t* __restrict__ status) {
+    const int frame = blockIdx.x, tid = threadIdx.x;
+    __shared__ double s_st[PEAC_MAX_PLANES * 9];
+    __shared__ double s_geo[PEAC_MAX_PLANES * 8];
+    __shared__ int32_t s_n[PEAC_MAX_PLANES], s_rid[PEAC_MAX_PLANES], s_cid[PEAC_MAX_PLANES], s_heap[PEAC_MAX_PLANES], s_nb[PEAC_MAX_PLANES];
+    __shared__ uint8_t s_alive[PEAC_MAX_PLANES];
+    __shared__ int32_t s_ex[PEAC_MAX_PLANES], s_map[PEAC_MAX_PLANES];
+    __shared__ int s_nfinal;
+    PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
+    PeacPlaneRec* O = out_planes + (size_t)frame * PEAC_MAX_PLANES;
+    const int np = n_planes[frame];
+    const size_t fo = (size_t)frame * g.nblk;
+    for (int i = tid; i < np; i += 256) {
+        for (int k = 0; k < 9; ++k) s_st[i * 9 + k] = P[i].st[k];
+        for (int k = 0; k < 3; ++k) { s_geo[i * 8 + k] = P[i].center[k]; s_geo[i * 8 + 3 + k] = P[i].normal[k]; }
+        s_geo[i * 8 + 6] = P[i].mse; s_geo[i * 8 + 7] = P[i].curvature;
+        s_n[i] = P[i].N; s_rid[i] = P[i].rid; s_cid[i] = P[i].cid; s_alive[i] = (uint8_t)P[i].valid;
+        s_map[i] = -1;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        AhcState S;
+        S.nslots = np; S.words = PEAC_PL_WORDS;
+        S.st = s_st; S.geo = s_geo; S.N = s_n; S.rid = s_rid; S.cid = s_cid; S.alive = s_alive;
+        S.adj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
+        S.heap = s_heap; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
+        // planes that were eroded completely take no part: drop their adjacency (they never got any) and skip the push
+        int heap_len = 0;
+        if (tid == 0) for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, S.geo, i);
+        heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
+        __syncwarp();
+        int n_ex = 0, next_cid = next_cid_in[frame];
+        bool overflow = false;
+        ahc_run(g, S, heap_len, next_cid, s_ex, n_ex, overflow);
+        if (overflow && tid == 0) atomicOr(status + frame, 16);
+        // final plane records, and old plane -> final plane map through the disjoint set (:329-344)
+        for (int j = tid; j < n_ex; j += 32) {
+            const int s = s_ex[j];
+            PeacPlaneRec r;
+            for (int k = 0; k < 3; ++k) { r.center[k] = s_geo[s * 8 + k]; r.normal[k] = s_geo[s * 8 + 3 + k]; }
+            r.mse = s_geo[s * 8 + 6]; r.curvature = s_geo[s * 8 + 7];
+            for (int k = 0; k < 9; ++k) r.st[k] = s_st[s * 9 + k];
+            r.N = s_n[s]; r.rid = s_rid[s]; r.cid = s_cid[s]; r.valid = 1;
+            O[j] = r;
+            pslam_plane a;
+            for (int k = 0; k < 3; ++k) { a.normal[k] = r.normal[k]; a.center[k] = r.center[k]; }
+            a.mse = r.mse; a.curvature = r.curvature; a.N = r.N; a.rid = r.rid;
+            abi_planes[(size_t)frame * PEAC_MAX_PLANES + j] = a;
+        }
+        __syncwarp();
+        if (tid == 0) {
+            for (int i = 0; i < np; ++i) {
+                if (!P[i].valid) continue;
+                const int root = ds_find(S.ds_parent, P[i].rid);
+                for (int j = 0; j < n_ex; ++j) if (O[j].rid == root) { s_map[i] = j; break; }
+            }
+            s_nfinal = n_ex;
+            out_n[frame] = n_ex;
+        }
+    }
+    __syncthreads();
+    // ---- relabel (:362-372) + ordered per-plane pixel lists: contiguous pixel chunk per thread, two passes ----
+    const int nf = s_nfinal;
+    int32_t* lab = labels + (size_t)frame * g.w * g.h;
+    const int npx = g.w * g.h;
+    const int per = (npx + 255) / 256;
+    const int p0 = tid * per, p1 = min(npx, p0 + per);
+    int32_t* cnt = scratch + ((size_t)frame * 256 + tid) * PEAC_MAX_PLANES;     // this thread's per-plane counts
+    for (int k = 0; k < nf; ++k) cnt[k] = 0;
+    for (int p = p0; p < p1; ++p) {
+        const int v = lab[p];
+        if (v >= 0 && s_map[v] >= 0) ++cnt[s_map[v]];
+    }
+    __syncthreads();
+    // exclusive scan over threads for each plane, and plane offsets
+    int32_t* allcnt = scratch + (size_t)frame * 256 * PEAC_MAX_PLANES;
+    int32_t* moff = member_off + (size_t)frame * (PEAC_MAX_PLANES + 1);
+    if (tid < nf) {
+        int run = 0;
+        for (int t = 0; t < 256; ++t) { const int v = allcnt[t * PEAC_MAX_PLANES + tid]; allcnt[t * PEAC_MAX_PLANES + tid] = run; run += v; }
+        s_heap[tid] = run;                  // total pixels of plane tid
+    }
+    __syncthreads();
+    if (tid == 0) { int run = 0; for (int k = 0; k < nf; ++k) { moff[k] = run; run += s_heap[k]; } moff[nf] = run; }
+    __syncthreads();
+    int32_t* midx = member_idx + (size_t)frame * npx;
+    for (int p = p0; p < p1; ++p) {
+        const int v = lab[p];
+        if (v >= 0 && s_map[v] >= 0) {                // pixels of other values keep their raw trail counter (:369-371)
+            const int nv = s_map[v];
+            lab[p] = nv;
+            midx[moff[nv] + cnt[nv]] = p;
+            ++cnt[nv];
+        }
+    }
+}
+
+}  // namespace pslam

@@ -1,0 +1,156 @@
+// Host side of the PEAC plane extractor: parameters (compiled-in defaults of the reference), buffers, launch sequence.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "peac_kernels.cuh"
+
+namespace pslam {
+
+int peac_build_geometry(pslam_ctx* c) {
+    const pslam_config& cf = c->cfg;
+    PeacGeom& g = c->pgeom;
+    std::memset(&g, 0, sizeof(g));
+    g.w = cf.width; g.h = cf.height; g.win = 10;                       // windowWidth/Height, AHCPlaneFitter.hpp:156
+    g.nbw = g.w / g.win; g.nbh = g.h / g.win; g.nblk = g.nbw * g.nbh;
+    g.min_support = 3000; g.max_step = 100000;                         // :155
+    g.adj_words = (g.nblk + 31) / 32;
+    g.queue_cap = 2 * g.w * g.h;
+    g.scale = cf.depth_scale; g.fx = cf.fx; g.fy = cf.fy; g.cx = cf.cx; g.cy = cf.cy;
+    g.depth_sigma = 1.6e-6; g.std_tol_init = 5; g.std_tol_merge = 8;   // AHCParamSet.hpp:68-76
+    g.z_near = 500; g.z_far = 4000;
+    g.angle_near = 15.0 * M_PI / 180.0; g.angle_far = 90.0 * M_PI / 180.0;
+    {   // T_ang(P_INIT, z <= z_near), AHCParamSet.hpp:120-127, evaluated with the host libm like the CPU path does
+        const double factor = (g.angle_far - g.angle_near) / (g.z_far - g.z_near);
+        g.t_ang_init_near = std::cos(factor * g.z_near + g.angle_near - factor * g.z_near);
+    }
+    g.sim_merge = std::cos(60.0 * M_PI / 180.0);
+    g.sim_refine = std::cos(30.0 * M_PI / 180.0);
+    g.depth_alpha = 0.04; g.depth_change_tol = 0.02;
+    if ((long long)g.w * g.h / g.min_support + 1 > PEAC_MAX_PLANES) return set_error(c, PSLAM_E_INVALID, "frame too large for PEAC_MAX_PLANES");
+    if ((long long)g.w * g.h >= (1 << 24)) return set_error(c, PSLAM_E_INVALID, "frame too large for the 24-bit pixel index");
+    if (g.nblk < 1) return set_error(c, PSLAM_E_INVALID, "frame smaller than one PEAC block");
+    if (!(cf.fx != 0.f) || !(cf.fy != 0.f) || !(cf.depth_scale > 0.f)) return set_error(c, PSLAM_E_INVALID, "fx, fy must be non-zero and depth_scale > 0");
+    return PSLAM_OK;
+}
+
+template <typename T>
+static int dmalloc(pslam_ctx* c, T** p, size_t n) { return check_cuda(c, cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)), "cudaMalloc"); }
+
+int peac_alloc(pslam_ctx* c) {
+    const PeacGeom& g = c->pgeom;
+    const size_t B = c->cfg.max_batch, nb = g.nblk, px = (size_t)g.w * g.h;
+    int rc;
+#define A(call) if ((rc = (call)) != PSLAM_OK) return rc
+    A(dmalloc(c, &c->d_depth, B * px));
+    A(dmalloc(c, &c->d_blk_st, B * nb * 9)); A(dmalloc(c, &c->d_blk_geo, B * nb * 8)); A(dmalloc(c, &c->d_blk_n, B * nb)); A(dmalloc(c, &c->d_blk_valid, B * nb));
+    A(dmalloc(c, &c->d_node_st, B * nb * 9)); A(dmalloc(c, &c->d_node_geo, B * nb * 8)); A(dmalloc(c, &c->d_node_n, B * nb));
+    A(dmalloc(c, &c->d_node_rid, B * nb)); A(dmalloc(c, &c->d_node_cid, B * nb)); A(dmalloc(c, &c->d_node_alive, B * nb));
+    A(dmalloc(c, &c->d_adj, B * nb * g.adj_words)); A(dmalloc(c, &c->d_heap, B * nb)); A(dmalloc(c, &c->d_nb_list, B * nb));
+    A(dmalloc(c, &c->d_ds_parent, B * nb)); A(dmalloc(c, &c->d_ds_size, B * nb));
+    A(dmalloc(c, &c->d_coarse, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_ncoarse, B)); A(dmalloc(c, &c->d_next_cid, B)); A(dmalloc(c, &c->d_blk_map, B * nb));
+    A(dmalloc(c, &c->d_dist, B * px)); A(dmalloc(c, &c->d_queue, B * g.queue_cap)); A(dmalloc(c, &c->d_qlen, B));
+    A(dmalloc(c, &c->d_pl_adj, B * PEAC_MAX_PLANES * PEAC_PL_WORDS));
+    A(dmalloc(c, &c->d_final, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_scratch, B * 256 * PEAC_MAX_PLANES));
+    A(dmalloc(c, &c->d_labels, B * px)); A(dmalloc(c, &c->d_planes, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_nplanes, B));
+    A(dmalloc(c, &c->d_midx, B * px)); A(dmalloc(c, &c->d_moff, B * (PEAC_MAX_PLANES + 1)));
+    A(check_cuda(c, cudaMallocHost((void**)&c->h_depth, B * px * sizeof(uint16_t)), "cudaMallocHost"));
+#undef A
+    return PSLAM_OK;
+}
+
+void peac_free(pslam_ctx* c) {
+    cudaFree(c->d_depth); cudaFree(c->d_blk_st); cudaFree(c->d_blk_geo); cudaFree(c->d_blk_n); cudaFree(c->d_blk_valid);
+    cudaFree(c->d_node_st); cudaFree(c->d_node_geo); cudaFree(c->d_node_n); cudaFree(c->d_node_rid); cudaFree(c->d_node_cid);
+    cudaFree(c->d_node_alive); cudaFree(c->d_adj); cudaFree(c->d_heap); cudaFree(c->d_nb_list); cudaFree(c->d_ds_parent); cudaFree(c->d_ds_size);
+    cudaFree(c->d_coarse); cudaFree(c->d_ncoarse); cudaFree(c->d_next_cid); cudaFree(c->d_blk_map); cudaFree(c->d_dist); cudaFree(c->d_queue);
+    cudaFree(c->d_qlen); cudaFree(c->d_pl_adj); cudaFree(c->d_final); cudaFree(c->d_scratch); cudaFree(c->d_labels); cudaFree(c->d_planes);
+    cudaFree(c->d_nplanes); cudaFree(c->d_midx); cudaFree(c->d_moff); cudaFreeHost(c->h_depth);
+}
+
+int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes, int32_t* d_nplanes,
+                 int32_t* d_member_idx, int32_t* d_member_off) {
+    const PeacGeom& g = c->pgeom;
+    if (nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "nframes outside [1, max_batch]");
+    if (!d_depth || !d_labels || !d_planes || !d_nplanes || !d_member_idx || !d_member_off) return set_error(c, PSLAM_E_INVALID, "null device pointer");
+    cudaStream_t st = c->stream;
+    c->last_nframes = nframes;
+    PSLAM_CUDA(c, cudaMemsetAsync(c->d_status, 0, nframes * sizeof(int32_t), st));
+    PSLAM_CUDA(c, cudaMemsetAsync(c->d_adj, 0, (size_t)nframes * g.nblk * g.adj_words * sizeof(uint32_t), st));
+    PSLAM_CUDA(c, cudaMemsetAsync(c->d_pl_adj, 0, (size_t)nframes * PEAC_MAX_PLANES * PEAC_PL_WORDS * sizeof(uint32_t), st));
+    PSLAM_LAUNCH(c, "peac_blocks", k_peac_blocks<<<dim3((g.nblk + 127) / 128, nframes), 128, 0, st>>>(g, d_depth, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid));
+    PSLAM_LAUNCH(c, "peac_cluster", k_peac_cluster<<<nframes, 32, 0, st>>>(g, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid, c->d_node_st, c->d_node_geo,
+                 c->d_node_n, c->d_node_rid, c->d_node_cid, c->d_node_alive, c->d_adj, c->d_heap, c->d_nb_list, c->d_ds_parent, c->d_ds_size, c->d_coarse,
+                 c->d_ncoarse, c->d_blk_map, c->d_next_cid, c->d_status));
+    PSLAM_LAUNCH(c, "peac_seed", k_peac_seed<<<nframes, 256, 0, st>>>(g, c->d_blk_map, d_labels, c->d_dist, c->d_queue, c->d_qlen));
+    PSLAM_LAUNCH(c, "peac_flood", k_peac_flood<<<nframes, 32, 0, st>>>(g, d_depth, c->d_blk_map, c->d_coarse, d_labels, c->d_dist, c->d_queue, c->d_qlen, c->d_pl_adj,
+                 c->d_status));
+    PSLAM_LAUNCH(c, "peac_final", k_peac_final<<<nframes, 256, 0, st>>>(g, c->d_coarse, c->d_ncoarse, c->d_next_cid, c->d_pl_adj, c->d_ds_parent, c->d_ds_size, d_labels,
+                 c->d_final, d_planes, d_nplanes, d_member_idx, d_member_off, c->d_scratch, c->d_status));
+    PSLAM_CUDA(c, cudaGetLastError());
+    return PSLAM_OK;
+}
+
+}  // namespace pslam
+
+using namespace pslam;
+
+extern "C" {
+
+int pslam_peac_max_planes(const pslam_ctx*) { return PEAC_MAX_PLANES; }
+int pslam_peac_num_blocks(const pslam_ctx* c) { return c ? c->pgeom.nblk : 0; }
+
+int pslam_peac_run_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes, int32_t* d_nplanes,
+                             int32_t* d_member_idx, int32_t* d_member_off) {
+    if (!c) return PSLAM_E_INVALID;
+    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    return peac_run_dev(c, d_depth, nframes, d_labels, d_planes, d_nplanes, d_member_idx, d_member_off);
+}
+
+int pslam_peac_run_batch(pslam_ctx* c, const uint16_t* depth, int nframes, int32_t* labels, pslam_plane* planes, int32_t* nplanes,
+                         int32_t* member_idx, int32_t* member_off) {
+    if (!c) return PSLAM_E_INVALID;
+    if (!depth || !labels || !planes || !nplanes) return set_error(c, PSLAM_E_INVALID, "null pointer");
+    if (nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "nframes outside [1, max_batch]");
+    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    const PeacGeom& g = c->pgeom;
+    const size_t px = (size_t)g.w * g.h;
+    cudaStream_t st = c->stream;
+    std::memcpy(c->h_depth, depth, px * nframes * sizeof(uint16_t));
+    PSLAM_CUDA(c, cudaMemcpyAsync(c->d_depth, c->h_depth, px * nframes * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    int rc = peac_run_dev(c, c->d_depth, nframes, c->d_labels, c->d_planes, c->d_nplanes, c->d_midx, c->d_moff);
+    if (rc != PSLAM_OK) return rc;
+    PSLAM_CUDA(c, cudaMemcpyAsync(labels, c->d_labels, px * nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(planes, c->d_planes, (size_t)nframes * PEAC_MAX_PLANES * sizeof(pslam_plane), cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(nplanes, c->d_nplanes, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (member_idx) PSLAM_CUDA(c, cudaMemcpyAsync(member_idx, c->d_midx, px * nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (member_off) PSLAM_CUDA(c, cudaMemcpyAsync(member_off, c->d_moff, (size_t)nframes * (PEAC_MAX_PLANES + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaStreamSynchronize(st));
+    int bits = 0;
+    for (int i = 0; i < nframes; ++i) bits |= c->h_status[i];
+    if (bits) return set_error(c, PSLAM_E_CAPACITY, "PEAC capacity exceeded (16: more than PEAC_MAX_PLANES planes, 32: region-growing queue)");
+    return PSLAM_OK;
+}
+
+int pslam_peac_debug_blocks(pslam_ctx* c, int frame, double* st9, double* geo8, int32_t* n, uint8_t* valid) {
+    if (!c || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t nb = c->pgeom.nblk, o = (size_t)frame * nb;
+    if (st9) PSLAM_CUDA(c, cudaMemcpy(st9, c->d_blk_st + o * 9, nb * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (geo8) PSLAM_CUDA(c, cudaMemcpy(geo8, c->d_blk_geo + o * 8, nb * 8 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (n) PSLAM_CUDA(c, cudaMemcpy(n, c->d_blk_n + o, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (valid) PSLAM_CUDA(c, cudaMemcpy(valid, c->d_blk_valid + o, nb, cudaMemcpyDeviceToHost));
+    return PSLAM_OK;
+}
+
+int pslam_peac_debug_coarse(pslam_ctx* c, int frame, int32_t* blk_map, int32_t* n_coarse) {
+    if (!c || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t nb = c->pgeom.nblk;
+    if (blk_map) PSLAM_CUDA(c, cudaMemcpy(blk_map, c->d_blk_map + (size_t)frame * nb, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (n_coarse) PSLAM_CUDA(c, cudaMemcpy(n_coarse, c->d_ncoarse + frame, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return PSLAM_OK;
+}
+
+}  // extern "C"

@@ -46,6 +46,20 @@ struct OrbGeom {
     int umax[16];
 };
 
+// PEAC parameters and sizes (compiled-in defaults of the reference: AHCPlaneFitter.hpp:154-158, AHCParamSet.hpp:68-76)
+struct PeacGeom {
+    int w, h, nbw, nbh, nblk, win;
+    int min_support, max_step;
+    int adj_words, queue_cap;
+    float scale, fx, fy, cx, cy;
+    double depth_sigma, std_tol_init, std_tol_merge;
+    double z_near, z_far, angle_near, angle_far, t_ang_init_near;
+    double sim_merge, sim_refine;
+    double depth_alpha, depth_change_tol;
+};
+
+struct PeacPlaneRec;
+
 }  // namespace pslam
 
 struct pslam_ctx {
@@ -55,6 +69,10 @@ struct pslam_ctx {
     std::vector<int> quota;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int64_t launches = 0;
+    // optional per-kernel timing (pslam_profile_enable): one CUDA event pair per launch on the launching stream
+    bool profile = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
     std::string err;
     int last_nframes = 0;
 
@@ -79,6 +97,18 @@ struct pslam_ctx {
     pslam_keypoint* d_kps = nullptr;  // outputs for host-pointer entry points
     uint8_t* d_desc = nullptr;
     int32_t* d_n = nullptr;
+    // ---- PEAC ----
+    pslam::PeacGeom pgeom;
+    uint16_t* d_depth = nullptr;                 // staging copy of host depth
+    double* d_blk_st = nullptr; double* d_blk_geo = nullptr; int32_t* d_blk_n = nullptr; uint8_t* d_blk_valid = nullptr;
+    double* d_node_st = nullptr; double* d_node_geo = nullptr; int32_t* d_node_n = nullptr; int32_t* d_node_rid = nullptr;
+    int32_t* d_node_cid = nullptr; uint8_t* d_node_alive = nullptr; uint32_t* d_adj = nullptr; int32_t* d_heap = nullptr;
+    int32_t* d_nb_list = nullptr; int32_t* d_ds_parent = nullptr; int32_t* d_ds_size = nullptr;
+    pslam::PeacPlaneRec* d_coarse = nullptr; int32_t* d_ncoarse = nullptr; int32_t* d_next_cid = nullptr; int32_t* d_blk_map = nullptr;
+    float* d_dist = nullptr; uint32_t* d_queue = nullptr; int32_t* d_qlen = nullptr; uint32_t* d_pl_adj = nullptr;
+    pslam::PeacPlaneRec* d_final = nullptr; int32_t* d_scratch = nullptr;
+    int32_t* d_labels = nullptr; pslam_plane* d_planes = nullptr; int32_t* d_nplanes = nullptr; int32_t* d_midx = nullptr; int32_t* d_moff = nullptr;
+    uint16_t* h_depth = nullptr;                 // pinned
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
     int32_t* h_status = nullptr;
@@ -93,7 +123,23 @@ int orb_alloc(pslam_ctx* c);
 void orb_free(pslam_ctx* c);
 int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint* d_kps, uint8_t* d_desc, int cap,
                 int32_t* d_n);
+// PEAC pipeline (peac_pipeline.cu)
+int peac_build_geometry(pslam_ctx* c);
+int peac_alloc(pslam_ctx* c);
+void peac_free(pslam_ctx* c);
+int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes, int32_t* d_nplanes,
+                 int32_t* d_member_idx, int32_t* d_member_off);
 }  // namespace pslam
+
+// Launch wrapper: counts the launch and, when profiling is on, brackets it with events on the same stream.
+#define PSLAM_LAUNCH(c, name, ...)                                            \
+    do {                                                                      \
+        pslam_ctx::ProfRec _r{name, nullptr, nullptr};                        \
+        if ((c)->profile) { cudaEventCreate(&_r.a); cudaEventCreate(&_r.b); cudaEventRecord(_r.a, (c)->stream); } \
+        __VA_ARGS__;                                                          \
+        if ((c)->profile) { cudaEventRecord(_r.b, (c)->stream); (c)->prof.push_back(_r); } \
+        ++(c)->launches;                                                      \
+    } while (0)
 
 #define PSLAM_CUDA(c, call)                                                   \
     do {                                                                      \

@@ -40,6 +40,18 @@ def lib():
         L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
         L.orc_fast_atan2.restype = C.c_float
         L.orc_cv_round.argtypes = [C.c_double]
+        L.orc_peac_run.restype = vp
+        L.orc_peac_run.argtypes = [vp, i, i] + [C.c_float] * 5
+        L.orc_peac_free.argtypes = [vp]
+        L.orc_peac_num_planes.argtypes = [vp]
+        L.orc_peac_num_coarse.argtypes = [vp]
+        L.orc_peac_labels.argtypes = [vp, vp]
+        L.orc_peac_plane.argtypes = [vp, i, vp, vp]
+        L.orc_peac_membership.argtypes = [vp, i, vp, i]
+        L.orc_peac_blocks.argtypes = [vp, vp, vp]
+        L.orc_peac_coarse_blocks.argtypes = [vp, vp]
+        L.orc_eig33.argtypes = [vp, vp, vp]
+        L.orc_heap_selftest.argtypes = [vp, i, vp, i]
         _lib = L
     return _lib
 
@@ -99,3 +111,34 @@ def blur(gray: np.ndarray) -> np.ndarray:
     out = np.empty_like(gray)
     lib().orc_gaussian_blur_7x7_s2(gray.ctypes.data, gray.shape[1], gray.shape[0], gray.shape[1], out.ctypes.data)
     return out
+
+
+class PeacOracle:
+    """Result of the oracle PEAC on one depth image."""
+
+    def __init__(self, depth: np.ndarray, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 / 5000.0)):
+        L = lib()
+        depth = np.ascontiguousarray(depth)
+        h, w = depth.shape
+        r = C.c_void_p(L.orc_peac_run(depth.ctypes.data, w, h, K[0], K[1], K[2], K[3], float(np.float32(scale))))
+        n = L.orc_peac_num_planes(r)
+        self.n_coarse = L.orc_peac_num_coarse(r)
+        self.labels = np.zeros((h, w), np.int32)
+        L.orc_peac_labels(r, self.labels.ctypes.data)
+        self.planes = []
+        self.membership = []
+        for i in range(n):
+            d8 = np.zeros(8)
+            i2 = np.zeros(2, np.int32)
+            L.orc_peac_plane(r, i, d8.ctypes.data, i2.ctypes.data)
+            self.planes.append((d8, i2))
+            buf = np.zeros(h * w, np.int32)
+            m = L.orc_peac_membership(r, i, buf.ctypes.data, h * w)
+            self.membership.append(buf[:m].copy())
+        nb = (h // 10) * (w // 10)
+        self.blk_d = np.zeros((nb, 17))
+        self.blk_i = np.zeros((nb, 2), np.int32)
+        L.orc_peac_blocks(r, self.blk_d.ctypes.data, self.blk_i.ctypes.data)
+        self.coarse_blocks = np.zeros(nb, np.int32)
+        L.orc_peac_coarse_blocks(r, self.coarse_blocks.ctypes.data)
+        L.orc_peac_free(r)
