@@ -144,6 +144,42 @@ int pslam_peac_debug_blocks(pslam_ctx* ctx, int frame, double* st9, double* geo8
 int pslam_peac_debug_coarse(pslam_ctx* ctx, int frame, int32_t* blk_map, int32_t* n_coarse);
 int pslam_peac_num_blocks(const pslam_ctx* ctx);
 
+/* ---- Pose optimisation ---------------------------------------------------------------------------
+ * Replaces  static int Optimizer::PoseOptimization(Frame* pFrame)     include/Optimizer.h:38, src/Optimizer.cc:550-1275.
+ * A pslam_pose_problem carries exactly what that function reads from the Frame and the matched map objects:
+ *   points   mvpMapPoints[i]->GetWorldPos() (float), mvKeysUn[i].pt + mvuRight[i] (uR < 0 => monocular edge),
+ *            mvInvLevelSigma2[octave]                                                   (:593-669)
+ *   lines    mvpMapLines[i]->mWorldPos (two endpoints, double), mvKeyLineFunctions[i]   (:693-745)
+ *   planes   mvPlaneCoefficients[i] (float 4) with the matched / parallel / vertical map plane's GetWorldPos()  (:789-981)
+ *   settings Plane.AngleInfo, DistanceInfo, ParallelInfo, VerticalInfo, Chi, VPChi (Config::Get, :771-783); fx, fy, cx, cy, mbf
+ * Tcw_io is Frame::mTcw (float 4x4, row-major) in and out; the outlier arrays are mvbOutlier, mvbLineOutlier,
+ * mvbPlaneOutlier, mvbParPlaneOutlier, mvbVerPlaneOutlier.  The single-problem call returns the reference's return value
+ * (nInitialCorrespondences - nBad, 0 when there are fewer than 3 correspondences) or a negative pslam_status. */
+typedef struct pslam_pose_problem {
+    float fx, fy, cx, cy, bf;
+    int32_t n_points; const float* Xw /* [n][3] */; const float* obs /* [n][3] = u, v, uR */; const float* inv_sigma2 /* [n] */;
+    int32_t n_lines; const double* line_Xw /* [n][6] */; const double* line_obs /* [n][3] */;
+    int32_t n_planes, n_par, n_ver;
+    const float *plane_meas, *plane_map, *par_meas, *par_map, *ver_meas, *ver_map;   /* [n][4] each */
+    double angle_info, dist_info, par_info, ver_info, plane_chi, vp_chi;
+} pslam_pose_problem;
+
+int pslam_pose_optimization(pslam_ctx* ctx, const pslam_pose_problem* prob, float* Tcw_io /* [16] */, uint8_t* outlier_pt,
+                            uint8_t* outlier_line, uint8_t* outlier_plane, uint8_t* outlier_par, uint8_t* outlier_ver);
+/* n independent problems (replayed frames).  Tcw_io is [n][16]; each outlier array is the concatenation over the problems
+ * in order; n_inliers is [n]. */
+int pslam_pose_optimization_batch(pslam_ctx* ctx, const pslam_pose_problem* probs, int n, float* Tcw_io, uint8_t* outlier_pt,
+                                  uint8_t* outlier_line, uint8_t* outlier_plane, uint8_t* outlier_par, uint8_t* outlier_ver,
+                                  int32_t* n_inliers);
+/* Split form for callers that keep the packed problems resident in HBM (bench.py's device-resident number):
+ * pack + upload once, run (asynchronous on the context's stream) any number of times, fetch results.
+ * Tcw_d: [n][16] double pose before the float cast; trace_i: [n][4][3] = LM iterations, trials, nBad per round (-1: round not
+ * run); trace_d: [n][4][2] = final robust chi2 and lambda per round.  Any output pointer may be NULL. */
+int pslam_pose_pack(pslam_ctx* ctx, const pslam_pose_problem* probs, int n, const float* Tcw0 /* [n][16] */);
+int pslam_pose_run_packed(pslam_ctx* ctx);
+int pslam_pose_fetch(pslam_ctx* ctx, float* Tcw, double* Tcw_d, uint8_t* outlier_pt, uint8_t* outlier_line, uint8_t* outlier_plane,
+                     uint8_t* outlier_par, uint8_t* outlier_ver, int32_t* n_inliers, int32_t* trace_i, double* trace_d);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ void* orc_peac_run(const uint16_t* depth, int w, int h, float fx, float fy, floa
 void orc_peac_free(void* p) { delete (PeacResult*)p; }
 int orc_peac_num_planes(void* p) { return (int)((PeacResult*)p)->planes.size(); }
 int orc_peac_num_coarse(void* p) { return ((PeacResult*)p)->n_coarse_planes; }
+int orc_peac_queue_len(void* p, int which) { return which ? ((PeacResult*)p)->n_queue : ((PeacResult*)p)->n_seeds; }
 void orc_peac_labels(void* p, int32_t* out) { auto* r = (PeacResult*)p; std::memcpy(out, r->labels.data(), r->labels.size() * 4); }
 // per plane: normal[3], center[3], mse, curvature (8 doubles); N, rid (2 ints)
 void orc_peac_plane(void* p, int i, double* d8, int* i2) {

@@ -376,6 +376,7 @@ void peac_run(const uint16_t* depth, int w, int h, float fx, float fy, float cx,
     out.coarse_block_plane.assign(blk.begin(), blk.end());
 
     // ---- floodFill (:428-476) ----
+    out.n_seeds = (int)rfq.size();
     {
         std::vector<float> dist((size_t)w * h, std::numeric_limits<float>::max());
         for (size_t k = 0; k < rfq.size(); ++k) {
@@ -417,6 +418,7 @@ void peac_run(const uint16_t* depth, int w, int h, float fx, float fy, float cx,
         }
     }
 
+    out.n_queue = (int)rfq.size();
     // ---- last merge (:318-345) and relabel (:352-372) ----
     std::vector<int> final_planes;
     {

@@ -51,6 +51,7 @@ struct PeacResult {
     std::vector<PeacBlock> blocks;               // per 10x10 block
     std::vector<int32_t> coarse_block_plane;     // blkMap after erosion (plane index before the final merge, or -1)
     int n_coarse_planes = 0;
+    int n_queue = 0, n_seeds = 0;               // region-growing queue length (final / initial)
 };
 
 void eig33sym_jacobi(const double K[3][3], double s[3], double V[3][3]);

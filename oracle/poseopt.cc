@@ -1,0 +1,474 @@
+// TEST INFRASTRUCTURE ONLY — CPU oracle restating Optimizer::PoseOptimization and the g2o pieces it uses
+// (see poseopt.h for the file:line map).
+#include "poseopt.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace oracle {
+namespace {
+
+struct V3 { double x, y, z; };
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double norm(V3 a) { return std::sqrt(dot(a, a)); }
+
+struct M3 { double m[3][3]; };
+inline V3 mul(const M3& A, V3 v) {
+    return {A.m[0][0] * v.x + A.m[0][1] * v.y + A.m[0][2] * v.z, A.m[1][0] * v.x + A.m[1][1] * v.y + A.m[1][2] * v.z,
+            A.m[2][0] * v.x + A.m[2][1] * v.y + A.m[2][2] * v.z};
+}
+inline M3 mul(const M3& A, const M3& B) {
+    M3 C;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
+    return C;
+}
+inline M3 transpose(const M3& A) { M3 T; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T.m[i][j] = A.m[j][i]; return T; }
+
+struct Quat { double x, y, z, w; };
+inline Quat qmul(Quat a, Quat b) {
+    return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+            a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+inline Quat qnormalized_pos(Quat q) {   // SE3Quat::normalizeRotation
+    if (q.w < 0) { q.x = -q.x; q.y = -q.y; q.z = -q.z; q.w = -q.w; }
+    const double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+    return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+inline V3 qrot(Quat q, V3 v) {          // Eigen QuaternionBase::_transformVector
+    const V3 u{q.x, q.y, q.z};
+    V3 uv = cross(u, v);
+    uv = uv + uv;
+    return v + q.w * uv + cross(u, uv);
+}
+Quat quat_from_matrix(const M3& R) {    // Eigen quaternionbase_assign_impl<.., 3, 3>
+    Quat q;
+    double t = R.m[0][0] + R.m[1][1] + R.m[2][2];
+    if (t > 0) {
+        t = std::sqrt(t + 1.0);
+        q.w = 0.5 * t;
+        t = 0.5 / t;
+        q.x = (R.m[2][1] - R.m[1][2]) * t; q.y = (R.m[0][2] - R.m[2][0]) * t; q.z = (R.m[1][0] - R.m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (R.m[1][1] > R.m[0][0]) i = 1;
+        if (R.m[2][2] > R.m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(R.m[i][i] - R.m[j][j] - R.m[k][k] + 1.0);
+        double c[3];
+        c[i] = 0.5 * t;
+        t = 0.5 / t;
+        q.w = (R.m[k][j] - R.m[j][k]) * t;
+        c[j] = (R.m[j][i] + R.m[i][j]) * t;
+        c[k] = (R.m[k][i] + R.m[i][k]) * t;
+        q.x = c[0]; q.y = c[1]; q.z = c[2];
+    }
+    return q;
+}
+M3 quat_to_matrix(Quat q) {             // Eigen QuaternionBase::toRotationMatrix
+    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    M3 R;
+    R.m[0][0] = 1 - (tyy + tzz); R.m[0][1] = txy - twz; R.m[0][2] = txz + twy;
+    R.m[1][0] = txy + twz; R.m[1][1] = 1 - (txx + tzz); R.m[1][2] = tyz - twx;
+    R.m[2][0] = txz - twy; R.m[2][1] = tyz + twx; R.m[2][2] = 1 - (txx + tyy);
+    return R;
+}
+
+struct SE3 { Quat q; V3 t; };
+inline V3 se3_map(const SE3& T, V3 p) { return qrot(T.q, p) + T.t; }
+SE3 se3_from_Rt(const M3& R, V3 t) { return {qnormalized_pos(quat_from_matrix(R)), t}; }
+SE3 se3_mul(const SE3& a, const SE3& b) {   // SE3Quat::operator*
+    SE3 r;
+    r.t = a.t + qrot(a.q, b.t);
+    r.q = qnormalized_pos(qmul(a.q, b.q));
+    return r;
+}
+SE3 se3_exp(const double u[6]) {            // SE3Quat::exp, update = [omega, upsilon]
+    const V3 om{u[0], u[1], u[2]}, up{u[3], u[4], u[5]};
+    const double theta = norm(om);
+    M3 O = {{{0, -om.z, om.y}, {om.z, 0, -om.x}, {-om.y, om.x, 0}}};
+    M3 O2 = mul(O, O), R, V;
+    if (theta < 0.00001) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R.m[i][j] = (i == j ? 1.0 : 0.0) + O.m[i][j] + O2.m[i][j];
+        V = R;
+    } else {
+        const double a = std::sin(theta) / theta, b = (1 - std::cos(theta)) / (theta * theta), c = (theta - std::sin(theta)) / std::pow(theta, 3);
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            R.m[i][j] = (i == j ? 1.0 : 0.0) + a * O.m[i][j] + b * O2.m[i][j];
+            V.m[i][j] = (i == j ? 1.0 : 0.0) + b * O.m[i][j] + c * O2.m[i][j];
+        }
+    }
+    return se3_from_Rt(R, mul(V, up));
+}
+
+// ---- Plane3D ----
+struct Plane { double c[4]; };
+inline void plane_normalize(Plane& p) {
+    const double n = std::sqrt(p.c[0] * p.c[0] + p.c[1] * p.c[1] + p.c[2] * p.c[2]);
+    const double s = 1. / n;
+    for (int i = 0; i < 4; ++i) p.c[i] = p.c[i] * s;
+    if (p.c[3] < 0.0) for (int i = 0; i < 4; ++i) p.c[i] = -p.c[i];
+}
+Plane plane_from_float4(const float* v) {   // Converter::toPlane3D
+    Plane p{{v[0], v[1], v[2], v[3]}};
+    if (v[3] < 0.0f) for (int i = 0; i < 4; ++i) p.c[i] = -p.c[i];
+    plane_normalize(p);
+    return p;
+}
+inline V3 pn(const Plane& p) { return {p.c[0], p.c[1], p.c[2]}; }
+inline double azimuth(V3 v) { return std::atan2(v.y, v.x); }
+inline double elevation(V3 v) { return std::atan2(v.z, std::sqrt(v.x * v.x + v.y * v.y)); }
+M3 plane_rotation(V3 v) {                    // Rz(azimuth) * Ry(-elevation)
+    const double a = azimuth(v), e = -elevation(v);
+    const double ca = std::cos(a), sa = std::sin(a), ce = std::cos(e), se = std::sin(e);
+    M3 Rz = {{{ca, -sa, 0}, {sa, ca, 0}, {0, 0, 1}}}, Ry = {{{ce, 0, se}, {0, 1, 0}, {-se, 0, ce}}};
+    return mul(Rz, Ry);
+}
+Plane plane_transform(const SE3& T, const Plane& p) {   // operator*(Isometry3D, Plane3D)
+    const M3 R = quat_to_matrix(T.q);
+    const V3 n = mul(R, pn(p));
+    Plane r{{n.x, n.y, n.z, p.c[3] - dot(T.t, n)}};
+    if (r.c[3] < 0.0) for (int i = 0; i < 4; ++i) r.c[i] = -r.c[i];
+    plane_normalize(r);
+    return r;
+}
+void plane_ominus(const Plane& self, const Plane& meas, double e[3]) {
+    const M3 R = transpose(plane_rotation(pn(self)));
+    const V3 n = mul(R, pn(meas));
+    e[0] = azimuth(n); e[1] = elevation(n); e[2] = (-self.c[3]) - (-meas.c[3]);
+}
+void plane_ominus_par(const Plane& self, const Plane& meas, double e[2]) {
+    V3 nor = pn(self);
+    if (dot(pn(meas), nor) < 0) nor = -1.0 * nor;
+    const M3 R = transpose(plane_rotation(nor));
+    const V3 n = mul(R, pn(meas));
+    e[0] = azimuth(n); e[1] = elevation(n);
+}
+void plane_ominus_ver(const Plane& self, const Plane& meas, double e[2]) {
+    const V3 v = cross(pn(self), pn(meas));
+    const V3 ax = (1.0 / norm(v)) * v;
+    // AngleAxis(pi/2, ax) * normal  (Rodrigues)
+    const double ang = M_PI / 2, c = std::cos(ang), s = std::sin(ang);
+    const V3 nrm = pn(self);
+    const V3 b = c * nrm + s * cross(ax, nrm) + ((1 - c) * dot(ax, nrm)) * ax;
+    const M3 R = transpose(plane_rotation(b));
+    const V3 n = mul(R, pn(meas));
+    e[0] = azimuth(n); e[1] = elevation(n);
+}
+
+// ---- edges ----
+enum Kind { MONO, STEREO, LINE, PLANE, PAR, VER };
+struct Edge {
+    Kind kind;
+    int dim;                 // residual dimension
+    int idx;                 // index in its family (point i, line i, plane i)
+    V3 Xw;                   // point edges
+    double obs[3];
+    double info[3];          // diagonal information
+    double delta;            // Huber delta (float-rounded like the reference's const float)
+    Plane pw, pm;            // plane edges: world plane, measurement
+    bool robust = true;
+    int level = 0;
+    double err[3] = {0, 0, 0};
+};
+
+struct Cam { double fx, fy, cx, cy, bf; };
+
+void compute_error(Edge& e, const SE3& T, const Cam& K) {
+    switch (e.kind) {
+        case MONO: {
+            const V3 p = se3_map(T, e.Xw);
+            e.err[0] = e.obs[0] - (p.x / p.z * K.fx + K.cx);
+            e.err[1] = e.obs[1] - (p.y / p.z * K.fy + K.cy);
+            break;
+        }
+        case STEREO: {
+            const V3 p = se3_map(T, e.Xw);
+            const float invz = 1.0f / (float)p.z;                                 // sic: float reciprocal, .cpp:300
+            const double r0 = p.x * invz * K.fx + K.cx, r1 = p.y * invz * K.fy + K.cy, r2 = r0 - K.bf * invz;
+            e.err[0] = e.obs[0] - r0; e.err[1] = e.obs[1] - r1; e.err[2] = e.obs[2] - r2;
+            break;
+        }
+        case LINE: {
+            const V3 p = se3_map(T, e.Xw);
+            const double u = p.x / p.z * K.fx + K.cx, v = p.y / p.z * K.fy + K.cy;
+            e.err[0] = e.obs[0] * u + e.obs[1] * v + e.obs[2]; e.err[1] = 0; e.err[2] = 0;
+            break;
+        }
+        case PLANE: plane_ominus(plane_transform(T, e.pw), e.pm, e.err); break;
+        case PAR: plane_ominus_par(plane_transform(T, e.pw), e.pm, e.err); break;
+        case VER: plane_ominus_ver(plane_transform(T, e.pw), e.pm, e.err); break;
+    }
+}
+inline double chi2(const Edge& e) { double s = 0; for (int i = 0; i < e.dim; ++i) s += e.err[i] * e.info[i] * e.err[i]; return s; }
+
+void jacobian(Edge& e, const SE3& T, const Cam& K, double J[3][6]) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 6; ++j) J[i][j] = 0;
+    if (e.kind == MONO || e.kind == STEREO || e.kind == LINE) {
+        const V3 p = se3_map(T, e.Xw);
+        const double x = p.x, y = p.y, invz = 1.0 / p.z, invz_2 = invz * invz;
+        if (e.kind == LINE) {
+            const double lx = e.obs[0], ly = e.obs[1], fx = K.fx, fy = K.fy;
+            J[0][0] = -fy * ly - fx * lx * x * y * invz_2 - fy * ly * y * y * invz_2;
+            J[0][1] = fx * lx + fx * lx * x * x * invz_2 + fy * ly * x * y * invz_2;
+            J[0][2] = -fx * lx * y * invz + fy * ly * x * invz;
+            J[0][3] = fx * lx * invz;
+            J[0][4] = fy * ly * invz;
+            J[0][5] = -(fx * lx * x + fy * ly * y) * invz_2;
+            return;
+        }
+        J[0][0] = x * y * invz_2 * K.fx; J[0][1] = -(1 + (x * x * invz_2)) * K.fx; J[0][2] = y * invz * K.fx;
+        J[0][3] = -invz * K.fx; J[0][4] = 0; J[0][5] = x * invz_2 * K.fx;
+        J[1][0] = (1 + y * y * invz_2) * K.fy; J[1][1] = -x * y * invz_2 * K.fy; J[1][2] = -x * invz * K.fy;
+        J[1][3] = 0; J[1][4] = -invz * K.fy; J[1][5] = y * invz_2 * K.fy;
+        if (e.kind == STEREO) {
+            J[2][0] = J[0][0] - K.bf * y * invz_2; J[2][1] = J[0][1] + K.bf * x * invz_2; J[2][2] = J[0][2];
+            J[2][3] = J[0][3]; J[2][4] = 0; J[2][5] = J[0][5] - K.bf * invz_2;
+        }
+        return;
+    }
+    // numeric central differences, delta = 1e-9 (base_unary_edge.hpp:94-116); _error is restored afterwards
+    const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+    double keep[3] = {e.err[0], e.err[1], e.err[2]};
+    for (int d = 0; d < 6; ++d) {
+        double add[6] = {0, 0, 0, 0, 0, 0};
+        add[d] = delta;
+        compute_error(e, se3_mul(se3_exp(add), T), K);
+        const double e1[3] = {e.err[0], e.err[1], e.err[2]};
+        add[d] = -delta;
+        compute_error(e, se3_mul(se3_exp(add), T), K);
+        for (int i = 0; i < e.dim; ++i) J[i][d] = scalar * (e1[i] - e.err[i]);
+    }
+    for (int i = 0; i < 3; ++i) e.err[i] = keep[i];
+}
+
+inline void huber(double e2, double delta, double rho[3]) {
+    const double dsqr = delta * delta;
+    if (e2 <= dsqr) { rho[0] = e2; rho[1] = 1.; rho[2] = 0.; }
+    else { const double s = std::sqrt(e2); rho[0] = 2 * s * delta - dsqr; rho[1] = delta / s; rho[2] = -0.5 * rho[1] / e2; }
+}
+
+// unpivoted LDL^T of a symmetric 6x6; false when a pivot is not positive (LDLT::isPositive)
+bool solve6(const double H[6][6], const double b[6], double x[6]) {
+    double L[6][6] = {{0}}, D[6];
+    for (int j = 0; j < 6; ++j) {
+        double d = H[j][j];
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k] * D[k];
+        if (!(d > 0)) return false;
+        D[j] = d;
+        L[j][j] = 1;
+        for (int i = j + 1; i < 6; ++i) {
+            double v = H[i][j];
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = v / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i][k] * y[k]; y[i] = v; }
+    for (int i = 0; i < 6; ++i) y[i] /= D[i];
+    for (int i = 5; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k]; x[i] = v; }
+    return true;
+}
+
+struct Lm {
+    std::vector<Edge>& E;
+    const Cam& K;
+    SE3 T;
+    double lambda = 0, ni = 2;
+    int nBad = 0;
+    double H[6][6], b[6], x[6] = {0, 0, 0, 0, 0, 0};
+    int last_trials = 0;
+    double last_chi = 0;
+
+    void active_errors() { for (Edge& e : E) if (e.level == 0) compute_error(e, T, K); }
+    double robust_chi2() const {
+        double chi = 0;
+        for (const Edge& e : E) if (e.level == 0) {
+            const double c = chi2(e);
+            if (e.robust) { double rho[3]; huber(c, e.delta, rho); chi += rho[0]; } else chi += c;
+        }
+        return chi;
+    }
+    void build_system() {
+        for (int i = 0; i < 6; ++i) { b[i] = 0; for (int j = 0; j < 6; ++j) H[i][j] = 0; }
+        for (Edge& e : E) if (e.level == 0) {
+            double J[3][6];
+            jacobian(e, T, K, J);
+            double w = 1.0;
+            if (e.robust) { double rho[3]; huber(chi2(e), e.delta, rho); w = rho[1]; }
+            for (int r = 0; r < e.dim; ++r) {
+                const double oe = e.info[r] * e.err[r];
+                for (int i = 0; i < 6; ++i) {
+                    b[i] -= w * J[r][i] * oe;
+                    const double wi = w * e.info[r] * J[r][i];
+                    for (int j = 0; j < 6; ++j) H[i][j] += wi * J[r][j];
+                }
+            }
+        }
+    }
+    // returns 0 OK, 1 Terminate
+    int solve(int iteration) {
+        active_errors();
+        double currentChi = robust_chi2(), tempChi = currentChi;
+        const double iniChi = currentChi;
+        build_system();
+        if (iteration == 0) {
+            double mx = 0;
+            for (int j = 0; j < 6; ++j) mx = std::max(std::fabs(H[j][j]), mx);
+            lambda = 1e-5 * mx; ni = 2; nBad = 0;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            const SE3 backup = T;
+            double Hl[6][6];
+            for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) Hl[i][j] = H[i][j] + (i == j ? lambda : 0.0);
+            const bool ok2 = solve6(Hl, b, x);
+            // on failure g2o leaves x untouched (the previous solution, zero at the very start) and still applies it
+            T = se3_mul(se3_exp(x), T);
+            active_errors();
+            tempChi = robust_chi2();
+            if (!ok2) tempChi = DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = 0;
+            for (int j = 0; j < 6; ++j) scale += x[j] * (lambda * x[j] + b[j]);
+            scale += 1e-3;
+            rho /= scale;
+            if (rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1. - std::pow((2 * rho - 1), 3);
+                alpha = std::min(alpha, 2. / 3.);
+                const double sf = std::max(1. / 3., alpha);
+                lambda *= sf; ni = 2; currentChi = tempChi;
+            } else {
+                lambda *= ni; ni *= 2; T = backup;
+            }
+            ++qmax;
+        } while (rho < 0 && qmax < 10);
+        last_trials += qmax;
+        last_chi = currentChi;
+        if (qmax == 10 || rho == 0) return 1;
+        if ((iniChi - currentChi) * 1e3 < iniChi) ++nBad; else nBad = 0;
+        if (nBad >= 3) return 1;
+        return 0;
+    }
+    int optimize(int iterations) {
+        int done = 0;
+        last_trials = 0;
+        bool ok = true;
+        for (int i = 0; i < iterations && ok; ++i) { ok = solve(i) == 0; ++done; }
+        return done;
+    }
+};
+
+SE3 se3_from_float16(const float* T) {
+    M3 R;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R.m[i][j] = T[i * 4 + j];
+    return se3_from_Rt(R, {T[3], T[7], T[11]});
+}
+
+}  // namespace
+
+void pose_optimization(const PoseProblem& P, const float* Tcw_in, PoseResult& out) {
+    const Cam K{P.fx, P.fy, P.cx, P.cy, P.bf};
+    std::vector<Edge> E;
+    const float deltaMono = std::sqrt(5.991), deltaStereo = std::sqrt(7.815);
+    double angleInfo = 3282.8 / (P.angle_info * P.angle_info), disInfo = P.dist_info * P.dist_info;
+    double parInfo = 3282.8 / (P.par_info * P.par_info), verInfo = 3282.8 / (P.ver_info * P.ver_info);
+    const float deltaPlane = std::sqrt(P.plane_chi), VPdeltaPlane = std::sqrt(P.vp_chi);
+    out.outlier_pt.assign(P.n_points, 0); out.outlier_line.assign(P.n_lines, 0); out.outlier_plane.assign(P.n_planes, 0);
+    out.outlier_par.assign(P.n_par, 0); out.outlier_ver.assign(P.n_ver, 0);
+    int nInitial = 0;
+    for (int i = 0; i < P.n_points; ++i) {
+        Edge e;
+        const bool mono = P.obs[3 * i + 2] < 0;
+        e.kind = mono ? MONO : STEREO; e.dim = mono ? 2 : 3; e.idx = i;
+        e.Xw = {P.Xw[3 * i], P.Xw[3 * i + 1], P.Xw[3 * i + 2]};
+        for (int k = 0; k < 3; ++k) { e.obs[k] = P.obs[3 * i + k]; e.info[k] = P.inv_sigma2[i]; }
+        e.delta = mono ? deltaMono : deltaStereo;
+        E.push_back(e);
+        ++nInitial;
+    }
+    for (int i = 0; i < P.n_lines; ++i)
+        for (int s = 0; s < 2; ++s) {
+            Edge e;
+            e.kind = LINE; e.dim = 3; e.idx = i;
+            e.Xw = {P.line_Xw[6 * i + 3 * s], P.line_Xw[6 * i + 3 * s + 1], P.line_Xw[6 * i + 3 * s + 2]};
+            for (int k = 0; k < 3; ++k) { e.obs[k] = P.line_obs[3 * i + k]; e.info[k] = 1.0; }
+            e.delta = deltaStereo;
+            E.push_back(e);
+            if (s == 0) ++nInitial;
+        }
+    auto add_plane = [&](Kind kd, int n, const float* meas, const float* map, double i0, double i1, double i2, double delta) {
+        for (int i = 0; i < n; ++i) {
+            Edge e;
+            e.kind = kd; e.dim = (kd == PLANE) ? 3 : 2; e.idx = i;
+            e.pm = plane_from_float4(meas + 4 * i); e.pw = plane_from_float4(map + 4 * i);
+            e.info[0] = i0; e.info[1] = i1; e.info[2] = i2; e.delta = delta;
+            e.obs[0] = e.obs[1] = e.obs[2] = 0; e.Xw = {0, 0, 0};
+            E.push_back(e);
+            ++nInitial;
+        }
+    };
+    add_plane(PLANE, P.n_planes, P.plane_meas, P.plane_map, angleInfo, angleInfo, disInfo, deltaPlane);
+    add_plane(PAR, P.n_par, P.par_meas, P.par_map, parInfo, parInfo, 0, VPdeltaPlane);
+    add_plane(VER, P.n_ver, P.ver_meas, P.ver_map, verInfo, verInfo, 0, VPdeltaPlane);
+
+    const SE3 T0 = se3_from_float16(Tcw_in);
+    auto write_pose = [&](const SE3& T) {
+        const M3 R = quat_to_matrix(T.q);
+        const double tt[3] = {T.t.x, T.t.y, T.t.z};
+        for (int i = 0; i < 16; ++i) out.Tcw_d[i] = (i == 15) ? 1.0 : 0.0;
+        for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) out.Tcw_d[i * 4 + j] = R.m[i][j]; out.Tcw_d[i * 4 + 3] = tt[i]; }
+        for (int i = 0; i < 16; ++i) out.Tcw[i] = (float)out.Tcw_d[i];
+    };
+    out.n_rounds = 0;
+    if (nInitial < 3) { out.n_inliers = 0; write_pose(T0); for (int i = 0; i < 16; ++i) out.Tcw[i] = Tcw_in[i]; return; }
+    // the reference evaluates computeError() once on every plane edge while building the graph (:896, :935, :975)
+    for (Edge& e : E) if (e.kind == PLANE || e.kind == PAR || e.kind == VER) compute_error(e, T0, K);
+
+    const float chi2Mono = 5.991f, chi2Stereo = 7.815f;
+    Lm lm{E, K, T0};
+    int nBad = 0;
+    for (int it = 0; it < 4; ++it) {
+        lm.T = T0;
+        const int iters = lm.optimize(10);
+        nBad = 0;
+        for (size_t k = 0; k < E.size(); ++k) {
+            Edge& e = E[k];
+            if (e.kind == MONO || e.kind == STEREO) {
+                if (out.outlier_pt[e.idx]) compute_error(e, lm.T, K);
+                const float c = (float)chi2(e);
+                if (c > (e.kind == MONO ? chi2Mono : chi2Stereo)) { out.outlier_pt[e.idx] = 1; e.level = 1; ++nBad; }
+                else { out.outlier_pt[e.idx] = 0; e.level = 0; }
+            } else if (e.kind == LINE) {
+                Edge& e2 = E[k + 1];                       // start / end edges are adjacent
+                compute_error(e, lm.T, K); compute_error(e2, lm.T, K);
+                const float cs = (float)(e.err[0] * e.err[0]), ce = (float)(e2.err[0] * e2.err[0]);
+                if (cs > 2 * chi2Mono || ce > 2 * chi2Mono) { out.outlier_line[e.idx] = 1; e.level = e2.level = 1; ++nBad; }
+                else { out.outlier_line[e.idx] = 0; e.level = e2.level = 0; }
+                if (it == 2) e2.robust = false;
+                ++k;
+            } else {
+                std::vector<uint8_t>& flags = e.kind == PLANE ? out.outlier_plane : (e.kind == PAR ? out.outlier_par : out.outlier_ver);
+                if (flags[e.idx]) compute_error(e, lm.T, K);
+                const float c = (float)chi2(e);
+                const double th = e.kind == PLANE ? P.plane_chi : P.vp_chi;
+                if (c > th) { flags[e.idx] = 1; e.level = 1; ++nBad; } else { flags[e.idx] = 0; e.level = 0; }
+            }
+            if (it == 2) e.robust = false;
+        }
+        out.rounds[it] = {iters, lm.last_trials, lm.last_chi, lm.lambda, nBad};
+        out.n_rounds = it + 1;
+        if (E.size() < 10) break;
+    }
+    write_pose(lm.T);
+    out.n_inliers = nInitial - nBad;
+}
+
+}  // namespace oracle

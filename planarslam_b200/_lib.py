@@ -30,6 +30,18 @@ class Config(C.Structure):
                 ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("depth_scale", C.c_float)]
 
 
+class PoseProblem(C.Structure):
+    """pslam_pose_problem (include/pslam_abi.h)."""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("n_points", C.c_int32), ("Xw", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p),
+                ("n_lines", C.c_int32), ("line_Xw", C.c_void_p), ("line_obs", C.c_void_p),
+                ("n_planes", C.c_int32), ("n_par", C.c_int32), ("n_ver", C.c_int32),
+                ("plane_meas", C.c_void_p), ("plane_map", C.c_void_p), ("par_meas", C.c_void_p), ("par_map", C.c_void_p),
+                ("ver_meas", C.c_void_p), ("ver_map", C.c_void_p),
+                ("angle_info", C.c_double), ("dist_info", C.c_double), ("par_info", C.c_double), ("ver_info", C.c_double),
+                ("plane_chi", C.c_double), ("vp_chi", C.c_double)]
+
+
 class PslamError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"pslam error {code}: {msg}")
@@ -72,6 +84,11 @@ def lib() -> C.CDLL:
     L.pslam_peac_run_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pslam_peac_debug_blocks.argtypes = [vp, i32, vp, vp, vp, vp]
     L.pslam_peac_debug_coarse.argtypes = [vp, i32, vp, i32p]
+    L.pslam_pose_optimization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.pslam_pose_optimization_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.pslam_pose_pack.argtypes = [vp, vp, i32, vp]
+    L.pslam_pose_run_packed.argtypes = [vp]
+    L.pslam_pose_fetch.argtypes = [vp] + [vp] * 10
     _lib = L
     return L
 

@@ -25,7 +25,7 @@
 
 namespace pslam {
 
-#define PEAC_MAX_PLANES 128          // >= H*W / minSupport for 640x480 (102); checked at context creation
+#define PEAC_MAX_PLANES 128          // capacity (640x480 / minSupport = 102 at most); overflow raises a status flag
 #define PEAC_PL_WORDS (PEAC_MAX_PLANES / 32)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -544,9 +544,10 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
     const int item_in_group = lane >> 2, nbr = lane & 3;
     bool overflow = false;
 
-    for (int head = 0; head < tail; head += 8) {
+    for (int head = 0; head < tail;) {
+        const int group = min(8, tail - head);          // items consumed by this step (a partial group must not skip later pushes)
         const int k = head + item_in_group;
-        bool have = k < tail;
+        bool have = item_in_group < group;
         int c = -1, plid = 0;
         if (have) {
             const uint32_t e = q[k];
@@ -626,6 +627,7 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
             if (pos < g.queue_cap) q[pos] = (uint32_t)c | ((uint32_t)plid << 24); else overflow = true;
         }
         tail = min(tail + __popc(pm), g.queue_cap);
+        head += group;
         __syncwarp();
     }
     if (__any_sync(full, overflow) && lane == 0) atomicOr(status + frame, 32);

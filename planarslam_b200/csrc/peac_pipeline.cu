@@ -27,7 +27,8 @@ int peac_build_geometry(pslam_ctx* c) {
     g.sim_merge = std::cos(60.0 * M_PI / 180.0);
     g.sim_refine = std::cos(30.0 * M_PI / 180.0);
     g.depth_alpha = 0.04; g.depth_change_tol = 0.02;
-    if ((long long)g.w * g.h / g.min_support + 1 > PEAC_MAX_PLANES) return set_error(c, PSLAM_E_INVALID, "frame too large for PEAC_MAX_PLANES");
+    // PEAC_MAX_PLANES (128) is a capacity, not a bound derived from the frame size: a frame with more planes of >= 3000
+    // points each raises PSLAM_E_CAPACITY at run time (status flag 16).
     if ((long long)g.w * g.h >= (1 << 24)) return set_error(c, PSLAM_E_INVALID, "frame too large for the 24-bit pixel index");
     if (g.nblk < 1) return set_error(c, PSLAM_E_INVALID, "frame smaller than one PEAC block");
     if (!(cf.fx != 0.f) || !(cf.fy != 0.f) || !(cf.depth_scale > 0.f)) return set_error(c, PSLAM_E_INVALID, "fx, fy must be non-zero and depth_scale > 0");

@@ -59,6 +59,7 @@ struct PeacGeom {
 };
 
 struct PeacPlaneRec;
+struct PoseBuffers;
 
 }  // namespace pslam
 
@@ -109,6 +110,7 @@ struct pslam_ctx {
     pslam::PeacPlaneRec* d_final = nullptr; int32_t* d_scratch = nullptr;
     int32_t* d_labels = nullptr; pslam_plane* d_planes = nullptr; int32_t* d_nplanes = nullptr; int32_t* d_midx = nullptr; int32_t* d_moff = nullptr;
     uint16_t* h_depth = nullptr;                 // pinned
+    pslam::PoseBuffers* pose = nullptr;          // pose-optimisation staging (pose_pipeline.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
     int32_t* h_status = nullptr;
@@ -123,6 +125,8 @@ int orb_alloc(pslam_ctx* c);
 void orb_free(pslam_ctx* c);
 int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint* d_kps, uint8_t* d_desc, int cap,
                 int32_t* d_n);
+// pose optimisation (pose_pipeline.cu)
+void pose_free(pslam_ctx* c);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

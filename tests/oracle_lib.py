@@ -142,3 +142,44 @@ class PeacOracle:
         self.coarse_blocks = np.zeros(nb, np.int32)
         L.orc_peac_coarse_blocks(r, self.coarse_blocks.ctypes.data)
         L.orc_peac_free(r)
+
+
+class _PoseProblemC(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("n_points", C.c_int32), ("Xw", C.c_void_p), ("obs", C.c_void_p), ("inv_sigma2", C.c_void_p),
+                ("n_lines", C.c_int32), ("line_Xw", C.c_void_p), ("line_obs", C.c_void_p),
+                ("n_planes", C.c_int32), ("n_par", C.c_int32), ("n_ver", C.c_int32),
+                ("plane_meas", C.c_void_p), ("plane_map", C.c_void_p), ("par_meas", C.c_void_p), ("par_map", C.c_void_p),
+                ("ver_meas", C.c_void_p), ("ver_map", C.c_void_p),
+                ("angle_info", C.c_double), ("dist_info", C.c_double), ("par_info", C.c_double), ("ver_info", C.c_double),
+                ("plane_chi", C.c_double), ("vp_chi", C.c_double)]
+
+
+def pose_problem_struct(p: dict, cls=_PoseProblemC):
+    """Build the C struct (shared layout between the oracle and the product ABI) from a synth_pose problem dict.
+    Keeps references to the arrays alive on the returned object."""
+    s = cls()
+    s._keep = p
+    for k in ("fx", "fy", "cx", "cy", "bf", "angle_info", "dist_info", "par_info", "ver_info", "plane_chi", "vp_chi"):
+        setattr(s, k, p[k])
+    s.n_points, s.n_lines = len(p["Xw"]), len(p["line_Xw"])
+    s.n_planes, s.n_par, s.n_ver = len(p["plane_meas"]), len(p["par_meas"]), len(p["ver_meas"])
+    for k in ("Xw", "obs", "inv_sigma2", "line_Xw", "line_obs", "plane_meas", "plane_map", "par_meas", "par_map", "ver_meas", "ver_map"):
+        setattr(s, k, p[k].ctypes.data if p[k].size else None)
+    return s
+
+
+def pose_optimization(p: dict):
+    """Oracle PoseOptimization. Returns dict(Tcw float 4x4, Tcw_d, n_inliers, outlier flags, trace)."""
+    L = lib()
+    L.orc_pose_optimization.argtypes = [C.c_void_p] * 11
+    s = pose_problem_struct(p)
+    T0 = np.ascontiguousarray(p["Tcw0"], np.float32)
+    T = np.zeros((4, 4), np.float32)
+    Td = np.zeros((4, 4))
+    o = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes, s.n_par, s.n_ver)]
+    ti, td = np.zeros((4, 3), np.int32), np.zeros((4, 2))
+    n = L.orc_pose_optimization(C.byref(s), T0.ctypes.data, T.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], ti.ctypes.data,
+                                td.ctypes.data)
+    return dict(Tcw=T, Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes],
+                outlier_par=o[3][:s.n_par], outlier_ver=o[4][:s.n_ver], trace_i=ti, trace_d=td)
