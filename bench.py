@@ -33,8 +33,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H = 640, 480
-SUB_BATCH = 64            # frames per library call (context max_batch)
-SUBS_PER_STEP = 4         # library calls per step -> 256 frames = 236 MB of gray+depth input, larger than the 126 MB L2
+SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "256"))     # frames per library call (context max_batch)
+SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "1"))         # library calls per step; 256 frames = 236 MB of gray+depth input > 126 MB L2
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
 DISTINCT_FRAMES = 16      # rendered once (CPU, ~0.4 s each) and tiled with a per-copy intensity offset
 
@@ -45,6 +45,12 @@ ALGO_BYTES = {
     "orb_blur_level": 2 * 950532,             # read + write every level once
     "orb_quadtree": 30000 * 4 * 2,
     "orb_orient_describe": 1000 * (709 + 512 + 60),
+    "peac_blocks": 614400 + 3072 * (17 * 8 + 5),       # read depth once, write per-block sums + PCA
+    "peac_cluster": 2 * 3072 * (17 * 8 + 5) + 128 * 176,  # read block records, write node state + plane list
+    "peac_seed": 1228800 + 1228800 + 8000 * 4,         # write labels + distance map + seed queue
+    "peac_flood": 614400 + 130000 * (4 + 4 + 4 + 4),   # re-read depth at touched pixels, labels/dist RW, queue RW
+    "peac_final": 2 * 1228800 + 1228800,               # labels read + rewritten, member index lists written
+    "pose_optimization": 1046 * 104 + 1046 * 24 + 2048,   # edge records read once, residuals + flags written (per problem)
 }
 
 
@@ -109,8 +115,13 @@ def cpu_oracle_fps(gray, depth, seconds=12.0, threads=1):
     oracle_lib.lib()
     n = len(gray)
 
+    from planarslam_b200 import synth_pose
+    probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(min(n, 4))]
+
     def work(i):
-        oracle_lib.orb_extract(gray[i % n])      # ctypes releases the GIL inside the C call
+        oracle_lib.orb_extract(gray[i % n])      # ctypes releases the GIL inside the C calls
+        oracle_lib.PeacOracle(depth[i % n])
+        oracle_lib.pose_optimization(probs[i % len(probs)])
         return 1
 
     work(0)                                      # warm
@@ -140,15 +151,16 @@ def run_reference(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
             "config": workload_config(),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"oracle ORB stage on {len(gray)} frames looped for 6 s per step, {cores} threads"},
+                             "sample": f"oracle ORB + PEAC + PoseOptimization on {len(gray)} frames looped for 6 s per step, {cores} threads"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config():
-    return {"workload": "640x480 synthetic RGB-D sequence, ORB front end (1000 feats, 8 levels) [stages built so far: orb]",
+    return {"workload": "640x480 synthetic RGB-D sequence: ORB (1000 feats, 8 levels) + PEAC planes + PoseOptimization "
+                        "(1000 point + 40 line (80 edges) + 6 plane edges per frame); LSD/LBD and descriptor matching not built yet",
             "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "l2": "inputs_larger_than_l2",
-            "stages": ["orb"]}
+            "stages": ["orb", "peac", "pose_opt"], "streams": 3}
 
 
 def main():
@@ -173,37 +185,76 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from planarslam_b200._lib import Context, KEYPOINT_DTYPE
+    from planarslam_b200._lib import Context, KEYPOINT_DTYPE, PLANE_DTYPE
+    from planarslam_b200.optimizer import Optimizer
+    from planarslam_b200 import synth_pose
 
     gray, depth = make_frames()
     reps = FRAMES_PER_STEP // DISTINCT_FRAMES
     gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * r, 0, 255).astype(np.uint8) for r in range(reps)])
+    depth_step = np.concatenate([depth for _ in range(reps)])
     dev = torch.device("cuda", local_rank)
-    ctx = Context(W, H, SUB_BATCH, device=local_rank)
-    stream = torch.cuda.current_stream(dev)
-    ctx.set_stream(stream.cuda_stream)
-    cap = ctx.L.pslam_orb_max_keypoints(ctx.h)
+    main = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(3)]
+    ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(3)]       # one context (= one stream) per stage family
+    for c, st in zip(ctxs, streams):
+        c.set_stream(st.cuda_stream)
+    c_orb, c_peac, c_pose = ctxs
+    cap = c_orb.L.pslam_orb_max_keypoints(c_orb.h)
+    maxp = c_peac.L.pslam_peac_max_planes(c_peac.h)
+    L = c_orb.L
 
     d_gray = torch.from_numpy(gray_step).to(dev)                       # [FRAMES_PER_STEP, H, W] resident in HBM
-    d_kps = torch.empty((FRAMES_PER_STEP, cap, 28), dtype=torch.uint8, device=dev)
-    d_desc = torch.empty((FRAMES_PER_STEP, cap, 32), dtype=torch.uint8, device=dev)
+    d_depth = torch.from_numpy(depth_step.view(np.int16)).to(dev)      # uint16 bits
+    d_kps = torch.empty((SUB_BATCH, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.empty((SUB_BATCH, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.empty(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
+    d_labels = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
+    d_planes = torch.empty((SUB_BATCH, maxp, PLANE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_npl = torch.empty(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
+    d_midx = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
+    d_moff = torch.empty((SUB_BATCH, maxp + 1), dtype=torch.int32, device=dev)
     h_gray = torch.from_numpy(gray_step).pin_memory()
+    h_depth = torch.from_numpy(depth_step.view(np.int16)).pin_memory()
     h_kps = np.zeros((SUB_BATCH, cap), KEYPOINT_DTYPE)
     h_desc = np.zeros((SUB_BATCH, cap, 32), np.uint8)
     h_n = np.zeros(SUB_BATCH, np.int32)
+    h_labels = np.zeros((SUB_BATCH, H * W), np.int32)
+    h_planes = np.zeros((SUB_BATCH, maxp), PLANE_DTYPE)
+    h_npl = np.zeros(SUB_BATCH, np.int32)
+    # pose problems: one per frame of a sub-batch (the correspondences a tracker would hand over), packed + uploaded once
+    base_probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(16)]
+    probs = [base_probs[k % 16] for k in range(SUB_BATCH)]
+    opt = Optimizer(c_pose)
+    opt.pack(probs)
+    pose_h2d = sum(sum(p[k].nbytes for k in ("Xw", "obs", "inv_sigma2", "line_Xw", "line_obs", "plane_meas", "plane_map", "par_meas",
+                                              "par_map", "ver_meas", "ver_map")) + 64 for p in probs)
 
     def step_dev():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for st in streams:
+            st.wait_event(ev)
         for s in range(SUBS_PER_STEP):
             o = s * SUB_BATCH
-            ctx.check(ctx.L.pslam_orb_extract_batch_dev(ctx.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps[o].data_ptr(), d_desc[o].data_ptr(),
-                                                        cap, d_n[o:].data_ptr()))
+            c_orb.check(L.pslam_orb_extract_batch_dev(c_orb.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                                      d_n[o:].data_ptr()))
+            c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
+                                                    d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
+            opt.run_packed()
+        for st in streams:
+            e = torch.cuda.Event()
+            e.record(st)
+            main.wait_event(e)
 
     def step_e2e():
         for s in range(SUBS_PER_STEP):
             o = s * SUB_BATCH
-            ctx.check(ctx.L.pslam_orb_extract_batch(ctx.h, h_gray[o].data_ptr(), SUB_BATCH, h_kps.ctypes.data, h_desc.ctypes.data, cap,
-                                                    h_n.ctypes.data))
+            c_orb.check(L.pslam_orb_extract_batch(c_orb.h, h_gray[o].data_ptr(), SUB_BATCH, h_kps.ctypes.data, h_desc.ctypes.data, cap,
+                                                  h_n.ctypes.data))
+            c_peac.check(L.pslam_peac_run_batch(c_peac.h, h_depth[o].data_ptr(), SUB_BATCH, h_labels.ctypes.data, h_planes.ctypes.data,
+                                                h_npl.ctypes.data, None, None))
+            opt.PoseOptimizationBatch(probs)
 
     def barrier():
         if world > 1:
@@ -216,17 +267,18 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = ctx.launch_count
+    l0 = sum(c.launch_count for c in ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(main)
     for _ in range(args.steps):
         step_dev()
-    e1.record(stream)
+    e1.record(main)
     barrier()
     sampler.stop_flag = True
-    launches = ctx.launch_count - l0
+    launches = sum(c.launch_count for c in ctxs) - l0
     ms = e0.elapsed_time(e1)
     n_found = int(d_n.sum().item())
+    n_planes_found = int(d_npl.sum().item())
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -234,11 +286,10 @@ def main():
     value = world * FRAMES_PER_STEP * args.steps / (ms_max / 1e3)
 
     # ---- end to end through the host-pointer ABI ----
-    for _ in range(2):
-        step_e2e()
+    step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, args.steps // 2)
+    e2e_steps = max(2, args.steps // 3)
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
@@ -247,27 +298,32 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
-    h2d = FRAMES_PER_STEP * W * H
-    d2h = FRAMES_PER_STEP * (cap * 60 + 8)
+    h2d = FRAMES_PER_STEP * (W * H + 2 * W * H) + SUBS_PER_STEP * pose_h2d
+    d2h = FRAMES_PER_STEP * (cap * 60 + 8 + 4 * W * H + maxp * PLANE_DTYPE.itemsize + 4 + 64 + 1046 + 4)
 
     # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
-    ctx.profile(True)
+    for c in ctxs:
+        c.profile(True)
     step_dev()
-    rep = ctx.profile_report()
-    ctx.profile(False)
+    torch.cuda.synchronize(dev)
+    rep = {}
+    for c in ctxs:
+        rep.update(c.profile_report())
+        c.profile(False)
     peak, peak_kind = _peaks()
     per_kernel = {}
     for name, (n, tot_ms) in rep.items():
-        launches_per_frame_batch = n / SUBS_PER_STEP
-        bytes_per_launch = ALGO_BYTES.get(name, 0) * SUB_BATCH / max(launches_per_frame_batch, 1)
-        per_kernel[name] = {"launches": n, "ms_total": round(tot_ms, 4), "share": None,
+        frames_per_launch = FRAMES_PER_STEP / n
+        bytes_per_launch = ALGO_BYTES.get(name, 0) * frames_per_launch
+        per_kernel[name] = {"launches": n, "ms_total": round(tot_ms, 4), "share": None, "algo_bytes_per_launch": int(bytes_per_launch),
                             "achieved_gbs": round(bytes_per_launch / (tot_ms / n * 1e-3) / 1e9, 2)}
     tot = sum(v["ms_total"] for v in per_kernel.values()) or 1.0
     for v in per_kernel.values():
         v["share"] = round(v["ms_total"] / tot, 4)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_total"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 5), "traffic": None, "peak_kind": peak_kind,
+                "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 6), "traffic": None, "peak_kind": peak_kind,
+                "note": "serial-order kernels (quadtree, AHC, region growing, LM) run one warp/CTA per frame: latency-bound, see DESIGN.md",
                 "per_kernel": per_kernel}
 
     if rank == 0:
@@ -279,8 +335,8 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": roofline,
                 "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                                 "sample": f"oracle (restatement of the reference, -O2, scalar) ORB stage, {cpu_n} frames in ~12 s"},
-                "keypoints_per_frame": n_found / FRAMES_PER_STEP}
+                                 "sample": f"oracle (restatement of the reference, -O2, scalar) ORB + PEAC + PoseOptimization, {cpu_n} frames in ~12 s"},
+                "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,156 @@
+// pslam_adapter.hpp — header-only C++ adapter that re-creates the reference's class interfaces on top of the C ABI
+// (include/pslam_abi.h), so Frame / Tracking can switch to the B200 path without changing their call sites.
+//
+// The OpenCV/Eigen-typed overloads (cv::InputArray, std::vector<cv::KeyPoint>, cv::Mat K, ...) are compiled only when
+// PSLAM_WITH_OPENCV is defined (OpenCV headers are not installed in the authoring image); the plain-pointer overloads
+// below carry the same names and argument order and are what tests/test_adapter_compiles.py builds.
+//
+//   Planar_SLAM::ORBextractor::operator()      include/ORBextractor.h:59-61   -> pslam_orb_extract
+//   ORBextractor getters                       include/ORBextractor.h:63-83   -> pslam_orb_get_scale_tables
+//   PlaneDetection::readDepthImage / run...    include/PlaneExtractor.h:36-56 -> pslam_peac_run_batch
+//   Optimizer::PoseOptimization                include/Optimizer.h:38         -> pslam_pose_optimization
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "pslam_abi.h"
+
+namespace pslam_adapter {
+
+struct Image8 { const uint8_t* data; int width, height, stride; };       // CV_8UC1 view
+struct Image16 { const uint16_t* data; int width, height; };             // CV_16UC1 view, dense
+
+class Context {
+public:
+    Context(int width, int height, const pslam_config* overrides = nullptr) {
+        pslam_config cfg;
+        if (overrides) cfg = *overrides; else pslam_default_config(&cfg, width, height, 1);
+        cfg.width = width; cfg.height = height;
+        if (pslam_create(&cfg, &ctx_) != PSLAM_OK) throw std::runtime_error("pslam_create failed: no sm_100 GPU or bad configuration");
+        cfg_ = cfg;
+    }
+    ~Context() { pslam_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    pslam_ctx* get() const { return ctx_; }
+    const pslam_config& config() const { return cfg_; }
+private:
+    pslam_ctx* ctx_ = nullptr;
+    pslam_config cfg_;
+};
+
+// Same constructor arguments, getters and call operator as Planar_SLAM::ORBextractor.
+class ORBextractor {
+public:
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+        : nfeatures_(nfeatures), scaleFactor_(scaleFactor), nlevels_(nlevels), iniThFAST_(iniThFAST), minThFAST_(minThFAST) {}
+    ~ORBextractor() { delete ctx_; }
+
+    // void operator()(InputArray image, InputArray mask, vector<KeyPoint>& keypoints, OutputArray descriptors)
+    void operator()(const Image8& image, const void* /*mask, ignored like the reference*/, std::vector<pslam_keypoint>& keypoints,
+                    std::vector<uint8_t>& descriptors) {
+        keypoints.clear(); descriptors.clear();
+        if (!image.data || image.width <= 0 || image.height <= 0) return;           // reference: silent return on empty input
+        ensure(image.width, image.height);
+        const int cap = pslam_orb_max_keypoints(ctx_->get());
+        keypoints.resize(cap); descriptors.resize((size_t)cap * 32);
+        int32_t n = 0;
+        const int rc = pslam_orb_extract(ctx_->get(), image.data, image.stride, keypoints.data(), descriptors.data(), cap, &n);
+        if (rc != PSLAM_OK) throw std::runtime_error(pslam_last_error(ctx_->get()));
+        keypoints.resize(n); descriptors.resize((size_t)n * 32);
+    }
+    int GetLevels() const { return nlevels_; }
+    float GetScaleFactor() const { return scaleFactor_; }
+    std::vector<float> GetScaleFactors() { return table(0); }
+    std::vector<float> GetInverseScaleFactors() { return table(1); }
+    std::vector<float> GetScaleSigmaSquares() { return table(2); }
+    std::vector<float> GetInverseScaleSigmaSquares() { return table(3); }
+
+private:
+    void ensure(int w, int h) {
+        if (ctx_ && ctx_->config().width == w && ctx_->config().height == h) return;
+        delete ctx_; ctx_ = nullptr;
+        pslam_config cfg;
+        pslam_default_config(&cfg, w, h, 1);
+        cfg.nfeatures = nfeatures_; cfg.scale_factor = scaleFactor_; cfg.nlevels = nlevels_; cfg.ini_th_fast = iniThFAST_; cfg.min_th_fast = minThFAST_;
+        ctx_ = new Context(w, h, &cfg);
+    }
+    std::vector<float> table(int which) {
+        if (!ctx_) ensure(640, 480);
+        std::vector<float> t[4];
+        for (auto& v : t) v.resize(nlevels_);
+        pslam_orb_get_scale_tables(ctx_->get(), t[0].data(), t[1].data(), t[2].data(), t[3].data(), nullptr);
+        return t[which];
+    }
+    int nfeatures_; float scaleFactor_; int nlevels_, iniThFAST_, minThFAST_;
+    Context* ctx_ = nullptr;
+};
+
+// Same public surface as the reference's PlaneDetection (global namespace there).
+class PlaneDetection {
+public:
+    std::vector<std::vector<int>> plane_vertices_;     // vertex (pixel) indices each plane contains
+    std::vector<pslam_plane> extractedPlanes;          // plane_filter.extractedPlanes[i]->{normal, center, N, mse}
+    std::vector<int32_t> membershipImg;                // plane_filter.membershipImg (int32 per pixel)
+    int plane_num_ = 0;
+    ~PlaneDetection() { delete ctx_; }
+
+    // bool readDepthImage(cv::Mat depthImg, cv::Mat& K, float kScaleFactor); K = {fx, fy, cx, cy} of the float 3x3
+    bool readDepthImage(const Image16& depthImg, const float K[4], float kScaleFactor) {
+        if (!depthImg.data || depthImg.width <= 0) return false;
+        if (!ctx_ || ctx_->config().width != depthImg.width || ctx_->config().height != depthImg.height || std::memcmp(K, K_, sizeof K_) || kScaleFactor != scale_) {
+            delete ctx_; ctx_ = nullptr;
+            pslam_config cfg;
+            pslam_default_config(&cfg, depthImg.width, depthImg.height, 1);
+            cfg.fx = K[0]; cfg.fy = K[1]; cfg.cx = K[2]; cfg.cy = K[3]; cfg.depth_scale = kScaleFactor;
+            ctx_ = new Context(depthImg.width, depthImg.height, &cfg);
+            std::memcpy(K_, K, sizeof K_); scale_ = kScaleFactor;
+        }
+        depth_ = depthImg;
+        return true;
+    }
+    // void runPlaneDetection(int kDepthHeight, int kDepthWidth)
+    void runPlaneDetection(int /*kDepthHeight*/, int /*kDepthWidth*/) {
+        const size_t px = (size_t)depth_.width * depth_.height;
+        const int maxp = pslam_peac_max_planes(ctx_->get());
+        membershipImg.assign(px, -1);
+        std::vector<pslam_plane> planes(maxp);
+        std::vector<int32_t> midx(px), moff(maxp + 1);
+        int32_t n = 0;
+        const int rc = pslam_peac_run_batch(ctx_->get(), depth_.data, 1, membershipImg.data(), planes.data(), &n, midx.data(), moff.data());
+        if (rc != PSLAM_OK) throw std::runtime_error(pslam_last_error(ctx_->get()));
+        plane_num_ = n;
+        extractedPlanes.assign(planes.begin(), planes.begin() + n);
+        plane_vertices_.assign(n, {});
+        for (int k = 0; k < n; ++k) plane_vertices_[k].assign(midx.begin() + moff[k], midx.begin() + moff[k + 1]);
+    }
+private:
+    Context* ctx_ = nullptr;
+    Image16 depth_{nullptr, 0, 0};
+    float K_[4] = {0, 0, 0, 0}, scale_ = 0;
+};
+
+// static int Optimizer::PoseOptimization(Frame* pFrame): the Frame fields it reads are gathered into a pslam_pose_problem
+// by the caller under the same mutexes the reference takes (MapPoint/MapLine/MapPlane::mGlobalMutex, src/Optimizer.cc:590,691,786).
+class Optimizer {
+public:
+    explicit Optimizer(Context& ctx) : ctx_(ctx) {}
+    int PoseOptimization(const pslam_pose_problem& prob, float Tcw_io[16], std::vector<uint8_t>& mvbOutlier, std::vector<uint8_t>& mvbLineOutlier,
+                         std::vector<uint8_t>& mvbPlaneOutlier, std::vector<uint8_t>& mvbParPlaneOutlier, std::vector<uint8_t>& mvbVerPlaneOutlier) {
+        mvbOutlier.assign(prob.n_points > 0 ? prob.n_points : 1, 0); mvbLineOutlier.assign(prob.n_lines > 0 ? prob.n_lines : 1, 0);
+        mvbPlaneOutlier.assign(prob.n_planes > 0 ? prob.n_planes : 1, 0); mvbParPlaneOutlier.assign(prob.n_par > 0 ? prob.n_par : 1, 0);
+        mvbVerPlaneOutlier.assign(prob.n_ver > 0 ? prob.n_ver : 1, 0);
+        const int rc = pslam_pose_optimization(ctx_.get(), &prob, Tcw_io, mvbOutlier.data(), mvbLineOutlier.data(), mvbPlaneOutlier.data(),
+                                               mvbParPlaneOutlier.data(), mvbVerPlaneOutlier.data());
+        if (rc < 0) throw std::runtime_error(pslam_last_error(ctx_.get()));
+        mvbOutlier.resize(prob.n_points); mvbLineOutlier.resize(prob.n_lines); mvbPlaneOutlier.resize(prob.n_planes);
+        mvbParPlaneOutlier.resize(prob.n_par); mvbVerPlaneOutlier.resize(prob.n_ver);
+        return rc;      // nInitialCorrespondences - nBad
+    }
+private:
+    Context& ctx_;
+};
+
+}  // namespace pslam_adapter
