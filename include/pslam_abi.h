@@ -144,6 +144,24 @@ int pslam_peac_debug_blocks(pslam_ctx* ctx, int frame, double* st9, double* geo8
 int pslam_peac_debug_coarse(pslam_ctx* ctx, int frame, int32_t* blk_map, int32_t* n_coarse);
 int pslam_peac_num_blocks(const pslam_ctx* ctx);
 
+/* ---- Descriptor matching --------------------------------------------------------------------------
+ * Replaces the brute-force searches on the tracking path:
+ *   static int ORBmatcher::DescriptorDistance(const cv::Mat&, const cv::Mat&)            src/ORBmatcher.cc:1712-1728
+ *   int ORBmatcher::MatchORBPoints(Frame& cur, const Frame& last)                        src/ORBmatcher.cc:1332-1394
+ *       (cv::BFMatcher(NORM_HAMMING).match(cur.mDescriptors, last.mDescriptors) + the "dist < max(2*min_dist, 15)" gate;
+ *        the MapPoint* copy that follows, incl. its mvbOutlier[i] index quirk, stays in the caller)
+ *   int LSDmatcher::SearchByDescriptor(KeyFrame*, Frame&, vector<MapLine*>&)             src/LSDmatcher.cpp:242-279
+ *       (BFMatcher knnMatch k=2; the ratio test dist0/dist1 < 1/1.5 is one compare per row in the caller)
+ * For every query row: the two nearest train rows in (distance, train index) order -> idx2[i][0..1], dist2[i][0..1]
+ * (-1 / 256 when missing).  good / n_good (optional): MatchORBPoints' kept query indices in ascending order. */
+int pslam_hamming_knn2(pslam_ctx* ctx, const uint8_t* q, int nq, const uint8_t* t, int nt, int32_t* idx2, int32_t* dist2,
+                       int32_t* good, int32_t* n_good);
+/* Batched, device pointers, asynchronous: q [nframes][capq][32], t [nframes][capt][32], per-frame counts d_nq / d_nt,
+ * outputs [nframes][capq][2]; d_good [nframes][capq] and d_ngood [nframes] may be NULL. capt <= 65535. */
+int pslam_hamming_knn2_batch_dev(pslam_ctx* ctx, const uint8_t* d_q, const int32_t* d_nq, int capq, const uint8_t* d_t,
+                                 const int32_t* d_nt, int capt, int nframes, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_good,
+                                 int32_t* d_ngood);
+
 /* ---- Pose optimisation ---------------------------------------------------------------------------
  * Replaces  static int Optimizer::PoseOptimization(Frame* pFrame)     include/Optimizer.h:38, src/Optimizer.cc:550-1275.
  * A pslam_pose_problem carries exactly what that function reads from the Frame and the matched map objects:

@@ -84,6 +84,8 @@ def lib() -> C.CDLL:
     L.pslam_peac_run_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pslam_peac_debug_blocks.argtypes = [vp, i32, vp, vp, vp, vp]
     L.pslam_peac_debug_coarse.argtypes = [vp, i32, vp, i32p]
+    L.pslam_hamming_knn2.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, i32p]
+    L.pslam_hamming_knn2_batch_dev.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
     L.pslam_pose_optimization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.pslam_pose_optimization_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.pslam_pose_pack.argtypes = [vp, vp, i32, vp]

@@ -1,0 +1,46 @@
+"""Host-side mirror of the reference's brute-force descriptor searches (include/ORBmatcher.h:37-64,
+include/LSDmatcher.h:21-24) on top of the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Context
+
+
+class ORBmatcher:
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30          # src/ORBmatcher.cc:38-40
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, ctx: Context | None = None):
+        self.mfNNratio, self.mbCheckOrientation = nnratio, checkOri
+        self.ctx = ctx or Context(640, 480, 1)
+
+    def knn2(self, q: np.ndarray, t: np.ndarray, gate: bool = False):
+        q, t = np.ascontiguousarray(q, np.uint8), np.ascontiguousarray(t, np.uint8)
+        nq, nt = len(q), len(t)
+        idx, dist = np.full((max(nq, 1), 2), -1, np.int32), np.full((max(nq, 1), 2), 256, np.int32)
+        good, ng = np.zeros(max(nq, 1), np.int32), C.c_int32(0)
+        self.ctx.check(self.ctx.L.pslam_hamming_knn2(self.ctx.h, q.ctypes.data if nq else None, nq, t.ctypes.data if nt else None, nt,
+                                                     idx.ctypes.data, dist.ctypes.data, good.ctypes.data if gate else None, C.byref(ng)))
+        return idx[:nq], dist[:nq], good[:ng.value]
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:
+        return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+    def MatchORBPoints(self, cur_desc: np.ndarray, last_desc: np.ndarray):
+        """Returns (NPair, [(queryIdx, trainIdx, distance)] of the good matches)."""
+        idx, dist, good = self.knn2(cur_desc, last_desc, gate=True)
+        return len(good), [(int(i), int(idx[i, 0]), int(dist[i, 0])) for i in good]
+
+
+class LSDmatcher:
+    def __init__(self, ctx: Context | None = None):
+        self.orb = ORBmatcher(ctx=ctx)
+
+    def SearchByDescriptor(self, kf_desc: np.ndarray, frame_desc: np.ndarray):
+        """knn-2 of the key frame's line descriptors in the frame + ratio test 1/1.5 (src/LSDmatcher.cpp:256-276)."""
+        idx, dist, _ = self.orb.knn2(kf_desc, frame_desc)
+        keep = [(i, int(idx[i, 0])) for i in range(len(idx)) if idx[i, 1] >= 0 and dist[i, 0] / max(dist[i, 1], 1e-9) < 1.0 / 1.5]
+        return len(keep), keep
