@@ -198,6 +198,18 @@ int pslam_pose_run_packed(pslam_ctx* ctx);
 int pslam_pose_fetch(pslam_ctx* ctx, float* Tcw, double* Tcw_d, uint8_t* outlier_pt, uint8_t* outlier_line, uint8_t* outlier_plane,
                      uint8_t* outlier_par, uint8_t* outlier_ver, int32_t* n_inliers, int32_t* trace_i, double* trace_d);
 
+/* ---- Translation-only optimisation ---------------------------------------------------------------
+ * Replaces  static int Optimizer::TranslationOptimization(Frame* pFrame)   include/Optimizer.h, src/Optimizer.cc:2995-3737
+ * (rotation fixed by the Manhattan-frame tracker; map points, line endpoints and plane normals are pre-rotated by the
+ * float R_cw of Tcw_io and the edges use SE3Quat::mapTrans).  Same problem struct; par / ver planes are ignored like in the
+ * reference (:3215-3220); only points count as correspondences and the call returns 0 with the pose untouched when fewer
+ * than 3 points are matched (:3198-3200).  pslam_translation_pack + pslam_pose_run_packed + pslam_pose_fetch is the split form. */
+int pslam_translation_optimization(pslam_ctx* ctx, const pslam_pose_problem* prob, float* Tcw_io, uint8_t* outlier_pt,
+                                   uint8_t* outlier_line, uint8_t* outlier_plane);
+int pslam_translation_optimization_batch(pslam_ctx* ctx, const pslam_pose_problem* probs, int n, float* Tcw_io, uint8_t* outlier_pt,
+                                         uint8_t* outlier_line, uint8_t* outlier_plane, int32_t* n_inliers);
+int pslam_translation_pack(pslam_ctx* ctx, const pslam_pose_problem* probs, int n, const float* Tcw0);
+
 #ifdef __cplusplus
 }
 #endif

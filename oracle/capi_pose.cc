@@ -12,8 +12,8 @@ struct orc_pose_problem {
     double angle_info, dist_info, par_info, ver_info, plane_chi, vp_chi;
 };
 // trace: per round {lm_iterations, trials, n_bad} ints [4][3]; chi/lambda doubles [4][2]
-int orc_pose_optimization(const orc_pose_problem* p, const float* Tcw_in, float* Tcw_out, double* Tcw_d, uint8_t* o_pt, uint8_t* o_line,
-                          uint8_t* o_plane, uint8_t* o_par, uint8_t* o_ver, int32_t* trace_i, double* trace_d) {
+static int run_pose(int mode, const orc_pose_problem* p, const float* Tcw_in, float* Tcw_out, double* Tcw_d, uint8_t* o_pt, uint8_t* o_line,
+                    uint8_t* o_plane, uint8_t* o_par, uint8_t* o_ver, int32_t* trace_i, double* trace_d) {
     PoseProblem P;
     P.fx = p->fx; P.fy = p->fy; P.cx = p->cx; P.cy = p->cy; P.bf = p->bf;
     P.n_points = p->n_points; P.Xw = p->Xw; P.obs = p->obs; P.inv_sigma2 = p->inv_sigma2;
@@ -24,7 +24,7 @@ int orc_pose_optimization(const orc_pose_problem* p, const float* Tcw_in, float*
     P.angle_info = p->angle_info; P.dist_info = p->dist_info; P.par_info = p->par_info; P.ver_info = p->ver_info;
     P.plane_chi = p->plane_chi; P.vp_chi = p->vp_chi;
     PoseResult R;
-    pose_optimization(P, Tcw_in, R);
+    if (mode == 0) pose_optimization(P, Tcw_in, R); else translation_optimization(P, Tcw_in, R);
     std::memcpy(Tcw_out, R.Tcw, sizeof R.Tcw);
     if (Tcw_d) std::memcpy(Tcw_d, R.Tcw_d, sizeof R.Tcw_d);
     if (o_pt && P.n_points) std::memcpy(o_pt, R.outlier_pt.data(), P.n_points);
@@ -38,5 +38,13 @@ int orc_pose_optimization(const orc_pose_problem* p, const float* Tcw_in, float*
         if (trace_d) { trace_d[2 * r] = ok ? R.rounds[r].chi2_final : 0; trace_d[2 * r + 1] = ok ? R.rounds[r].lambda_final : 0; }
     }
     return R.n_inliers;
+}
+int orc_pose_optimization(const orc_pose_problem* p, const float* Tcw_in, float* Tcw_out, double* Tcw_d, uint8_t* o_pt, uint8_t* o_line,
+                          uint8_t* o_plane, uint8_t* o_par, uint8_t* o_ver, int32_t* trace_i, double* trace_d) {
+    return run_pose(0, p, Tcw_in, Tcw_out, Tcw_d, o_pt, o_line, o_plane, o_par, o_ver, trace_i, trace_d);
+}
+int orc_translation_optimization(const orc_pose_problem* p, const float* Tcw_in, float* Tcw_out, double* Tcw_d, uint8_t* o_pt, uint8_t* o_line,
+                                 uint8_t* o_plane, uint8_t* o_par, uint8_t* o_ver, int32_t* trace_i, double* trace_d) {
+    return run_pose(1, p, Tcw_in, Tcw_out, Tcw_d, o_pt, o_line, o_plane, o_par, o_ver, trace_i, trace_d);
 }
 }

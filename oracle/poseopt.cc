@@ -163,7 +163,7 @@ void plane_ominus_ver(const Plane& self, const Plane& meas, double e[2]) {
 }
 
 // ---- edges ----
-enum Kind { MONO, STEREO, LINE, PLANE, PAR, VER };
+enum Kind { MONO, STEREO, LINE, PLANE, PAR, VER, MONO_T, STEREO_T, LINE_T, PLANE_T };
 struct Edge {
     Kind kind;
     int dim;                 // residual dimension
@@ -201,6 +201,32 @@ void compute_error(Edge& e, const SE3& T, const Cam& K) {
             e.err[0] = e.obs[0] * u + e.obs[1] * v + e.obs[2]; e.err[1] = 0; e.err[2] = 0;
             break;
         }
+        case MONO_T: {
+            const V3 p = e.Xw + T.t;                                              // mapTrans: Xc + t
+            e.err[0] = e.obs[0] - (p.x / p.z * K.fx + K.cx);
+            e.err[1] = e.obs[1] - (p.y / p.z * K.fy + K.cy);
+            break;
+        }
+        case STEREO_T: {
+            const V3 p = e.Xw + T.t;
+            const float invz = 1.0f / (float)p.z;
+            const double r0 = p.x * invz * K.fx + K.cx, r1 = p.y * invz * K.fy + K.cy, r2 = r0 - K.bf * invz;
+            e.err[0] = e.obs[0] - r0; e.err[1] = e.obs[1] - r1; e.err[2] = e.obs[2] - r2;
+            break;
+        }
+        case LINE_T: {
+            const V3 p = e.Xw + T.t;
+            const double u = p.x / p.z * K.fx + K.cx, v = p.y / p.z * K.fy + K.cy;
+            e.err[0] = e.obs[0] * u + e.obs[1] * v + e.obs[2]; e.err[1] = 0; e.err[2] = 0;
+            break;
+        }
+        case PLANE_T: {                                                           // operator+(Isometry3D, Plane3D), Plane3D.h:201-209
+            Plane r{{e.pw.c[0], e.pw.c[1], e.pw.c[2], e.pw.c[3] - (T.t.x * e.pw.c[0] + T.t.y * e.pw.c[1] + T.t.z * e.pw.c[2])}};
+            if (r.c[3] < 0.0) for (int i = 0; i < 4; ++i) r.c[i] = -r.c[i];
+            plane_normalize(r);
+            plane_ominus(r, e.pm, e.err);
+            break;
+        }
         case PLANE: plane_ominus(plane_transform(T, e.pw), e.pm, e.err); break;
         case PAR: plane_ominus_par(plane_transform(T, e.pw), e.pm, e.err); break;
         case VER: plane_ominus_ver(plane_transform(T, e.pw), e.pm, e.err); break;
@@ -233,6 +259,19 @@ void jacobian(Edge& e, const SE3& T, const Cam& K, double J[3][6]) {
         }
         return;
     }
+    if (e.kind == MONO_T || e.kind == STEREO_T || e.kind == LINE_T) {
+        const V3 p = e.Xw + T.t;
+        const double x = p.x, y = p.y, invz = 1.0 / p.z, invz_2 = invz * invz;
+        if (e.kind == LINE_T) {
+            const double lx = e.obs[0], ly = e.obs[1];
+            J[0][3] = K.fx * lx * invz; J[0][4] = K.fy * ly * invz; J[0][5] = -(K.fx * lx * x + K.fy * ly * y) * invz_2;
+            return;
+        }
+        J[0][3] = -invz * K.fx; J[0][5] = x * invz_2 * K.fx;
+        J[1][4] = -invz * K.fy; J[1][5] = y * invz_2 * K.fy;
+        if (e.kind == STEREO_T) { J[2][3] = J[0][3]; J[2][5] = J[0][5] - K.bf * invz_2; }
+        return;
+    }
     // numeric central differences, delta = 1e-9 (base_unary_edge.hpp:94-116); _error is restored afterwards
     const double delta = 1e-9, scalar = 1.0 / (2 * delta);
     double keep[3] = {e.err[0], e.err[1], e.err[2]};
@@ -246,6 +285,7 @@ void jacobian(Edge& e, const SE3& T, const Cam& K, double J[3][6]) {
         for (int i = 0; i < e.dim; ++i) J[i][d] = scalar * (e1[i] - e.err[i]);
     }
     for (int i = 0; i < 3; ++i) e.err[i] = keep[i];
+    if (e.kind == PLANE_T) for (int i = 0; i < 3; ++i) J[i][0] = J[i][1] = J[i][2] = 0;   // EdgePlane.h:292-308
 }
 
 inline void huber(double e2, double delta, double rho[3]) {
@@ -460,6 +500,102 @@ void pose_optimization(const PoseProblem& P, const float* Tcw_in, PoseResult& ou
                 const float c = (float)chi2(e);
                 const double th = e.kind == PLANE ? P.plane_chi : P.vp_chi;
                 if (c > th) { flags[e.idx] = 1; e.level = 1; ++nBad; } else { flags[e.idx] = 0; e.level = 0; }
+            }
+            if (it == 2) e.robust = false;
+        }
+        out.rounds[it] = {iters, lm.last_trials, lm.last_chi, lm.lambda, nBad};
+        out.n_rounds = it + 1;
+        if (E.size() < 10) break;
+    }
+    write_pose(lm.T);
+    out.n_inliers = nInitial - nBad;
+}
+
+
+void translation_optimization(const PoseProblem& P, const float* Tcw_in, PoseResult& out) {
+    const Cam K{P.fx, P.fy, P.cx, P.cy, P.bf};
+    std::vector<Edge> E;
+    const float deltaMono = std::sqrt(5.991), deltaStereo = std::sqrt(7.815);
+    const double angleInfo = 3282.8 / (P.angle_info * P.angle_info), disInfo = P.dist_info * P.dist_info;
+    const float deltaPlane = std::sqrt(P.plane_chi);
+    out.outlier_pt.assign(P.n_points, 0); out.outlier_line.assign(P.n_lines, 0); out.outlier_plane.assign(P.n_planes, 0);
+    out.outlier_par.assign(P.n_par, 0); out.outlier_ver.assign(P.n_ver, 0);
+    // R_cw * X in float matrices (cv::Mat CV_32F product: double accumulation, float result)
+    auto rot_f = [&](double x, double y, double z, int row) -> float {
+        return (float)((double)Tcw_in[row * 4 + 0] * (double)(float)x + (double)Tcw_in[row * 4 + 1] * (double)(float)y + (double)Tcw_in[row * 4 + 2] * (double)(float)z);
+    };
+    int nInitial = 0;
+    for (int i = 0; i < P.n_points; ++i) {
+        Edge e;
+        const bool mono = P.obs[3 * i + 2] < 0;
+        e.kind = mono ? MONO_T : STEREO_T; e.dim = mono ? 2 : 3; e.idx = i;
+        e.Xw = {rot_f(P.Xw[3 * i], P.Xw[3 * i + 1], P.Xw[3 * i + 2], 0), rot_f(P.Xw[3 * i], P.Xw[3 * i + 1], P.Xw[3 * i + 2], 1),
+                rot_f(P.Xw[3 * i], P.Xw[3 * i + 1], P.Xw[3 * i + 2], 2)};
+        for (int k = 0; k < 3; ++k) { e.obs[k] = P.obs[3 * i + k]; e.info[k] = P.inv_sigma2[i]; }
+        e.delta = mono ? deltaMono : deltaStereo;
+        E.push_back(e);
+        ++nInitial;
+    }
+    for (int i = 0; i < P.n_lines; ++i)
+        for (int s = 0; s < 2; ++s) {
+            Edge e;
+            e.kind = LINE_T; e.dim = 3; e.idx = i;
+            const double* X = P.line_Xw + 6 * i + 3 * s;      // Converter::toCvVec: double -> float before the product
+            e.Xw = {rot_f(X[0], X[1], X[2], 0), rot_f(X[0], X[1], X[2], 1), rot_f(X[0], X[1], X[2], 2)};
+            for (int k = 0; k < 3; ++k) { e.obs[k] = P.line_obs[3 * i + k]; e.info[k] = 1.0; }
+            e.delta = deltaStereo;
+            E.push_back(e);
+        }
+    const SE3 T0 = se3_from_float16(Tcw_in);
+    auto write_pose = [&](const SE3& T) {
+        const M3 R = quat_to_matrix(T.q);
+        const double tt[3] = {T.t.x, T.t.y, T.t.z};
+        for (int i = 0; i < 16; ++i) out.Tcw_d[i] = (i == 15) ? 1.0 : 0.0;
+        for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) out.Tcw_d[i * 4 + j] = R.m[i][j]; out.Tcw_d[i * 4 + 3] = tt[i]; }
+        for (int i = 0; i < 16; ++i) out.Tcw[i] = (float)out.Tcw_d[i];
+    };
+    out.n_rounds = 0;
+    if (nInitial < 3) { out.n_inliers = 0; write_pose(T0); for (int i = 0; i < 16; ++i) out.Tcw[i] = Tcw_in[i]; return; }
+    for (int i = 0; i < P.n_planes; ++i) {
+        Edge e;
+        e.kind = PLANE_T; e.dim = 3; e.idx = i;
+        e.pm = plane_from_float4(P.plane_meas + 4 * i);
+        Plane pw = plane_from_float4(P.plane_map + 4 * i);
+        // Xw.rotateNormal(Converter::toMatrix3d(R_cw)): the float rotation widened to double, no renormalisation
+        const double n[3] = {pw.c[0], pw.c[1], pw.c[2]};
+        for (int r = 0; r < 3; ++r) pw.c[r] = (double)Tcw_in[r * 4 + 0] * n[0] + (double)Tcw_in[r * 4 + 1] * n[1] + (double)Tcw_in[r * 4 + 2] * n[2];
+        e.pw = pw;
+        e.info[0] = angleInfo; e.info[1] = angleInfo; e.info[2] = disInfo; e.delta = deltaPlane;
+        e.obs[0] = e.obs[1] = e.obs[2] = 0; e.Xw = {0, 0, 0};
+        compute_error(e, T0, K);                           // :3300-3305
+        E.push_back(e);
+    }
+    const float chi2Mono = 5.991f, chi2Stereo = 7.815f;
+    Lm lm{E, K, T0};
+    int nBad = 0;
+    for (int it = 0; it < 4; ++it) {
+        lm.T = T0;
+        const int iters = lm.optimize(10);
+        nBad = 0;
+        for (size_t k = 0; k < E.size(); ++k) {
+            Edge& e = E[k];
+            if (e.kind == MONO_T || e.kind == STEREO_T) {
+                if (out.outlier_pt[e.idx]) compute_error(e, lm.T, K);
+                const float c = (float)chi2(e);
+                if (c > (e.kind == MONO_T ? chi2Mono : chi2Stereo)) { out.outlier_pt[e.idx] = 1; e.level = 1; ++nBad; }
+                else { out.outlier_pt[e.idx] = 0; e.level = 0; }
+            } else if (e.kind == LINE_T) {
+                Edge& e2 = E[k + 1];
+                if (out.outlier_line[e.idx]) { compute_error(e, lm.T, K); compute_error(e2, lm.T, K); }
+                const float cs = (float)(e.err[0] * e.err[0]), ce = (float)(e2.err[0] * e2.err[0]);
+                if (cs > 2 * chi2Mono || ce > 2 * chi2Mono) { out.outlier_line[e.idx] = 1; e.level = e2.level = 1; }   // nLineBad, not nBad
+                else { out.outlier_line[e.idx] = 0; e.level = e2.level = 0; }
+                if (it == 2) e2.robust = false;
+                ++k;
+            } else {
+                if (out.outlier_plane[e.idx]) compute_error(e, lm.T, K);
+                const float c = (float)chi2(e);
+                if (c > P.plane_chi) { out.outlier_plane[e.idx] = 1; e.level = 1; ++nBad; } else { out.outlier_plane[e.idx] = 0; e.level = 0; }
             }
             if (it == 2) e.robust = false;
         }

@@ -55,4 +55,13 @@ struct PoseResult {
 // Tcw_in: float 4x4 row-major (Frame::mTcw)
 void pose_optimization(const PoseProblem& P, const float* Tcw_in, PoseResult& out);
 
+// Optimizer::TranslationOptimization (src/Optimizer.cc:2995-3737): rotation frozen, every map point / line endpoint /
+// plane normal is pre-rotated by R_cw (float, :3019,3066,3259) and the edges use SE3Quat::mapTrans (se3quat.h:221):
+//   EdgeSE3ProjectXYZOnlyTranslation / EdgeStereoSE3ProjectXYZOnlyTranslation  types_six_dof_expmap.h:173-201,233-261, .cpp:368-375,404-432,463-485
+//   EdgeLineProjectXYZOnlyTranslation  include/EdgeLine.h:247-337 ;  EdgePlaneOnlyTranslation  g2oAddition/EdgePlane.h:226-315
+// Differences from PoseOptimization that are reproduced: only points count as correspondences (:3137-3139, :3245-3246), the
+// function returns 0 before adding plane edges when fewer than 3 points are matched (:3198-3200), no parallel / vertical
+// plane edges (:3215-3220), line errors are only recomputed for flagged lines and line outliers do not enter nBad.
+void translation_optimization(const PoseProblem& P, const float* Tcw_in, PoseResult& out);
+
 }  // namespace oracle

@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
     L.pslam_pose_optimization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.pslam_pose_optimization_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.pslam_pose_pack.argtypes = [vp, vp, i32, vp]
+    L.pslam_translation_pack.argtypes = [vp, vp, i32, vp]
+    L.pslam_translation_optimization.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.pslam_translation_optimization_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pslam_pose_run_packed.argtypes = [vp]
     L.pslam_pose_fetch.argtypes = [vp] + [vp] * 10
     _lib = L

@@ -180,7 +180,10 @@ struct AhcState {
     int32_t* cid;            // [nslots] creation order (canonical neighbour order)
     uint8_t* alive;          // [nslots] still in the graph
     uint32_t* adj;           // [nslots][words]
-    int32_t* heap;           // [nslots]
+    int16_t* wlo;            // [nslots] first / last adjacency word that can hold a set bit (scans are limited to it)
+    int16_t* whi;
+    int32_t* heap;           // [nslots]  (shared memory)
+    double* key;             // [nslots]  mse of every slot, the heap key (shared memory)
     int32_t* nb_list;        // [nslots] scratch
     int32_t* ds_parent;      // disjoint set over initial blocks
     int32_t* ds_size;
@@ -200,25 +203,25 @@ __device__ __forceinline__ void ds_union(int32_t* parent, int32_t* size, int x, 
 }
 
 // libstdc++ binary-heap algorithms (std::priority_queue<.., PlaneSegMinMSECmp>): comp(a,b) = mse[b] < mse[a]
-__device__ __forceinline__ bool heap_comp(const double* geo, int a, int b) { return geo[b * 8 + 6] < geo[a * 8 + 6]; }
-__device__ __forceinline__ void heap_sift_up(int32_t* h, const double* geo, int hole, int top, int value) {
+__device__ __forceinline__ bool heap_comp(const double* key, int a, int b) { return key[b] < key[a]; }
+__device__ __forceinline__ void heap_sift_up(int32_t* h, const double* key, int hole, int top, int value) {
     int parent = (hole - 1) / 2;
-    while (hole > top && heap_comp(geo, h[parent], value)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
+    while (hole > top && heap_comp(key, h[parent], value)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
     h[hole] = value;
 }
-__device__ __forceinline__ void heap_push(int32_t* h, int& len, const double* geo, int id) { h[len] = id; ++len; heap_sift_up(h, geo, len - 1, 0, id); }
-__device__ __forceinline__ int heap_pop(int32_t* h, int& len, const double* geo) {
+__device__ __forceinline__ void heap_push(int32_t* h, int& len, const double* key, int id) { h[len] = id; ++len; heap_sift_up(h, key, len - 1, 0, id); }
+__device__ __forceinline__ int heap_pop(int32_t* h, int& len, const double* key) {
     const int top = h[0], value = h[len - 1];
     --len;
     if (len > 0) {
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            if (heap_comp(geo, h[child], h[child - 1])) --child;
+            if (heap_comp(key, h[child], h[child - 1])) --child;
             h[hole] = h[child]; hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); h[hole] = h[child - 1]; hole = child - 1; }
-        heap_sift_up(h, geo, hole, 0, value);
+        heap_sift_up(h, key, hole, 0, value);
     }
     return top;
 }
@@ -231,15 +234,16 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
     int step = 0;
     while (heap_len > 0 && step <= g.max_step) {
         int p = 0;
-        if (lane == 0) p = heap_pop(S.heap, heap_len, S.geo);
+        if (lane == 0) p = heap_pop(S.heap, heap_len, S.key);
         p = __shfl_sync(full, p, 0);
         heap_len = __shfl_sync(full, heap_len, 0);
         if (!S.alive[p]) continue;
+        const int plo = S.wlo[p], phi = S.whi[p];
         // ---- neighbours of p (set bits of its adjacency row), compacted in slot order ----
         int cnt = 0;
-        for (int w0 = 0; w0 < S.words; w0 += 32) {
+        for (int w0 = plo; w0 <= phi; w0 += 32) {
             const int w = w0 + lane;
-            uint32_t bits = (w < S.words) ? S.adj[(size_t)p * S.words + w] : 0u;
+            uint32_t bits = (w <= phi) ? S.adj[(size_t)p * S.words + w] : 0u;
             const int c = __popc(bits);
             int inc = c;
 #pragma unroll
@@ -253,8 +257,10 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
         const double* gp = S.geo + (size_t)p * 8;
         const double* sp = S.st + (size_t)p * 9;
         const int Np = S.N[p];
-        double best_mse = 0.0;
-        int best_nb = -1, best_cid = 0x7fffffff;
+        double bst[9], bgeo[8];
+        int best_nb = -1, best_cid = 0x7fffffff, best_N = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bgeo[k] = 0;
         for (int i = lane; i < cnt; i += 32) {
             const int q = S.nb_list[i];
             const double* gq = S.geo + (size_t)q * 8;
@@ -263,36 +269,48 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
             const double* sq = S.st + (size_t)q * 9;
 #pragma unroll
             for (int k = 0; k < 9; ++k) st[k] = sp[k] + sq[k];
-            peac_stats_compute(st, Np + S.N[q], geo);
+            const int Nq = S.N[q];
+            peac_stats_compute(st, Np + Nq, geo);
             const int cq = S.cid[q];
-            if (best_nb < 0 || geo[6] < best_mse || (geo[6] == best_mse && cq < best_cid)) { best_mse = geo[6]; best_nb = q; best_cid = cq; }
+            if (best_nb < 0 || geo[6] < bgeo[6] || (geo[6] == bgeo[6] && cq < best_cid)) {
+                best_nb = q; best_cid = cq; best_N = Np + Nq;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) bst[k] = st[k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bgeo[k] = geo[k];
+            }
         }
         // warp argmin over (mse, cid); lanes without a candidate carry best_nb = -1
+        double w_mse = bgeo[6];
+        int w_nb = best_nb, w_cid = best_cid;
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            const double om = __shfl_xor_sync(full, best_mse, o);
-            const int onb = __shfl_xor_sync(full, best_nb, o), oc = __shfl_xor_sync(full, best_cid, o);
-            if (onb >= 0 && (best_nb < 0 || om < best_mse || (om == best_mse && oc < best_cid))) { best_mse = om; best_nb = onb; best_cid = oc; }
+            const double om = __shfl_xor_sync(full, w_mse, o);
+            const int onb = __shfl_xor_sync(full, w_nb, o), oc = __shfl_xor_sync(full, w_cid, o);
+            if (onb >= 0 && (w_nb < 0 || om < w_mse || (om == w_mse && oc < w_cid))) { w_mse = om; w_nb = onb; w_cid = oc; }
         }
         // (The reference's tie rule `cand.N < merge.mse` (AHCPlaneFitter.hpp:1045) can only fire when two merges have
         //  bit-identical mse AND mse exceeds the point count; with metre-valued clouds mse << 1, so the first
         //  candidate in canonical order wins a tie, which is what the (mse, cid) order above implements.)
         bool merged = false;
-        if (best_nb >= 0) {
-            const int nb = best_nb;
+        if (w_nb >= 0) {
+            const int nb = w_nb;
+            // the lane that evaluated the winning merge broadcasts its sums and PCA
+            const int src = __ffs(__ballot_sync(full, best_nb == nb)) - 1;
             double st[9], geo[8];
-            const double* sq = S.st + (size_t)nb * 9;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) st[k] = sp[k] + sq[k];
-            const int Nc = Np + S.N[nb];
-            peac_stats_compute(st, Nc, geo);
+            for (int k = 0; k < 9; ++k) st[k] = __shfl_sync(full, bst[k], src);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) geo[k] = __shfl_sync(full, bgeo[k], src);
+            const int Nc = __shfl_sync(full, best_N, src);
             if (geo[6] < peac_t_mse(g, g.std_tol_merge, geo[2])) {
                 merged = true;
                 // mergeNbsFrom: union in the disjoint set, new neighbour set = nbs(p) | nbs(nb) - {p, nb}
                 const int rid_c = Np >= S.N[nb] ? S.rid[p] : S.rid[nb];
                 if (lane == 0) ds_union(S.ds_parent, S.ds_size, S.rid[p], S.rid[nb]);
+                const int nlo = S.wlo[nb], nhi = S.whi[nb];
                 // every neighbour q of nb: forget nb, learn p (the merged node lives in p's slot)
-                for (int w = lane; w < S.words; w += 32) {
+                for (int w = nlo + lane; w <= nhi; w += 32) {
                     uint32_t bits = S.adj[(size_t)nb * S.words + w];
                     while (bits) {
                         const int q = w * 32 + __ffs(bits) - 1;
@@ -300,10 +318,13 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
                         if (q == p) continue;
                         atomicAnd(&S.adj[(size_t)q * S.words + (nb >> 5)], ~(1u << (nb & 31)));
                         atomicOr(&S.adj[(size_t)q * S.words + (p >> 5)], 1u << (p & 31));
+                        if ((p >> 5) < S.wlo[q]) S.wlo[q] = (int16_t)(p >> 5);      // q is touched by exactly one lane here
+                        if ((p >> 5) > S.whi[q]) S.whi[q] = (int16_t)(p >> 5);
                     }
                 }
                 __syncwarp();
-                for (int w = lane; w < S.words; w += 32) {
+                const int clo = min(plo, nlo), chi = max(phi, nhi);
+                for (int w = clo + lane; w <= chi; w += 32) {
                     uint32_t u = S.adj[(size_t)p * S.words + w] | S.adj[(size_t)nb * S.words + w];
                     if (w == (p >> 5)) u &= ~(1u << (p & 31));
                     if (w == (nb >> 5)) u &= ~(1u << (nb & 31));
@@ -312,17 +333,20 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
                 }
                 if (lane < 9) S.st[(size_t)p * 9 + lane] = st[lane];
                 if (lane < 8) S.geo[(size_t)p * 8 + lane] = geo[lane];
-                if (lane == 0) { S.N[p] = Nc; S.rid[p] = rid_c; S.cid[p] = next_cid; S.alive[nb] = 0; }
+                if (lane == 0) {
+                    S.N[p] = Nc; S.rid[p] = rid_c; S.cid[p] = next_cid; S.alive[nb] = 0; S.key[p] = geo[6];
+                    S.wlo[p] = (int16_t)clo; S.whi[p] = (int16_t)chi;
+                }
                 ++next_cid;
                 __syncwarp();
-                if (lane == 0) heap_push(S.heap, heap_len, S.geo, p);
+                if (lane == 0) heap_push(S.heap, heap_len, S.key, p);
                 heap_len = __shfl_sync(full, heap_len, 0);
             }
         }
         if (!merged) {
             if (Np >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex] = p; ++n_ex; } else overflow = true; }
             // disconnectAllNbs(p)
-            for (int w = lane; w < S.words; w += 32) {
+            for (int w = plo + lane; w <= phi; w += 32) {
                 uint32_t bits = S.adj[(size_t)p * S.words + w];
                 while (bits) { const int q = w * 32 + __ffs(bits) - 1; bits &= bits - 1; atomicAnd(&S.adj[(size_t)q * S.words + (p >> 5)], ~(1u << (p & 31))); }
                 S.adj[(size_t)p * S.words + w] = 0u;
@@ -335,7 +359,7 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
     // (maxStep is never reached in practice; the reference then just drains the queue, :1168-1175)
     while (heap_len > 0) {
         int p = 0;
-        if (lane == 0) p = heap_pop(S.heap, heap_len, S.geo);
+        if (lane == 0) p = heap_pop(S.heap, heap_len, S.key);
         p = __shfl_sync(full, p, 0);
         heap_len = __shfl_sync(full, heap_len, 0);
         if (S.alive[p] && S.N[p] >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex] = p; ++n_ex; } else overflow = true; }
@@ -362,7 +386,7 @@ struct PeacPlaneRec {
 __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* __restrict__ blk_st, const double* __restrict__ blk_geo,
                                                      const int32_t* __restrict__ blk_n, const uint8_t* __restrict__ blk_valid,
                                                      double* node_st, double* node_geo, int32_t* node_n, int32_t* node_rid, int32_t* node_cid,
-                                                     uint8_t* node_alive, uint32_t* adj, int32_t* heap, int32_t* nb_list, int32_t* ds_parent,
+                                                     uint8_t* node_alive, uint32_t* adj, int16_t* wlo_all, int16_t* whi_all, int32_t* nb_list, int32_t* ds_parent,
                                                      int32_t* ds_size, PeacPlaneRec* planes, int32_t* n_planes, int32_t* blk_map,
                                                      int32_t* next_cid_out, int32_t* status) {
     const int frame = blockIdx.x, lane = threadIdx.x;
@@ -370,7 +394,11 @@ __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* _
     AhcState S;
     S.nslots = g.nblk; S.words = g.adj_words;
     S.st = node_st + fo * 9; S.geo = node_geo + fo * 8; S.N = node_n + fo; S.rid = node_rid + fo; S.cid = node_cid + fo;
-    S.alive = node_alive + fo; S.adj = adj + fo * g.adj_words; S.heap = heap + fo; S.nb_list = nb_list + fo;
+    extern __shared__ __align__(16) unsigned char cluster_smem[];
+    S.key = reinterpret_cast<double*>(cluster_smem);                               // [nblk]
+    S.heap = reinterpret_cast<int32_t*>(cluster_smem + (size_t)g.nblk * sizeof(double));   // [nblk]
+    S.alive = node_alive + fo; S.adj = adj + fo * g.adj_words; S.nb_list = nb_list + fo;
+    S.wlo = wlo_all + fo; S.whi = whi_all + fo;
     S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
     const uint8_t* valid = blk_valid + fo;
     // node slots = blocks
@@ -379,6 +407,9 @@ __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* _
         for (int k = 0; k < 8; ++k) S.geo[(size_t)b * 8 + k] = blk_geo[(fo + b) * 8 + k];
         S.N[b] = blk_n[fo + b]; S.rid[b] = b; S.cid[b] = b; S.alive[b] = valid[b];
         S.ds_parent[b] = b; S.ds_size[b] = 1;
+        S.key[b] = blk_geo[(fo + b) * 8 + 6];
+        // a block can only be connected to b-1, b+1, b-Nw, b+Nw
+        S.wlo[b] = (int16_t)(max(b - g.nbw, 0) >> 5); S.whi[b] = (int16_t)(min(b + g.nbw, g.nblk - 1) >> 5);
     }
     __syncwarp();
     auto connect = [&](int a, int b) {
@@ -422,7 +453,7 @@ __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* _
     // initial heap: valid blocks pushed in block order (:810-811)
     int heap_len = 0;
     if (lane == 0)
-        for (int b = 0; b < g.nblk; ++b) if (valid[b]) heap_push(S.heap, heap_len, S.geo, b);
+        for (int b = 0; b < g.nblk; ++b) if (valid[b]) heap_push(S.heap, heap_len, S.key, b);
     heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
     __syncwarp();
 
@@ -524,12 +555,19 @@ __global__ void __launch_bounds__(256) k_peac_seed(PeacGeom g, const int32_t* __
 
 // ---------------------------------------------------------------------------------------------------------
 // K-P4: region growing (floodFill :428-476). One warp per frame; lane = (queue item % 8) * 4 + neighbour.
-// All 32 (item, neighbour) touches of a group run in parallel unless two lanes address the same pixel and at
-// least one of them would change it; such a group is replayed lane by lane in queue order (exact FIFO semantics).
+// The 32 (item, neighbour) touches of a step are independent unless two lanes address the same pixel; lanes that share
+// a pixel run in lane (= queue) order, one per round, while all other lanes run in the first round — exact FIFO
+// semantics, at most 4 rounds.  Plane records and the block map live in shared memory (they are read on every touch).
+struct FloodPlane { double n[3], c[3], th; };     // th = 9 * mse + 1e-5
+
 __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* __restrict__ depth, const int32_t* __restrict__ blk_map,
-                                                   const PeacPlaneRec* __restrict__ planes, int32_t* __restrict__ labels, float* __restrict__ dist,
+                                                   const PeacPlaneRec* __restrict__ planes, const int32_t* __restrict__ n_planes,
+                                                   int32_t* __restrict__ labels, float* __restrict__ dist,
                                                    uint32_t* __restrict__ queue, int32_t* __restrict__ q_len, uint32_t* __restrict__ pl_adj,
                                                    int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char flood_smem[];
+    FloodPlane* sP = reinterpret_cast<FloodPlane*>(flood_smem);                       // [PEAC_MAX_PLANES]
+    int8_t* sbm = reinterpret_cast<int8_t*>(flood_smem + PEAC_MAX_PLANES * sizeof(FloodPlane));   // [nblk] plane id or -1
     const int frame = blockIdx.x, lane = threadIdx.x;
     const uint32_t full = 0xffffffffu;
     const uint16_t* D = depth + (size_t)frame * g.w * g.h;
@@ -539,6 +577,15 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
     float* dm = dist + (size_t)frame * g.w * g.h;
     uint32_t* q = queue + (size_t)frame * g.queue_cap;
     uint32_t* padj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
+    const int np = n_planes[frame];
+    for (int i = lane; i < np; i += 32) {
+        FloodPlane f;
+        for (int k = 0; k < 3; ++k) { f.n[k] = P[i].normal[k]; f.c[k] = P[i].center[k]; }
+        f.th = 9 * P[i].mse + 1e-5;
+        sP[i] = f;
+    }
+    for (int b = lane; b < g.nblk; b += 32) sbm[b] = (int8_t)bm[b];
+    __syncwarp();
     int tail = q_len[frame];
     const double scale = (double)g.scale, fx = (double)g.fx, fy = (double)g.fy, cx = (double)g.cx, cy = (double)g.cy;
     const int item_in_group = lane >> 2, nbr = lane & 3;
@@ -548,78 +595,66 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
         const int group = min(8, tail - head);          // items consumed by this step (a partial group must not skip later pushes)
         const int k = head + item_in_group;
         bool have = item_in_group < group;
-        int c = -1, plid = 0;
+        int c = -1, plid = 0, cx_ = 0, cy_ = 0;
         if (have) {
             const uint32_t e = q[k];
             const int s = e & 0xffffff;
             plid = e >> 24;
             const int sy = s / g.w, sx = s - sy * g.w;
             // neighbour order of getValid4Neighbor (:393-405): left, right, up, down, skipping the ones outside
-            int cand[4], nn = 0;
-            if (sx > 0) cand[nn++] = s - 1;
-            if (sx < g.w - 1) cand[nn++] = s + 1;
-            if (sy > 0) cand[nn++] = s - g.w;
-            if (sy < g.h - 1) cand[nn++] = s + g.w;
-            if (nbr < nn) c = cand[nbr]; else have = false;
+            int n = nbr;
+            have = false;
+            if (sx > 0) { if (n == 0) { c = s - 1; cx_ = sx - 1; cy_ = sy; have = true; } --n; }
+            if (sx < g.w - 1) { if (n == 0 && !have) { c = s + 1; cx_ = sx + 1; cy_ = sy; have = true; } --n; }
+            if (sy > 0) { if (n == 0 && !have) { c = s - g.w; cx_ = sx; cy_ = sy - 1; have = true; } --n; }
+            if (sy < g.h - 1) { if (n == 0 && !have) { c = s + g.w; cx_ = sx; cy_ = sy + 1; have = true; } --n; }
         }
-        // a touch is "inert" when the reference skips it before reading the point (:445-450 for the state seen now)
-        auto inert_now = [&](int cc, int pl) -> bool {
-            const int tr = lab[cc];
-            if (tr <= -6) return true;
-            if (tr >= 0 && tr == pl) return true;
-            const int cy_ = cc / g.w, cx_ = cc - cy_ * g.w;
+        // pixels inside a kept block are skipped by every touch and never change: drop them before the conflict test
+        if (have) {
             const int by = cy_ / g.win, bx = cx_ / g.win;
-            return by < g.nbh && bx < g.nbw && bm[by * g.nbw + bx] >= 0;
-        };
-        // full reference semantics for one touch; returns true when the pixel is pushed
-        auto touch = [&](int cc, int pl) -> bool {
-            int tr = lab[cc];
+            if (by < g.nbh && bx < g.nbw && sbm[by * g.nbw + bx] >= 0) have = false;
+        }
+        // full reference semantics for one touch (:444-473); returns true when the pixel is pushed
+        auto touch = [&]() -> bool {
+            const int tr = lab[c];
             if (tr <= -6) return false;
-            if (tr >= 0 && tr == pl) return false;
-            const int cy_ = cc / g.w, cx_ = cc - cy_ * g.w;
-            const int by = cy_ / g.win, bx = cx_ / g.win;
-            if (by < g.nbh && bx < g.nbw && bm[by * g.nbw + bx] >= 0) return false;
-            const PeacPlaneRec& pr = P[pl];
-            const int dv = D[cc];
+            if (tr >= 0 && tr == plid) return false;
+            const FloodPlane& pr = sP[plid];
+            const int dv = D[c];
             bool ok = false;
             float cdist = -1.f;
             if (dv != 0) {
                 const double z = (double)dv * scale;
                 const double x = ((double)cx_ - cx) * z / fx, y = ((double)cy_ - cy) * z / fy;
-                const double sd = pr.normal[0] * (x - pr.center[0]) + pr.normal[1] * (y - pr.center[1]) + pr.normal[2] * (z - pr.center[2]);
+                const double sd = pr.n[0] * (x - pr.c[0]) + pr.n[1] * (y - pr.c[1]) + pr.n[2] * (z - pr.c[2]);
                 cdist = (float)fabs(sd);
-                ok = (double)cdist * (double)cdist < 9 * pr.mse + 1e-5;
+                ok = (double)cdist * (double)cdist < pr.th;
             }
             bool pushed = false;
             if (ok) {
                 if (tr >= 0) {
-                    const PeacPlaneRec& other = P[tr];
-                    const double sim = fabs(pr.normal[0] * other.normal[0] + pr.normal[1] * other.normal[1] + pr.normal[2] * other.normal[2]);
+                    const FloodPlane& other = sP[tr];
+                    const double sim = fabs(pr.n[0] * other.n[0] + pr.n[1] * other.n[1] + pr.n[2] * other.n[2]);
                     if (sim >= g.sim_refine) {
-                        atomicOr(&padj[tr * PEAC_PL_WORDS + (pl >> 5)], 1u << (pl & 31));
-                        atomicOr(&padj[pl * PEAC_PL_WORDS + (tr >> 5)], 1u << (tr & 31));
+                        atomicOr(&padj[tr * PEAC_PL_WORDS + (plid >> 5)], 1u << (plid & 31));
+                        atomicOr(&padj[plid * PEAC_PL_WORDS + (tr >> 5)], 1u << (tr & 31));
                     }
                 }
-                if (cdist < dm[cc]) { lab[cc] = pl; dm[cc] = cdist; pushed = true; }
-                else if (tr < 0) lab[cc] = tr - 1;
-            } else if (tr < 0) lab[cc] = tr - 1;
+                if (cdist < dm[c]) { lab[c] = plid; dm[c] = cdist; pushed = true; }
+                else if (tr < 0) lab[c] = tr - 1;
+            } else if (tr < 0) lab[c] = tr - 1;
             return pushed;
         };
-
-        const bool active = have && !inert_now(c, plid);
-        // conflict: two lanes of the group address the same pixel and at least one of them is active
+        // lanes that address the same pixel form a group and execute in lane order, one per round
         const uint32_t peers = __match_any_sync(full, have ? c : -1 - lane);
-        const uint32_t act_mask = __ballot_sync(full, active);
-        const bool conflict = have && (__popc(peers) > 1) && (peers & act_mask);
+        const int my_round = __popc(peers & ((1u << lane) - 1));
+        int rounds = __popc(peers);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) rounds = max(rounds, __shfl_xor_sync(full, rounds, o));
         bool pushed = false;
-        if (!__any_sync(full, conflict)) {
-            if (active) pushed = touch(c, plid);
+        for (int r = 0; r < rounds; ++r) {
+            if (have && my_round == r) pushed = touch();
             __syncwarp();
-        } else {
-            for (int l = 0; l < 32; ++l) {
-                if (lane == l && have) pushed = touch(c, plid);
-                __syncwarp();
-            }
         }
         const uint32_t pm = __ballot_sync(full, pushed);
         if (pushed) {
@@ -647,6 +682,8 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
     __shared__ double s_geo[PEAC_MAX_PLANES * 8];
     __shared__ int32_t s_n[PEAC_MAX_PLANES], s_rid[PEAC_MAX_PLANES], s_cid[PEAC_MAX_PLANES], s_heap[PEAC_MAX_PLANES], s_nb[PEAC_MAX_PLANES];
     __shared__ uint8_t s_alive[PEAC_MAX_PLANES];
+    __shared__ double s_key[PEAC_MAX_PLANES];
+    __shared__ int16_t s_wlo[PEAC_MAX_PLANES], s_whi[PEAC_MAX_PLANES];
     __shared__ int32_t s_ex[PEAC_MAX_PLANES], s_map[PEAC_MAX_PLANES];
     __shared__ int s_nfinal;
     PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
@@ -658,6 +695,7 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
         for (int k = 0; k < 3; ++k) { s_geo[i * 8 + k] = P[i].center[k]; s_geo[i * 8 + 3 + k] = P[i].normal[k]; }
         s_geo[i * 8 + 6] = P[i].mse; s_geo[i * 8 + 7] = P[i].curvature;
         s_n[i] = P[i].N; s_rid[i] = P[i].rid; s_cid[i] = P[i].cid; s_alive[i] = (uint8_t)P[i].valid;
+        s_key[i] = P[i].mse; s_wlo[i] = 0; s_whi[i] = PEAC_PL_WORDS - 1;
         s_map[i] = -1;
     }
     __syncthreads();
@@ -666,10 +704,10 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
         S.nslots = np; S.words = PEAC_PL_WORDS;
         S.st = s_st; S.geo = s_geo; S.N = s_n; S.rid = s_rid; S.cid = s_cid; S.alive = s_alive;
         S.adj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
-        S.heap = s_heap; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
+        S.heap = s_heap; S.key = s_key; S.wlo = s_wlo; S.whi = s_whi; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
         // planes that were eroded completely take no part: drop their adjacency (they never got any) and skip the push
         int heap_len = 0;
-        if (tid == 0) for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, S.geo, i);
+        if (tid == 0) for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, S.key, i);
         heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
         __syncwarp();
         int n_ex = 0, next_cid = next_cid_in[frame];

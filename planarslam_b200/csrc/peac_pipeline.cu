@@ -47,7 +47,7 @@ int peac_alloc(pslam_ctx* c) {
     A(dmalloc(c, &c->d_blk_st, B * nb * 9)); A(dmalloc(c, &c->d_blk_geo, B * nb * 8)); A(dmalloc(c, &c->d_blk_n, B * nb)); A(dmalloc(c, &c->d_blk_valid, B * nb));
     A(dmalloc(c, &c->d_node_st, B * nb * 9)); A(dmalloc(c, &c->d_node_geo, B * nb * 8)); A(dmalloc(c, &c->d_node_n, B * nb));
     A(dmalloc(c, &c->d_node_rid, B * nb)); A(dmalloc(c, &c->d_node_cid, B * nb)); A(dmalloc(c, &c->d_node_alive, B * nb));
-    A(dmalloc(c, &c->d_adj, B * nb * g.adj_words)); A(dmalloc(c, &c->d_heap, B * nb)); A(dmalloc(c, &c->d_nb_list, B * nb));
+    A(dmalloc(c, &c->d_adj, B * nb * g.adj_words)); A(dmalloc(c, &c->d_wlo, B * nb)); A(dmalloc(c, &c->d_whi, B * nb)); A(dmalloc(c, &c->d_nb_list, B * nb));
     A(dmalloc(c, &c->d_ds_parent, B * nb)); A(dmalloc(c, &c->d_ds_size, B * nb));
     A(dmalloc(c, &c->d_coarse, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_ncoarse, B)); A(dmalloc(c, &c->d_next_cid, B)); A(dmalloc(c, &c->d_blk_map, B * nb));
     A(dmalloc(c, &c->d_dist, B * px)); A(dmalloc(c, &c->d_queue, B * g.queue_cap)); A(dmalloc(c, &c->d_qlen, B));
@@ -63,7 +63,7 @@ int peac_alloc(pslam_ctx* c) {
 void peac_free(pslam_ctx* c) {
     cudaFree(c->d_depth); cudaFree(c->d_blk_st); cudaFree(c->d_blk_geo); cudaFree(c->d_blk_n); cudaFree(c->d_blk_valid);
     cudaFree(c->d_node_st); cudaFree(c->d_node_geo); cudaFree(c->d_node_n); cudaFree(c->d_node_rid); cudaFree(c->d_node_cid);
-    cudaFree(c->d_node_alive); cudaFree(c->d_adj); cudaFree(c->d_heap); cudaFree(c->d_nb_list); cudaFree(c->d_ds_parent); cudaFree(c->d_ds_size);
+    cudaFree(c->d_node_alive); cudaFree(c->d_adj); cudaFree(c->d_wlo); cudaFree(c->d_whi); cudaFree(c->d_nb_list); cudaFree(c->d_ds_parent); cudaFree(c->d_ds_size);
     cudaFree(c->d_coarse); cudaFree(c->d_ncoarse); cudaFree(c->d_next_cid); cudaFree(c->d_blk_map); cudaFree(c->d_dist); cudaFree(c->d_queue);
     cudaFree(c->d_qlen); cudaFree(c->d_pl_adj); cudaFree(c->d_final); cudaFree(c->d_scratch); cudaFree(c->d_labels); cudaFree(c->d_planes);
     cudaFree(c->d_nplanes); cudaFree(c->d_midx); cudaFree(c->d_moff); cudaFreeHost(c->h_depth);
@@ -80,12 +80,16 @@ int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_adj, 0, (size_t)nframes * g.nblk * g.adj_words * sizeof(uint32_t), st));
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_pl_adj, 0, (size_t)nframes * PEAC_MAX_PLANES * PEAC_PL_WORDS * sizeof(uint32_t), st));
     PSLAM_LAUNCH(c, "peac_blocks", k_peac_blocks<<<dim3((g.nblk + 127) / 128, nframes), 128, 0, st>>>(g, d_depth, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid));
-    PSLAM_LAUNCH(c, "peac_cluster", k_peac_cluster<<<nframes, 32, 0, st>>>(g, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid, c->d_node_st, c->d_node_geo,
-                 c->d_node_n, c->d_node_rid, c->d_node_cid, c->d_node_alive, c->d_adj, c->d_heap, c->d_nb_list, c->d_ds_parent, c->d_ds_size, c->d_coarse,
+    const size_t cluster_smem = (size_t)g.nblk * (sizeof(double) + sizeof(int32_t));     // heap + heap keys
+    PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem));
+    PSLAM_LAUNCH(c, "peac_cluster", k_peac_cluster<<<nframes, 32, cluster_smem, st>>>(g, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid, c->d_node_st, c->d_node_geo,
+                 c->d_node_n, c->d_node_rid, c->d_node_cid, c->d_node_alive, c->d_adj, c->d_wlo, c->d_whi, c->d_nb_list, c->d_ds_parent, c->d_ds_size, c->d_coarse,
                  c->d_ncoarse, c->d_blk_map, c->d_next_cid, c->d_status));
     PSLAM_LAUNCH(c, "peac_seed", k_peac_seed<<<nframes, 256, 0, st>>>(g, c->d_blk_map, d_labels, c->d_dist, c->d_queue, c->d_qlen));
-    PSLAM_LAUNCH(c, "peac_flood", k_peac_flood<<<nframes, 32, 0, st>>>(g, d_depth, c->d_blk_map, c->d_coarse, d_labels, c->d_dist, c->d_queue, c->d_qlen, c->d_pl_adj,
-                 c->d_status));
+    const size_t flood_smem = PEAC_MAX_PLANES * sizeof(FloodPlane) + (size_t)g.nblk;
+    PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flood_smem));
+    PSLAM_LAUNCH(c, "peac_flood", k_peac_flood<<<nframes, 32, flood_smem, st>>>(g, d_depth, c->d_blk_map, c->d_coarse, c->d_ncoarse, d_labels, c->d_dist, c->d_queue,
+                 c->d_qlen, c->d_pl_adj, c->d_status));
     PSLAM_LAUNCH(c, "peac_final", k_peac_final<<<nframes, 256, 0, st>>>(g, c->d_coarse, c->d_ncoarse, c->d_next_cid, c->d_pl_adj, c->d_ds_parent, c->d_ds_size, d_labels,
                  c->d_final, d_planes, d_nplanes, d_member_idx, d_member_off, c->d_scratch, c->d_status));
     PSLAM_CUDA(c, cudaGetLastError());

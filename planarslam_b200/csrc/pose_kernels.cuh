@@ -20,7 +20,11 @@
 
 namespace pslam {
 
-enum { PK_MONO = 0, PK_STEREO = 1, PK_LINE = 2, PK_PLANE = 3, PK_PAR = 4, PK_VER = 5 };
+enum { PK_MONO = 0, PK_STEREO = 1, PK_LINE = 2, PK_PLANE = 3, PK_PAR = 4, PK_VER = 5,
+       PK_MONO_T = 6, PK_STEREO_T = 7, PK_LINE_T = 8, PK_PLANE_T = 9 };   // translation-only variants (TranslationOptimization)
+__host__ __device__ inline bool pk_is_plane(int k) { return k == PK_PLANE || k == PK_PAR || k == PK_VER || k == PK_PLANE_T; }
+__host__ __device__ inline bool pk_is_point(int k) { return k == PK_MONO || k == PK_STEREO || k == PK_MONO_T || k == PK_STEREO_T; }
+__host__ __device__ inline bool pk_is_line(int k) { return k == PK_LINE || k == PK_LINE_T; }
 
 struct PoseEdgeDev {            // 104 bytes
     int32_t kind, idx;          // idx: index inside its family (point i / line i / plane i)
@@ -34,6 +38,7 @@ struct PoseHeaderDev {
     int32_t n_pt, n_line, n_plane, n_par, n_ver;
     int32_t flag_off[5];        // offsets of this problem's outlier flags inside the five concatenated flag arrays
     int32_t n_initial;          // nInitialCorrespondences
+    int32_t mode;               // 0 = PoseOptimization, 1 = TranslationOptimization
     double fx, fy, cx, cy, bf, plane_chi, vp_chi;
     float Tcw0[16];
 };
@@ -182,14 +187,15 @@ struct PoseCam { double fx, fy, cx, cy, bf; };
 
 // residual of one edge at pose T (computeError of the six edge classes)
 __device__ __noinline__ void pose_edge_error(const PoseEdgeDev& e, const dSE3& T, const PoseCam& K, double err[3]) {
-    if (e.kind <= PK_LINE) {
-        const dV3 p = qrot(T.q, dv(e.a[0], e.a[1], e.a[2])) + T.t;
-        if (e.kind == PK_MONO) {
+    if (e.kind <= PK_LINE || (e.kind >= PK_MONO_T && e.kind <= PK_LINE_T)) {
+        const bool tonly = e.kind >= PK_MONO_T;                                   // mapTrans: Xc + t (se3quat.h:221)
+        const dV3 p = tonly ? dv(e.a[0], e.a[1], e.a[2]) + T.t : qrot(T.q, dv(e.a[0], e.a[1], e.a[2])) + T.t;
+        if (e.kind == PK_MONO || e.kind == PK_MONO_T) {
             err[0] = e.a[3] - (p.x / p.z * K.fx + K.cx);
             err[1] = e.a[4] - (p.y / p.z * K.fy + K.cy);
             err[2] = 0;
-        } else if (e.kind == PK_STEREO) {
-            const float invz = 1.0f / (float)p.z;                             // sic: float reciprocal (types_six_dof_expmap.cpp:300)
+        } else if (e.kind == PK_STEREO || e.kind == PK_STEREO_T) {
+            const float invz = 1.0f / (float)p.z;                             // sic: float reciprocal (types_six_dof_expmap.cpp:300,369)
             const double r0 = p.x * invz * K.fx + K.cx, r1 = p.y * invz * K.fy + K.cy, r2 = r0 - K.bf * invz;
             err[0] = e.a[3] - r0; err[1] = e.a[4] - r1; err[2] = e.a[5] - r2;
         } else {
@@ -198,9 +204,9 @@ __device__ __noinline__ void pose_edge_error(const PoseEdgeDev& e, const dSE3& T
         }
         return;
     }
-    // localPlane = T * Xw  (Plane3D operator*, Plane3D.h:186-199)
-    const dM3 R = quat_to_matrix(T.q);
-    const dV3 n = mmul(R, dv(e.a[0], e.a[1], e.a[2]));
+    // localPlane = T * Xw  (Plane3D operator*, Plane3D.h:186-199), or T + Xc for the translation-only edge (:201-209)
+    dV3 n = dv(e.a[0], e.a[1], e.a[2]);
+    if (e.kind != PK_PLANE_T) n = mmul(quat_to_matrix(T.q), n);
     double lp[4] = {n.x, n.y, n.z, e.a[3] - ddot(T.t, n)};
     if (lp[3] < 0.0) { lp[0] = -lp[0]; lp[1] = -lp[1]; lp[2] = -lp[2]; lp[3] = -lp[3]; }
     plane_normalize(lp);
@@ -216,10 +222,10 @@ __device__ __noinline__ void pose_edge_error(const PoseEdgeDev& e, const dSE3& T
     }
     const dV3 nn = mmul(plane_rotation_T(base), mn);
     err[0] = azimuth(nn); err[1] = elevation(nn);
-    err[2] = (e.kind == PK_PLANE) ? ((-lp[3]) - (-e.a[7])) : 0.0;
+    err[2] = (e.kind == PK_PLANE || e.kind == PK_PLANE_T) ? ((-lp[3]) - (-e.a[7])) : 0.0;
 }
 
-__device__ __forceinline__ int pose_edge_dim(int kind) { return kind == PK_MONO || kind == PK_PAR || kind == PK_VER ? 2 : 3; }
+__device__ __forceinline__ int pose_edge_dim(int kind) { return kind == PK_MONO || kind == PK_MONO_T || kind == PK_PAR || kind == PK_VER ? 2 : 3; }
 
 __device__ __noinline__ void pose_edge_jacobian(const PoseEdgeDev& e, const dSE3& T, const PoseCam& K, double J[3][6]) {
 #pragma unroll
@@ -249,6 +255,19 @@ __device__ __noinline__ void pose_edge_jacobian(const PoseEdgeDev& e, const dSE3
         }
         return;
     }
+    if (e.kind >= PK_MONO_T && e.kind <= PK_LINE_T) {          // rotation columns are zero (types_six_dof_expmap.cpp:404-485, EdgeLine.h:283-310)
+        const dV3 p = dv(e.a[0], e.a[1], e.a[2]) + T.t;
+        const double x = p.x, y = p.y, invz = 1.0 / p.z, invz_2 = invz * invz;
+        if (e.kind == PK_LINE_T) {
+            const double lx = e.a[3], ly = e.a[4];
+            J[0][3] = K.fx * lx * invz; J[0][4] = K.fy * ly * invz; J[0][5] = -(K.fx * lx * x + K.fy * ly * y) * invz_2;
+            return;
+        }
+        J[0][3] = -invz * K.fx; J[0][5] = x * invz_2 * K.fx;
+        J[1][4] = -invz * K.fy; J[1][5] = y * invz_2 * K.fy;
+        if (e.kind == PK_STEREO_T) { J[2][3] = J[0][3]; J[2][5] = J[0][5] - K.bf * invz_2; }
+        return;
+    }
     // numeric central differences with delta = 1e-9 like BaseUnaryEdge::linearizeOplus (the reference does this for
     // every plane edge; an analytic Jacobian would change the iterates)
     const double delta = 1e-9, scalar = 1.0 / (2 * delta);
@@ -261,6 +280,8 @@ __device__ __noinline__ void pose_edge_jacobian(const PoseEdgeDev& e, const dSE3
         pose_edge_error(e, se3_mul(se3_exp(add), T), K, e2);
         for (int i = 0; i < dim; ++i) J[i][d] = scalar * (e1[i] - e2[i]);
     }
+    if (e.kind == PK_PLANE_T)                                  // EdgePlaneOnlyTranslation zeroes the rotation columns (EdgePlane.h:292-308)
+        for (int i = 0; i < 3; ++i) { J[i][0] = 0; J[i][1] = 0; J[i][2] = 0; }
 }
 
 __device__ __forceinline__ void huber(double e2, double delta, double& rho0, double& rho1) {
@@ -369,7 +390,7 @@ __global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const PoseHe
     for (int i = tid; i < ne; i += POSE_THREADS) {
         level[i] = 0;
         double e3[3] = {0, 0, 0};
-        if (E[i].kind >= PK_PLANE) pose_edge_error(E[i], T0, K, e3);      // computeError() while the graph is built (:896,:935,:975)
+        if (pk_is_plane(E[i].kind)) pose_edge_error(E[i], T0, K, e3);      // computeError() while the graph is built (:896,:935,:975,:3300)
         err[3 * i] = e3[0]; err[3 * i + 1] = e3[1]; err[3 * i + 2] = e3[2];
     }
     __syncthreads();
@@ -487,35 +508,39 @@ __global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const PoseHe
         double nb[1] = {0};
         for (int i = tid; i < ne; i += POSE_THREADS) {
             const PoseEdgeDev& e = E[i];
-            if (e.kind <= PK_STEREO) {
+            if (pk_is_point(e.kind)) {
                 uint8_t& f = fl[0][e.idx];
                 if (f) { double e3[3]; pose_edge_error(e, T, K, e3); err[3 * i] = e3[0]; err[3 * i + 1] = e3[1]; err[3 * i + 2] = e3[2]; }
                 const int dim = pose_edge_dim(e.kind);
                 double c = 0;
                 for (int r = 0; r < dim; ++r) c += err[3 * i + r] * e.info[r] * err[3 * i + r];
                 const float cf = (float)c;
-                if (cf > (e.kind == PK_MONO ? 5.991f : 7.815f)) { f = 1; level[i] = 1; nb[0] += 1; } else { f = 0; level[i] = 0; }
-            } else if (e.kind == PK_LINE) {
+                if (cf > ((e.kind == PK_MONO || e.kind == PK_MONO_T) ? 5.991f : 7.815f)) { f = 1; level[i] = 1; nb[0] += 1; } else { f = 0; level[i] = 0; }
+            } else if (pk_is_line(e.kind)) {
                 // start (even) and end (odd) edges of a line are adjacent; the thread owning the start edge classifies both
                 const int first = hd.n_pt;               // first line edge
                 if (((i - first) & 1) == 0) {
-                    double ea[3], eb[3];
-                    pose_edge_error(E[i], T, K, ea); pose_edge_error(E[i + 1], T, K, eb);
-                    err[3 * i] = ea[0]; err[3 * i + 1] = 0; err[3 * i + 2] = 0;
-                    err[3 * (i + 1)] = eb[0]; err[3 * (i + 1) + 1] = 0; err[3 * (i + 1) + 2] = 0;
-                    const float cs = (float)(ea[0] * ea[0]), ce = (float)(eb[0] * eb[0]);
                     uint8_t& f = fl[1][e.idx];
-                    if (cs > 2 * 5.991f || ce > 2 * 5.991f) { f = 1; level[i] = 1; level[i + 1] = 1; nb[0] += 1; }
+                    // PoseOptimization recomputes both endpoint errors unconditionally (:1087-1088); TranslationOptimization only
+                    // for lines currently flagged as outliers (:3598-3601) and keeps a separate nLineBad
+                    if (hd.mode == 0 || f) {
+                        double ea[3], eb[3];
+                        pose_edge_error(E[i], T, K, ea); pose_edge_error(E[i + 1], T, K, eb);
+                        err[3 * i] = ea[0]; err[3 * i + 1] = 0; err[3 * i + 2] = 0;
+                        err[3 * (i + 1)] = eb[0]; err[3 * (i + 1) + 1] = 0; err[3 * (i + 1) + 2] = 0;
+                    }
+                    const float cs = (float)(err[3 * i] * err[3 * i]), ce = (float)(err[3 * (i + 1)] * err[3 * (i + 1)]);
+                    if (cs > 2 * 5.991f || ce > 2 * 5.991f) { f = 1; level[i] = 1; level[i + 1] = 1; if (hd.mode == 0) nb[0] += 1; }
                     else { f = 0; level[i] = 0; level[i + 1] = 0; }
                 }
             } else {
-                uint8_t& f = fl[e.kind - PK_PLANE + 2][e.idx];
+                uint8_t& f = fl[e.kind == PK_PLANE_T ? 2 : e.kind - PK_PLANE + 2][e.idx];
                 if (f) { double e3[3]; pose_edge_error(e, T, K, e3); err[3 * i] = e3[0]; err[3 * i + 1] = e3[1]; err[3 * i + 2] = e3[2]; }
                 const int dim = pose_edge_dim(e.kind);
                 double c = 0;
                 for (int r = 0; r < dim; ++r) c += err[3 * i + r] * e.info[r] * err[3 * i + r];
                 const float cf = (float)c;
-                const double th = e.kind == PK_PLANE ? hd.plane_chi : hd.vp_chi;
+                const double th = (e.kind == PK_PLANE || e.kind == PK_PLANE_T) ? hd.plane_chi : hd.vp_chi;
                 if ((double)cf > th) { f = 1; level[i] = 1; nb[0] += 1; } else { f = 0; level[i] = 0; }
             }
         }

@@ -44,7 +44,7 @@ static int grow(pslam_ctx* c, T** p, size_t* cap, size_t need) {
     return rc;
 }
 
-int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const float* Tcw0) {
+int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const float* Tcw0, int mode) {
     if (!c->pose) c->pose = new PoseBuffers();
     PoseBuffers& B = *c->pose;
     B.h_hdr.assign(n, PoseHeaderDev());
@@ -61,7 +61,13 @@ int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const
         H.n_pt = P.n_points; H.n_line = P.n_lines; H.n_plane = P.n_planes; H.n_par = P.n_par; H.n_ver = P.n_ver;
         for (int k = 0; k < 5; ++k) H.flag_off[k] = off[k];
         off[0] += P.n_points; off[1] += P.n_lines; off[2] += P.n_planes; off[3] += P.n_par; off[4] += P.n_ver;
-        H.n_initial = P.n_points + P.n_lines + P.n_planes + P.n_par + P.n_ver;
+        H.n_initial = mode == 0 ? P.n_points + P.n_lines + P.n_planes + P.n_par + P.n_ver : P.n_points;   // :3137-3139, :3245-3246
+        H.mode = mode;
+        const float* T0 = Tcw0 + 16 * p;
+        // R_cw * X as cv::Mat(CV_32F) products do it: double accumulation, float result (TranslationOptimization :3019,:3066,:3161)
+        auto rot_f = [&](double x, double y, double z, int row) -> double {
+            return (double)(float)((double)T0[row * 4 + 0] * (double)(float)x + (double)T0[row * 4 + 1] * (double)(float)y + (double)T0[row * 4 + 2] * (double)(float)z);
+        };
         H.fx = P.fx; H.fy = P.fy; H.cx = P.cx; H.cy = P.cy; H.bf = P.bf; H.plane_chi = P.plane_chi; H.vp_chi = P.vp_chi;
         std::memcpy(H.Tcw0, Tcw0 + 16 * p, sizeof H.Tcw0);
         const float deltaMono = std::sqrt(5.991), deltaStereo = std::sqrt(7.815);       // const float in the reference (:583-584)
@@ -72,8 +78,11 @@ int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const
             PoseEdgeDev e;
             std::memset(&e, 0, sizeof e);
             const bool mono = P.obs[3 * i + 2] < 0;
-            e.kind = mono ? PK_MONO : PK_STEREO; e.idx = i;
-            for (int k = 0; k < 3; ++k) { e.a[k] = P.Xw[3 * i + k]; e.a[3 + k] = P.obs[3 * i + k]; e.info[k] = P.inv_sigma2[i]; }
+            e.kind = mode == 0 ? (mono ? PK_MONO : PK_STEREO) : (mono ? PK_MONO_T : PK_STEREO_T); e.idx = i;
+            for (int k = 0; k < 3; ++k) {
+                e.a[k] = mode == 0 ? (double)P.Xw[3 * i + k] : rot_f(P.Xw[3 * i], P.Xw[3 * i + 1], P.Xw[3 * i + 2], k);
+                e.a[3 + k] = P.obs[3 * i + k]; e.info[k] = P.inv_sigma2[i];
+            }
             e.delta = mono ? deltaMono : deltaStereo;
             B.h_edges.push_back(e);
         }
@@ -81,8 +90,9 @@ int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const
             for (int s = 0; s < 2; ++s) {
                 PoseEdgeDev e;
                 std::memset(&e, 0, sizeof e);
-                e.kind = PK_LINE; e.idx = i;
-                for (int k = 0; k < 3; ++k) { e.a[k] = P.line_Xw[6 * i + 3 * s + k]; e.a[3 + k] = P.line_obs[3 * i + k]; e.info[k] = 1.0; }
+                e.kind = mode == 0 ? PK_LINE : PK_LINE_T; e.idx = i;
+                const double* X = P.line_Xw + 6 * i + 3 * s;
+                for (int k = 0; k < 3; ++k) { e.a[k] = mode == 0 ? X[k] : rot_f(X[0], X[1], X[2], k); e.a[3 + k] = P.line_obs[3 * i + k]; e.info[k] = 1.0; }
                 e.delta = deltaStereo;
                 B.h_edges.push_back(e);
             }
@@ -96,9 +106,19 @@ int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const
                 B.h_edges.push_back(e);
             }
         };
-        add_planes(PK_PLANE, P.n_planes, P.plane_meas, P.plane_map, angleInfo, angleInfo, disInfo, deltaPlane);
-        add_planes(PK_PAR, P.n_par, P.par_meas, P.par_map, parInfo, parInfo, 0, deltaVP);
-        add_planes(PK_VER, P.n_ver, P.ver_meas, P.ver_map, verInfo, verInfo, 0, deltaVP);
+        if (mode == 0) {
+            add_planes(PK_PLANE, P.n_planes, P.plane_meas, P.plane_map, angleInfo, angleInfo, disInfo, deltaPlane);
+            add_planes(PK_PAR, P.n_par, P.par_meas, P.par_map, parInfo, parInfo, 0, deltaVP);
+            add_planes(PK_VER, P.n_ver, P.ver_meas, P.ver_map, verInfo, verInfo, 0, deltaVP);
+        } else if (P.n_points >= 3) {          // the reference returns before adding planes when < 3 points are matched (:3198-3200)
+            const size_t first = B.h_edges.size();
+            add_planes(PK_PLANE_T, P.n_planes, P.plane_meas, P.plane_map, angleInfo, angleInfo, disInfo, deltaPlane);
+            for (size_t k = first; k < B.h_edges.size(); ++k) {    // Xw.rotateNormal(toMatrix3d(R_cw)): widened float rotation, not renormalised
+                double* a = B.h_edges[k].a;
+                const double nrm[3] = {a[0], a[1], a[2]};
+                for (int r = 0; r < 3; ++r) a[r] = (double)T0[r * 4 + 0] * nrm[0] + (double)T0[r * 4 + 1] * nrm[1] + (double)T0[r * 4 + 2] * nrm[2];
+            }
+        }
         H.n_edges = (int)B.h_edges.size() - H.edge_off;
     }
     B.n_prob = n;
@@ -166,12 +186,14 @@ using namespace pslam;
 
 extern "C" {
 
-int pslam_pose_pack(pslam_ctx* c, const pslam_pose_problem* probs, int n, const float* Tcw0) {
+static int pack_mode(pslam_ctx* c, const pslam_pose_problem* probs, int n, const float* Tcw0, int mode) {
     if (!c) return PSLAM_E_INVALID;
     if (!probs || !Tcw0 || n < 1) return set_error(c, PSLAM_E_INVALID, "null problems or n < 1");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
-    return pose_pack_upload(c, probs, n, Tcw0);
+    return pose_pack_upload(c, probs, n, Tcw0, mode);
 }
+int pslam_pose_pack(pslam_ctx* c, const pslam_pose_problem* probs, int n, const float* Tcw0) { return pack_mode(c, probs, n, Tcw0, 0); }
+int pslam_translation_pack(pslam_ctx* c, const pslam_pose_problem* probs, int n, const float* Tcw0) { return pack_mode(c, probs, n, Tcw0, 1); }
 
 int pslam_pose_run_packed(pslam_ctx* c) {
     if (!c) return PSLAM_E_INVALID;
@@ -198,6 +220,20 @@ int pslam_pose_optimization(pslam_ctx* c, const pslam_pose_problem* prob, float*
                             uint8_t* o_par, uint8_t* o_ver) {
     int32_t n_inl = 0;
     const int rc = pslam_pose_optimization_batch(c, prob, 1, Tcw_io, o_pt, o_line, o_plane, o_par, o_ver, &n_inl);
+    return rc != PSLAM_OK ? rc : n_inl;
+}
+
+int pslam_translation_optimization_batch(pslam_ctx* c, const pslam_pose_problem* probs, int n, float* Tcw_io, uint8_t* o_pt, uint8_t* o_line,
+                                         uint8_t* o_plane, int32_t* n_inliers) {
+    int rc = pslam_translation_pack(c, probs, n, Tcw_io);
+    if (rc != PSLAM_OK) return rc;
+    if ((rc = pose_run_packed(c)) != PSLAM_OK) return rc;
+    return pose_fetch(c, Tcw_io, nullptr, o_pt, o_line, o_plane, nullptr, nullptr, n_inliers, nullptr, nullptr);
+}
+
+int pslam_translation_optimization(pslam_ctx* c, const pslam_pose_problem* prob, float* Tcw_io, uint8_t* o_pt, uint8_t* o_line, uint8_t* o_plane) {
+    int32_t n_inl = 0;
+    const int rc = pslam_translation_optimization_batch(c, prob, 1, Tcw_io, o_pt, o_line, o_plane, &n_inl);
     return rc != PSLAM_OK ? rc : n_inl;
 }
 

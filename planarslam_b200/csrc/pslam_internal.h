@@ -103,7 +103,7 @@ struct pslam_ctx {
     uint16_t* d_depth = nullptr;                 // staging copy of host depth
     double* d_blk_st = nullptr; double* d_blk_geo = nullptr; int32_t* d_blk_n = nullptr; uint8_t* d_blk_valid = nullptr;
     double* d_node_st = nullptr; double* d_node_geo = nullptr; int32_t* d_node_n = nullptr; int32_t* d_node_rid = nullptr;
-    int32_t* d_node_cid = nullptr; uint8_t* d_node_alive = nullptr; uint32_t* d_adj = nullptr; int32_t* d_heap = nullptr;
+    int32_t* d_node_cid = nullptr; uint8_t* d_node_alive = nullptr; uint32_t* d_adj = nullptr; int16_t* d_wlo = nullptr; int16_t* d_whi = nullptr;
     int32_t* d_nb_list = nullptr; int32_t* d_ds_parent = nullptr; int32_t* d_ds_size = nullptr;
     pslam::PeacPlaneRec* d_coarse = nullptr; int32_t* d_ncoarse = nullptr; int32_t* d_next_cid = nullptr; int32_t* d_blk_map = nullptr;
     float* d_dist = nullptr; uint32_t* d_queue = nullptr; int32_t* d_qlen = nullptr; uint32_t* d_pl_adj = nullptr;

@@ -32,12 +32,13 @@ class Optimizer:
     def __init__(self, ctx: Context | None = None, device: int = 0):
         self.ctx = ctx or Context(640, 480, 1, device)
 
-    def pack(self, problems: list[dict]):
+    def pack(self, problems: list[dict], translation_only: bool = False):
         """Pack + upload problems once (device-resident form used by bench.py)."""
         self._keep = problems
         arr = (PoseProblem * len(problems))(*[_to_struct(p) for p in problems])
         T0 = np.ascontiguousarray(np.stack([p["Tcw0"] for p in problems]), np.float32)
-        self.ctx.check(self.ctx.L.pslam_pose_pack(self.ctx.h, arr, len(problems), T0.ctypes.data))
+        fn = self.ctx.L.pslam_translation_pack if translation_only else self.ctx.L.pslam_pose_pack
+        self.ctx.check(fn(self.ctx.h, arr, len(problems), T0.ctypes.data))
         self._counts = [(len(p["Xw"]), len(p["line_Xw"]), len(p["plane_meas"]), len(p["par_meas"]), len(p["ver_meas"])) for p in problems]
 
     def run_packed(self):
@@ -63,6 +64,18 @@ class Optimizer:
 
     def PoseOptimizationBatch(self, problems: list[dict]):
         self.pack(problems)
+        self.run_packed()
+        return self.fetch()
+
+    # static int TranslationOptimization(Frame*)
+    def TranslationOptimization(self, problem: dict):
+        self.pack([problem], translation_only=True)
+        self.run_packed()
+        r = self.fetch()[0]
+        return r["n_inliers"], r
+
+    def TranslationOptimizationBatch(self, problems: list[dict]):
+        self.pack(problems, translation_only=True)
         self.run_packed()
         return self.fetch()
 

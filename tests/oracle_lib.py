@@ -169,17 +169,23 @@ def pose_problem_struct(p: dict, cls=_PoseProblemC):
     return s
 
 
-def pose_optimization(p: dict):
-    """Oracle PoseOptimization. Returns dict(Tcw float 4x4, Tcw_d, n_inliers, outlier flags, trace)."""
+def translation_optimization(p: dict):
+    return pose_optimization(p, translation_only=True)
+
+
+def pose_optimization(p: dict, translation_only: bool = False):
+    """Oracle PoseOptimization / TranslationOptimization. Returns dict(Tcw float 4x4, Tcw_d, n_inliers, outlier flags, trace)."""
     L = lib()
     L.orc_pose_optimization.argtypes = [C.c_void_p] * 11
+    L.orc_translation_optimization.argtypes = [C.c_void_p] * 11
     s = pose_problem_struct(p)
     T0 = np.ascontiguousarray(p["Tcw0"], np.float32)
     T = np.zeros((4, 4), np.float32)
     Td = np.zeros((4, 4))
     o = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes, s.n_par, s.n_ver)]
     ti, td = np.zeros((4, 3), np.int32), np.zeros((4, 2))
-    n = L.orc_pose_optimization(C.byref(s), T0.ctypes.data, T.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], ti.ctypes.data,
+    fn = L.orc_translation_optimization if translation_only else L.orc_pose_optimization
+    n = fn(C.byref(s), T0.ctypes.data, T.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], ti.ctypes.data,
                                 td.ctypes.data)
     return dict(Tcw=T, Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes],
                 outlier_par=o[3][:s.n_par], outlier_ver=o[4][:s.n_ver], trace_i=ti, trace_d=td)
