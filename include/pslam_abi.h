@@ -162,6 +162,31 @@ int pslam_hamming_knn2_batch_dev(pslam_ctx* ctx, const uint8_t* d_q, const int32
                                  const int32_t* d_nt, int capt, int nframes, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_good,
                                  int32_t* d_ngood);
 
+/* ---- Projection-guided search ---------------------------------------------------------------------
+ * Replaces  int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th)        src/ORBmatcher.cc:46-130
+ *           (together with the Frame::isInFrustum pass of Tracking::SearchLocalPoints, src/Tracking.cc:2286-2329, src/Frame.cc:312-367)
+ *           int ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, float th, bool bMono)              src/ORBmatcher.cc:1396-1535
+ * The Frame / MapPoint objects are passed as plain-array views gathered by the caller under the map mutex:
+ *   pslam_frame_view   N, mvKeysUn, mvuRight, mDescriptors, mTcw, fx..mbf, mnMinX..mnMaxY, mvScaleFactors, mfLogScaleFactor
+ *   pslam_map_points   GetWorldPos, GetNormal, mfMaxDistance, mfMinDistance, GetDescriptor, skip (= mnLastFrameSeen == frame id or
+ *                      isBad()), has_obs (= Observations() > 0)
+ *   pslam_last_frame   mvKeys (octave, angle), index of mvpMapPoints[i] in the map arrays (-1: none), mvbOutlier, mTcw
+ * matches_io[i] is the index (into the map arrays) held by F.mvpMapPoints[i], -1 for none; it is updated in place with the
+ * reference's greedy order-dependent assignment.  Both calls return nmatches (>= 0) or a negative pslam_status. */
+typedef struct pslam_frame_view {
+    int32_t n; const pslam_keypoint* keys_un; const float* u_right; const uint8_t* desc; float Tcw[16];
+    float fx, fy, cx, cy, bf, min_x, max_x, min_y, max_y; int32_t n_levels; const float* scale_factors; float log_scale_factor;
+} pslam_frame_view;
+typedef struct pslam_map_points {
+    int32_t n; const float *pos, *normal, *max_distance, *min_distance; const uint8_t *desc, *skip, *has_obs;
+} pslam_map_points;
+typedef struct pslam_last_frame { int32_t n; const pslam_keypoint* keys; const int32_t* map_point; const uint8_t* outlier; float Tcw[16]; } pslam_last_frame;
+
+int pslam_search_by_projection_map(pslam_ctx* ctx, const pslam_frame_view* frame, const pslam_map_points* map, float th, float nnratio,
+                                   int32_t* matches_io, uint8_t* in_view /* [map.n] mbTrackInView, may be NULL */);
+int pslam_search_by_projection_last(pslam_ctx* ctx, const pslam_frame_view* cur, const pslam_last_frame* last, const pslam_map_points* map,
+                                    float th, int mono, int check_orientation, int32_t* matches_io);
+
 /* ---- Pose optimisation ---------------------------------------------------------------------------
  * Replaces  static int Optimizer::PoseOptimization(Frame* pFrame)     include/Optimizer.h:38, src/Optimizer.cc:550-1275.
  * A pslam_pose_problem carries exactly what that function reads from the Frame and the matched map objects:

@@ -42,6 +42,22 @@ class PoseProblem(C.Structure):
                 ("plane_chi", C.c_double), ("vp_chi", C.c_double)]
 
 
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("u_right", C.c_void_p), ("desc", C.c_void_p), ("Tcw", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("n_levels", C.c_int32), ("scale_factors", C.c_void_p), ("log_scale_factor", C.c_float)]
+
+
+class MapPoints(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos", C.c_void_p), ("normal", C.c_void_p), ("max_distance", C.c_void_p), ("min_distance", C.c_void_p),
+                ("desc", C.c_void_p), ("skip", C.c_void_p), ("has_obs", C.c_void_p)]
+
+
+class LastFrame(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("map_point", C.c_void_p), ("outlier", C.c_void_p), ("Tcw", C.c_float * 16)]
+
+
 class PslamError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"pslam error {code}: {msg}")
@@ -86,6 +102,8 @@ def lib() -> C.CDLL:
     L.pslam_peac_debug_coarse.argtypes = [vp, i32, vp, i32p]
     L.pslam_hamming_knn2.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, i32p]
     L.pslam_hamming_knn2_batch_dev.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.pslam_search_by_projection_map.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp, vp]
+    L.pslam_search_by_projection_last.argtypes = [vp, vp, vp, vp, C.c_float, i32, i32, vp]
     L.pslam_pose_optimization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.pslam_pose_optimization_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.pslam_pose_pack.argtypes = [vp, vp, i32, vp]

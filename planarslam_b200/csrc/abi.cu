@@ -77,6 +77,7 @@ void pslam_destroy(pslam_ctx* c) {
     orb_free(c);
     peac_free(c);
     pose_free(c);
+    search_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

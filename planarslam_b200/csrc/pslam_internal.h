@@ -60,6 +60,7 @@ struct PeacGeom {
 
 struct PeacPlaneRec;
 struct PoseBuffers;
+struct SearchBuffers;
 
 }  // namespace pslam
 
@@ -111,6 +112,7 @@ struct pslam_ctx {
     int32_t* d_labels = nullptr; pslam_plane* d_planes = nullptr; int32_t* d_nplanes = nullptr; int32_t* d_midx = nullptr; int32_t* d_moff = nullptr;
     uint16_t* h_depth = nullptr;                 // pinned
     pslam::PoseBuffers* pose = nullptr;          // pose-optimisation staging (pose_pipeline.cu)
+    pslam::SearchBuffers* search = nullptr;      // projection-search staging (search_kernels.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
     int32_t* h_status = nullptr;
@@ -127,6 +129,7 @@ int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint
                 int32_t* d_n);
 // pose optimisation (pose_pipeline.cu)
 void pose_free(pslam_ctx* c);
+void search_free(pslam_ctx* c);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

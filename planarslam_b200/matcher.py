@@ -6,7 +6,39 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import Context
+from ._lib import Context, FrameView, LastFrame, MapPoints
+
+
+def _frame_view(fv: dict) -> FrameView:
+    s = FrameView()
+    s._keep = fv
+    s.n = fv["n"]
+    for k in ("keys_un", "u_right", "desc", "scale_factors"):
+        setattr(s, k, fv[k].ctypes.data)
+    s.Tcw = (C.c_float * 16)(*np.asarray(fv["Tcw"], np.float32).ravel().tolist())
+    for k in ("fx", "fy", "cx", "cy", "bf", "min_x", "max_x", "min_y", "max_y", "log_scale_factor"):
+        setattr(s, k, fv[k])
+    s.n_levels = fv["n_levels"]
+    return s
+
+
+def _map_points(m: dict) -> MapPoints:
+    s = MapPoints()
+    s._keep = m
+    s.n = m["n"]
+    for k in ("pos", "normal", "max_distance", "min_distance", "desc", "skip", "has_obs"):
+        setattr(s, k, m[k].ctypes.data)
+    return s
+
+
+def _last_frame(lf: dict) -> LastFrame:
+    s = LastFrame()
+    s._keep = lf
+    s.n = lf["n"]
+    for k in ("keys", "map_point", "outlier"):
+        setattr(s, k, lf[k].ctypes.data)
+    s.Tcw = (C.c_float * 16)(*np.asarray(lf["Tcw"], np.float32).ravel().tolist())
+    return s
 
 
 class ORBmatcher:
@@ -24,6 +56,25 @@ class ORBmatcher:
         self.ctx.check(self.ctx.L.pslam_hamming_knn2(self.ctx.h, q.ctypes.data if nq else None, nq, t.ctypes.data if nt else None, nt,
                                                      idx.ctypes.data, dist.ctypes.data, good.ctypes.data if gate else None, C.byref(ng)))
         return idx[:nq], dist[:nq], good[:ng.value]
+
+    # int SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, const float th)
+    def SearchByProjection(self, frame_view: dict, map_points: dict, th: float = 3.0, matches=None):
+        m = np.full(frame_view["n"], -1, np.int32) if matches is None else np.ascontiguousarray(matches, np.int32).copy()
+        in_view = np.zeros(max(map_points["n"], 1), np.uint8)
+        n = self.ctx.L.pslam_search_by_projection_map(self.ctx.h, C.byref(_frame_view(frame_view)), C.byref(_map_points(map_points)), th,
+                                                      self.mfNNratio, m.ctypes.data, in_view.ctypes.data)
+        if n < 0:
+            self.ctx.check(n)
+        return n, m, in_view[:map_points["n"]]
+
+    # int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono)
+    def SearchByProjectionLast(self, cur_view: dict, last: dict, map_points: dict, th: float, bMono: bool = False, matches=None):
+        m = np.full(cur_view["n"], -1, np.int32) if matches is None else np.ascontiguousarray(matches, np.int32).copy()
+        n = self.ctx.L.pslam_search_by_projection_last(self.ctx.h, C.byref(_frame_view(cur_view)), C.byref(_last_frame(last)),
+                                                       C.byref(_map_points(map_points)), th, int(bMono), int(self.mbCheckOrientation), m.ctypes.data)
+        if n < 0:
+            self.ctx.check(n)
+        return n, m
 
     @staticmethod
     def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:

@@ -189,3 +189,70 @@ def pose_optimization(p: dict, translation_only: bool = False):
                                 td.ctypes.data)
     return dict(Tcw=T, Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes],
                 outlier_par=o[3][:s.n_par], outlier_ver=o[4][:s.n_ver], trace_i=ti, trace_d=td)
+
+
+class _FrameViewC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys_un", C.c_void_p), ("u_right", C.c_void_p), ("desc", C.c_void_p), ("Tcw", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("n_levels", C.c_int32), ("scale_factors", C.c_void_p), ("log_scale_factor", C.c_float)]
+
+
+class _MapPointsC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("pos", C.c_void_p), ("normal", C.c_void_p), ("max_distance", C.c_void_p), ("min_distance", C.c_void_p),
+                ("desc", C.c_void_p), ("skip", C.c_void_p), ("has_obs", C.c_void_p)]
+
+
+class _LastFrameC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("keys", C.c_void_p), ("map_point", C.c_void_p), ("outlier", C.c_void_p), ("Tcw", C.c_float * 16)]
+
+
+def frame_view_struct(fv: dict, cls=_FrameViewC):
+    s = cls()
+    s._keep = fv
+    s.n = fv["n"]
+    for k in ("keys_un", "u_right", "desc", "scale_factors"):
+        setattr(s, k, fv[k].ctypes.data)
+    s.Tcw = (C.c_float * 16)(*np.asarray(fv["Tcw"], np.float32).ravel().tolist())
+    for k in ("fx", "fy", "cx", "cy", "bf", "min_x", "max_x", "min_y", "max_y", "log_scale_factor"):
+        setattr(s, k, fv[k])
+    s.n_levels = fv["n_levels"]
+    return s
+
+
+def map_points_struct(m: dict, cls=_MapPointsC):
+    s = cls()
+    s._keep = m
+    s.n = m["n"]
+    for k in ("pos", "normal", "max_distance", "min_distance", "desc", "skip", "has_obs"):
+        setattr(s, k, m[k].ctypes.data)
+    return s
+
+
+def last_frame_struct(lf: dict, cls=_LastFrameC):
+    s = cls()
+    s._keep = lf
+    s.n = lf["n"]
+    for k in ("keys", "map_point", "outlier"):
+        setattr(s, k, lf[k].ctypes.data)
+    s.Tcw = (C.c_float * 16)(*np.asarray(lf["Tcw"], np.float32).ravel().tolist())
+    return s
+
+
+def search_by_projection_map(fv: dict, m: dict, th: float, nnratio: float, matches0: np.ndarray):
+    L = lib()
+    L.orc_search_by_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    matches = np.ascontiguousarray(matches0, np.int32).copy()
+    in_view = np.zeros(max(m["n"], 1), np.uint8)
+    n = L.orc_search_by_projection_map(C.byref(frame_view_struct(fv)), C.byref(map_points_struct(m)), th, nnratio, matches.ctypes.data,
+                                       in_view.ctypes.data)
+    return n, matches, in_view[:m["n"]]
+
+
+def search_by_projection_last(fv: dict, lf: dict, m: dict, th: float, mono: bool, check_ori: bool, matches0: np.ndarray):
+    L = lib()
+    L.orc_search_by_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    matches = np.ascontiguousarray(matches0, np.int32).copy()
+    n = L.orc_search_by_projection_last(C.byref(frame_view_struct(fv)), C.byref(last_frame_struct(lf)), C.byref(map_points_struct(m)), th,
+                                        int(mono), int(check_ori), matches.ctypes.data)
+    return n, matches
