@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = one pass of the hot path over one batch of synthetic 640x480 RGB-D frames (seeded "room corner"
+A "step" = one pass of the hot path over one batch (1024 by default) of synthetic 640x480 RGB-D frames (seeded "room corner"
 sequence, planarslam_b200/synth.py).  Frames are independent units, so ranks shard them with no data-path
 collective (weak scaling: every rank processes FRAMES_PER_STEP frames per step).
 
@@ -33,8 +33,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H = 640, 480
-SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "256"))     # frames per library call (context max_batch)
-SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "1"))         # library calls per step; 256 frames = 236 MB of gray+depth input > 126 MB L2
+SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "1024"))    # frames per library call (context max_batch); throughput of the one-warp-per-frame kernels scales with frames in flight
+SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "1"))         # library calls per step; 1024 frames = 944 MB of gray+depth input >> 126 MB L2
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
 DISTINCT_FRAMES = 16      # rendered once (CPU, ~0.4 s each) and tiled with a per-copy intensity offset
 

@@ -187,6 +187,16 @@ int pslam_search_by_projection_map(pslam_ctx* ctx, const pslam_frame_view* frame
 int pslam_search_by_projection_last(pslam_ctx* ctx, const pslam_frame_view* cur, const pslam_last_frame* last, const pslam_map_points* map,
                                     float th, int mono, int check_orientation, int32_t* matches_io);
 
+/* ---- Plane association -------------------------------------------------------------------------
+ * Replaces  int PlaneMatcher::SearchMapByCoefficients(Frame& pF, const vector<MapPlane*>& vpMapPlanes)   src/PlaneMatcher.cpp:10-67
+ * (with Frame::ComputePlaneWorldCoeff, src/Frame.cc:815-820).  frame_coef: mvPlaneCoefficients [n_frame][4]; map_coef: GetWorldPos()
+ * [n_map][4]; map_bad: isBad(); pts / pts_off: the map planes' mvPlanePoints concatenated ([pts_off[n_map]][3], plane j owns
+ * [pts_off[j], pts_off[j+1])).  Outputs per frame plane: index of the associated map plane (mvpMapPlanes), of the most
+ * perpendicular one (mvpVerticalPlanes) and of the most parallel one (mvpParallelPlanes), -1 for none.  Returns nmatches. */
+int pslam_plane_match(pslam_ctx* ctx, const float* Tcw, int n_frame, const float* frame_coef, int n_map, const float* map_coef,
+                      const uint8_t* map_bad, const int32_t* pts_off, const float* pts, float dTh, float aTh, float verTh, float parTh,
+                      int32_t* match, int32_t* ver, int32_t* par);
+
 /* ---- Pose optimisation ---------------------------------------------------------------------------
  * Replaces  static int Optimizer::PoseOptimization(Frame* pFrame)     include/Optimizer.h:38, src/Optimizer.cc:550-1275.
  * A pslam_pose_problem carries exactly what that function reads from the Frame and the matched map objects:

@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
     L.pslam_peac_debug_coarse.argtypes = [vp, i32, vp, i32p]
     L.pslam_hamming_knn2.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, i32p]
     L.pslam_hamming_knn2_batch_dev.argtypes = [vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.pslam_plane_match.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float, vp, vp, vp]
     L.pslam_search_by_projection_map.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp, vp]
     L.pslam_search_by_projection_last.argtypes = [vp, vp, vp, vp, C.c_float, i32, i32, vp]
     L.pslam_pose_optimization.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

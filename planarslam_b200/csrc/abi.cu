@@ -59,8 +59,8 @@ int pslam_create(const pslam_config* cfg, pslam_ctx** out) {
     if (rc == PSLAM_OK) rc = peac_build_geometry(c);
     if (rc == PSLAM_OK) rc = check_cuda(c, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     c->stream = c->own_stream;
-    if (rc == PSLAM_OK) rc = orb_alloc(c);
-    if (rc == PSLAM_OK) rc = peac_alloc(c);
+    if (rc == PSLAM_OK) rc = check_cuda(c, cudaMalloc((void**)&c->d_status, (size_t)cfg->max_batch * sizeof(int32_t)), "cudaMalloc");
+    if (rc == PSLAM_OK) rc = check_cuda(c, cudaMallocHost((void**)&c->h_status, (size_t)cfg->max_batch * sizeof(int32_t)), "cudaMallocHost");
     if (rc != PSLAM_OK) {
         std::fprintf(stderr, "pslam_create failed: %s\n", c->err.c_str());
         pslam_destroy(c);
@@ -74,8 +74,9 @@ void pslam_destroy(pslam_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    orb_free(c);
-    peac_free(c);
+    if (c->orb_ready) orb_free(c);
+    if (c->peac_ready) peac_free(c);
+    cudaFree(c->d_status); cudaFreeHost(c->h_status);
     pose_free(c);
     search_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -151,6 +152,7 @@ int pslam_orb_extract_batch(pslam_ctx* c, const uint8_t* gray, int nframes, psla
     if (!gray || !kps || !desc || !n || cap < 1) return set_error(c, PSLAM_E_INVALID, "null pointer or cap < 1");
     if (nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "nframes outside [1, max_batch]");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (!c->orb_ready) { const int arc = orb_alloc(c); if (arc != PSLAM_OK) return arc; }
     const OrbGeom& g = c->geom;
     const size_t frame_px = (size_t)g.width * g.height;
     const int icap = g.total_kp;                       // internal capacity is always sufficient
@@ -192,7 +194,7 @@ int pslam_orb_debug_level_size(const pslam_ctx* c, int level, int32_t* w, int32_
 }
 
 int pslam_orb_debug_level_pixels(pslam_ctx* c, int frame, int level, uint8_t* out) {
-    if (!c || !out || level < 0 || level >= c->geom.nlevels || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    if (!c || !c->orb_ready || !out || level < 0 || level >= c->geom.nlevels || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
     PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
     const OrbGeom& g = c->geom;
     const LevelGeom& v = g.lv[level];
@@ -202,7 +204,7 @@ int pslam_orb_debug_level_pixels(pslam_ctx* c, int frame, int level, uint8_t* ou
 }
 
 int pslam_orb_debug_level_blurred(pslam_ctx* c, int frame, int level, uint8_t* out) {
-    if (!c || !out || level < 0 || level >= c->geom.nlevels || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    if (!c || !c->orb_ready || !out || level < 0 || level >= c->geom.nlevels || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
     PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
     const LevelGeom& v = c->geom.lv[level];
     PSLAM_CUDA(c, cudaMemcpy2D(out, v.w, c->d_blur + (size_t)frame * c->blur_frame_bytes + v.blur_off, v.blur_pitch, v.w, v.h,
@@ -211,7 +213,7 @@ int pslam_orb_debug_level_blurred(pslam_ctx* c, int frame, int level, uint8_t* o
 }
 
 int pslam_orb_debug_level_candidates(pslam_ctx* c, int frame, int level, int32_t* xys, int cap, int32_t* n) {
-    if (!c || !xys || !n || level < 0 || level >= c->geom.nlevels || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    if (!c || !c->orb_ready || !xys || !n || level < 0 || level >= c->geom.nlevels || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
     PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
     const OrbGeom& g = c->geom;
     const LevelGeom& v = g.lv[level];

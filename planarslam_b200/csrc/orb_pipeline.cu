@@ -110,7 +110,6 @@ int orb_alloc(pslam_ctx* c) {
     A(dmalloc(c, &c->d_work, B * g.total_work));
     A(dmalloc(c, &c->d_lvl_kp, B * g.total_kp));
     A(dmalloc(c, &c->d_lvl_cnt, B * g.nlevels));
-    A(dmalloc(c, &c->d_status, B));
     A(dmalloc(c, &c->d_kps, B * cap));
     A(dmalloc(c, &c->d_desc, B * cap * 32));
     A(dmalloc(c, &c->d_n, B));
@@ -118,7 +117,6 @@ int orb_alloc(pslam_ctx* c) {
     A(check_cuda(c, cudaMallocHost((void**)&c->h_kps, B * cap * sizeof(pslam_keypoint)), "cudaMallocHost"));
     A(check_cuda(c, cudaMallocHost((void**)&c->h_desc, B * cap * 32), "cudaMallocHost"));
     A(check_cuda(c, cudaMallocHost((void**)&c->h_n, B * sizeof(int32_t)), "cudaMallocHost"));
-    A(check_cuda(c, cudaMallocHost((void**)&c->h_status, B * sizeof(int32_t)), "cudaMallocHost"));
 #undef A
     // resize tables (cv::resize INTER_LINEAR 8-bit: 11-bit coefficients, see oracle/cvprims.cc for the pinned restatement)
     std::vector<int16_t> xofs(g.total_tabx), xa(2 * g.total_tabx), yofs(g.total_taby), ya(2 * g.total_taby);
@@ -148,6 +146,7 @@ int orb_alloc(pslam_ctx* c) {
     PSLAM_CUDA(c, cudaMemcpy(c->d_xa, xa.data(), xa.size() * 2, cudaMemcpyHostToDevice));
     PSLAM_CUDA(c, cudaMemcpy(c->d_yofs, yofs.data(), yofs.size() * 2, cudaMemcpyHostToDevice));
     PSLAM_CUDA(c, cudaMemcpy(c->d_ya, ya.data(), ya.size() * 2, cudaMemcpyHostToDevice));
+    c->orb_ready = true;
     return PSLAM_OK;
 }
 
@@ -155,14 +154,15 @@ void orb_free(pslam_ctx* c) {
     cudaFree(c->d_gray); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_xofs); cudaFree(c->d_xa); cudaFree(c->d_yofs);
     cudaFree(c->d_ya); cudaFree(c->d_slots); cudaFree(c->d_cell_cnt); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt);
     cudaFree(c->d_nodes); cudaFree(c->d_links); cudaFree(c->d_work); cudaFree(c->d_lvl_kp); cudaFree(c->d_lvl_cnt);
-    cudaFree(c->d_status); cudaFree(c->d_kps); cudaFree(c->d_desc); cudaFree(c->d_n);
-    cudaFreeHost(c->h_gray); cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n); cudaFreeHost(c->h_status);
+    cudaFree(c->d_kps); cudaFree(c->d_desc); cudaFree(c->d_n);
+    cudaFreeHost(c->h_gray); cudaFreeHost(c->h_kps); cudaFreeHost(c->h_desc); cudaFreeHost(c->h_n);
 }
 
 int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_n) {
     const OrbGeom& g = c->geom;
     if (nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "nframes outside [1, max_batch]");
     if (!d_gray || !d_kps || !d_desc || !d_n || cap < 1) return set_error(c, PSLAM_E_INVALID, "null output or cap < 1");
+    if (!c->orb_ready) { const int arc = orb_alloc(c); if (arc != PSLAM_OK) return arc; }
     cudaStream_t st = c->stream;
     c->d_gray_cur = d_gray;
     c->last_nframes = nframes;

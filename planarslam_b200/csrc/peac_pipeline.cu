@@ -57,6 +57,7 @@ int peac_alloc(pslam_ctx* c) {
     A(dmalloc(c, &c->d_midx, B * px)); A(dmalloc(c, &c->d_moff, B * (PEAC_MAX_PLANES + 1)));
     A(check_cuda(c, cudaMallocHost((void**)&c->h_depth, B * px * sizeof(uint16_t)), "cudaMallocHost"));
 #undef A
+    c->peac_ready = true;
     return PSLAM_OK;
 }
 
@@ -74,6 +75,7 @@ int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_
     const PeacGeom& g = c->pgeom;
     if (nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "nframes outside [1, max_batch]");
     if (!d_depth || !d_labels || !d_planes || !d_nplanes || !d_member_idx || !d_member_off) return set_error(c, PSLAM_E_INVALID, "null device pointer");
+    if (!c->peac_ready) { const int arc = peac_alloc(c); if (arc != PSLAM_OK) return arc; }
     cudaStream_t st = c->stream;
     c->last_nframes = nframes;
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_status, 0, nframes * sizeof(int32_t), st));
@@ -118,6 +120,7 @@ int pslam_peac_run_batch(pslam_ctx* c, const uint16_t* depth, int nframes, int32
     if (!depth || !labels || !planes || !nplanes) return set_error(c, PSLAM_E_INVALID, "null pointer");
     if (nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "nframes outside [1, max_batch]");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    if (!c->peac_ready) { const int arc = peac_alloc(c); if (arc != PSLAM_OK) return arc; }
     const PeacGeom& g = c->pgeom;
     const size_t px = (size_t)g.w * g.h;
     cudaStream_t st = c->stream;
@@ -139,7 +142,7 @@ int pslam_peac_run_batch(pslam_ctx* c, const uint16_t* depth, int nframes, int32
 }
 
 int pslam_peac_debug_blocks(pslam_ctx* c, int frame, double* st9, double* geo8, int32_t* n, uint8_t* valid) {
-    if (!c || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    if (!c || !c->peac_ready || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
     PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
     const size_t nb = c->pgeom.nblk, o = (size_t)frame * nb;
     if (st9) PSLAM_CUDA(c, cudaMemcpy(st9, c->d_blk_st + o * 9, nb * 9 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -150,7 +153,7 @@ int pslam_peac_debug_blocks(pslam_ctx* c, int frame, double* st9, double* geo8, 
 }
 
 int pslam_peac_debug_coarse(pslam_ctx* c, int frame, int32_t* blk_map, int32_t* n_coarse) {
-    if (!c || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
+    if (!c || !c->peac_ready || frame < 0 || frame >= c->last_nframes) return PSLAM_E_INVALID;
     PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
     const size_t nb = c->pgeom.nblk;
     if (blk_map) PSLAM_CUDA(c, cudaMemcpy(blk_map, c->d_blk_map + (size_t)frame * nb, nb * sizeof(int32_t), cudaMemcpyDeviceToHost));

@@ -77,6 +77,7 @@ struct pslam_ctx {
     std::vector<ProfRec> prof;
     std::string err;
     int last_nframes = 0;
+    bool orb_ready = false, peac_ready = false;   // stage buffers are allocated on first use of the stage
 
     // device buffers (sized for cfg.max_batch frames)
     uint8_t* d_gray = nullptr;        // staging copy of host input (host-pointer entry points)

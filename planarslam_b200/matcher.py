@@ -95,3 +95,23 @@ class LSDmatcher:
         idx, dist, _ = self.orb.knn2(kf_desc, frame_desc)
         keep = [(i, int(idx[i, 0])) for i in range(len(idx)) if idx[i, 1] >= 0 and dist[i, 0] / max(dist[i, 1], 1e-9) < 1.0 / 1.5]
         return len(keep), keep
+
+
+class PlaneMatcher:
+    """PlaneMatcher(dTh, aTh, verTh, parTh), include/PlaneMatcher.h:16-30."""
+
+    def __init__(self, dTh: float = 0.1, aTh: float = 0.86, verTh: float = 0.08716, parTh: float = 0.9962, ctx: Context | None = None):
+        self.dTh, self.aTh, self.verTh, self.parTh = dTh, aTh, verTh, parTh
+        self.ctx = ctx or Context(640, 480, 1)
+
+    def SearchMapByCoefficients(self, Tcw, frame_coef, map_coef, map_bad, pts_off, pts):
+        Tcw = np.ascontiguousarray(Tcw, np.float32)
+        fc, mc = np.ascontiguousarray(frame_coef, np.float32).reshape(-1, 4), np.ascontiguousarray(map_coef, np.float32).reshape(-1, 4)
+        bad, off, pts = np.ascontiguousarray(map_bad, np.uint8), np.ascontiguousarray(pts_off, np.int32), np.ascontiguousarray(pts, np.float32)
+        nf = len(fc)
+        out = [np.full(max(nf, 1), -1, np.int32) for _ in range(3)]
+        n = self.ctx.L.pslam_plane_match(self.ctx.h, Tcw.ctypes.data, nf, fc.ctypes.data, len(mc), mc.ctypes.data, bad.ctypes.data, off.ctypes.data,
+                                         pts.ctypes.data, self.dTh, self.aTh, self.verTh, self.parTh, *[o.ctypes.data for o in out])
+        if n < 0:
+            self.ctx.check(n)
+        return n, out[0][:nf], out[1][:nf], out[2][:nf]

@@ -47,7 +47,7 @@ def make_pose_problem(seed: int, frame: int = 0, n_points: int = 1000, n_lines: 
                         best = t
             if np.isfinite(best):
                 pts.append(t_wc + best * d)
-        return np.array(pts)
+        return np.array(pts, np.float64).reshape(-1, 3)
 
     def project(Xw):
         Xc = Xw @ R_cw.T + t_cw
