@@ -33,8 +33,12 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H = 640, 480
-SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "1024"))    # frames per library call (context max_batch); throughput of the one-warp-per-frame kernels scales with frames in flight
-SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "1"))         # library calls per step; 1024 frames = 944 MB of gray+depth input >> 126 MB L2
+# Frames per library call (context max_batch).  The serial-order kernels run one warp per frame, so throughput scales with
+# frames in flight; the default is one full wave of the clustering kernel (pslam_peac_wave_frames: SMs x resident CTAs/SM,
+# 1776 on a 148-SM B200), set in main().  1776 frames = 1.6 GB of gray+depth input >> 126 MB L2.
+SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "0"))
+DEFAULT_WAVE = 1776                                            # 148 SMs x 12 resident clustering CTAs
+SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "1"))         # library calls per step
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
 DISTINCT_FRAMES = 16      # rendered once (CPU, ~0.4 s each) and tiled with a per-copy intensity offset
 
@@ -139,6 +143,10 @@ def run_reference(args, rank, world):
     so this arm times the oracle port on all host cores.  Rank 0 only."""
     if rank != 0:
         return
+    global SUB_BATCH, FRAMES_PER_STEP
+    if SUB_BATCH <= 0:
+        SUB_BATCH = DEFAULT_WAVE                 # no GPU is touched in this arm: the same config as the default GPU arm
+    FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
     gray, depth = make_frames(4)
     cores = os.cpu_count() or 1
     vals = []
@@ -189,10 +197,17 @@ def main():
     from planarslam_b200.optimizer import Optimizer
     from planarslam_b200 import synth_pose
 
+    global SUB_BATCH, FRAMES_PER_STEP
+    if SUB_BATCH <= 0:
+        probe = Context(W, H, 1, device=local_rank)
+        SUB_BATCH = int(probe.L.pslam_peac_wave_frames(probe.h)) or DEFAULT_WAVE
+        del probe
+    FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
+
     gray, depth = make_frames()
-    reps = FRAMES_PER_STEP // DISTINCT_FRAMES
-    gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * r, 0, 255).astype(np.uint8) for r in range(reps)])
-    depth_step = np.concatenate([depth for _ in range(reps)])
+    reps = (FRAMES_PER_STEP + DISTINCT_FRAMES - 1) // DISTINCT_FRAMES
+    gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * r, 0, 255).astype(np.uint8) for r in range(reps)])[:FRAMES_PER_STEP]
+    depth_step = np.concatenate([depth for _ in range(reps)])[:FRAMES_PER_STEP]
     dev = torch.device("cuda", local_rank)
     main = torch.cuda.current_stream(dev)
     streams = [torch.cuda.Stream(dev) for _ in range(3)]
@@ -216,12 +231,18 @@ def main():
     d_moff = torch.empty((SUB_BATCH, maxp + 1), dtype=torch.int32, device=dev)
     h_gray = torch.from_numpy(gray_step).pin_memory()
     h_depth = torch.from_numpy(depth_step.view(np.int16)).pin_memory()
-    h_kps = np.zeros((SUB_BATCH, cap), KEYPOINT_DTYPE)
-    h_desc = np.zeros((SUB_BATCH, cap, 32), np.uint8)
-    h_n = np.zeros(SUB_BATCH, np.int32)
-    h_labels = np.zeros((SUB_BATCH, H * W), np.int32)
-    h_planes = np.zeros((SUB_BATCH, maxp), PLANE_DTYPE)
-    h_npl = np.zeros(SUB_BATCH, np.int32)
+    def pinned(shape, dtype):          # page-locked host result buffers (what a replay driver would hand to the ABI)
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        t = torch.empty(n, dtype=torch.uint8).pin_memory()
+        pinned.keep.append(t)
+        return t.numpy().view(dtype).reshape(shape)
+    pinned.keep = []
+    h_kps = pinned((SUB_BATCH, cap), KEYPOINT_DTYPE)
+    h_desc = pinned((SUB_BATCH, cap, 32), np.uint8)
+    h_n = pinned((SUB_BATCH,), np.int32)
+    h_labels = pinned((SUB_BATCH, H * W), np.int32)
+    h_planes = pinned((SUB_BATCH, maxp), PLANE_DTYPE)
+    h_npl = pinned((SUB_BATCH,), np.int32)
     # pose problems: one per frame of a sub-batch (the correspondences a tracker would hand over), packed + uploaded once
     base_probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(16)]
     probs = [base_probs[k % 16] for k in range(SUB_BATCH)]
@@ -230,6 +251,14 @@ def main():
     pose_h2d = sum(sum(p[k].nbytes for k in ("Xw", "obs", "inv_sigma2", "line_Xw", "line_obs", "plane_meas", "plane_map", "par_meas",
                                               "par_map", "ver_meas", "ver_map")) + 64 for p in probs)
 
+    def dev_orb(o):
+        c_orb.check(L.pslam_orb_extract_batch_dev(c_orb.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                                  d_n[o:].data_ptr()))
+
+    def dev_peac(o):
+        c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
+                                                d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
+
     def step_dev():
         ev = torch.cuda.Event()
         ev.record(main)
@@ -237,24 +266,38 @@ def main():
             st.wait_event(ev)
         for s in range(SUBS_PER_STEP):
             o = s * SUB_BATCH
-            c_orb.check(L.pslam_orb_extract_batch_dev(c_orb.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps.data_ptr(), d_desc.data_ptr(), cap,
-                                                      d_n[o:].data_ptr()))
-            c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
-                                                    d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
+            dev_orb(o)
+            dev_peac(o)
             opt.run_packed()
         for st in streams:
             e = torch.cuda.Event()
             e.record(st)
             main.wait_event(e)
 
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(3)
+
     def step_e2e():
-        for s in range(SUBS_PER_STEP):
-            o = s * SUB_BATCH
-            c_orb.check(L.pslam_orb_extract_batch(c_orb.h, h_gray[o].data_ptr(), SUB_BATCH, h_kps.ctypes.data, h_desc.ctypes.data, cap,
-                                                  h_n.ctypes.data))
-            c_peac.check(L.pslam_peac_run_batch(c_peac.h, h_depth[o].data_ptr(), SUB_BATCH, h_labels.ctypes.data, h_planes.ctypes.data,
-                                                h_npl.ctypes.data, None, None))
-            opt.PoseOptimizationBatch(probs)
+        # the three stage families are independent per frame; a replay driver calls the (blocking, host-pointer) ABI
+        # entry points from three host threads, one per context / stream (ctypes releases the GIL during the call)
+        def e_orb():
+            torch.cuda.set_device(local_rank)
+            for s in range(SUBS_PER_STEP):
+                c_orb.check(L.pslam_orb_extract_batch(c_orb.h, h_gray[s * SUB_BATCH].data_ptr(), SUB_BATCH, h_kps.ctypes.data, h_desc.ctypes.data,
+                                                      cap, h_n.ctypes.data))
+
+        def e_peac():
+            torch.cuda.set_device(local_rank)
+            for s in range(SUBS_PER_STEP):
+                c_peac.check(L.pslam_peac_run_batch(c_peac.h, h_depth[s * SUB_BATCH].data_ptr(), SUB_BATCH, h_labels.ctypes.data,
+                                                    h_planes.ctypes.data, h_npl.ctypes.data, None, None))
+
+        def e_pose():
+            torch.cuda.set_device(local_rank)
+            for s in range(SUBS_PER_STEP):
+                opt.PoseOptimizationBatch(probs)
+        for f in [pool.submit(fn) for fn in (e_orb, e_peac, e_pose)]:
+            f.result()
 
     def barrier():
         if world > 1:
@@ -302,12 +345,13 @@ def main():
     d2h = FRAMES_PER_STEP * (cap * 60 + 8 + 4 * W * H + maxp * PLANE_DTYPE.itemsize + 4 + 64 + 1046 + 4)
 
     # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
-    for c in ctxs:
-        c.profile(True)
-    step_dev()
-    torch.cuda.synchronize(dev)
+    # one stage family at a time, so a launch's duration is not inflated by kernels of the other two streams
     rep = {}
-    for c in ctxs:
+    for c, fn in ((c_orb, lambda: dev_orb(0)), (c_peac, lambda: dev_peac(0)), (c_pose, opt.run_packed)):
+        c.profile(True)
+        for _ in range(SUBS_PER_STEP):
+            fn()
+        torch.cuda.synchronize(dev)
         rep.update(c.profile_report())
         c.profile(False)
     peak, peak_kind = _peaks()

@@ -143,6 +143,9 @@ int pslam_peac_run_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframe
 int pslam_peac_debug_blocks(pslam_ctx* ctx, int frame, double* st9, double* geo8, int32_t* n, uint8_t* valid);
 int pslam_peac_debug_coarse(pslam_ctx* ctx, int frame, int32_t* blk_map, int32_t* n_coarse);
 int pslam_peac_num_blocks(const pslam_ctx* ctx);
+/* Frames the clustering kernel (one warp per frame, the longest stage) keeps resident at once on this device: SM count x
+ * resident CTAs per SM.  A replay batch that is a multiple of this number runs in full waves (no reference counterpart). */
+int pslam_peac_wave_frames(const pslam_ctx* ctx);
 
 /* ---- Descriptor matching --------------------------------------------------------------------------
  * Replaces the brute-force searches on the tracking path:

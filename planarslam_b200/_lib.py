@@ -96,6 +96,7 @@ def lib() -> C.CDLL:
     L.pslam_orb_debug_level_candidates.argtypes = [vp, i32, i32, vp, i32, i32p]
     L.pslam_peac_max_planes.argtypes = [vp]
     L.pslam_peac_num_blocks.argtypes = [vp]
+    L.pslam_peac_wave_frames.argtypes = [vp]
     L.pslam_peac_run_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pslam_peac_run_batch_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pslam_peac_debug_blocks.argtypes = [vp, i32, vp, vp, vp, vp]

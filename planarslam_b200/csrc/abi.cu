@@ -157,18 +157,22 @@ int pslam_orb_extract_batch(pslam_ctx* c, const uint8_t* gray, int nframes, psla
     const size_t frame_px = (size_t)g.width * g.height;
     const int icap = g.total_kp;                       // internal capacity is always sufficient
     cudaStream_t st = c->stream;
-    std::memcpy(c->h_gray, gray, frame_px * nframes);  // pageable -> pinned, then one async H2D
-    PSLAM_CUDA(c, cudaMemcpyAsync(c->d_gray, c->h_gray, frame_px * nframes, cudaMemcpyHostToDevice, st));
+    const uint8_t* src = gray;                         // page-locked caller memory goes straight to the copy engine
+    if (!host_ptr_is_pinned(gray)) { std::memcpy(c->h_gray, gray, frame_px * nframes); src = c->h_gray; }   // pageable -> pinned staging
+    PSLAM_CUDA(c, cudaMemcpyAsync(c->d_gray, src, frame_px * nframes, cudaMemcpyHostToDevice, st));
     int rc = orb_run_dev(c, c->d_gray, nframes, c->d_kps, c->d_desc, icap, c->d_n);
     if (rc != PSLAM_OK) return rc;
     PSLAM_CUDA(c, cudaMemcpyAsync(c->h_n, c->d_n, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     PSLAM_CUDA(c, cudaMemcpyAsync(c->h_status, c->d_status, nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    PSLAM_CUDA(c, cudaMemcpyAsync(c->h_kps, c->d_kps, (size_t)nframes * icap * sizeof(pslam_keypoint), cudaMemcpyDeviceToHost, st));
-    PSLAM_CUDA(c, cudaMemcpyAsync(c->h_desc, c->d_desc, (size_t)nframes * icap * 32, cudaMemcpyDeviceToHost, st));
+    // caller buffers with the internal row capacity that are page-locked receive the records directly
+    const bool direct = cap == icap && host_ptr_is_pinned(kps) && host_ptr_is_pinned(desc);
+    PSLAM_CUDA(c, cudaMemcpyAsync(direct ? kps : c->h_kps, c->d_kps, (size_t)nframes * icap * sizeof(pslam_keypoint), cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(direct ? desc : c->h_desc, c->d_desc, (size_t)nframes * icap * 32, cudaMemcpyDeviceToHost, st));
     PSLAM_CUDA(c, cudaStreamSynchronize(st));
     rc = status_to_rc(c, nframes);
     for (int f = 0; f < nframes; ++f) {
         n[f] = c->h_n[f];
+        if (direct) continue;
         const int m = std::min(c->h_n[f], cap);
         if (c->h_n[f] > cap) rc = set_error(c, PSLAM_E_CAPACITY, "caller keypoint capacity too small");
         std::memcpy(kps + (size_t)f * cap, c->h_kps + (size_t)f * icap, (size_t)m * sizeof(pslam_keypoint));

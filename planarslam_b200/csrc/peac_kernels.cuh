@@ -80,22 +80,15 @@ __device__ __forceinline__ void eig33sym_jacobi(const double K[3][3], double s[3
 #pragma unroll
         for (int i = 0; i < 3; ++i) { b[i] += z[i]; d[i] = b[i]; z[i] = 0.0; }
     }
-    int o0 = 0, o1 = 1, o2 = 2;
-    if (d[o1] < d[o0]) { const int t = o0; o0 = o1; o1 = t; }
-    if (d[o2] < d[o0]) { const int t = o0; o0 = o2; o2 = t; }
-    if (d[o2] < d[o1]) { const int t = o1; o1 = o2; o2 = t; }
-    double Vc[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) Vc[i][j] = V[i][j];
-    const int ord[3] = {o0, o1, o2};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        s[k] = d[ord[k]];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) V[i][k] = Vc[i][ord[k]];
-    }
+    // ascending eigenvalues; the three compare-swaps of the oracle's index sort applied in place (static indices keep
+    // everything in registers)
+#define PEAC_CSWAP(i, j) if (d[j] < d[i]) { double t_ = d[i]; d[i] = d[j]; d[j] = t_; \
+        t_ = V[0][i]; V[0][i] = V[0][j]; V[0][j] = t_; t_ = V[1][i]; V[1][i] = V[1][j]; V[1][j] = t_; t_ = V[2][i]; V[2][i] = V[2][j]; V[2][j] = t_; }
+    PEAC_CSWAP(0, 1)
+    PEAC_CSWAP(0, 2)
+    PEAC_CSWAP(1, 2)
+#undef PEAC_CSWAP
+    s[0] = d[0]; s[1] = d[1]; s[2] = d[2];
 }
 
 // Stats::compute (AHCPlaneSeg.hpp:125-156): geo = {center[3], normal[3], mse, curvature}
@@ -182,8 +175,10 @@ struct AhcState {
     uint32_t* adj;           // [nslots][words]
     int16_t* wlo;            // [nslots] first / last adjacency word that can hold a set bit (scans are limited to it)
     int16_t* whi;
-    int32_t* heap;           // [nslots]  (shared memory)
-    double* key;             // [nslots]  mse of every slot, the heap key (shared memory)
+    uint16_t* heap;          // [nslots]  slot ids (shared memory; nslots <= 65535 is checked at context creation)
+    float* keyf;             // [nslots]  float(mse) of every slot (shared memory): the heap orders by it and falls back to the
+                             //           double mse in geo[slot*8+6] only when two float keys are equal (rounding is monotone, so
+                             //           the order is exactly the double order)
     int32_t* nb_list;        // [nslots] scratch
     int32_t* ds_parent;      // disjoint set over initial blocks
     int32_t* ds_size;
@@ -203,21 +198,29 @@ __device__ __forceinline__ void ds_union(int32_t* parent, int32_t* size, int x, 
 }
 
 // libstdc++ binary-heap algorithms (std::priority_queue<.., PlaneSegMinMSECmp>): comp(a,b) = mse[b] < mse[a]
-__device__ __forceinline__ bool heap_comp(const double* key, int a, int b) { return key[b] < key[a]; }
-__device__ __forceinline__ void heap_sift_up(int32_t* h, const double* key, int hole, int top, int value) {
+struct HeapKey {
+    const float* kf; const double* geo;
+    __device__ __forceinline__ bool comp(int a, int b) const {
+        const float fa = kf[a], fb = kf[b];
+        if (fb < fa) return true;
+        if (fb > fa) return false;
+        return geo[(size_t)b * 8 + 6] < geo[(size_t)a * 8 + 6];
+    }
+};
+__device__ __forceinline__ void heap_sift_up(uint16_t* h, const HeapKey& key, int hole, int top, int value) {
     int parent = (hole - 1) / 2;
-    while (hole > top && heap_comp(key, h[parent], value)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
-    h[hole] = value;
+    while (hole > top && key.comp(h[parent], value)) { h[hole] = h[parent]; hole = parent; parent = (hole - 1) / 2; }
+    h[hole] = (uint16_t)value;
 }
-__device__ __forceinline__ void heap_push(int32_t* h, int& len, const double* key, int id) { h[len] = id; ++len; heap_sift_up(h, key, len - 1, 0, id); }
-__device__ __forceinline__ int heap_pop(int32_t* h, int& len, const double* key) {
+__device__ __forceinline__ void heap_push(uint16_t* h, int& len, const HeapKey& key, int id) { h[len] = (uint16_t)id; ++len; heap_sift_up(h, key, len - 1, 0, id); }
+__device__ __forceinline__ int heap_pop(uint16_t* h, int& len, const HeapKey& key) {
     const int top = h[0], value = h[len - 1];
     --len;
     if (len > 0) {
         int hole = 0, child = 0;
         while (child < (len - 1) / 2) {
             child = 2 * (child + 1);
-            if (heap_comp(key, h[child], h[child - 1])) --child;
+            if (key.comp(h[child], h[child - 1])) --child;
             h[hole] = h[child]; hole = child;
         }
         if ((len & 1) == 0 && child == (len - 2) / 2) { child = 2 * (child + 1); h[hole] = h[child - 1]; hole = child - 1; }
@@ -227,14 +230,17 @@ __device__ __forceinline__ int heap_pop(int32_t* h, int& len, const double* key)
 }
 
 // One warp. heap_len: current heap size (entries already pushed in the reference's order). next_cid: next creation id.
-// Extracted slots are appended to ex[] (at most PEAC_MAX_PLANES) and finally stable-sorted by N descending.
-__device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_cid, int32_t* ex, int& n_ex, bool& overflow) {
+// Extracted slots are appended to ex[i * exs] (at most PEAC_MAX_PLANES; exs = +1 or -1) and finally stable-sorted by N
+// descending.  The coarse pass stores them downwards from the last heap entry: every extraction follows a pop that is
+// not pushed back, so heap_len + n_ex < nslots whenever an entry is written.
+__device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_cid, uint16_t* ex, const int exs, int& n_ex, bool& overflow) {
     const int lane = threadIdx.x & 31;
     const uint32_t full = 0xffffffffu;
+    const HeapKey hkey{S.keyf, S.geo};
     int step = 0;
     while (heap_len > 0 && step <= g.max_step) {
         int p = 0;
-        if (lane == 0) p = heap_pop(S.heap, heap_len, S.key);
+        if (lane == 0) p = heap_pop(S.heap, heap_len, hkey);
         p = __shfl_sync(full, p, 0);
         heap_len = __shfl_sync(full, heap_len, 0);
         if (!S.alive[p]) continue;
@@ -331,20 +337,22 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
                     S.adj[(size_t)p * S.words + w] = u;
                     S.adj[(size_t)nb * S.words + w] = 0u;
                 }
-                if (lane < 9) S.st[(size_t)p * 9 + lane] = st[lane];
-                if (lane < 8) S.geo[(size_t)p * 8 + lane] = geo[lane];
-                if (lane == 0) {
-                    S.N[p] = Nc; S.rid[p] = rid_c; S.cid[p] = next_cid; S.alive[nb] = 0; S.key[p] = geo[6];
+                if (lane == 0) {      // static indices: st / geo stay in registers
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) S.st[(size_t)p * 9 + k] = st[k];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) S.geo[(size_t)p * 8 + k] = geo[k];
+                    S.N[p] = Nc; S.rid[p] = rid_c; S.cid[p] = next_cid; S.alive[nb] = 0; S.keyf[p] = (float)geo[6];
                     S.wlo[p] = (int16_t)clo; S.whi[p] = (int16_t)chi;
                 }
                 ++next_cid;
                 __syncwarp();
-                if (lane == 0) heap_push(S.heap, heap_len, S.key, p);
+                if (lane == 0) heap_push(S.heap, heap_len, hkey, p);
                 heap_len = __shfl_sync(full, heap_len, 0);
             }
         }
         if (!merged) {
-            if (Np >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex] = p; ++n_ex; } else overflow = true; }
+            if (Np >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex * exs] = (uint16_t)p; ++n_ex; } else overflow = true; }
             // disconnectAllNbs(p)
             for (int w = plo + lane; w <= phi; w += 32) {
                 uint32_t bits = S.adj[(size_t)p * S.words + w];
@@ -359,18 +367,18 @@ __device__ void ahc_run(const PeacGeom& g, AhcState S, int heap_len, int& next_c
     // (maxStep is never reached in practice; the reference then just drains the queue, :1168-1175)
     while (heap_len > 0) {
         int p = 0;
-        if (lane == 0) p = heap_pop(S.heap, heap_len, S.key);
+        if (lane == 0) p = heap_pop(S.heap, heap_len, hkey);
         p = __shfl_sync(full, p, 0);
         heap_len = __shfl_sync(full, heap_len, 0);
-        if (S.alive[p] && S.N[p] >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex] = p; ++n_ex; } else overflow = true; }
+        if (S.alive[p] && S.N[p] >= g.min_support) { if (n_ex < PEAC_MAX_PLANES) { if (lane == 0) ex[n_ex * exs] = (uint16_t)p; ++n_ex; } else overflow = true; }
     }
     __syncwarp();
     if (lane == 0)      // stable insertion sort by N descending (std::sort on <= 16 elements is exactly this)
         for (int i = 1; i < n_ex; ++i) {
-            const int v = ex[i];
+            const int v = ex[i * exs];
             int j = i - 1;
-            while (j >= 0 && S.N[ex[j]] < S.N[v]) { ex[j + 1] = ex[j]; --j; }
-            ex[j + 1] = v;
+            while (j >= 0 && S.N[ex[j * exs]] < S.N[v]) { ex[(j + 1) * exs] = ex[j * exs]; --j; }
+            ex[(j + 1) * exs] = (uint16_t)v;
         }
     __syncwarp();
 }
@@ -395,8 +403,8 @@ __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* _
     S.nslots = g.nblk; S.words = g.adj_words;
     S.st = node_st + fo * 9; S.geo = node_geo + fo * 8; S.N = node_n + fo; S.rid = node_rid + fo; S.cid = node_cid + fo;
     extern __shared__ __align__(16) unsigned char cluster_smem[];
-    S.key = reinterpret_cast<double*>(cluster_smem);                               // [nblk]
-    S.heap = reinterpret_cast<int32_t*>(cluster_smem + (size_t)g.nblk * sizeof(double));   // [nblk]
+    S.keyf = reinterpret_cast<float*>(cluster_smem);                               // [nblk]
+    S.heap = reinterpret_cast<uint16_t*>(cluster_smem + (size_t)g.nblk * sizeof(float));   // [nblk]
     S.alive = node_alive + fo; S.adj = adj + fo * g.adj_words; S.nb_list = nb_list + fo;
     S.wlo = wlo_all + fo; S.whi = whi_all + fo;
     S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* _
         for (int k = 0; k < 8; ++k) S.geo[(size_t)b * 8 + k] = blk_geo[(fo + b) * 8 + k];
         S.N[b] = blk_n[fo + b]; S.rid[b] = b; S.cid[b] = b; S.alive[b] = valid[b];
         S.ds_parent[b] = b; S.ds_size[b] = 1;
-        S.key[b] = blk_geo[(fo + b) * 8 + 6];
+        S.keyf[b] = (float)blk_geo[(fo + b) * 8 + 6];
         // a block can only be connected to b-1, b+1, b-Nw, b+Nw
         S.wlo[b] = (int16_t)(max(b - g.nbw, 0) >> 5); S.whi[b] = (int16_t)(min(b + g.nbw, g.nblk - 1) >> 5);
     }
@@ -453,19 +461,19 @@ __global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* _
     // initial heap: valid blocks pushed in block order (:810-811)
     int heap_len = 0;
     if (lane == 0)
-        for (int b = 0; b < g.nblk; ++b) if (valid[b]) heap_push(S.heap, heap_len, S.key, b);
+        { const HeapKey hkey{S.keyf, S.geo}; for (int b = 0; b < g.nblk; ++b) if (valid[b]) heap_push(S.heap, heap_len, hkey, b); }
     heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
     __syncwarp();
 
-    __shared__ int32_t ex[PEAC_MAX_PLANES];
+    uint16_t* ex = S.heap + (g.nblk - 1);          // grows downwards inside the heap array (see ahc_run)
     int n_ex = 0, next_cid = g.nblk;
     bool overflow = false;
-    ahc_run(g, S, heap_len, next_cid, ex, n_ex, overflow);
+    ahc_run(g, S, heap_len, next_cid, ex, -1, n_ex, overflow);
     if (overflow && lane == 0) atomicOr(status + frame, 16);
 
     PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
     for (int i = lane; i < n_ex; i += 32) {
-        const int s = ex[i];
+        const int s = ex[-i];
         PeacPlaneRec r;
         for (int k = 0; k < 3; ++k) { r.center[k] = S.geo[(size_t)s * 8 + k]; r.normal[k] = S.geo[(size_t)s * 8 + 3 + k]; }
         r.mse = S.geo[(size_t)s * 8 + 6]; r.curvature = S.geo[(size_t)s * 8 + 7];
@@ -616,11 +624,13 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
         }
         // full reference semantics for one touch (:444-473); returns true when the pixel is pushed
         auto touch = [&]() -> bool {
+            // the three per-pixel loads are independent: issue them together (one memory round trip instead of three)
             const int tr = lab[c];
+            const int dv = D[c];
+            const float old = dm[c];
             if (tr <= -6) return false;
             if (tr >= 0 && tr == plid) return false;
             const FloodPlane& pr = sP[plid];
-            const int dv = D[c];
             bool ok = false;
             float cdist = -1.f;
             if (dv != 0) {
@@ -640,7 +650,7 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
                         atomicOr(&padj[plid * PEAC_PL_WORDS + (tr >> 5)], 1u << (tr & 31));
                     }
                 }
-                if (cdist < dm[c]) { lab[c] = plid; dm[c] = cdist; pushed = true; }
+                if (cdist < old) { lab[c] = plid; dm[c] = cdist; pushed = true; }
                 else if (tr < 0) lab[c] = tr - 1;
             } else if (tr < 0) lab[c] = tr - 1;
             return pushed;
@@ -680,11 +690,13 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
     const int frame = blockIdx.x, tid = threadIdx.x;
     __shared__ double s_st[PEAC_MAX_PLANES * 9];
     __shared__ double s_geo[PEAC_MAX_PLANES * 8];
-    __shared__ int32_t s_n[PEAC_MAX_PLANES], s_rid[PEAC_MAX_PLANES], s_cid[PEAC_MAX_PLANES], s_heap[PEAC_MAX_PLANES], s_nb[PEAC_MAX_PLANES];
+    __shared__ int32_t s_n[PEAC_MAX_PLANES], s_rid[PEAC_MAX_PLANES], s_cid[PEAC_MAX_PLANES], s_tot[PEAC_MAX_PLANES], s_nb[PEAC_MAX_PLANES];
+    __shared__ uint16_t s_heap[PEAC_MAX_PLANES];
     __shared__ uint8_t s_alive[PEAC_MAX_PLANES];
-    __shared__ double s_key[PEAC_MAX_PLANES];
+    __shared__ float s_key[PEAC_MAX_PLANES];
     __shared__ int16_t s_wlo[PEAC_MAX_PLANES], s_whi[PEAC_MAX_PLANES];
-    __shared__ int32_t s_ex[PEAC_MAX_PLANES], s_map[PEAC_MAX_PLANES];
+    __shared__ int32_t s_map[PEAC_MAX_PLANES];
+    __shared__ uint16_t s_ex[PEAC_MAX_PLANES];
     __shared__ int s_nfinal;
     PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
     PeacPlaneRec* O = out_planes + (size_t)frame * PEAC_MAX_PLANES;
@@ -695,7 +707,7 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
         for (int k = 0; k < 3; ++k) { s_geo[i * 8 + k] = P[i].center[k]; s_geo[i * 8 + 3 + k] = P[i].normal[k]; }
         s_geo[i * 8 + 6] = P[i].mse; s_geo[i * 8 + 7] = P[i].curvature;
         s_n[i] = P[i].N; s_rid[i] = P[i].rid; s_cid[i] = P[i].cid; s_alive[i] = (uint8_t)P[i].valid;
-        s_key[i] = P[i].mse; s_wlo[i] = 0; s_whi[i] = PEAC_PL_WORDS - 1;
+        s_key[i] = (float)P[i].mse; s_wlo[i] = 0; s_whi[i] = PEAC_PL_WORDS - 1;
         s_map[i] = -1;
     }
     __syncthreads();
@@ -704,15 +716,15 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
         S.nslots = np; S.words = PEAC_PL_WORDS;
         S.st = s_st; S.geo = s_geo; S.N = s_n; S.rid = s_rid; S.cid = s_cid; S.alive = s_alive;
         S.adj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
-        S.heap = s_heap; S.key = s_key; S.wlo = s_wlo; S.whi = s_whi; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
+        S.heap = s_heap; S.keyf = s_key; S.wlo = s_wlo; S.whi = s_whi; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
         // planes that were eroded completely take no part: drop their adjacency (they never got any) and skip the push
         int heap_len = 0;
-        if (tid == 0) for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, S.key, i);
+        if (tid == 0) { const HeapKey hkey{S.keyf, S.geo}; for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, hkey, i); }
         heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
         __syncwarp();
         int n_ex = 0, next_cid = next_cid_in[frame];
         bool overflow = false;
-        ahc_run(g, S, heap_len, next_cid, s_ex, n_ex, overflow);
+        ahc_run(g, S, heap_len, next_cid, s_ex, 1, n_ex, overflow);
         if (overflow && tid == 0) atomicOr(status + frame, 16);
         // final plane records, and old plane -> final plane map through the disjoint set (:329-344)
         for (int j = tid; j < n_ex; j += 32) {
@@ -759,10 +771,10 @@ __global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __
     if (tid < nf) {
         int run = 0;
         for (int t = 0; t < 256; ++t) { const int v = allcnt[t * PEAC_MAX_PLANES + tid]; allcnt[t * PEAC_MAX_PLANES + tid] = run; run += v; }
-        s_heap[tid] = run;                  // total pixels of plane tid
+        s_tot[tid] = run;                   // total pixels of plane tid
     }
     __syncthreads();
-    if (tid == 0) { int run = 0; for (int k = 0; k < nf; ++k) { moff[k] = run; run += s_heap[k]; } moff[nf] = run; }
+    if (tid == 0) { int run = 0; for (int k = 0; k < nf; ++k) { moff[k] = run; run += s_tot[k]; } moff[nf] = run; }
     __syncthreads();
     int32_t* midx = member_idx + (size_t)frame * npx;
     for (int p = p0; p < p1; ++p) {

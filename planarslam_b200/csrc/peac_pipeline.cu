@@ -31,6 +31,7 @@ int peac_build_geometry(pslam_ctx* c) {
     // points each raises PSLAM_E_CAPACITY at run time (status flag 16).
     if ((long long)g.w * g.h >= (1 << 24)) return set_error(c, PSLAM_E_INVALID, "frame too large for the 24-bit pixel index");
     if (g.nblk < 1) return set_error(c, PSLAM_E_INVALID, "frame smaller than one PEAC block");
+    if (g.nblk > 65535) return set_error(c, PSLAM_E_INVALID, "more than 65535 PEAC blocks per frame (the clustering heap holds 16-bit slot ids)");
     if (!(cf.fx != 0.f) || !(cf.fy != 0.f) || !(cf.depth_scale > 0.f)) return set_error(c, PSLAM_E_INVALID, "fx, fy must be non-zero and depth_scale > 0");
     return PSLAM_OK;
 }
@@ -82,8 +83,9 @@ int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_adj, 0, (size_t)nframes * g.nblk * g.adj_words * sizeof(uint32_t), st));
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_pl_adj, 0, (size_t)nframes * PEAC_MAX_PLANES * PEAC_PL_WORDS * sizeof(uint32_t), st));
     PSLAM_LAUNCH(c, "peac_blocks", k_peac_blocks<<<dim3((g.nblk + 127) / 128, nframes), 128, 0, st>>>(g, d_depth, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid));
-    const size_t cluster_smem = (size_t)g.nblk * (sizeof(double) + sizeof(int32_t));     // heap + heap keys
+    const size_t cluster_smem = (size_t)g.nblk * (sizeof(float) + sizeof(uint16_t));     // float heap keys + u16 heap
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem));
+    PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     PSLAM_LAUNCH(c, "peac_cluster", k_peac_cluster<<<nframes, 32, cluster_smem, st>>>(g, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid, c->d_node_st, c->d_node_geo,
                  c->d_node_n, c->d_node_rid, c->d_node_cid, c->d_node_alive, c->d_adj, c->d_wlo, c->d_whi, c->d_nb_list, c->d_ds_parent, c->d_ds_size, c->d_coarse,
                  c->d_ncoarse, c->d_blk_map, c->d_next_cid, c->d_status));
@@ -107,6 +109,18 @@ extern "C" {
 int pslam_peac_max_planes(const pslam_ctx*) { return PEAC_MAX_PLANES; }
 int pslam_peac_num_blocks(const pslam_ctx* c) { return c ? c->pgeom.nblk : 0; }
 
+int pslam_peac_wave_frames(const pslam_ctx* c) {
+    if (!c) return 0;
+    const size_t cluster_smem = (size_t)c->pgeom.nblk * (sizeof(float) + sizeof(uint16_t));
+    int per_sm = 0, sms = 0, dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem) != cudaSuccess) return 0;
+    cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_peac_cluster, 32, cluster_smem) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return per_sm * sms;
+}
+
 int pslam_peac_run_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes, int32_t* d_nplanes,
                              int32_t* d_member_idx, int32_t* d_member_off) {
     if (!c) return PSLAM_E_INVALID;
@@ -124,8 +138,9 @@ int pslam_peac_run_batch(pslam_ctx* c, const uint16_t* depth, int nframes, int32
     const PeacGeom& g = c->pgeom;
     const size_t px = (size_t)g.w * g.h;
     cudaStream_t st = c->stream;
-    std::memcpy(c->h_depth, depth, px * nframes * sizeof(uint16_t));
-    PSLAM_CUDA(c, cudaMemcpyAsync(c->d_depth, c->h_depth, px * nframes * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    const uint16_t* src = depth;                       // page-locked caller memory goes straight to the copy engine
+    if (!host_ptr_is_pinned(depth)) { std::memcpy(c->h_depth, depth, px * nframes * sizeof(uint16_t)); src = c->h_depth; }
+    PSLAM_CUDA(c, cudaMemcpyAsync(c->d_depth, src, px * nframes * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
     int rc = peac_run_dev(c, c->d_depth, nframes, c->d_labels, c->d_planes, c->d_nplanes, c->d_midx, c->d_moff);
     if (rc != PSLAM_OK) return rc;
     PSLAM_CUDA(c, cudaMemcpyAsync(labels, c->d_labels, px * nframes * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

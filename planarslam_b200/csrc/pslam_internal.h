@@ -149,6 +149,13 @@ int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_
         ++(c)->launches;                                                      \
     } while (0)
 
+// true when p is page-locked host memory known to the CUDA runtime (cudaMallocHost / cudaHostRegister / torch pin_memory)
+static inline bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 #define PSLAM_CUDA(c, call)                                                   \
     do {                                                                      \
         int _rc = pslam::check_cuda((c), (call), #call);                      \

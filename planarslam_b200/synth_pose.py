@@ -115,5 +115,7 @@ def make_pose_problem(seed: int, frame: int = 0, n_points: int = 1000, n_lines: 
 def pose_error(Ta: np.ndarray, Tb: np.ndarray):
     """(rotation angle in rad, translation distance in m) between two 4x4 poses."""
     Ra, Rb = np.asarray(Ta, np.float64)[:3, :3], np.asarray(Tb, np.float64)[:3, :3]
-    c = (np.trace(Ra.T @ Rb) - 1) / 2
-    return float(np.arccos(np.clip(c, -1, 1))), float(np.linalg.norm(np.asarray(Ta, np.float64)[:3, 3] - np.asarray(Tb, np.float64)[:3, 3]))
+    # chord form: exact 0 for identical inputs even when they are float-rounded (not perfectly orthonormal) rotations,
+    # where the arccos(trace) form is ill-conditioned
+    ang = 2.0 * np.arcsin(min(1.0, float(np.linalg.norm(Ra - Rb)) / (2.0 * np.sqrt(2.0))))
+    return float(ang), float(np.linalg.norm(np.asarray(Ta, np.float64)[:3, 3] - np.asarray(Tb, np.float64)[:3, 3]))

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 ROT_TOL, TRANS_TOL = 1e-7, 1e-7            # rad, m   (requirement: 1e-4 rad, 1e-3 m)
 
 
-def _compare(r, o, p):
+def _compare(r, o, p, tag=""):
     er, et = synth_pose.pose_error(r["Tcw_d"], o["Tcw_d"])
-    assert er < ROT_TOL and et < TRANS_TOL, (er, et)
+    assert er < ROT_TOL and et < TRANS_TOL, (tag, er, et, r["trace_i"].tolist(), o["trace_i"].tolist(), r["trace_d"].tolist(), o["trace_d"].tolist())
     assert np.abs(r["Tcw"] - o["Tcw"]).max() < 1e-6
     assert r["n_inliers"] == o["n_inliers"]
     for k in ("outlier_pt", "outlier_line", "outlier_plane", "outlier_par", "outlier_ver"):
@@ -53,8 +53,8 @@ def test_single_call_and_edge_mixes():
         p = synth_pose.make_pose_problem(100 + i, frame=i, **kw)
         n, r = opt.PoseOptimization(p)
         o = oracle_lib.pose_optimization(p)
-        assert n == o["n_inliers"]
-        _compare(r, o, p)
+        assert n == o["n_inliers"], (i, n, o["n_inliers"])
+        _compare(r, o, p, tag=f"case {i}")
     p = synth_pose.make_pose_problem(7, n_points=2, n_lines=0, n_planes=0, n_par=0, n_ver=0)
     n, r = opt.PoseOptimization(p)
     assert n == 0 and np.array_equal(r["Tcw"], p["Tcw0"])
