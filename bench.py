@@ -53,7 +53,10 @@ ALGO_BYTES = {
     "peac_cluster": 2 * 3072 * (17 * 8 + 5) + 128 * 176,  # read block records, write node state + plane list
     "peac_seed": 1228800 + 1228800 + 8000 * 4,         # write labels + distance map + seed queue
     "peac_flood": 614400 + 130000 * (4 + 4 + 4 + 4),   # re-read depth at touched pixels, labels/dist RW, queue RW
-    "peac_final": 2 * 1228800 + 1228800,               # labels read + rewritten, member index lists written
+    "peac_final_merge": 128 * 176 * 2,                 # coarse plane records in, final records out
+    "peac_member_count": 1228800 + 300 * 128 * 4,      # labels read once, per-(sub-chunk, plane) counts written
+    "peac_member_scan": 2 * 300 * 128 * 4,
+    "peac_member_scatter": 2 * 1228800 + 1228800,      # labels read + rewritten, member index lists written
     "pose_optimization": 1046 * 104 + 1046 * 24 + 2048,   # edge records read once, residuals + flags written (per problem)
 }
 
@@ -210,7 +213,9 @@ def main():
     depth_step = np.concatenate([depth for _ in range(reps)])[:FRAMES_PER_STEP]
     dev = torch.device("cuda", local_rank)
     main = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(dev) for _ in range(3)]
+    # ORB, PEAC, pose.  The PEAC chain (one warp per frame, latency-bound) is the critical path: high priority, so its CTAs
+    # are placed first and the bulk-parallel ORB / pose kernels fill the remaining issue slots.
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)]
     ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(3)]       # one context (= one stream) per stage family
     for c, st in zip(ctxs, streams):
         c.set_stream(st.cuda_stream)
@@ -259,16 +264,19 @@ def main():
         c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
                                                 d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
 
-    def step_dev():
+    def steps_dev(nsteps):
+        """nsteps passes over the batch.  The three stage families are independent per frame, so each runs its own
+        sequence of batches on its stream (fork at the start, join at the end: ORB of pass i+1 may overlap PEAC of pass i)."""
         ev = torch.cuda.Event()
         ev.record(main)
         for st in streams:
             st.wait_event(ev)
-        for s in range(SUBS_PER_STEP):
-            o = s * SUB_BATCH
-            dev_orb(o)
-            dev_peac(o)
-            opt.run_packed()
+        for _ in range(nsteps):
+            for s in range(SUBS_PER_STEP):
+                o = s * SUB_BATCH
+                dev_orb(o)
+                dev_peac(o)
+                opt.run_packed()
         for st in streams:
             e = torch.cuda.Event()
             e.record(st)
@@ -305,16 +313,14 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ----
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
+    steps_dev(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = sum(c.launch_count for c in ctxs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main)
-    for _ in range(args.steps):
-        step_dev()
+    steps_dev(args.steps)
     e1.record(main)
     barrier()
     sampler.stop_flag = True

@@ -468,7 +468,7 @@ void pose_optimization(const PoseProblem& P, const float* Tcw_in, PoseResult& ou
         for (int i = 0; i < 16; ++i) out.Tcw[i] = (float)out.Tcw_d[i];
     };
     out.n_rounds = 0;
-    if (nInitial < 3) { out.n_inliers = 0; write_pose(T0); for (int i = 0; i < 16; ++i) out.Tcw[i] = Tcw_in[i]; return; }
+    if (nInitial < 3) { out.n_inliers = 0; for (int i = 0; i < 16; ++i) { out.Tcw[i] = Tcw_in[i]; out.Tcw_d[i] = Tcw_in[i]; } return; }   // return 0, mTcw untouched
     // the reference evaluates computeError() once on every plane edge while building the graph (:896, :935, :975)
     for (Edge& e : E) if (e.kind == PLANE || e.kind == PAR || e.kind == VER) compute_error(e, T0, K);
 
@@ -555,7 +555,7 @@ void translation_optimization(const PoseProblem& P, const float* Tcw_in, PoseRes
         for (int i = 0; i < 16; ++i) out.Tcw[i] = (float)out.Tcw_d[i];
     };
     out.n_rounds = 0;
-    if (nInitial < 3) { out.n_inliers = 0; write_pose(T0); for (int i = 0; i < 16; ++i) out.Tcw[i] = Tcw_in[i]; return; }
+    if (nInitial < 3) { out.n_inliers = 0; for (int i = 0; i < 16; ++i) { out.Tcw[i] = Tcw_in[i]; out.Tcw_d[i] = Tcw_in[i]; } return; }   // return 0, mTcw untouched
     for (int i = 0; i < P.n_planes; ++i) {
         Edge e;
         e.kind = PLANE_T; e.dim = 3; e.idx = i;

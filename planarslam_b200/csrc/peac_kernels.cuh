@@ -522,6 +522,9 @@ __device__ __forceinline__ int peac_seed_count(const PeacGeom& g, const int32_t*
     return n;
 }
 
+// region-growing queue entry: x | y << 12 | plane << 24
+__host__ __device__ __forceinline__ uint32_t peac_q_pack(int x, int y, uint32_t plane) { return (uint32_t)x | ((uint32_t)y << 12) | (plane << 24); }
+
 __global__ void __launch_bounds__(256) k_peac_seed(PeacGeom g, const int32_t* __restrict__ blk_map, int32_t* __restrict__ labels,
                                                    float* __restrict__ dist, uint32_t* __restrict__ queue, int32_t* __restrict__ q_len) {
     const int frame = blockIdx.x, tid = threadIdx.x;
@@ -547,16 +550,16 @@ __global__ void __launch_bounds__(256) k_peac_seed(PeacGeom g, const int32_t* __
     if (tid == 0) { int run = 0; for (int t = 0; t < 256; ++t) { const int v = s_part[t]; s_part[t] = run; run += v; } q_len[frame] = run; }
     __syncthreads();
     int pos = s_part[tid];
-    const int W = g.win, iw = g.w;
+    const int W = g.win;
     for (int b = b0; b < b1; ++b) {
         const int i = b / g.nbw, j = b - i * g.nbw;
         if (bm[b] < 0) {
-            if (i > 0 && bm[b - g.nbw] >= 0) { const int s0 = (i * W - 1) * iw + j * W; const uint32_t pl = (uint32_t)bm[b - g.nbw] << 24; for (int k = 1; k < W; ++k) q[pos++] = (uint32_t)(s0 + k) | pl; }
-            if (j > 0 && bm[b - 1] >= 0) { const int s0 = (i * W) * iw + j * W - 1; const uint32_t pl = (uint32_t)bm[b - 1] << 24; for (int k = 0; k < W - 1; ++k) q[pos++] = (uint32_t)(s0 + k * iw) | pl; }
+            if (i > 0 && bm[b - g.nbw] >= 0) { const uint32_t pl = (uint32_t)bm[b - g.nbw]; for (int k = 1; k < W; ++k) q[pos++] = peac_q_pack(j * W + k, i * W - 1, pl); }
+            if (j > 0 && bm[b - 1] >= 0) { const uint32_t pl = (uint32_t)bm[b - 1]; for (int k = 0; k < W - 1; ++k) q[pos++] = peac_q_pack(j * W - 1, i * W + k, pl); }
         } else {
-            const uint32_t pl = (uint32_t)bm[b] << 24;
-            if (i > 0 && bm[b - g.nbw] != bm[b]) { const int s0 = (i * W) * iw + j * W; for (int k = 0; k < W - 1; ++k) q[pos++] = (uint32_t)(s0 + k) | pl; }
-            if (j > 0 && bm[b - 1] != bm[b]) { const int s0 = (i * W) * iw + j * W; for (int k = 1; k < W; ++k) q[pos++] = (uint32_t)(s0 + k * iw) | pl; }
+            const uint32_t pl = (uint32_t)bm[b];
+            if (i > 0 && bm[b - g.nbw] != bm[b]) { for (int k = 0; k < W - 1; ++k) q[pos++] = peac_q_pack(j * W + k, i * W, pl); }
+            if (j > 0 && bm[b - 1] != bm[b]) { for (int k = 1; k < W; ++k) q[pos++] = peac_q_pack(j * W, i * W + k, pl); }
         }
     }
 }
@@ -564,8 +567,13 @@ __global__ void __launch_bounds__(256) k_peac_seed(PeacGeom g, const int32_t* __
 // ---------------------------------------------------------------------------------------------------------
 // K-P4: region growing (floodFill :428-476). One warp per frame; lane = (queue item % 8) * 4 + neighbour.
 // The 32 (item, neighbour) touches of a step are independent unless two lanes address the same pixel; lanes that share
-// a pixel run in lane (= queue) order, one per round, while all other lanes run in the first round — exact FIFO
-// semantics, at most 4 rounds.  Plane records and the block map live in shared memory (they are read on every touch).
+// a pixel are applied in lane (= queue) order — exact FIFO semantics, at most 4 rounds.  A touch is split in two:
+//   stage A  everything that depends only on immutable data (queue entry, depth, plane records, kept-block map): the
+//            neighbour pixel, its distance to the plane and the inlier test.  It is computed ONE STEP AHEAD for the entries
+//            already in the queue, so its depth load and FP64 arithmetic overlap the current step instead of extending it.
+//   stage B  the order-dependent decision on (label, best distance): the pixel state is loaded once per step, passed
+//            between the lanes that share the pixel by shuffles (no memory round trip per round) and stored once.
+// Queue entries: x | y << 12 | plane << 24.  Plane records and the block map live in shared memory.
 struct FloodPlane { double n[3], c[3], th; };     // th = 9 * mse + 1e-5
 
 __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* __restrict__ depth, const int32_t* __restrict__ blk_map,
@@ -597,79 +605,109 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
     int tail = q_len[frame];
     const double scale = (double)g.scale, fx = (double)g.fx, fy = (double)g.fy, cx = (double)g.cx, cy = (double)g.cy;
     const int item_in_group = lane >> 2, nbr = lane & 3;
+    const uint32_t lt_mask = (1u << lane) - 1;
     bool overflow = false;
 
+    struct Touch { int c, x, y, plid; float cdist; bool have, ok; };
+    // stage A for queue entry e and this lane's neighbour slot.  Neighbour order of getValid4Neighbor (:393-405): left,
+    // right, up, down, skipping the ones outside the image.
+    auto stage_a = [&](uint32_t e) -> Touch {
+        Touch t;
+        const int sx = e & 0xfff, sy = (e >> 12) & 0xfff;
+        t.plid = e >> 24; t.c = -1; t.x = 0; t.y = 0; t.cdist = -1.f; t.ok = false; t.have = false;
+        int n = nbr;
+        if (sx > 0) { if (n == 0) { t.x = sx - 1; t.y = sy; t.have = true; } --n; }
+        if (sx < g.w - 1) { if (n == 0 && !t.have) { t.x = sx + 1; t.y = sy; t.have = true; } --n; }
+        if (sy > 0) { if (n == 0 && !t.have) { t.x = sx; t.y = sy - 1; t.have = true; } --n; }
+        if (sy < g.h - 1) { if (n == 0 && !t.have) { t.x = sx; t.y = sy + 1; t.have = true; } --n; }
+        if (t.have) {
+            // pixels inside a kept block are skipped by every touch and never change: drop them before the conflict test
+            const int by = (t.y * g.win_magic) >> 16, bx = (t.x * g.win_magic) >> 16;
+            if (by < g.nbh && bx < g.nbw && sbm[by * g.nbw + bx] >= 0) t.have = false;
+        }
+        if (t.have) {
+            t.c = t.y * g.w + t.x;
+            const int dv = D[t.c];
+            if (dv != 0) {
+                const FloodPlane& pr = sP[t.plid];
+                const double z = (double)dv * scale;
+                const double x = ((double)t.x - cx) * z / fx, y = ((double)t.y - cy) * z / fy;
+                const double sd = pr.n[0] * (x - pr.c[0]) + pr.n[1] * (y - pr.c[1]) + pr.n[2] * (z - pr.c[2]);
+                t.cdist = (float)fabs(sd);
+                t.ok = (double)t.cdist * (double)t.cdist < pr.th;
+            }
+        }
+        return t;
+    };
+
+    Touch nxt;
+    nxt.c = -1; nxt.x = nxt.y = nxt.plid = 0; nxt.cdist = -1.f; nxt.have = nxt.ok = false;
+    bool next_ready = false;                            // nxt = stage A of q[head + item_in_group] of the coming step
     for (int head = 0; head < tail;) {
         const int group = min(8, tail - head);          // items consumed by this step (a partial group must not skip later pushes)
         const int k = head + item_in_group;
-        bool have = item_in_group < group;
-        int c = -1, plid = 0, cx_ = 0, cy_ = 0;
-        if (have) {
-            const uint32_t e = q[k];
-            const int s = e & 0xffffff;
-            plid = e >> 24;
-            const int sy = s / g.w, sx = s - sy * g.w;
-            // neighbour order of getValid4Neighbor (:393-405): left, right, up, down, skipping the ones outside
-            int n = nbr;
-            have = false;
-            if (sx > 0) { if (n == 0) { c = s - 1; cx_ = sx - 1; cy_ = sy; have = true; } --n; }
-            if (sx < g.w - 1) { if (n == 0 && !have) { c = s + 1; cx_ = sx + 1; cy_ = sy; have = true; } --n; }
-            if (sy > 0) { if (n == 0 && !have) { c = s - g.w; cx_ = sx; cy_ = sy - 1; have = true; } --n; }
-            if (sy < g.h - 1) { if (n == 0 && !have) { c = s + g.w; cx_ = sx; cy_ = sy + 1; have = true; } --n; }
+        Touch t = nxt;
+        if (!next_ready) {
+            t.have = false; t.c = -1;
+            if (item_in_group < group) t = stage_a(q[k]);
         }
-        // pixels inside a kept block are skipped by every touch and never change: drop them before the conflict test
-        if (have) {
-            const int by = cy_ / g.win, bx = cx_ / g.win;
-            if (by < g.nbh && bx < g.nbw && sbm[by * g.nbw + bx] >= 0) have = false;
-        }
-        // full reference semantics for one touch (:444-473); returns true when the pixel is pushed
-        auto touch = [&]() -> bool {
-            // the three per-pixel loads are independent: issue them together (one memory round trip instead of three)
-            const int tr = lab[c];
-            const int dv = D[c];
-            const float old = dm[c];
-            if (tr <= -6) return false;
-            if (tr >= 0 && tr == plid) return false;
-            const FloodPlane& pr = sP[plid];
-            bool ok = false;
-            float cdist = -1.f;
-            if (dv != 0) {
-                const double z = (double)dv * scale;
-                const double x = ((double)cx_ - cx) * z / fx, y = ((double)cy_ - cy) * z / fy;
-                const double sd = pr.n[0] * (x - pr.c[0]) + pr.n[1] * (y - pr.c[1]) + pr.n[2] * (z - pr.c[2]);
-                cdist = (float)fabs(sd);
-                ok = (double)cdist * (double)cdist < pr.th;
+        // pixel state for this step (mutable: always loaded after the previous step's stores)
+        int tr = 0;
+        float old = 0.f;
+        if (t.have) { tr = lab[t.c]; old = dm[t.c]; }
+        // stage A of the next step for entries that already exist (entries never change once written), plus an L1
+        // prefetch of the two mutable lines it will read
+        next_ready = false;
+        if (group == 8 && head + 16 <= tail) {          // the whole next group is already queued (warp-uniform)
+            nxt = stage_a(q[k + 8]);
+            next_ready = true;
+            if (nxt.have) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(lab + nxt.c));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(dm + nxt.c));
             }
-            bool pushed = false;
-            if (ok) {
-                if (tr >= 0) {
-                    const FloodPlane& other = sP[tr];
-                    const double sim = fabs(pr.n[0] * other.n[0] + pr.n[1] * other.n[1] + pr.n[2] * other.n[2]);
-                    if (sim >= g.sim_refine) {
-                        atomicOr(&padj[tr * PEAC_PL_WORDS + (plid >> 5)], 1u << (plid & 31));
-                        atomicOr(&padj[plid * PEAC_PL_WORDS + (tr >> 5)], 1u << (tr & 31));
-                    }
-                }
-                if (cdist < old) { lab[c] = plid; dm[c] = cdist; pushed = true; }
-                else if (tr < 0) lab[c] = tr - 1;
-            } else if (tr < 0) lab[c] = tr - 1;
-            return pushed;
-        };
-        // lanes that address the same pixel form a group and execute in lane order, one per round
-        const uint32_t peers = __match_any_sync(full, have ? c : -1 - lane);
-        const int my_round = __popc(peers & ((1u << lane) - 1));
-        int rounds = __popc(peers);
+        }
+        // ---- stage B: lanes that address the same pixel apply their touches in lane order (:444-473) ----
+        const uint32_t peers = __match_any_sync(full, t.have ? t.c : -1 - lane);
+        const int rank = __popc(peers & lt_mask);
+        int rounds = t.have ? __popc(peers) : 0;
 #pragma unroll
         for (int o = 16; o; o >>= 1) rounds = max(rounds, __shfl_xor_sync(full, rounds, o));
+        const int tr0 = tr;
+        const float old0 = old;
         bool pushed = false;
+        uint32_t rem = peers;
         for (int r = 0; r < rounds; ++r) {
-            if (have && my_round == r) pushed = touch();
-            __syncwarp();
+            int ntr = tr;
+            float nold = old;
+            if (t.have && rank == r && tr > -6 && !(tr >= 0 && tr == t.plid)) {
+                if (t.ok) {
+                    if (tr >= 0) {
+                        const FloodPlane& pr = sP[t.plid];
+                        const FloodPlane& other = sP[tr];
+                        const double sim = fabs(pr.n[0] * other.n[0] + pr.n[1] * other.n[1] + pr.n[2] * other.n[2]);
+                        if (sim >= g.sim_refine) {
+                            atomicOr(&padj[tr * PEAC_PL_WORDS + (t.plid >> 5)], 1u << (t.plid & 31));
+                            atomicOr(&padj[t.plid * PEAC_PL_WORDS + (tr >> 5)], 1u << (tr & 31));
+                        }
+                    }
+                    if (t.cdist < old) { ntr = t.plid; nold = t.cdist; pushed = true; }
+                    else if (tr < 0) ntr = tr - 1;
+                } else if (tr < 0) ntr = tr - 1;
+            }
+            // the r-th lane of every pixel group hands the new state to its peers
+            const int src = rem ? (__ffs(rem) - 1) : lane;
+            rem &= rem - 1;
+            tr = __shfl_sync(full, ntr, src);
+            old = __shfl_sync(full, nold, src);
+        }
+        if (t.have && rank == 0) {                       // one store per pixel
+            if (tr != tr0) lab[t.c] = tr;
+            if (old != old0) dm[t.c] = old;
         }
         const uint32_t pm = __ballot_sync(full, pushed);
         if (pushed) {
-            const int pos = tail + __popc(pm & ((1u << lane) - 1));
-            if (pos < g.queue_cap) q[pos] = (uint32_t)c | ((uint32_t)plid << 24); else overflow = true;
+            const int pos = tail + __popc(pm & lt_mask);
+            if (pos < g.queue_cap) q[pos] = peac_q_pack(t.x, t.y, (uint32_t)t.plid); else overflow = true;
         }
         tail = min(tail + __popc(pm), g.queue_cap);
         head += group;
@@ -680,111 +718,162 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K-P5: last merge over the coarse planes (warp 0), then relabel and build the per-plane pixel lists.
-// grid (frames), block 256.
-__global__ void __launch_bounds__(256) k_peac_final(PeacGeom g, PeacPlaneRec* __restrict__ planes, const int32_t* __restrict__ n_planes,
-                                                    const int32_t* __restrict__ next_cid_in, uint32_t* __restrict__ pl_adj,
-                                                    int32_t* ds_parent, int32_t* ds_size, int32_t* __restrict__ labels,
-                                                    PeacPlaneRec* __restrict__ out_planes, pslam_plane* __restrict__ abi_planes, int32_t* __restrict__ out_n, int32_t* __restrict__ member_idx,
-                                                    int32_t* __restrict__ member_off, int32_t* __restrict__ scratch, int32_t* __restrict__ status) {
+// K-P5a: last merge over the coarse planes (plane_merge, PlaneExtractor / AHCPlaneFitter.hpp:303-360). grid (frames), block 32.
+// Writes the final plane records, the coarse plane -> final plane map (-1: dropped) and the final plane count.
+__global__ void __launch_bounds__(32) k_peac_final_merge(PeacGeom g, PeacPlaneRec* __restrict__ planes, const int32_t* __restrict__ n_planes,
+                                                         const int32_t* __restrict__ next_cid_in, uint32_t* __restrict__ pl_adj,
+                                                         int32_t* ds_parent, int32_t* ds_size, PeacPlaneRec* __restrict__ out_planes,
+                                                         pslam_plane* __restrict__ abi_planes, int32_t* __restrict__ out_n,
+                                                         int32_t* __restrict__ final_map, int32_t* __restrict__ status) {
     const int frame = blockIdx.x, tid = threadIdx.x;
     __shared__ double s_st[PEAC_MAX_PLANES * 9];
     __shared__ double s_geo[PEAC_MAX_PLANES * 8];
-    __shared__ int32_t s_n[PEAC_MAX_PLANES], s_rid[PEAC_MAX_PLANES], s_cid[PEAC_MAX_PLANES], s_tot[PEAC_MAX_PLANES], s_nb[PEAC_MAX_PLANES];
+    __shared__ int32_t s_n[PEAC_MAX_PLANES], s_rid[PEAC_MAX_PLANES], s_cid[PEAC_MAX_PLANES], s_nb[PEAC_MAX_PLANES];
     __shared__ uint16_t s_heap[PEAC_MAX_PLANES];
     __shared__ uint8_t s_alive[PEAC_MAX_PLANES];
     __shared__ float s_key[PEAC_MAX_PLANES];
     __shared__ int16_t s_wlo[PEAC_MAX_PLANES], s_whi[PEAC_MAX_PLANES];
-    __shared__ int32_t s_map[PEAC_MAX_PLANES];
     __shared__ uint16_t s_ex[PEAC_MAX_PLANES];
-    __shared__ int s_nfinal;
     PeacPlaneRec* P = planes + (size_t)frame * PEAC_MAX_PLANES;
     PeacPlaneRec* O = out_planes + (size_t)frame * PEAC_MAX_PLANES;
+    int32_t* fmap = final_map + (size_t)frame * PEAC_MAX_PLANES;
     const int np = n_planes[frame];
     const size_t fo = (size_t)frame * g.nblk;
-    for (int i = tid; i < np; i += 256) {
+    for (int i = tid; i < np; i += 32) {
         for (int k = 0; k < 9; ++k) s_st[i * 9 + k] = P[i].st[k];
         for (int k = 0; k < 3; ++k) { s_geo[i * 8 + k] = P[i].center[k]; s_geo[i * 8 + 3 + k] = P[i].normal[k]; }
         s_geo[i * 8 + 6] = P[i].mse; s_geo[i * 8 + 7] = P[i].curvature;
         s_n[i] = P[i].N; s_rid[i] = P[i].rid; s_cid[i] = P[i].cid; s_alive[i] = (uint8_t)P[i].valid;
         s_key[i] = (float)P[i].mse; s_wlo[i] = 0; s_whi[i] = PEAC_PL_WORDS - 1;
-        s_map[i] = -1;
     }
-    __syncthreads();
-    if (tid < 32) {
-        AhcState S;
-        S.nslots = np; S.words = PEAC_PL_WORDS;
-        S.st = s_st; S.geo = s_geo; S.N = s_n; S.rid = s_rid; S.cid = s_cid; S.alive = s_alive;
-        S.adj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
-        S.heap = s_heap; S.keyf = s_key; S.wlo = s_wlo; S.whi = s_whi; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
-        // planes that were eroded completely take no part: drop their adjacency (they never got any) and skip the push
-        int heap_len = 0;
-        if (tid == 0) { const HeapKey hkey{S.keyf, S.geo}; for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, hkey, i); }
-        heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
-        __syncwarp();
-        int n_ex = 0, next_cid = next_cid_in[frame];
-        bool overflow = false;
-        ahc_run(g, S, heap_len, next_cid, s_ex, 1, n_ex, overflow);
-        if (overflow && tid == 0) atomicOr(status + frame, 16);
-        // final plane records, and old plane -> final plane map through the disjoint set (:329-344)
-        for (int j = tid; j < n_ex; j += 32) {
-            const int s = s_ex[j];
-            PeacPlaneRec r;
-            for (int k = 0; k < 3; ++k) { r.center[k] = s_geo[s * 8 + k]; r.normal[k] = s_geo[s * 8 + 3 + k]; }
-            r.mse = s_geo[s * 8 + 6]; r.curvature = s_geo[s * 8 + 7];
-            for (int k = 0; k < 9; ++k) r.st[k] = s_st[s * 9 + k];
-            r.N = s_n[s]; r.rid = s_rid[s]; r.cid = s_cid[s]; r.valid = 1;
-            O[j] = r;
-            pslam_plane a;
-            for (int k = 0; k < 3; ++k) { a.normal[k] = r.normal[k]; a.center[k] = r.center[k]; }
-            a.mse = r.mse; a.curvature = r.curvature; a.N = r.N; a.rid = r.rid;
-            abi_planes[(size_t)frame * PEAC_MAX_PLANES + j] = a;
-        }
-        __syncwarp();
-        if (tid == 0) {
-            for (int i = 0; i < np; ++i) {
-                if (!P[i].valid) continue;
-                const int root = ds_find(S.ds_parent, P[i].rid);
-                for (int j = 0; j < n_ex; ++j) if (O[j].rid == root) { s_map[i] = j; break; }
-            }
-            s_nfinal = n_ex;
-            out_n[frame] = n_ex;
-        }
+    for (int i = tid; i < PEAC_MAX_PLANES; i += 32) fmap[i] = -1;
+    __syncwarp();
+    AhcState S;
+    S.nslots = np; S.words = PEAC_PL_WORDS;
+    S.st = s_st; S.geo = s_geo; S.N = s_n; S.rid = s_rid; S.cid = s_cid; S.alive = s_alive;
+    S.adj = pl_adj + (size_t)frame * PEAC_MAX_PLANES * PEAC_PL_WORDS;
+    S.heap = s_heap; S.keyf = s_key; S.wlo = s_wlo; S.whi = s_whi; S.nb_list = s_nb; S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;
+    // planes that were eroded completely take no part: drop their adjacency (they never got any) and skip the push
+    int heap_len = 0;
+    if (tid == 0) { const HeapKey hkey{S.keyf, S.geo}; for (int i = 0; i < np; ++i) if (s_alive[i]) heap_push(S.heap, heap_len, hkey, i); }
+    heap_len = __shfl_sync(0xffffffffu, heap_len, 0);
+    __syncwarp();
+    int n_ex = 0, next_cid = next_cid_in[frame];
+    bool overflow = false;
+    ahc_run(g, S, heap_len, next_cid, s_ex, 1, n_ex, overflow);
+    if (overflow && tid == 0) atomicOr(status + frame, 16);
+    // final plane records, and old plane -> final plane map through the disjoint set (:329-344)
+    for (int j = tid; j < n_ex; j += 32) {
+        const int s = s_ex[j];
+        PeacPlaneRec r;
+        for (int k = 0; k < 3; ++k) { r.center[k] = s_geo[s * 8 + k]; r.normal[k] = s_geo[s * 8 + 3 + k]; }
+        r.mse = s_geo[s * 8 + 6]; r.curvature = s_geo[s * 8 + 7];
+        for (int k = 0; k < 9; ++k) r.st[k] = s_st[s * 9 + k];
+        r.N = s_n[s]; r.rid = s_rid[s]; r.cid = s_cid[s]; r.valid = 1;
+        O[j] = r;
+        pslam_plane a;
+        for (int k = 0; k < 3; ++k) { a.normal[k] = r.normal[k]; a.center[k] = r.center[k]; }
+        a.mse = r.mse; a.curvature = r.curvature; a.N = r.N; a.rid = r.rid;
+        abi_planes[(size_t)frame * PEAC_MAX_PLANES + j] = a;
     }
-    __syncthreads();
-    // ---- relabel (:362-372) + ordered per-plane pixel lists: contiguous pixel chunk per thread, two passes ----
-    const int nf = s_nfinal;
-    int32_t* lab = labels + (size_t)frame * g.w * g.h;
+    __syncwarp();
+    if (tid == 0) {
+        for (int i = 0; i < np; ++i) {
+            if (!P[i].valid) continue;
+            const int root = ds_find(S.ds_parent, P[i].rid);
+            for (int j = 0; j < n_ex; ++j) if (O[j].rid == root) { fmap[i] = j; break; }
+        }
+        out_n[frame] = n_ex;
+    }
+}
+
+// K-P5b/c/d: relabel (:362-372) + per-plane pixel lists in ascending pixel order.  The image is cut into sub-chunks of
+// PEAC_SUB pixels, one warp each (32 coalesced pixels per row); per-(sub-chunk, plane) counts -> exclusive scan over the
+// sub-chunks of a frame -> ordered scatter.  Within a row the rank among pixels of the same plane comes from match_any.
+#define PEAC_SUB 1024
+#define PEAC_SUB_WARPS 4
+__host__ __device__ inline int peac_num_sub(const PeacGeom& g) { return (g.w * g.h + PEAC_SUB - 1) / PEAC_SUB; }
+__device__ __forceinline__ int peac_final_id(const int32_t* __restrict__ s_map, int v) { return (v >= 0 && v < PEAC_MAX_PLANES) ? s_map[v] : -1; }
+
+// grid (ceil(nsub / 4), frames), block 128.  counts[frame][sub][plane]
+__global__ void __launch_bounds__(32 * PEAC_SUB_WARPS) k_peac_member_count(PeacGeom g, const int32_t* __restrict__ labels, const int32_t* __restrict__ final_map,
+                                                                           const int32_t* __restrict__ out_n, int32_t* __restrict__ counts, int nsub) {
+    __shared__ int32_t s_map[PEAC_MAX_PLANES];
+    __shared__ int32_t s_cnt[PEAC_SUB_WARPS][PEAC_MAX_PLANES];
+    const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = blockIdx.x * PEAC_SUB_WARPS + warp;
     const int npx = g.w * g.h;
-    const int per = (npx + 255) / 256;
-    const int p0 = tid * per, p1 = min(npx, p0 + per);
-    int32_t* cnt = scratch + ((size_t)frame * 256 + tid) * PEAC_MAX_PLANES;     // this thread's per-plane counts
-    for (int k = 0; k < nf; ++k) cnt[k] = 0;
-    for (int p = p0; p < p1; ++p) {
-        const int v = lab[p];
-        if (v >= 0 && s_map[v] >= 0) ++cnt[s_map[v]];
+    for (int i = threadIdx.x; i < PEAC_MAX_PLANES; i += blockDim.x) s_map[i] = final_map[(size_t)frame * PEAC_MAX_PLANES + i];
+    for (int i = lane; i < PEAC_MAX_PLANES; i += 32) s_cnt[warp][i] = 0;
+    __syncthreads();
+    if (sub >= nsub) return;
+    const int nf = out_n[frame];
+    const int32_t* lab = labels + (size_t)frame * npx;
+    const int p0 = sub * PEAC_SUB, p1 = min(npx, p0 + PEAC_SUB);
+    for (int base = p0; base < p1; base += 32) {
+        const int p = base + lane;
+        const int nv = (p < p1) ? peac_final_id(s_map, lab[p]) : -1;
+        const uint32_t peers = __match_any_sync(0xffffffffu, nv);
+        if (nv >= 0 && (peers & ((1u << lane) - 1)) == 0) s_cnt[warp][nv] += __popc(peers);     // one leader per plane per row
+        __syncwarp();
     }
+    int32_t* out = counts + ((size_t)frame * nsub + sub) * PEAC_MAX_PLANES;
+    for (int k = lane; k < nf; k += 32) out[k] = s_cnt[warp][k];
+}
+
+// grid (frames), block 128: thread = plane.  counts -> exclusive prefix over sub-chunks (in place); member_off
+__global__ void __launch_bounds__(PEAC_MAX_PLANES) k_peac_member_scan(const int32_t* __restrict__ out_n, int32_t* __restrict__ counts,
+                                                                      int32_t* __restrict__ member_off, int nsub) {
+    __shared__ int32_t s_tot[PEAC_MAX_PLANES];
+    const int frame = blockIdx.x, k = threadIdx.x;
+    const int nf = out_n[frame];
+    int32_t* cf = counts + (size_t)frame * nsub * PEAC_MAX_PLANES;
+    int run = 0;
+    if (k < nf)
+        for (int sb = 0; sb < nsub; ++sb) { const int v = cf[(size_t)sb * PEAC_MAX_PLANES + k]; cf[(size_t)sb * PEAC_MAX_PLANES + k] = run; run += v; }
+    s_tot[k] = (k < nf) ? run : 0;
     __syncthreads();
-    // exclusive scan over threads for each plane, and plane offsets
-    int32_t* allcnt = scratch + (size_t)frame * 256 * PEAC_MAX_PLANES;
-    int32_t* moff = member_off + (size_t)frame * (PEAC_MAX_PLANES + 1);
-    if (tid < nf) {
-        int run = 0;
-        for (int t = 0; t < 256; ++t) { const int v = allcnt[t * PEAC_MAX_PLANES + tid]; allcnt[t * PEAC_MAX_PLANES + tid] = run; run += v; }
-        s_tot[tid] = run;                   // total pixels of plane tid
+    if (k == 0) {
+        int32_t* moff = member_off + (size_t)frame * (PEAC_MAX_PLANES + 1);
+        int acc = 0;
+        for (int j = 0; j < nf; ++j) { moff[j] = acc; acc += s_tot[j]; }
+        moff[nf] = acc;
     }
+}
+
+// grid (ceil(nsub / 4), frames), block 128
+__global__ void __launch_bounds__(32 * PEAC_SUB_WARPS) k_peac_member_scatter(PeacGeom g, int32_t* __restrict__ labels, const int32_t* __restrict__ final_map,
+                                                                             const int32_t* __restrict__ out_n, const int32_t* __restrict__ counts,
+                                                                             const int32_t* __restrict__ member_off, int32_t* __restrict__ member_idx, int nsub) {
+    __shared__ int32_t s_map[PEAC_MAX_PLANES];
+    __shared__ int32_t s_pos[PEAC_SUB_WARPS][PEAC_MAX_PLANES];
+    const int frame = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = blockIdx.x * PEAC_SUB_WARPS + warp;
+    const int npx = g.w * g.h;
+    for (int i = threadIdx.x; i < PEAC_MAX_PLANES; i += blockDim.x) s_map[i] = final_map[(size_t)frame * PEAC_MAX_PLANES + i];
     __syncthreads();
-    if (tid == 0) { int run = 0; for (int k = 0; k < nf; ++k) { moff[k] = run; run += s_tot[k]; } moff[nf] = run; }
-    __syncthreads();
+    if (sub >= nsub) return;
+    const int nf = out_n[frame];
+    const int32_t* base_cnt = counts + ((size_t)frame * nsub + sub) * PEAC_MAX_PLANES;
+    const int32_t* moff = member_off + (size_t)frame * (PEAC_MAX_PLANES + 1);
+    for (int k = lane; k < nf; k += 32) s_pos[warp][k] = moff[k] + base_cnt[k];
+    __syncwarp();
+    int32_t* lab = labels + (size_t)frame * npx;
     int32_t* midx = member_idx + (size_t)frame * npx;
-    for (int p = p0; p < p1; ++p) {
-        const int v = lab[p];
-        if (v >= 0 && s_map[v] >= 0) {                // pixels of other values keep their raw trail counter (:369-371)
-            const int nv = s_map[v];
+    const int p0 = sub * PEAC_SUB, p1 = min(npx, p0 + PEAC_SUB);
+    for (int base = p0; base < p1; base += 32) {
+        const int p = base + lane;
+        const int nv = (p < p1) ? peac_final_id(s_map, lab[p]) : -1;
+        const uint32_t peers = __match_any_sync(0xffffffffu, nv);
+        if (nv >= 0) {                                  // pixels of other values keep their raw trail counter (:369-371)
+            const int rank = __popc(peers & ((1u << lane) - 1));
+            const int at = s_pos[warp][nv] + rank;
             lab[p] = nv;
-            midx[moff[nv] + cnt[nv]] = p;
-            ++cnt[nv];
+            midx[at] = p;
         }
+        __syncwarp();
+        if (nv >= 0 && (peers & ((1u << lane) - 1)) == 0) s_pos[warp][nv] += __popc(peers);
+        __syncwarp();
     }
 }
 

@@ -29,7 +29,10 @@ int peac_build_geometry(pslam_ctx* c) {
     g.depth_alpha = 0.04; g.depth_change_tol = 0.02;
     // PEAC_MAX_PLANES (128) is a capacity, not a bound derived from the frame size: a frame with more planes of >= 3000
     // points each raises PSLAM_E_CAPACITY at run time (status flag 16).
-    if ((long long)g.w * g.h >= (1 << 24)) return set_error(c, PSLAM_E_INVALID, "frame too large for the 24-bit pixel index");
+    if (g.w > 4096 || g.h > 4096) return set_error(c, PSLAM_E_INVALID, "frame larger than 4096 in one dimension (12-bit queue coordinates)");
+    g.win_magic = (65536 + g.win - 1) / g.win;
+    for (int x = 0; x < std::max(g.w, g.h); ++x)
+        if (((x * g.win_magic) >> 16) != x / g.win) return set_error(c, PSLAM_E_INVALID, "block index reciprocal is not exact for this frame size");
     if (g.nblk < 1) return set_error(c, PSLAM_E_INVALID, "frame smaller than one PEAC block");
     if (g.nblk > 65535) return set_error(c, PSLAM_E_INVALID, "more than 65535 PEAC blocks per frame (the clustering heap holds 16-bit slot ids)");
     if (!(cf.fx != 0.f) || !(cf.fy != 0.f) || !(cf.depth_scale > 0.f)) return set_error(c, PSLAM_E_INVALID, "fx, fy must be non-zero and depth_scale > 0");
@@ -53,7 +56,8 @@ int peac_alloc(pslam_ctx* c) {
     A(dmalloc(c, &c->d_coarse, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_ncoarse, B)); A(dmalloc(c, &c->d_next_cid, B)); A(dmalloc(c, &c->d_blk_map, B * nb));
     A(dmalloc(c, &c->d_dist, B * px)); A(dmalloc(c, &c->d_queue, B * g.queue_cap)); A(dmalloc(c, &c->d_qlen, B));
     A(dmalloc(c, &c->d_pl_adj, B * PEAC_MAX_PLANES * PEAC_PL_WORDS));
-    A(dmalloc(c, &c->d_final, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_scratch, B * 256 * PEAC_MAX_PLANES));
+    A(dmalloc(c, &c->d_final, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_scratch, B * (size_t)peac_num_sub(g) * PEAC_MAX_PLANES));
+    A(dmalloc(c, &c->d_final_map, B * PEAC_MAX_PLANES));
     A(dmalloc(c, &c->d_labels, B * px)); A(dmalloc(c, &c->d_planes, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_nplanes, B));
     A(dmalloc(c, &c->d_midx, B * px)); A(dmalloc(c, &c->d_moff, B * (PEAC_MAX_PLANES + 1)));
     A(check_cuda(c, cudaMallocHost((void**)&c->h_depth, B * px * sizeof(uint16_t)), "cudaMallocHost"));
@@ -67,7 +71,7 @@ void peac_free(pslam_ctx* c) {
     cudaFree(c->d_node_st); cudaFree(c->d_node_geo); cudaFree(c->d_node_n); cudaFree(c->d_node_rid); cudaFree(c->d_node_cid);
     cudaFree(c->d_node_alive); cudaFree(c->d_adj); cudaFree(c->d_wlo); cudaFree(c->d_whi); cudaFree(c->d_nb_list); cudaFree(c->d_ds_parent); cudaFree(c->d_ds_size);
     cudaFree(c->d_coarse); cudaFree(c->d_ncoarse); cudaFree(c->d_next_cid); cudaFree(c->d_blk_map); cudaFree(c->d_dist); cudaFree(c->d_queue);
-    cudaFree(c->d_qlen); cudaFree(c->d_pl_adj); cudaFree(c->d_final); cudaFree(c->d_scratch); cudaFree(c->d_labels); cudaFree(c->d_planes);
+    cudaFree(c->d_qlen); cudaFree(c->d_pl_adj); cudaFree(c->d_final); cudaFree(c->d_scratch); cudaFree(c->d_final_map); cudaFree(c->d_labels); cudaFree(c->d_planes);
     cudaFree(c->d_nplanes); cudaFree(c->d_midx); cudaFree(c->d_moff); cudaFreeHost(c->h_depth);
 }
 
@@ -94,8 +98,14 @@ int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flood_smem));
     PSLAM_LAUNCH(c, "peac_flood", k_peac_flood<<<nframes, 32, flood_smem, st>>>(g, d_depth, c->d_blk_map, c->d_coarse, c->d_ncoarse, d_labels, c->d_dist, c->d_queue,
                  c->d_qlen, c->d_pl_adj, c->d_status));
-    PSLAM_LAUNCH(c, "peac_final", k_peac_final<<<nframes, 256, 0, st>>>(g, c->d_coarse, c->d_ncoarse, c->d_next_cid, c->d_pl_adj, c->d_ds_parent, c->d_ds_size, d_labels,
-                 c->d_final, d_planes, d_nplanes, d_member_idx, d_member_off, c->d_scratch, c->d_status));
+    PSLAM_LAUNCH(c, "peac_final_merge", k_peac_final_merge<<<nframes, 32, 0, st>>>(g, c->d_coarse, c->d_ncoarse, c->d_next_cid, c->d_pl_adj, c->d_ds_parent,
+                 c->d_ds_size, c->d_final, d_planes, d_nplanes, c->d_final_map, c->d_status));
+    const int nsub = peac_num_sub(g);
+    const dim3 mgrid((nsub + PEAC_SUB_WARPS - 1) / PEAC_SUB_WARPS, nframes);
+    PSLAM_LAUNCH(c, "peac_member_count", k_peac_member_count<<<mgrid, 32 * PEAC_SUB_WARPS, 0, st>>>(g, d_labels, c->d_final_map, d_nplanes, c->d_scratch, nsub));
+    PSLAM_LAUNCH(c, "peac_member_scan", k_peac_member_scan<<<nframes, PEAC_MAX_PLANES, 0, st>>>(d_nplanes, c->d_scratch, d_member_off, nsub));
+    PSLAM_LAUNCH(c, "peac_member_scatter", k_peac_member_scatter<<<mgrid, 32 * PEAC_SUB_WARPS, 0, st>>>(g, d_labels, c->d_final_map, d_nplanes, c->d_scratch,
+                 d_member_off, d_member_idx, nsub));
     PSLAM_CUDA(c, cudaGetLastError());
     return PSLAM_OK;
 }

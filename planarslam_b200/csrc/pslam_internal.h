@@ -49,6 +49,7 @@ struct OrbGeom {
 // PEAC parameters and sizes (compiled-in defaults of the reference: AHCPlaneFitter.hpp:154-158, AHCParamSet.hpp:68-76)
 struct PeacGeom {
     int w, h, nbw, nbh, nblk, win;
+    int win_magic;            // ceil(2^16 / win): (x * win_magic) >> 16 == x / win for every pixel coordinate (checked at creation)
     int min_support, max_step;
     int adj_words, queue_cap;
     float scale, fx, fy, cx, cy;
@@ -109,7 +110,7 @@ struct pslam_ctx {
     int32_t* d_nb_list = nullptr; int32_t* d_ds_parent = nullptr; int32_t* d_ds_size = nullptr;
     pslam::PeacPlaneRec* d_coarse = nullptr; int32_t* d_ncoarse = nullptr; int32_t* d_next_cid = nullptr; int32_t* d_blk_map = nullptr;
     float* d_dist = nullptr; uint32_t* d_queue = nullptr; int32_t* d_qlen = nullptr; uint32_t* d_pl_adj = nullptr;
-    pslam::PeacPlaneRec* d_final = nullptr; int32_t* d_scratch = nullptr;
+    pslam::PeacPlaneRec* d_final = nullptr; int32_t* d_scratch = nullptr; int32_t* d_final_map = nullptr;
     int32_t* d_labels = nullptr; pslam_plane* d_planes = nullptr; int32_t* d_nplanes = nullptr; int32_t* d_midx = nullptr; int32_t* d_moff = nullptr;
     uint16_t* h_depth = nullptr;                 // pinned
     pslam::PoseBuffers* pose = nullptr;          // pose-optimisation staging (pose_pipeline.cu)
