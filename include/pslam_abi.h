@@ -248,6 +248,52 @@ int pslam_translation_optimization_batch(pslam_ctx* ctx, const pslam_pose_proble
                                          uint8_t* outlier_line, uint8_t* outlier_plane, int32_t* n_inliers);
 int pslam_translation_pack(pslam_ctx* ctx, const pslam_pose_problem* probs, int n, const float* Tcw0);
 
+/* ---- Local bundle adjustment ---------------------------------------------------------------------
+ * Replaces  static void Optimizer::LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Map* pMap)
+ *           include/Optimizer.h:34, src/Optimizer.cc:1853-2678  (graph fill :1971-2358, optimize(5) :2363, chi2 gating
+ *           :2373-2455, optimize(10) :2460, erase lists :2462-2560, recovery :2620-2677).
+ * The Map / KeyFrame pointer walk that selects local and fixed key frames and collects observations (:1853-1969) stays on
+ * the host; it hands over plain arrays (include/pslam_adapter.hpp shows the gathering loop):
+ *   key frames  GetPose() (float 4x4 row-major), fixed flag (lFixedCameras, or mnId == 0), fx fy cx cy mbf; vertex order =
+ *               array order (g2o orders vertices by id: pass key frames sorted by mnId)
+ *   points      GetWorldPos() (float 3); observations (key frame, point, mvKeysUn pt + mvuRight (< 0 => monocular edge
+ *               EdgeSE3ProjectXYZ, else EdgeStereoSE3ProjectXYZ), mvInvLevelSigma2[octave])
+ *   lines       GetWorldPos() (two endpoints, double 6) -> two VertexSBAPointXYZ; one observation = two EdgeLineProjectXYZ
+ *               (start, end) sharing mvKeyLineFunctions (double 3).  The reference attaches every line edge to the CURRENT
+ *               key frame pKF (:2169-2201); pass pKF's index in line_obs_kf to reproduce that.
+ *   planes      GetWorldPos() (float 4) -> VertexPlane; observations [0] EdgePlane, [1] EdgeVerticalPlane, [2] EdgeParallelPlane
+ *               with the key frame's mvPlaneCoefficients (float 4)
+ *   settings    Plane.AngleInfo, DistanceInfo, Chi, VPChi (vertical / parallel edges use angleInfo like the reference, :2274)
+ * Outputs: optimised key-frame poses (fixed ones returned unchanged), point / line / plane positions rounded to float like
+ * Converter::toCvMat, and per-observation erase flags = membership of vToErase, vLineToErase, vPlaneToErase,
+ * vVerPlaneToErase, vParPlaneToErase.  pbStopFlag is not supported (the result would depend on thread timing).
+ * Any output pointer may be NULL.  trace: [0] = optimize(5), [1] = optimize(10). */
+typedef struct pslam_lba_problem {
+    int32_t n_kf; const float* kf_Tcw /* [n_kf][16] */; const uint8_t* kf_fixed /* [n_kf] */; const float* kf_K /* [n_kf][5] */;
+    int32_t n_points; const float* pt_Xw /* [n_points][3] */;
+    int32_t n_pt_obs; const int32_t* pt_obs_kf; const int32_t* pt_obs_pt; const float* pt_obs_uvr /* [n][3] */; const float* pt_obs_inv_sigma2;
+    int32_t n_lines; const double* line_Xw /* [n_lines][6] */;
+    int32_t n_line_obs; const int32_t* line_obs_kf; const int32_t* line_obs_line; const double* line_obs_l /* [n][3] */;
+    int32_t n_planes; const float* plane_Xw /* [n_planes][4] */;
+    int32_t n_plane_obs[3]; const int32_t* plane_obs_kf[3]; const int32_t* plane_obs_plane[3]; const float* plane_obs_meas[3] /* [n][4] */;
+    double angle_info, dist_info, plane_chi, vp_chi;
+} pslam_lba_problem;
+
+typedef struct pslam_lba_result {
+    float* kf_Tcw /* [n_kf][16] */; double* kf_Tcw_d; float* pt_Xw /* [n_points][3] */; double* pt_Xw_d;
+    double* line_Xw /* [n_lines][6], float-rounded */; double* line_Xw_d; float* plane_Xw /* [n_planes][4] */; double* plane_Xw_d;
+    uint8_t* erase_pt; uint8_t* erase_line; uint8_t* erase_plane[3];
+    int32_t iterations[2], trials[2]; double chi2[2], lambda[2];
+} pslam_lba_result;
+
+int pslam_local_bundle_adjustment(pslam_ctx* ctx, const pslam_lba_problem* prob, pslam_lba_result* res);
+/* n independent problems (one per key frame of a replayed sequence), one CTA each; res is [n]. */
+int pslam_local_bundle_adjustment_batch(pslam_ctx* ctx, const pslam_lba_problem* probs, int n, pslam_lba_result* res);
+/* Split form (device-resident problems): pack + upload once, run asynchronously on the context's stream, fetch. */
+int pslam_lba_pack(pslam_ctx* ctx, const pslam_lba_problem* probs, int n);
+int pslam_lba_run_packed(pslam_ctx* ctx);
+int pslam_lba_fetch(pslam_ctx* ctx, pslam_lba_result* res /* [n] */);
+
 #ifdef __cplusplus
 }
 #endif

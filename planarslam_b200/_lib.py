@@ -114,6 +114,11 @@ def lib() -> C.CDLL:
     L.pslam_translation_optimization_batch.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.pslam_pose_run_packed.argtypes = [vp]
     L.pslam_pose_fetch.argtypes = [vp] + [vp] * 10
+    L.pslam_local_bundle_adjustment.argtypes = [vp, vp, vp]
+    L.pslam_local_bundle_adjustment_batch.argtypes = [vp, vp, i32, vp]
+    L.pslam_lba_pack.argtypes = [vp, vp, i32]
+    L.pslam_lba_run_packed.argtypes = [vp]
+    L.pslam_lba_fetch.argtypes = [vp, vp]
     _lib = L
     return L
 

@@ -62,6 +62,7 @@ struct PeacGeom {
 struct PeacPlaneRec;
 struct PoseBuffers;
 struct SearchBuffers;
+struct LbaBuffers;
 
 }  // namespace pslam
 
@@ -115,6 +116,7 @@ struct pslam_ctx {
     uint16_t* h_depth = nullptr;                 // pinned
     pslam::PoseBuffers* pose = nullptr;          // pose-optimisation staging (pose_pipeline.cu)
     pslam::SearchBuffers* search = nullptr;      // projection-search staging (search_kernels.cu)
+    pslam::LbaBuffers* lba = nullptr;            // local bundle adjustment staging (lba_pipeline.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
     int32_t* h_status = nullptr;
@@ -132,6 +134,7 @@ int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint
 // pose optimisation (pose_pipeline.cu)
 void pose_free(pslam_ctx* c);
 void search_free(pslam_ctx* c);
+void lba_free(pslam_ctx* c);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

@@ -256,3 +256,15 @@ def search_by_projection_last(fv: dict, lf: dict, m: dict, th: float, mono: bool
     n = L.orc_search_by_projection_last(C.byref(frame_view_struct(fv)), C.byref(last_frame_struct(lf)), C.byref(map_points_struct(m)), th,
                                         int(mono), int(check_ori), matches.ctypes.data)
     return n, matches
+
+
+def local_bundle_adjustment(p: dict) -> dict:
+    """Oracle Optimizer::LocalBundleAdjustment on a planarslam_b200.synth_lba problem dict (same ctypes mirror as the ABI)."""
+    from planarslam_b200 import lba as _lba
+    L = lib()
+    L.orc_local_bundle_adjustment.argtypes = [C.c_void_p, C.c_void_p]
+    s = _lba.problem_struct(p)
+    r, o = _lba.result_struct(s)
+    rc = L.orc_local_bundle_adjustment(C.byref(s), C.byref(r))
+    assert rc == 0
+    return _lba.finish(r, o)
