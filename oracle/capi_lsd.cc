@@ -1,0 +1,42 @@
+// TEST INFRASTRUCTURE ONLY — C entry points (ctypes) onto the oracle line-segment detector.
+#include "lsd.h"
+#include <cstring>
+using namespace oracle;
+extern "C" {
+// segs: float[cap][4]; wpn: double[cap][3] (width, precision, log-NFA); returns the number of segments found
+int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, float* segs, double* wpn, int cap) {
+    std::vector<LsdSegment> out;
+    lsd_detect(Img8{img, w, h, stride}, refine, out);
+    const int n = (int)out.size();
+    for (int i = 0; i < n && i < cap; ++i) {
+        segs[4 * i] = out[i].x1; segs[4 * i + 1] = out[i].y1; segs[4 * i + 2] = out[i].x2; segs[4 * i + 3] = out[i].y2;
+        wpn[3 * i] = out[i].width; wpn[3 * i + 1] = out[i].prec; wpn[3 * i + 2] = out[i].nfa;
+    }
+    return n;
+}
+// stage outputs for the GPU stage-parity tests: blurred [h][w] u8, scaled [sh][sw] u8, modgrad / angles [sh][sw] double,
+// order [(sw-1)(sh-1)] int32, region_id [sh][sw] int32.  Any pointer may be null.  Returns the number of segments.
+int orc_lsd_stages(const uint8_t* img, int w, int h, int stride, int refine, uint8_t* blurred, uint8_t* scaled, double* modgrad, double* angles,
+                   int32_t* order, int32_t* region_id, int32_t* sw_sh) {
+    std::vector<LsdSegment> out;
+    LsdStages st;
+    lsd_detect_stages(Img8{img, w, h, stride}, refine, out, st);
+    if (blurred) std::memcpy(blurred, st.blurred.data(), st.blurred.size());
+    if (scaled) std::memcpy(scaled, st.scaled.data(), st.scaled.size());
+    if (modgrad) std::memcpy(modgrad, st.modgrad.data(), st.modgrad.size() * 8);
+    if (angles) std::memcpy(angles, st.angles.data(), st.angles.size() * 8);
+    if (order) std::memcpy(order, st.order.data(), st.order.size() * 4);
+    if (region_id) std::memcpy(region_id, st.region_id.data(), st.region_id.size() * 4);
+    if (sw_sh) { sw_sh[0] = st.w; sw_sh[1] = st.h; }
+    return (int)out.size();
+}
+// keylines: KeyLine[cap] (68 bytes each), lf: double[cap][3]; returns the number kept
+int orc_extract_line_segments(const uint8_t* img, int w, int h, int stride, int max_lines, void* keylines, double* lf, int cap) {
+    std::vector<KeyLine> kl; std::vector<double> f;
+    extract_line_segments(Img8{img, w, h, stride}, max_lines, kl, f);
+    const int n = std::min((int)kl.size(), cap);
+    static_assert(sizeof(KeyLine) == 68, "KeyLine layout");
+    if (n) { std::memcpy(keylines, kl.data(), (size_t)n * sizeof(KeyLine)); std::memcpy(lf, f.data(), (size_t)n * 3 * 8); }
+    return n;
+}
+}

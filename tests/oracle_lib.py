@@ -268,3 +268,49 @@ def local_bundle_adjustment(p: dict) -> dict:
     rc = L.orc_local_bundle_adjustment(C.byref(s), C.byref(r))
     assert rc == 0
     return _lba.finish(r, o)
+
+
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt", "<f4", 2), ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"), ("endPointY", "<f4"),
+                          ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])
+assert KEYLINE_DTYPE.itemsize == 68
+
+
+def lsd_detect(gray: np.ndarray, refine: int = 2, cap: int = 16384):
+    """Oracle cv::LineSegmentDetector::detect. Returns (segments float32 [n][4], width, prec, nfa float64 [n])."""
+    L = lib()
+    L.orc_lsd_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    g = np.ascontiguousarray(gray, np.uint8)
+    segs, wpn = np.zeros((cap, 4), np.float32), np.zeros((cap, 3))
+    n = L.orc_lsd_detect(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], refine, segs.ctypes.data, wpn.ctypes.data, cap)
+    assert n <= cap
+    return segs[:n].copy(), wpn[:n, 0].copy(), wpn[:n, 1].copy(), wpn[:n, 2].copy()
+
+
+def lsd_stages(gray: np.ndarray, refine: int = 2):
+    """Intermediate products of the oracle detector (for the GPU stage-parity tests)."""
+    L = lib()
+    L.orc_lsd_stages.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 7
+    g = np.ascontiguousarray(gray, np.uint8)
+    h, w = g.shape
+    sw, sh = int(round(w * 0.8)), int(round(h * 0.8))
+    out = dict(blurred=np.zeros((h, w), np.uint8), scaled=np.zeros((sh, sw), np.uint8), modgrad=np.zeros((sh, sw)), angles=np.zeros((sh, sw)),
+               order=np.zeros((sw - 1) * (sh - 1), np.int32), region_id=np.zeros((sh, sw), np.int32))
+    dims = np.zeros(2, np.int32)
+    n = L.orc_lsd_stages(g.ctypes.data, w, h, g.strides[0], refine, out["blurred"].ctypes.data, out["scaled"].ctypes.data, out["modgrad"].ctypes.data,
+                         out["angles"].ctypes.data, out["order"].ctypes.data, out["region_id"].ctypes.data, dims.ctypes.data)
+    assert (dims[0], dims[1]) == (sw, sh)
+    out["n_segments"] = n
+    return out
+
+
+def extract_line_segments(gray: np.ndarray, max_lines: int = 40):
+    """Oracle LineSegment::ExtractLineSegment without LBD. Returns (KeyLine structured array, line functions [n][3])."""
+    L = lib()
+    L.orc_extract_line_segments.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    g = np.ascontiguousarray(gray, np.uint8)
+    cap = max(max_lines, 1)
+    kl, lf = np.zeros(cap, KEYLINE_DTYPE), np.zeros((cap, 3))
+    n = L.orc_extract_line_segments(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], max_lines, kl.ctypes.data, lf.ctypes.data, cap)
+    return kl[:n].copy(), lf[:n].copy()

