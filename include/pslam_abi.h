@@ -294,6 +294,38 @@ int pslam_lba_pack(pslam_ctx* ctx, const pslam_lba_problem* probs, int n);
 int pslam_lba_run_packed(pslam_ctx* ctx);
 int pslam_lba_fetch(pslam_ctx* ctx, pslam_lba_result* res /* [n] */);
 
+/* ---- Line segments ---------------------------------------------------------------------------------
+ * Replaces the detector half of
+ *     void LineSegment::ExtractLineSegment(const cv::Mat& img, std::vector<KeyLine>& keylines, cv::Mat& ldesc,
+ *                                          std::vector<Eigen::Vector3d>& keylineFunctions, float scale, int numOctaves)
+ *     include/LSDextractor.h:349, src/LSDextractor.cpp:13-39  (called from Frame::ExtractLSD, src/Frame.cc:170-179)
+ * i.e. LSDDetector::detect (opencv_contrib line_descriptor, one octave) = cv::LineSegmentDetector(LSD_REFINE_ADV) on the
+ * input image, the KeyLine records built from the segments, the reference's "sort by response, keep 40, renumber class_id"
+ * filter (:18-26) and the line functions sp x ep / |sp x ep| (:30-38).  The LBD descriptors (BinaryDescriptor::compute, :28)
+ * are NOT produced: no upstream implementation is obtainable here to pin them against.
+ * pslam_keyline has the memory layout of cv::line_descriptor::KeyLine (17 four-byte fields, 68 bytes).
+ * refine: 0 = LSD_REFINE_NONE, 1 = LSD_REFINE_STD, 2 = LSD_REFINE_ADV (what the reference runs). */
+typedef struct pslam_keyline {
+    float angle; int32_t class_id; int32_t octave; float pt_x, pt_y; float response; float size;
+    float startPointX, startPointY, endPointX, endPointY, sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+    float lineLength; int32_t numOfPixels;
+} pslam_keyline;
+
+int pslam_lsd_max_segments(const pslam_ctx* ctx);     /* segment capacity per frame of the calls below */
+/* cv::LineSegmentDetector::detect on nframes frames: segs [nframes][cap][4] float (x1 y1 x2 y2), wpn [nframes][cap][3] double
+ * (width, precision, log-NFA; -1 unless refine == 2), n [nframes].  PSLAM_E_CAPACITY when a frame has more than cap segments. */
+int pslam_lsd_detect_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int refine, float* segs, double* wpn, int cap, int32_t* n);
+/* ExtractLineSegment without descriptors: kl [nframes][max_lines], line_functions [nframes][max_lines][3], n [nframes]. */
+int pslam_lines_extract_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int max_lines, pslam_keyline* kl, double* line_functions,
+                              int32_t* n);
+/* Same with device pointers; only enqueues on the context's stream. */
+int pslam_lines_extract_batch_dev(pslam_ctx* ctx, const uint8_t* d_gray, int nframes, int max_lines, pslam_keyline* d_kl,
+                                  double* d_line_functions, int32_t* d_n);
+/* Debug / stage parity (after a detect or extract call): the scaled image [H][W] u8, gradient norm and level-line angle
+ * [H][W] double (-1024 = undefined), the seed order (pixel indices y * W + x) and its length.  Any pointer may be NULL. */
+int pslam_lsd_debug_stage(pslam_ctx* ctx, int frame, int32_t* dims /* W, H */, uint8_t* scaled, double* modgrad, double* angles,
+                          int32_t* order, int32_t* n_order);
+
 #ifdef __cplusplus
 }
 #endif

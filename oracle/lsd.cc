@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle restating cv::LineSegmentDetector (OpenCV imgproc lsd.cpp), the KeyLine glue of
 // opencv_contrib's LSDDetector and LineSegment::ExtractLineSegment (see lsd.h for the map and the pinning status).
 #include "lsd.h"
+#include "detmath.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -156,8 +157,10 @@ struct Lsd {
         reg.clear();
         reg_angle = angles[(size_t)sy * W + sx];
         reg.push_back({sx, sy, reg_angle, modgrad[(size_t)sy * W + sx]});
-        float sumdx = float(std::cos(reg_angle));
-        float sumdy = float(std::sin(reg_angle));
+        double sn, cs;
+        det_sincos(reg_angle, sn, cs);             // std::cos / std::sin in OpenCV; see detmath.h
+        float sumdx = float(cs);
+        float sumdy = float(sn);
         used[(size_t)sy * W + sx] = 1;
         for (size_t i = 0; i < reg.size(); ++i) {
             const int px = reg[i].x, py = reg[i].y;
@@ -206,7 +209,8 @@ struct Lsd {
         x /= sum;
         y /= sum;
         const double theta = get_theta(reg, x, y, reg_angle, prec);
-        const double dx = std::cos(theta), dy = std::sin(theta);
+        double dx, dy;
+        det_sincos(theta, dy, dx);                 // std::cos / std::sin in OpenCV; see detmath.h
         double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
         for (size_t i = 0; i < reg.size(); ++i) {
             const double regdx = double(reg[i].x) - x, regdy = double(reg[i].y) - y;

@@ -119,6 +119,11 @@ def lib() -> C.CDLL:
     L.pslam_lba_pack.argtypes = [vp, vp, i32]
     L.pslam_lba_run_packed.argtypes = [vp]
     L.pslam_lba_fetch.argtypes = [vp, vp]
+    L.pslam_lsd_max_segments.argtypes = [vp]
+    L.pslam_lsd_detect_batch.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
+    L.pslam_lines_extract_batch.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.pslam_lines_extract_batch_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.pslam_lsd_debug_stage.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -79,6 +79,7 @@ void pslam_destroy(pslam_ctx* c) {
     cudaFree(c->d_status); cudaFreeHost(c->h_status);
     pose_free(c);
     lba_free(c);
+    lsd_free(c);
     search_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;

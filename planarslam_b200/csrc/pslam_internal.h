@@ -63,6 +63,7 @@ struct PeacPlaneRec;
 struct PoseBuffers;
 struct SearchBuffers;
 struct LbaBuffers;
+struct LsdBuffers;
 
 }  // namespace pslam
 
@@ -117,6 +118,7 @@ struct pslam_ctx {
     pslam::PoseBuffers* pose = nullptr;          // pose-optimisation staging (pose_pipeline.cu)
     pslam::SearchBuffers* search = nullptr;      // projection-search staging (search_kernels.cu)
     pslam::LbaBuffers* lba = nullptr;            // local bundle adjustment staging (lba_pipeline.cu)
+    pslam::LsdBuffers* lsd = nullptr;            // line-segment detector buffers (lsd_pipeline.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
     int32_t* h_status = nullptr;
@@ -135,6 +137,7 @@ int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint
 void pose_free(pslam_ctx* c);
 void search_free(pslam_ctx* c);
 void lba_free(pslam_ctx* c);
+void lsd_free(pslam_ctx* c);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

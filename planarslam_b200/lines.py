@@ -1,0 +1,55 @@
+"""Host-side mirror of the reference's LineSegment (include/LSDextractor.h:349, src/LSDextractor.cpp:13-39) on top of the C ABI.
+
+    LineSegment(ctx).ExtractLineSegment(gray) -> (keylines structured array, line functions [n][3])
+
+The LBD descriptors of the reference's ExtractLineSegment are not produced (no pinnable upstream implementation here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Context, E_CAPACITY
+
+KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4"), ("pt", "<f4", 2), ("response", "<f4"), ("size", "<f4"),
+                          ("startPointX", "<f4"), ("startPointY", "<f4"), ("endPointX", "<f4"), ("endPointY", "<f4"),
+                          ("sPointInOctaveX", "<f4"), ("sPointInOctaveY", "<f4"), ("ePointInOctaveX", "<f4"), ("ePointInOctaveY", "<f4"),
+                          ("lineLength", "<f4"), ("numOfPixels", "<i4")])       # cv::line_descriptor::KeyLine, 68 bytes
+
+
+class LineSegment:
+    def __init__(self, ctx: Context | None = None, width: int = 640, height: int = 480, max_batch: int = 1, device: int = 0):
+        self.ctx = ctx or Context(width, height, max_batch, device)
+
+    # cv::LineSegmentDetector::detect (refine: 0 NONE, 1 STD, 2 ADV)
+    def detect(self, gray: np.ndarray, refine: int = 2):
+        g = np.ascontiguousarray(gray, np.uint8)
+        frames = g[None] if g.ndim == 2 else g
+        n = len(frames)
+        cap = int(self.ctx.L.pslam_lsd_max_segments(self.ctx.h))
+        segs, wpn, cnt = np.zeros((n, cap, 4), np.float32), np.zeros((n, cap, 3)), np.zeros(n, np.int32)
+        self.ctx.check(self.ctx.L.pslam_lsd_detect_batch(self.ctx.h, frames.ctypes.data, n, refine, segs.ctypes.data, wpn.ctypes.data, cap, cnt.ctypes.data))
+        out = [(segs[i, :cnt[i]].copy(), wpn[i, :cnt[i], 0].copy(), wpn[i, :cnt[i], 1].copy(), wpn[i, :cnt[i], 2].copy()) for i in range(n)]
+        return out[0] if g.ndim == 2 else out
+
+    # void ExtractLineSegment(const Mat& img, vector<KeyLine>&, Mat& ldesc, vector<Vector3d>& lineFunctions, ...)
+    def ExtractLineSegment(self, gray: np.ndarray, max_lines: int = 40):
+        g = np.ascontiguousarray(gray, np.uint8)
+        frames = g[None] if g.ndim == 2 else g
+        n = len(frames)
+        kl, lf, cnt = np.zeros((n, max_lines), KEYLINE_DTYPE), np.zeros((n, max_lines, 3)), np.zeros(n, np.int32)
+        self.ctx.check(self.ctx.L.pslam_lines_extract_batch(self.ctx.h, frames.ctypes.data, n, max_lines, kl.ctypes.data, lf.ctypes.data, cnt.ctypes.data))
+        out = [(kl[i, :cnt[i]].copy(), lf[i, :cnt[i]].copy()) for i in range(n)]
+        return out[0] if g.ndim == 2 else out
+
+    def debug_stage(self, frame: int = 0):
+        dims = np.zeros(2, np.int32)
+        self.ctx.check(self.ctx.L.pslam_lsd_debug_stage(self.ctx.h, frame, dims.ctypes.data, None, None, None, None, None))
+        W, H = int(dims[0]), int(dims[1])
+        out = dict(scaled=np.zeros((H, W), np.uint8), modgrad=np.zeros((H, W)), angles=np.zeros((H, W)), order=np.zeros(W * H, np.int32))
+        no = np.zeros(1, np.int32)
+        self.ctx.check(self.ctx.L.pslam_lsd_debug_stage(self.ctx.h, frame, dims.ctypes.data, out["scaled"].ctypes.data, out["modgrad"].ctypes.data,
+                                                        out["angles"].ctypes.data, out["order"].ctypes.data, no.ctypes.data))
+        out["order"] = out["order"][:int(no[0])]
+        return out
