@@ -58,7 +58,14 @@ ALGO_BYTES = {
     "peac_member_scan": 2 * 300 * 128 * 4,
     "peac_member_scatter": 2 * 1228800 + 1228800,      # labels read + rewritten, member index lists written
     "pose_optimization": 1046 * 104 + 1046 * 24 + 2048,   # edge records read once, residuals + flags written (per problem)
+    "lsd_blur_scale": 307200 + 196608,                 # read the frame once, write the 512x384 scaled image
+    "lsd_gradient": 196608 + 196608 * 16,              # read the scaled image, write one 16-byte record per pixel
+    "lsd_regions": 196608 * 16 + 2 * 60000 * 4 + 2 * 120000 * 4 + 2 * 196608 + 2500 * 96,   # records once, seed order W+R, region FIFO W+R, used map, candidates
+    "lsd_validate": 2500 * (96 + 8) + 2500 * 100 * 16, # candidate rectangles + the records under each rectangle once
+    "lsd_emit": 2500 * 104 + 800 * 40,
+    "lsd_keylines": 800 * 16 + 40 * (68 + 24),
 }
+STAGES = [s for s in os.environ.get("PSLAM_STAGES", "orb,lsd,peac,pose").split(",") if s]
 
 
 def _peaks():
@@ -126,9 +133,14 @@ def cpu_oracle_fps(gray, depth, seconds=12.0, threads=1):
     probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(min(n, 4))]
 
     def work(i):
-        oracle_lib.orb_extract(gray[i % n])      # ctypes releases the GIL inside the C calls
-        oracle_lib.PeacOracle(depth[i % n])
-        oracle_lib.pose_optimization(probs[i % len(probs)])
+        if "orb" in STAGES:
+            oracle_lib.orb_extract(gray[i % n])      # ctypes releases the GIL inside the C calls
+        if "lsd" in STAGES:
+            oracle_lib.extract_line_segments(gray[i % n], 40)
+        if "peac" in STAGES:
+            oracle_lib.PeacOracle(depth[i % n])
+        if "pose" in STAGES:
+            oracle_lib.pose_optimization(probs[i % len(probs)])
         return 1
 
     work(0)                                      # warm
@@ -162,16 +174,17 @@ def run_reference(args, rank, world):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
             "config": workload_config(),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"oracle ORB + PEAC + PoseOptimization on {len(gray)} frames looped for 6 s per step, {cores} threads"},
+                             "sample": f"oracle {' + '.join(STAGES)} on {len(gray)} frames looped for 6 s per step, {cores} threads"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 def workload_config():
-    return {"workload": "640x480 synthetic RGB-D sequence: ORB (1000 feats, 8 levels) + PEAC planes + PoseOptimization "
-                        "(1000 point + 40 line (80 edges) + 6 plane edges per frame); LSD/LBD and descriptor matching not built yet",
+    return {"workload": "640x480 synthetic RGB-D sequence: ORB (1000 feats, 8 levels) + LSD line segments (REFINE_ADV, 40 longest -> KeyLines + "
+                        "line functions; LBD descriptors not built) + PEAC planes + PoseOptimization (1000 point + 40 line (80 edges) + 6 plane "
+                        "edges per frame)",
             "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "l2": "inputs_larger_than_l2",
-            "stages": ["orb", "peac", "pose_opt"], "streams": 3}
+            "stages": STAGES, "streams": len(STAGES)}
 
 
 def main():
@@ -209,17 +222,20 @@ def main():
 
     gray, depth = make_frames()
     reps = (FRAMES_PER_STEP + DISTINCT_FRAMES - 1) // DISTINCT_FRAMES
-    gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * r, 0, 255).astype(np.uint8) for r in range(reps)])[:FRAMES_PER_STEP]
+    # copies differ by a small intensity offset (0..21 grey levels): every frame keeps the full content of a rendered frame
+    gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * (r % 8), 0, 255).astype(np.uint8) for r in range(reps)])[:FRAMES_PER_STEP]
     depth_step = np.concatenate([depth for _ in range(reps)])[:FRAMES_PER_STEP]
     dev = torch.device("cuda", local_rank)
     main = torch.cuda.current_stream(dev)
     # ORB, PEAC, pose.  The PEAC chain (one warp per frame, latency-bound) is the critical path: high priority, so its CTAs
     # are placed first and the bulk-parallel ORB / pose kernels fill the remaining issue slots.
-    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev)]
-    ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(3)]       # one context (= one stream) per stage family
+    streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)]
+    ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(4)]       # one context (= one stream) per stage family
     for c, st in zip(ctxs, streams):
         c.set_stream(st.cuda_stream)
-    c_orb, c_peac, c_pose = ctxs
+    c_orb, c_peac, c_pose, c_lsd = ctxs
+    from planarslam_b200.lines import KEYLINE_DTYPE
+    MAX_LINES = 40
     cap = c_orb.L.pslam_orb_max_keypoints(c_orb.h)
     maxp = c_peac.L.pslam_peac_max_planes(c_peac.h)
     L = c_orb.L
@@ -228,12 +244,15 @@ def main():
     d_depth = torch.from_numpy(depth_step.view(np.int16)).to(dev)      # uint16 bits
     d_kps = torch.empty((SUB_BATCH, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.empty((SUB_BATCH, cap, 32), dtype=torch.uint8, device=dev)
-    d_n = torch.empty(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
+    d_n = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
     d_labels = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
     d_planes = torch.empty((SUB_BATCH, maxp, PLANE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    d_npl = torch.empty(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
+    d_npl = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
     d_midx = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
     d_moff = torch.empty((SUB_BATCH, maxp + 1), dtype=torch.int32, device=dev)
+    d_kl = torch.empty((SUB_BATCH, MAX_LINES, KEYLINE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_lf = torch.empty((SUB_BATCH, MAX_LINES, 3), dtype=torch.float64, device=dev)
+    d_nkl = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
     h_gray = torch.from_numpy(gray_step).pin_memory()
     h_depth = torch.from_numpy(depth_step.view(np.int16)).pin_memory()
     def pinned(shape, dtype):          # page-locked host result buffers (what a replay driver would hand to the ABI)
@@ -248,6 +267,9 @@ def main():
     h_labels = pinned((SUB_BATCH, H * W), np.int32)
     h_planes = pinned((SUB_BATCH, maxp), PLANE_DTYPE)
     h_npl = pinned((SUB_BATCH,), np.int32)
+    h_kl = pinned((SUB_BATCH, MAX_LINES), KEYLINE_DTYPE)
+    h_lf = pinned((SUB_BATCH, MAX_LINES, 3), np.float64)
+    h_nkl = pinned((SUB_BATCH,), np.int32)
     # pose problems: one per frame of a sub-batch (the correspondences a tracker would hand over), packed + uploaded once
     base_probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(16)]
     probs = [base_probs[k % 16] for k in range(SUB_BATCH)]
@@ -264,6 +286,10 @@ def main():
         c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
                                                 d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
 
+    def dev_lsd(o):
+        c_lsd.check(L.pslam_lines_extract_batch_dev(c_lsd.h, d_gray[o].data_ptr(), SUB_BATCH, MAX_LINES, d_kl.data_ptr(), d_lf.data_ptr(),
+                                                    d_nkl[o:].data_ptr()))
+
     def steps_dev(nsteps):
         """nsteps passes over the batch.  The three stage families are independent per frame, so each runs its own
         sequence of batches on its stream (fork at the start, join at the end: ORB of pass i+1 may overlap PEAC of pass i)."""
@@ -274,16 +300,21 @@ def main():
         for _ in range(nsteps):
             for s in range(SUBS_PER_STEP):
                 o = s * SUB_BATCH
-                dev_orb(o)
-                dev_peac(o)
-                opt.run_packed()
+                if "peac" in STAGES:
+                    dev_peac(o)
+                if "lsd" in STAGES:
+                    dev_lsd(o)
+                if "orb" in STAGES:
+                    dev_orb(o)
+                if "pose" in STAGES:
+                    opt.run_packed()
         for st in streams:
             e = torch.cuda.Event()
             e.record(st)
             main.wait_event(e)
 
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(3)
+    pool = ThreadPoolExecutor(4)
 
     def step_e2e():
         # the three stage families are independent per frame; a replay driver calls the (blocking, host-pointer) ABI
@@ -304,7 +335,13 @@ def main():
             torch.cuda.set_device(local_rank)
             for s in range(SUBS_PER_STEP):
                 opt.PoseOptimizationBatch(probs)
-        for f in [pool.submit(fn) for fn in (e_orb, e_peac, e_pose)]:
+        def e_lsd():
+            torch.cuda.set_device(local_rank)
+            for s in range(SUBS_PER_STEP):
+                c_lsd.check(L.pslam_lines_extract_batch(c_lsd.h, h_gray[s * SUB_BATCH].data_ptr(), SUB_BATCH, MAX_LINES, h_kl.ctypes.data,
+                                                        h_lf.ctypes.data, h_nkl.ctypes.data))
+        fns = [fn for nm, fn in (("peac", e_peac), ("lsd", e_lsd), ("orb", e_orb), ("pose", e_pose)) if nm in STAGES]
+        for f in [pool.submit(fn) for fn in fns]:
             f.result()
 
     def barrier():
@@ -347,13 +384,17 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
-    h2d = FRAMES_PER_STEP * (W * H + 2 * W * H) + SUBS_PER_STEP * pose_h2d
-    d2h = FRAMES_PER_STEP * (cap * 60 + 8 + 4 * W * H + maxp * PLANE_DTYPE.itemsize + 4 + 64 + 1046 + 4)
+    h2d = FRAMES_PER_STEP * (("orb" in STAGES) * W * H + ("lsd" in STAGES) * W * H + ("peac" in STAGES) * 2 * W * H) + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
+    d2h = FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 60 + 8) + ("peac" in STAGES) * (4 * W * H + maxp * PLANE_DTYPE.itemsize + 4) +
+                             ("pose" in STAGES) * (64 + 1046 + 4) + ("lsd" in STAGES) * (MAX_LINES * (68 + 24) + 4))
 
     # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
     # one stage family at a time, so a launch's duration is not inflated by kernels of the other two streams
     rep = {}
-    for c, fn in ((c_orb, lambda: dev_orb(0)), (c_peac, lambda: dev_peac(0)), (c_pose, opt.run_packed)):
+    for nm, c, fn in (("orb", c_orb, lambda: dev_orb(0)), ("lsd", c_lsd, lambda: dev_lsd(0)), ("peac", c_peac, lambda: dev_peac(0)),
+                      ("pose", c_pose, opt.run_packed)):
+        if nm not in STAGES:
+            continue
         c.profile(True)
         for _ in range(SUBS_PER_STEP):
             fn()
@@ -373,8 +414,31 @@ def main():
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_total"])
     roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 6), "traffic": None, "peak_kind": peak_kind,
-                "note": "serial-order kernels (quadtree, AHC, region growing, LM) run one warp/CTA per frame: latency-bound, see DESIGN.md",
+                "note": "serial-order kernels (quadtree, AHC, PEAC / LSD region growing, LM) run one warp/CTA per frame: latency-bound, see DESIGN.md",
                 "per_kernel": per_kernel}
+
+    # ---- auxiliary: LocalBundleAdjustment throughput (BASELINE.json config 4: 20 KFs, 5000 point + 200 line + 30 plane edges) ----
+    aux = {}
+    try:
+        from planarslam_b200 import synth_lba
+        from planarslam_b200.lba import LocalBundleAdjuster
+        n_lba = 296
+        base = [synth_lba.make_lba_problem(k) for k in range(4)]
+        ba = LocalBundleAdjuster(c_pose)
+        ba.pack([base[k % 4] for k in range(n_lba)])
+        ba.run_packed()
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(streams[2]):
+            a0.record()
+            for _ in range(3):
+                ba.run_packed()
+            a1.record()
+        torch.cuda.synchronize(dev)
+        aux["local_bundle_adjustments_per_sec"] = round(3 * n_lba / (a0.elapsed_time(a1) * 1e-3), 1)
+        aux["lba_config"] = "20 key frames (1 fixed), 5000 point + 100 line (200 edges) + 30 plane-type edges, 296 problems per launch"
+    except Exception as ex:                      # auxiliary only: never fail the headline
+        aux["lba_error"] = repr(ex)
 
     if rank == 0:
         cpu_fps, cpu_n = cpu_oracle_fps(gray, depth, seconds=12.0, threads=1)
@@ -385,8 +449,9 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": roofline,
                 "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
-                                 "sample": f"oracle (restatement of the reference, -O2, scalar) ORB + PEAC + PoseOptimization, {cpu_n} frames in ~12 s"},
-                "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP}
+                                 "sample": f"oracle (restatement of the reference, -O2, scalar) {' + '.join(STAGES)}, {cpu_n} frames in ~12 s"},
+                "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP,
+                "keylines_per_frame": float(d_nkl.sum().item()) / FRAMES_PER_STEP if "lsd" in STAGES else None, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
