@@ -326,6 +326,18 @@ int pslam_lines_extract_batch_dev(pslam_ctx* ctx, const uint8_t* d_gray, int nfr
 int pslam_lsd_debug_stage(pslam_ctx* ctx, int frame, int32_t* dims /* W, H */, uint8_t* scaled, double* modgrad, double* angles,
                           int32_t* order, int32_t* n_order);
 
+/* Replaces  int LSDmatcher::SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, float th)
+ *           include/LSDmatcher.h:24, src/LSDmatcher.cpp:141-211 (+ Frame::GetLinesInArea src/Frame.cc:491-523).
+ * Frame side: KeyLine pt / angle / octave and the LBD rows of the <= 64 frame lines, has_obs[i] = (mvpMapLines[i] &&
+ * mvpMapLines[i]->Observations() > 0) on entry, mvScaleFactors.  Map side, one entry per element of vpMapLines: skip (null /
+ * isBad() / !mbTrackInView), mnTrackScaleLevel, mTrackViewCos, mTrackProjX1 Y1 X2 Y2, GetDescriptor(), Observations() > 0.
+ * assigned[i] = index of the map line the call stores into F.mvpMapLines[i], -1 where it leaves the entry alone.
+ * Returns nmatches (>= 0) or a negative pslam_status. */
+int pslam_line_search_by_projection(pslam_ctx* ctx, int n_frame_lines, const float* pt, const float* angle, const int32_t* octave, const uint8_t* desc,
+                                    const uint8_t* has_obs, const float* scale_factors, int n_levels, int n_map_lines, const uint8_t* skip,
+                                    const int32_t* level, const float* view_cos, const float* proj, const uint8_t* map_desc,
+                                    const uint8_t* map_has_obs, float th, float nnratio, int32_t* assigned);
+
 #ifdef __cplusplus
 }
 #endif

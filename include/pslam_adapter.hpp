@@ -9,6 +9,8 @@
 //   ORBextractor getters                       include/ORBextractor.h:63-83   -> pslam_orb_get_scale_tables
 //   PlaneDetection::readDepthImage / run...    include/PlaneExtractor.h:36-56 -> pslam_peac_run_batch
 //   Optimizer::PoseOptimization                include/Optimizer.h:38         -> pslam_pose_optimization
+//   Optimizer::LocalBundleAdjustment           include/Optimizer.h:34         -> pslam_local_bundle_adjustment
+//   LineSegment::ExtractLineSegment            include/LSDextractor.h:349     -> pslam_lines_extract_batch
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -132,6 +134,38 @@ private:
     float K_[4] = {0, 0, 0, 0}, scale_ = 0;
 };
 
+// Same method name and argument order as Planar_SLAM::LineSegment (include/LSDextractor.h:349); the descriptor matrix is not
+// produced (LBD stays with OpenCV's BinaryDescriptor on the returned key lines).
+class LineSegment {
+public:
+    ~LineSegment() { delete ctx_; }
+    // void ExtractLineSegment(const Mat& img, vector<KeyLine>& keylines, Mat& ldesc, vector<Vector3d>& keylineFunctions, float scale, int numOctaves)
+    void ExtractLineSegment(const Image8& img, std::vector<pslam_keyline>& keylines, std::vector<double>& keylineFunctions /* 3 per line, appended */,
+                            float /*scale*/ = 1.2f, int /*numOctaves*/ = 1) {
+        keylines.clear();
+        if (!img.data || img.width <= 0 || img.height <= 0) return;
+        if (!ctx_ || ctx_->config().width != img.width || ctx_->config().height != img.height) { delete ctx_; ctx_ = new Context(img.width, img.height); }
+        std::vector<uint8_t> dense;
+        const uint8_t* src = img.data;
+        if (img.stride != img.width) {
+            dense.resize((size_t)img.width * img.height);
+            for (int y = 0; y < img.height; ++y) std::memcpy(&dense[(size_t)y * img.width], img.data + (size_t)y * img.stride, img.width);
+            src = dense.data();
+        }
+        const int max_lines = 40;                                             // lsdNFeatures, src/LSDextractor.cpp:18
+        keylines.resize(max_lines);
+        std::vector<double> lf((size_t)max_lines * 3);
+        int32_t n = 0;
+        if (pslam_lines_extract_batch(ctx_->get(), src, 1, max_lines, keylines.data(), lf.data(), &n) != PSLAM_OK)
+            throw std::runtime_error(pslam_last_error(ctx_->get()));
+        keylines.resize(n);
+        keylineFunctions.insert(keylineFunctions.end(), lf.begin(), lf.begin() + 3 * n);
+    }
+private:
+    Context* ctx_ = nullptr;
+};
+
+
 // static int Optimizer::PoseOptimization(Frame* pFrame): the Frame fields it reads are gathered into a pslam_pose_problem
 // by the caller under the same mutexes the reference takes (MapPoint/MapLine/MapPlane::mGlobalMutex, src/Optimizer.cc:590,691,786).
 class Optimizer {
@@ -152,5 +186,12 @@ public:
 private:
     Context& ctx_;
 };
+
+
+// static void Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*): the caller gathers the local map into a
+// pslam_lba_problem and owns the output arrays of pslam_lba_result.
+inline void LocalBundleAdjustment(Context& ctx, const pslam_lba_problem& prob, pslam_lba_result& res) {
+    if (pslam_local_bundle_adjustment(ctx.get(), &prob, &res) != PSLAM_OK) throw std::runtime_error(pslam_last_error(ctx.get()));
+}
 
 }  // namespace pslam_adapter

@@ -40,3 +40,14 @@ int orc_extract_line_segments(const uint8_t* img, int w, int h, int stride, int 
     return n;
 }
 }
+
+#include "linesearch.h"
+extern "C" int orc_line_search_by_projection(int nf, const float* pt, const float* angle, const int32_t* octave, const uint8_t* desc, const uint8_t* has_obs,
+                                             const float* scale_factors, int n_levels, int nm, const uint8_t* skip, const int32_t* level,
+                                             const float* view_cos, const float* proj, const uint8_t* mdesc, const uint8_t* m_has_obs, float th,
+                                             float nnratio, int32_t* assigned) {
+    oracle::LineFrameView F; oracle::MapLinesView M;
+    F.n = nf; F.pt = pt; F.angle = angle; F.octave = octave; F.desc = desc; F.has_obs = has_obs; F.scale_factors = scale_factors; F.n_levels = n_levels;
+    M.n = nm; M.skip = skip; M.level = level; M.view_cos = view_cos; M.proj = proj; M.desc = mdesc; M.has_obs = m_has_obs;
+    return oracle::line_search_by_projection(F, M, th, nnratio, assigned);
+}

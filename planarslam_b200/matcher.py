@@ -115,3 +115,27 @@ class PlaneMatcher:
         if n < 0:
             self.ctx.check(n)
         return n, out[0][:nf], out[1][:nf], out[2][:nf]
+
+
+class LSDmatcher:
+    """Mirror of Planar_SLAM::LSDmatcher for the projection search (include/LSDmatcher.h:21-24)."""
+
+    def __init__(self, nnratio: float = 0.6, ctx: Context | None = None):
+        self.nnratio = nnratio
+        self.ctx = ctx or Context(640, 480, 1)
+
+    # int SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, const float th = 3)
+    def SearchByProjection(self, frame: dict, map_lines: dict, th: float = 3.0):
+        """frame: pt [n][2] f32, angle [n] f32, octave [n] i32, desc [n][32] u8, has_obs [n] u8, scale_factors [L] f32;
+        map_lines: skip u8, level i32, view_cos f32, proj [m][4] f32, desc [m][32] u8, has_obs u8.  Returns (nmatches, assigned)."""
+        f = {k: np.ascontiguousarray(v) for k, v in frame.items()}
+        m = {k: np.ascontiguousarray(v) for k, v in map_lines.items()}
+        nf, nm = len(f["angle"]), len(m["level"])
+        assigned = np.full(max(nf, 1), -1, np.int32)
+        n = self.ctx.L.pslam_line_search_by_projection(
+            self.ctx.h, nf, f["pt"].ctypes.data, f["angle"].ctypes.data, f["octave"].ctypes.data, f["desc"].ctypes.data, f["has_obs"].ctypes.data,
+            f["scale_factors"].ctypes.data, len(f["scale_factors"]), nm, m["skip"].ctypes.data, m["level"].ctypes.data, m["view_cos"].ctypes.data,
+            m["proj"].ctypes.data, m["desc"].ctypes.data, m["has_obs"].ctypes.data, th, self.nnratio, assigned.ctypes.data)
+        if n < 0:
+            self.ctx.check(n)
+        return n, assigned[:nf]

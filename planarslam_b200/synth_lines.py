@@ -1,0 +1,31 @@
+"""Seeded synthetic inputs for LSDmatcher::SearchByProjection: a frame's key lines with binary descriptors and a local map of
+lines projected into it (the fields Frame::isInFrustum(MapLine*) fills), with noisy descriptor copies, occluded / bad
+entries, octave mismatches and near-duplicate descriptors so that the ratio test and the occupancy rule fire."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def make_line_search(seed: int, n_frame: int = 40, n_map: int = 120, n_levels: int = 8):
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 613 + 5))
+    pt = np.stack([rng.uniform(20, 620, n_frame), rng.uniform(20, 460, n_frame)], 1).astype(np.float32)
+    angle = rng.uniform(-np.pi, np.pi, n_frame).astype(np.float32)
+    octave = rng.integers(0, 2, n_frame).astype(np.int32)
+    desc = rng.integers(0, 256, (n_frame, 32), dtype=np.uint8)
+    frame = dict(pt=pt, angle=angle, octave=octave, desc=desc, has_obs=(rng.random(n_frame) < 0.15).astype(np.uint8),
+                 scale_factors=(1.2 ** np.arange(n_levels)).astype(np.float32))
+    src = rng.integers(0, n_frame, n_map)                       # the frame line each map line really corresponds to
+    half = rng.uniform(10, 60, n_map)
+    ang = angle[src] + rng.normal(0, 0.3, n_map)
+    mid = pt[src] + rng.normal(0, 3.0, (n_map, 2))
+    d = np.stack([np.cos(ang), np.sin(ang)], 1) * half[:, None]
+    proj = np.concatenate([mid - d, mid + d], 1).astype(np.float32)
+    mdesc = desc[src].copy()
+    flips = rng.random((n_map, 256)) < rng.choice([0.02, 0.1, 0.3], n_map)[:, None]
+    mdesc ^= np.packbits(flips, axis=1)
+    dup = rng.random(n_map) < 0.2                               # near-duplicate descriptors of another frame line: ratio test
+    mdesc[dup] = desc[(src[dup] + 1) % n_frame]
+    level = np.clip(octave[src] + rng.integers(-1, 2, n_map), 0, n_levels - 1).astype(np.int32)
+    mp = dict(skip=(rng.random(n_map) < 0.1).astype(np.uint8), level=level, view_cos=rng.uniform(0.99, 1.0, n_map).astype(np.float32), proj=proj,
+              desc=np.ascontiguousarray(mdesc), has_obs=(rng.random(n_map) < 0.7).astype(np.uint8))
+    return frame, mp

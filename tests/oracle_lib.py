@@ -314,3 +314,18 @@ def extract_line_segments(gray: np.ndarray, max_lines: int = 40):
     kl, lf = np.zeros(cap, KEYLINE_DTYPE), np.zeros((cap, 3))
     n = L.orc_extract_line_segments(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], max_lines, kl.ctypes.data, lf.ctypes.data, cap)
     return kl[:n].copy(), lf[:n].copy()
+
+
+def line_search_by_projection(frame: dict, map_lines: dict, th: float, nnratio: float):
+    """Oracle LSDmatcher::SearchByProjection(Frame&, vector<MapLine*>&, th).  Same dict layout as planarslam_b200.matcher.LSDmatcher."""
+    L = lib()
+    L.orc_line_search_by_projection.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p]
+    f = {k: np.ascontiguousarray(v) for k, v in frame.items()}
+    m = {k: np.ascontiguousarray(v) for k, v in map_lines.items()}
+    nf, nm = len(f["angle"]), len(m["level"])
+    assigned = np.full(max(nf, 1), -1, np.int32)
+    n = L.orc_line_search_by_projection(nf, f["pt"].ctypes.data, f["angle"].ctypes.data, f["octave"].ctypes.data, f["desc"].ctypes.data,
+                                        f["has_obs"].ctypes.data, f["scale_factors"].ctypes.data, len(f["scale_factors"]), nm, m["skip"].ctypes.data,
+                                        m["level"].ctypes.data, m["view_cos"].ctypes.data, m["proj"].ctypes.data, m["desc"].ctypes.data,
+                                        m["has_obs"].ctypes.data, th, nnratio, assigned.ctypes.data)
+    return n, assigned[:nf]
