@@ -338,6 +338,17 @@ int pslam_line_search_by_projection(pslam_ctx* ctx, int n_frame_lines, const flo
                                     const int32_t* level, const float* view_cos, const float* proj, const uint8_t* map_desc,
                                     const uint8_t* map_has_obs, float th, float nnratio, int32_t* assigned);
 
+/* Replaces  int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches)
+ *           include/ORBmatcher.h:53, src/ORBmatcher.cc:160-292.
+ * Both sides: ORB descriptors [n][32], key-point angles (key frame: mvKeysUn, frame: mvKeys) and the DBoW2 FeatureVector as CSR
+ * (node ids ascending like the std::map, offsets, feature indices in insertion order); kf_has_mp[i] = the key frame's
+ * map point i exists and is not bad.  The DBoW2 transform that builds the feature vectors stays on the host.
+ * match[j] = key-frame feature whose map point the call stores into vpMapPointMatches[j] (-1: NULL).  Returns nmatches. */
+int pslam_search_by_bow(pslam_ctx* ctx, int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_mp, int kf_nodes,
+                        const int32_t* kf_node_id, const int32_t* kf_node_off, const int32_t* kf_node_feat, int n_f, const uint8_t* f_desc,
+                        const float* f_angle, int f_nodes, const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat,
+                        float nnratio, int check_orientation, int32_t* match);
+
 #ifdef __cplusplus
 }
 #endif

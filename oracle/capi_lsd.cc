@@ -51,3 +51,13 @@ extern "C" int orc_line_search_by_projection(int nf, const float* pt, const floa
     M.n = nm; M.skip = skip; M.level = level; M.view_cos = view_cos; M.proj = proj; M.desc = mdesc; M.has_obs = m_has_obs;
     return oracle::line_search_by_projection(F, M, th, nnratio, assigned);
 }
+
+#include "bow.h"
+extern "C" int orc_search_by_bow(int nkf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_mp, int kf_nodes, const int32_t* kf_node_id,
+                                 const int32_t* kf_node_off, const int32_t* kf_node_feat, int nf, const uint8_t* f_desc, const float* f_angle, int f_nodes,
+                                 const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat, float nnratio, int check_ori, int32_t* match) {
+    oracle::BowSide K, F;
+    K.n = nkf; K.desc = kf_desc; K.angle = kf_angle; K.n_nodes = kf_nodes; K.node_id = kf_node_id; K.node_off = kf_node_off; K.node_feat = kf_node_feat;
+    F.n = nf; F.desc = f_desc; F.angle = f_angle; F.n_nodes = f_nodes; F.node_id = f_node_id; F.node_off = f_node_off; F.node_feat = f_node_feat;
+    return oracle::search_by_bow(K, kf_has_mp, F, nnratio, check_ori != 0, match);
+}

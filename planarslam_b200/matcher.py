@@ -139,3 +139,19 @@ class LSDmatcher:
         if n < 0:
             self.ctx.check(n)
         return n, assigned[:nf]
+
+
+def search_by_bow(ctx: Context, kf: dict, frame: dict, nnratio: float = 0.7, check_orientation: bool = True):
+    """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF, F, vpMapPointMatches).  kf / frame: desc [n][32] u8, angle [n] f32, node_id,
+    node_off, node_feat i32 (DBoW2 FeatureVector as CSR); kf additionally has_mp [n] u8.  Returns (nmatches, match [n_frame])."""
+    k = {a: np.ascontiguousarray(b) for a, b in kf.items()}
+    f = {a: np.ascontiguousarray(b) for a, b in frame.items()}
+    nf = len(f["angle"])
+    match = np.full(max(nf, 1), -1, np.int32)
+    n = ctx.L.pslam_search_by_bow(ctx.h, len(k["angle"]), k["desc"].ctypes.data, k["angle"].ctypes.data, k["has_mp"].ctypes.data, len(k["node_id"]),
+                                  k["node_id"].ctypes.data, k["node_off"].ctypes.data, k["node_feat"].ctypes.data, nf, f["desc"].ctypes.data,
+                                  f["angle"].ctypes.data, len(f["node_id"]), f["node_id"].ctypes.data, f["node_off"].ctypes.data,
+                                  f["node_feat"].ctypes.data, nnratio, 1 if check_orientation else 0, match.ctypes.data)
+    if n < 0:
+        ctx.check(n)
+    return n, match[:nf]

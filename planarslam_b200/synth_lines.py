@@ -29,3 +29,33 @@ def make_line_search(seed: int, n_frame: int = 40, n_map: int = 120, n_levels: i
     mp = dict(skip=(rng.random(n_map) < 0.1).astype(np.uint8), level=level, view_cos=rng.uniform(0.99, 1.0, n_map).astype(np.float32), proj=proj,
               desc=np.ascontiguousarray(mdesc), has_obs=(rng.random(n_map) < 0.7).astype(np.uint8))
     return frame, mp
+
+
+def make_bow_pair(seed: int, n_kf: int = 1000, n_f: int = 1000, n_nodes: int = 300, shared: float = 0.7):
+    """A key frame and a frame for ORBmatcher::SearchByBoW: `shared` of the frame features are noisy copies of key-frame features
+    (same vocabulary node, rotated by a common in-plane angle plus noise), the rest is clutter; feature vectors as CSR."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 9176 + 3))
+    kf_desc = rng.integers(0, 256, (n_kf, 32), dtype=np.uint8)
+    kf_node = rng.integers(0, n_nodes, n_kf)
+    kf_angle = rng.uniform(0, 360, n_kf).astype(np.float32)
+    src = rng.integers(0, n_kf, n_f)
+    is_copy = rng.random(n_f) < shared
+    f_desc = rng.integers(0, 256, (n_f, 32), dtype=np.uint8)
+    flips = rng.random((n_f, 256)) < rng.choice([0.02, 0.06, 0.15], n_f)[:, None]
+    f_desc[is_copy] = kf_desc[src[is_copy]] ^ np.packbits(flips, axis=1)[is_copy]
+    f_node = np.where(is_copy, kf_node[src], rng.integers(0, n_nodes + 40, n_f))
+    rot = 17.0
+    f_angle = np.where(is_copy, (kf_angle[src] - rot + rng.normal(0, 4, n_f)) % 360, rng.uniform(0, 360, n_f)).astype(np.float32)
+    wrong = is_copy & (rng.random(n_f) < 0.1)
+    f_angle[wrong] = rng.uniform(0, 360, int(wrong.sum())).astype(np.float32)          # inconsistent rotation: removed by the histogram
+
+    def csr(node):
+        ids = np.unique(node)
+        order = np.argsort(node, kind="stable")
+        counts = np.array([(node == i).sum() for i in ids])
+        return ids.astype(np.int32), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), order.astype(np.int32)
+    kid, koff, kfeat = csr(kf_node)
+    fid, foff, ffeat = csr(f_node)
+    kf = dict(desc=kf_desc, angle=kf_angle, has_mp=(rng.random(n_kf) < 0.8).astype(np.uint8), node_id=kid, node_off=koff, node_feat=kfeat)
+    fr = dict(desc=np.ascontiguousarray(f_desc), angle=f_angle, node_id=fid, node_off=foff, node_feat=ffeat)
+    return kf, fr

@@ -329,3 +329,19 @@ def line_search_by_projection(frame: dict, map_lines: dict, th: float, nnratio: 
                                         m["level"].ctypes.data, m["view_cos"].ctypes.data, m["proj"].ctypes.data, m["desc"].ctypes.data,
                                         m["has_obs"].ctypes.data, th, nnratio, assigned.ctypes.data)
     return n, assigned[:nf]
+
+
+def search_by_bow(kf: dict, frame: dict, nnratio: float = 0.7, check_orientation: bool = True):
+    """Oracle ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...).  Same dict layout as planarslam_b200.matcher.search_by_bow."""
+    L = lib()
+    L.orc_search_by_bow.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    k = {a: np.ascontiguousarray(b) for a, b in kf.items()}
+    f = {a: np.ascontiguousarray(b) for a, b in frame.items()}
+    nf = len(f["angle"])
+    match = np.full(max(nf, 1), -1, np.int32)
+    n = L.orc_search_by_bow(len(k["angle"]), k["desc"].ctypes.data, k["angle"].ctypes.data, k["has_mp"].ctypes.data, len(k["node_id"]), k["node_id"].ctypes.data,
+                            k["node_off"].ctypes.data, k["node_feat"].ctypes.data, nf, f["desc"].ctypes.data, f["angle"].ctypes.data, len(f["node_id"]),
+                            f["node_id"].ctypes.data, f["node_off"].ctypes.data, f["node_feat"].ctypes.data, nnratio, 1 if check_orientation else 0,
+                            match.ctypes.data)
+    return n, match[:nf]
