@@ -412,8 +412,14 @@ def main():
     for v in per_kernel.values():
         v["share"] = round(v["ms_total"] / tot, 4)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_total"])
+    # DRAM bytes per frame of the dominant kernels from the committed `ncu --set full` capture (profiles/r1_ncu_full_summary.csv,
+    # dram__bytes_read.sum + dram__bytes_write.sum at 296 frames per launch), scaled to this run's frames per launch
+    NCU_DRAM_BYTES_PER_FRAME = {"lsd_regions": (7.700881e9 + 0.565746e9) / 296, "peac_cluster": (0.603116e9 + 0.338629e9) / 296,
+                                "peac_flood": (4.953115e9 + 1.131992e9) / 296}
+    traffic = NCU_DRAM_BYTES_PER_FRAME.get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 6), "traffic": None, "peak_kind": peak_kind,
+                "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 6),
+                "traffic": int(traffic * FRAMES_PER_STEP / per_kernel[dom]["launches"]) if traffic else None, "peak_kind": peak_kind,
                 "note": "serial-order kernels (quadtree, AHC, PEAC / LSD region growing, LM) run one warp/CTA per frame: latency-bound, see DESIGN.md",
                 "per_kernel": per_kernel}
 

@@ -13,7 +13,7 @@ struct LsdBuffers {
     LsdGeom g;
     int max_batch = 0, last_n = 0, max_lines_cap = 0;
     int16_t *d_ix = nullptr, *d_ax = nullptr, *d_iy = nullptr, *d_ay = nullptr;
-    float2* d_lut = nullptr;
+    float2* d_lut = nullptr; double* d_lgamma = nullptr;
     uint8_t* d_gray = nullptr;        // staging for the host-pointer entry points
     uint8_t* d_scaled = nullptr; LsdRec* d_rec = nullptr; int32_t* d_smax = nullptr;
     uint8_t* d_used = nullptr; uint32_t* d_reg = nullptr; uint32_t* d_order = nullptr; int32_t* d_norder = nullptr;
@@ -88,9 +88,21 @@ int lsd_alloc(pslam_ctx* c) {
             const float af = (float)ang;
             lut[(size_t)(gx + 510) * 1021 + (gy + 510)] = make_float2(std::cos(af), std::sin(af));
         }
+    // log_gamma(i), i = 0 .. LSD_LGAMMA_N - 1, with the reference's two approximations (lsd.cpp log_gamma_lanczos / _windschitl)
+    std::vector<double> lgam(LSD_LGAMMA_N, 0.0);
+    for (int i = 1; i < LSD_LGAMMA_N; ++i) {
+        const double x = (double)i;
+        if (x > 15.0) lgam[i] = 0.918938533204673 + (x - 0.5) * std::log(x) - x + 0.5 * x * std::log(x * std::sinh(1 / x) + 1 / (810.0 * std::pow(x, 6.0)));
+        else {
+            static const double q[7] = {75122.6331530, 80916.6278952, 36308.2951477, 8687.24529705, 1168.92649479, 83.8676043424, 2.50662827511};
+            double a = (x + 0.5) * std::log(x + 5.5) - (x + 5.5), b = 0;
+            for (int n = 0; n < 7; ++n) { a -= std::log(x + double(n)); b += q[n] * std::pow(x, double(n)); }
+            lgam[i] = a + std::log(b);
+        }
+    }
     const size_t npx = (size_t)g.W * g.H, nb = (size_t)B.max_batch;
 #define LA(ptr, bytes) do { const int rc_ = check_cuda(c, cudaMalloc((void**)&(ptr), (bytes)), "cudaMalloc(lsd)"); if (rc_ != PSLAM_OK) { c->lsd = Bp; lsd_free(c); return rc_; } } while (0)
-    LA(B.d_ix, g.W * 2); LA(B.d_ax, g.W * 2); LA(B.d_iy, g.H * 2); LA(B.d_ay, g.H * 2); LA(B.d_lut, lut.size() * sizeof(float2));
+    LA(B.d_ix, g.W * 2); LA(B.d_ax, g.W * 2); LA(B.d_iy, g.H * 2); LA(B.d_ay, g.H * 2); LA(B.d_lut, lut.size() * sizeof(float2)); LA(B.d_lgamma, LSD_LGAMMA_N * 8);
     LA(B.d_gray, nb * g.w * g.h); LA(B.d_scaled, nb * npx); LA(B.d_rec, nb * npx * sizeof(LsdRec)); LA(B.d_smax, nb * 4);
     LA(B.d_used, nb * npx); LA(B.d_reg, nb * npx * 4); LA(B.d_order, nb * npx * 4); LA(B.d_norder, nb * 4);
     LA(B.d_cands, nb * g.cand_cap * 12 * 8); LA(B.d_cand_nfa, nb * g.cand_cap * 8); LA(B.d_ncand, nb * 4);
@@ -102,6 +114,8 @@ int lsd_alloc(pslam_ctx* c) {
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_iy, iy.data(), g.H * 2, cudaMemcpyHostToDevice, st));
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_ay, ay.data(), g.H * 2, cudaMemcpyHostToDevice, st));
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_lut, lut.data(), lut.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(B.d_lgamma, lgam.data(), LSD_LGAMMA_N * 8, cudaMemcpyHostToDevice, st));
+    g.lgamma_tab = B.d_lgamma;
     PSLAM_CUDA(c, cudaStreamSynchronize(st));
     c->lsd = Bp;
     return PSLAM_OK;
@@ -110,7 +124,7 @@ int lsd_alloc(pslam_ctx* c) {
 void lsd_free(pslam_ctx* c) {
     if (!c->lsd) return;
     LsdBuffers& B = *c->lsd;
-    for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_rec,
+    for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_rec,
                     (void*)B.d_smax, (void*)B.d_used, (void*)B.d_reg, (void*)B.d_order, (void*)B.d_norder, (void*)B.d_segs, (void*)B.d_wpn,
                     (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl})
         if (p) cudaFree(p);
