@@ -231,6 +231,16 @@ def main():
     # are placed first and the bulk-parallel ORB / pose kernels fill the remaining issue slots.
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)]
     ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(4)]       # one context (= one stream) per stage family
+    # PSLAM_LSD_STREAM=peac puts the two latency-bound one-warp-per-frame chains (PEAC, LSD) on one stream: their CTAs compete for
+    # the same register file, and running them back to back avoids half-resident waves of both
+    mode = os.environ.get("PSLAM_LSD_STREAM", "peac")
+    if mode == "peac":
+        streams[3] = streams[1]
+    elif mode == "one":
+        streams[0] = streams[2] = streams[3] = streams[1]
+    elif mode == "two":                     # bulk-parallel families (ORB, pose) on one stream, serial-order families (PEAC, LSD) on the other
+        streams[2] = streams[0]
+        streams[3] = streams[1]
     for c, st in zip(ctxs, streams):
         c.set_stream(st.cuda_stream)
     c_orb, c_peac, c_pose, c_lsd = ctxs

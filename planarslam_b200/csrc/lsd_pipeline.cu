@@ -4,6 +4,8 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
+#include <string>
 
 #include "lsd_kernels.cuh"
 
@@ -153,8 +155,8 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
                                                                         B.d_status));
     if (refine >= 2) {
         // grid.x covers the candidate capacity; warps beyond a frame's candidate count exit at once
-        const dim3 gv((g.cand_cap + 3) / 4, nframes);
-        PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 128, 0, st>>>(g, B.d_rec, B.d_cands, B.d_ncand, B.d_cand_nfa));
+        const dim3 gv((g.cand_cap + 63) / 64, nframes);
+        PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 64, 0, st>>>(g, B.d_rec, B.d_cands, B.d_ncand, B.d_cand_nfa));
     }
     PSLAM_LAUNCH(c, "lsd_emit", k_lsd_emit<<<nframes, 256, 0, st>>>(g, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_segs, B.d_wpn, B.d_nsegs, B.d_status));
     PSLAM_CUDA(c, cudaGetLastError());
