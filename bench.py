@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = one pass of the hot path over one batch (1024 by default) of synthetic 640x480 RGB-D frames (seeded "room corner"
-sequence, planarslam_b200/synth.py).  Frames are independent units, so ranks shard them with no data-path
+A "step" = one pass of the hot path over 7104 synthetic 640x480 RGB-D frames (seeded "room corner" sequence,
+planarslam_b200/synth.py): four library calls of 1776 frames for ORB / PEAC / PoseOptimization and three of 2368 for LSD, so that
+every call of a one-warp-per-frame kernel is exactly one resident wave.  Frames are independent units, so ranks shard them with no data-path
 collective (weak scaling: every rank processes FRAMES_PER_STEP frames per step).
 
 Prints ONE JSON line on rank 0 (see DESIGN.md §measurement for every field):
@@ -38,8 +39,11 @@ W, H = 640, 480
 # 1776 on a 148-SM B200), set in main().  1776 frames = 1.6 GB of gray+depth input >> 126 MB L2.
 SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "0"))
 DEFAULT_WAVE = 1776                                            # 148 SMs x 12 resident clustering CTAs
-SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "1"))         # library calls per step
+SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "4"))         # ORB / PEAC / pose library calls per step (LSD takes the whole step in one call:
+                                                               # its one-warp-per-frame kernel needs 32 frames per SM in flight, PEAC clustering fits 12)
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
+LSD_SUBS = int(os.environ.get("PSLAM_LSD_SUBS", "3"))          # LSD calls per step: 4 x 1776 = 3 x 2368 frames, i.e. every LSD call is exactly one wave of its
+                                                               # one-warp-per-frame kernel (16 resident CTAs per SM x 148), every PEAC call one wave of the clustering kernel (12 x 148)
 DISTINCT_FRAMES = 16      # rendered once (CPU, ~0.4 s each) and tiled with a per-copy intensity offset
 
 # Algorithmic bytes per 640x480 frame of each kernel family (restated in DESIGN.md §kernels)
@@ -219,6 +223,7 @@ def main():
         SUB_BATCH = int(probe.L.pslam_peac_wave_frames(probe.h)) or DEFAULT_WAVE
         del probe
     FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
+    assert LSD_SUBS <= SUBS_PER_STEP
 
     gray, depth = make_frames()
     reps = (FRAMES_PER_STEP + DISTINCT_FRAMES - 1) // DISTINCT_FRAMES
@@ -230,7 +235,7 @@ def main():
     # ORB, PEAC, pose.  The PEAC chain (one warp per frame, latency-bound) is the critical path: high priority, so its CTAs
     # are placed first and the bulk-parallel ORB / pose kernels fill the remaining issue slots.
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)]
-    ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(4)]       # one context (= one stream) per stage family
+    ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(3)] + [Context(W, H, (FRAMES_PER_STEP + LSD_SUBS - 1) // LSD_SUBS, device=local_rank)]   # one context per stage family
     # PSLAM_LSD_STREAM=peac puts the two latency-bound one-warp-per-frame chains (PEAC, LSD) on one stream: their CTAs compete for
     # the same register file, and running them back to back avoids half-resident waves of both
     mode = os.environ.get("PSLAM_LSD_STREAM", "peac")
@@ -260,8 +265,8 @@ def main():
     d_npl = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
     d_midx = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
     d_moff = torch.empty((SUB_BATCH, maxp + 1), dtype=torch.int32, device=dev)
-    d_kl = torch.empty((SUB_BATCH, MAX_LINES, KEYLINE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    d_lf = torch.empty((SUB_BATCH, MAX_LINES, 3), dtype=torch.float64, device=dev)
+    d_kl = torch.empty((FRAMES_PER_STEP, MAX_LINES, KEYLINE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_lf = torch.empty((FRAMES_PER_STEP, MAX_LINES, 3), dtype=torch.float64, device=dev)
     d_nkl = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
     h_gray = torch.from_numpy(gray_step).pin_memory()
     h_depth = torch.from_numpy(depth_step.view(np.int16)).pin_memory()
@@ -277,9 +282,9 @@ def main():
     h_labels = pinned((SUB_BATCH, H * W), np.int32)
     h_planes = pinned((SUB_BATCH, maxp), PLANE_DTYPE)
     h_npl = pinned((SUB_BATCH,), np.int32)
-    h_kl = pinned((SUB_BATCH, MAX_LINES), KEYLINE_DTYPE)
-    h_lf = pinned((SUB_BATCH, MAX_LINES, 3), np.float64)
-    h_nkl = pinned((SUB_BATCH,), np.int32)
+    h_kl = pinned((FRAMES_PER_STEP, MAX_LINES), KEYLINE_DTYPE)
+    h_lf = pinned((FRAMES_PER_STEP, MAX_LINES, 3), np.float64)
+    h_nkl = pinned((FRAMES_PER_STEP,), np.int32)
     # pose problems: one per frame of a sub-batch (the correspondences a tracker would hand over), packed + uploaded once
     base_probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(16)]
     probs = [base_probs[k % 16] for k in range(SUB_BATCH)]
@@ -296,9 +301,13 @@ def main():
         c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
                                                 d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
 
-    def dev_lsd(o):
-        c_lsd.check(L.pslam_lines_extract_batch_dev(c_lsd.h, d_gray[o].data_ptr(), SUB_BATCH, MAX_LINES, d_kl.data_ptr(), d_lf.data_ptr(),
-                                                    d_nkl[o:].data_ptr()))
+    LSD_BATCH = (FRAMES_PER_STEP + LSD_SUBS - 1) // LSD_SUBS
+
+    def dev_lsd(j=None):
+        for q in (range(LSD_SUBS) if j is None else [j]):
+            o, n = q * LSD_BATCH, min(LSD_BATCH, FRAMES_PER_STEP - q * LSD_BATCH)
+            c_lsd.check(L.pslam_lines_extract_batch_dev(c_lsd.h, d_gray[o].data_ptr(), n, MAX_LINES, d_kl[o].data_ptr(), d_lf[o].data_ptr(),
+                                                        d_nkl[o:].data_ptr()))
 
     def steps_dev(nsteps):
         """nsteps passes over the batch.  The three stage families are independent per frame, so each runs its own
@@ -310,10 +319,10 @@ def main():
         for _ in range(nsteps):
             for s in range(SUBS_PER_STEP):
                 o = s * SUB_BATCH
+                if "lsd" in STAGES and s < LSD_SUBS:
+                    dev_lsd(s)
                 if "peac" in STAGES:
                     dev_peac(o)
-                if "lsd" in STAGES:
-                    dev_lsd(o)
                 if "orb" in STAGES:
                     dev_orb(o)
                 if "pose" in STAGES:
@@ -347,9 +356,10 @@ def main():
                 opt.PoseOptimizationBatch(probs)
         def e_lsd():
             torch.cuda.set_device(local_rank)
-            for s in range(SUBS_PER_STEP):
-                c_lsd.check(L.pslam_lines_extract_batch(c_lsd.h, h_gray[s * SUB_BATCH].data_ptr(), SUB_BATCH, MAX_LINES, h_kl.ctypes.data,
-                                                        h_lf.ctypes.data, h_nkl.ctypes.data))
+            for q in range(LSD_SUBS):
+                o, n = q * LSD_BATCH, min(LSD_BATCH, FRAMES_PER_STEP - q * LSD_BATCH)
+                c_lsd.check(L.pslam_lines_extract_batch(c_lsd.h, h_gray[o].data_ptr(), n, MAX_LINES, h_kl[o:].ctypes.data, h_lf[o:].ctypes.data,
+                                                        h_nkl[o:].ctypes.data))
         fns = [fn for nm, fn in (("peac", e_peac), ("lsd", e_lsd), ("orb", e_orb), ("pose", e_pose)) if nm in STAGES]
         for f in [pool.submit(fn) for fn in fns]:
             f.result()
@@ -401,12 +411,12 @@ def main():
     # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
     # one stage family at a time, so a launch's duration is not inflated by kernels of the other two streams
     rep = {}
-    for nm, c, fn in (("orb", c_orb, lambda: dev_orb(0)), ("lsd", c_lsd, lambda: dev_lsd(0)), ("peac", c_peac, lambda: dev_peac(0)),
+    for nm, c, fn in (("orb", c_orb, lambda: dev_orb(0)), ("lsd", c_lsd, dev_lsd), ("peac", c_peac, lambda: dev_peac(0)),
                       ("pose", c_pose, opt.run_packed)):
         if nm not in STAGES:
             continue
         c.profile(True)
-        for _ in range(SUBS_PER_STEP):
+        for _ in range(1 if nm == "lsd" else SUBS_PER_STEP):       # dev_lsd() without argument runs its LSD_SUBS calls
             fn()
         torch.cuda.synchronize(dev)
         rep.update(c.profile_report())

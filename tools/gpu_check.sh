@@ -3,11 +3,12 @@
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -25 | cut -c1-1500
 timeout 600 python bench.py --steps 5 --warmup 3 2>gpurun_out/bench_err.log | tail -1 > gpurun_out/bench_latest.log
-PSLAM_STAGES=orb,peac,pose timeout 600 python bench.py --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_nolsd.log
+if [ -n "$WITH_ABLATION" ]; then PSLAM_STAGES=orb,peac,pose timeout 600 python bench.py --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_nolsd.log; fi
 tail -5 gpurun_out/bench_err.log
 python - <<PY
 import json
-for f in ("gpurun_out/bench_latest.log","gpurun_out/bench_nolsd.log"):
+import os
+for f in [x for x in ("gpurun_out/bench_latest.log","gpurun_out/bench_nolsd.log") if os.path.exists(x)]:
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
