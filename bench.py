@@ -226,10 +226,15 @@ def main():
     assert LSD_SUBS <= SUBS_PER_STEP
 
     gray, depth = make_frames()
-    reps = (FRAMES_PER_STEP + DISTINCT_FRAMES - 1) // DISTINCT_FRAMES
-    # copies differ by a small intensity offset (0..21 grey levels): every frame keeps the full content of a rendered frame
-    gray_step = np.concatenate([np.clip(gray.astype(np.int16) + 3 * (r % 8), 0, 255).astype(np.uint8) for r in range(reps)])[:FRAMES_PER_STEP]
-    depth_step = np.concatenate([depth for _ in range(reps)])[:FRAMES_PER_STEP]
+    # the step's frames are built once, directly in page-locked host memory (the buffers the end-to-end leg hands to the ABI): 16 rendered
+    # frames tiled with a small intensity offset (0..21 grey levels) so that every copy keeps the full content of a rendered frame
+    h_gray = torch.empty((FRAMES_PER_STEP, H, W), dtype=torch.uint8).pin_memory()
+    h_depth = torch.empty((FRAMES_PER_STEP, H, W), dtype=torch.int16).pin_memory()      # uint16 bits
+    hg, hd = h_gray.numpy(), h_depth.numpy()
+    for o in range(0, FRAMES_PER_STEP, DISTINCT_FRAMES):
+        n = min(DISTINCT_FRAMES, FRAMES_PER_STEP - o)
+        hg[o:o + n] = np.clip(gray[:n].astype(np.int16) + 3 * ((o // DISTINCT_FRAMES) % 8), 0, 255).astype(np.uint8)
+        hd[o:o + n] = depth[:n].view(np.int16)
     dev = torch.device("cuda", local_rank)
     main = torch.cuda.current_stream(dev)
     # ORB, PEAC, pose.  The PEAC chain (one warp per frame, latency-bound) is the critical path: high priority, so its CTAs
@@ -255,8 +260,8 @@ def main():
     maxp = c_peac.L.pslam_peac_max_planes(c_peac.h)
     L = c_orb.L
 
-    d_gray = torch.from_numpy(gray_step).to(dev)                       # [FRAMES_PER_STEP, H, W] resident in HBM
-    d_depth = torch.from_numpy(depth_step.view(np.int16)).to(dev)      # uint16 bits
+    d_gray = h_gray.to(dev)                                            # [FRAMES_PER_STEP, H, W] resident in HBM
+    d_depth = h_depth.to(dev)
     d_kps = torch.empty((SUB_BATCH, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.empty((SUB_BATCH, cap, 32), dtype=torch.uint8, device=dev)
     d_n = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
@@ -268,8 +273,6 @@ def main():
     d_kl = torch.empty((FRAMES_PER_STEP, MAX_LINES, KEYLINE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     d_lf = torch.empty((FRAMES_PER_STEP, MAX_LINES, 3), dtype=torch.float64, device=dev)
     d_nkl = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
-    h_gray = torch.from_numpy(gray_step).pin_memory()
-    h_depth = torch.from_numpy(depth_step.view(np.int16)).pin_memory()
     def pinned(shape, dtype):          # page-locked host result buffers (what a replay driver would hand to the ABI)
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         t = torch.empty(n, dtype=torch.uint8).pin_memory()

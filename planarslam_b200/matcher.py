@@ -86,17 +86,6 @@ class ORBmatcher:
         return len(good), [(int(i), int(idx[i, 0]), int(dist[i, 0])) for i in good]
 
 
-class LSDmatcher:
-    def __init__(self, ctx: Context | None = None):
-        self.orb = ORBmatcher(ctx=ctx)
-
-    def SearchByDescriptor(self, kf_desc: np.ndarray, frame_desc: np.ndarray):
-        """knn-2 of the key frame's line descriptors in the frame + ratio test 1/1.5 (src/LSDmatcher.cpp:256-276)."""
-        idx, dist, _ = self.orb.knn2(kf_desc, frame_desc)
-        keep = [(i, int(idx[i, 0])) for i in range(len(idx)) if idx[i, 1] >= 0 and dist[i, 0] / max(dist[i, 1], 1e-9) < 1.0 / 1.5]
-        return len(keep), keep
-
-
 class PlaneMatcher:
     """PlaneMatcher(dTh, aTh, verTh, parTh), include/PlaneMatcher.h:16-30."""
 
@@ -123,6 +112,14 @@ class LSDmatcher:
     def __init__(self, nnratio: float = 0.6, ctx: Context | None = None):
         self.nnratio = nnratio
         self.ctx = ctx or Context(640, 480, 1)
+        self.orb = ORBmatcher(ctx=self.ctx)
+
+    # int SearchByDescriptor(KeyFrame* pKF, Frame& F, std::vector<MapLine*>& vpMapLineMatches)
+    def SearchByDescriptor(self, kf_desc: np.ndarray, frame_desc: np.ndarray):
+        """knn-2 of the key frame's line descriptors in the frame + ratio test 1/1.5 (src/LSDmatcher.cpp:256-276)."""
+        idx, dist, _ = self.orb.knn2(kf_desc, frame_desc)
+        keep = [(i, int(idx[i, 0])) for i in range(len(idx)) if idx[i, 1] >= 0 and dist[i, 0] / max(dist[i, 1], 1e-9) < 1.0 / 1.5]
+        return len(keep), keep
 
     # int SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, const float th = 3)
     def SearchByProjection(self, frame: dict, map_lines: dict, th: float = 3.0):
