@@ -349,6 +349,16 @@ int pslam_search_by_bow(pslam_ctx* ctx, int n_kf, const uint8_t* kf_desc, const 
                         const float* f_angle, int f_nodes, const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat,
                         float nnratio, int check_orientation, int32_t* match);
 
+/* Replaces  DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
+ *           Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1125-1252, called by Frame::ComputeBoW / KeyFrame::ComputeBoW
+ *           (src/KeyFrame.cc:66-76: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4); TF_IDF weights, L1 norm).
+ * Vocabulary as flat arrays in DBoW2's node-id order: 32-byte node descriptors, children as CSR, word id and weight per node
+ * (leaves).  Outputs (caller-allocated, n entries each, node_off n + 1): BowVector as (word_id ascending, value) pairs and the
+ * FeatureVector as CSR (node_id ascending, node_off, node_feat in insertion order); counts[0] = words, counts[1] = nodes. */
+int pslam_bow_transform(pslam_ctx* ctx, int n_nodes, int L, const uint8_t* voc_desc, const int32_t* child_off, const int32_t* child_id,
+                        const int32_t* voc_word_id, const double* voc_weight, const uint8_t* features, int n, int levelsup, int32_t* word_id,
+                        double* word_val, int32_t* node_id, int32_t* node_off, int32_t* node_feat, int32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

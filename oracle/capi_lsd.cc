@@ -61,3 +61,23 @@ extern "C" int orc_search_by_bow(int nkf, const uint8_t* kf_desc, const float* k
     F.n = nf; F.desc = f_desc; F.angle = f_angle; F.n_nodes = f_nodes; F.node_id = f_node_id; F.node_off = f_node_off; F.node_feat = f_node_feat;
     return oracle::search_by_bow(K, kf_has_mp, F, nnratio, check_ori != 0, match);
 }
+
+#include "bow_transform.h"
+// outputs sized by the caller: word_id / word_val [n], node_id [n], node_off [n + 1], node_feat [n], feat_word / feat_node [n]; counts[2] = {n_words, n_nodes}
+extern "C" void orc_bow_transform(int n_nodes, int L, const uint8_t* vdesc, const int32_t* child_off, const int32_t* child_id, const int32_t* vword,
+                                  const double* vweight, const uint8_t* features, int n, int levelsup, int32_t* word_id, double* word_val,
+                                  int32_t* node_id, int32_t* node_off, int32_t* node_feat, int32_t* feat_word, int32_t* feat_node, int32_t* counts) {
+    oracle::BowVocabulary V;
+    V.n_nodes = n_nodes; V.L = L; V.desc = vdesc; V.child_off = child_off; V.child_id = child_id; V.word_id = vword; V.weight = vweight;
+    oracle::BowResult R;
+    oracle::bow_transform(V, features, n, levelsup, R);
+    counts[0] = (int32_t)R.word_id.size(); counts[1] = (int32_t)R.node_id.size();
+    std::memcpy(word_id, R.word_id.data(), R.word_id.size() * 4); std::memcpy(word_val, R.word_val.data(), R.word_val.size() * 8);
+    std::memcpy(node_id, R.node_id.data(), R.node_id.size() * 4); std::memcpy(node_off, R.node_off.data(), R.node_off.size() * 4);
+    std::memcpy(node_feat, R.node_feat.data(), R.node_feat.size() * 4);
+    if (feat_word) std::memcpy(feat_word, R.feat_word.data(), (size_t)n * 4);
+    if (feat_node) std::memcpy(feat_node, R.feat_node.data(), (size_t)n * 4);
+}
+extern "C" double orc_bow_score_l1(const int32_t* id1, const double* v1, int n1, const int32_t* id2, const double* v2, int n2) {
+    return oracle::bow_score_l1(id1, v1, n1, id2, v2, n2);
+}

@@ -152,3 +152,22 @@ def search_by_bow(ctx: Context, kf: dict, frame: dict, nnratio: float = 0.7, che
     if n < 0:
         ctx.check(n)
     return n, match[:nf]
+
+
+def bow_transform(ctx: Context, voc: dict, features: np.ndarray, levelsup: int = 4) -> dict:
+    """ORBVocabulary::transform(vCurrentDesc, mBowVec, mFeatVec, levelsup).  voc: L, desc [nodes][32] u8, child_off, child_id, word_id i32, weight f64
+    (planarslam_b200.synth_lines.make_vocabulary builds synthetic ones).  Returns dict(word_id, word_val, node_id, node_off, node_feat)."""
+    f = np.ascontiguousarray(features, np.uint8)
+    n = len(f)
+    o = dict(word_id=np.zeros(max(n, 1), np.int32), word_val=np.zeros(max(n, 1)), node_id=np.zeros(max(n, 1), np.int32),
+             node_off=np.zeros(n + 1, np.int32), node_feat=np.zeros(max(n, 1), np.int32))
+    cnt = np.zeros(2, np.int32)
+    ctx.check(ctx.L.pslam_bow_transform(ctx.h, len(voc["word_id"]), voc["L"], voc["desc"].ctypes.data, voc["child_off"].ctypes.data,
+                                        voc["child_id"].ctypes.data, voc["word_id"].ctypes.data, voc["weight"].ctypes.data, f.ctypes.data, n, levelsup,
+                                        o["word_id"].ctypes.data, o["word_val"].ctypes.data, o["node_id"].ctypes.data, o["node_off"].ctypes.data,
+                                        o["node_feat"].ctypes.data, cnt.ctypes.data))
+    nw, nn = int(cnt[0]), int(cnt[1])
+    o["word_id"], o["word_val"] = o["word_id"][:nw], o["word_val"][:nw]
+    o["node_id"], o["node_off"] = o["node_id"][:nn], o["node_off"][:nn + 1]
+    o["node_feat"] = o["node_feat"][:int(o["node_off"][-1])] if nn else o["node_feat"][:0]
+    return o

@@ -59,3 +59,43 @@ def make_bow_pair(seed: int, n_kf: int = 1000, n_f: int = 1000, n_nodes: int = 3
     kf = dict(desc=kf_desc, angle=kf_angle, has_mp=(rng.random(n_kf) < 0.8).astype(np.uint8), node_id=kid, node_off=koff, node_feat=kfeat)
     fr = dict(desc=np.ascontiguousarray(f_desc), angle=f_angle, node_id=fid, node_off=foff, node_feat=ffeat)
     return kf, fr
+
+
+def make_vocabulary(seed: int, k: int = 10, L: int = 3, stop_frac: float = 0.05):
+    """A synthetic DBoW2 vocabulary tree (branching factor k, depth L) as flat arrays in node-id order: 32-byte node descriptors, children CSR,
+    word ids for the leaves (in creation order) and word weights (idf-like; a few zero = "stopped" words).  The real ORBvoc has k = 10, L = 6."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 31 + 11))
+    desc = [np.zeros(32, np.uint8)]
+    children = [[]]
+    level = [0]
+    frontier = [0]
+    for lv in range(1, L + 1):
+        nxt = []
+        for parent in frontier:
+            base = desc[parent]
+            for _ in range(k):
+                flips = np.packbits(rng.random(256) < (0.5 if lv == 1 else 0.12))
+                desc.append(base ^ flips if lv > 1 else rng.integers(0, 256, 32, dtype=np.uint8))
+                children.append([])
+                level.append(lv)
+                children[parent].append(len(desc) - 1)
+                nxt.append(len(desc) - 1)
+        frontier = nxt
+    n = len(desc)
+    word_id = np.full(n, -1, np.int32)
+    weight = np.zeros(n)
+    for w, leaf in enumerate(frontier):
+        word_id[leaf] = w
+        weight[leaf] = 0.0 if rng.random() < stop_frac else float(rng.uniform(0.5, 9.0))
+    child_off = np.concatenate([[0], np.cumsum([len(c) for c in children])]).astype(np.int32)
+    child_id = np.array([c for ch in children for c in ch], np.int32)
+    return dict(L=L, k=k, desc=np.ascontiguousarray(np.array(desc, np.uint8)), child_off=child_off, child_id=child_id, word_id=word_id, weight=weight,
+                leaves=np.array(frontier, np.int32))
+
+
+def make_features_for_vocabulary(seed: int, voc: dict, n: int = 1000):
+    """ORB-like descriptors: noisy copies of random leaf descriptors (so that several features fall into the same word / node)."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 77 + 1))
+    src = voc["leaves"][rng.integers(0, len(voc["leaves"]) // 3 + 1, n)]
+    flips = np.packbits(rng.random((n, 256)) < 0.08, axis=1)
+    return np.ascontiguousarray(voc["desc"][src] ^ flips)

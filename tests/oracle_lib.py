@@ -345,3 +345,31 @@ def search_by_bow(kf: dict, frame: dict, nnratio: float = 0.7, check_orientation
                             f["node_id"].ctypes.data, f["node_off"].ctypes.data, f["node_feat"].ctypes.data, nnratio, 1 if check_orientation else 0,
                             match.ctypes.data)
     return n, match[:nf]
+
+
+def bow_transform(voc: dict, features: np.ndarray, levelsup: int = 4):
+    """Oracle DBoW2 TemplatedVocabulary::transform (TF_IDF, L1).  Returns dict(word_id, word_val, node_id, node_off, node_feat, feat_word, feat_node)."""
+    L = lib()
+    L.orc_bow_transform.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 8
+    f = np.ascontiguousarray(features, np.uint8)
+    n = len(f)
+    o = dict(word_id=np.zeros(n, np.int32), word_val=np.zeros(n), node_id=np.zeros(n, np.int32), node_off=np.zeros(n + 1, np.int32),
+             node_feat=np.zeros(n, np.int32), feat_word=np.zeros(n, np.int32), feat_node=np.zeros(n, np.int32))
+    cnt = np.zeros(2, np.int32)
+    L.orc_bow_transform(len(voc["word_id"]), voc["L"], voc["desc"].ctypes.data, voc["child_off"].ctypes.data, voc["child_id"].ctypes.data,
+                        voc["word_id"].ctypes.data, voc["weight"].ctypes.data, f.ctypes.data, n, levelsup, o["word_id"].ctypes.data,
+                        o["word_val"].ctypes.data, o["node_id"].ctypes.data, o["node_off"].ctypes.data, o["node_feat"].ctypes.data,
+                        o["feat_word"].ctypes.data, o["feat_node"].ctypes.data, cnt.ctypes.data)
+    nw, nn = int(cnt[0]), int(cnt[1])
+    o["word_id"], o["word_val"] = o["word_id"][:nw], o["word_val"][:nw]
+    o["node_id"], o["node_off"] = o["node_id"][:nn], o["node_off"][:nn + 1]
+    o["node_feat"] = o["node_feat"][:o["node_off"][-1]] if nn else o["node_feat"][:0]
+    return o
+
+
+def bow_score_l1(a: dict, b: dict) -> float:
+    L = lib()
+    L.orc_bow_score_l1.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_bow_score_l1.restype = C.c_double
+    return float(L.orc_bow_score_l1(a["word_id"].ctypes.data, a["word_val"].ctypes.data, len(a["word_id"]), b["word_id"].ctypes.data,
+                                    b["word_val"].ctypes.data, len(b["word_id"])))
