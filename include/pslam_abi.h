@@ -312,6 +312,12 @@ typedef struct pslam_keyline {
 } pslam_keyline;
 
 int pslam_lsd_max_segments(const pslam_ctx* ctx);     /* segment capacity per frame of the calls below */
+/* Which pixels the NFA validation of LSD_REFINE_ADV counts inside a rectangle (LineSegmentDetectorImpl::rect_nfa, OpenCV
+ * imgproc lsd.cpp - reached from src/LSDextractor.cpp:16): 0 = the published LSD rectangle iterator (default; the variant the
+ * round-1 GPU parity runs validated), 1 = OpenCV 4.x's enumeration (pinned bit for bit against cv2 4.13 in the oracle; device
+ * code checked on the host only so far).  The environment variable PSLAM_LSD_RECT_ENUM=cv4 selects 1
+ * as the default of a new context. */
+int pslam_lsd_set_rect_enumeration(pslam_ctx* ctx, int mode);
 /* cv::LineSegmentDetector::detect on nframes frames: segs [nframes][cap][4] float (x1 y1 x2 y2), wpn [nframes][cap][3] double
  * (width, precision, log-NFA; -1 unless refine == 2), n [nframes].  PSLAM_E_CAPACITY when a frame has more than cap segments. */
 int pslam_lsd_detect_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int refine, float* segs, double* wpn, int cap, int32_t* n);

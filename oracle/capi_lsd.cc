@@ -4,9 +4,10 @@
 using namespace oracle;
 extern "C" {
 // segs: float[cap][4]; wpn: double[cap][3] (width, precision, log-NFA); returns the number of segments found
-int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, float* segs, double* wpn, int cap) {
+// rect_enum: 0 published LSD rectangle iterator, 1 cv2 4.13's enumeration (lsd.cc rect_nfa)
+int orc_lsd_detect_enum(const uint8_t* img, int w, int h, int stride, int refine, int rect_enum, float* segs, double* wpn, int cap) {
     std::vector<LsdSegment> out;
-    lsd_detect(Img8{img, w, h, stride}, refine, out);
+    lsd_detect(Img8{img, w, h, stride}, refine, out, rect_enum);
     const int n = (int)out.size();
     for (int i = 0; i < n && i < cap; ++i) {
         segs[4 * i] = out[i].x1; segs[4 * i + 1] = out[i].y1; segs[4 * i + 2] = out[i].x2; segs[4 * i + 3] = out[i].y2;
@@ -14,6 +15,10 @@ int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, flo
     }
     return n;
 }
+int orc_lsd_detect(const uint8_t* img, int w, int h, int stride, int refine, float* segs, double* wpn, int cap) {
+    return orc_lsd_detect_enum(img, w, h, stride, refine, 0, segs, wpn, cap);
+}
+int orc_lsd_cv4_spans(const double* rect, int W, int H, int32_t* rows, int cap) { return lsd_cv4_spans(rect, W, H, rows, cap); }
 // stage outputs for the GPU stage-parity tests: blurred [h][w] u8, scaled [sh][sw] u8, modgrad / angles [sh][sw] double,
 // order [(sw-1)(sh-1)] int32, region_id [sh][sw] int32.  Any pointer may be null.  Returns the number of segments.
 int orc_lsd_stages(const uint8_t* img, int w, int h, int stride, int refine, uint8_t* blurred, uint8_t* scaled, double* modgrad, double* angles,
@@ -31,13 +36,16 @@ int orc_lsd_stages(const uint8_t* img, int w, int h, int stride, int refine, uin
     return (int)out.size();
 }
 // keylines: KeyLine[cap] (68 bytes each), lf: double[cap][3]; returns the number kept
-int orc_extract_line_segments(const uint8_t* img, int w, int h, int stride, int max_lines, void* keylines, double* lf, int cap) {
+int orc_extract_line_segments_enum(const uint8_t* img, int w, int h, int stride, int max_lines, int rect_enum, void* keylines, double* lf, int cap) {
     std::vector<KeyLine> kl; std::vector<double> f;
-    extract_line_segments(Img8{img, w, h, stride}, max_lines, kl, f);
+    extract_line_segments(Img8{img, w, h, stride}, max_lines, kl, f, rect_enum);
     const int n = std::min((int)kl.size(), cap);
     static_assert(sizeof(KeyLine) == 68, "KeyLine layout");
     if (n) { std::memcpy(keylines, kl.data(), (size_t)n * sizeof(KeyLine)); std::memcpy(lf, f.data(), (size_t)n * 3 * 8); }
     return n;
+}
+int orc_extract_line_segments(const uint8_t* img, int w, int h, int stride, int max_lines, void* keylines, double* lf, int cap) {
+    return orc_extract_line_segments_enum(img, w, h, stride, max_lines, 0, keylines, lf, cap);
 }
 }
 

@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE ONLY — CPU oracle restating cv::LineSegmentDetector (OpenCV imgproc lsd.cpp), the KeyLine glue of
 // opencv_contrib's LSDDetector and LineSegment::ExtractLineSegment (see lsd.h for the map and the pinning status).
 #include "lsd.h"
+#include <cstdio>
+#include <cstdlib>
 #include "detmath.h"
 
 #include <algorithm>
@@ -104,6 +106,35 @@ inline double log_gamma_lanczos(double x) {
 }
 inline double log_gamma(double x) { return x > 15.0 ? log_gamma_windschitl(x) : log_gamma_lanczos(x); }
 
+// Row spans (y, first column, last column; clamped to the W x H image, empty rows skipped) of cv2 4.13's rect_nfa enumeration -
+// see the comment at Lsd::rect_count_cv4.
+template <class F>
+void rect_rows_cv4(double x1, double y1, double x2, double y2, double width, double dx, double dy, int W, int H, F&& emit) {
+    const double half = 0.5 * width, dyhw = dy * half, dxhw = half * dx;
+    const double cx[4] = {x1 - dyhw, x2 - dyhw, x2 + dyhw, x1 + dyhw};
+    const double cy[4] = {y1 + dxhw, y2 + dxhw, y2 - dxhw, y1 - dxhw};
+    int off = 0;
+    for (int i = 1; i < 4; ++i)
+        if (cy[i] < cy[off] || (cy[i] == cy[off] && cx[off] > cx[i])) off = i;
+    double vx[4], vy[4];
+    for (int q = 0; q < 4; ++q) { vx[q] = cx[(off + q) & 3]; vy[q] = cy[(off + q) & 3]; }
+    const int y0 = (int)std::ceil(vy[0]), c1 = (int)std::ceil(vy[1]), c2 = (int)std::ceil(vy[2]), c3 = (int)std::ceil(vy[3]);
+    const double s01 = c1 != y0 ? (vx[1] - vx[0]) / (vy[1] - vy[0]) : 0.0;
+    const double s12 = c2 != c1 ? (vx[2] - vx[1]) / (vy[2] - vy[1]) : 0.0;
+    const double s03 = c3 != y0 ? (vx[3] - vx[0]) / (vy[3] - vy[0]) : 0.0;
+    const double s32 = c3 != c2 ? (vx[2] - vx[3]) / (vy[2] - vy[3]) : 0.0;
+    for (int y = y0; y <= c2; ++y) {
+        if (y < 0 || y >= H) continue;
+        const double yd = (double)y;
+        const double left = y > c1 ? (yd - vy[1]) * s12 + vx[1] : (yd - vy[0]) * s01 + vx[0];
+        const double right = y >= c3 ? (yd - vy[3]) * s32 + vx[3] : (yd - vy[0]) * s03 + vx[0];
+        int xa = (int)std::ceil(left), xb = (int)right;       // x86 conversions: out-of-range -> INT_MIN, like the reference binary
+        if (xa < 0) xa = 0;
+        if (xb > W - 1) xb = W - 1;
+        if (xb >= xa) emit(y, xa, xb);
+    }
+}
+
 struct Lsd {
     int W = 0, H = 0;
     std::vector<uint8_t> scaled;
@@ -159,6 +190,7 @@ struct Lsd {
         reg.push_back({sx, sy, reg_angle, modgrad[(size_t)sy * W + sx]});
         double sn, cs;
         det_sincos(reg_angle, sn, cs);             // std::cos / std::sin in OpenCV; see detmath.h
+        if (libm_sincos) { cs = std::cos(reg_angle); sn = std::sin(reg_angle); }
         float sumdx = float(cs);
         float sumdy = float(sn);
         used[(size_t)sy * W + sx] = 1;
@@ -211,6 +243,7 @@ struct Lsd {
         const double theta = get_theta(reg, x, y, reg_angle, prec);
         double dx, dy;
         det_sincos(theta, dy, dx);                 // std::cos / std::sin in OpenCV; see detmath.h
+        if (libm_sincos) { dx = std::cos(theta); dy = std::sin(theta); }
         double l_min = 0, l_max = 0, w_min = 0, w_max = 0;
         for (size_t i = 0; i < reg.size(); ++i) {
             const double regdx = double(reg[i].x) - x, regdy = double(reg[i].y) - y;
@@ -333,15 +366,40 @@ struct Lsd {
         }
     }
 
-    // NOTE (pinning status): cv2 4.13's rect_nfa enumerates a slightly different pixel set than the published LSD
-    // rectangle iterator (measured through the returned log-NFA on controlled images: a few percent more points for
-    // oblique rectangles, one stray scan line for rectangles that touch the image border); that enumeration could not
-    // be reproduced without the OpenCV source.  The published iterator is used here.  Consequence: REFINE_NONE / REFINE_STD
-    // agree with cv2 bit for bit; with REFINE_ADV the accepted set differs for short, barely meaningful segments, while
-    // the 40 longest segments - all the reference consumes (src/LSDextractor.cpp:18-26) - agree (tests/test_oracle_lsd.py).
+    // cv2 4.13's rect_nfa enumeration (OpenCV >= 4.5.x imgproc lsd.cpp; no source in this image - recovered from the behaviour of the
+    // in-container cv2 build and pinned by tests/test_oracle_lsd.py on whole detections, log-NFA included): the four corners as
+    // doubles, rotated so that the first is the top one (smallest y, ties -> smallest x); rows from ceil(top.y) to ceil(bottom.y)
+    // INCLUSIVE; per row the left bound follows top -> v1 -> bottom (switching after row ceil(v1.y)), the right bound follows
+    // top -> v3 -> bottom (switching AT row ceil(v3.y)); an edge whose two ends round up to the same row has slope 0; columns from
+    // ceil(left) to trunc(right).  Points outside the image are not counted.
+    void rect_count_cv4(const Rect& r, int& n, int& k) const {
+        n = 0; k = 0;
+        rect_rows_cv4(r.x1, r.y1, r.x2, r.y2, r.width, r.dx, r.dy, W, H, [&](int y, int xa, int xb) {
+            for (int x = xa; x <= xb; ++x) {
+                ++n;
+                if (is_aligned(x, y, r.theta, r.prec)) ++k;
+            }
+        });
+    }
+
+    // Which enumeration rect_nfa uses.  0: the published LSD rectangle iterator (what the CUDA path implements this round);
+    // 1: cv2 4.13's (above).  NONE / STD never call rect_nfa.  With 1 the oracle agrees with cv2 4.13 LSD_REFINE_ADV bit for bit;
+    // with 0 the accepted set differs for short, barely meaningful segments while the 40 longest - all the reference consumes
+    // (src/LSDextractor.cpp:18-26) - agree (tests/test_oracle_lsd.py).  The reference's own pinned OpenCV 3.4.1 predates the
+    // 4.x rewrite and enumerates with integer-truncated corners; no build of it is available here, so that variant is unpinned
+    // (DESIGN.md §5.7).
+    int rect_enum = 0;                 // bit 0 of the rect_enum argument
+    // bit 1 of the rect_enum argument: rectangle axes from the host libm (what OpenCV calls) instead of detmath.h.  The two differ by 1 ulp now and
+    // then, which moves a scan-line bound across an integer for about one rectangle in a few thousand; with the libm axes the
+    // oracle reproduces cv2 4.13 LSD_REFINE_ADV in every field.  The CUDA path has no libm, hence detmath.h as the default.
+    bool libm_sincos = false;
+    bool debug = std::getenv("ORC_LSD_DEBUG") != nullptr;
     double rect_nfa(const Rect& rec) const {
         int total_pts = 0, alg_pts = 0;
-        rect_iter_count(rec, total_pts, alg_pts);
+        if (rect_enum == 1) rect_count_cv4(rec, total_pts, alg_pts);
+        else rect_iter_count(rec, total_pts, alg_pts);
+        if (debug) std::fprintf(stderr, "rect_nfa %.17g %.17g %.17g %.17g w %.17g th %.17g dx %.17g dy %.17g prec %.17g p %.17g n %d k %d nfa %.17g\n", rec.x1, rec.y1,
+                                rec.x2, rec.y2, rec.width, rec.theta, rec.dx, rec.dy, rec.prec, rec.p, total_pts, alg_pts, nfa(total_pts, alg_pts, rec.p));
         return nfa(total_pts, alg_pts, rec.p);
     }
 
@@ -399,13 +457,24 @@ struct Lsd {
 
 }  // namespace
 
-void lsd_detect_stages(const Img8& img, int refine, std::vector<LsdSegment>& out, LsdStages& st) {
+int lsd_cv4_spans(const double* rect, int W, int H, int32_t* rows, int cap) {
+    int m = 0;
+    rect_rows_cv4(rect[0], rect[1], rect[2], rect[3], rect[4], rect[5], rect[6], W, H, [&](int y, int xa, int xb) {
+        if (m < cap) { rows[3 * m] = y; rows[3 * m + 1] = xa; rows[3 * m + 2] = xb; }
+        ++m;
+    });
+    return m;
+}
+
+void lsd_detect_stages(const Img8& img, int refine, std::vector<LsdSegment>& out, LsdStages& st, int rect_enum) {
     out.clear();
     const double SCALE = 0.8, SIGMA_SCALE = 0.6, QUANT = 2.0, ANG_TH = 22.5;
     const int N_BINS = 1024;
     const double prec = kPi * ANG_TH / 180, p = ANG_TH / 180, rho = QUANT / std::sin(prec);
     (void)SIGMA_SCALE;
     Lsd L;
+    L.rect_enum = rect_enum & 1;
+    L.libm_sincos = (rect_enum & 2) != 0;
     // sigma = 0.6 / 0.8 = 0.75, h = ceil(0.75 * sqrt(2 * 3 * ln 10)) = 3 -> 7x7 kernel
     st.blurred.resize((size_t)img.w * img.h);
     gaussian_blur_7x7_s075_u8(img, st.blurred.data());
@@ -446,14 +515,14 @@ void lsd_detect_stages(const Img8& img, int refine, std::vector<LsdSegment>& out
     for (size_t i = 0; i < L.ordered.size(); ++i) st.order[i] = L.ordered[i].y * L.W + L.ordered[i].x;
 }
 
-void lsd_detect(const Img8& img, int refine, std::vector<LsdSegment>& out) {
+void lsd_detect(const Img8& img, int refine, std::vector<LsdSegment>& out, int rect_enum) {
     LsdStages st;
-    lsd_detect_stages(img, refine, out, st);
+    lsd_detect_stages(img, refine, out, st, rect_enum);
 }
 
-void extract_line_segments(const Img8& img, int max_lines, std::vector<KeyLine>& kls, std::vector<double>& lf) {
+void extract_line_segments(const Img8& img, int max_lines, std::vector<KeyLine>& kls, std::vector<double>& lf, int rect_enum) {
     std::vector<LsdSegment> segs;
-    lsd_detect(img, 2, segs);
+    lsd_detect(img, 2, segs, rect_enum);
     kls.clear();
     int class_counter = -1;
     for (const LsdSegment& s : segs) {

@@ -120,6 +120,7 @@ def lib() -> C.CDLL:
     L.pslam_lba_run_packed.argtypes = [vp]
     L.pslam_lba_fetch.argtypes = [vp, vp]
     L.pslam_lsd_max_segments.argtypes = [vp]
+    L.pslam_lsd_set_rect_enumeration.argtypes = [vp, i32]
     L.pslam_lsd_detect_batch.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
     L.pslam_lines_extract_batch.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     L.pslam_lines_extract_batch_dev.argtypes = [vp, vp, i32, i32, vp, vp, vp]

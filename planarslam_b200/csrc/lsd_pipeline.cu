@@ -53,6 +53,10 @@ int lsd_alloc(pslam_ctx* c) {
     g.W = lsd_cv_round(g.w * SCALE); g.H = lsd_cv_round(g.h * SCALE);
     if (g.W < 8 || g.H < 8 || g.W > 32767 || g.H > 32767) { delete Bp; return set_error(c, PSLAM_E_INVALID, "image size unsupported by the line-segment detector"); }
     g.refine = 2; g.seg_cap = LSD_SEG_CAP; g.cand_cap = LSD_SEG_CAP;
+    {   // default enumeration of the NFA validation; pslam_lsd_set_rect_enumeration overrides it
+        const char* e = std::getenv("PSLAM_LSD_RECT_ENUM");
+        g.rect_enum = (e && (!std::strcmp(e, "cv4") || !std::strcmp(e, "1"))) ? 1 : 0;
+    }
     g.prec = LSD_PI * ANG_TH / 180; g.p = ANG_TH / 180; g.rho = QUANT / std::sin(g.prec);
     g.log_nt = 5 * (std::log10(double(g.W)) + std::log10(double(g.H))) / 2 + std::log10(11.0);
     g.min_reg_size = (int)(size_t)(-g.log_nt / std::log10(g.p));
@@ -178,6 +182,15 @@ using namespace pslam;
 extern "C" {
 
 int pslam_lsd_max_segments(const pslam_ctx* c) { return c ? LSD_SEG_CAP : 0; }
+
+int pslam_lsd_set_rect_enumeration(pslam_ctx* c, int mode) {
+    if (!c) return PSLAM_E_INVALID;
+    if (mode != 0 && mode != 1) return set_error(c, PSLAM_E_INVALID, "rect enumeration: 0 (published LSD iterator) or 1 (OpenCV 4.x rect_nfa)");
+    const int rc = lsd_alloc(c);
+    if (rc != PSLAM_OK) return rc;
+    c->lsd->g.rect_enum = mode;
+    return PSLAM_OK;
+}
 
 static int lsd_upload(pslam_ctx* c, const uint8_t* gray, int nframes) {
     int rc = lsd_alloc(c);

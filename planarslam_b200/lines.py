@@ -22,6 +22,11 @@ class LineSegment:
     def __init__(self, ctx: Context | None = None, width: int = 640, height: int = 480, max_batch: int = 1, device: int = 0):
         self.ctx = ctx or Context(width, height, max_batch, device)
 
+    def set_rect_enumeration(self, mode: int):
+        """Pixel enumeration of the NFA validation: 0 the published LSD rectangle iterator (default), 1 OpenCV 4.x's rect_nfa
+        (include/pslam_abi.h pslam_lsd_set_rect_enumeration)."""
+        self.ctx.check(self.ctx.L.pslam_lsd_set_rect_enumeration(self.ctx.h, int(mode)))
+
     # cv::LineSegmentDetector::detect (refine: 0 NONE, 1 STD, 2 ADV)
     def detect(self, gray: np.ndarray, refine: int = 2):
         g = np.ascontiguousarray(gray, np.uint8)

@@ -277,13 +277,14 @@ KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4
 assert KEYLINE_DTYPE.itemsize == 68
 
 
-def lsd_detect(gray: np.ndarray, refine: int = 2, cap: int = 16384):
-    """Oracle cv::LineSegmentDetector::detect. Returns (segments float32 [n][4], width, prec, nfa float64 [n])."""
+def lsd_detect(gray: np.ndarray, refine: int = 2, cap: int = 16384, rect_enum: int = 0):
+    """Oracle cv::LineSegmentDetector::detect. Returns (segments float32 [n][4], width, prec, nfa float64 [n]).
+    rect_enum: NFA pixel enumeration - 0 the published LSD iterator (the CUDA path), 1 cv2 4.13's (oracle/lsd.cc rect_nfa)."""
     L = lib()
-    L.orc_lsd_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_lsd_detect_enum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     g = np.ascontiguousarray(gray, np.uint8)
     segs, wpn = np.zeros((cap, 4), np.float32), np.zeros((cap, 3))
-    n = L.orc_lsd_detect(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], refine, segs.ctypes.data, wpn.ctypes.data, cap)
+    n = L.orc_lsd_detect_enum(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], refine, rect_enum, segs.ctypes.data, wpn.ctypes.data, cap)
     assert n <= cap
     return segs[:n].copy(), wpn[:n, 0].copy(), wpn[:n, 1].copy(), wpn[:n, 2].copy()
 
@@ -305,14 +306,14 @@ def lsd_stages(gray: np.ndarray, refine: int = 2):
     return out
 
 
-def extract_line_segments(gray: np.ndarray, max_lines: int = 40):
+def extract_line_segments(gray: np.ndarray, max_lines: int = 40, rect_enum: int = 0):
     """Oracle LineSegment::ExtractLineSegment without LBD. Returns (KeyLine structured array, line functions [n][3])."""
     L = lib()
-    L.orc_extract_line_segments.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.orc_extract_line_segments_enum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     g = np.ascontiguousarray(gray, np.uint8)
     cap = max(max_lines, 1)
     kl, lf = np.zeros(cap, KEYLINE_DTYPE), np.zeros((cap, 3))
-    n = L.orc_extract_line_segments(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], max_lines, kl.ctypes.data, lf.ctypes.data, cap)
+    n = L.orc_extract_line_segments_enum(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], max_lines, rect_enum, kl.ctypes.data, lf.ctypes.data, cap)
     return kl[:n].copy(), lf[:n].copy()
 
 

@@ -5,8 +5,12 @@ line_descriptor, not vendored in /root/reference).
   * LSD_REFINE_NONE and LSD_REFINE_STD: every segment (float32 end points, order included), width and precision must be
     bit-identical (width: to 1 ulp, it carries a double cos / sin).  This pins the Gaussian 7x7 s=0.75 + INTER_LINEAR_EXACT down-scaling, the level-line field, the
     pseudo-ordering, region growing, the rectangle fit and the density refinement.
-  * LSD_REFINE_ADV (what the reference runs): cv2's rect_nfa point enumeration could not be reproduced (oracle/lsd.cc
-    note), so the accepted sets differ for short segments; what the reference consumes - the 40 longest segments
+  * LSD_REFINE_ADV (what the reference runs), oracle variant 3 (cv2 4.13's rect_nfa pixel enumeration + libm rectangle axes):
+    every field - end points, order, width, precision and log-NFA - bit-identical on 16 frames.  Variant 1 (same enumeration,
+    the deterministic sincos the CUDA path shares): identical except where a 1-ulp axis difference moves a scan-line bound across
+    an integer (about one rectangle in a few thousand).
+  * LSD_REFINE_ADV, oracle variant 0 (published LSD rectangle iterator - what the CUDA path of this round implements): the
+    accepted sets differ for short segments; what the reference consumes - the 40 longest segments
     (src/LSDextractor.cpp:18-26) - must be identical on the frames listed here.
 """
 import cv2
@@ -48,6 +52,25 @@ def test_lsd_oracle_small_and_flat_images():
 def _top(segs, k=40):
     length = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
     return segs[np.argsort(-length, kind="stable")[:k]]
+
+
+def test_lsd_oracle_adv_bit_exact_vs_cv2():
+    det = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV)
+    frames = [synth.render_frame(seed=s, frame=3 * s)[0] for s in range(16)] + [synth.polygon_image(11)]
+    n_total = n_same_det = 0
+    for g in frames:
+        ref = det.detect(g)
+        segs, width, prec, nfa = oracle_lib.lsd_detect(g, 2, rect_enum=3)
+        assert len(segs) == len(ref[0]) > 50
+        assert np.array_equal(segs, ref[0].reshape(-1, 4))
+        assert np.array_equal(width, ref[1].ravel()) and np.array_equal(prec, ref[2].ravel()) and np.array_equal(nfa, ref[3].ravel())
+        # same enumeration with the deterministic sincos: the segment lists may differ by the odd borderline rectangle
+        segs1 = oracle_lib.lsd_detect(g, 2, rect_enum=1)[0]
+        a, b = {s.tobytes() for s in segs1}, {s.tobytes() for s in segs}
+        n_total += len(b)
+        n_same_det += len(a & b)
+        assert np.array_equal(_top(segs1), _top(segs))
+    assert n_same_det >= n_total - 8, (n_same_det, n_total)
 
 
 def test_lsd_oracle_adv_top40_matches_cv2():
