@@ -332,6 +332,36 @@ int pslam_lines_extract_batch_dev(pslam_ctx* ctx, const uint8_t* d_gray, int nfr
 int pslam_lsd_debug_stage(pslam_ctx* ctx, int frame, int32_t* dims /* W, H */, uint8_t* scaled, double* modgrad, double* angles,
                           int32_t* order, int32_t* n_order);
 
+/* ---- 3-D lines ---------------------------------------------------------------------------------------
+ * Replaces  void Frame::isLineGood(const cv::Mat& imGray, const cv::Mat& imDepth, cv::Mat K)            src/Frame.cc:189-267
+ * with      compPt3dCov, extract3dline_mahdist, verify3dLine, mah_dist3d_pt_line, computeLine3d_svd     src/LineExtractor.cpp:1157-1470
+ * and       random_unique                                                                               include/LSDextractor.h:239-251
+ * Per 2-D line: up to 51 samples along the segment, nearest-pixel depth, back-projection, per-point covariance + cv::SVD, up to 10
+ * RANSAC iterations on the Mahalanobis point-line distance, SVD refit, end points, accept test (inliers / length > 0.4, length > 2 cm).
+ * Outputs per line what the reference stores: mvLines3D[i] (A, B), mvDepthLine[i], FrameLine::direction and the supporting samples.
+ * rand(): the reference draws from the process-wide libc stream; here each frame has its own glibc-compatible stream, started
+ * with srand(seed[f]) and advanced by skip[f] draws (skip may be NULL).  n_drawn[f] returns the number of rand() calls the frame
+ * made, so a caller that wants the reference's single stream passes seed = its srand seed, skip = draws made so far, and adds
+ * n_drawn.  depth: raw uint16 [nframes][height][width]; metres = (float)raw * depth_factor (imDepth.convertTo(CV_32F, factor)).
+ * cam: fx, fy, cx, cy (float, as Frame::fx ... are). */
+typedef struct pslam_line3d {
+    double A[3], B[3];       /* mvLines3D[i]; zero unless valid */
+    double director[3];      /* (A - B) / |A - B| of the fitted line (NaN when the fit found no support) */
+    uint64_t inliers;        /* bit j: sample j (in sampling order, samples without depth dropped) supports the line */
+    float depth;             /* mvDepthLine[i]; -1 unless valid */
+    int32_t n_points;        /* samples with depth */
+    int32_t n_inliers;       /* RandomLine3d::pts.size() */
+    int32_t valid;           /* the accept test of isLineGood passed */
+} pslam_line3d;
+
+int pslam_lines3d_batch(pslam_ctx* ctx, const pslam_keyline* keylines /* [nframes][max_lines] */, const int32_t* n_lines /* [nframes] */, int max_lines,
+                        const uint16_t* depth, int nframes, float depth_factor, const float* cam /* [4] */, const uint32_t* seed /* [nframes] */,
+                        const int32_t* skip /* [nframes] or NULL */, pslam_line3d* out /* [nframes][max_lines] */, int32_t* n_drawn /* [nframes] */);
+/* Same with device pointers (cam stays a host pointer); only enqueues on the context's stream - chains after
+ * pslam_lines_extract_batch_dev on the key lines it leaves in HBM. */
+int pslam_lines3d_batch_dev(pslam_ctx* ctx, const pslam_keyline* d_keylines, const int32_t* d_n_lines, int max_lines, const uint16_t* d_depth, int nframes,
+                            float depth_factor, const float* cam, const uint32_t* d_seed, const int32_t* d_skip, pslam_line3d* d_out, int32_t* d_n_drawn);
+
 /* Replaces  int LSDmatcher::SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, float th)
  *           include/LSDmatcher.h:24, src/LSDmatcher.cpp:141-211 (+ Frame::GetLinesInArea src/Frame.cc:491-523).
  * Frame side: KeyLine pt / angle / octave and the LBD rows of the <= 64 frame lines, has_obs[i] = (mvpMapLines[i] &&

@@ -58,3 +58,28 @@ class LineSegment:
                                                         out["angles"].ctypes.data, out["order"].ctypes.data, no.ctypes.data))
         out["order"] = out["order"][:int(no[0])]
         return out
+
+
+LINE3D_DTYPE = np.dtype([("A", "<f8", 3), ("B", "<f8", 3), ("director", "<f8", 3), ("inliers", "<u8"), ("depth", "<f4"), ("n_points", "<i4"),
+                         ("n_inliers", "<i4"), ("valid", "<i4")])
+assert LINE3D_DTYPE.itemsize == 96
+
+
+def isLineGood(ctx: Context, keylines: np.ndarray, n_lines, depth: np.ndarray, K, depth_factor: float, seed=1, skip=None):
+    """void Frame::isLineGood(const cv::Mat& imGray, const cv::Mat& imDepth, cv::Mat K) (src/Frame.cc:189-267) for a batch of frames.
+
+    keylines: KEYLINE_DTYPE [nframes][max_lines] (as ExtractLineSegment returns them, padded), n_lines [nframes]; depth uint16
+    [nframes][h][w] raw (metres = raw * depth_factor); K = (fx, fy, cx, cy); seed / skip: per-frame rand() stream (scalars are
+    broadcast).  Returns (LINE3D_DTYPE [nframes][max_lines], n_drawn [nframes])."""
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    assert kl.ndim == 2
+    nframes, max_lines = kl.shape
+    nl = np.ascontiguousarray(np.broadcast_to(np.asarray(n_lines, np.int32), (nframes,)))
+    d = np.ascontiguousarray(depth, np.uint16).reshape(nframes, ctx.cfg.height, ctx.cfg.width)
+    cam = np.asarray(K, np.float32)
+    sd = np.ascontiguousarray(np.broadcast_to(np.asarray(seed, np.uint32), (nframes,)))
+    sk = None if skip is None else np.ascontiguousarray(np.broadcast_to(np.asarray(skip, np.int32), (nframes,)))
+    out, drawn = np.zeros((nframes, max_lines), LINE3D_DTYPE), np.zeros(nframes, np.int32)
+    ctx.check(ctx.L.pslam_lines3d_batch(ctx.h, kl.ctypes.data, nl.ctypes.data, max_lines, d.ctypes.data, nframes, float(depth_factor), cam.ctypes.data,
+                                        sd.ctypes.data, None if sk is None else sk.ctypes.data, out.ctypes.data, drawn.ctypes.data))
+    return out, drawn

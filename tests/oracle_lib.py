@@ -374,3 +374,43 @@ def bow_score_l1(a: dict, b: dict) -> float:
     L.orc_bow_score_l1.restype = C.c_double
     return float(L.orc_bow_score_l1(a["word_id"].ctypes.data, a["word_val"].ctypes.data, len(a["word_id"]), b["word_id"].ctypes.data,
                                     b["word_val"].ctypes.data, len(b["word_id"])))
+
+
+def glibc_rand(seed: int, n: int) -> np.ndarray:
+    """The first n values of rand() after srand(seed), from the oracle's restatement of glibc's TYPE_3 generator."""
+    L = lib()
+    L.orc_glibc_rand.argtypes = [C.c_uint32, C.c_int, C.c_void_p]
+    out = np.zeros(n, np.int32)
+    L.orc_glibc_rand(seed, n, out.ctypes.data)
+    return out
+
+
+def cv_svd(A: np.ndarray):
+    """cv::SVD::compute (no FULL_UV) by OpenCV's Jacobi algorithm (oracle/cvsvd.h). Returns (w, u, vt)."""
+    L = lib()
+    A = np.ascontiguousarray(A)
+    assert A.dtype in (np.float32, np.float64) and A.ndim == 2
+    m, n = A.shape
+    k = min(m, n)
+    w, u, vt = np.zeros(k, A.dtype), np.zeros((m, k), A.dtype), np.zeros((k, n), A.dtype)
+    fn = L.orc_cv_svd64 if A.dtype == np.float64 else L.orc_cv_svd32
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn(A.ctypes.data, m, n, w.ctypes.data, u.ctypes.data, vt.ctypes.data)
+    return w, u, vt
+
+
+def lines3d_frame(keylines: np.ndarray, depth: np.ndarray, cam, seed: int = 1, skip: int = 0):
+    """Oracle Frame::isLineGood for one frame. keylines: KEYLINE_DTYPE[n]; depth float32 [h][w] metres; cam (fx, fy, cx, cy).
+    Returns dict(valid, depth_line, lines3d [n][6], director [n][3], n_points, n_inliers, inliers u64, n_drawn)."""
+    L = lib()
+    L.orc_lines3d_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_int] + [C.c_void_p] * 7
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = len(kl)
+    camv = np.asarray(cam, np.float32)
+    o = dict(valid=np.zeros(n, np.uint8), depth_line=np.zeros(n, np.float32), lines3d=np.zeros((n, 6)), director=np.zeros((n, 3)),
+             n_points=np.zeros(n, np.int32), n_inliers=np.zeros(n, np.int32), inliers=np.zeros(n, np.uint64))
+    o["n_drawn"] = L.orc_lines3d_frame(kl.ctypes.data, n, d.ctypes.data, d.shape[1], d.shape[0], camv.ctypes.data, seed, skip, o["valid"].ctypes.data,
+                                       o["depth_line"].ctypes.data, o["lines3d"].ctypes.data, o["director"].ctypes.data, o["n_points"].ctypes.data,
+                                       o["n_inliers"].ctypes.data, o["inliers"].ctypes.data)
+    return o
