@@ -32,3 +32,14 @@ int orc_lines3d_frame(const void* keylines, int n_lines, const float* depth, int
     return (int)g.drawn;
 }
 }
+
+#include "manhattan.h"
+// out_i: found[3], n_cone[3], n_selected[3], min_num, svd_applied (11 ints); out_f: R[9], density[3] (12 floats)
+extern "C" void orc_track_manhattan_frame(const float* R_last, const float* normals, int n, const double* dirs, int m, int32_t* out_i, float* out_f,
+                                          uint8_t* normal_mask, uint8_t* dir_mask) {
+    oracle::ManhattanResult r;
+    oracle::track_manhattan_frame(R_last, normals, n, dirs, m, r, normal_mask, dir_mask);
+    for (int i = 0; i < 3; ++i) { out_i[i] = r.found[i]; out_i[3 + i] = r.n_cone[i]; out_i[6 + i] = r.n_selected[i]; out_f[9 + i] = r.density[i]; }
+    out_i[9] = r.min_num; out_i[10] = r.svd_applied;
+    for (int i = 0; i < 9; ++i) out_f[i] = r.R[i];
+}

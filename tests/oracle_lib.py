@@ -414,3 +414,18 @@ def lines3d_frame(keylines: np.ndarray, depth: np.ndarray, cam, seed: int = 1, s
                                        o["depth_line"].ctypes.data, o["lines3d"].ctypes.data, o["director"].ctypes.data, o["n_points"].ctypes.data,
                                        o["n_inliers"].ctypes.data, o["inliers"].ctypes.data)
     return o
+
+
+def track_manhattan_frame(R_last: np.ndarray, normals: np.ndarray, dirs: np.ndarray):
+    """Oracle Tracking::TrackManhattanFrame. R_last 3x3 float32, normals [n][3] float32, dirs [m][3] float64.
+    Returns dict(R, found, density, n_cone, n_selected, min_num, svd_applied, normal_mask, dir_mask)."""
+    L = lib()
+    L.orc_track_manhattan_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R = np.ascontiguousarray(R_last, np.float32).reshape(3, 3)
+    nr = np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+    dr = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+    oi, of = np.zeros(11, np.int32), np.zeros(12, np.float32)
+    nm, dm = np.zeros(max(len(nr), 1), np.uint8), np.zeros(max(len(dr), 1), np.uint8)
+    L.orc_track_manhattan_frame(R.ctypes.data, nr.ctypes.data, len(nr), dr.ctypes.data, len(dr), oi.ctypes.data, of.ctypes.data, nm.ctypes.data, dm.ctypes.data)
+    return dict(R=of[:9].reshape(3, 3).copy(), density=of[9:].copy(), found=oi[:3].copy(), n_cone=oi[3:6].copy(), n_selected=oi[6:9].copy(), min_num=int(oi[9]),
+                svd_applied=int(oi[10]), normal_mask=nm[:len(nr)].copy(), dir_mask=dm[:len(dr)].copy())
