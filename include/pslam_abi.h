@@ -362,6 +362,35 @@ int pslam_lines3d_batch(pslam_ctx* ctx, const pslam_keyline* keylines /* [nframe
 int pslam_lines3d_batch_dev(pslam_ctx* ctx, const pslam_keyline* d_keylines, const int32_t* d_n_lines, int max_lines, const uint16_t* d_depth, int nframes,
                             float depth_factor, const float* cam, const uint32_t* d_seed, const int32_t* d_skip, pslam_line3d* d_out, int32_t* d_n_drawn);
 
+/* ---- Manhattan frame ---------------------------------------------------------------------------------
+ * Replaces  cv::Mat Tracking::TrackManhattanFrame(cv::Mat& mLastRcm, std::vector<SurfaceNormal>&, std::vector<FrameLine>&)   src/Tracking.cc:963-1137
+ * with      ProjectSN2Conic :888-961, ProjectSN2MF :763-886, MeanShift :1139-1157.
+ * Per axis: surface normals / 3-D line directions inside the cone around the current axis (sin 0.2018 / sin 0.1018), tangent-plane
+ * coordinates of those inside sin 0.2518, one Gaussian mean-shift step (c = 20), back-projection; a missing third axis from the cross
+ * product; projection onto SO(3) by cv::SVD.  The reference's aliasing of R_cm and R_cm_update (:970) is reproduced.
+ * R_last / result R: row-major 3x3 float (the CV_32F cv::Mat).  normals: SurfaceNormal::normal (float x 3, camera frame); dirs:
+ * FrameLine::direction (double x 3) of the lines with depth (pslam_line3d.director of the valid lines).
+ * Masks (always written): bit a-1 (a = 1..3) - the element was appended to Frame::vSurfaceNormal{x,y,z} / vVanishingLine{x,y,z};
+ * bit 3+a - it is inside the first-pass cone of axis a. */
+typedef struct pslam_manhattan_result {
+    float R[9];                  /* the returned R_cm */
+    float density[3];            /* s_j_density per axis, 0 when the axis was not found */
+    int32_t found[3];            /* directionFound1..3 */
+    int32_t n_cone[3];           /* numInCone */
+    int32_t n_selected[3];       /* m_j_selected.size() */
+    int32_t min_num;             /* minNumOfSN after the (a+b)/2 fallback */
+    int32_t svd_applied;         /* 0: fewer than two directions - the partially updated matrix is returned as the reference does */
+} pslam_manhattan_result;
+
+int pslam_track_manhattan_batch(pslam_ctx* ctx, const float* R_last /* [nframes][9] */, const float* normals /* [nframes][max_normals][3] */,
+                                const int32_t* n_normals /* [nframes] */, int max_normals, const double* dirs /* [nframes][max_dirs][3] */,
+                                const int32_t* n_dirs /* [nframes] */, int max_dirs, int nframes, pslam_manhattan_result* res /* [nframes] */,
+                                uint8_t* normal_mask /* [nframes][max_normals] */, uint8_t* dir_mask /* [nframes][max_dirs] */);
+/* Same with device pointers; only enqueues on the context's stream. */
+int pslam_track_manhattan_batch_dev(pslam_ctx* ctx, const float* d_R_last, const float* d_normals, const int32_t* d_n_normals, int max_normals,
+                                    const double* d_dirs, const int32_t* d_n_dirs, int max_dirs, int nframes, pslam_manhattan_result* d_res,
+                                    uint8_t* d_normal_mask, uint8_t* d_dir_mask);
+
 /* Replaces  int LSDmatcher::SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, float th)
  *           include/LSDmatcher.h:24, src/LSDmatcher.cpp:141-211 (+ Frame::GetLinesInArea src/Frame.cc:491-523).
  * Frame side: KeyLine pt / angle / octave and the LBD rows of the <= 64 frame lines, has_obs[i] = (mvpMapLines[i] &&
