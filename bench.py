@@ -468,6 +468,20 @@ def main():
         aux["lba_config"] = "20 key frames (1 fixed), 5000 point + 100 line (200 edges) + 30 plane-type edges, 296 problems per launch"
     except Exception as ex:                      # auxiliary only: never fail the headline
         aux["lba_error"] = repr(ex)
+    # ---- auxiliary: Frame::isLineGood and Tracking::TrackManhattanFrame (kernels added after the round-1 GPU budget was spent): run in a
+    # child process so that a fault there cannot touch this process' CUDA context; it reports throughput and whether the results match
+    # the signatures computed on the CPU at commit time (tests/golden/aux_new_kernels_expected.json) ----
+    if rank == 0 and os.environ.get("PSLAM_AUX_NEW", "1") != "0":
+        import subprocess
+        try:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "aux_new_kernels.py")], capture_output=True, text=True, timeout=240, env=env)
+            if r.returncode == 0 and r.stdout.strip():
+                aux["new_kernels"] = json.loads(r.stdout.strip().splitlines()[-1])
+            else:
+                aux["new_kernels"] = {"error": f"exit code {r.returncode}", "stderr": r.stderr[-300:]}
+        except Exception as ex:
+            aux["new_kernels"] = {"error": repr(ex)}
 
     if rank == 0:
         cpu_fps, cpu_n = cpu_oracle_fps(gray, depth, seconds=12.0, threads=1)
