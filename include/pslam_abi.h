@@ -391,6 +391,21 @@ int pslam_track_manhattan_batch_dev(pslam_ctx* ctx, const float* d_R_last, const
                                     const double* d_dirs, const int32_t* d_n_dirs, int max_dirs, int nframes, pslam_manhattan_result* d_res,
                                     uint8_t* d_normal_mask, uint8_t* d_dir_mask);
 
+/* Replaces the  mCurrentFrame.isInFrustum(pML, 0.6)  pass of Tracking::SearchLocalLines (src/Tracking.cc:2352-2366):
+ *           bool Frame::isInFrustum(MapLine* pML, float viewingCosLimit)   src/Frame.cc:369-437
+ *           int MapLine::PredictScale(const float&, const float&)          src/MapLine.cpp:381-390 (no clamping)
+ * for n map lines: pos [n][6] = GetWorldPos() (start, end), normal [n][3] = GetNormal(), max_distance / min_distance = mfMaxDistance /
+ * mfMinDistance (the 1.2 / 0.8 factors of Get*DistanceInvariance are applied here).  Outputs the fields the function writes into the
+ * MapLine: in_view = mbTrackInView, proj [n][4] = mTrackProjX1, Y1, X2, Y2, level = mnTrackScaleLevel, view_cos = mTrackViewCos (zero when
+ * not in view) - exactly the inputs of pslam_line_search_by_projection below.  Returns the number of lines in view (nToMatch). */
+typedef struct pslam_line_frustum_frame {
+    float Tcw[16];                                   /* mTcw, row-major */
+    float fx, fy, cx, cy, min_x, max_x, min_y, max_y;  /* Frame::fx.., mnMinX..mnMaxY */
+    float log_scale_factor;                          /* mfLogScaleFactor */
+} pslam_line_frustum_frame;
+int pslam_lines_in_frustum(pslam_ctx* ctx, const pslam_line_frustum_frame* frame, int n, const double* pos, const double* normal, const float* max_distance,
+                           const float* min_distance, float cos_limit, uint8_t* in_view, float* proj, int32_t* level, float* view_cos);
+
 /* Replaces  int LSDmatcher::SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, float th)
  *           include/LSDmatcher.h:24, src/LSDmatcher.cpp:141-211 (+ Frame::GetLinesInArea src/Frame.cc:491-523).
  * Frame side: KeyLine pt / angle / octave and the LBD rows of the <= 64 frame lines, has_obs[i] = (mvpMapLines[i] &&

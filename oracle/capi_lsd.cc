@@ -89,3 +89,13 @@ extern "C" void orc_bow_transform(int n_nodes, int L, const uint8_t* vdesc, cons
 extern "C" double orc_bow_score_l1(const int32_t* id1, const double* v1, int n1, const int32_t* id2, const double* v2, int n2) {
     return oracle::bow_score_l1(id1, v1, n1, id2, v2, n2);
 }
+
+// frame: Tcw[16], fx, fy, cx, cy, min_x, max_x, min_y, max_y, log_scale_factor (25 floats)
+extern "C" void orc_lines_in_frustum(const float* frame, int n, const double* pos, const double* normal, const float* max_distance, const float* min_distance,
+                                     float cos_limit, uint8_t* in_view, float* proj, int32_t* level, float* view_cos) {
+    oracle::LineFrustumFrame F;
+    for (int i = 0; i < 16; ++i) F.Tcw[i] = frame[i];
+    F.fx = frame[16]; F.fy = frame[17]; F.cx = frame[18]; F.cy = frame[19]; F.min_x = frame[20]; F.max_x = frame[21]; F.min_y = frame[22]; F.max_y = frame[23];
+    F.log_scale_factor = frame[24];
+    oracle::lines_in_frustum(F, n, pos, normal, max_distance, min_distance, cos_limit, in_view, proj, level, view_cos);
+}

@@ -30,3 +30,14 @@ struct MapLinesView {
 int line_search_by_projection(const LineFrameView& F, const MapLinesView& M, float th, float nnratio, int32_t* assigned);
 
 }  // namespace oracle
+
+namespace oracle {
+// Frame::isInFrustum(MapLine*, viewingCosLimit)  src/Frame.cc:369-437 with MapLine::PredictScale src/MapLine.cpp:381-390 and
+// Get{Min,Max}DistanceInvariance :370-379 - the pass of Tracking::SearchLocalLines (src/Tracking.cc:2352-2366) that fills the
+// MapLinesView fields above.  Float arithmetic as cv::Mat CV_32F does it (double accumulation inside a product / norm / dot, one
+// rounding per Mat operation), same conventions as the map-point version in search.cc.
+struct LineFrustumFrame { float Tcw[16]; float fx, fy, cx, cy, min_x, max_x, min_y, max_y, log_scale_factor; };
+// pos [n][6] (GetWorldPos: start, end), normal [n][3] (GetNormal) as double (Vector6d / Vector3d); max_distance / min_distance: mfMaxDistance / mfMinDistance
+void lines_in_frustum(const LineFrustumFrame& F, int n, const double* pos, const double* normal, const float* max_distance, const float* min_distance,
+                      float cos_limit, uint8_t* in_view, float* proj /* [n][4] */, int32_t* level, float* view_cos);
+}  // namespace oracle

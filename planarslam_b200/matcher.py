@@ -171,3 +171,20 @@ def bow_transform(ctx: Context, voc: dict, features: np.ndarray, levelsup: int =
     o["node_id"], o["node_off"] = o["node_id"][:nn], o["node_off"][:nn + 1]
     o["node_feat"] = o["node_feat"][:int(o["node_off"][-1])] if nn else o["node_feat"][:0]
     return o
+
+
+def lines_in_frustum(ctx: Context, frame: dict, pos, normal, max_distance, min_distance, cos_limit: float = 0.6):
+    """bool Frame::isInFrustum(MapLine*, float viewingCosLimit) (src/Frame.cc:369-437) for n map lines - the visibility pass of
+    Tracking::SearchLocalLines.  frame: dict(Tcw 4x4 float32, fx, fy, cx, cy, min_x, max_x, min_y, max_y, log_scale_factor).
+    Returns (n_in_view, dict(in_view, proj [n][4], level, view_cos)) - the map-line fields LSDmatcher.SearchByProjection takes."""
+    fv = np.concatenate([np.asarray(frame["Tcw"], np.float32).ravel(), np.array([frame[k] for k in ("fx", "fy", "cx", "cy", "min_x", "max_x", "min_y", "max_y",
+                                                                                                      "log_scale_factor")], np.float32)])
+    P, Nn = np.ascontiguousarray(pos, np.float64).reshape(-1, 6), np.ascontiguousarray(normal, np.float64).reshape(-1, 3)
+    mx, mn = np.ascontiguousarray(max_distance, np.float32), np.ascontiguousarray(min_distance, np.float32)
+    n = len(P)
+    o = dict(in_view=np.zeros(n, np.uint8), proj=np.zeros((n, 4), np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    rc = ctx.L.pslam_lines_in_frustum(ctx.h, fv.ctypes.data, n, P.ctypes.data, Nn.ctypes.data, mx.ctypes.data, mn.ctypes.data, cos_limit, o["in_view"].ctypes.data,
+                                      o["proj"].ctypes.data, o["level"].ctypes.data, o["view_cos"].ctypes.data)
+    if rc < 0:
+        ctx.check(rc)
+    return rc, o

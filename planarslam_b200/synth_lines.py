@@ -99,3 +99,35 @@ def make_features_for_vocabulary(seed: int, voc: dict, n: int = 1000):
     src = voc["leaves"][rng.integers(0, len(voc["leaves"]) // 3 + 1, n)]
     flips = np.packbits(rng.random((n, 256)) < 0.08, axis=1)
     return np.ascontiguousarray(voc["desc"][src] ^ flips)
+
+
+def make_line_frustum(seed: int, n: int = 400):
+    """A camera pose + n map lines for Frame::isInFrustum(MapLine*): about half in view, the rest behind the camera, outside the image,
+    outside the scale-invariance distance range or seen too obliquely.  Returns (frame dict, pos [n][6], normal [n][3], max_distance, min_distance)."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 7919 + 17))
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    ang = rng.uniform(0, 0.6)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    t = rng.normal(0, 0.5, 3)
+    Tcw = np.eye(4, dtype=np.float32); Tcw[:3, :3] = R; Tcw[:3, 3] = t
+    fx, fy, cx, cy = 535.4, 539.2, 320.1, 247.6
+    frame = dict(Tcw=Tcw, fx=fx, fy=fy, cx=cx, cy=cy, min_x=0.0, max_x=640.0, min_y=0.0, max_y=480.0, log_scale_factor=float(np.log(np.float32(1.2))))
+    z = rng.uniform(-1.0, 6.0, n)                              # some behind the camera
+    u, v = rng.uniform(-100, 740, n), rng.uniform(-80, 560, n)
+    mid_c = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    half = rng.uniform(0.05, 0.5, n)[:, None]
+    Rt = R.T
+    to_w = lambda Pc: (Pc - t) @ Rt.T
+    sp, ep = to_w(mid_c - d * half), to_w(mid_c + d * half)
+    pos = np.concatenate([sp, ep], 1)
+    Ow = -Rt @ t
+    view = 0.5 * (sp + ep) - Ow
+    view /= np.linalg.norm(view, axis=1, keepdims=True) + 1e-12
+    nrm = view + rng.normal(0, 0.6, (n, 3))                    # GetNormal(): mean viewing direction; noisy -> some below cos 0.6
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    dist = np.linalg.norm(0.5 * (sp + ep) - Ow, axis=1)
+    max_d = (dist * rng.uniform(0.7, 2.5, n)).astype(np.float32)
+    min_d = (max_d / np.float32(1.2 ** 7)).astype(np.float32)
+    return frame, pos, nrm, max_d, min_d

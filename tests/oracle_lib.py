@@ -429,3 +429,19 @@ def track_manhattan_frame(R_last: np.ndarray, normals: np.ndarray, dirs: np.ndar
     L.orc_track_manhattan_frame(R.ctypes.data, nr.ctypes.data, len(nr), dr.ctypes.data, len(dr), oi.ctypes.data, of.ctypes.data, nm.ctypes.data, dm.ctypes.data)
     return dict(R=of[:9].reshape(3, 3).copy(), density=of[9:].copy(), found=oi[:3].copy(), n_cone=oi[3:6].copy(), n_selected=oi[6:9].copy(), min_num=int(oi[9]),
                 svd_applied=int(oi[10]), normal_mask=nm[:len(nr)].copy(), dir_mask=dm[:len(dr)].copy())
+
+
+def lines_in_frustum(frame: dict, pos, normal, max_distance, min_distance, cos_limit: float = 0.6):
+    """Oracle Frame::isInFrustum(MapLine*, cosLimit) for n map lines. frame: dict(Tcw 4x4, fx, fy, cx, cy, min_x, max_x, min_y, max_y, log_scale_factor).
+    Returns dict(in_view, proj [n][4], level, view_cos)."""
+    L = lib()
+    L.orc_lines_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 4
+    fv = np.concatenate([np.asarray(frame["Tcw"], np.float32).ravel(), np.array([frame[k] for k in ("fx", "fy", "cx", "cy", "min_x", "max_x", "min_y", "max_y",
+                                                                                                      "log_scale_factor")], np.float32)])
+    P, Nn = np.ascontiguousarray(pos, np.float64).reshape(-1, 6), np.ascontiguousarray(normal, np.float64).reshape(-1, 3)
+    mx, mn = np.ascontiguousarray(max_distance, np.float32), np.ascontiguousarray(min_distance, np.float32)
+    n = len(P)
+    o = dict(in_view=np.zeros(n, np.uint8), proj=np.zeros((n, 4), np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    L.orc_lines_in_frustum(fv.ctypes.data, n, P.ctypes.data, Nn.ctypes.data, mx.ctypes.data, mn.ctypes.data, cos_limit, o["in_view"].ctypes.data, o["proj"].ctypes.data,
+                           o["level"].ctypes.data, o["view_cos"].ctypes.data)
+    return o
