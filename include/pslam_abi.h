@@ -165,6 +165,18 @@ int pslam_hamming_knn2_batch_dev(pslam_ctx* ctx, const uint8_t* d_q, const int32
                                  const int32_t* d_nt, int capt, int nframes, int32_t* d_idx2, int32_t* d_dist2, int32_t* d_good,
                                  int32_t* d_ngood);
 
+/* ---- RGB-D "stereo" fields -------------------------------------------------------------------------
+ * Replaces  void Frame::ComputeStereoFromRGBD(const cv::Mat& imDepth)   src/Frame.cc:603-621
+ * keys = mvKeys, keys_un = mvKeysUn (the same pointer when the camera has no distortion, Frame::UndistortKeyPoints :545-549), both
+ * [nframes][cap] with n[f] valid entries; depth: raw uint16 [nframes][height][width], metres = (float)raw * depth_factor (the Frame
+ * constructor's convertTo, :80-83); bf = mbf.  Outputs [nframes][cap]: u_right = mvuRight, depth_out = mvDepth (-1 where there is
+ * no depth, and for the padding entries). */
+int pslam_compute_stereo_from_rgbd_batch(pslam_ctx* ctx, const pslam_keypoint* keys, const pslam_keypoint* keys_un, const int32_t* n, int cap,
+                                         const uint16_t* depth, int nframes, float depth_factor, float bf, float* u_right, float* depth_out);
+/* Same with device pointers; only enqueues on the context's stream (chains after pslam_orb_extract_batch_dev). */
+int pslam_compute_stereo_from_rgbd_batch_dev(pslam_ctx* ctx, const pslam_keypoint* d_keys, const pslam_keypoint* d_keys_un, const int32_t* d_n, int cap,
+                                             const uint16_t* d_depth, int nframes, float depth_factor, float bf, float* d_u_right, float* d_depth_out);
+
 /* ---- Projection-guided search ---------------------------------------------------------------------
  * Replaces  int ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, float th)        src/ORBmatcher.cc:46-130
  *           (together with the Frame::isInFrustum pass of Tracking::SearchLocalPoints, src/Tracking.cc:2286-2329, src/Frame.cc:312-367)

@@ -130,6 +130,8 @@ def lib() -> C.CDLL:
     L.pslam_track_manhattan_batch.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]
     L.pslam_track_manhattan_batch_dev.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, i32, vp, vp, vp]
     L.pslam_lines_in_frustum.argtypes = [vp, vp, i32, vp, vp, vp, vp, C.c_float, vp, vp, vp, vp]
+    L.pslam_compute_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i32, vp, i32, C.c_float, C.c_float, vp, vp]
+    L.pslam_compute_stereo_from_rgbd_batch_dev.argtypes = [vp, vp, vp, vp, i32, vp, i32, C.c_float, C.c_float, vp, vp]
     L.pslam_bow_transform.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.pslam_search_by_bow.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, C.c_float, i32, vp]
     L.pslam_line_search_by_projection.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, vp]

@@ -445,3 +445,15 @@ def lines_in_frustum(frame: dict, pos, normal, max_distance, min_distance, cos_l
     L.orc_lines_in_frustum(fv.ctypes.data, n, P.ctypes.data, Nn.ctypes.data, mx.ctypes.data, mn.ctypes.data, cos_limit, o["in_view"].ctypes.data, o["proj"].ctypes.data,
                            o["level"].ctypes.data, o["view_cos"].ctypes.data)
     return o
+
+
+def compute_stereo_from_rgbd(keys_xy, keys_un_xy, depth, bf: float):
+    """Oracle Frame::ComputeStereoFromRGBD. keys_xy / keys_un_xy [n][2] float32, depth float32 [h][w]. Returns (mvuRight, mvDepth)."""
+    L = lib()
+    L.orc_compute_stereo_from_rgbd.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    k, ku = np.ascontiguousarray(keys_xy, np.float32), np.ascontiguousarray(keys_un_xy, np.float32)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = len(k)
+    ur, dz = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    L.orc_compute_stereo_from_rgbd(n, k.ctypes.data, ku.ctypes.data, d.ctypes.data, d.shape[1], bf, ur.ctypes.data, dz.ctypes.data)
+    return ur, dz
