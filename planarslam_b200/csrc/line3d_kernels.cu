@@ -65,7 +65,7 @@ extern "C" {
 int pslam_lines3d_batch_dev(pslam_ctx* c, const pslam_keyline* keylines, const int32_t* n_lines, int max_lines, const uint16_t* depth, int nframes,
                             float depth_factor, const float* cam, const uint32_t* seed, const int32_t* skip, pslam_line3d* out, int32_t* n_drawn) {
     if (!c) return PSLAM_E_INVALID;
-    if (!keylines || !n_lines || !depth || !cam || !seed || !out || !n_drawn || nframes < 1 || max_lines < 1 || !(cam[0] > 0) || !(cam[1] > 0))
+    if (!keylines || !n_lines || !depth || !cam || !seed || !out || !n_drawn || nframes < 1 || max_lines < 1 || cam[0] == 0 || cam[1] == 0)        // fy < 0 is legal (Examples/RGB-D/ICL.yaml:9)
         return set_error(c, PSLAM_E_INVALID, "bad lines3d arguments");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
     return lines3d_launch(c, keylines, n_lines, max_lines, depth, nframes, depth_factor, cam, seed, skip, out, n_drawn);
@@ -74,7 +74,7 @@ int pslam_lines3d_batch_dev(pslam_ctx* c, const pslam_keyline* keylines, const i
 int pslam_lines3d_batch(pslam_ctx* c, const pslam_keyline* keylines, const int32_t* n_lines, int max_lines, const uint16_t* depth, int nframes, float depth_factor,
                         const float* cam, const uint32_t* seed, const int32_t* skip, pslam_line3d* out, int32_t* n_drawn) {
     if (!c) return PSLAM_E_INVALID;
-    if (!keylines || !n_lines || !depth || !cam || !seed || !out || !n_drawn || nframes < 1 || max_lines < 1 || !(cam[0] > 0) || !(cam[1] > 0))
+    if (!keylines || !n_lines || !depth || !cam || !seed || !out || !n_drawn || nframes < 1 || max_lines < 1 || cam[0] == 0 || cam[1] == 0)        // fy < 0 is legal (Examples/RGB-D/ICL.yaml:9)
         return set_error(c, PSLAM_E_INVALID, "bad lines3d arguments");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
     cudaStream_t st = c->stream;

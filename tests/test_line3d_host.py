@@ -84,3 +84,18 @@ def test_body_edge_cases(host_lib):
     o = oracle_lib.lines3d_frame(hz, depth, synth.TUM3_K)
     for k in ("valid", "n_points", "inliers", "lines3d", "depth_line"):
         assert np.array_equal(r[k], o[k]), k
+
+
+def test_body_matches_oracle_with_icl_intrinsics(host_lib):
+    """Examples/RGB-D/ICL.yaml:6-10: fy = -480 (y flips sign in every back-projection), depth factor 5000."""
+    icl = (481.2, -480.0, 319.5, 239.5)
+    for s in (1, 5):
+        gray, d16, _, _ = synth.render_frame(seed=s, frame=3 * s)
+        kl, _ = oracle_lib.extract_line_segments(gray, 40)
+        depth = d16.astype(np.float32) * np.float32(1.0 / synth.DEPTH_FACTOR)
+        o = oracle_lib.lines3d_frame(kl, depth, icl, seed=3)
+        p = host_lines3d(host_lib, kl, d16, icl, seed=3)
+        for k in ("valid", "n_points", "inliers", "lines3d", "depth_line"):
+            assert np.array_equal(p[k], o[k]), k
+        assert p["n_drawn"] == o["n_drawn"] and p["valid"].sum() > 20
+        assert (p["lines3d"][p["valid"].astype(bool)][:, [1, 4]] != 0).all()
