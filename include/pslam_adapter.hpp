@@ -11,6 +11,10 @@
 //   Optimizer::PoseOptimization                include/Optimizer.h:38         -> pslam_pose_optimization
 //   Optimizer::LocalBundleAdjustment           include/Optimizer.h:34         -> pslam_local_bundle_adjustment
 //   LineSegment::ExtractLineSegment            include/LSDextractor.h:349     -> pslam_lines_extract_batch
+//   Frame::isLineGood                          include/Frame.h (src/Frame.cc:189)  -> pslam_lines3d_batch
+//   Frame::ComputeStereoFromRGBD               src/Frame.cc:603               -> pslam_compute_stereo_from_rgbd_batch
+//   Frame::isInFrustum(MapLine*, float)        src/Frame.cc:369               -> pslam_lines_in_frustum
+//   Tracking::TrackManhattanFrame              src/Tracking.cc:963            -> pslam_track_manhattan_batch
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -192,6 +196,67 @@ private:
 // pslam_lba_problem and owns the output arrays of pslam_lba_result.
 inline void LocalBundleAdjustment(Context& ctx, const pslam_lba_problem& prob, pslam_lba_result& res) {
     if (pslam_local_bundle_adjustment(ctx.get(), &prob, &res) != PSLAM_OK) throw std::runtime_error(pslam_last_error(ctx.get()));
+}
+
+// void Frame::isLineGood(const cv::Mat& imGray, const cv::Mat& imDepth, cv::Mat K): fills what the reference stores per key line.
+// rand_draws: the number of libc rand() calls the process has made so far (the reference never seeds: srand(1)); it is advanced by
+// the draws this frame makes, so consecutive frames see the stream the reference's single libc stream would give them.
+inline void isLineGood(Context& ctx, const std::vector<pslam_keyline>& mvKeylinesUn, const Image16& rawDepth, float depthMapFactor, const float K[4] /* fx fy cx cy */,
+                       int32_t& rand_draws, std::vector<pslam_line3d>& lines3d) {
+    const int32_t n = (int32_t)mvKeylinesUn.size();
+    lines3d.assign(n > 0 ? n : 1, pslam_line3d());
+    if (n == 0) { lines3d.clear(); return; }
+    if (rawDepth.width != ctx.config().width || rawDepth.height != ctx.config().height) throw std::runtime_error("depth size differs from the context");
+    const uint32_t seed = 1;
+    int32_t drawn = 0;
+    if (pslam_lines3d_batch(ctx.get(), mvKeylinesUn.data(), &n, n, rawDepth.data, 1, depthMapFactor, K, &seed, &rand_draws, lines3d.data(), &drawn) != PSLAM_OK)
+        throw std::runtime_error(pslam_last_error(ctx.get()));
+    rand_draws += drawn;
+}
+
+// void Frame::ComputeStereoFromRGBD(const cv::Mat& imDepth): mvuRight / mvDepth for N key points (mvKeysUn may alias mvKeys).
+inline void ComputeStereoFromRGBD(Context& ctx, const std::vector<pslam_keypoint>& mvKeys, const std::vector<pslam_keypoint>& mvKeysUn, const Image16& rawDepth,
+                                  float depthMapFactor, float mbf, std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+    const int32_t n = (int32_t)mvKeys.size();
+    mvuRight.assign(n, -1.f); mvDepth.assign(n, -1.f);
+    if (n == 0) return;
+    if (mvKeysUn.size() != mvKeys.size()) throw std::runtime_error("mvKeysUn and mvKeys differ in size");
+    if (pslam_compute_stereo_from_rgbd_batch(ctx.get(), mvKeys.data(), mvKeysUn.data(), &n, n, rawDepth.data, 1, depthMapFactor, mbf, mvuRight.data(), mvDepth.data()) !=
+        PSLAM_OK)
+        throw std::runtime_error(pslam_last_error(ctx.get()));
+}
+
+// cv::Mat Tracking::TrackManhattanFrame(cv::Mat& mLastRcm, vector<SurfaceNormal>&, vector<FrameLine>&): normals = SurfaceNormal::normal
+// (3 floats each), directions = FrameLine::direction (3 doubles each); returns the result record (R = the returned matrix) and the
+// per-element membership masks (bit a-1: appended to vSurfaceNormal{x,y,z} / vVanishingLine{x,y,z}).
+inline pslam_manhattan_result TrackManhattanFrame(Context& ctx, const float mLastRcm[9], const std::vector<float>& normals, const std::vector<double>& directions,
+                                                  std::vector<uint8_t>& normal_mask, std::vector<uint8_t>& direction_mask) {
+    const int32_t nn = (int32_t)(normals.size() / 3), nd = (int32_t)(directions.size() / 3);
+    const int mn = nn > 0 ? nn : 1, md = nd > 0 ? nd : 1;
+    normal_mask.assign(mn, 0); direction_mask.assign(md, 0);
+    const float zero3f[3] = {0, 0, 0};
+    const double zero3d[3] = {0, 0, 0};
+    pslam_manhattan_result r;
+    if (pslam_track_manhattan_batch(ctx.get(), mLastRcm, nn ? normals.data() : zero3f, &nn, mn, nd ? directions.data() : zero3d, &nd, md, 1, &r, normal_mask.data(),
+                                    direction_mask.data()) != PSLAM_OK)
+        throw std::runtime_error(pslam_last_error(ctx.get()));
+    normal_mask.resize(nn); direction_mask.resize(nd);
+    return r;
+}
+
+// bool Frame::isInFrustum(MapLine* pML, float viewingCosLimit) for the local map lines gathered into plain arrays (GetWorldPos: 6 doubles,
+// GetNormal: 3 doubles, mfMaxDistance, mfMinDistance); returns nToMatch and fills the MapLine tracking fields.
+inline int LinesInFrustum(Context& ctx, const pslam_line_frustum_frame& frame, const std::vector<double>& worldPos, const std::vector<double>& normal,
+                          const std::vector<float>& mfMaxDistance, const std::vector<float>& mfMinDistance, float viewingCosLimit, std::vector<uint8_t>& mbTrackInView,
+                          std::vector<float>& mTrackProj /* X1 Y1 X2 Y2 */, std::vector<int32_t>& mnTrackScaleLevel, std::vector<float>& mTrackViewCos) {
+    const int n = (int)mfMaxDistance.size();
+    mbTrackInView.assign(n, 0); mTrackProj.assign((size_t)4 * n, 0.f); mnTrackScaleLevel.assign(n, 0); mTrackViewCos.assign(n, 0.f);
+    if (n == 0) return 0;
+    if (worldPos.size() != (size_t)6 * n || normal.size() != (size_t)3 * n || mfMinDistance.size() != (size_t)n) throw std::runtime_error("map line arrays differ in size");
+    const int rc = pslam_lines_in_frustum(ctx.get(), &frame, n, worldPos.data(), normal.data(), mfMaxDistance.data(), mfMinDistance.data(), viewingCosLimit,
+                                          mbTrackInView.data(), mTrackProj.data(), mnTrackScaleLevel.data(), mTrackViewCos.data());
+    if (rc < 0) throw std::runtime_error(pslam_last_error(ctx.get()));
+    return rc;
 }
 
 }  // namespace pslam_adapter

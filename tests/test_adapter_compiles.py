@@ -20,7 +20,15 @@ int main(int argc, char**) {
         pslam_adapter::Optimizer opt(ctx);
         pslam_pose_problem p{}; float T[16] = {0};
         std::vector<uint8_t> a, b, c, e, f;
-        return opt.PoseOptimization(p, T, a, b, c, e, f);
+        std::vector<pslam_keyline> kl; std::vector<pslam_line3d> l3; int32_t draws = 0;
+        pslam_adapter::isLineGood(ctx, kl, dep, 1.f / 5000.f, K, draws, l3);
+        std::vector<float> ur, dz, nrm; std::vector<double> dir;
+        pslam_adapter::ComputeStereoFromRGBD(ctx, k, k, dep, 1.f / 5000.f, 40.f, ur, dz);
+        const float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        pslam_manhattan_result mr = pslam_adapter::TrackManhattanFrame(ctx, R, nrm, dir, a, b);
+        pslam_line_frustum_frame ff{}; std::vector<int32_t> lvl; std::vector<float> mx, mn;
+        const int nv = pslam_adapter::LinesInFrustum(ctx, ff, dir, dir, mx, mn, 0.6f, a, ur, lvl, dz);
+        return opt.PoseOptimization(p, T, a, b, c, e, f) + nv + mr.svd_applied;
     }
     return 0;
 }
