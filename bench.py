@@ -475,7 +475,7 @@ def main():
         import subprocess
         try:
             env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "aux_new_kernels.py")], capture_output=True, text=True, timeout=240, env=env)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "aux_new_kernels.py")], capture_output=True, text=True, timeout=150, env=env)
             if r.returncode == 0 and r.stdout.strip():
                 aux["new_kernels"] = json.loads(r.stdout.strip().splitlines()[-1])
             else:
