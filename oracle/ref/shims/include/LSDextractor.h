@@ -1,0 +1,12 @@
+// TEST INFRASTRUCTURE ONLY.  include/peac/AHCPlaneFitter.hpp:39 includes "include/LSDextractor.h" for one type, SurfaceNormal
+// (include/LSDextractor.h:34-41; a member vector of it is declared at AHCPlaneFitter.hpp:139 and never used).  This stand-in declares that
+// type and keeps the OpenCV line_descriptor module out of the plane-extractor build.
+#pragma once
+#include <opencv2/opencv.hpp>
+class SurfaceNormal {
+public:
+    cv::Point3f normal;
+    cv::Point3f cameraPosition;
+    cv::Point2i FramePosition;
+    SurfaceNormal() {}
+};

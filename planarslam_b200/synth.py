@@ -150,3 +150,34 @@ def polygon_image(seed: int, width: int = 640, height: int = 480, n_poly: int = 
         img += amp * (_hash2(gx, gy, 91 + octv) / 255.0 - 0.5) * 2
     img = _blur3(img)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def piecewise_planar_depth(seed: int, width: int = 640, height: int = 480, n_rect: int = 14, noise_mm: float = 3.0, hole_frac: float = 0.01,
+                           curved: bool = True):
+    """uint16 depth (1/5000 m units) of a wall with `n_rect` tilted rectangular patches in front of it (depth steps at their borders), sensor
+    noise, disc-shaped holes and - optionally - one curved (non-planar) patch: more planes, more merges and more rejected blocks per
+    frame than render_frame's three-plane room.  For the plane-extractor parity tests."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 4099 + 7))
+    uu, vv = np.meshgrid(np.arange(width, dtype=np.float64), np.arange(height, dtype=np.float64))
+    z = 3.0 + 0.0006 * (uu - width / 2) + 0.0003 * (vv - height / 2)
+    for _ in range(n_rect):
+        w, h = int(rng.integers(60, width // 2)), int(rng.integers(60, height // 2))
+        x0, y0 = int(rng.integers(0, width - w)), int(rng.integers(0, height - h))
+        zc = rng.uniform(0.8, 2.8)
+        a, b = rng.normal(0, 0.0015, 2)
+        patch = zc + a * (uu - x0) + b * (vv - y0)
+        m = (uu >= x0) & (uu < x0 + w) & (vv >= y0) & (vv < y0 + h) & (patch < z)
+        z = np.where(m, patch, z)
+    if curved:
+        cx, cy, r = rng.uniform(100, width - 100), rng.uniform(100, height - 100), rng.uniform(50, 110)
+        d2 = (uu - cx) ** 2 + (vv - cy) ** 2
+        z = np.where(d2 < r * r, np.minimum(z, 1.5 - 0.4 * np.sqrt(np.maximum(1 - d2 / (r * r), 0))), z)
+    z = z + rng.normal(0, noise_mm * 1e-3, z.shape) * (z / 2.0) ** 2
+    d16 = np.clip(np.rint(z * DEPTH_FACTOR), 0, 65535).astype(np.uint16)
+    yy, xx = np.mgrid[0:height, 0:width]
+    covered, target = 0.0, hole_frac * width * height
+    while covered < target:
+        hx, hy, hr = rng.uniform(0, width), rng.uniform(0, height), rng.uniform(2.0, 9.0)
+        d16[(xx - hx) ** 2 + (yy - hy) ** 2 < hr * hr] = 0
+        covered += np.pi * hr * hr
+    return d16

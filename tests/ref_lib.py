@@ -1,0 +1,60 @@
+"""ctypes access to oracle/_ref/*.so - the REFERENCE's own sources compiled in the build container (make -C oracle ref) against the
+stand-in headers of oracle/ref/shims/.  Test infrastructure only; the libraries are prebuilt artefacts on the GPU box."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _load(name):
+    path = os.path.join(REF_DIR, name)
+    if not os.path.exists(path) and os.path.isdir("/root/reference/src"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], check=True, stdout=subprocess.DEVNULL)
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+_peac = None
+
+
+def peac_lib():
+    global _peac
+    if _peac is None:
+        L = _load("libpeac_ref.so")
+        if L is None:
+            return None
+        vp = C.c_void_p
+        L.ref_peac_run.restype = vp
+        L.ref_peac_run.argtypes = [vp, C.c_int, C.c_int] + [C.c_float] * 5
+        L.ref_peac_free.argtypes = [vp]
+        L.ref_peac_num_planes.argtypes = [vp]
+        L.ref_peac_labels.argtypes = [vp, vp]
+        L.ref_peac_plane.argtypes = [vp, C.c_int, vp, vp]
+        L.ref_peac_membership.argtypes = [vp, C.c_int, vp, C.c_int]
+        _peac = L
+    return _peac
+
+
+def ref_peac_run(depth16, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 / 5000.0)):
+    """PlaneDetection::readDepthImage + runPlaneDetection of the reference itself.  Returns (labels int32 [h][w] = membershipImg,
+    planes [(normal3 + center3 + mse + curvature, N)], plane_vertices_ lists)."""
+    L = peac_lib()
+    d = np.ascontiguousarray(depth16, np.uint16)
+    h, w = d.shape
+    p = C.c_void_p(L.ref_peac_run(d.ctypes.data, w, h, *[float(x) for x in K], float(np.float32(scale))))
+    n = L.ref_peac_num_planes(p)
+    labels = np.zeros((h, w), np.int32)
+    L.ref_peac_labels(p, labels.ctypes.data)
+    planes, members = [], []
+    for i in range(n):
+        d8, N = np.zeros(8), C.c_int()
+        L.ref_peac_plane(p, i, d8.ctypes.data, C.byref(N))
+        planes.append((d8, N.value))
+        buf = np.zeros(h * w, np.int32)
+        k = L.ref_peac_membership(p, i, buf.ctypes.data, h * w)
+        members.append(buf[:k].copy())
+    L.ref_peac_free(p)
+    return labels, planes, members

@@ -1,0 +1,45 @@
+"""Golden vectors from the REFERENCE's own code compiled in the build container (oracle/_ref, `make -C oracle ref`: the reference
+sources under /root/reference, unmodified, against the stand-in headers of oracle/ref/shims/).  /root/reference does not exist on
+the GPU box and may not exist in a later container, so the outputs are committed as small fixtures:
+  tests/golden/peac_reference.npz   PlaneDetection::readDepthImage + runPlaneDetection on seeded synthetic depth frames: per frame the
+                                    label image (membershipImg, int16-packed), plane parameters, supports and plane_vertices_ digests
+Run: python tools/make_golden_ref.py"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import ref_lib  # noqa: E402
+from planarslam_b200 import synth  # noqa: E402
+
+PEAC_SCENES = [("room", s) for s in (0, 3)] + [("patches", s) for s in (0, 2, 5, 11)]
+
+
+def peac_scene(kind, seed):
+    if kind == "room":
+        return synth.render_frame(seed=seed, frame=3 * seed)[1]
+    return synth.piecewise_planar_depth(seed, n_rect=6 + seed, curved=(seed % 2 == 0))
+
+
+def digest(a):
+    return np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), np.uint8).copy()
+
+
+if __name__ == "__main__":
+    out = {}
+    for kind, seed in PEAC_SCENES:
+        labels, planes, members = ref_lib.ref_peac_run(peac_scene(kind, seed))
+        key = f"{kind}{seed}"
+        assert labels.min() >= -32768 and labels.max() <= 32767
+        out[key + "_labels"] = labels.astype(np.int16)
+        out[key + "_planes"] = np.stack([p[0] for p in planes])
+        out[key + "_N"] = np.array([p[1] for p in planes], np.int32)
+        out[key + "_members_sha1"] = np.stack([digest(m) for m in members])
+        print(key, len(planes), "planes")
+    path = os.path.join(ROOT, "tests", "golden", "peac_reference.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
