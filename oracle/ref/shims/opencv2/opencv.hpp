@@ -5,6 +5,9 @@
 #pragma once
 #include <algorithm>
 #include <chrono>
+#include <cassert>
+#include <cmath>
+#include <math.h>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -35,41 +38,65 @@ struct Vec3b {
 };
 struct Vec2d { double v[2]; Vec2d() : v{0, 0} {} Vec2d(double a, double b) : v{a, b} {} };
 struct Point3f { float x = 0, y = 0, z = 0; };
-struct Point2i { int x = 0, y = 0; };
+template <class T>
+struct Point_ {
+    T x, y;
+    Point_() : x(0), y(0) {}
+    Point_(T a, T b) : x(a), y(b) {}
+    template <class U> Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
+    Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }        // Point2f *= float: float products
+};
+typedef Point_<int> Point2i;
+typedef Point_<int> Point;
+typedef Point_<float> Point2f;
+struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
+struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int a, int b, int w, int h) : x(a), y(b), width(w), height(h) {} };
+struct KeyPoint {
+    Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1;
+    KeyPoint() {}
+    KeyPoint(float x, float y, float s, float a = -1, float r = 0, int o = 0, int c = -1) : pt(x, y), size(s), angle(a), response(r), octave(o), class_id(c) {}
+};
 struct Range { int start, end; Range(int s, int e) : start(s), end(e) {} };
 
 inline int64_t getTickCount() { return (int64_t)std::chrono::steady_clock::now().time_since_epoch().count(); }
 inline double getTickFrequency() { return (double)std::chrono::steady_clock::period::den / std::chrono::steady_clock::period::num; }
 
+struct MatZeros { int rows, cols, type, value; };          // Mat::zeros / Mat::ones: like cv::MatExpr, assigning one to a matrix that already
+                                                           // has that size and type fills it IN PLACE (src/ORBextractor.cc:1037 relies on it)
 class Mat {
 public:
     int rows = 0, cols = 0;
+    size_t step = 0;
     Mat() {}
+    Mat(Size sz, int type) { create(sz.height, sz.width, type); }
+    Mat(const MatZeros& e) { *this = e; }
+    Mat& operator=(const MatZeros& e) { create(e.rows, e.cols, e.type); for (int r = 0; r < rows; ++r) std::memset(data_ + (size_t)r * step, 0, (size_t)cols * esz(type_)); if (e.value) setTo(e.value); return *this; }
+    static MatZeros zeros(int r, int c, int type) { return MatZeros{r, c, type, 0}; }
     Mat(int r, int c, int type) { create(r, c, type); }
-    Mat(int r, int c, int type, void* ext) : rows(r), cols(c), type_(type), step_((size_t)c * esz(type)), data_((uchar*)ext) {}     // external data, not owned
-    static Mat ones(int r, int c, int type) { Mat m(r, c, type); std::memset(m.data_, 0, (size_t)r * m.step_); m.setTo(1); return m; }
+    Mat(int r, int c, int type, void* ext, size_t stp = 0) : rows(r), cols(c), step(stp ? stp : (size_t)c * esz(type)), type_(type), data_((uchar*)ext) {}   // external data, not owned
+    static MatZeros ones(int r, int c, int type) { return MatZeros{r, c, type, 1}; }
     void create(int r, int c, int type) {
         if (data_ && r == rows && c == cols && type == type_) return;
-        rows = r; cols = c; type_ = type; step_ = (size_t)c * esz(type);
-        owner_ = std::shared_ptr<uchar>(new uchar[(size_t)r * step_ + 8], std::default_delete<uchar[]>());
+        rows = r; cols = c; type_ = type; step = (size_t)c * esz(type);
+        owner_ = std::shared_ptr<uchar>(new uchar[(size_t)r * step + 8], std::default_delete<uchar[]>());
         data_ = owner_.get();
     }
     void release() { owner_.reset(); data_ = nullptr; rows = cols = 0; }
     bool empty() const { return data_ == nullptr || rows == 0 || cols == 0; }
     int depth() const { return type_ & 7; }
     int type() const { return type_; }
-    template <class T> T& at(int r, int c) { return *(T*)(data_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
-    template <class T> const T& at(int r, int c) const { return *(const T*)(data_ + (size_t)r * step_ + (size_t)c * sizeof(T)); }
+    template <class T> T& at(int r, int c) { return *(T*)(data_ + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <class T> const T& at(int r, int c) const { return *(const T*)(data_ + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <class T> T& at(int i) { return at<T>(i / cols, i % cols); }                 // continuous matrices only (all uses here)
     Mat operator()(const Range& rr, const Range& cr) const {
-        Mat m; m.rows = rr.end - rr.start; m.cols = cr.end - cr.start; m.type_ = type_; m.step_ = step_; m.owner_ = owner_;
-        m.data_ = data_ + (size_t)rr.start * step_ + (size_t)cr.start * esz(type_);
+        Mat m; m.rows = rr.end - rr.start; m.cols = cr.end - cr.start; m.type_ = type_; m.step = step; m.owner_ = owner_;
+        m.data_ = data_ + (size_t)rr.start * step + (size_t)cr.start * esz(type_);
         return m;
     }
     Mat& setTo(int value) {
         for (int r = 0; r < rows; ++r)
             for (int c = 0; c < cols; ++c) {
-                uchar* p = data_ + (size_t)r * step_ + (size_t)c * esz(type_);
+                uchar* p = data_ + (size_t)r * step + (size_t)c * esz(type_);
                 switch (depth()) {
                     case CV_8U: for (int k = 0; k < channels(); ++k) p[k] = k == 0 ? (uchar)value : 0; break;
                     case CV_16U: *(uint16_t*)p = (uint16_t)value; break;
@@ -81,17 +108,96 @@ public:
     }
     Mat& setTo(const Vec3b& value) {
         for (int r = 0; r < rows; ++r)
-            for (int c = 0; c < cols; ++c) std::memcpy(data_ + (size_t)r * step_ + (size_t)c * 3, value.v, 3);
+            for (int c = 0; c < cols; ++c) std::memcpy(data_ + (size_t)r * step + (size_t)c * 3, value.v, 3);
         return *this;
     }
+    Mat rowRange(int a, int b) const { return (*this)(Range(a, b), Range(0, cols)); }
+    Mat colRange(int a, int b) const { return (*this)(Range(0, rows), Range(a, b)); }
+    Mat operator()(const Rect& r) const { return (*this)(Range(r.y, r.y + r.height), Range(r.x, r.x + r.width)); }
+    Mat clone() const {                                         // continuous copy (step = cols * elemSize)
+        Mat m(rows, cols, type_);
+        for (int r = 0; r < rows; ++r) std::memcpy(m.data_ + (size_t)r * m.step, data_ + (size_t)r * step, (size_t)cols * esz(type_));
+        return m;
+    }
+    uchar* ptr(int r = 0) const { return data_ + (size_t)r * step; }
+    size_t step1() const { static const size_t d[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return step / d[type_ & 7]; }
     uchar* data() const { return data_; }
 private:
     int channels() const { return (type_ >> 3) + 1; }
     static size_t esz(int type) { static const size_t d[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return d[type & 7] * (size_t)((type >> 3) + 1); }
     int type_ = 0;
-    size_t step_ = 0;
     std::shared_ptr<uchar> owner_;
     uchar* data_ = nullptr;
 };
 
 }  // namespace cv
+
+// ---- what src/ORBextractor.cc needs on top of the containers: array proxies and the six image primitives.  The primitives are the
+// oracle's restatements (oracle/cvprims.cc), each pinned bit-for-bit against cv2 4.13 (tests/test_oracle_cvprims.py); everything
+// else the extractor computes - cell grid, threshold fallback, quadtree distribution, orientation, steered BRIEF, scaling - is the
+// reference's own code.
+#include "../../../cvprims.h"
+
+#define CV_PI 3.1415926535897932384626433832795
+
+namespace cv {
+
+enum { BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16, INTER_LINEAR = 1 };
+
+inline int cvRound(double v) { return oracle::cv_round(v); }
+inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
+inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
+inline float fastAtan2(float y, float x) { return oracle::fast_atan2_deg(y, x); }
+
+class _InputArray {
+public:
+    _InputArray(const Mat& m) : m_(const_cast<Mat*>(&m)) {}
+    Mat getMat() const { return *m_; }
+    bool empty() const { return m_->empty(); }
+protected:
+    Mat* m_;
+};
+class _OutputArray : public _InputArray {
+public:
+    _OutputArray(Mat& m) : _InputArray(m) {}
+    void create(int r, int c, int type) const { m_->create(r, c, type); }
+    void release() const { m_->release(); }
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
+
+// cv::FAST(image, keypoints, threshold, nonmaxSuppression = true), TYPE_9_16
+inline void FAST(const Mat& img, std::vector<KeyPoint>& kps, int threshold, bool /*nonmax*/ = true) {
+    std::vector<oracle::FastKp> out;
+    oracle::fast_detect(oracle::Img8{img.ptr(0), img.cols, img.rows, (int)img.step}, threshold, out);
+    kps.clear();
+    for (const oracle::FastKp& k : out) kps.push_back(KeyPoint((float)k.x, (float)k.y, 7.f, -1.f, (float)k.score));
+}
+inline void resize(const Mat& src, Mat& dst, Size sz, double = 0, double = 0, int = INTER_LINEAR) {
+    dst.create(sz.height, sz.width, src.type());          // no-op for the pre-sized pyramid ROI: the result lands inside the bordered buffer
+    std::vector<uint8_t> tmp((size_t)sz.width * sz.height);
+    oracle::resize_linear_u8(oracle::Img8{src.ptr(0), src.cols, src.rows, (int)src.step}, tmp.data(), sz.width, sz.height);
+    for (int r = 0; r < sz.height; ++r) std::memcpy(dst.ptr(r), &tmp[(size_t)r * sz.width], sz.width);
+}
+inline void copyMakeBorder(const Mat& src, Mat& dst, int top, int bottom, int left, int right, int /*BORDER_REFLECT_101 [+ BORDER_ISOLATED]*/) {
+    (void)bottom; (void)left; (void)right;                // the extractor passes one width on all four sides
+    dst.create(src.rows + 2 * top, src.cols + 2 * top, src.type());
+    std::vector<uint8_t> tmp((size_t)dst.rows * dst.cols);
+    oracle::copy_make_border_reflect101(oracle::Img8{src.ptr(0), src.cols, src.rows, (int)src.step}, tmp.data(), top);
+    for (int r = 0; r < dst.rows; ++r) std::memcpy(dst.ptr(r), &tmp[(size_t)r * dst.cols], dst.cols);
+}
+inline void GaussianBlur(const Mat& src, Mat& dst, Size /*7x7*/, double /*2*/, double /*2*/, int /*BORDER_REFLECT_101*/) {
+    std::vector<uint8_t> tmp((size_t)src.rows * src.cols);
+    oracle::gaussian_blur_7x7_s2_u8(oracle::Img8{src.ptr(0), src.cols, src.rows, (int)src.step}, tmp.data());
+    dst.create(src.rows, src.cols, src.type());
+    for (int r = 0; r < src.rows; ++r) std::memcpy(dst.ptr(r), &tmp[(size_t)r * src.cols], src.cols);
+}
+struct KeyPointsFilter {                                   // only referenced by the dead ComputeKeyPointsOld (src/ORBextractor.cc:855-1032)
+    static void retainBest(std::vector<KeyPoint>& k, int n) {
+        std::stable_sort(k.begin(), k.end(), [](const KeyPoint& a, const KeyPoint& b) { return a.response > b.response; });
+        if ((int)k.size() > n) k.resize(n);
+    }
+};
+
+}  // namespace cv
+using cv::cvRound; using cv::cvFloor; using cv::cvCeil;

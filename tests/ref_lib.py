@@ -58,3 +58,30 @@ def ref_peac_run(depth16, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 /
         members.append(buf[:k].copy())
     L.ref_peac_free(p)
     return labels, planes, members
+
+
+_orb = None
+
+
+def orb_lib():
+    global _orb
+    if _orb is None:
+        L = _load("liborb_ref.so")
+        if L is None:
+            return None
+        L.ref_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _orb = L
+    return _orb
+
+
+def ref_orb_extract(gray, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, monotonic_alloc=True, cap=8192):
+    """Planar_SLAM::ORBextractor::operator() of the reference itself. Returns (key points as 28-byte records, descriptors [n][32]).
+    monotonic_alloc: the library's allocations come from a bump arena, so the quadtree's address ties follow creation order."""
+    from planarslam_b200._lib import KEYPOINT_DTYPE
+    L = orb_lib()
+    g = np.ascontiguousarray(gray, np.uint8)
+    h, w = g.shape
+    k, d = np.zeros(cap, KEYPOINT_DTYPE), np.zeros((cap, 32), np.uint8)
+    n = L.ref_orb_extract(g.ctypes.data, w, h, nfeatures, scale, nlevels, ini_th, min_th, int(bool(monotonic_alloc)), k.ctypes.data, d.ctypes.data, cap)
+    assert 0 <= n <= cap, n
+    return k[:n].copy(), d[:n].copy()

@@ -3,6 +3,8 @@ sources under /root/reference, unmodified, against the stand-in headers of oracl
 the GPU box and may not exist in a later container, so the outputs are committed as small fixtures:
   tests/golden/peac_reference.npz   PlaneDetection::readDepthImage + runPlaneDetection on seeded synthetic depth frames: per frame the
                                     label image (membershipImg, int16-packed), plane parameters, supports and plane_vertices_ digests
+  tests/golden/orb_reference.npz    Planar_SLAM::ORBextractor::operator() (monotonic allocator, see oracle/ref/orb_driver.cc) on seeded synthetic
+                                    frames: the key-point records and descriptors of two frames in full, SHA-1 digests of more
 Run: python tools/make_golden_ref.py"""
 import hashlib
 import os
@@ -29,6 +31,16 @@ def digest(a):
     return np.frombuffer(hashlib.sha1(np.ascontiguousarray(a).tobytes()).digest(), np.uint8).copy()
 
 
+ORB_CASES = [("tum%d" % s, dict(seed=s), {}) for s in (0, 7)] + [("nf500", dict(seed=1), dict(nfeatures=500)), ("nf2000", dict(seed=1), dict(nfeatures=2000)),
+                                                                    ("l4s15", dict(seed=1), dict(nlevels=4, scale=1.5)), ("th40", dict(seed=1), dict(ini_th=40, min_th=10)),
+                                                                    ("big", dict(seed=2, width=1280, height=960), dict(nfeatures=2000)),
+                                                                    ("small", dict(seed=3, width=320, height=240), {})]
+
+
+def orb_image(kw):
+    return synth.render_frame(frame=3 * kw["seed"], **kw)[0]
+
+
 if __name__ == "__main__":
     out = {}
     for kind, seed in PEAC_SCENES:
@@ -41,5 +53,16 @@ if __name__ == "__main__":
         out[key + "_members_sha1"] = np.stack([digest(m) for m in members])
         print(key, len(planes), "planes")
     path = os.path.join(ROOT, "tests", "golden", "peac_reference.npz")
+    np.savez_compressed(path, **out)
+    print(path, os.path.getsize(path), "bytes")
+    out = {}
+    for name, ikw, okw in ORB_CASES:
+        k, d = ref_lib.ref_orb_extract(orb_image(ikw), **okw)
+        out[name + "_n"] = np.array([len(k)], np.int32)
+        out[name + "_kps_sha1"], out[name + "_desc_sha1"] = digest(k), digest(d)
+        if name.startswith("tum"):
+            out[name + "_kps"], out[name + "_desc"] = k.view(np.uint8).reshape(len(k), 28), d
+        print(name, len(k), "key points")
+    path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
