@@ -6,6 +6,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cassert>
+#include <fstream>
+#include <iostream>
+#include <sstream>
 #include <cmath>
 #include <math.h>
 #include <cstdint>
@@ -120,6 +123,7 @@ public:
         return m;
     }
     uchar* ptr(int r = 0) const { return data_ + (size_t)r * step; }
+    template <class T> T* ptr(int r = 0) const { return (T*)(data_ + (size_t)r * step); }
     size_t step1() const { static const size_t d[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return step / d[type_ & 7]; }
     uchar* data() const { return data_; }
 private:
@@ -130,6 +134,30 @@ private:
     uchar* data_ = nullptr;
 };
 
+}  // namespace cv
+
+// cv::FileStorage / FileNode: named by the YAML save / load members of Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h (:1453-1632), which the
+// reference never calls (it loads ORBvoc.txt through loadFromTextFile, :1338-1434); inert placeholders so that the class template compiles.
+#include <string>
+namespace cv {
+struct FileNode {
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileNode operator[](const char*) const { return FileNode(); }
+    FileNode operator[](int) const { return FileNode(); }
+    size_t size() const { return 0; }
+    operator int() const { return 0; }
+    operator double() const { return 0; }
+    operator std::string() const { return std::string(); }
+};
+struct FileStorage {
+    enum { READ = 0, WRITE = 1 };
+    FileStorage() {}
+    FileStorage(const std::string&, int) {}
+    bool isOpened() const { return false; }
+    void release() {}
+    FileNode operator[](const std::string&) const { return FileNode(); }
+    template <class T> FileStorage& operator<<(const T&) { return *this; }
+};
 }  // namespace cv
 
 // ---- what src/ORBextractor.cc needs on top of the containers: array proxies and the six image primitives.  The primitives are the

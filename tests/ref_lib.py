@@ -85,3 +85,74 @@ def ref_orb_extract(gray, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_t
     n = L.ref_orb_extract(g.ctypes.data, w, h, nfeatures, scale, nlevels, ini_th, min_th, int(bool(monotonic_alloc)), k.ctypes.data, d.ctypes.data, cap)
     assert 0 <= n <= cap, n
     return k[:n].copy(), d[:n].copy()
+
+
+_bow = None
+
+
+def bow_lib():
+    global _bow
+    if _bow is None:
+        L = _load("libbow_ref.so")
+        if L is None:
+            return None
+        vp = C.c_void_p
+        L.ref_voc_load.restype = vp
+        L.ref_voc_load.argtypes = [C.c_char_p]
+        L.ref_voc_free.argtypes = [vp]
+        L.ref_voc_size.argtypes = [vp]
+        L.ref_bow_transform.argtypes = [vp, vp, C.c_int, C.c_int] + [vp] * 6
+        L.ref_bow_score.restype = C.c_double
+        L.ref_bow_score.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int]
+        _bow = L
+    return _bow
+
+
+def write_vocabulary_txt(voc: dict, path: str):
+    """The ORBvoc.txt format TemplatedVocabulary::loadFromTextFile reads (Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1434):
+    'k L scoring weighting' then one line per node in id order: parent isLeaf 32 descriptor bytes weight.  No trailing newline (the
+    loader's while(!f.eof()) would append an empty node)."""
+    n = len(voc["word_id"])
+    parent = np.zeros(n, np.int64)
+    for p in range(n):
+        parent[voc["child_id"][voc["child_off"][p]:voc["child_off"][p + 1]]] = p
+    lines = [f"{voc['k']} {voc['L']} 0 0"]                     # L1_NORM, TF_IDF
+    for i in range(1, n):
+        leaf = int(voc["word_id"][i] >= 0)
+        lines.append(f"{parent[i]} {leaf} " + " ".join(str(int(b)) for b in voc["desc"][i]) + f" {float(voc['weight'][i])!r}")
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+class RefVocabulary:
+    """ORBVocabulary of the reference (DBoW2 compiled from /root/reference) loaded from a text file."""
+
+    def __init__(self, path: str):
+        self.L = bow_lib()
+        self.h = C.c_void_p(self.L.ref_voc_load(path.encode()))
+        assert self.h.value, "loadFromTextFile failed"
+
+    def size(self):
+        return self.L.ref_voc_size(self.h)
+
+    def transform(self, features: np.ndarray, levelsup: int = 4):
+        f = np.ascontiguousarray(features, np.uint8)
+        n = len(f)
+        o = dict(word_id=np.zeros(n, np.int32), word_val=np.zeros(n), node_id=np.zeros(n, np.int32), node_off=np.zeros(n + 1, np.int32), node_feat=np.zeros(n, np.int32))
+        cnt = np.zeros(2, np.int32)
+        self.L.ref_bow_transform(self.h, f.ctypes.data, n, levelsup, o["word_id"].ctypes.data, o["word_val"].ctypes.data, o["node_id"].ctypes.data,
+                                 o["node_off"].ctypes.data, o["node_feat"].ctypes.data, cnt.ctypes.data)
+        nw, nn = int(cnt[0]), int(cnt[1])
+        return dict(word_id=o["word_id"][:nw], word_val=o["word_val"][:nw], node_id=o["node_id"][:nn], node_off=o["node_off"][:nn + 1],
+                    node_feat=o["node_feat"][:o["node_off"][nn]])
+
+    def score(self, a: dict, b: dict) -> float:
+        ia, va = np.ascontiguousarray(a["word_id"], np.int32), np.ascontiguousarray(a["word_val"], np.float64)
+        ib, vb = np.ascontiguousarray(b["word_id"], np.int32), np.ascontiguousarray(b["word_val"], np.float64)
+        return float(self.L.ref_bow_score(self.h, ia.ctypes.data, va.ctypes.data, len(ia), ib.ctypes.data, vb.ctypes.data, len(ib)))
+
+    def __del__(self):
+        try:
+            self.L.ref_voc_free(self.h)
+        except Exception:
+            pass

@@ -5,6 +5,8 @@ the GPU box and may not exist in a later container, so the outputs are committed
                                     label image (membershipImg, int16-packed), plane parameters, supports and plane_vertices_ digests
   tests/golden/orb_reference.npz    Planar_SLAM::ORBextractor::operator() (monotonic allocator, see oracle/ref/orb_driver.cc) on seeded synthetic
                                     frames: the key-point records and descriptors of two frames in full, SHA-1 digests of more
+  tests/golden/bow_reference.npz    ORBVocabulary::transform (DBoW2 compiled from the reference; vocabulary read by its loadFromTextFile) on synthetic
+                                    vocabularies / features: BowVector and FeatureVector in full for each case
 Run: python tools/make_golden_ref.py"""
 import hashlib
 import os
@@ -41,6 +43,15 @@ def orb_image(kw):
     return synth.render_frame(frame=3 * kw["seed"], **kw)[0]
 
 
+BOW_CASES = [(0, 10, 3, 4), (1, 10, 4, 4), (2, 6, 5, 2), (3, 9, 3, 0)]          # (seed, k, L, levelsup)
+
+
+def bow_case(seed, k, L):
+    from planarslam_b200 import synth_lines as sl
+    voc = sl.make_vocabulary(seed, k=k, L=L)
+    return voc, sl.make_features_for_vocabulary(seed + 10, voc, 1000)
+
+
 if __name__ == "__main__":
     out = {}
     for kind, seed in PEAC_SCENES:
@@ -63,6 +74,19 @@ if __name__ == "__main__":
         if name.startswith("tum"):
             out[name + "_kps"], out[name + "_desc"] = k.view(np.uint8).reshape(len(k), 28), d
         print(name, len(k), "key points")
+    import tempfile
+    bow = {}
+    for seed, k, L, lu in BOW_CASES:
+        voc, feats = bow_case(seed, k, L)
+        with tempfile.TemporaryDirectory() as td:
+            ref_lib.write_vocabulary_txt(voc, os.path.join(td, "voc.txt"))
+            r = ref_lib.RefVocabulary(os.path.join(td, "voc.txt")).transform(feats, lu)
+        for key, v in r.items():
+            bow[f"s{seed}_{key}"] = v
+        print("bow", seed, len(r["word_id"]), "words", len(r["node_id"]), "nodes")
+    bpath = os.path.join(ROOT, "tests", "golden", "bow_reference.npz")
+    np.savez_compressed(bpath, **bow)
+    print(bpath, os.path.getsize(bpath), "bytes")
     path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
