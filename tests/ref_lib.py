@@ -60,6 +60,16 @@ def ref_peac_run(depth16, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 /
     return labels, planes, members
 
 
+def ref_peac_time(depth16, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 / 5000.0)):
+    """Run the reference's plane extractor and drop the result (bench.py's CPU baseline)."""
+    L = peac_lib()
+    d = np.ascontiguousarray(depth16, np.uint16)
+    p = C.c_void_p(L.ref_peac_run(d.ctypes.data, d.shape[1], d.shape[0], *[float(x) for x in K], float(np.float32(scale))))
+    n = L.ref_peac_num_planes(p)
+    L.ref_peac_free(p)
+    return n
+
+
 _orb = None
 
 
