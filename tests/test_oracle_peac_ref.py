@@ -56,3 +56,21 @@ def test_oracle_peac_identical_to_compiled_reference():
             assert np.array_equal(members[i], o.membership[i]), (k, i)
         n_planes += len(planes)
     assert n_planes > 150
+
+
+@pytest.mark.skipif(ref_lib.peac_lib() is None, reason="oracle/_ref/libpeac_ref.so not built and no /root/reference to build it from")
+def test_oracle_peac_identical_to_compiled_reference_other_cameras_and_sizes():
+    def same(d16, K, sc):
+        labels, planes, members = ref_lib.ref_peac_run(d16, K, sc)
+        o = oracle_lib.PeacOracle(d16, K, sc)
+        assert np.array_equal(labels, o.labels) and len(planes) == len(o.planes)
+        for i, (d8, N) in enumerate(planes):
+            assert np.array_equal(d8, o.planes[i][0]) and N == o.planes[i][1][0] and np.array_equal(members[i], o.membership[i])
+        return len(planes)
+    tum, s5k = (535.4, 539.2, 320.1, 247.6), np.float32(1.0 / 5000.0)
+    d = synth.render_frame(seed=3, frame=9)[1]
+    assert same(d, (481.2, -480.0, 319.5, 239.5), s5k) >= 2                                      # Examples/RGB-D/ICL.yaml: fy < 0
+    assert same((d // 5).astype(np.uint16), tum, np.float32(1.0 / 1000.0)) >= 2               # another DepthMapFactor
+    assert same(synth.render_frame(seed=2, frame=6, width=1280, height=960)[1], (1070.8, 1078.4, 640.2, 495.2), s5k) >= 2
+    assert same(synth.render_frame(seed=2, frame=6, width=320, height=240)[1], (267.7, 269.6, 160.0, 123.8), s5k) >= 1
+    assert same(synth.piecewise_planar_depth(3)[:475, :633].copy(), tum, s5k) >= 5                # size not a multiple of the 10 x 10 block
