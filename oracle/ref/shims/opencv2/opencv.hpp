@@ -22,12 +22,14 @@ typedef unsigned char uchar;
 #define CV_16U 2
 #define CV_32S 4
 #define CV_32F 5
+#define CV_64F 6
 #define CV_MAKETYPE(depth, cn) ((depth) + (((cn) - 1) << 3))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
 #define CV_32SC1 CV_MAKETYPE(CV_32S, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 
 namespace cv {
 
@@ -40,7 +42,26 @@ struct Vec3b {
     const uchar& operator[](int i) const { return v[i]; }
 };
 struct Vec2d { double v[2]; Vec2d() : v{0, 0} {} Vec2d(double a, double b) : v{a, b} {} };
-struct Point3f { float x = 0, y = 0, z = 0; };
+template <class T>
+struct Point3_ {
+    T x, y, z;
+    Point3_() : x(0), y(0), z(0) {}
+    Point3_(T a, T b, T c) : x(a), y(b), z(c) {}
+    template <class U> Point3_(const Point3_<U>& o) : x((T)o.x), y((T)o.y), z((T)o.z) {}
+    T dot(const Point3_& o) const { return (T)(x * o.x + y * o.y + z * o.z); }
+    double ddot(const Point3_& o) const { return (double)x * o.x + (double)y * o.y + (double)z * o.z; }
+    Point3_ cross(const Point3_& o) const { return Point3_(y * o.z - z * o.y, z * o.x - x * o.z, x * o.y - y * o.x); }
+};
+typedef Point3_<float> Point3f;
+typedef Point3_<double> Point3d;
+template <class T> inline Point3_<T> operator+(const Point3_<T>& a, const Point3_<T>& b) { return Point3_<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <class T> inline Point3_<T> operator-(const Point3_<T>& a, const Point3_<T>& b) { return Point3_<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <class T> inline Point3_<T> operator-(const Point3_<T>& a) { return Point3_<T>(-a.x, -a.y, -a.z); }
+template <class T> inline Point3_<T> operator*(const Point3_<T>& a, double s) { return Point3_<T>((T)(a.x * s), (T)(a.y * s), (T)(a.z * s)); }
+template <class T> inline Point3_<T> operator*(double s, const Point3_<T>& a) { return a * s; }
+template <class T> inline Point3_<T> operator/(const Point3_<T>& a, double s) { return Point3_<T>((T)(a.x / s), (T)(a.y / s), (T)(a.z / s)); }
+template <class T> inline Point3_<T>& operator+=(Point3_<T>& a, const Point3_<T>& b) { a = a + b; return a; }
+template <class T> inline double norm(const Point3_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y + (double)p.z * p.z); }
 template <class T>
 struct Point_ {
     T x, y;
@@ -48,10 +69,21 @@ struct Point_ {
     Point_(T a, T b) : x(a), y(b) {}
     template <class U> Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
     Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }        // Point2f *= float: float products
+    T dot(const Point_& o) const { return (T)(x * o.x + y * o.y); }
+    double cross(const Point_& o) const { return (double)x * o.y - (double)y * o.x; }
 };
+template <class T> inline Point_<T> operator+(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x + b.x, a.y + b.y); }
+template <class T> inline Point_<T> operator-(const Point_<T>& a, const Point_<T>& b) { return Point_<T>(a.x - b.x, a.y - b.y); }
+template <class T> inline Point_<T> operator-(const Point_<T>& a) { return Point_<T>(-a.x, -a.y); }
+template <class T> inline Point_<T> operator*(const Point_<T>& a, double s) { return Point_<T>((T)(a.x * s), (T)(a.y * s)); }
+template <class T> inline Point_<T> operator*(double s, const Point_<T>& a) { return a * s; }
+template <class T> inline Point_<T> operator/(const Point_<T>& a, double s) { return Point_<T>((T)(a.x / s), (T)(a.y / s)); }
+template <class T> inline bool operator==(const Point_<T>& a, const Point_<T>& b) { return a.x == b.x && a.y == b.y; }
+template <class T> inline double norm(const Point_<T>& p) { return std::sqrt((double)p.x * p.x + (double)p.y * p.y); }
 typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
+typedef Point_<double> Point2d;
 struct Size { int width = 0, height = 0; Size() {} Size(int w, int h) : width(w), height(h) {} };
 struct Rect { int x = 0, y = 0, width = 0, height = 0; Rect() {} Rect(int a, int b, int w, int h) : x(a), y(b), width(w), height(h) {} };
 struct KeyPoint {
@@ -90,7 +122,6 @@ public:
     int type() const { return type_; }
     template <class T> T& at(int r, int c) { return *(T*)(data_ + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <class T> const T& at(int r, int c) const { return *(const T*)(data_ + (size_t)r * step + (size_t)c * sizeof(T)); }
-    template <class T> T& at(int i) { return at<T>(i / cols, i % cols); }                 // continuous matrices only (all uses here)
     Mat operator()(const Range& rr, const Range& cr) const {
         Mat m; m.rows = rr.end - rr.start; m.cols = cr.end - cr.start; m.type_ = type_; m.step = step; m.owner_ = owner_;
         m.data_ = data_ + (size_t)rr.start * step + (size_t)cr.start * esz(type_);
@@ -122,11 +153,25 @@ public:
         for (int r = 0; r < rows; ++r) std::memcpy(m.data_ + (size_t)r * m.step, data_ + (size_t)r * step, (size_t)cols * esz(type_));
         return m;
     }
+    template <class T, class P> T& at(const P& p) const { return const_cast<Mat*>(this)->at<T>((int)p.y, (int)p.x); }     // at<T>(cv::Point)
     uchar* ptr(int r = 0) const { return data_ + (size_t)r * step; }
     template <class T> T* ptr(int r = 0) const { return (T*)(data_ + (size_t)r * step); }
     size_t step1() const { static const size_t d[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return step / d[type_ & 7]; }
+    Mat col(int c) const { return colRange(c, c + 1); }
+    Mat row(int r) const { return rowRange(r, r + 1); }
+    Mat t() const;
+    Mat inv(int = 0) const;
+    double dot(const Mat& o) const;
+    Mat cross(const Mat& o) const;
+    void copyTo(Mat& dst) const { dst.create(rows, cols, type_); copyRows(dst); }
+    void copyTo(Mat&& view) const { copyRows(view); }             // into a row / column / ROI view of the same size
+    static Mat eye(int r, int c, int type) { Mat m(MatZeros{r, c, type, 0}); for (int i = 0; i < r && i < c; ++i) m.setd(i, i, 1.0); return m; }
+    double getd(int r, int c) const { return depth() == CV_64F ? at<double>(r, c) : (double)at<float>(r, c); }
+    void setd(int r, int c, double v) { if (depth() == CV_64F) at<double>(r, c) = v; else at<float>(r, c) = (float)v; }
+    template <class T> T& at(int i) const { return cols == 1 ? const_cast<Mat*>(this)->at<T>(i, 0) : const_cast<Mat*>(this)->at<T>(i / cols, i % cols); }
     uchar* data() const { return data_; }
 private:
+    void copyRows(Mat& dst) const { for (int r = 0; r < rows; ++r) std::memcpy(dst.data_ + (size_t)r * dst.step, data_ + (size_t)r * step, (size_t)cols * esz(type_)); }
     int channels() const { return (type_ >> 3) + 1; }
     static size_t esz(int type) { static const size_t d[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return d[type & 7] * (size_t)((type >> 3) + 1); }
     int type_ = 0;
@@ -135,6 +180,8 @@ private:
 };
 
 }  // namespace cv
+
+#include "mat_algebra.hpp"
 
 // cv::FileStorage / FileNode: named by the YAML save / load members of Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h (:1453-1632), which the
 // reference never calls (it loads ORBvoc.txt through loadFromTextFile, :1338-1434); inert placeholders so that the class template compiles.

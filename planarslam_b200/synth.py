@@ -181,3 +181,16 @@ def piecewise_planar_depth(seed: int, width: int = 640, height: int = 480, n_rec
         d16[(xx - hx) ** 2 + (yy - hy) ** 2 < hr * hr] = 0
         covered += np.pi * hr * hr
     return d16
+
+
+def noisy_depth(d16: np.ndarray, seed: int, outlier_frac: float = 0.2, sigma_m: float = 0.01):
+    """Corrupt a uint16 depth frame for the 3-D line-fit tests: `outlier_frac` of the pixels scaled by a random factor in [0.7, 1.3] and
+    Gaussian noise of `sigma_m` metres everywhere, so that the per-line RANSAC needs several iterations, rejects hypotheses in
+    verify3dLine and refits.  Returns uint16 (same 1/5000 m units)."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 131 + 9))
+    z = d16.astype(np.float64) / DEPTH_FACTOR
+    bad = rng.random(z.shape) < outlier_frac
+    z = np.where(bad, z * rng.uniform(0.7, 1.3, z.shape), z) + rng.normal(0, sigma_m, z.shape)
+    out = np.clip(np.rint(z * DEPTH_FACTOR), 0, 65535).astype(np.uint16)
+    out[d16 == 0] = 0
+    return out

@@ -166,3 +166,33 @@ class RefVocabulary:
             self.L.ref_voc_free(self.h)
         except Exception:
             pass
+
+
+_line3d = None
+
+
+def line3d_lib():
+    global _line3d
+    if _line3d is None:
+        L = _load("libline3d_ref.so")
+        if L is None:
+            return None
+        L.ref_lines3d_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_int] + [C.c_void_p] * 7
+        _line3d = L
+    return _line3d
+
+
+def ref_lines3d_frame(keylines, depth, cam, seed=1, skip=0):
+    """The reference's compPt3dCov + extract3dline_mahdist (src/LineExtractor.cpp, libc rand() after srand(seed) and `skip` draws) inside a
+    restated Frame::isLineGood loop.  Same outputs as oracle_lib.lines3d_frame (without the draw count)."""
+    from oracle_lib import KEYLINE_DTYPE
+    L = line3d_lib()
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    d = np.ascontiguousarray(depth, np.float32)
+    n = len(kl)
+    camv = np.asarray(cam, np.float32)
+    o = dict(valid=np.zeros(n, np.uint8), depth_line=np.zeros(n, np.float32), lines3d=np.zeros((n, 6)), director=np.zeros((n, 3)),
+             n_points=np.zeros(n, np.int32), n_inliers=np.zeros(n, np.int32), inliers=np.zeros(n, np.uint64))
+    L.ref_lines3d_frame(kl.ctypes.data, n, d.ctypes.data, d.shape[1], d.shape[0], camv.ctypes.data, seed, skip, o["valid"].ctypes.data, o["depth_line"].ctypes.data,
+                        o["lines3d"].ctypes.data, o["director"].ctypes.data, o["n_points"].ctypes.data, o["n_inliers"].ctypes.data, o["inliers"].ctypes.data)
+    return o

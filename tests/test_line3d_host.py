@@ -99,3 +99,22 @@ def test_body_matches_oracle_with_icl_intrinsics(host_lib):
             assert np.array_equal(p[k], o[k]), k
         assert p["n_drawn"] == o["n_drawn"] and p["valid"].sum() > 20
         assert (p["lines3d"][p["valid"].astype(bool)][:, [1, 4]] != 0).all()
+
+
+def test_body_matches_oracle_on_corrupted_depth(host_lib):
+    """Depth with outliers and noise: the RANSAC iterates (about 10 draws per line), verify3dLine rejects hypotheses, the SVD refit loop runs."""
+    draws = n_valid = 0
+    for s in range(8):
+        gray, d16, _, _ = synth.render_frame(seed=s, frame=3 * s)
+        kl, _ = oracle_lib.extract_line_segments(gray, 40)
+        dn = synth.noisy_depth(d16, s, 0.1 + 0.04 * s, 0.004 * (s + 1))
+        depth = dn.astype(np.float32) * np.float32(1.0 / synth.DEPTH_FACTOR)
+        o = oracle_lib.lines3d_frame(kl, depth, synth.TUM3_K, seed=11 + s, skip=s)
+        p = host_lines3d(host_lib, kl, dn, synth.TUM3_K, seed=11 + s, skip=s)
+        assert p["n_drawn"] == o["n_drawn"], s
+        for k in ("valid", "n_points", "inliers", "n_inliers", "lines3d", "depth_line"):
+            assert np.array_equal(p[k], o[k]), (s, k)
+        assert np.array_equal(p["director"], o["director"], equal_nan=True), s
+        draws += o["n_drawn"]
+        n_valid += int(p["valid"].sum())
+    assert draws > 3000 and 100 < n_valid < 320

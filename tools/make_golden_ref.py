@@ -7,6 +7,7 @@ the GPU box and may not exist in a later container, so the outputs are committed
                                     frames: the key-point records and descriptors of two frames in full, SHA-1 digests of more
   tests/golden/bow_reference.npz    ORBVocabulary::transform (DBoW2 compiled from the reference; vocabulary read by its loadFromTextFile) on synthetic
                                     vocabularies / features: BowVector and FeatureVector in full for each case
+  tests/golden/line3d_reference.npz the 3-D line fit of src/LineExtractor.cpp (+ libc rand) on clean and corrupted depth: every output field
 Run: python tools/make_golden_ref.py"""
 import hashlib
 import os
@@ -87,6 +88,17 @@ if __name__ == "__main__":
     bpath = os.path.join(ROOT, "tests", "golden", "bow_reference.npz")
     np.savez_compressed(bpath, **bow)
     print(bpath, os.path.getsize(bpath), "bytes")
+    from test_oracle_line3d_ref import CASES as L3_CASES, KEYS as L3_KEYS, case_inputs
+    l3 = {}
+    for s_, frac, sigma, seed in L3_CASES:
+        kl, depth = case_inputs(s_, frac, sigma)
+        r = ref_lib.ref_lines3d_frame(kl, depth, synth.TUM3_K, seed=seed)
+        for k in L3_KEYS:
+            l3[f"c{s_}_{k}"] = r[k]
+        print("line3d", s_, int(r["valid"].sum()), "valid lines")
+    lpath = os.path.join(ROOT, "tests", "golden", "line3d_reference.npz")
+    np.savez_compressed(lpath, **l3)
+    print(lpath, os.path.getsize(lpath), "bytes")
     path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
