@@ -9,7 +9,7 @@ mkdir -p $OUT
 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1
 # 1. the GPU suite as the driver runs it, then the xfail-marked tests strictly
 python -m pytest tests -q -m gpu -x > $OUT/pytest_gpu.log 2>&1; echo "pytest gpu rc=$?" >> $OUT/summary.txt
-python -m pytest tests/test_line3d_gpu.py tests/test_manhattan_gpu.py tests/test_lsd_gpu.py -q -m gpu --runxfail > $OUT/pytest_runxfail.log 2>&1; echo "pytest runxfail rc=$?" >> $OUT/summary.txt
+python -m pytest tests/test_line3d_gpu.py tests/test_manhattan_gpu.py tests/test_lsd_gpu.py tests/test_linefrustum_gpu.py tests/test_framefill.py tests/test_vs_compiled_reference_gpu.py -q -m gpu --runxfail > $OUT/pytest_runxfail.log 2>&1; echo "pytest runxfail rc=$?" >> $OUT/summary.txt
 # 2. throughput + signatures of the new kernels
 PYTHONPATH=. timeout 300 python tools/aux_new_kernels.py > $OUT/aux_new_kernels.json 2> $OUT/aux_new_kernels.err; echo "aux rc=$?" >> $OUT/summary.txt
 # 3. LSD: published iterator vs OpenCV 4.x enumeration (same bench, LSD stage only)
