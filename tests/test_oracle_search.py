@@ -49,3 +49,98 @@ def test_search_by_projection_last_frame():
     assert n == (matches >= 0).sum() and n > 150
     n_no_ori, _ = oracle_lib.search_by_projection_last(fv, lf, m, 15.0, False, False, np.full(fv["n"], -1, np.int32))
     assert n_no_ori >= n
+
+
+def _py_search_by_projection_map(fv, m, th, nnratio, matches0, cos_limit=0.5):
+    """Independent plain-Python statement of Tracking::SearchLocalPoints' visibility pass + ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th)
+    (src/Frame.cc:312-367, :439-490, :526-535; src/MapPoint.cc:419-434; src/ORBmatcher.cc:46-140), written from the reference with numpy float32
+    scalars so that every operation rounds as the C++ float code does."""
+    f = np.float32
+    T = np.asarray(fv["Tcw"], np.float32)
+    R, t = T[:3, :3], T[:3, 3]
+    fx, fy, cx, cy, bf = (f(fv[k]) for k in ("fx", "fy", "cx", "cy", "bf"))
+    mnx, mxx, mny, mxy = (f(fv[k]) for k in ("min_x", "max_x", "min_y", "max_y"))
+    sf, nlev, logsf = np.asarray(fv["scale_factors"], np.float32), int(fv["n_levels"]), f(fv["log_scale_factor"])
+    Ow = np.array([f(sum(float(-R[k, r]) * float(t[k]) for k in range(3))) for r in range(3)], np.float32)        # -R^T t, cv::Mat product
+    invw, invh = f(64) / f(mxx - mnx), f(48) / f(mxy - mny)
+    kp = fv["keys_un"]
+    grid = {}
+    for i in range(fv["n"]):                                          # Frame::AssignFeaturesToGrid / PosInGrid: round(), not floor()
+        gx, gy = float(f(f(f(kp["x"][i]) - mnx) * invw)), float(f(f(f(kp["y"][i]) - mny) * invh))
+        px = int(np.floor(gx + 0.5)) if gx >= 0 else -int(np.floor(-gx + 0.5))          # C round(): halves away from zero (numpy rounds to even)
+        py = int(np.floor(gy + 0.5)) if gy >= 0 else -int(np.floor(-gy + 0.5))
+        if 0 <= px < 64 and 0 <= py < 48:
+            grid.setdefault((px, py), []).append(i)
+    matches = np.asarray(matches0, np.int32).copy()
+    in_view = np.zeros(m["n"], np.uint8)
+    n_matches = 0
+    for k in range(m["n"]):
+        if m["skip"][k]:
+            continue
+        P = m["pos"][k].astype(np.float32)
+        Pc = np.array([f(f(sum(float(R[r, c]) * float(P[c]) for c in range(3))) + t[r]) for r in range(3)], np.float32)
+        if Pc[2] < f(0):
+            continue
+        invz = f(1) / Pc[2]
+        u, v = f(f(f(fx * Pc[0]) * invz) + cx), f(f(f(fy * Pc[1]) * invz) + cy)
+        if u < mnx or u > mxx or v < mny or v > mxy:
+            continue
+        maxd, mind = f(f(1.2) * m["max_distance"][k]), f(f(0.8) * m["min_distance"][k])
+        PO = (P - Ow).astype(np.float32)
+        dist = f(np.sqrt(sum(float(x) * float(x) for x in PO)))
+        if dist < mind or dist > maxd:
+            continue
+        view_cos = f(sum(float(PO[c]) * float(m["normal"][k][c]) for c in range(3)) / float(dist))
+        if view_cos < f(cos_limit):
+            continue
+        ratio = f(m["max_distance"][k] / dist)
+        lvl = int(np.ceil(f(f(np.log(float(ratio))) / logsf)))
+        lvl = 0 if lvl < 0 else (nlev - 1 if lvl >= nlev else lvl)
+        in_view[k] = 1
+        ur_proj = f(u - f(bf * invz))
+        r = f(2.5) if view_cos > f(0.998) else f(4.0)
+        if th != 1.0:
+            r = f(r * f(th))
+        rr = f(r * sf[lvl])
+        min_level, max_level = lvl - 1, lvl
+        x0, x1 = max(0, int(np.floor(float(f(f(f(u - mnx) - rr) * invw))))), min(63, int(np.ceil(float(f(f(f(u - mnx) + rr) * invw)))))
+        y0, y1 = max(0, int(np.floor(float(f(f(f(v - mny) - rr) * invh))))), min(47, int(np.ceil(float(f(f(f(v - mny) + rr) * invh)))))
+        if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+            continue
+        best, best2, blev, blev2, bidx = 256, 256, -1, -1, -1
+        for ix in range(x0, x1 + 1):
+            for iy in range(y0, y1 + 1):
+                for i in grid.get((ix, iy), ()):
+                    octv = int(kp["octave"][i])
+                    if octv < min_level or octv > max_level:
+                        continue
+                    if not (abs(f(f(kp["x"][i]) - u)) < rr and abs(f(f(kp["y"][i]) - v)) < rr):
+                        continue
+                    if matches[i] >= 0 and m["has_obs"][matches[i]]:
+                        continue
+                    if fv["u_right"][i] > 0 and abs(f(ur_proj - f(fv["u_right"][i]))) > rr:
+                        continue
+                    d = int(np.unpackbits(m["desc"][k] ^ fv["desc"][i]).sum())
+                    if d < best:
+                        best2, best, blev2, blev, bidx = best, d, blev, octv, i
+                    elif d < best2:
+                        blev2, best2 = octv, d
+        if best <= 100:
+            if blev == blev2 and best > f(nnratio) * best2:
+                continue
+            matches[bidx] = k
+            n_matches += 1
+    return n_matches, matches, in_view
+
+
+def test_search_by_projection_map_oracle_matches_independent_python():
+    for seed, th, nnr in ((0, 3.0, 0.8), (1, 1.0, 0.8), (2, 5.0, 0.9)):
+        fv, m, lf = scenario(f0=10 + seed, f1=11 + seed, seed=seed)
+        m["skip"][::17] = 1                                            # some points already seen in this frame / bad
+        pre = np.full(fv["n"], -1, np.int32)
+        pre[::23] = 3                                                  # key points that already hold a map point with observations
+        n, matches, in_view = oracle_lib.search_by_projection_map(fv, m, th, nnr, pre)
+        pn, pmatches, pin_view = _py_search_by_projection_map(fv, m, th, nnr, pre)
+        assert np.array_equal(in_view, pin_view), seed
+        assert n == pn and np.array_equal(matches, pmatches), seed
+        assert n > 100
