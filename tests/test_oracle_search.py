@@ -144,3 +144,132 @@ def test_search_by_projection_map_oracle_matches_independent_python():
         assert np.array_equal(in_view, pin_view), seed
         assert n == pn and np.array_equal(matches, pmatches), seed
         assert n > 100
+
+
+class _PyFrame:
+    """Plain-Python Frame pieces shared by the independent statements: the feature grid (PosInGrid rounds, src/Frame.cc:526-535) and
+    GetFeaturesInArea (:439-490)."""
+
+    def __init__(self, fv):
+        f = np.float32
+        self.fv, self.kp = fv, fv["keys_un"]
+        self.mnx, self.mxx, self.mny, self.mxy = (f(fv[k]) for k in ("min_x", "max_x", "min_y", "max_y"))
+        self.invw, self.invh = f(64) / f(self.mxx - self.mnx), f(48) / f(self.mxy - self.mny)
+        self.grid = {}
+        for i in range(fv["n"]):
+            gx, gy = float(f(f(f(self.kp["x"][i]) - self.mnx) * self.invw)), float(f(f(f(self.kp["y"][i]) - self.mny) * self.invh))
+            px = int(np.floor(gx + 0.5)) if gx >= 0 else -int(np.floor(-gx + 0.5))
+            py = int(np.floor(gy + 0.5)) if gy >= 0 else -int(np.floor(-gy + 0.5))
+            if 0 <= px < 64 and 0 <= py < 48:
+                self.grid.setdefault((px, py), []).append(i)
+
+    def features_in_area(self, u, v, r, min_level, max_level=-1):
+        f = np.float32
+        x0, x1 = max(0, int(np.floor(float(f(f(f(u - self.mnx) - r) * self.invw))))), min(63, int(np.ceil(float(f(f(f(u - self.mnx) + r) * self.invw)))))
+        y0, y1 = max(0, int(np.floor(float(f(f(f(v - self.mny) - r) * self.invh))))), min(47, int(np.ceil(float(f(f(f(v - self.mny) + r) * self.invh)))))
+        if x0 >= 64 or x1 < 0 or y0 >= 48 or y1 < 0:
+            return []
+        check = min_level > 0 or max_level >= 0
+        out = []
+        for ix in range(x0, x1 + 1):
+            for iy in range(y0, y1 + 1):
+                for i in self.grid.get((ix, iy), ()):
+                    o = int(self.kp["octave"][i])
+                    if check and (o < min_level or (max_level >= 0 and o > max_level)):
+                        continue
+                    if abs(f(f(self.kp["x"][i]) - u)) < r and abs(f(f(self.kp["y"][i]) - v)) < r:
+                        out.append(i)
+        return out
+
+
+def _py_search_by_projection_last(fv, lf, m, th, mono, check_ori, matches0):
+    """Independent statement of ORBmatcher::SearchByProjection(Frame& cur, const Frame& last, th, bMono) (src/ORBmatcher.cc:1396-1535) with
+    ComputeThreeMaxima (:1666-1707)."""
+    f = np.float32
+    F = _PyFrame(fv)
+    T, Tl = np.asarray(fv["Tcw"], np.float32), np.asarray(lf["Tcw"], np.float32)
+    R, t = T[:3, :3], T[:3, 3]
+    fx, fy, cx, cy, bf = (f(fv[k]) for k in ("fx", "fy", "cx", "cy", "bf"))
+    sf = np.asarray(fv["scale_factors"], np.float32)
+    twc = np.array([f(sum(float(-R[k, r]) * float(t[k]) for k in range(3))) for r in range(3)], np.float32)
+    tlc = np.array([f(f(sum(float(Tl[r, c]) * float(twc[c]) for c in range(3))) + Tl[r, 3]) for r in range(3)], np.float32)
+    mb = f(bf / fx)
+    forward, backward = (tlc[2] > mb) and not mono, (-tlc[2] > mb) and not mono
+    matches = np.asarray(matches0, np.int32).copy()
+    hist = [[] for _ in range(30)]
+    n = 0
+    for i in range(lf["n"]):
+        k = int(lf["map_point"][i])
+        if k < 0 or lf["outlier"][i]:
+            continue
+        P = m["pos"][k].astype(np.float32)
+        xc = np.array([f(f(sum(float(R[r, c]) * float(P[c]) for c in range(3))) + t[r]) for r in range(3)], np.float32)
+        invzc = f(1.0 / float(xc[2]))
+        if invzc < 0:
+            continue
+        u, v = f(f(f(fx * xc[0]) * invzc) + cx), f(f(f(fy * xc[1]) * invzc) + cy)
+        if u < F.mnx or u > F.mxx or v < F.mny or v > F.mxy:
+            continue
+        octv = int(lf["keys"]["octave"][i])
+        radius = f(f(th) * sf[octv])
+        if forward:
+            cand = F.features_in_area(u, v, radius, octv)
+        elif backward:
+            cand = F.features_in_area(u, v, radius, 0, octv)
+        else:
+            cand = F.features_in_area(u, v, radius, octv - 1, octv + 1)
+        best, bidx = 256, -1
+        for i2 in cand:
+            if matches[i2] >= 0 and m["has_obs"][matches[i2]]:
+                continue
+            if fv["u_right"][i2] > 0:
+                ur = f(u - f(bf * invzc))
+                if abs(f(ur - f(fv["u_right"][i2]))) > radius:
+                    continue
+            d = int(np.unpackbits(m["desc"][k] ^ fv["desc"][i2]).sum())
+            if d < best:
+                best, bidx = d, i2
+        if best <= 100:
+            matches[bidx] = k
+            n += 1
+            if check_ori:
+                rot = f(f(lf["keys"]["angle"][i]) - f(F.kp["angle"][bidx]))
+                if rot < 0:
+                    rot = f(rot + f(360))
+                g = float(f(rot * f(f(1.0) / f(30))))
+                b = int(np.floor(g + 0.5))
+                if b == 30:
+                    b = 0
+                hist[b].append(bidx)
+    if check_ori:
+        mx, ind = [0, 0, 0], [-1, -1, -1]
+        for i in range(30):
+            sz = len(hist[i])
+            if sz > mx[0]:
+                mx, ind = [sz, mx[0], mx[1]], [i, ind[0], ind[1]]
+            elif sz > mx[1]:
+                mx, ind = [mx[0], sz, mx[1]], [ind[0], i, ind[1]]
+            elif sz > mx[2]:
+                mx[2], ind[2] = sz, i
+        if mx[1] < f(0.1) * f(mx[0]):
+            ind[1] = ind[2] = -1
+        elif mx[2] < f(0.1) * f(mx[0]):
+            ind[2] = -1
+        for i in range(30):
+            if i not in ind:
+                for j in hist[i]:
+                    matches[j] = -1
+                    n -= 1
+    return n, matches
+
+
+def test_search_by_projection_last_oracle_matches_independent_python():
+    for seed, th, mono, ori in ((0, 15.0, False, True), (1, 7.0, False, True), (2, 15.0, True, False), (3, 30.0, False, True)):
+        fv, m, lf = scenario(f0=10 + 2 * seed, f1=11 + 2 * seed + (seed == 3), seed=seed)
+        lf["outlier"][::13] = 1
+        pre = np.full(fv["n"], -1, np.int32)
+        pre[::29] = 5
+        n, matches = oracle_lib.search_by_projection_last(fv, lf, m, th, mono, ori, pre)
+        pn, pmatches = _py_search_by_projection_last(fv, lf, m, th, mono, ori, pre)
+        assert n == pn and np.array_equal(matches, pmatches), seed
+        assert n > 100
