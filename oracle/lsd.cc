@@ -41,10 +41,11 @@ void gaussian_blur_7x7_s075_u8(const Img8& s, uint8_t* dst) {
 }
 
 // cv::resize(u8, INTER_LINEAR_EXACT): 8.8 fixed-point coefficients, horizontal pass in 8.8, vertical in 16.16, round half up
-void resize_linear_exact_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh) {
-    auto coef = [](int dn, int sn, std::vector<int>& idx, std::vector<int>& a) {
+// cv::resize(src, dst, Size(), fx, fy, INTER_LINEAR_EXACT): the destination size is cvRound(size * f) but the sampling step stays 1 / f
+// (it is NOT recomputed as src / dst; the two differ whenever size * f is not an integer - checked against cv2 on 641 x 479)
+void resize_linear_exact_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh, double inv_fx, double inv_fy) {
+    auto coef = [](int dn, int sn, double scale, std::vector<int>& idx, std::vector<int>& a) {
         idx.resize(dn); a.resize(dn);
-        const double scale = (double)sn / dn;
         for (int d = 0; d < dn; ++d) {
             const double f = (d + 0.5) * scale - 0.5;
             int i = (int)std::floor(f);
@@ -55,7 +56,7 @@ void resize_linear_exact_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, in
         }
     };
     std::vector<int> ix, ax, iy, ay;
-    coef(dw, sw, ix, ax); coef(dh, sh, iy, ay);
+    coef(dw, sw, inv_fx, ix, ax); coef(dh, sh, inv_fy, iy, ay);
     std::vector<uint32_t> hl((size_t)sh * dw);
     for (int y = 0; y < sh; ++y)
         for (int x = 0; x < dw; ++x) {
@@ -480,7 +481,7 @@ void lsd_detect_stages(const Img8& img, int refine, std::vector<LsdSegment>& out
     gaussian_blur_7x7_s075_u8(img, st.blurred.data());
     L.W = cv_round(img.w * SCALE); L.H = cv_round(img.h * SCALE);
     L.scaled.resize((size_t)L.W * L.H);
-    resize_linear_exact_u8(st.blurred.data(), img.w, img.h, L.scaled.data(), L.W, L.H);
+    resize_linear_exact_u8(st.blurred.data(), img.w, img.h, L.scaled.data(), L.W, L.H, 1.0 / SCALE, 1.0 / SCALE);
     L.ll_angle(rho, N_BINS);
     L.LOG_NT = 5 * (std::log10(double(L.W)) + std::log10(double(L.H))) / 2 + std::log10(11.0);
     const size_t min_reg_size = size_t(-L.LOG_NT / std::log10(p));

@@ -63,9 +63,11 @@ int lsd_alloc(pslam_ctx* c) {
     g.density_th = 0.7; g.log_eps = 0;
     B.max_batch = c->cfg.max_batch;
     // INTER_LINEAR_EXACT taps (8.8 fixed point)
-    auto coef = [](int dn, int sn, std::vector<int16_t>& idx, std::vector<int16_t>& a) {
+    // cv::resize(src, dst, Size(), 0.8, 0.8, INTER_LINEAR_EXACT): destination size cvRound(0.8 * size), sampling step exactly 1 / 0.8 (not src / dst;
+    // the two coincide when 0.8 * size is an integer, e.g. 640 x 480 and 1280 x 960)
+    auto coef = [SCALE](int dn, int sn, std::vector<int16_t>& idx, std::vector<int16_t>& a) {
         idx.resize(dn); a.resize(dn);
-        const double scale = (double)sn / dn;
+        const double scale = 1.0 / SCALE;
         for (int d = 0; d < dn; ++d) {
             const double f = (d + 0.5) * scale - 0.5;
             int i = (int)std::floor(f);

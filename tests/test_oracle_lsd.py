@@ -95,3 +95,19 @@ def test_extract_line_segments_keylines():
     l = np.cross(sp, ep)
     assert np.allclose(lf, l / np.linalg.norm(l, axis=1, keepdims=True), rtol=1e-14, atol=0)
     assert np.allclose(kl["lineLength"], np.hypot(top[:, 0] - top[:, 2], top[:, 1] - top[:, 3]), rtol=1e-6)
+
+
+def test_lsd_oracle_other_image_sizes_vs_cv2():
+    """1280 x 960 (BASELINE config 5), 320 x 240, and sizes whose 0.8-scaled dimensions are not integers (641 x 479, 333 x 251): the down-scaling samples with
+    step 1 / 0.8 while the destination size is cvRound(0.8 * size) - cv::resize(..., Size(), 0.8, 0.8, INTER_LINEAR_EXACT)."""
+    cases = [synth.render_frame(seed=2, frame=6, width=1280, height=960)[0], synth.render_frame(seed=3, frame=9, width=320, height=240)[0]]
+    base = synth.render_frame(seed=5, frame=15)[0]
+    cases += [np.ascontiguousarray(np.pad(base[:479], ((0, 0), (0, 1)), mode="edge")), np.ascontiguousarray(base[100:351, 200:533])]
+    for g in cases:
+        for refine, flag in ((1, cv2.LSD_REFINE_STD), (2, cv2.LSD_REFINE_ADV)):
+            segs, width, prec, nfa = oracle_lib.lsd_detect(g, refine, cap=65536, rect_enum=3)
+            ref = cv2.createLineSegmentDetector(flag).detect(g)
+            assert len(segs) == len(ref[0]) > 100, g.shape
+            assert np.array_equal(segs, ref[0].reshape(-1, 4)) and np.array_equal(width, ref[1].ravel()) and np.array_equal(prec, ref[2].ravel()), g.shape
+            if refine == 2:
+                assert np.array_equal(nfa, ref[3].ravel()), g.shape
