@@ -111,3 +111,31 @@ def test_lsd_oracle_other_image_sizes_vs_cv2():
             assert np.array_equal(segs, ref[0].reshape(-1, 4)) and np.array_equal(width, ref[1].ravel()) and np.array_equal(prec, ref[2].ravel()), g.shape
             if refine == 2:
                 assert np.array_equal(nfa, ref[3].ravel()), g.shape
+
+
+def test_lsd_oracle_fuzz_sizes_and_content_vs_cv2():
+    """Random image sizes (24 .. 420 x 24 .. 320) and content (noise, blurred noise, filled polygons, crops of the synthetic room): all three refinement
+    modes identical to cv2 in every field (180 such cases were run when the enumeration was pinned; 24 are kept here)."""
+    rng = np.random.default_rng(1)
+    for it in range(24):
+        w, h = int(rng.integers(24, 420)), int(rng.integers(24, 320))
+        kind = it % 4
+        if kind == 0:
+            g = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif kind == 1:
+            g = cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (0, 0), 3)
+        elif kind == 2:
+            g = np.zeros((h, w), np.uint8)
+            for _ in range(6):
+                cv2.fillPoly(g, [rng.integers(0, [w, h], (4, 2)).astype(np.int32)], int(rng.integers(40, 255)))
+        else:
+            g = synth.render_frame(seed=it, frame=it)[0][:h, :w].copy()
+        for refine, flag in ((0, cv2.LSD_REFINE_NONE), (1, cv2.LSD_REFINE_STD), (2, cv2.LSD_REFINE_ADV)):
+            segs, width, prec, nfa = oracle_lib.lsd_detect(g, refine, cap=65536, rect_enum=3)
+            ref = cv2.createLineSegmentDetector(flag).detect(g)
+            if ref[0] is None:
+                assert len(segs) == 0, (it, refine)
+                continue
+            assert np.array_equal(segs, ref[0].reshape(-1, 4)) and np.array_equal(width, ref[1].ravel()) and np.array_equal(prec, ref[2].ravel()), (it, refine, w, h)
+            if refine == 2:
+                assert np.array_equal(nfa, ref[3].ravel()), (it, w, h)

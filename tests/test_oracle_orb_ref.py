@@ -69,3 +69,31 @@ def test_allocator_dependence_of_the_reference_is_confined_to_ties():
         a = {(int(q["octave"]), float(q["x"]), float(q["y"])) for q in k0}
         b = {(int(q["octave"]), float(q["x"]), float(q["y"])) for q in k1}
         assert len(a - b) <= 0.03 * len(a)
+
+
+@pytest.mark.skipif(ref_lib.orb_lib() is None, reason="oracle/_ref/liborb_ref.so not built and no /root/reference to build it from")
+def test_oracle_orb_fuzz_sizes_settings_and_content_vs_compiled_reference():
+    """Random image sizes (160 .. 700 x 120 .. 520), content, feature counts, level counts and scale factors (pyramids whose top level stays above 40 px: the
+    reference itself fails on smaller ones)."""
+    import cv2
+    rng = np.random.default_rng(2)
+    done = 0
+    for it in range(60):
+        w, h = int(rng.integers(160, 700)), int(rng.integers(120, 520))
+        nf, nl, sf = int(rng.choice([300, 1000, 1500])), int(rng.choice([4, 8])), float(rng.choice([1.2, 1.5]))
+        if min(w, h) / sf ** (nl - 1) < 40 or w < 0.75 * h:      # portrait frames with (w - 32) / (h - 32) < 0.5 at some level give nIni = 0 root nodes in
+            continue                                               # DistributeOctTree (src/ORBextractor.cc:543-550): the reference indexes an empty vector
+        kind = it % 3
+        if kind == 0:
+            g = cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (0, 0), 1.5)
+        elif kind == 1:
+            g = np.zeros((h, w), np.uint8)
+            for _ in range(25):
+                cv2.fillPoly(g, [rng.integers(0, [w, h], (4, 2)).astype(np.int32)], int(rng.integers(40, 255)))
+        else:
+            g = synth.render_frame(seed=it, frame=it, width=w, height=h)[0]
+        k, d = ref_lib.ref_orb_extract(g, nfeatures=nf, scale=sf, nlevels=nl)
+        ok, od = _oracle(g, nfeatures=nf, scale=sf, nlevels=nl)
+        assert len(k) == len(ok) and k.tobytes() == ok.tobytes() and np.array_equal(d, od), (it, w, h, nf, nl, sf)
+        done += 1
+    assert done >= 25
