@@ -74,3 +74,22 @@ def test_oracle_peac_identical_to_compiled_reference_other_cameras_and_sizes():
     assert same(synth.render_frame(seed=2, frame=6, width=1280, height=960)[1], (1070.8, 1078.4, 640.2, 495.2), s5k) >= 2
     assert same(synth.render_frame(seed=2, frame=6, width=320, height=240)[1], (267.7, 269.6, 160.0, 123.8), s5k) >= 1
     assert same(synth.piecewise_planar_depth(3)[:475, :633].copy(), tum, s5k) >= 5                # size not a multiple of the 10 x 10 block
+
+
+@pytest.mark.skipif(ref_lib.peac_lib() is None, reason="oracle/_ref/libpeac_ref.so not built and no /root/reference to build it from")
+def test_oracle_peac_fuzz_vs_compiled_reference():
+    """Random image sizes (not multiples of the block size), cameras (some with fy < 0), patch counts, noise levels and hole fractions."""
+    rng = np.random.default_rng(5)
+    n_planes = 0
+    for it in range(24):
+        w, h = int(rng.integers(100, 700)), int(rng.integers(100, 520))
+        d = synth.piecewise_planar_depth(100 + it, width=max(w, 200), height=max(h, 200), n_rect=int(rng.integers(3, 25)), noise_mm=float(rng.uniform(0.5, 12)),
+                                         hole_frac=float(rng.uniform(0, 0.08)), curved=bool(it % 2))[:h, :w].copy()
+        K = (float(rng.uniform(300, 700)), float(rng.uniform(300, 700)) * (1 if it % 5 else -1), w / 2 + float(rng.normal(0, 5)), h / 2 + float(rng.normal(0, 5)))
+        labels, planes, members = ref_lib.ref_peac_run(d, K)
+        o = oracle_lib.PeacOracle(d, K)
+        assert np.array_equal(labels, o.labels) and len(planes) == len(o.planes), (it, w, h)
+        for i, (d8, N) in enumerate(planes):
+            assert np.array_equal(d8, o.planes[i][0]) and N == o.planes[i][1][0] and np.array_equal(members[i], o.membership[i]), (it, i)
+        n_planes += len(planes)
+    assert n_planes > 80
