@@ -196,3 +196,32 @@ def ref_lines3d_frame(keylines, depth, cam, seed=1, skip=0):
     L.ref_lines3d_frame(kl.ctypes.data, n, d.ctypes.data, d.shape[1], d.shape[0], camv.ctypes.data, seed, skip, o["valid"].ctypes.data, o["depth_line"].ctypes.data,
                         o["lines3d"].ctypes.data, o["director"].ctypes.data, o["n_points"].ctypes.data, o["n_inliers"].ctypes.data, o["inliers"].ctypes.data)
     return o
+
+
+_pose = None
+
+
+def pose_lib():
+    global _pose
+    if _pose is None:
+        L = _load("libpose_ref.so")
+        if L is None:
+            return None
+        L.ref_pose_optimization.argtypes = [C.c_void_p] * 9
+        _pose = L
+    return _pose
+
+
+def ref_pose_optimization(p: dict):
+    """PoseOptimization run by the reference's own g2o, edges and Converter (compiled against the Eigen stand-in) on a planarslam_b200.synth_pose problem;
+    the graph construction and the four optimise-and-classify rounds are restated in oracle/ref/pose_driver.cc.  Same keys as oracle_lib.pose_optimization."""
+    import oracle_lib
+    L = pose_lib()
+    s = oracle_lib.pose_problem_struct(p)
+    T0 = np.ascontiguousarray(p["Tcw0"], np.float32)
+    Td = np.zeros((4, 4))
+    o = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes, s.n_par, s.n_ver)]
+    it = np.zeros(4, np.int32)
+    n = L.ref_pose_optimization(C.byref(s), T0.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], it.ctypes.data)
+    return dict(Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes], outlier_par=o[3][:s.n_par],
+                outlier_ver=o[4][:s.n_ver], iterations=it)

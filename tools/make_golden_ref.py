@@ -8,6 +8,7 @@ the GPU box and may not exist in a later container, so the outputs are committed
   tests/golden/bow_reference.npz    ORBVocabulary::transform (DBoW2 compiled from the reference; vocabulary read by its loadFromTextFile) on synthetic
                                     vocabularies / features: BowVector and FeatureVector in full for each case
   tests/golden/line3d_reference.npz the 3-D line fit of src/LineExtractor.cpp (+ libc rand) on clean and corrupted depth: every output field
+  tests/golden/pose_reference.npz   PoseOptimization by the reference's g2o (libpose_ref.so): optimised pose, inlier count and outlier flags
 Run: python tools/make_golden_ref.py"""
 import hashlib
 import os
@@ -99,6 +100,16 @@ if __name__ == "__main__":
     lpath = os.path.join(ROOT, "tests", "golden", "line3d_reference.npz")
     np.savez_compressed(lpath, **l3)
     print(lpath, os.path.getsize(lpath), "bytes")
+    from test_oracle_pose_ref import FLAGS as POSE_FLAGS, GOLD_CASES as POSE_CASES
+    from planarslam_b200 import synth_pose
+    pg = {}
+    for i, kw in enumerate(POSE_CASES):
+        r = ref_lib.ref_pose_optimization(synth_pose.make_pose_problem(**kw))
+        pg[f"c{i}_Tcw_d"], pg[f"c{i}_n"] = r["Tcw_d"], np.array([r["n_inliers"]], np.int32)
+        for k in POSE_FLAGS:
+            pg[f"c{i}_{k}"] = r[k]
+        print("pose", i, r["n_inliers"], "inliers")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pose_reference.npz"), **pg)
     path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
