@@ -234,4 +234,156 @@ int ref_pose_optimization(const ref_pose_problem* P, const float* Tcw_in, double
     for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Tcw_d[4 * i + j] = T(i, j);
     return nInitialCorrespondences - nBad;
 }
+
+// Optimizer::TranslationOptimization (src/Optimizer.cc:2995-3737) restated the same way: rotation frozen, points / line end points pre-rotated by the float
+// R_cw, only point correspondences counted, early return before the plane edges when there are fewer than three, planes of the first family only.
+int ref_translation_optimization(const ref_pose_problem* P, const float* Tcw_in, double* Tcw_d, uint8_t* o_pt, uint8_t* o_line, uint8_t* o_plane, int32_t* iters) {
+    g2o::SparseOptimizer optimizer;
+    g2o::BlockSolver_6_3::LinearSolverType* linearSolver = new g2o::LinearSolverDense<g2o::BlockSolver_6_3::PoseMatrixType>();
+    g2o::BlockSolver_6_3* solver_ptr = new g2o::BlockSolver_6_3(linearSolver);
+    g2o::OptimizationAlgorithmLevenberg* solver = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
+    optimizer.setAlgorithm(solver);
+    cv::Mat mTcw(4, 4, CV_32F);
+    for (int i = 0; i < 16; ++i) mTcw.at<float>(i / 4, i % 4) = Tcw_in[i];
+    int nInitialCorrespondences = 0;
+    g2o::VertexSE3Expmap* vSE3 = new g2o::VertexSE3Expmap();
+    vSE3->setEstimate(Converter::toSE3Quat(mTcw));
+    vSE3->setId(0);
+    vSE3->setFixed(false);
+    optimizer.addVertex(vSE3);
+    cv::Mat R_cw = mTcw.rowRange(0, 3).colRange(0, 3).clone();
+    std::vector<g2o::EdgeSE3ProjectXYZOnlyTranslation*> eMono; std::vector<int> iMono;
+    std::vector<g2o::EdgeStereoSE3ProjectXYZOnlyTranslation*> eStereo; std::vector<int> iStereo;
+    const float deltaMono = sqrt(5.991), deltaStereo = sqrt(7.815);
+    auto f3 = [](double a, double b, double c) { cv::Mat m(3, 1, CV_32F); m.at<float>(0) = (float)a; m.at<float>(1) = (float)b; m.at<float>(2) = (float)c; return m; };
+    for (int i = 0; i < P->n_points; ++i) {
+        o_pt[i] = 0;
+        ++nInitialCorrespondences;
+        const float invSigma2 = P->inv_sigma2[i];
+        cv::Mat Xw = f3(P->Xw[3 * i], P->Xw[3 * i + 1], P->Xw[3 * i + 2]);
+        cv::Mat Xc = R_cw * Xw;
+        if (P->obs[3 * i + 2] < 0) {
+            Eigen::Matrix<double, 2, 1> obs;
+            obs << P->obs[3 * i], P->obs[3 * i + 1];
+            g2o::EdgeSE3ProjectXYZOnlyTranslation* e = new g2o::EdgeSE3ProjectXYZOnlyTranslation();
+            e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(optimizer.vertex(0)));
+            e->setMeasurement(obs);
+            e->setInformation(Eigen::Matrix2d::Identity() * invSigma2);
+            g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+            e->setRobustKernel(rk);
+            rk->setDelta(deltaMono);
+            e->fx = P->fx; e->fy = P->fy; e->cx = P->cx; e->cy = P->cy;
+            for (int k = 0; k < 3; ++k) e->Xc[k] = Xc.at<float>(k);
+            optimizer.addEdge(e);
+            eMono.push_back(e); iMono.push_back(i);
+        } else {
+            Eigen::Matrix<double, 3, 1> obs;
+            obs << P->obs[3 * i], P->obs[3 * i + 1], P->obs[3 * i + 2];
+            g2o::EdgeStereoSE3ProjectXYZOnlyTranslation* e = new g2o::EdgeStereoSE3ProjectXYZOnlyTranslation();
+            e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(optimizer.vertex(0)));
+            e->setMeasurement(obs);
+            Eigen::Matrix3d Info = Eigen::Matrix3d::Identity() * invSigma2;
+            e->setInformation(Info);
+            g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+            e->setRobustKernel(rk);
+            rk->setDelta(deltaStereo);
+            e->fx = P->fx; e->fy = P->fy; e->cx = P->cx; e->cy = P->cy; e->bf = P->bf;
+            for (int k = 0; k < 3; ++k) e->Xc[k] = Xc.at<float>(k);
+            optimizer.addEdge(e);
+            eStereo.push_back(e); iStereo.push_back(i);
+        }
+    }
+    std::vector<EdgeLineProjectXYZOnlyTranslation*> eLs, eLe;
+    for (int i = 0; i < P->n_lines; ++i) {
+        o_line[i] = 0;
+        Eigen::Vector3d line_obs(P->line_obs[3 * i], P->line_obs[3 * i + 1], P->line_obs[3 * i + 2]);
+        for (int s = 0; s < 2; ++s) {
+            EdgeLineProjectXYZOnlyTranslation* el = new EdgeLineProjectXYZOnlyTranslation();
+            el->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(optimizer.vertex(0)));
+            el->setMeasurement(line_obs);
+            el->setInformation(Eigen::Matrix3d::Identity() * 1);
+            g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+            el->setRobustKernel(rk);
+            rk->setDelta(deltaStereo);
+            el->fx = P->fx; el->fy = P->fy; el->cx = P->cx; el->cy = P->cy;
+            cv::Mat Xw = Converter::toCvVec(Eigen::Vector3d(P->line_Xw[6 * i + 3 * s], P->line_Xw[6 * i + 3 * s + 1], P->line_Xw[6 * i + 3 * s + 2]));
+            cv::Mat Xc = R_cw * Xw;
+            for (int k = 0; k < 3; ++k) el->Xc[k] = Xc.at<float>(k);
+            optimizer.addEdge(el);
+            (s == 0 ? eLs : eLe).push_back(el);
+        }
+    }
+    for (int i = 0; i < 16; ++i) Tcw_d[i] = Tcw_in[i];
+    for (int i = 0; i < 4; ++i) iters[i] = -1;
+    for (int i = 0; i < P->n_planes; ++i) o_plane[i] = 0;
+    if (nInitialCorrespondences < 3) return 0;
+    double angleInfo = P->angle_info; angleInfo = 3282.8 / (angleInfo * angleInfo);
+    double disInfo = P->dist_info; disInfo = disInfo * disInfo;
+    const double planeChi = P->plane_chi;
+    const float deltaPlane = sqrt(planeChi);
+    std::vector<g2o::EdgePlaneOnlyTranslation*> ePl;
+    for (int i = 0; i < P->n_planes; ++i) {
+        g2o::EdgePlaneOnlyTranslation* e = new g2o::EdgePlaneOnlyTranslation();
+        e->setVertex(0, dynamic_cast<g2o::OptimizableGraph::Vertex*>(optimizer.vertex(0)));
+        e->setMeasurement(Converter::toPlane3D(coeff4(P->plane_meas + 4 * i)));
+        Eigen::Matrix3d Info;
+        Info << angleInfo, 0, 0, 0, angleInfo, 0, 0, 0, disInfo;
+        e->setInformation(Info);
+        g2o::Plane3D Xw = Converter::toPlane3D(coeff4(P->plane_map + 4 * i));
+        Xw.rotateNormal(Converter::toMatrix3d(R_cw));
+        e->Xc = Xw;
+        g2o::RobustKernelHuber* rk = new g2o::RobustKernelHuber;
+        e->setRobustKernel(rk);
+        rk->setDelta(deltaPlane);
+        optimizer.addEdge(e);
+        ePl.push_back(e);
+        e->computeError();
+    }
+    const float chi2Mono[4] = {5.991, 5.991, 5.991, 5.991};
+    const float chi2Stereo[4] = {7.815, 7.815, 7.815, 7.815};
+    const int its[4] = {10, 10, 10, 10};
+    int nBad = 0;
+    for (size_t it = 0; it < 4; it++) {
+        vSE3->setEstimate(Converter::toSE3Quat(mTcw));
+        optimizer.initializeOptimization(0);
+        iters[it] = optimizer.optimize(its[it]);
+        nBad = 0;
+        for (size_t i = 0; i < eMono.size(); i++) {
+            g2o::EdgeSE3ProjectXYZOnlyTranslation* e = eMono[i];
+            const int idx = iMono[i];
+            if (o_pt[idx]) e->computeError();
+            const float chi2 = e->chi2();
+            if (chi2 > chi2Mono[it]) { o_pt[idx] = 1; e->setLevel(1); nBad++; } else { o_pt[idx] = 0; e->setLevel(0); }
+            if (it == 2) e->setRobustKernel(0);
+        }
+        for (size_t i = 0; i < eStereo.size(); i++) {
+            g2o::EdgeStereoSE3ProjectXYZOnlyTranslation* e = eStereo[i];
+            const int idx = iStereo[i];
+            if (o_pt[idx]) e->computeError();
+            const float chi2 = e->chi2();
+            if (chi2 > chi2Stereo[it]) { o_pt[idx] = 1; e->setLevel(1); nBad++; } else { e->setLevel(0); o_pt[idx] = 0; }
+            if (it == 2) e->setRobustKernel(0);
+        }
+        for (size_t i = 0; i < eLs.size(); i++) {
+            EdgeLineProjectXYZOnlyTranslation *e1 = eLs[i], *e2 = eLe[i];
+            if (o_line[i]) { e1->computeError(); e2->computeError(); }
+            const float chi2_s = e1->chiline(), chi2_e = e2->chiline();
+            if (chi2_s > 2 * chi2Mono[it] || chi2_e > 2 * chi2Mono[it]) { o_line[i] = 1; e1->setLevel(1); e2->setLevel(1); }
+            else { o_line[i] = 0; e1->setLevel(0); e2->setLevel(0); }
+            if (it == 2) { e1->setRobustKernel(0); e2->setRobustKernel(0); }
+        }
+        for (size_t i = 0; i < ePl.size(); i++) {
+            g2o::EdgePlaneOnlyTranslation* e = ePl[i];
+            if (o_plane[i]) e->computeError();
+            const float chi2 = e->chi2();
+            if (chi2 > planeChi) { o_plane[i] = 1; e->setLevel(1); nBad++; } else { e->setLevel(0); o_plane[i] = 0; }
+            if (it == 2) e->setRobustKernel(0);
+        }
+        if (optimizer.edges().size() < 10) break;
+    }
+    g2o::VertexSE3Expmap* vSE3_recov = static_cast<g2o::VertexSE3Expmap*>(optimizer.vertex(0));
+    const Eigen::Matrix<double, 4, 4> T = vSE3_recov->estimate().to_homogeneous_matrix();
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Tcw_d[4 * i + j] = T(i, j);
+    return nInitialCorrespondences - nBad;
+}
 }

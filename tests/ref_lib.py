@@ -208,6 +208,7 @@ def pose_lib():
         if L is None:
             return None
         L.ref_pose_optimization.argtypes = [C.c_void_p] * 9
+        L.ref_translation_optimization.argtypes = [C.c_void_p] * 7
         _pose = L
     return _pose
 
@@ -225,3 +226,16 @@ def ref_pose_optimization(p: dict):
     n = L.ref_pose_optimization(C.byref(s), T0.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], it.ctypes.data)
     return dict(Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes], outlier_par=o[3][:s.n_par],
                 outlier_ver=o[4][:s.n_ver], iterations=it)
+
+
+def ref_translation_optimization(p: dict):
+    """TranslationOptimization by the reference's g2o and OnlyTranslation edges (oracle/ref/pose_driver.cc)."""
+    import oracle_lib
+    L = pose_lib()
+    s = oracle_lib.pose_problem_struct(p)
+    T0 = np.ascontiguousarray(p["Tcw0"], np.float32)
+    Td = np.zeros((4, 4))
+    o = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes)]
+    it = np.zeros(4, np.int32)
+    n = L.ref_translation_optimization(C.byref(s), T0.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], it.ctypes.data)
+    return dict(Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes], iterations=it)

@@ -45,3 +45,20 @@ def test_oracle_pose_agrees_with_compiled_reference_g2o():
     for kw in cases:
         p = synth_pose.make_pose_problem(**kw)
         _same(oracle_lib.pose_optimization(p), ref_lib.ref_pose_optimization(p))
+
+
+@pytest.mark.skipif(ref_lib.pose_lib() is None, reason="oracle/_ref/libpose_ref.so not built and no /root/reference to build it from")
+def test_oracle_translation_optimization_agrees_with_compiled_reference_g2o():
+    """Optimizer::TranslationOptimization (src/Optimizer.cc:2995-3737) with the reference's OnlyTranslation edges: identical inlier counts and flags,
+    rotation untouched on both sides, translation within 5e-6 m."""
+    cases = [dict(seed=s, frame=3 * s, rot_pert=0.0 if s % 2 == 0 else 0.003) for s in range(8)]
+    cases += [dict(seed=40 + s, frame=s, outlier_frac=0.25, trans_pert=0.08) for s in range(3)]
+    cases += [dict(seed=50, frame=4, n_points=2, n_lines=5, n_planes=3, outlier_frac=0.0), dict(seed=51, frame=6, n_points=25, n_lines=0, n_planes=0)]
+    for kw in cases:
+        p = synth_pose.make_pose_problem(**kw)
+        o, r = oracle_lib.pose_optimization(p, translation_only=True), ref_lib.ref_translation_optimization(p)
+        assert o["n_inliers"] == r["n_inliers"], kw
+        for k in ("outlier_pt", "outlier_line", "outlier_plane"):
+            assert np.array_equal(o[k], r[k]), (kw, k)
+        assert np.allclose(o["Tcw_d"][:3, :3], r["Tcw_d"][:3, :3], rtol=0, atol=1e-12)
+        assert np.linalg.norm(o["Tcw_d"][:3, 3] - r["Tcw_d"][:3, 3]) < 5e-6, kw
