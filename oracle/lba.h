@@ -20,8 +20,9 @@
 // vertical / parallel information uses angleInfo (:2274-2276).  Quirk left to the caller: the reference
 // attaches every line edge to the *current* key frame's vertex, intrinsics and line function (:2169-2201) - pass that
 // key frame's index in line_obs_kf to reproduce it.
-// "parity unpinned": the reference ships no tests for this path, its only call site is commented out
-// (src/LocalMapping.cc:68) and it cannot be compiled here.
+// Pinned: the reference ships no tests for this path (its only call site is commented out, src/LocalMapping.cc:68) and
+// Optimizer.cc cannot be compiled here, but its g2o, vertices and edges can (oracle/ref/lba_driver.cc -> oracle/_ref/libpose_ref.so):
+// identical erase lists and iteration counts, poses within 2e-6 rad / 5e-6 m (tests/test_oracle_lba_ref.py, tests/golden/lba_reference.npz).
 #pragma once
 #include <cstdint>
 #include <vector>

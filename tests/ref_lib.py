@@ -239,3 +239,17 @@ def ref_translation_optimization(p: dict):
     it = np.zeros(4, np.int32)
     n = L.ref_translation_optimization(C.byref(s), T0.ctypes.data, Td.ctypes.data, *[a.ctypes.data for a in o], it.ctypes.data)
     return dict(Tcw_d=Td, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes], iterations=it)
+
+
+def ref_local_bundle_adjustment(p: dict) -> dict:
+    """LocalBundleAdjustment run by the reference's own g2o (BlockSolver_6_3 + Schur complement + Levenberg-Marquardt), edges and vertices on a
+    planarslam_b200.synth_lba problem; the graph construction, the 5 + 10 iterations with the chi-square gating in between and the erase lists are
+    restated in oracle/ref/lba_driver.cc.  Same keys as oracle_lib.local_bundle_adjustment."""
+    from planarslam_b200 import lba as _lba
+    L = pose_lib()
+    L.ref_local_bundle_adjustment.argtypes = [C.c_void_p, C.c_void_p]
+    s = _lba.problem_struct(p)
+    r, o = _lba.result_struct(s)
+    rc = L.ref_local_bundle_adjustment(C.byref(s), C.byref(r))
+    assert rc == 0
+    return _lba.finish(r, o)

@@ -9,6 +9,7 @@ the GPU box and may not exist in a later container, so the outputs are committed
                                     vocabularies / features: BowVector and FeatureVector in full for each case
   tests/golden/line3d_reference.npz the 3-D line fit of src/LineExtractor.cpp (+ libc rand) on clean and corrupted depth: every output field
   tests/golden/pose_reference.npz   PoseOptimization by the reference's g2o (libpose_ref.so): optimised pose, inlier count and outlier flags
+  tests/golden/lba_reference.npz    LocalBundleAdjustment by the reference's g2o (libpose_ref.so): key-frame poses, points, lines, planes, erase flags
 Run: python tools/make_golden_ref.py"""
 import hashlib
 import os
@@ -110,6 +111,18 @@ if __name__ == "__main__":
             pg[f"c{i}_{k}"] = r[k]
         print("pose", i, r["n_inliers"], "inliers")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "pose_reference.npz"), **pg)
+
+    from test_oracle_lba_ref import GOLD_CASES as LBA_CASES
+    from planarslam_b200 import synth_lba
+    lg = {}
+    for i, kw in enumerate(LBA_CASES):
+        r = ref_lib.ref_local_bundle_adjustment(synth_lba.make_lba_problem(**kw))
+        for k in ("kf_Tcw_d", "pt_Xw_d", "line_Xw_d", "plane_Xw_d", "erase_pt", "erase_line"):
+            lg[f"c{i}_{k}"] = r[k]
+        for t in range(3):
+            lg[f"c{i}_erase_plane{t}"] = r["erase_plane"][t]
+        print("lba", i, r["iterations"], int(r["erase_pt"].sum()), "point observations erased")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lba_reference.npz"), **lg)
     path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
