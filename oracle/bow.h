@@ -3,7 +3,8 @@
 // DBoW2 feature vectors, per common node an ordered greedy best / second-best Hamming match with TH_LOW = 50 and the ratio
 // test, rotation histogram + ComputeThreeMaxima :1666-1707).  The DBoW2 transform that produces the feature vectors
 // (Thirdparty/DBoW2) is an input here: feature vectors arrive as CSR arrays (node ids ascending like the
-// std::map they come from).  "parity unpinned": the reference ships no tests.
+// std::map they come from).  Pinned: identical match lists to the reference's own src/ORBmatcher.cc
+// compiled here (oracle/ref/match_driver.cc -> oracle/_ref/libmatch_ref.so, tests/test_oracle_match_ref.py).
 #pragma once
 #include <cstdint>
 

@@ -3,8 +3,8 @@
 // Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1125-1193 with the per-feature tree descent :1213-1252, FORB::distance
 // FORB.cpp:81-101, BowVector::addWeight / normalize BowVector.cpp:34-46,62-84 and FeatureVector::addFeature, as
 // Frame::ComputeBoW / KeyFrame::ComputeBoW call it (src/Frame.cc, src/KeyFrame.cc:66-76: TF_IDF weighting, L1 norm, levelsup 4).
-// DBoW2 is vendored in the reference, so the algorithm is fully specified in-tree; "parity unpinned" only in the sense that
-// the reference ships no tests.  The vocabulary is passed as flat arrays (node table in DBoW2's m_nodes order).
+// DBoW2 is vendored in the reference, so the algorithm is fully specified in-tree; pinned: byte-identical to the reference's
+// Thirdparty/DBoW2 compiled here (oracle/_ref/libbow_ref.so, tests/test_oracle_bow_ref.py).  The vocabulary is passed as flat arrays (node table in DBoW2's m_nodes order).
 #pragma once
 #include <cstdint>
 #include <vector>

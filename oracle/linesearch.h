@@ -2,7 +2,8 @@
 // Restatement of LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th)  src/LSDmatcher.cpp:141-211 with
 // Frame::GetLinesInArea src/Frame.cc:491-523 (mid-point distance gate, the one-sided slope-minus-angle gate, octave gate)
 // and LSDmatcher::RadiusByViewingCos :369-375.  The map-line fields are those Frame::isInFrustum(MapLine*) fills
-// (mbTrackInView, mTrackProjX1..Y2, mnTrackScaleLevel, mTrackViewCos).  "parity unpinned": the reference ships no tests.
+// (mbTrackInView, mTrackProjX1..Y2, mnTrackScaleLevel, mTrackViewCos).  Pinned: identical to the reference's own
+// src/LSDmatcher.cpp + src/Frame.cc compiled here (oracle/ref/match_driver.cc -> oracle/_ref/libmatch_ref.so, tests/test_oracle_match_ref.py).
 #pragma once
 #include <cstdint>
 

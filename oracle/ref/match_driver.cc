@@ -1,0 +1,318 @@
+// TEST INFRASTRUCTURE ONLY.  The reference's own matchers - src/ORBmatcher.cc (SearchByProjection x2, SearchByBoW), src/LSDmatcher.cpp (SearchByProjection),
+// src/PlaneMatcher.cpp (SearchMapByCoefficients), with the Frame / KeyFrame /
+// MapPoint / Map classes they walk (src/Frame.cc: SetPose, AssignFeaturesToGrid, PosInGrid, GetFeaturesInArea, isInFrustum; src/MapPoint.cc:
+// PredictScale, GetDescriptor ...; src/KeyFrame.cc) - compiled unmodified against the stand-ins of oracle/ref/shims/ into oracle/_ref/libmatch_ref.so.
+// This driver only BUILDS the object graph from the plain arrays of the C ABI views (pslam_frame_view, pslam_map_points, pslam_last_frame ...) and
+// reads the result back; every decision (frustum test, candidate gathering, descriptor gates, rotation histogram) is taken by the reference's code.
+// What of Tracking is restated: SearchLocalPoints' loop (src/Tracking.cc: skip the points already seen / bad, isInFrustum(pMP, 0.5) for the rest).
+// The reference's members are protected; the driver opens them for itself only (the reference's translation units are compiled as they are).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <list>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <set>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include <chrono>
+#include <tuple>
+
+#define private public
+#define protected public
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "Map.h"
+#include "MapPoint.h"
+#include "MapLine.h"
+#include "MapPlane.h"
+#include "ORBmatcher.h"
+#include "LSDmatcher.h"
+#include "PlaneMatcher.h"
+#undef private
+#undef protected
+#include "pslam_abi.h"
+
+using namespace Planar_SLAM;
+
+// src/LSDextractor.cpp wraps OpenCV-contrib's LSDDetector / BinaryDescriptor classes, which are not in this image; the only caller is Frame's image
+// constructor (Frame.cc:170-176), which no pinned path runs.  Defined here so that Frame.cc links.
+namespace Planar_SLAM {
+void LineSegment::ExtractLineSegment(const cv::Mat&, std::vector<cv::line_descriptor::KeyLine>&, cv::Mat&, std::vector<Eigen::Vector3d>&, float, int) {
+    std::fprintf(stderr, "oracle/ref/match_driver.cc: LineSegment::ExtractLineSegment is a link-only stand-in\n");
+    std::abort();
+}
+}  // namespace Planar_SLAM
+
+namespace {
+
+cv::KeyPoint to_kp(const pslam_keypoint& k) {
+    cv::KeyPoint kp;
+    kp.pt.x = k.x; kp.pt.y = k.y; kp.size = k.size; kp.angle = k.angle; kp.response = k.response; kp.octave = k.octave; kp.class_id = k.class_id;
+    return kp;
+}
+cv::Mat mat44(const float* T) { cv::Mat m(4, 4, CV_32F); for (int i = 0; i < 16; ++i) m.at<float>(i / 4, i % 4) = T[i]; return m; }
+
+// a Frame carrying what the matchers read (everything else stays default-constructed)
+void fill_frame(Frame& F, const pslam_frame_view& v, unsigned long id) {
+    F.mnId = id;
+    F.N = v.n;
+    F.mvKeysUn.resize(v.n);
+    for (int i = 0; i < v.n; ++i) F.mvKeysUn[i] = to_kp(v.keys_un[i]);
+    F.mvKeys = F.mvKeysUn;
+    F.mvuRight.assign(v.u_right, v.u_right + v.n);
+    F.mvDepth.assign(v.n, -1.f);
+    F.mDescriptors = cv::Mat(v.n, 32, CV_8U);
+    for (int i = 0; i < v.n; ++i) std::memcpy(F.mDescriptors.ptr(i), v.desc + 32 * (size_t)i, 32);
+    Frame::fx = v.fx; Frame::fy = v.fy; Frame::cx = v.cx; Frame::cy = v.cy; Frame::invfx = 1.0f / v.fx; Frame::invfy = 1.0f / v.fy;
+    Frame::mnMinX = v.min_x; Frame::mnMaxX = v.max_x; Frame::mnMinY = v.min_y; Frame::mnMaxY = v.max_y;
+    Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);     // Frame.cc:124-125
+    Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+    F.mbf = v.bf; F.mb = F.mbf / Frame::fx;
+    F.mnScaleLevels = v.n_levels;
+    F.mvScaleFactors.assign(v.scale_factors, v.scale_factors + v.n_levels);
+    F.mfScaleFactor = v.n_levels > 1 ? v.scale_factors[1] : 1.2f;
+    F.mfLogScaleFactor = v.log_scale_factor;
+    F.mvLevelSigma2.resize(v.n_levels); F.mvInvLevelSigma2.resize(v.n_levels); F.mvInvScaleFactors.resize(v.n_levels);
+    for (int l = 0; l < v.n_levels; ++l) { F.mvLevelSigma2[l] = v.scale_factors[l] * v.scale_factors[l]; F.mvInvLevelSigma2[l] = 1.0f / F.mvLevelSigma2[l]; F.mvInvScaleFactors[l] = 1.0f / v.scale_factors[l]; }
+    F.mvpMapPoints.assign(v.n, static_cast<MapPoint*>(NULL));
+    F.mvbOutlier.assign(v.n, false);
+    F.mK = cv::Mat::eye(3, 3, CV_32F);
+    F.mK.at<float>(0, 0) = v.fx; F.mK.at<float>(1, 1) = v.fy; F.mK.at<float>(0, 2) = v.cx; F.mK.at<float>(1, 2) = v.cy;
+    F.SetPose(mat44(v.Tcw));
+    F.AssignFeaturesToGrid();
+}
+
+struct World {                          // one Map, one anchor key frame (MapPoint's constructor reads its ids), the map points of a pslam_map_points view
+    Map map;
+    Frame anchor_frame;
+    KeyFrame* anchor = nullptr;
+    std::vector<MapPoint*> pts;
+    std::unordered_map<MapPoint*, int> index;
+    World() {
+        anchor_frame.N = 0;
+        anchor_frame.mTcw = cv::Mat::eye(4, 4, CV_32F);
+        anchor_frame.SetPose(cv::Mat::eye(4, 4, CV_32F));
+        anchor = new KeyFrame(anchor_frame, &map, static_cast<KeyFrameDatabase*>(NULL));
+    }
+    MapPoint* make_point(const float* pos, const float* normal, float maxd, float mind, const uint8_t* desc, bool has_obs) {
+        cv::Mat X(3, 1, CV_32F);
+        for (int c = 0; c < 3; ++c) X.at<float>(c) = pos[c];
+        MapPoint* p = new MapPoint(X, anchor, &map);
+        p->mNormalVector = cv::Mat(3, 1, CV_32F);
+        for (int c = 0; c < 3; ++c) p->mNormalVector.at<float>(c) = normal ? normal[c] : 0.f;
+        p->mfMaxDistance = maxd; p->mfMinDistance = mind;
+        p->mDescriptor = cv::Mat(1, 32, CV_8U);
+        if (desc) std::memcpy(p->mDescriptor.ptr(0), desc, 32); else std::memset(p->mDescriptor.ptr(0), 0, 32);
+        p->nObs = has_obs ? 1 : 0;
+        p->mbTrackInView = false;
+        return p;
+    }
+    void add(const pslam_map_points& m) {
+        for (int i = 0; i < m.n; ++i) {
+            MapPoint* p = make_point(m.pos + 3 * i, m.normal + 3 * i, m.max_distance[i], m.min_distance[i], m.desc + 32 * (size_t)i, m.has_obs[i] != 0);
+            index[p] = (int)pts.size();
+            pts.push_back(p);
+        }
+    }
+    ~World() { for (MapPoint* p : pts) delete p; delete anchor; }
+};
+
+void hold(Frame& F, const World& w, const int32_t* matches) {
+    for (int i = 0; i < F.N; ++i) F.mvpMapPoints[i] = matches[i] >= 0 ? w.pts[matches[i]] : static_cast<MapPoint*>(NULL);
+}
+void read_back(const Frame& F, const World& w, int32_t* matches) {
+    for (int i = 0; i < F.N; ++i) { MapPoint* p = F.mvpMapPoints[i]; matches[i] = p ? w.index.at(p) : -1; }
+}
+
+DBoW2::FeatureVector feat_vec(int n_nodes, const int32_t* node_id, const int32_t* node_off, const int32_t* node_feat) {
+    DBoW2::FeatureVector fv;
+    for (int k = 0; k < n_nodes; ++k)
+        for (int j = node_off[k]; j < node_off[k + 1]; ++j) fv.addFeature((DBoW2::NodeId)node_id[k], (unsigned)node_feat[j]);
+    return fv;
+}
+
+}  // namespace
+
+// Tracking::SearchLocalPoints + ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)   src/ORBmatcher.cc:46-130
+extern "C" int ref_search_by_projection_map(const pslam_frame_view* fv, const pslam_map_points* m, float th, float nnratio, int32_t* matches_io, uint8_t* in_view) {
+    World w;
+    w.add(*m);
+    Frame F;
+    fill_frame(F, *fv, 7);
+    hold(F, w, matches_io);
+    for (int i = 0; i < m->n; ++i) {
+        MapPoint* pMP = w.pts[i];
+        if (m->skip[i]) { pMP->mbTrackInView = false; continue; }
+        F.isInFrustum(pMP, 0.5);
+    }
+    ORBmatcher matcher(nnratio);
+    const int n = matcher.SearchByProjection(F, w.pts, th);
+    read_back(F, w, matches_io);
+    if (in_view) for (int i = 0; i < m->n; ++i) in_view[i] = w.pts[i]->mbTrackInView ? 1 : 0;
+    return n;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)   src/ORBmatcher.cc:1396-1535
+extern "C" int ref_search_by_projection_last(const pslam_frame_view* cur, const pslam_last_frame* last, const pslam_map_points* m, float th, int mono,
+                                             int check_orientation, int32_t* matches_io) {
+    World w;
+    w.add(*m);
+    Frame C;
+    fill_frame(C, *cur, 8);
+    hold(C, w, matches_io);
+    Frame L;
+    L.mnId = 7;
+    L.N = last->n;
+    L.mvKeys.resize(last->n);
+    for (int i = 0; i < last->n; ++i) L.mvKeys[i] = to_kp(last->keys[i]);
+    L.mvKeysUn = L.mvKeys;
+    L.mvpMapPoints.assign(last->n, static_cast<MapPoint*>(NULL));
+    L.mvbOutlier.assign(last->n, false);
+    for (int i = 0; i < last->n; ++i) { if (last->map_point[i] >= 0) L.mvpMapPoints[i] = w.pts[last->map_point[i]]; L.mvbOutlier[i] = last->outlier[i] != 0; }
+    L.SetPose(mat44(last->Tcw));
+    ORBmatcher matcher(0.9, check_orientation != 0);
+    const int n = matcher.SearchByProjection(C, L, th, mono != 0);
+    read_back(C, w, matches_io);
+    return n;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)   src/ORBmatcher.cc:160-292
+extern "C" int ref_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_mp, int kf_nodes, const int32_t* kf_node_id,
+                                 const int32_t* kf_node_off, const int32_t* kf_node_feat, int n_f, const uint8_t* f_desc, const float* f_angle, int f_nodes,
+                                 const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat, float nnratio, int check_orientation, int32_t* match) {
+    World w;
+    const float zero3[3] = {0, 0, 0};
+    auto basic = [](Frame& F, int n, const uint8_t* desc, const float* angle) {
+        F.N = n;
+        F.mvKeysUn.resize(n);
+        for (int i = 0; i < n; ++i) { F.mvKeysUn[i].angle = angle[i]; F.mvKeysUn[i].octave = 0; }
+        F.mvKeys = F.mvKeysUn;
+        F.mDescriptors = cv::Mat(n, 32, CV_8U);
+        for (int i = 0; i < n; ++i) std::memcpy(F.mDescriptors.ptr(i), desc + 32 * (size_t)i, 32);
+        F.mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL));
+        F.mvbOutlier.assign(n, false);
+        F.SetPose(cv::Mat::eye(4, 4, CV_32F));
+    };
+    Frame K;
+    basic(K, n_kf, kf_desc, kf_angle);
+    K.mFeatVec = feat_vec(kf_nodes, kf_node_id, kf_node_off, kf_node_feat);
+    for (int i = 0; i < n_kf; ++i)
+        if (kf_has_mp[i]) { MapPoint* p = w.make_point(zero3, zero3, 0, 0, nullptr, true); w.index[p] = i; w.pts.push_back(p); K.mvpMapPoints[i] = p; }
+    KeyFrame* pKF = new KeyFrame(K, &w.map, static_cast<KeyFrameDatabase*>(NULL));
+    Frame F;
+    basic(F, n_f, f_desc, f_angle);
+    F.mFeatVec = feat_vec(f_nodes, f_node_id, f_node_off, f_node_feat);
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    std::vector<MapPoint*> vpMapPointMatches;
+    const int n = matcher.SearchByBoW(pKF, F, vpMapPointMatches);
+    for (int i = 0; i < n_f; ++i) match[i] = vpMapPointMatches[i] ? w.index.at(vpMapPointMatches[i]) : -1;     // index of the key-frame feature whose map point was taken
+    delete pKF;
+    return n;
+}
+
+// Frame::isInFrustum(MapLine*, viewingCosLimit)   src/Frame.cc:369-437 (with MapLine::PredictScale / Get{Min,Max}DistanceInvariance, src/MapLine.cpp:364-390)
+// fv: Tcw[16], fx, fy, cx, cy, min_x, max_x, min_y, max_y, log_scale_factor
+extern "C" void ref_lines_in_frustum(const float* fv, int n, const double* pos, const double* normal, const float* max_distance, const float* min_distance,
+                                     float cos_limit, uint8_t* in_view, float* proj, int32_t* level, float* view_cos) {
+    World w;
+    Frame F;
+    Frame::fx = fv[16]; Frame::fy = fv[17]; Frame::cx = fv[18]; Frame::cy = fv[19];
+    Frame::mnMinX = fv[20]; Frame::mnMaxX = fv[21]; Frame::mnMinY = fv[22]; Frame::mnMaxY = fv[23];
+    F.mfLogScaleFactor = fv[24];
+    F.SetPose(mat44(fv));
+    for (int i = 0; i < n; ++i) {
+        Vector6d P;
+        for (int c = 0; c < 6; ++c) P(c) = pos[6 * i + c];
+        MapLine* pML = new MapLine(P, w.anchor, &w.map);
+        pML->mNormalVector = Eigen::Vector3d(normal[3 * i], normal[3 * i + 1], normal[3 * i + 2]);
+        pML->mfMaxDistance = max_distance[i]; pML->mfMinDistance = min_distance[i];
+        pML->mTrackProjX1 = pML->mTrackProjY1 = pML->mTrackProjX2 = pML->mTrackProjY2 = 0; pML->mnTrackScaleLevel = 0; pML->mTrackViewCos = 0;
+        F.isInFrustum(pML, cos_limit);
+        in_view[i] = pML->mbTrackInView ? 1 : 0;
+        proj[4 * i] = pML->mTrackProjX1; proj[4 * i + 1] = pML->mTrackProjY1; proj[4 * i + 2] = pML->mTrackProjX2; proj[4 * i + 3] = pML->mTrackProjY2;
+        level[i] = pML->mnTrackScaleLevel; view_cos[i] = pML->mTrackViewCos;
+        delete pML;
+    }
+}
+
+// LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th)   src/LSDmatcher.cpp:141-211 (Frame::GetLinesInArea src/Frame.cc:491-523)
+extern "C" int ref_line_search_by_projection(int nf, const float* pt, const float* angle, const int32_t* octave, const uint8_t* desc, const uint8_t* has_obs,
+                                             const float* scale_factors, int n_levels, int nm, const uint8_t* skip, const int32_t* level, const float* view_cos,
+                                             const float* proj, const uint8_t* mdesc, const uint8_t* m_has_obs, float th, float nnratio, int32_t* assigned) {
+    World w;
+    Vector6d zero6 = Vector6d::Zero();
+    Frame F;
+    F.NL = nf;
+    F.mvKeylinesUn.resize(nf);
+    for (int i = 0; i < nf; ++i) { F.mvKeylinesUn[i].pt.x = pt[2 * i]; F.mvKeylinesUn[i].pt.y = pt[2 * i + 1]; F.mvKeylinesUn[i].angle = angle[i]; F.mvKeylinesUn[i].octave = octave[i]; }
+    F.mLdesc = cv::Mat(nf, 32, CV_8U);
+    for (int i = 0; i < nf; ++i) std::memcpy(F.mLdesc.ptr(i), desc + 32 * (size_t)i, 32);
+    F.mvScaleFactors.assign(scale_factors, scale_factors + n_levels);
+    std::vector<MapLine*> own;
+    F.mvpMapLines.assign(nf, static_cast<MapLine*>(NULL));
+    for (int i = 0; i < nf; ++i)
+        if (has_obs[i]) { MapLine* p = new MapLine(zero6, w.anchor, &w.map); p->nObs = 1; own.push_back(p); F.mvpMapLines[i] = p; }     // already holds an observed map line
+    std::vector<MapLine*> held = F.mvpMapLines;
+    std::vector<MapLine*> vpMapLines(nm);
+    std::unordered_map<MapLine*, int> index;
+    for (int j = 0; j < nm; ++j) {
+        MapLine* p = new MapLine(zero6, w.anchor, &w.map);
+        p->mbTrackInView = !skip[j];
+        p->mnTrackScaleLevel = level[j]; p->mTrackViewCos = view_cos[j];
+        p->mTrackProjX1 = proj[4 * j]; p->mTrackProjY1 = proj[4 * j + 1]; p->mTrackProjX2 = proj[4 * j + 2]; p->mTrackProjY2 = proj[4 * j + 3];
+        p->mLDescriptor = cv::Mat(1, 32, CV_8U);
+        std::memcpy(p->mLDescriptor.ptr(0), mdesc + 32 * (size_t)j, 32);
+        p->nObs = m_has_obs[j] ? 1 : 0;
+        vpMapLines[j] = p; index[p] = j; own.push_back(p);
+    }
+    LSDmatcher matcher(nnratio);
+    const int n = matcher.SearchByProjection(F, vpMapLines, th);
+    for (int i = 0; i < nf; ++i) assigned[i] = (F.mvpMapLines[i] && F.mvpMapLines[i] != held[i]) ? index.at(F.mvpMapLines[i]) : -1;
+    for (MapLine* p : own) delete p;
+    return n;
+}
+
+// PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)   src/PlaneMatcher.cpp:10-82 (Frame::ComputePlaneWorldCoeff src/Frame.cc:815-820)
+extern "C" int ref_plane_match(const float* Tcw, int n_frame, const float* frame_coef, int n_map, const float* map_coef, const uint8_t* map_bad, const int32_t* pts_off,
+                               const float* pts, float dTh, float aTh, float verTh, float parTh, int32_t* match, int32_t* ver, int32_t* par) {
+    World w;
+    Frame F;
+    F.SetPose(mat44(Tcw));
+    F.mnPlaneNum = n_frame;
+    for (int i = 0; i < n_frame; ++i) {
+        cv::Mat c(4, 1, CV_32F);
+        for (int k = 0; k < 4; ++k) c.at<float>(k) = frame_coef[4 * i + k];
+        F.mvPlaneCoefficients.push_back(c);
+    }
+    F.mvpMapPlanes.assign(n_frame, static_cast<MapPlane*>(nullptr));
+    F.mvpVerticalPlanes.assign(n_frame, static_cast<MapPlane*>(nullptr));
+    F.mvpParallelPlanes.assign(n_frame, static_cast<MapPlane*>(nullptr));
+    std::vector<MapPlane*> planes(n_map);
+    std::unordered_map<MapPlane*, int> index;
+    for (int j = 0; j < n_map; ++j) {
+        cv::Mat c(4, 1, CV_32F);
+        for (int k = 0; k < 4; ++k) c.at<float>(k) = map_coef[4 * j + k];
+        MapPlane* p = new MapPlane(c, w.anchor, &w.map);
+        p->mbBad = map_bad[j] != 0;
+        for (int q = pts_off[j]; q < pts_off[j + 1]; ++q) { pcl::PointXYZRGB pt; pt.x = pts[3 * q]; pt.y = pts[3 * q + 1]; pt.z = pts[3 * q + 2]; p->mvPlanePoints->points.push_back(pt); }
+        planes[j] = p; index[p] = j;
+    }
+    PlaneMatcher matcher(dTh, aTh, verTh, parTh);
+    const int n = matcher.SearchMapByCoefficients(F, planes);
+    for (int i = 0; i < n_frame; ++i) {
+        match[i] = F.mvpMapPlanes[i] ? index.at(F.mvpMapPlanes[i]) : -1;
+        ver[i] = F.mvpVerticalPlanes[i] ? index.at(F.mvpVerticalPlanes[i]) : -1;
+        par[i] = F.mvpParallelPlanes[i] ? index.at(F.mvpParallelPlanes[i]) : -1;
+    }
+    for (MapPlane* p : planes) delete p;
+    return n;
+}

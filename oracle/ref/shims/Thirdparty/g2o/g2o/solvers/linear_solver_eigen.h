@@ -3,7 +3,7 @@
 // pokes at Eigen internals; all of its arithmetic is Eigen's.  LocalBundleAdjustment only needs "solve the Schur-reduced pose system", so the
 // class keeps its name and interface and solves densely with the reference's own LinearSolverDense (same solution up to rounding).
 #pragma once
-#include "/root/reference/Thirdparty/g2o/g2o/solvers/linear_solver_dense.h"
+#include <Thirdparty/g2o/g2o/solvers/linear_solver_dense.h>   // the reference's (only linear_solver_eigen.h is shadowed)
 
 namespace g2o {
 template <typename MatrixType>

@@ -3,6 +3,9 @@
 // type and keeps the OpenCV line_descriptor module out of the plane-extractor build.
 #pragma once
 #include <opencv2/opencv.hpp>
+#ifdef PSLAM_REF_FULL_HEADERS            // the matcher builds compile the reference's real header (found on the include path after ref/shims)
+#include <LSDextractor.h>
+#else
 class SurfaceNormal {
 public:
     cv::Point3f normal;
@@ -10,3 +13,4 @@ public:
     cv::Point2i FramePosition;
     SurfaceNormal() {}
 };
+#endif

@@ -2,6 +2,10 @@
 // src/LineExtractor.cpp: products accumulate left to right over k in double like cv::gemm's generic path, 3x3 inverse by cofactors like
 // cv::invert, cv::SVD = OpenCV's Jacobi algorithm as restated in oracle/cvsvd.h.  Included from opencv.hpp inside no namespace.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <ostream>
+#include "../../../match.h"
 #include "../../../cvsvd.h"
 
 namespace cv {
@@ -92,6 +96,20 @@ inline Mat Mat::inv(int) const {
 }
 inline double norm(const Mat& m) { return std::sqrt(m.dot(m)); }
 inline double norm(const Mat& a, const Mat& b) { return norm(a - b); }
+inline double norm(const Mat& a, const Mat& b, int normType) {          // NORM_HAMMING (6) over 8-bit rows, else L2
+    if (normType != 6) return norm(a - b);
+    int d = 0;
+    for (int r = 0; r < a.rows; ++r) for (int c = 0; c < a.cols; ++c) d += __builtin_popcount((unsigned)(a.ptr(r)[c] ^ b.ptr(r)[c]));
+    return d;
+}
+inline void transpose(const Mat& src, Mat& dst) { dst = src.t(); }
+inline Mat& operator/=(Mat& m, double s) { for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) m.setd(r, c, m.depth() == CV_64F ? m.getd(r, c) / s : (double)((float)m.getd(r, c) / (float)s)); return m; }
+inline std::ostream& operator<<(std::ostream& os, const Mat& m) {
+    os << "[";
+    for (int r = 0; r < m.rows; ++r) { for (int c = 0; c < m.cols; ++c) os << (c ? ", " : "") << m.getd(r, c); os << (r + 1 < m.rows ? ";\n " : ""); }
+    return os << "]";
+}
+inline void undistortPoints(const Mat&, Mat&, const Mat&, const Mat&, const Mat&, const Mat&) { std::fprintf(stderr, "oracle/ref/shims: cv::undistortPoints is a compile-only stand-in (zero distortion returns before it, Frame.cc:543-547)\n"); std::abort(); }
 inline void minMaxLoc(const Mat& m, double* minVal, double* maxVal = nullptr, Point* minLoc = nullptr, Point* maxLoc = nullptr) {
     double mn = m.getd(0, 0), mx = mn;
     Point pn(0, 0), px(0, 0);
@@ -139,6 +157,23 @@ public:
 };
 
 struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = 0; };
+enum { NORM_HAMMING = 6 };
+class BFMatcher {                                        // brute force, first minimum wins: the oracle's cv2-pinned one (oracle/match.h)
+public:
+    explicit BFMatcher(int = NORM_HAMMING, bool = false) {}
+    void match(const Mat& q, const Mat& t, std::vector<DMatch>& out) const {
+        std::vector<int32_t> idx(q.rows), dist(q.rows);
+        oracle::bf_match(q.ptr<uint8_t>(0), q.rows, t.ptr<uint8_t>(0), t.rows, idx.data(), dist.data());
+        out.clear();
+        for (int i = 0; i < q.rows; ++i) if (idx[i] >= 0) { DMatch m; m.queryIdx = i; m.trainIdx = idx[i]; m.imgIdx = 0; m.distance = (float)dist[i]; out.push_back(m); }
+    }
+    void knnMatch(const Mat& q, const Mat& t, std::vector<std::vector<DMatch>>& out, int k) const {
+        std::vector<int32_t> idx(2 * (size_t)q.rows), dist(2 * (size_t)q.rows);
+        oracle::bf_knn2(q.ptr<uint8_t>(0), q.rows, t.ptr<uint8_t>(0), t.rows, idx.data(), dist.data());
+        out.assign(q.rows, {});
+        for (int i = 0; i < q.rows; ++i) for (int j = 0; j < 2 && j < k; ++j) if (idx[2 * i + j] >= 0) { DMatch m; m.queryIdx = i; m.trainIdx = idx[2 * i + j]; m.imgIdx = 0; m.distance = (float)dist[2 * i + j]; out[i].push_back(m); }
+    }
+};
 template <class T> using Ptr = std::shared_ptr<T>;
 
 class LineIterator {                                     // only met in code the tracker never reaches

@@ -165,6 +165,23 @@ public:
     Mat cross(const Mat& o) const;
     void copyTo(Mat& dst) const { dst.create(rows, cols, type_); copyRows(dst); }
     void copyTo(Mat&& view) const { copyRows(view); }             // into a row / column / ROI view of the same size
+    static Mat eye(Size sz, int type) { return eye(sz.height, sz.width, type); }
+    void convertTo(Mat& dst, int type, double alpha = 1, double beta = 0) const {      // single channel, to float / double (Frame.cc:82 depth scaling)
+        Mat out(rows, cols, type);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) {
+                double v;
+                switch (depth()) { case CV_8U: v = at<uchar>(r, c); break; case CV_16U: v = at<uint16_t>(r, c); break; case CV_32S: v = at<int32_t>(r, c); break;
+                                   case CV_64F: v = at<double>(r, c); break; default: v = at<float>(r, c); }
+                out.setd(r, c, v * alpha + beta);
+            }
+        dst = out;
+    }
+    Mat reshape(int cn) const {                                   // same rows, channels regrouped (Frame.cc:559-561); continuous data only
+        Mat m = *this; const int total = cols * channels();
+        m.type_ = (type_ & 7) | ((cn - 1) << 3); m.cols = total / cn;
+        return m;
+    }
     static Mat eye(int r, int c, int type) { Mat m(MatZeros{r, c, type, 0}); for (int i = 0; i < r && i < c; ++i) m.setd(i, i, 1.0); return m; }
     double getd(int r, int c) const { return depth() == CV_64F ? at<double>(r, c) : (double)at<float>(r, c); }
     void setd(int r, int c, double v) { if (depth() == CV_64F) at<double>(r, c) = v; else at<float>(r, c) = (float)v; }

@@ -9,6 +9,8 @@
 // Arithmetic conventions (the reference leaves them to OpenCV / libm): cv::Mat float products and cv::norm
 // accumulate in double and round once to float; float expressions are evaluated left to right without FMA;
 // log(ratio) of PredictScale is evaluated in double and rounded to float.
+// Pinned: identical match lists / mbTrackInView flags to the reference's own src/ORBmatcher.cc + src/Frame.cc + src/MapPoint.cc compiled here
+// (oracle/ref/match_driver.cc -> oracle/_ref/libmatch_ref.so, tests/test_oracle_match_ref.py, tests/golden/match_reference.npz).
 #pragma once
 #include <cstdint>
 #include <vector>

@@ -253,3 +253,98 @@ def ref_local_bundle_adjustment(p: dict) -> dict:
     rc = L.ref_local_bundle_adjustment(C.byref(s), C.byref(r))
     assert rc == 0
     return _lba.finish(r, o)
+
+
+_match = None
+
+
+def match_lib():
+    """oracle/_ref/libmatch_ref.so: the reference's ORBmatcher / LSDmatcher / PlaneMatcher with its Frame, KeyFrame, MapPoint, MapLine, MapPlane and Map
+    classes, compiled unmodified; oracle/ref/match_driver.cc builds the objects from the C ABI's plain-array views."""
+    global _match
+    if _match is None:
+        _match = _load("libmatch_ref.so")
+    return _match
+
+
+def ref_search_by_projection_map(fv: dict, m: dict, th: float, nnratio: float, matches0: np.ndarray):
+    """Tracking::SearchLocalPoints' frustum loop + ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) by the reference's own code.
+    Same arguments and returns as oracle_lib.search_by_projection_map."""
+    import oracle_lib
+    L = match_lib()
+    L.ref_search_by_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    matches = np.ascontiguousarray(matches0, np.int32).copy()
+    in_view = np.zeros(max(m["n"], 1), np.uint8)
+    n = L.ref_search_by_projection_map(C.byref(oracle_lib.frame_view_struct(fv)), C.byref(oracle_lib.map_points_struct(m)), th, nnratio, matches.ctypes.data,
+                                       in_view.ctypes.data)
+    return n, matches, in_view[:m["n"]]
+
+
+def ref_search_by_projection_last(fv: dict, lf: dict, m: dict, th: float, mono: bool, check_ori: bool, matches0: np.ndarray):
+    """ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) by the reference's own code."""
+    import oracle_lib
+    L = match_lib()
+    L.ref_search_by_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    matches = np.ascontiguousarray(matches0, np.int32).copy()
+    n = L.ref_search_by_projection_last(C.byref(oracle_lib.frame_view_struct(fv)), C.byref(oracle_lib.last_frame_struct(lf)), C.byref(oracle_lib.map_points_struct(m)),
+                                        th, int(mono), int(check_ori), matches.ctypes.data)
+    return n, matches
+
+
+def ref_search_by_bow(kf: dict, frame: dict, nnratio: float = 0.7, check_orientation: bool = True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) by the reference's own code.  Same layout as oracle_lib.search_by_bow."""
+    L = match_lib()
+    L.ref_search_by_bow.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
+    k = {a: np.ascontiguousarray(b) for a, b in kf.items()}
+    f = {a: np.ascontiguousarray(b) for a, b in frame.items()}
+    nf = len(f["angle"])
+    match = np.full(max(nf, 1), -1, np.int32)
+    n = L.ref_search_by_bow(len(k["angle"]), k["desc"].ctypes.data, k["angle"].ctypes.data, k["has_mp"].ctypes.data, len(k["node_id"]), k["node_id"].ctypes.data,
+                            k["node_off"].ctypes.data, k["node_feat"].ctypes.data, nf, f["desc"].ctypes.data, f["angle"].ctypes.data, len(f["node_id"]),
+                            f["node_id"].ctypes.data, f["node_off"].ctypes.data, f["node_feat"].ctypes.data, nnratio, 1 if check_orientation else 0,
+                            match.ctypes.data)
+    return n, match[:nf]
+
+
+def ref_lines_in_frustum(frame: dict, pos, normal, max_distance, min_distance, cos_limit: float = 0.5):
+    """Frame::isInFrustum(MapLine*, cosLimit) by the reference's own code.  Same arguments / returns as oracle_lib.lines_in_frustum."""
+    L = match_lib()
+    L.ref_lines_in_frustum.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 4
+    L.ref_lines_in_frustum.restype = None
+    fv = np.concatenate([np.asarray(frame["Tcw"], np.float32).ravel(), np.array([frame[k] for k in ("fx", "fy", "cx", "cy", "min_x", "max_x", "min_y", "max_y",
+                                                                                                      "log_scale_factor")], np.float32)])
+    P, Nn = np.ascontiguousarray(pos, np.float64).reshape(-1, 6), np.ascontiguousarray(normal, np.float64).reshape(-1, 3)
+    mx, mn = np.ascontiguousarray(max_distance, np.float32), np.ascontiguousarray(min_distance, np.float32)
+    n = len(P)
+    o = dict(in_view=np.zeros(n, np.uint8), proj=np.zeros((n, 4), np.float32), level=np.zeros(n, np.int32), view_cos=np.zeros(n, np.float32))
+    L.ref_lines_in_frustum(fv.ctypes.data, n, P.ctypes.data, Nn.ctypes.data, mx.ctypes.data, mn.ctypes.data, cos_limit, o["in_view"].ctypes.data, o["proj"].ctypes.data,
+                           o["level"].ctypes.data, o["view_cos"].ctypes.data)
+    return o
+
+
+def ref_line_search_by_projection(frame: dict, map_lines: dict, th: float, nnratio: float):
+    """LSDmatcher::SearchByProjection(Frame&, vector<MapLine*>&, th) by the reference's own code.  Same layout as oracle_lib.line_search_by_projection."""
+    L = match_lib()
+    L.ref_line_search_by_projection.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p]
+    f = {k: np.ascontiguousarray(v) for k, v in frame.items()}
+    m = {k: np.ascontiguousarray(v) for k, v in map_lines.items()}
+    nf, nm = len(f["angle"]), len(m["level"])
+    assigned = np.full(max(nf, 1), -1, np.int32)
+    n = L.ref_line_search_by_projection(nf, f["pt"].ctypes.data, f["angle"].ctypes.data, f["octave"].ctypes.data, f["desc"].ctypes.data,
+                                        f["has_obs"].ctypes.data, f["scale_factors"].ctypes.data, len(f["scale_factors"]), nm, m["skip"].ctypes.data,
+                                        m["level"].ctypes.data, m["view_cos"].ctypes.data, m["proj"].ctypes.data, m["desc"].ctypes.data,
+                                        m["has_obs"].ctypes.data, th, nnratio, assigned.ctypes.data)
+    return n, assigned[:nf]
+
+
+def ref_plane_match(T, fc, mc, bad, off, pts, dTh, aTh, verTh, parTh):
+    """PlaneMatcher::SearchMapByCoefficients by the reference's own code.  Returns (nmatches, match, vertical, parallel)."""
+    L = match_lib()
+    L.ref_plane_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 3
+    T, fc, mc = np.ascontiguousarray(T, np.float32), np.ascontiguousarray(fc, np.float32), np.ascontiguousarray(mc, np.float32)
+    bad, off, pts = np.ascontiguousarray(bad, np.uint8), np.ascontiguousarray(off, np.int32), np.ascontiguousarray(pts, np.float32)
+    om, ov, op = [np.zeros(max(len(fc), 1), np.int32) for _ in range(3)]
+    n = L.ref_plane_match(T.ctypes.data, len(fc), fc.ctypes.data, len(mc), mc.ctypes.data, bad.ctypes.data, off.ctypes.data, pts.ctypes.data, dTh, aTh, verTh, parTh,
+                          om.ctypes.data, ov.ctypes.data, op.ctypes.data)
+    return n, om[:len(fc)], ov[:len(fc)], op[:len(fc)]

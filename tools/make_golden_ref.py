@@ -9,6 +9,7 @@ the GPU box and may not exist in a later container, so the outputs are committed
                                     vocabularies / features: BowVector and FeatureVector in full for each case
   tests/golden/line3d_reference.npz the 3-D line fit of src/LineExtractor.cpp (+ libc rand) on clean and corrupted depth: every output field
   tests/golden/pose_reference.npz   PoseOptimization by the reference's g2o (libpose_ref.so): optimised pose, inlier count and outlier flags
+  tests/golden/match_reference.npz  the matchers (libmatch_ref.so): SearchByProjection x2, SearchByBoW, LSDmatcher::SearchByProjection, PlaneMatcher
   tests/golden/lba_reference.npz    LocalBundleAdjustment by the reference's g2o (libpose_ref.so): key-frame poses, points, lines, planes, erase flags
 Run: python tools/make_golden_ref.py"""
 import hashlib
@@ -123,6 +124,16 @@ if __name__ == "__main__":
             lg[f"c{i}_erase_plane{t}"] = r["erase_plane"][t]
         print("lba", i, r["iterations"], int(r["erase_pt"].sum()), "point observations erased")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "lba_reference.npz"), **lg)
+
+    from test_oracle_match_ref import gold_cases
+    mg = {}
+    for name, _, ref_call in gold_cases():
+        r = ref_call()
+        mg[f"{name}_n"] = np.array([r[0]], np.int32)
+        for k, arr in enumerate(r[1:]):
+            mg[f"{name}_{k}"] = arr
+        print("match", name, int(r[0]), "matches")
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "match_reference.npz"), **mg)
     path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
