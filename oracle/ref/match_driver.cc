@@ -37,6 +37,8 @@
 #include "ORBmatcher.h"
 #include "LSDmatcher.h"
 #include "PlaneMatcher.h"
+#include "Optimizer.h"
+#include "Config.h"
 #undef private
 #undef protected
 #include "pslam_abi.h"
@@ -314,5 +316,71 @@ extern "C" int ref_plane_match(const float* Tcw, int n_frame, const float* frame
         par[i] = F.mvpParallelPlanes[i] ? index.at(F.mvpParallelPlanes[i]) : -1;
     }
     for (MapPlane* p : planes) delete p;
+    return n;
+}
+
+// ---- the optimisers, called as they are ------------------------------------------------------------------------------------------------------------
+// Optimizer::PoseOptimization(Frame*) src/Optimizer.cc:550-1275 and Optimizer::TranslationOptimization(Frame*) :2995-3737 run on a Frame built from a
+// pslam_pose_problem: graph construction, the four optimise-and-classify rounds and the pose write-back are the reference's (oracle/ref/pose_driver.cc
+// restates them; this entry point removes that caveat).  The Plane.* settings come through Config::Get from the settings table of the FileStorage
+// stand-in.  A frame has one coefficient vector per plane slot; the problem's plane / parallel / vertical observations take consecutive slots.
+static void set_plane_settings(double angle_info, double dist_info, double par_info, double ver_info, double plane_chi, double vp_chi) {
+    auto& t = cv::FileStorage::table();
+    t["Plane.AngleInfo"] = angle_info; t["Plane.DistanceInfo"] = dist_info; t["Plane.ParallelInfo"] = par_info; t["Plane.VerticalInfo"] = ver_info;
+    t["Plane.Chi"] = plane_chi; t["Plane.VPChi"] = vp_chi;
+    Config::SetParameterFile("pslam-settings-table");
+}
+
+extern "C" int ref_full_pose_optimization(const pslam_pose_problem* P, const float* Tcw_in, int translation_only, float* Tcw_out, uint8_t* o_pt, uint8_t* o_line,
+                                          uint8_t* o_plane, uint8_t* o_par, uint8_t* o_ver) {
+    set_plane_settings(P->angle_info, P->dist_info, P->par_info, P->ver_info, P->plane_chi, P->vp_chi);
+    World w;
+    Frame F;
+    Frame::fx = P->fx; Frame::fy = P->fy; Frame::cx = P->cx; Frame::cy = P->cy; Frame::invfx = 1.0f / P->fx; Frame::invfy = 1.0f / P->fy;
+    F.mbf = P->bf; F.mb = F.mbf / Frame::fx;
+    F.N = P->n_points;
+    F.mvKeysUn.resize(F.N); F.mvuRight.resize(F.N); F.mvInvLevelSigma2.resize(std::max(F.N, 1)); F.mvpMapPoints.resize(F.N); F.mvbOutlier.assign(F.N, false);
+    const float zero3[3] = {0, 0, 0};
+    for (int i = 0; i < F.N; ++i) {
+        F.mvKeysUn[i].pt.x = P->obs[3 * i]; F.mvKeysUn[i].pt.y = P->obs[3 * i + 1]; F.mvKeysUn[i].octave = i;      // one "level" per point: mvInvLevelSigma2[octave]
+        F.mvuRight[i] = P->obs[3 * i + 2];
+        F.mvInvLevelSigma2[i] = P->inv_sigma2[i];
+        F.mvpMapPoints[i] = w.make_point(P->Xw + 3 * i, zero3, 0, 0, nullptr, true);
+        w.pts.push_back(F.mvpMapPoints[i]);
+    }
+    F.mvKeys = F.mvKeysUn;
+    F.NL = P->n_lines;
+    F.mvpMapLines.resize(F.NL); F.mvbLineOutlier.assign(F.NL, false); F.mvKeyLineFunctions.resize(F.NL); F.mvKeylinesUn.resize(F.NL);
+    std::vector<MapLine*> lines;
+    for (int i = 0; i < F.NL; ++i) {
+        Vector6d X;
+        for (int c = 0; c < 6; ++c) X(c) = P->line_Xw[6 * i + c];
+        lines.push_back(new MapLine(X, w.anchor, &w.map));
+        F.mvpMapLines[i] = lines.back();
+        F.mvKeyLineFunctions[i] = Eigen::Vector3d(P->line_obs[3 * i], P->line_obs[3 * i + 1], P->line_obs[3 * i + 2]);
+    }
+    const int M = P->n_planes + P->n_par + P->n_ver;
+    F.mnPlaneNum = M;
+    F.mvpMapPlanes.assign(M, static_cast<MapPlane*>(nullptr)); F.mvpParallelPlanes.assign(M, static_cast<MapPlane*>(nullptr)); F.mvpVerticalPlanes.assign(M, static_cast<MapPlane*>(nullptr));
+    F.mvbPlaneOutlier.assign(M, false); F.mvbParPlaneOutlier.assign(M, false); F.mvbVerPlaneOutlier.assign(M, false);
+    std::vector<MapPlane*> planes;
+    auto coef = [](const float* v) { cv::Mat m(4, 1, CV_32F); for (int k = 0; k < 4; ++k) m.at<float>(k) = v[k]; return m; };
+    for (int i = 0; i < M; ++i) {
+        const bool is_plane = i < P->n_planes, is_par = !is_plane && i < P->n_planes + P->n_par;
+        const int j = is_plane ? i : is_par ? i - P->n_planes : i - P->n_planes - P->n_par;
+        F.mvPlaneCoefficients.push_back(coef((is_plane ? P->plane_meas : is_par ? P->par_meas : P->ver_meas) + 4 * j));
+        planes.push_back(new MapPlane(coef((is_plane ? P->plane_map : is_par ? P->par_map : P->ver_map) + 4 * j), w.anchor, &w.map));
+        (is_plane ? F.mvpMapPlanes : is_par ? F.mvpParallelPlanes : F.mvpVerticalPlanes)[i] = planes.back();
+    }
+    F.SetPose(mat44(Tcw_in));
+    const int n = translation_only ? Optimizer::TranslationOptimization(&F) : Optimizer::PoseOptimization(&F);
+    for (int i = 0; i < 16; ++i) Tcw_out[i] = F.mTcw.at<float>(i / 4, i % 4);
+    for (int i = 0; i < F.N; ++i) o_pt[i] = F.mvbOutlier[i] ? 1 : 0;
+    for (int i = 0; i < F.NL; ++i) o_line[i] = F.mvbLineOutlier[i] ? 1 : 0;
+    for (int i = 0; i < P->n_planes; ++i) o_plane[i] = F.mvbPlaneOutlier[i] ? 1 : 0;
+    for (int i = 0; i < P->n_par; ++i) o_par[i] = F.mvbParPlaneOutlier[P->n_planes + i] ? 1 : 0;
+    for (int i = 0; i < P->n_ver; ++i) o_ver[i] = F.mvbVerPlaneOutlier[P->n_planes + P->n_par + i] ? 1 : 0;
+    for (MapLine* l : lines) delete l;
+    for (MapPlane* q : planes) delete q;
     return n;
 }

@@ -202,24 +202,33 @@ private:
 
 // cv::FileStorage / FileNode: named by the YAML save / load members of Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h (:1453-1632), which the
 // reference never calls (it loads ORBvoc.txt through loadFromTextFile, :1338-1434); inert placeholders so that the class template compiles.
+#include <map>
 #include <string>
 namespace cv {
 struct FileNode {
+    double value = 0;                                       // set when the node comes from the settings table below
+    FileNode() {}
+    explicit FileNode(double v) : value(v) {}
     FileNode operator[](const std::string&) const { return FileNode(); }
     FileNode operator[](const char*) const { return FileNode(); }
     FileNode operator[](int) const { return FileNode(); }
     size_t size() const { return 0; }
-    operator int() const { return 0; }
-    operator double() const { return 0; }
+    operator int() const { return (int)value; }
+    operator double() const { return value; }
+    operator float() const { return (float)value; }
     operator std::string() const { return std::string(); }
 };
 struct FileStorage {
     enum { READ = 0, WRITE = 1 };
     FileStorage() {}
-    FileStorage(const std::string&, int) {}
-    bool isOpened() const { return false; }
-    void release() {}
-    FileNode operator[](const std::string&) const { return FileNode(); }
+    FileStorage(const std::string& name, int) : opened_(name == "pslam-settings-table") {}
+    bool isOpened() const { return opened_; }
+    void release() { opened_ = false; }
+    // No YAML parser here: a storage opened under the name "pslam-settings-table" reads numeric keys from this process-wide table, which the
+    // optimiser driver fills with the values of the reference's Examples/RGB-D/*.yaml (Plane.AngleInfo ...) before Config::SetParameterFile.
+    static std::map<std::string, double>& table() { static std::map<std::string, double> t; return t; }
+    FileNode operator[](const std::string& key) const { auto it = table().find(key); return it == table().end() || !opened_ ? FileNode() : FileNode(it->second); }
+    bool opened_ = false;
     template <class T> FileStorage& operator<<(const T&) { return *this; }
 };
 }  // namespace cv

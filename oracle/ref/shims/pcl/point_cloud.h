@@ -12,6 +12,7 @@ namespace pcl {
 #define PCL_ERROR(...) std::fprintf(stderr, __VA_ARGS__)
 [[noreturn]] inline void stub_reached(const char* what) { std::fprintf(stderr, "oracle/ref/shims/pcl: %s is a compile-only stand-in\n", what); std::abort(); }
 struct PointXYZRGB { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0; };
+struct PointXYZRGBA { float x = 0, y = 0, z = 0; unsigned char r = 0, g = 0, b = 0, a = 0; };
 struct Normal { float normal_x = 0, normal_y = 0, normal_z = 0, curvature = 0; };
 template <class T> struct PointCloud {
     typedef std::shared_ptr<PointCloud<T>> Ptr;

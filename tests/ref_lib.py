@@ -348,3 +348,18 @@ def ref_plane_match(T, fc, mc, bad, off, pts, dTh, aTh, verTh, parTh):
     n = L.ref_plane_match(T.ctypes.data, len(fc), fc.ctypes.data, len(mc), mc.ctypes.data, bad.ctypes.data, off.ctypes.data, pts.ctypes.data, dTh, aTh, verTh, parTh,
                           om.ctypes.data, ov.ctypes.data, op.ctypes.data)
     return n, om[:len(fc)], ov[:len(fc)], op[:len(fc)]
+
+
+def ref_full_pose_optimization(p: dict, translation_only: bool = False):
+    """Optimizer::PoseOptimization(Frame*) / TranslationOptimization(Frame*) THEMSELVES (src/Optimizer.cc compiled unmodified into libmatch_ref.so) on a
+    Frame built from a planarslam_b200.synth_pose problem.  Returns dict(Tcw float32 4x4 - the reference writes the pose back as float -, n_inliers, outlier_*)."""
+    import oracle_lib
+    L = match_lib()
+    L.ref_full_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    s = oracle_lib.pose_problem_struct(p)
+    T0 = np.ascontiguousarray(p["Tcw0"], np.float32)
+    T = np.zeros((4, 4), np.float32)
+    o = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes, s.n_par, s.n_ver)]
+    n = L.ref_full_pose_optimization(C.byref(s), T0.ctypes.data, int(translation_only), T.ctypes.data, *[a.ctypes.data for a in o])
+    return dict(Tcw=T, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes],
+                outlier_par=o[3][:s.n_par], outlier_ver=o[4][:s.n_ver])

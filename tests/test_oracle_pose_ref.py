@@ -62,3 +62,25 @@ def test_oracle_translation_optimization_agrees_with_compiled_reference_g2o():
             assert np.array_equal(o[k], r[k]), (kw, k)
         assert np.allclose(o["Tcw_d"][:3, :3], r["Tcw_d"][:3, :3], rtol=0, atol=1e-12)
         assert np.linalg.norm(o["Tcw_d"][:3, 3] - r["Tcw_d"][:3, 3]) < 5e-6, kw
+
+
+@pytest.mark.skipif(ref_lib.match_lib() is None, reason="oracle/_ref/libmatch_ref.so not built and no /root/reference to build it from")
+def test_oracle_pose_agrees_with_the_reference_functions_themselves():
+    """Optimizer::PoseOptimization(Frame*) and Optimizer::TranslationOptimization(Frame*) called AS THEY ARE (src/Optimizer.cc compiled unmodified into
+    libmatch_ref.so with Frame.cc / MapPoint.cc / MapLine.cpp / MapPlane.cc; oracle/ref/match_driver.cc only fills a Frame from the problem arrays and reads
+    mTcw and the mvb*Outlier vectors back; the Plane.* settings arrive through the reference's Config::Get).  Nothing of the function is restated here.
+    The reference writes the pose back as float (Converter::toCvMat), so the comparison is against the oracle's double pose to float rounding."""
+    cases = [dict(seed=s, frame=3 * s) for s in range(8)]
+    cases += [dict(seed=20 + s, frame=s, outlier_frac=0.25, rot_pert=0.05, trans_pert=0.08) for s in range(4)]
+    cases += [dict(seed=30, frame=1, n_points=0, n_lines=0), dict(seed=7, frame=21, n_planes=0, n_par=0, n_ver=0), dict(seed=9, frame=5, n_points=40, n_lines=6)]
+    for translation_only in (False, True):
+        for kw in cases:
+            p = synth_pose.make_pose_problem(**kw)
+            o = oracle_lib.pose_optimization(p, translation_only=True) if translation_only else oracle_lib.pose_optimization(p)
+            r = ref_lib.ref_full_pose_optimization(p, translation_only)
+            assert o["n_inliers"] == r["n_inliers"], (translation_only, kw)
+            for k in FLAGS:
+                if k in o and len(r[k]):
+                    assert np.array_equal(o[k], r[k]), (translation_only, kw, k)
+            da, dt = synth_pose.pose_error(o["Tcw_d"], r["Tcw"].astype(np.float64))
+            assert da < 5e-6 and dt < 2e-5, (translation_only, kw, da, dt)
