@@ -274,7 +274,9 @@ int pslam_translation_pack(pslam_ctx* ctx, const pslam_pose_problem* probs, int 
  *               (start, end) sharing mvKeyLineFunctions (double 3).  The reference attaches every line edge to the CURRENT
  *               key frame pKF (:2169-2201); pass pKF's index in line_obs_kf to reproduce that.
  *   planes      GetWorldPos() (float 4) -> VertexPlane; observations [0] EdgePlane, [1] EdgeVerticalPlane, [2] EdgeParallelPlane
- *               with the key frame's mvPlaneCoefficients (float 4)
+ *               with the key frame's mvPlaneCoefficients (float 4).  The reference adds a plane's vertical / parallel
+ *               observations while walking lLocalMapPlanes (:2250-2350): pass them only for planes that are LOCAL (held in
+ *               mvpMapPlanes by a local key frame) - the gathering loop of the adapter does exactly that
  *   settings    Plane.AngleInfo, DistanceInfo, Chi, VPChi (vertical / parallel edges use angleInfo like the reference, :2274)
  * Outputs: optimised key-frame poses (fixed ones returned unchanged), point / line / plane positions rounded to float like
  * Converter::toCvMat, and per-observation erase flags = membership of vToErase, vLineToErase, vPlaneToErase,

@@ -384,3 +384,125 @@ extern "C" int ref_full_pose_optimization(const pslam_pose_problem* P, const flo
     for (MapPlane* q : planes) delete q;
     return n;
 }
+
+// Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*) src/Optimizer.cc:1853-2678 called as it is on a KeyFrame / MapPoint / MapLine / MapPlane graph
+// built from a pslam_lba_problem.  The current key frame is the last one; its covisible list holds every non-fixed key frame plus key frame 0 (which the
+// reference fixes through mnId == 0); the other fixed key frames are left for the function to discover through the observations.  Observation j of a
+// family sits in feature slot j of its key frame.  Read back: the poses / positions the function wrote (float, Converter::toCvMat), which slots it cleared
+// (erase_*: the observation was erased, or its landmark went bad - *_bad tells which) - everything in between is the reference's code.
+extern "C" int ref_full_local_bundle_adjustment(const pslam_lba_problem* P, pslam_lba_result* R, uint8_t* pt_bad, uint8_t* line_bad, uint8_t* plane_bad) {
+    set_plane_settings(P->angle_info, P->dist_info, 0, 0, P->plane_chi, P->vp_chi);
+    World w;
+    w.anchor->mnId = 1000000;
+    const int NP = std::max(P->n_pt_obs, 1), NLn = std::max(P->n_line_obs, 1), off1 = P->n_plane_obs[0], off2 = off1 + P->n_plane_obs[1], NPl = std::max(off2 + P->n_plane_obs[2], 1);
+    const int cur = P->n_kf - 1;
+    std::vector<KeyFrame*> kfs(P->n_kf);
+    for (int k = 0; k < P->n_kf; ++k) {
+        Frame F;
+        const float* K = P->kf_K + 5 * k;
+        Frame::fx = K[0]; Frame::fy = K[1]; Frame::cx = K[2]; Frame::cy = K[3]; Frame::invfx = 1.0f / K[0]; Frame::invfy = 1.0f / K[1];
+        F.mbf = K[4]; F.mb = F.mbf / Frame::fx;
+        F.N = NP;
+        F.mvKeysUn.resize(NP); F.mvuRight.assign(NP, -1.f); F.mvDepth.assign(NP, -1.f); F.mvInvLevelSigma2.assign(std::max(NP, NLn), 1.f);
+        F.mvLevelSigma2.assign(std::max(NP, NLn), 1.f); F.mvScaleFactors.assign(std::max(NP, NLn), 1.f); F.mnScaleLevels = std::max(NP, NLn);
+        for (int j = 0; j < P->n_pt_obs; ++j) {
+            F.mvKeysUn[j].octave = j;
+            if (P->pt_obs_kf[j] != k) continue;
+            F.mvKeysUn[j].pt.x = P->pt_obs_uvr[3 * j]; F.mvKeysUn[j].pt.y = P->pt_obs_uvr[3 * j + 1]; F.mvuRight[j] = P->pt_obs_uvr[3 * j + 2];
+            F.mvInvLevelSigma2[j] = P->pt_obs_inv_sigma2[j];
+        }
+        F.mvKeys = F.mvKeysUn;
+        F.mvpMapPoints.assign(NP, static_cast<MapPoint*>(NULL));
+        F.NL = NLn;
+        F.mvKeylinesUn.resize(NLn); F.mvKeyLineFunctions.assign(NLn, Eigen::Vector3d(0, 0, 1)); F.mvpMapLines.assign(NLn, static_cast<MapLine*>(NULL));
+        for (int j = 0; j < P->n_line_obs; ++j) F.mvKeyLineFunctions[j] = Eigen::Vector3d(P->line_obs_l[3 * j], P->line_obs_l[3 * j + 1], P->line_obs_l[3 * j + 2]);
+        F.mnPlaneNum = NPl;
+        for (int q = 0; q < NPl; ++q) { cv::Mat c = cv::Mat::zeros(4, 1, CV_32F); c.at<float>(3) = 1.f; F.mvPlaneCoefficients.push_back(c); }
+        for (int t = 0; t < 3; ++t)
+            for (int j = 0; j < P->n_plane_obs[t]; ++j)
+                if (P->plane_obs_kf[t][j] == k) for (int c = 0; c < 4; ++c) F.mvPlaneCoefficients[(t == 0 ? 0 : t == 1 ? off1 : off2) + j].at<float>(c) = P->plane_obs_meas[t][4 * j + c];
+        F.mvPlanePoints.resize(NPl);
+        F.mvpMapPlanes.assign(NPl, static_cast<MapPlane*>(nullptr)); F.mvpParallelPlanes.assign(NPl, static_cast<MapPlane*>(nullptr)); F.mvpVerticalPlanes.assign(NPl, static_cast<MapPlane*>(nullptr));
+        F.mTcw = mat44(P->kf_Tcw + 16 * k);
+        F.SetPose(mat44(P->kf_Tcw + 16 * k));
+        kfs[k] = new KeyFrame(F, &w.map, static_cast<KeyFrameDatabase*>(NULL));
+        kfs[k]->mnId = k;
+    }
+    for (int k = 0; k < P->n_kf; ++k)
+        if (k != cur && (!P->kf_fixed[k] || k == 0)) kfs[cur]->mvpOrderedConnectedKeyFrames.push_back(kfs[k]);
+    const float zero3[3] = {0, 0, 0};
+    std::vector<MapPoint*> pts(P->n_points);
+    for (int i = 0; i < P->n_points; ++i) { pts[i] = w.make_point(P->pt_Xw + 3 * i, zero3, 0, 0, nullptr, false); pts[i]->mnId = i; pts[i]->mpRefKF = nullptr; }
+    for (int j = 0; j < P->n_pt_obs; ++j) {
+        KeyFrame* kf = kfs[P->pt_obs_kf[j]]; MapPoint* p = pts[P->pt_obs_pt[j]];
+        if (p->IsInKeyFrame(kf)) return -2;                                  // the object graph holds one observation per (point, key frame)
+        kf->mvpMapPoints[j] = p; p->AddObservation(kf, j);
+        if (!p->mpRefKF) p->mpRefKF = kf;
+    }
+    for (MapPoint* p : pts) if (!p->mpRefKF) p->mpRefKF = kfs[cur];
+    std::vector<MapLine*> lines(P->n_lines);
+    for (int i = 0; i < P->n_lines; ++i) {
+        Vector6d X;
+        for (int c = 0; c < 6; ++c) X(c) = P->line_Xw[6 * i + c];
+        lines[i] = new MapLine(X, kfs[cur], &w.map);
+        lines[i]->mnId = i; lines[i]->mpRefKF = nullptr;
+    }
+    std::vector<KeyFrame*> line_obs_holder(P->n_line_obs);
+    for (int j = 0; j < P->n_line_obs; ++j) {                               // every line edge hangs on the CURRENT key frame (the reference's quirk); the observing
+        MapLine* l = lines[P->line_obs_line[j]];                            // key frame only has to be distinct per observation of a line: take them in order
+        int k = 0;
+        while (k < P->n_kf && (l->mObservations.count(kfs[(cur + P->n_kf - k) % P->n_kf]))) ++k;
+        if (k == P->n_kf) return -3;
+        KeyFrame* kf = kfs[(cur + P->n_kf - k) % P->n_kf];
+        kf->mvpMapLines[j] = l; l->AddObservation(kf, j); line_obs_holder[j] = kf;
+        if (!l->mpRefKF) l->mpRefKF = kf;
+    }
+    for (MapLine* l : lines) if (!l->mpRefKF) l->mpRefKF = kfs[cur];
+    std::vector<MapPlane*> planes(P->n_planes);
+    for (int i = 0; i < P->n_planes; ++i) {
+        cv::Mat c(4, 1, CV_32F);
+        for (int q = 0; q < 4; ++q) c.at<float>(q) = P->plane_Xw[4 * i + q];
+        planes[i] = new MapPlane(c, kfs[cur], &w.map);
+        planes[i]->mnId = i;
+    }
+    for (int t = 0; t < 3; ++t)
+        for (int j = 0; j < P->n_plane_obs[t]; ++j) {
+            KeyFrame* kf = kfs[P->plane_obs_kf[t][j]]; MapPlane* q = planes[P->plane_obs_plane[t][j]];
+            const int slot = (t == 0 ? 0 : t == 1 ? off1 : off2) + j;
+            if (t == 0) { kf->mvpMapPlanes[slot] = q; q->AddObservation(kf, slot); }
+            else if (t == 1) { kf->mvpVerticalPlanes[slot] = q; q->AddVerObservation(kf, slot); }
+            else { kf->mvpParallelPlanes[slot] = q; q->AddParObservation(kf, slot); }
+        }
+    bool stop = false;
+    Optimizer::LocalBundleAdjustment(kfs[cur], &stop, &w.map);
+    for (int k = 0; k < P->n_kf; ++k) {
+        cv::Mat T = kfs[k]->GetPose();
+        for (int i = 0; i < 16; ++i) { R->kf_Tcw[16 * k + i] = T.at<float>(i / 4, i % 4); R->kf_Tcw_d[16 * k + i] = T.at<float>(i / 4, i % 4); }
+    }
+    for (int i = 0; i < P->n_points; ++i) {
+        cv::Mat X = pts[i]->GetWorldPos();
+        for (int c = 0; c < 3; ++c) { R->pt_Xw[3 * i + c] = X.at<float>(c); R->pt_Xw_d[3 * i + c] = X.at<float>(c); }
+        pt_bad[i] = pts[i]->isBad() ? 1 : 0;
+    }
+    for (int i = 0; i < P->n_lines; ++i) {
+        Vector6d X = lines[i]->GetWorldPos();
+        for (int c = 0; c < 6; ++c) { R->line_Xw[6 * i + c] = X(c); R->line_Xw_d[6 * i + c] = X(c); }
+        line_bad[i] = lines[i]->isBad() ? 1 : 0;
+    }
+    for (int i = 0; i < P->n_planes; ++i) {
+        cv::Mat X = planes[i]->GetWorldPos();
+        for (int c = 0; c < 4; ++c) { R->plane_Xw[4 * i + c] = X.at<float>(c); R->plane_Xw_d[4 * i + c] = X.at<float>(c); }
+        plane_bad[i] = planes[i]->isBad() ? 1 : 0;
+    }
+    for (int j = 0; j < P->n_pt_obs; ++j) R->erase_pt[j] = kfs[P->pt_obs_kf[j]]->mvpMapPoints[j] ? 0 : 1;
+    for (int j = 0; j < P->n_line_obs; ++j) R->erase_line[j] = line_obs_holder[j]->mvpMapLines[j] ? 0 : 1;
+    for (int j = 0; j < P->n_plane_obs[0]; ++j) R->erase_plane[0][j] = kfs[P->plane_obs_kf[0][j]]->mvpMapPlanes[j] ? 0 : 1;
+    for (int j = 0; j < P->n_plane_obs[1]; ++j) R->erase_plane[1][j] = kfs[P->plane_obs_kf[1][j]]->mvpVerticalPlanes[off1 + j] ? 0 : 1;
+    for (int j = 0; j < P->n_plane_obs[2]; ++j) R->erase_plane[2][j] = kfs[P->plane_obs_kf[2][j]]->mvpParallelPlanes[off2 + j] ? 0 : 1;
+    R->iterations[0] = R->iterations[1] = -1;
+    for (MapPlane* q : planes) delete q;
+    for (MapLine* l : lines) delete l;
+    for (MapPoint* q : pts) delete q;
+    for (KeyFrame* k : kfs) delete k;
+    return 0;
+}

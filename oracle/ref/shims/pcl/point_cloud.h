@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY.  The reference's headers and sources name PCL types for point-cloud members (plane boundary clouds, voxel filters, RANSAC
 // refits, integral-image normals) that none of the pinned paths (PEAC, optimisers, matchers) executes.  These stand-ins exist so that the
-// reference's translation units COMPILE; any PCL algorithm that would actually run aborts.
+// reference's translation units COMPILE; they pass EMPTY clouds through (MapPlane::UpdateCoefficientsAndPoints after a bundle adjustment refreshes the boundary
+// cloud, which the drivers leave empty) and abort if a PCL algorithm would actually have to run.
 #pragma once
 #include <cstdio>
 #include <cstdlib>
@@ -40,8 +41,9 @@ struct PointIndices { typedef std::shared_ptr<PointIndices> Ptr; std::vector<int
 enum { SACMODEL_PLANE = 0, SAC_RANSAC = 0 };
 template <class T> struct VoxelGrid {
     void setLeafSize(float, float, float) {}
-    template <class P> void setInputCloud(const P&) {}
-    void filter(PointCloud<T>&) { stub_reached("pcl::VoxelGrid::filter"); }
+    template <class P> void setInputCloud(const P& c) { n_in_ = c ? c->size() : 0; }
+    void filter(PointCloud<T>& out) { if (n_in_) stub_reached("pcl::VoxelGrid::filter on a non-empty cloud"); out.clear(); }     // empty in, empty out
+    size_t n_in_ = 0;
 };
 template <class T> struct SACSegmentation {
     void setOptimizeCoefficients(bool) {}
@@ -60,6 +62,6 @@ template <class T, class N> struct IntegralImageNormalEstimation {
     template <class P> void setInputCloud(const P&) {}
     void compute(PointCloud<N>&) { stub_reached("pcl::IntegralImageNormalEstimation::compute"); }
 };
-template <class T, class M> void transformPointCloud(const PointCloud<T>&, PointCloud<T>&, const M&) { stub_reached("pcl::transformPointCloud"); }
+template <class T, class M> void transformPointCloud(const PointCloud<T>& in, PointCloud<T>& out, const M&) { if (in.size()) stub_reached("pcl::transformPointCloud on a non-empty cloud"); out.clear(); }
 #endif
 }

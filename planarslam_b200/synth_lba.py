@@ -178,3 +178,18 @@ def make_lba_problem(seed: int, n_kf: int = 20, n_fixed: int = 1, n_points: int 
                 line_obs_line=c(line_obs_line), line_obs_l=c(line_obs_l), plane_Xw=c(plane0.astype(np.float32)),
                 plane_obs_kf=plane_obs_kf, plane_obs_plane=plane_obs_plane, plane_obs_meas=plane_obs_meas,
                 kf_Tcw_true=T_true, pt_Xw_true=Xw_true, line_Xw_true=line_true, plane_Xw_true=plane_true, **LBA_SETTINGS)
+
+
+def restrict_to_local_planes(p: dict) -> dict:
+    """Optimizer::LocalBundleAdjustment only walks LOCAL map planes - those a local key frame holds in mvpMapPlanes (src/Optimizer.cc:1917-1935) - and adds a
+    plane's vertical / parallel observations inside that walk (:2250-2350): a vertical / parallel observation of a plane nobody matched as a plane is never
+    read.  Drops such observations from a make_lba_problem dict in place (the C ABI expects the caller to pass only what the reference would read)."""
+    import numpy as np
+    has = np.zeros(len(p["plane_Xw"]), bool)
+    has[p["plane_obs_plane"][0]] = True
+    for t in (1, 2):
+        keep = has[p["plane_obs_plane"][t]]
+        p["plane_obs_plane"][t] = np.ascontiguousarray(p["plane_obs_plane"][t][keep])
+        p["plane_obs_kf"][t] = np.ascontiguousarray(p["plane_obs_kf"][t][keep])
+        p["plane_obs_meas"][t] = np.ascontiguousarray(p["plane_obs_meas"][t][keep])
+    return p

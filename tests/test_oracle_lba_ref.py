@@ -88,3 +88,43 @@ def test_oracle_lba_full_size_agrees_with_compiled_reference_g2o():
     """BASELINE.json's local-map size (20 key frames, 1700 points, 5000 observations, 100 lines, 30 plane observations)."""
     p = synth_lba.make_lba_problem(4)
     _same(oracle_lib.local_bundle_adjustment(p), ref_lib.ref_local_bundle_adjustment(p))
+
+
+@pytest.mark.skipif(ref_lib.match_lib() is None, reason="oracle/_ref/libmatch_ref.so not built and no /root/reference to build it from")
+def test_oracle_lba_agrees_with_the_reference_function_itself():
+    """Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*) called AS IT IS (src/Optimizer.cc compiled unmodified into libmatch_ref.so with KeyFrame.cc,
+    MapPoint.cc, MapLine.cpp, MapPlane.cc, Map.cc): oracle/ref/match_driver.cc builds the key frames (covisibility list, feature slots), map points / lines /
+    planes and their observation maps from the problem arrays, calls the function, and reads back the poses / positions it wrote (float) and the feature
+    slots it cleared.  The local / fixed key-frame discovery, graph construction, both optimisations, the gating, the erasures (with the bad-landmark cascade
+    of EraseObservation) and the write-back are all the reference's.  A cleared slot means "this observation was erased" or "its landmark went bad";
+    pt_bad / line_bad / plane_bad tell which.  Line edges hang on the current key frame (the reference's quirk), so the problems are made with line_kf_quirk."""
+    small = dict(SMALL, line_kf_quirk=True)
+    cases = [dict(seed=s, **small) for s in (1, 10, 11, 12)]
+    cases += [dict(seed=2, n_kf=8, n_points=300, n_pt_obs=900, n_lines=0, n_line_obs=0, n_plane_obs=(0, 0, 0)),
+              dict(seed=30, n_kf=5, n_points=150, n_pt_obs=400, n_lines=10, n_line_obs=12, n_plane_obs=(4, 1, 1), mono_frac=1.0, line_kf_quirk=True)]
+    hard = [dict(seed=3, n_kf=10, n_points=400, n_pt_obs=1200, n_lines=30, n_line_obs=40, n_plane_obs=(10, 3, 2), line_kf_quirk=True, line_norm3=False,
+                 outlier_frac=0.15, plane_outlier_frac=0.3)] + [dict(seed=20 + s, **small, line_norm3=False, outlier_frac=0.2, plane_outlier_frac=0.25) for s in range(3)]
+    big = [dict(seed=4, line_kf_quirk=True)]                               # BASELINE.json's local-map size
+    n_bad = n_erased = 0
+    for kw in cases + hard + big:
+        p = synth_lba.restrict_to_local_planes(synth_lba.make_lba_problem(**kw))
+        o, r = oracle_lib.local_bundle_adjustment(p), ref_lib.ref_full_local_bundle_adjustment(p)
+        assert np.array_equal(o["erase_pt"] | r["pt_bad"][p["pt_obs_pt"]], r["erase_pt"]), kw
+        assert np.array_equal(o["erase_pt"][r["pt_bad"][p["pt_obs_pt"]] == 0], r["erase_pt"][r["pt_bad"][p["pt_obs_pt"]] == 0]), kw
+        if len(p["line_obs_line"]):
+            assert np.array_equal(o["erase_line"] | r["line_bad"][p["line_obs_line"]], r["erase_line"]), kw
+        for t in range(3):
+            if len(p["plane_obs_plane"][t]):
+                assert np.array_equal(o["erase_plane"][t] | r["plane_bad"][p["plane_obs_plane"][t]], r["erase_plane"][t]), (kw, t)
+        tol = (2e-5, 5e-5) if kw in hard else (1e-6, 1e-6)                  # the reference writes float poses back; "hard": see the module docstring
+        for k in range(len(o["kf_Tcw_d"])):
+            da, dt = synth_pose.pose_error(o["kf_Tcw_d"][k], r["kf_Tcw_d"][k])
+            assert da < tol[0] and dt < tol[1], (kw, k, da, dt)
+        assert np.median(np.abs(o["pt_Xw_d"] - r["pt_Xw_d"]).max(1)) < 5e-6 and np.abs(o["pt_Xw_d"] - r["pt_Xw_d"]).max() < 2e-3, kw
+        has = np.zeros(len(p["plane_Xw"]), bool)
+        has[p["plane_obs_plane"][0]] = True
+        if has.any():
+            d = np.minimum(np.abs(o["plane_Xw_d"] - r["plane_Xw_d"]).max(1), np.abs(o["plane_Xw_d"] + r["plane_Xw_d"]).max(1))[has]
+            assert d.max() < 5e-5, (kw, d.max())
+        n_bad += int(r["pt_bad"].sum()); n_erased += int(o["erase_pt"].sum())
+    assert n_bad > 50 and n_erased > 1000
