@@ -506,3 +506,31 @@ extern "C" int ref_full_local_bundle_adjustment(const pslam_lba_problem* P, psla
     for (KeyFrame* k : kfs) delete k;
     return 0;
 }
+
+// Frame::ComputeStereoFromRGBD(imDepth) src/Frame.cc:603-621 and Frame::isLineGood(imGray, imDepth, K) src/Frame.cc:189-267 called as they are (with the
+// reference's src/LineExtractor.cpp and libc rand()) on a Frame holding the key points / key lines.
+extern "C" void ref_full_compute_stereo_from_rgbd(int n, const float* keys_xy, const float* keys_un_xy, const float* depth, int w, int h, float bf, float* u_right, float* z) {
+    Frame F;
+    F.N = n; F.mbf = bf;
+    F.mvKeys.resize(n); F.mvKeysUn.resize(n);
+    for (int i = 0; i < n; ++i) { F.mvKeys[i].pt.x = keys_xy[2 * i]; F.mvKeys[i].pt.y = keys_xy[2 * i + 1]; F.mvKeysUn[i].pt.x = keys_un_xy[2 * i]; F.mvKeysUn[i].pt.y = keys_un_xy[2 * i + 1]; }
+    cv::Mat imDepth(h, w, CV_32F, (void*)depth);
+    F.ComputeStereoFromRGBD(imDepth);
+    for (int i = 0; i < n; ++i) { u_right[i] = F.mvuRight[i]; z[i] = F.mvDepth[i]; }
+}
+
+extern "C" void ref_full_lines3d_frame(const void* keylines, int n_lines, const float* depth, int w, int h, const float* cam, uint32_t seed, int skip, float* depth_line,
+                                       double* lines3d) {
+    static_assert(sizeof(cv::line_descriptor::KeyLine) == 68, "KeyLine layout");
+    const cv::line_descriptor::KeyLine* kl = (const cv::line_descriptor::KeyLine*)keylines;
+    Frame F;
+    Frame::fx = cam[0]; Frame::fy = cam[1]; Frame::cx = cam[2]; Frame::cy = cam[3]; Frame::invfx = 1.0f / cam[0]; Frame::invfy = 1.0f / cam[1];
+    F.mvKeylinesUn.assign(kl, kl + n_lines);
+    F.NL = n_lines;
+    cv::Mat K = (cv::Mat_<double>(3, 3) << cam[0], 0, cam[2], 0, cam[1], cam[3], 0, 0, 1);       // tmpK, src/Frame.cc:84-86
+    cv::Mat imDepth(h, w, CV_32F, (void*)depth), imGray;
+    srand(seed);
+    for (int i = 0; i < skip; ++i) (void)rand();
+    F.isLineGood(imGray, imDepth, K);
+    for (int i = 0; i < n_lines; ++i) { depth_line[i] = F.mvDepthLine[i]; for (int c = 0; c < 6; ++c) lines3d[6 * i + c] = F.mvLines3D[i](c); }
+}

@@ -380,3 +380,26 @@ def ref_full_local_bundle_adjustment(p: dict) -> dict:
     out = _lba.finish(r, o)
     out["pt_bad"], out["line_bad"], out["plane_bad"] = bad[0][:s.n_points], bad[1][:s.n_lines], bad[2][:s.n_planes]
     return out
+
+
+def ref_full_compute_stereo_from_rgbd(keys_xy, keys_un_xy, depth, bf: float):
+    """Frame::ComputeStereoFromRGBD itself (compiled src/Frame.cc).  Same arguments / returns as oracle_lib.compute_stereo_from_rgbd."""
+    L = match_lib()
+    L.ref_full_compute_stereo_from_rgbd.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
+    L.ref_full_compute_stereo_from_rgbd.restype = None
+    k, ku, d = np.ascontiguousarray(keys_xy, np.float32), np.ascontiguousarray(keys_un_xy, np.float32), np.ascontiguousarray(depth, np.float32)
+    ur, dz = np.zeros(len(k), np.float32), np.zeros(len(k), np.float32)
+    L.ref_full_compute_stereo_from_rgbd(len(k), k.ctypes.data, ku.ctypes.data, d.ctypes.data, d.shape[1], d.shape[0], bf, ur.ctypes.data, dz.ctypes.data)
+    return ur, dz
+
+
+def ref_full_lines3d_frame(keylines, depth, cam, seed=1, skip=0):
+    """Frame::isLineGood itself (compiled src/Frame.cc + src/LineExtractor.cpp, libc rand() after srand(seed) and `skip` draws): (mvDepthLine, mvLines3D)."""
+    from oracle_lib import KEYLINE_DTYPE
+    L = match_lib()
+    L.ref_full_lines3d_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_full_lines3d_frame.restype = None
+    kl, d, camv = np.ascontiguousarray(keylines, KEYLINE_DTYPE), np.ascontiguousarray(depth, np.float32), np.asarray(cam, np.float32)
+    dl, l3 = np.zeros(len(kl), np.float32), np.zeros((len(kl), 6))
+    L.ref_full_lines3d_frame(kl.ctypes.data, len(kl), d.ctypes.data, d.shape[1], d.shape[0], camv.ctypes.data, seed, skip, dl.ctypes.data, l3.ctypes.data)
+    return dl, l3

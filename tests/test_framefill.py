@@ -48,3 +48,16 @@ def test_stereo_from_rgbd_gpu_matches_oracle():
         our, odz = oracle_lib.compute_stereo_from_rgbd(xy[f][:n[f]], xy[f][:n[f]], d16[f].astype(np.float32) * factor, bf)
         assert np.array_equal(ur[f, :n[f]], our) and np.array_equal(dz[f, :n[f]], odz), f
         assert (ur[f, n[f]:] == -1).all() and (dz[f, n[f]:] == -1).all()
+
+
+def test_oracle_identical_to_frame_compute_stereo_from_rgbd_itself():
+    """Frame::ComputeStereoFromRGBD called as it is (src/Frame.cc compiled unmodified into oracle/_ref/libmatch_ref.so)."""
+    import ref_lib
+    if ref_lib.match_lib() is None:
+        pytest.skip("oracle/_ref/libmatch_ref.so not built and no /root/reference to build it from")
+    for seed in range(4):
+        keys, d16 = _case(seed)
+        keys_un = keys + np.float32(0.25) * (seed % 2)
+        depth = d16.astype(np.float32) * np.float32(1.0 / synth.DEPTH_FACTOR)
+        o, r = oracle_lib.compute_stereo_from_rgbd(keys, keys_un, depth, 40.0), ref_lib.ref_full_compute_stereo_from_rgbd(keys, keys_un, depth, 40.0)
+        assert np.array_equal(o[0], r[0]) and np.array_equal(o[1], r[1]) and (r[1] > 0).sum() > 900

@@ -52,3 +52,20 @@ def test_oracle_line3d_identical_to_compiled_reference():
     kl, depth = case_inputs(2, 0.2, 0.01)
     o, r = oracle_lib.lines3d_frame(kl, depth, icl, seed=3), ref_lib.ref_lines3d_frame(kl, depth, icl, seed=3)
     assert all(np.array_equal(o[k], r[k], equal_nan=(k == "director")) for k in KEYS)
+
+
+@pytest.mark.skipif(ref_lib.match_lib() is None, reason="oracle/_ref/libmatch_ref.so not built and no /root/reference to build it from")
+def test_oracle_line3d_identical_to_frame_is_line_good_itself():
+    """Frame::isLineGood(imGray, imDepth, K) called AS IT IS (src/Frame.cc + src/LineExtractor.cpp compiled unmodified into libmatch_ref.so): the sampling /
+    back-projection loop that libline3d_ref's driver restates is the reference's here too.  mvDepthLine and mvLines3D bit-identical to the oracle."""
+    n_valid = 0
+    for s in range(10):
+        for frac, sigma in ((0.0, 0.0), (0.1 + 0.04 * s, 0.004 * (s + 1))):
+            kl, depth = case_inputs(s, frac, sigma)
+            for seed, skip in ((1, 0), (40 + s, 3 * s)):
+                o = oracle_lib.lines3d_frame(kl, depth, synth.TUM3_K, seed=seed, skip=skip)
+                dl, l3 = ref_lib.ref_full_lines3d_frame(kl, depth, synth.TUM3_K, seed=seed, skip=skip)
+                assert np.array_equal(o["depth_line"], dl) and np.array_equal(o["lines3d"], l3), (s, frac, seed)
+                assert np.array_equal(o["valid"].astype(bool), np.any(l3 != 0, axis=1)), (s, frac, seed)
+                n_valid += int(o["valid"].sum())
+    assert n_valid > 800
