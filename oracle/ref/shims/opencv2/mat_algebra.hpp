@@ -2,12 +2,14 @@
 // src/LineExtractor.cpp: products accumulate left to right over k in double like cv::gemm's generic path, 3x3 inverse by cofactors like
 // cv::invert, cv::SVD = OpenCV's Jacobi algorithm as restated in oracle/cvsvd.h.  Included from opencv.hpp inside no namespace.
 #pragma once
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <ostream>
 #include "../../../match.h"
 #include "../../../cvsvd.h"
 
+struct CvMat;                                            // legacy C type named by include/PnPsolver.h member declarations
 namespace cv {
 
 inline Mat newLike(int r, int c, int type) { return Mat(MatZeros{r, c, type, 0}); }
@@ -103,6 +105,18 @@ inline double norm(const Mat& a, const Mat& b, int normType) {          // NORM_
     return d;
 }
 inline void transpose(const Mat& src, Mat& dst) { dst = src.t(); }
+inline std::ostream& operator<<(std::ostream& os, const Mat::SizeTag&) { return os << "[size]"; }
+struct Scalar { double v[4] = {0, 0, 0, 0}; Scalar() {} Scalar(double a, double b = 0, double c = 0, double d = 0) { v[0] = a; v[1] = b; v[2] = c; v[3] = d; }
+                double& operator[](int i) { return v[i]; } const double& operator[](int i) const { return v[i]; } static Scalar all(double a) { return Scalar(a, a, a, a); } };
+// cv::sum / cv::trace: one channel, accumulated in double in row-major order like OpenCV's sum_ / the diagonal walk of cv::trace
+inline Scalar sum(const Mat& m) { double a = 0; for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) a += m.getd(r, c); return Scalar(a); }
+inline Scalar trace(const Mat& m) { double a = 0; for (int i = 0; i < m.rows && i < m.cols; ++i) a += m.getd(i, i); return Scalar(a); }
+enum { CV_BGR2GRAY = 6, CV_RGB2GRAY = 7, CV_BGRA2GRAY = 10, CV_RGBA2GRAY = 11 };
+[[noreturn]] inline void shim_unreachable(const char* what) { std::fprintf(stderr, "oracle/ref/shims: %s is a compile-only stand-in\n", what); std::abort(); }
+inline void cvtColor(const Mat&, Mat&, int) { shim_unreachable("cv::cvtColor"); }
+template <class... A> inline void initUndistortRectifyMap(A&&...) { shim_unreachable("cv::initUndistortRectifyMap"); }
+struct RNG { enum { UNIFORM = 0, NORMAL = 1 }; explicit RNG(uint64_t = 0) {} void fill(Mat&, int, const Scalar&, const Scalar&) { shim_unreachable("cv::RNG::fill"); } };
+template <class E> inline void eigen2cv(const E& src, Mat& dst) { dst = newLike((int)src.rows(), (int)src.cols(), CV_64F); for (int r = 0; r < dst.rows; ++r) for (int c = 0; c < dst.cols; ++c) dst.setd(r, c, (double)src(r, c)); }
 inline Mat& operator/=(Mat& m, double s) { for (int r = 0; r < m.rows; ++r) for (int c = 0; c < m.cols; ++c) m.setd(r, c, m.depth() == CV_64F ? m.getd(r, c) / s : (double)((float)m.getd(r, c) / (float)s)); return m; }
 inline std::ostream& operator<<(std::ostream& os, const Mat& m) {
     os << "[";
@@ -132,6 +146,7 @@ public:
     Mat_() {}
     Mat_(int r, int c) : Mat(MatZeros{r, c, sizeof(T) == 8 ? CV_64F : (sizeof(T) == 4 ? CV_32F : CV_8U), 0}) {}
     Mat_(const Mat& m) : Mat(m) {}
+    static Mat_ eye(int r, int c) { return Mat_(Mat::eye(r, c, sizeof(T) == 8 ? CV_64F : CV_32F)); }
     T& operator()(int r, int c) { return this->template at<T>(r, c); }
     const T& operator()(int r, int c) const { return this->template at<T>(r, c); }
     template <class U> MatCommaInitializer_<T> operator<<(U v) { (*this)(0, 0) = (T)v; return MatCommaInitializer_<T>{this, 1}; }

@@ -187,9 +187,14 @@ public:
     void setd(int r, int c, double v) { if (depth() == CV_64F) at<double>(r, c) = v; else at<float>(r, c) = (float)v; }
     template <class T> T& at(int i) const { return cols == 1 ? const_cast<Mat*>(this)->at<T>(i, 0) : const_cast<Mat*>(this)->at<T>(i / cols, i % cols); }
     uchar* data() const { return data_; }
+    static MatZeros zeros(Size sz, int type) { return MatZeros{sz.height, sz.width, type, 0}; }      // Size(width, height)
+    explicit Mat(const Point3f& p) { create(3, 1, CV_32F); at<float>(0, 0) = p.x; at<float>(1, 0) = p.y; at<float>(2, 0) = p.z; }
+    void resize(int nrows) { Mat m(nrows, cols, type_); for (int r = 0; r < nrows; ++r) std::memset(m.ptr(r), 0, m.step); for (int r = 0; r < nrows && r < rows; ++r) std::memcpy(m.ptr(r), ptr(r), step < m.step ? step : m.step); *this = m; }
+    struct SizeTag {};                                          // only streamed in a log line of Tracking's constructor
+    inline static const SizeTag size{};
+    int channels() const { return (type_ >> 3) + 1; }
 private:
     void copyRows(Mat& dst) const { for (int r = 0; r < rows; ++r) std::memcpy(dst.data_ + (size_t)r * dst.step, data_ + (size_t)r * step, (size_t)cols * esz(type_)); }
-    int channels() const { return (type_ >> 3) + 1; }
     static size_t esz(int type) { static const size_t d[8] = {1, 1, 2, 2, 4, 4, 8, 2}; return d[type & 7] * (size_t)((type >> 3) + 1); }
     int type_ = 0;
     std::shared_ptr<uchar> owner_;

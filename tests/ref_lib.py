@@ -403,3 +403,26 @@ def ref_full_lines3d_frame(keylines, depth, cam, seed=1, skip=0):
     dl, l3 = np.zeros(len(kl), np.float32), np.zeros((len(kl), 6))
     L.ref_full_lines3d_frame(kl.ctypes.data, len(kl), d.ctypes.data, d.shape[1], d.shape[0], camv.ctypes.data, seed, skip, dl.ctypes.data, l3.ctypes.data)
     return dl, l3
+
+
+_track = None
+
+
+def track_lib():
+    """oracle/_ref/libtrack_ref.so: src/Tracking.cc compiled unmodified (links against libmatch_ref.so); oracle/ref/track_driver.cc calls TrackManhattanFrame."""
+    global _track
+    if _track is None and match_lib() is not None:
+        _track = _load("libtrack_ref.so")
+    return _track
+
+
+def ref_track_manhattan_frame(R_last, normals, dirs):
+    """Tracking::TrackManhattanFrame itself.  Returns the 3x3 float32 rotation it returns."""
+    L = track_lib()
+    L.ref_track_manhattan_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    R = np.ascontiguousarray(R_last, np.float32).reshape(3, 3)
+    nr, dr = np.ascontiguousarray(normals, np.float32).reshape(-1, 3), np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+    out = np.zeros((3, 3), np.float32)
+    rc = L.ref_track_manhattan_frame(R.ctypes.data, nr.ctypes.data, len(nr), dr.ctypes.data, len(dr), out.ctypes.data)
+    assert rc == 33, rc
+    return out

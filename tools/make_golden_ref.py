@@ -9,6 +9,7 @@ the GPU box and may not exist in a later container, so the outputs are committed
                                     vocabularies / features: BowVector and FeatureVector in full for each case
   tests/golden/line3d_reference.npz the 3-D line fit of src/LineExtractor.cpp (+ libc rand) on clean and corrupted depth: every output field
   tests/golden/pose_reference.npz   PoseOptimization by the reference's g2o (libpose_ref.so): optimised pose, inlier count and outlier flags
+  tests/golden/manhattan_reference.npz  Tracking::TrackManhattanFrame (libtrack_ref.so): the returned rotation
   tests/golden/match_reference.npz  the matchers (libmatch_ref.so): SearchByProjection x2, SearchByBoW, LSDmatcher::SearchByProjection, PlaneMatcher
   tests/golden/lba_reference.npz    LocalBundleAdjustment by the reference's g2o (libpose_ref.so): key-frame poses, points, lines, planes, erase flags
 Run: python tools/make_golden_ref.py"""
@@ -134,6 +135,15 @@ if __name__ == "__main__":
             mg[f"{name}_{k}"] = arr
         print("match", name, int(r[0]), "matches")
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "match_reference.npz"), **mg)
+
+    from test_oracle_manhattan_ref import CASES as MH_CASES
+    from planarslam_b200.synth_manhattan import make_manhattan
+    hg = {}
+    for i, kw in enumerate(MH_CASES):
+        R_last, normals, dirs, _ = make_manhattan(**kw)
+        hg[f"R{i}"] = ref_lib.ref_track_manhattan_frame(R_last, normals, dirs)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "manhattan_reference.npz"), **hg)
+    print("manhattan", len(MH_CASES), "cases")
     path = os.path.join(ROOT, "tests", "golden", "orb_reference.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")
