@@ -10,6 +10,8 @@
 // Third-party arithmetic: cv::SVD on a 3x3 float matrix (oracle/cvsvd.h), cv::gemm float with double accumulators, cv::norm,
 // cv::determinant (only through |det + 1| < 0.5).  PARITY UNPINNED: the reference ships no vectors for this path; the input surface
 // normals come from PCL, so tests feed synthetic normals.
+// Pinned: agrees with the reference's own Tracking::TrackManhattanFrame (src/Tracking.cc compiled unmodified, oracle/ref/track_driver.cc ->
+// oracle/_ref/libtrack_ref.so) to 1-3 float ulp on 15 cases (tests/test_oracle_manhattan_ref.py, tests/golden/manhattan_reference.npz).
 #pragma once
 #include <cstdint>
 #include <vector>
