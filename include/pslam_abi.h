@@ -327,10 +327,9 @@ typedef struct pslam_keyline {
 
 int pslam_lsd_max_segments(const pslam_ctx* ctx);     /* segment capacity per frame of the calls below */
 /* Which pixels the NFA validation of LSD_REFINE_ADV counts inside a rectangle (LineSegmentDetectorImpl::rect_nfa, OpenCV
- * imgproc lsd.cpp - reached from src/LSDextractor.cpp:16): 0 = the published LSD rectangle iterator (default; the variant the
- * round-1 GPU parity runs validated), 1 = OpenCV 4.x's enumeration (pinned bit for bit against cv2 4.13 in the oracle; device
- * code checked on the host only so far).  The environment variable PSLAM_LSD_RECT_ENUM=cv4 selects 1
- * as the default of a new context. */
+ * imgproc lsd.cpp - reached from src/LSDextractor.cpp:16): 1 = OpenCV 4.x's enumeration (DEFAULT; pinned bit for bit against
+ * cv2 4.13 in the oracle), 0 = the published LSD rectangle iterator.  The environment variable
+ * PSLAM_LSD_RECT_ENUM=published selects 0 as the default of a new context. */
 int pslam_lsd_set_rect_enumeration(pslam_ctx* ctx, int mode);
 /* cv::LineSegmentDetector::detect on nframes frames: segs [nframes][cap][4] float (x1 y1 x2 y2), wpn [nframes][cap][3] double
  * (width, precision, log-NFA; -1 unless refine == 2), n [nframes].  PSLAM_E_CAPACITY when a frame has more than cap segments. */
@@ -426,6 +425,9 @@ int pslam_lines_in_frustum(pslam_ctx* ctx, const pslam_line_frustum_frame* frame
  * mvpMapLines[i]->Observations() > 0) on entry, mvScaleFactors.  Map side, one entry per element of vpMapLines: skip (null /
  * isBad() / !mbTrackInView), mnTrackScaleLevel, mTrackViewCos, mTrackProjX1 Y1 X2 Y2, GetDescriptor(), Observations() > 0.
  * assigned[i] = index of the map line the call stores into F.mvpMapLines[i], -1 where it leaves the entry alone.
+ * A predicted level outside [0, n_levels) - MapLine::PredictScale does not clamp, so pslam_lines_in_frustum produces them for lines seen
+ * from close by - is accepted: the radius uses scale_factors[clamp(level)] (the reference reads past mvScaleFactors there, undefined
+ * behaviour), the octave gate uses the raw level like the reference.
  * Returns nmatches (>= 0) or a negative pslam_status. */
 int pslam_line_search_by_projection(pslam_ctx* ctx, int n_frame_lines, const float* pt, const float* angle, const int32_t* octave, const uint8_t* desc,
                                     const uint8_t* has_obs, const float* scale_factors, int n_levels, int n_map_lines, const uint8_t* skip,

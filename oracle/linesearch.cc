@@ -21,7 +21,7 @@ int line_search_by_projection(const LineFrameView& F, const MapLinesView& M, flo
         if (bFactor) r *= th;
         // GetLinesInArea(x1, y1, x2, y2, r * scale[level], level - 1, level)
         const float x1 = M.proj[4 * m], y1 = M.proj[4 * m + 1], x2 = M.proj[4 * m + 2], y2 = M.proj[4 * m + 3];
-        const float rr = r * F.scale_factors[nPredictLevel];
+        const float rr = r * F.scale_factors[std::min(std::max(nPredictLevel, 0), F.n_levels - 1)];   // the reference reads past mvScaleFactors here (level not clamped by MapLine::PredictScale): index clamped, level gate keeps the raw level
         const int minLevel = nPredictLevel - 1, maxLevel = nPredictLevel;
         const bool bCheckLevels = (minLevel > 0) || (maxLevel > 0);
         int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;

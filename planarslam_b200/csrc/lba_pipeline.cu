@@ -277,11 +277,8 @@ int lba_run_packed(pslam_ctx* c) {
     A.kf_edge_off = (const int32_t*)B.d_kf_eoff.p; A.kf_edge_idx = (const int32_t*)B.d_kf_eidx.p; A.lm_edge_off = (const int32_t*)B.d_lm_eoff.p;
     A.plane_edges = (const int32_t*)B.d_plane_edges.p; A.blk_ij = (const int32_t*)B.d_blk_ij.p; A.blk_term_off = (const int32_t*)B.d_blk_toff.p;
     A.terms = (const int2*)B.d_terms.p; A.hs_global = (double*)B.d_hs.p; A.flags = (uint8_t*)B.d_flags.p; A.out = (LbaOutDev*)B.d_out.p;
-    static int attr_set = 0;
-    if (attr_set < B.max_smem) {
-        PSLAM_CUDA(c, cudaFuncSetAttribute(k_local_bundle_adjustment, cudaFuncAttributeMaxDynamicSharedMemorySize, LBA_SMEM_BUDGET));
-        attr_set = LBA_SMEM_BUDGET;
-    }
+    // per device and cheap: set on every launch (contexts of one process may live on different GPUs)
+    PSLAM_CUDA(c, cudaFuncSetAttribute(k_local_bundle_adjustment, cudaFuncAttributeMaxDynamicSharedMemorySize, LBA_SMEM_BUDGET));
     PSLAM_LAUNCH(c, "local_bundle_adjustment", k_local_bundle_adjustment<<<B.n_prob, LBA_THREADS, B.max_smem, c->stream>>>(A));
     PSLAM_CUDA(c, cudaGetLastError());
     return PSLAM_OK;

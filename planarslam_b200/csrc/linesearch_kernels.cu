@@ -14,7 +14,7 @@ namespace pslam {
 
 __global__ void __launch_bounds__(32) k_line_search(int nf, const float* __restrict__ pt, const float* __restrict__ angle, const int32_t* __restrict__ octave,
                                                     const uint8_t* __restrict__ desc, const uint8_t* __restrict__ has_obs, const float* __restrict__ scale,
-                                                    int nm, const uint8_t* __restrict__ skip, const int32_t* __restrict__ level,
+                                                    int n_levels, int nm, const uint8_t* __restrict__ skip, const int32_t* __restrict__ level,
                                                     const float* __restrict__ view_cos, const float* __restrict__ proj, const uint8_t* __restrict__ mdesc,
                                                     const uint8_t* __restrict__ m_has_obs, float th, float nnratio, int32_t* __restrict__ assigned,
                                                     int32_t* __restrict__ nmatches) {
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(32) k_line_search(int nf, const float* __restr
         float r = view_cos[m] > 0.998 ? 5.0f : 8.0f;
         if (bFactor) r = __fmul_rn(r, th);
         const float x1 = proj[4 * m], y1 = proj[4 * m + 1], x2 = proj[4 * m + 2], y2 = proj[4 * m + 3];
-        const float rr = __fmul_rn(r, scale[lv]);
+        const float rr = __fmul_rn(r, scale[min(max(lv, 0), n_levels - 1)]);   // MapLine::PredictScale does not clamp and the reference reads past mvScaleFactors;
+                                                                               // the scale index is clamped here, the level gate below keeps the raw level
         const int minLevel = lv - 1, maxLevel = lv;
         const bool bCheckLevels = (minLevel > 0) || (maxLevel > 0);
         uint32_t md[8];
@@ -92,7 +93,6 @@ extern "C" int pslam_line_search_by_projection(pslam_ctx* c, int nf, const float
         return set_error(c, PSLAM_E_INVALID, "bad line-search arrays (at most 64 frame lines)");
     for (int i = 0; i < nf; ++i) assigned[i] = -1;
     if (nf == 0 || nm == 0) return 0;
-    for (int m = 0; m < nm; ++m) if (!skip[m] && (level[m] < 0 || level[m] >= n_levels)) return set_error(c, PSLAM_E_INVALID, "map line level out of range");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
     cudaStream_t st = c->stream;
     // small POD arrays: one staging allocation per call (a live tracker calls this once per frame)
@@ -105,7 +105,7 @@ extern "C" int pslam_line_search_by_projection(pslam_ctx* c, int nf, const float
     PSLAM_CUDA(c, cudaMalloc((void**)&d, off[14]));
     for (int i = 0; i < 12; ++i) if (sz[i]) { const cudaError_t e = cudaMemcpyAsync(d + off[i], src[i], sz[i], cudaMemcpyHostToDevice, st); if (e != cudaSuccess) { cudaFree(d); return check_cuda(c, e, "line search upload"); } }
     PSLAM_LAUNCH(c, "line_search", k_line_search<<<1, 32, 0, st>>>(nf, (const float*)(d + off[0]), (const float*)(d + off[1]), (const int32_t*)(d + off[2]), d + off[3],
-                 d + off[4], (const float*)(d + off[5]), nm, d + off[6], (const int32_t*)(d + off[7]), (const float*)(d + off[8]), (const float*)(d + off[9]),
+                 d + off[4], (const float*)(d + off[5]), n_levels, nm, d + off[6], (const int32_t*)(d + off[7]), (const float*)(d + off[8]), (const float*)(d + off[9]),
                  d + off[10], d + off[11], th, nnratio, (int32_t*)(d + off[12]), (int32_t*)(d + off[13])));
     int32_t n = 0;
     cudaError_t e = cudaMemcpyAsync(assigned, d + off[12], (size_t)nf * 4, cudaMemcpyDeviceToHost, st);

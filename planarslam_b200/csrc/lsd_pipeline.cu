@@ -53,9 +53,10 @@ int lsd_alloc(pslam_ctx* c) {
     g.W = lsd_cv_round(g.w * SCALE); g.H = lsd_cv_round(g.h * SCALE);
     if (g.W < 8 || g.H < 8 || g.W > 32767 || g.H > 32767) { delete Bp; return set_error(c, PSLAM_E_INVALID, "image size unsupported by the line-segment detector"); }
     g.refine = 2; g.seg_cap = LSD_SEG_CAP; g.cand_cap = LSD_SEG_CAP;
-    {   // default enumeration of the NFA validation; pslam_lsd_set_rect_enumeration overrides it
+    {   // default enumeration of the NFA validation = OpenCV 4.x rect_nfa (the variant the oracle pins to cv2 4.13); PSLAM_LSD_RECT_ENUM=published
+        // or pslam_lsd_set_rect_enumeration(ctx, 0) select the published LSD iterator
         const char* e = std::getenv("PSLAM_LSD_RECT_ENUM");
-        g.rect_enum = (e && (!std::strcmp(e, "cv4") || !std::strcmp(e, "1"))) ? 1 : 0;
+        g.rect_enum = (e && (!std::strcmp(e, "published") || !std::strcmp(e, "0"))) ? 0 : 1;
     }
     g.prec = LSD_PI * ANG_TH / 180; g.p = ANG_TH / 180; g.rho = QUANT / std::sin(g.prec);
     g.log_nt = 5 * (std::log10(double(g.W)) + std::log10(double(g.H))) / 2 + std::log10(11.0);

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(MATCH_WARPS * 32) k_hamming_knn2(const uint8_t
 }
 
 // MatchORBPoints' gate: keep query i when dist < max(2 * min_dist, 15); kept query indices in ascending order.
-__global__ void __launch_bounds__(256) k_match_gate(const int32_t* __restrict__ nq, int capq, const int32_t* __restrict__ dist,
+__global__ void __launch_bounds__(256) k_match_gate(const int32_t* __restrict__ nq, int capq, const int32_t* __restrict__ idx, const int32_t* __restrict__ dist,
                                                     int32_t* __restrict__ good, int32_t* __restrict__ n_good) {
     __shared__ int s_min, s_part[256];
     const int frame = blockIdx.x, tid = threadIdx.x;
@@ -76,19 +76,20 @@ __global__ void __launch_bounds__(256) k_match_gate(const int32_t* __restrict__ 
     if (tid == 0) s_min = 1000;
     __syncthreads();
     int m = 1000;
-    for (int i = tid; i < nQ; i += 256) m = min(m, d[2 * i]);
+    const int32_t* ix = idx + (size_t)frame * capq * 2;          // rows without a neighbour (empty train set: idx -1) take no part: BFMatcher::match returns
+    for (int i = tid; i < nQ; i += 256) if (ix[2 * i] >= 0) m = min(m, d[2 * i]);      // no DMatch for them (src/ORBmatcher.cc:1346-1366)
     atomicMin(&s_min, m);
     __syncthreads();
     const double th = fmax(2.0 * (double)s_min, 15.0);
     const int per = (nQ + 255) / 256, b0 = tid * per, b1 = min(nQ, b0 + per);
     int c = 0;
-    for (int i = b0; i < b1; ++i) c += (double)d[2 * i] < th;
+    for (int i = b0; i < b1; ++i) c += ix[2 * i] >= 0 && (double)d[2 * i] < th;
     s_part[tid] = c;
     __syncthreads();
     if (tid == 0) { int run = 0; for (int k = 0; k < 256; ++k) { const int v = s_part[k]; s_part[k] = run; run += v; } n_good[frame] = run; }
     __syncthreads();
     int pos = s_part[tid];
-    for (int i = b0; i < b1; ++i) if ((double)d[2 * i] < th) good[(size_t)frame * capq + pos++] = i;
+    for (int i = b0; i < b1; ++i) if (ix[2 * i] >= 0 && (double)d[2 * i] < th) good[(size_t)frame * capq + pos++] = i;
 }
 
 }  // namespace pslam
@@ -105,7 +106,7 @@ int pslam_hamming_knn2_batch_dev(pslam_ctx* c, const uint8_t* d_q, const int32_t
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
     PSLAM_LAUNCH(c, "hamming_knn2", k_hamming_knn2<<<dim3((capq + MATCH_WARPS - 1) / MATCH_WARPS, nframes), MATCH_WARPS * 32, 0, c->stream>>>(
                      d_q, d_nq, capq, d_t, d_nt, capt, d_idx, d_dist));
-    if (d_good && d_ngood) PSLAM_LAUNCH(c, "match_gate", k_match_gate<<<nframes, 256, 0, c->stream>>>(d_nq, capq, d_dist, d_good, d_ngood));
+    if (d_good && d_ngood) PSLAM_LAUNCH(c, "match_gate", k_match_gate<<<nframes, 256, 0, c->stream>>>(d_nq, capq, d_idx, d_dist, d_good, d_ngood));
     PSLAM_CUDA(c, cudaGetLastError());
     return PSLAM_OK;
 }

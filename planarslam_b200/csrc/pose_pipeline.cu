@@ -16,7 +16,7 @@ struct PoseBuffers {
     PoseHeaderDev* d_hdr = nullptr; PoseEdgeDev* d_edges = nullptr; double* d_err = nullptr; uint8_t* d_level = nullptr;
     uint8_t* d_flags[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     PoseOutDev* d_out = nullptr;
-    size_t cap_prob = 0, cap_edges = 0, cap_flags[5] = {0, 0, 0, 0, 0};
+    size_t cap_prob = 0, cap_out = 0, cap_edges = 0, cap_level = 0, cap_err = 0, cap_flags[5] = {0, 0, 0, 0, 0};   // one capacity per buffer (elements)
     int n_prob = 0;
     int tot_flags[5] = {0, 0, 0, 0, 0};
     std::vector<PoseOutDev> h_out;
@@ -124,14 +124,11 @@ int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const
     B.n_prob = n;
     for (int k = 0; k < 5; ++k) B.tot_flags[k] = off[k];
     int rc;
-    size_t cap_out = B.cap_prob;
     if ((rc = grow(c, &B.d_hdr, &B.cap_prob, (size_t)n)) != PSLAM_OK) return rc;
-    if ((rc = grow(c, &B.d_out, &cap_out, (size_t)n)) != PSLAM_OK) return rc;
-    size_t ce = B.cap_edges, cl = B.cap_edges, cr = B.cap_edges * 3;
+    if ((rc = grow(c, &B.d_out, &B.cap_out, (size_t)n)) != PSLAM_OK) return rc;
     if ((rc = grow(c, &B.d_edges, &B.cap_edges, B.h_edges.size())) != PSLAM_OK) return rc;
-    if ((rc = grow(c, &B.d_level, &cl, B.h_edges.size())) != PSLAM_OK) return rc;
-    if ((rc = grow(c, &B.d_err, &cr, B.h_edges.size() * 3)) != PSLAM_OK) return rc;
-    (void)ce;
+    if ((rc = grow(c, &B.d_level, &B.cap_level, B.h_edges.size())) != PSLAM_OK) return rc;
+    if ((rc = grow(c, &B.d_err, &B.cap_err, B.h_edges.size() * 3)) != PSLAM_OK) return rc;
     for (int k = 0; k < 5; ++k) if ((rc = grow(c, &B.d_flags[k], &B.cap_flags[k], (size_t)std::max(off[k], 1))) != PSLAM_OK) return rc;
     cudaStream_t st = c->stream;
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_hdr, B.h_hdr.data(), n * sizeof(PoseHeaderDev), cudaMemcpyHostToDevice, st));

@@ -23,7 +23,7 @@ class LineSegment:
         self.ctx = ctx or Context(width, height, max_batch, device)
 
     def set_rect_enumeration(self, mode: int):
-        """Pixel enumeration of the NFA validation: 0 the published LSD rectangle iterator (default), 1 OpenCV 4.x's rect_nfa
+        """Pixel enumeration of the NFA validation: 1 OpenCV 4.x's rect_nfa (default), 0 the published LSD rectangle iterator
         (include/pslam_abi.h pslam_lsd_set_rect_enumeration)."""
         self.ctx.check(self.ctx.L.pslam_lsd_set_rect_enumeration(self.ctx.h, int(mode)))
 

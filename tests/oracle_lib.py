@@ -277,9 +277,10 @@ KEYLINE_DTYPE = np.dtype([("angle", "<f4"), ("class_id", "<i4"), ("octave", "<i4
 assert KEYLINE_DTYPE.itemsize == 68
 
 
-def lsd_detect(gray: np.ndarray, refine: int = 2, cap: int = 16384, rect_enum: int = 0):
+def lsd_detect(gray: np.ndarray, refine: int = 2, cap: int = 16384, rect_enum: int = 1):
     """Oracle cv::LineSegmentDetector::detect. Returns (segments float32 [n][4], width, prec, nfa float64 [n]).
-    rect_enum: NFA pixel enumeration - 0 the published LSD iterator (the CUDA path), 1 cv2 4.13's (oracle/lsd.cc rect_nfa)."""
+    rect_enum: NFA pixel enumeration - 1 cv2 4.13's with the deterministic sincos (the CUDA path's default, oracle/lsd.cc rect_nfa),
+    0 the published LSD iterator, 3 cv2 4.13's with libm axes (= cv2 bit for bit)."""
     L = lib()
     L.orc_lsd_detect_enum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     g = np.ascontiguousarray(gray, np.uint8)
@@ -306,7 +307,7 @@ def lsd_stages(gray: np.ndarray, refine: int = 2):
     return out
 
 
-def extract_line_segments(gray: np.ndarray, max_lines: int = 40, rect_enum: int = 0):
+def extract_line_segments(gray: np.ndarray, max_lines: int = 40, rect_enum: int = 1):
     """Oracle LineSegment::ExtractLineSegment without LBD. Returns (KeyLine structured array, line functions [n][3])."""
     L = lib()
     L.orc_extract_line_segments_enum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]

@@ -26,7 +26,6 @@ def test_oracle_matches_numpy():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="k_stereo_from_rgbd was written after the round-1 GPU budget was spent. Expected to pass; non-strict until it has run on a B200 once.")
 def test_stereo_from_rgbd_gpu_matches_oracle():
     from planarslam_b200._lib import Context
     from planarslam_b200.frame import ComputeStereoFromRGBD

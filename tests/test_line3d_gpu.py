@@ -11,8 +11,6 @@ from planarslam_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="k_lines3d was written after the round-1 GPU budget was spent: host-checked only (tests/test_line3d_host.py). "
-                                        "Expected to pass; kept non-strict until it has run on a B200 once.")
 def test_lines3d_match_oracle():
     from planarslam_b200._lib import Context
     from planarslam_b200.lines import KEYLINE_DTYPE, isLineGood

@@ -2,7 +2,7 @@
 with g++ and compared with the oracle (oracle/line3d.cc, an independent statement of Frame::isLineGood with std::vector sets, the
 generic Jacobi SVD and libm hypot).  The body is plain IEEE double arithmetic, nvcc builds it with --fmad=false, so the host
 result is what the device computes; the kernel around it only indexes frames.  No GPU time was left in round 1 to run the kernel
-itself (tests/test_line3d_gpu.py is non-strict xfail until it has)."""
+itself (GPU run: tests/test_line3d_gpu.py)."""
 import ctypes as C
 import os
 import subprocess

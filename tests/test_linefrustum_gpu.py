@@ -8,8 +8,6 @@ from planarslam_b200.synth_lines import make_line_frustum
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="k_lines_in_frustum was written after the round-1 GPU budget was spent: host-checked only "
-                                        "(tests/test_linefrustum_host.py). Expected to pass; kept non-strict until it has run on a B200 once.")
 def test_lines_in_frustum_match_oracle():
     from planarslam_b200._lib import Context
     from planarslam_b200.matcher import lines_in_frustum

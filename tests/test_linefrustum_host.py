@@ -1,6 +1,6 @@
 """CPU: Frame::isInFrustum(MapLine*) - oracle (oracle/linesearch.cc lines_in_frustum) vs an independent float64 numpy statement of the
 geometry, and planarslam_b200/csrc/linefrustum_body.h (the per-line code of k_lines_in_frustum) compiled for the host vs the oracle
-(bit-exact).  The kernel has not run on a B200 yet (GPU test non-strict xfail)."""
+(bit-exact).  GPU run: tests/test_linefrustum_gpu.py."""
 import ctypes as C
 import os
 import subprocess

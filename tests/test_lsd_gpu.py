@@ -75,23 +75,21 @@ def test_lsd_flat_image_and_box():
     assert len(segs) == 4 and np.array_equal(segs, osegs)
 
 
-@pytest.mark.xfail(strict=False, reason="OpenCV 4.x rect_nfa enumeration on the device: written after the round-1 GPU budget was spent; host-checked only "
-                                        "(tests/test_lsd_rectenum_host.py).  Expected to pass; kept non-strict until it has run on a B200 once.")
-def test_lsd_cv4_enumeration_matches_oracle():
-    """pslam_lsd_set_rect_enumeration(ctx, 1): the NFA validation counts the pixels cv2 4.x counts.  Oracle variant 1 (same
-    enumeration, same deterministic sincos) is the bit-exact target; variant 3 of the oracle is cv2 4.13 itself."""
+def test_lsd_published_enumeration_matches_oracle():
+    """pslam_lsd_set_rect_enumeration(ctx, 0): the published LSD rectangle iterator (non-default) against oracle variant 0; the default
+    (1 = cv2 4.x rect_nfa, oracle variant 1, same deterministic sincos) is what every other test in this file runs."""
     from planarslam_b200.lines import LineSegment
     g = np.concatenate([_frames(3), synth.polygon_image(11)[None]])
     ls = LineSegment(max_batch=4)
-    ls.set_rect_enumeration(1)
+    ls.set_rect_enumeration(0)
     res = ls.detect(g, 2)
     for f in range(4):
         segs, width, prec, nfa = res[f]
-        osegs, owidth, oprec, onfa = oracle_lib.lsd_detect(g[f], 2, rect_enum=1)
+        osegs, owidth, oprec, onfa = oracle_lib.lsd_detect(g[f], 2, rect_enum=0)
         assert len(segs) == len(osegs) > 50, (f, len(segs), len(osegs))
         assert np.array_equal(segs, osegs), f
         assert np.array_equal(width, owidth) and np.array_equal(prec, oprec), f
         assert np.allclose(nfa, onfa, rtol=1e-9, atol=1e-9), f
-    ls.set_rect_enumeration(0)
-    segs0 = ls.detect(g[:1], 2)[0][0]
-    assert np.array_equal(segs0, oracle_lib.lsd_detect(g[0], 2)[0])
+    ls.set_rect_enumeration(1)
+    segs1 = ls.detect(g[:1], 2)[0][0]
+    assert np.array_equal(segs1, oracle_lib.lsd_detect(g[0], 2, rect_enum=1)[0])

@@ -9,8 +9,6 @@ from planarslam_b200.synth_manhattan import make_manhattan
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="k_track_manhattan was written after the round-1 GPU budget was spent: host-checked only "
-                                        "(tests/test_manhattan_host.py). Expected to pass; kept non-strict until it has run on a B200 once.")
 def test_track_manhattan_matches_oracle():
     from planarslam_b200._lib import Context
     from planarslam_b200.manhattan import TrackManhattanFrame

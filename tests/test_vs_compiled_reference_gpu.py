@@ -53,8 +53,6 @@ def test_peac_cuda_identical_to_reference_code():
 
 
 @pytest.mark.skipif(ref_lib.peac_lib() is None, reason="oracle/_ref/libpeac_ref.so not present")
-@pytest.mark.xfail(strict=False, reason="scene family added after the round-1 GPU budget was spent (up to 12 planes, final merges): the CUDA path has only run "
-                                        "the room scenes on a B200 so far. Expected to pass.")
 def test_peac_cuda_identical_to_reference_code_many_planes():
     _peac_vs_reference(np.stack([synth.piecewise_planar_depth(2, n_rect=8), synth.piecewise_planar_depth(5, n_rect=11, curved=False),
                                  synth.piecewise_planar_depth(11, n_rect=17, curved=False)]), 20)

@@ -26,6 +26,12 @@ for seed in (0, 7):
             length = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
             segs = segs[np.argsort(-length, kind="stable")[:40]]
         lsd[f"seed{seed}_refine{refine}"] = segs.astype(np.float32)
+# the 40 longest LSD_REFINE_ADV segments (what ExtractLineSegment keeps) of the 17 LSD test frames
+adv_frames = [synth.render_frame(seed=s, frame=3 * s)[0] for s in range(16)] + [synth.polygon_image(11)]
+for k, g in enumerate(adv_frames):
+    segs = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(g)[0].reshape(-1, 4)
+    length = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
+    lsd[f"adv_top40_{k}"] = segs[np.argsort(-length, kind="stable")[:40]].astype(np.float32)
 np.savez_compressed(os.path.join(out, "lsd_cv2_4_13.npz"), **lsd)
 
 # ---- 8-bit primitives on a seeded random image ----
