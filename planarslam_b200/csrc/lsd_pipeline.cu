@@ -157,6 +157,8 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     PSLAM_LAUNCH(c, "lsd_blur_scale", k_lsd_blur_scale<<<gb, 256, 0, st>>>(g, d_gray, B.d_ix, B.d_ax, B.d_iy, B.d_ay, B.d_scaled));
     const dim3 gg((g.W + 63) / 64, (g.H + 3) / 4, nframes);
     PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient<<<gg, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_rec, B.d_smax));
+    PSLAM_CUDA(c, cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, LSD_ORDER_SMEM));
+    PSLAM_LAUNCH(c, "lsd_order", k_lsd_order<<<nframes, LSD_ORDER_THREADS, LSD_ORDER_SMEM, st>>>(g, B.d_scaled, B.d_smax, B.d_order, B.d_norder));
     PSLAM_CUDA(c, cudaMemsetAsync(B.d_used, 0, (size_t)nframes * npx, st));
     PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<<<nframes, 32, 0, st>>>(g, nframes, B.d_rec, B.d_smax, B.d_used, B.d_reg, B.d_order, B.d_norder, B.d_cands, B.d_ncand,
                                                                         B.d_status));

@@ -136,7 +136,8 @@ def test_pose_and_translation_optimization_cuda_vs_reference():
 def test_local_bundle_adjustment_cuda_vs_reference():
     from planarslam_b200.lba import LocalBundleAdjuster
     ba = LocalBundleAdjuster()
-    small = dict(n_kf=6, n_fixed=2, n_points=200, n_pt_obs=600, n_lines=16, n_line_obs=24, n_plane_obs=(6, 2, 2), line_kf_quirk=True)
+    from test_oracle_lba_ref import SMALL
+    small = dict(SMALL, line_kf_quirk=True)            # the cases of tests/test_oracle_lba_ref.py (oracle == reference there, on the CPU)
     cases = [dict(seed=s, **small) for s in (1, 10, 11)]
     cases += [dict(seed=2, n_kf=8, n_points=300, n_pt_obs=900, n_lines=0, n_line_obs=0, n_plane_obs=(0, 0, 0))]
     hard = [dict(seed=20 + s, **small, line_norm3=False, outlier_frac=0.2, plane_outlier_frac=0.25) for s in range(2)]
