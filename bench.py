@@ -126,79 +126,202 @@ class ClockSampler(threading.Thread):
 
 
 CPU_UNITS = {}
+CPU_SAMPLE_FRAMES = 16          # distinct rendered frames / pose problems the CPU arm cycles through
 
 
-def cpu_oracle_fps(gray, depth, seconds=12.0, threads=1):
-    """Frames/s of the CPU oracle (oracle/, a restatement of the reference compiled -O2, scalar) on `threads`
-    host threads over a bounded sample of the same frames."""
+def _cpu_stage_fns(stages):
+    """The per-frame CPU path, one callable per stage (called with a frame index), and what runs behind each.  ORB, PEAC and PoseOptimization are the
+    reference's OWN code compiled unmodified in the build container (oracle/_ref/fast: src/ORBextractor.cc, src/PlaneExtractor.cpp + include/peac,
+    src/Optimizer.cc + Thirdparty/g2o; -O3 -march=x86-64-v3, oracle/Makefile `fast`) where those libraries are present, else the oracle port; LSD is
+    upstream OpenCV's own LineSegmentDetector (cv2, the implementation behind the reference's LSDDetector call) when cv2 imports, else the oracle port."""
     import oracle_lib
-    from concurrent.futures import ThreadPoolExecutor
-    oracle_lib.lib()
-    n = len(gray)
-
-    from planarslam_b200 import synth_pose
-    probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(min(n, 4))]
-
-    # ORB and PEAC: the reference's OWN code where oracle/_ref holds it (src/ORBextractor.cc, src/PlaneExtractor.cpp + include/peac compiled
-    # unmodified in the build container, oracle/ref/); everything else - and both of them when the libraries are absent - is the oracle port
     import ref_lib
+    from planarslam_b200 import synth_pose
+    oracle_lib.lib()
+    d = np.load(os.environ["PSLAM_CPU_FRAMES"])
+    gray, depth = d["gray"], d["depth"]
+    n = len(gray)
+    probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(n)]
     use_ref = os.environ.get("PSLAM_CPU_REF", "1") != "0"
     ref_orb = ref_lib.orb_lib() if use_ref else None
     ref_peac = ref_lib.peac_lib() if use_ref else None
-    CPU_UNITS.clear()
-    CPU_UNITS.update({"orb": "reference (oracle/_ref/liborb_ref.so)" if ref_orb else "port", "peac": "reference (oracle/_ref/libpeac_ref.so)" if ref_peac else "port",
-                      "lsd": "port", "pose": "port"})
+    ref_match = ref_lib.match_lib() if use_ref else None
+    lsd_cv = None
+    if use_ref:
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            lsd_cv = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV)
+        except Exception:
+            lsd_cv = None
 
-    def work(i):
-        if "orb" in STAGES:
-            if ref_orb:
-                ref_lib.ref_orb_extract(gray[i % n], monotonic_alloc=False)      # ctypes releases the GIL inside the C calls
-            else:
-                oracle_lib.orb_extract(gray[i % n])
-        if "lsd" in STAGES:
-            oracle_lib.extract_line_segments(gray[i % n], 40)
-        if "peac" in STAGES:
-            if ref_peac:
-                ref_lib.ref_peac_time(depth[i % n])
-            else:
-                oracle_lib.PeacOracle(depth[i % n])
-        if "pose" in STAGES:
-            oracle_lib.pose_optimization(probs[i % len(probs)])
-        return 1
+    def f_lsd(i):
+        if lsd_cv is None:
+            return oracle_lib.extract_line_segments(gray[i % n], 40)
+        segs = lsd_cv.detect(gray[i % n])[0]                       # + ExtractLineSegment's keep-40 (src/LSDextractor.cpp:18-26)
+        if segs is not None:
+            segs = segs.reshape(-1, 4)
+            segs[np.argsort(-np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1]), kind="stable")[:40]]
 
-    work(0)                                      # warm
-    t0 = time.perf_counter()
-    done = 0
-    with ThreadPoolExecutor(threads) as ex:
-        while time.perf_counter() - t0 < seconds:
-            done += sum(ex.map(work, range(done, done + threads)))
-    dt = time.perf_counter() - t0
-    return done / dt, done
+    fns = {"orb": (lambda i: ref_lib.ref_orb_extract(gray[i % n], monotonic_alloc=False)) if ref_orb else (lambda i: oracle_lib.orb_extract(gray[i % n])),
+           "lsd": f_lsd,
+           "peac": (lambda i: ref_lib.ref_peac_time(depth[i % n])) if ref_peac else (lambda i: oracle_lib.PeacOracle(depth[i % n])),
+           "pose": (lambda i: ref_lib.ref_full_pose_optimization(probs[i % n], False)) if ref_match else (lambda i: oracle_lib.pose_optimization(probs[i % n]))}
+    units = {"orb": "reference src/ORBextractor.cc (OpenCV primitives inside it: scalar restatements)" if ref_orb else "port",
+             "lsd": "upstream cv2 LineSegmentDetector (1 thread)" if lsd_cv is not None else "port",
+             "peac": "reference src/PlaneExtractor.cpp + include/peac" if ref_peac else "port",
+             "pose": "reference src/Optimizer.cc PoseOptimization(Frame*) + Thirdparty/g2o" if ref_match else "port"}
+    return {k: v for k, v in fns.items() if k in stages}, {k: v for k, v in units.items() if k in stages}
+
+
+def cpu_worker_main(spec):
+    """Child process of the CPU arm (python bench.py --cpu-worker '<json>'): pinned to one core (or three for the reference's thread-per-extractor
+    mode), prints 'ready <units json>', then for every line 'go <first frame> <count>' on stdin processes the frames and prints 'done <seconds>'."""
+    os.environ["PSLAM_REF_VARIANT"] = "fast"
+    cores = spec["cores"]
+    try:
+        os.sched_setaffinity(0, set(cores))
+    except Exception:
+        pass
+    fns, units = _cpu_stage_fns(spec["stages"])
+    par = [k for k in ("orb", "lsd", "peac") if k in fns]
+    pool = None
+    if spec["mode"] == "ref3":
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(3)
+
+    def frame(i):
+        if pool is not None:                       # Frame::Frame: three std::threads (ExtractORB, ExtractLSD, ComputePlanes), join, src/Frame.cc:90-95
+            for f in [pool.submit(fns[k], i) for k in par]:
+                f.result()
+        else:
+            for k in par:
+                fns[k](i)
+        if "pose" in fns:
+            fns["pose"](i)
+
+    frame(spec["rank"])                            # warm (page in the libraries, the frames)
+    sys.stdout.write("ready " + json.dumps(units) + "\n")
+    sys.stdout.flush()
+    for line in sys.stdin:
+        tok = line.split()
+        if not tok or tok[0] != "go":
+            break
+        first, count = int(tok[1]), int(tok[2])
+        t0 = time.perf_counter()
+        for i in range(first, first + count):
+            frame(i)
+        sys.stdout.write(f"done {time.perf_counter() - t0:.6f}\n")
+        sys.stdout.flush()
+
+
+class CpuArm:
+    """Process pool of pinned CPU workers (one Python process per core, or per three cores in 'ref3' mode); a step = every worker processes
+    `per_worker` frames between a common start signal and the last 'done'."""
+
+    def __init__(self, gray, depth, mode, n_workers, stages):
+        import subprocess
+        import tempfile
+        self.mode, self.n = mode, n_workers
+        self.tmp = tempfile.NamedTemporaryFile(suffix=".npz", delete=False)
+        np.savez(self.tmp, gray=gray, depth=depth)
+        self.tmp.close()
+        avail = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+        width = 3 if mode == "ref3" else 1
+        env = dict(os.environ, PSLAM_CPU_FRAMES=self.tmp.name, PSLAM_REF_VARIANT="fast", OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1",
+                   CUDA_VISIBLE_DEVICES="")
+        self.procs = []
+        for r in range(n_workers):
+            spec = {"mode": mode, "rank": r, "stages": stages, "cores": [avail[(r * width + k) % len(avail)] for k in range(width)]}
+            self.procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", json.dumps(spec)], stdin=subprocess.PIPE,
+                                               stdout=subprocess.PIPE, text=True, env=env))
+        self.units = {}
+        for p in self.procs:
+            line = p.stdout.readline()
+            if not line.startswith("ready"):
+                raise RuntimeError("CPU worker failed to start: " + line)
+            self.units = json.loads(line[6:])
+
+    def step(self, per_worker):
+        t0 = time.perf_counter()
+        for r, p in enumerate(self.procs):
+            p.stdin.write(f"go {r * per_worker} {per_worker}\n")
+            p.stdin.flush()
+        for p in self.procs:
+            line = p.stdout.readline()
+            if not line.startswith("done"):
+                raise RuntimeError("CPU worker died: " + line)
+        return time.perf_counter() - t0, per_worker * self.n
+
+    def close(self):
+        for p in self.procs:
+            try:
+                p.stdin.close()
+                p.wait(timeout=10)
+            except Exception:
+                p.kill()
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+
+
+def cpu_modes(gray, depth, seconds=8.0):
+    """BASELINE.md section 3's three threading modes of the CPU path on this box: one thread; the reference's own layout (three extractor threads per
+    frame, src/Frame.cc:90-95, one frame at a time per process) replicated over cores // 3 processes; one frame per core on all cores."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    out = {}
+    for name, mode, nw in (("single_thread", "seq", 1), ("three_threads_per_frame", "ref3", max(1, cores // 3)), ("frame_parallel_all_cores", "seq", cores)):
+        arm = CpuArm(gray, depth, mode, nw, STAGES)
+        try:
+            arm.step(1)
+            t, n = 0.0, 0
+            while t < seconds:
+                dt, k = arm.step(2)
+                t += dt
+                n += k
+            out[name] = {"frames_per_sec": round(n / t, 3), "processes": nw, "threads": nw * (3 if mode == "ref3" else 1), "frames": n, "seconds": round(t, 2)}
+            CPU_UNITS.clear()
+            CPU_UNITS.update(arm.units)
+        finally:
+            arm.close()
+    out["host_cores"] = cores
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path cannot be built here (OpenCV/Eigen/PCL absent),
-    so this arm times the oracle port on all host cores.  Rank 0 only."""
+    """--impl reference: the reference's CPU path on all host cores of this box (rank 0 only): one pinned worker process per core, each running whole
+    frames through ORB + LSD + PEAC + PoseOptimization (see _cpu_stage_fns for what code runs behind each stage).  A step = 4 frames per worker; ms_per_step
+    is that step's measured wall time, value = frames of the timed steps / their summed time."""
     if rank != 0:
         return
     global SUB_BATCH, FRAMES_PER_STEP
     if SUB_BATCH <= 0:
-        SUB_BATCH = DEFAULT_WAVE                 # no GPU is touched in this arm: the same config as the default GPU arm
-    FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
-    gray, depth = make_frames(4)
-    cores = os.cpu_count() or 1
-    vals = []
-    for _ in range(max(args.warmup, 0) + max(args.steps, 1)):
-        fps, n = cpu_oracle_fps(gray, depth, seconds=6.0, threads=cores)
-        vals.append(fps)
-    v = float(np.mean(vals[max(args.warmup, 0):]))
+        SUB_BATCH = DEFAULT_WAVE
+    gray, depth = make_frames(CPU_SAMPLE_FRAMES)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_worker = int(os.environ.get("PSLAM_CPU_FRAMES_PER_WORKER", "4"))
+    arm = CpuArm(gray, depth, "seq", cores, STAGES)
+    try:
+        for _ in range(max(args.warmup, 0)):
+            arm.step(per_worker)
+        tot_t, tot_n = 0.0, 0
+        for _ in range(max(args.steps, 1)):
+            dt, n = arm.step(per_worker)
+            tot_t += dt
+            tot_n += n
+        units = dict(arm.units)
+    finally:
+        arm.close()
+    FRAMES_PER_STEP = per_worker * cores
+    v = tot_n / tot_t
+    cfg = workload_config()
+    cfg["reference_step"] = f"{per_worker} frames on each of {cores} pinned worker processes ({FRAMES_PER_STEP} frames per step, {CPU_SAMPLE_FRAMES} distinct)"
     line = {"impl": "reference", "metric": "rgbd_frames_per_sec_640x480", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * FRAMES_PER_STEP / v, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
-            "config": workload_config(),
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "units": {k: CPU_UNITS.get(k) for k in STAGES},
-                             "sample": f"{' + '.join(STAGES)} on {len(gray)} frames looped for 6 s per step, {cores} threads; ORB and PEAC are the reference's own "
-                                       f"code where oracle/_ref holds it (see units), LSD and pose the oracle port"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "units": units,
+                             "sample": f"{' + '.join(STAGES)}: {tot_n} frames in {tot_t:.1f} s, one pinned process per core ({cores}), -O3 -march=x86-64-v3"},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -217,7 +340,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-worker", default=None, help=argparse.SUPPRESS)       # internal: child process of the CPU arm
     args = ap.parse_args()
+    if args.cpu_worker:
+        cpu_worker_main(json.loads(args.cpu_worker))
+        return
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -504,16 +631,18 @@ def main():
             aux["new_kernels"] = {"error": repr(ex)}
 
     if rank == 0:
-        cpu_fps, cpu_n = cpu_oracle_fps(gray, depth, seconds=12.0, threads=1)
+        modes = cpu_modes(gray[:CPU_SAMPLE_FRAMES], depth[:CPU_SAMPLE_FRAMES], seconds=float(os.environ.get("PSLAM_CPU_SECONDS", "8")))
+        best = modes["frame_parallel_all_cores"]
         line = {"metric": "rgbd_frames_per_sec_640x480", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(),
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "roofline": roofline,
-                "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port", "units": {k: CPU_UNITS.get(k) for k in STAGES},
-                                 "sample": f"{' + '.join(STAGES)}, {cpu_n} frames in ~12 s, -O2 scalar; ORB and PEAC are the reference's own code where oracle/_ref "
-                                           f"holds it (see units), LSD and pose the oracle port"},
+                "cpu_baseline": {"value": best["frames_per_sec"], "unit": "frames/s", "cores": best["threads"], "kind": "reference",
+                                 "units": {k: CPU_UNITS.get(k) for k in STAGES}, "modes": modes,
+                                 "sample": f"{' + '.join(STAGES)}: {best['frames']} frames in {best['seconds']} s, one pinned process per host core "
+                                           f"({modes['host_cores']}), -O3 -march=x86-64-v3 (oracle/Makefile fast); modes = BASELINE.md section 3"},
                 "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP,
                 "keylines_per_frame": float(d_nkl.sum().item()) / FRAMES_PER_STEP if "lsd" in STAGES else None, "aux": aux}
         print(json.dumps(line))

@@ -130,6 +130,12 @@ void fast_detect(const Img8& sub, int thr, std::vector<FastKp>& out) {
     std::vector<int> sc((size_t)w * h, 0);
     for (int y = 3; y < h - 3; ++y)
         for (int x = 3; x < w - 3; ++x) {
+            // exact early-out: any arc of 9 of the 16 circle pixels holds at least two of the four compass points, so a corner at threshold
+            // thr needs two compass points darker than v - thr or two brighter than v + thr (the high-speed test of the published FAST)
+            const int v = sub.at(y, x);
+            int nd = 0, nb = 0;
+            for (int k = 0; k < 16; k += 4) { const int dv = v - sub.at(y + kCircle[k][1], x + kCircle[k][0]); nd += dv > thr; nb += -dv > thr; }
+            if (nd < 2 && nb < 2) continue;
             int s = fast_score_9_16(sub, x, y);
             sc[(size_t)y * w + x] = (s >= thr) ? s : 0;
         }

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+_PATH = os.path.join(ROOT, "oracle", "_build", "liboracle_fast.so" if os.environ.get("PSLAM_REF_VARIANT") == "fast" else "liboracle.so")   # fast: CPU-baseline build only
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
                            ("octave", "<i4"), ("class_id", "<i4")])
 _lib = None
@@ -18,7 +18,7 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(_PATH):
-            subprocess.run(["make"], cwd=os.path.join(ROOT, "oracle"), check=True, stdout=subprocess.DEVNULL)
+            subprocess.run(["make"] + (["fast"] if _PATH.endswith("_fast.so") else []), cwd=os.path.join(ROOT, "oracle"), check=True, stdout=subprocess.DEVNULL)
         L = C.CDLL(_PATH)
         vp, i = C.c_void_p, C.c_int
         L.orc_orb_create.restype = vp

@@ -7,7 +7,8 @@ import subprocess
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref", *([os.environ["PSLAM_REF_VARIANT"]] if os.environ.get("PSLAM_REF_VARIANT") else []))   # PSLAM_REF_VARIANT=fast:
+                                                                  # the -O3 build bench.py's CPU arm times (oracle/Makefile `fast`); parity tests use the default
 
 
 def _load(name):
