@@ -44,7 +44,8 @@ SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "4"))         # ORB / PEAC / po
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
 LSD_SUBS = int(os.environ.get("PSLAM_LSD_SUBS", "3"))          # LSD calls per step: 4 x 1776 = 3 x 2368 frames, i.e. every LSD call is exactly one wave of its
                                                                # one-warp-per-frame kernel (16 resident CTAs per SM x 148), every PEAC call one wave of the clustering kernel (12 x 148)
-DISTINCT_FRAMES = 16      # rendered once (CPU, ~0.4 s each) and tiled with a per-copy intensity offset
+DISTINCT_FRAMES = int(os.environ.get("PSLAM_DISTINCT_FRAMES", "256"))   # distinct frames of the replayed sequence (rendered on the host cores by a process pool)
+                                                                         # and distinct pose problems; the step's frames cycle through them
 
 # Algorithmic bytes per 640x480 frame of each kernel family (restated in DESIGN.md §kernels)
 ALGO_BYTES = {
@@ -80,9 +81,10 @@ def _peaks():
         return 6650.0, "fallback"
 
 
-def make_frames(n_distinct=DISTINCT_FRAMES):
+def make_frames(n_distinct=DISTINCT_FRAMES, world=1):
     from planarslam_b200 import synth
-    g, d = synth.render_sequence(seed=2, n=n_distinct, width=W, height=H)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    g, d = synth.render_sequence_parallel(seed=2, n=n_distinct, width=W, height=H, workers=max(1, min(64, cores // max(world, 1))))
     return g, d
 
 
@@ -330,7 +332,7 @@ def workload_config():
     return {"workload": "640x480 synthetic RGB-D sequence: ORB (1000 feats, 8 levels) + LSD line segments (REFINE_ADV, 40 longest -> KeyLines + "
                         "line functions; LBD descriptors not built) + PEAC planes + PoseOptimization (1000 point + 40 line (80 edges) + 6 plane "
                         "edges per frame)",
-            "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "l2": "inputs_larger_than_l2",
+            "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "distinct_frames": DISTINCT_FRAMES, "l2": "inputs_larger_than_l2",
             "stages": STAGES, "streams": len(STAGES)}
 
 
@@ -372,15 +374,15 @@ def main():
     FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
     assert LSD_SUBS <= SUBS_PER_STEP
 
-    gray, depth = make_frames()
-    # the step's frames are built once, directly in page-locked host memory (the buffers the end-to-end leg hands to the ABI): 16 rendered
-    # frames tiled with a small intensity offset (0..21 grey levels) so that every copy keeps the full content of a rendered frame
+    gray, depth = make_frames(world=world)
+    # the step's frames are built once, directly in page-locked host memory (the buffers the end-to-end leg hands to the ABI): the DISTINCT_FRAMES
+    # frames of the rendered sequence, repeated in order until the step is full
     h_gray = torch.empty((FRAMES_PER_STEP, H, W), dtype=torch.uint8).pin_memory()
     h_depth = torch.empty((FRAMES_PER_STEP, H, W), dtype=torch.int16).pin_memory()      # uint16 bits
     hg, hd = h_gray.numpy(), h_depth.numpy()
     for o in range(0, FRAMES_PER_STEP, DISTINCT_FRAMES):
         n = min(DISTINCT_FRAMES, FRAMES_PER_STEP - o)
-        hg[o:o + n] = np.clip(gray[:n].astype(np.int16) + 3 * ((o // DISTINCT_FRAMES) % 8), 0, 255).astype(np.uint8)
+        hg[o:o + n] = gray[:n]
         hd[o:o + n] = depth[:n].view(np.int16)
     dev = torch.device("cuda", local_rank)
     main = torch.cuda.current_stream(dev)
@@ -436,8 +438,8 @@ def main():
     h_lf = pinned((FRAMES_PER_STEP, MAX_LINES, 3), np.float64)
     h_nkl = pinned((FRAMES_PER_STEP,), np.int32)
     # pose problems: one per frame of a sub-batch (the correspondences a tracker would hand over), packed + uploaded once
-    base_probs = [synth_pose.make_pose_problem(11, frame=k) for k in range(16)]
-    probs = [base_probs[k % 16] for k in range(SUB_BATCH)]
+    base_probs = [synth_pose.make_pose_problem(11 + k // 64, frame=k % 64) for k in range(DISTINCT_FRAMES)]
+    probs = [base_probs[k % DISTINCT_FRAMES] for k in range(SUB_BATCH)]
     opt = Optimizer(c_pose)
     opt.pack(probs)
     pose_h2d = sum(sum(p[k].nbytes for k in ("Xw", "obs", "inv_sigma2", "line_Xw", "line_obs", "plane_meas", "plane_map", "par_meas",

@@ -42,6 +42,7 @@ static float host_fast_atan2_deg(float y, float x) {                            
 }
 
 static const int LSD_SEG_CAP = 4096;
+#define LSD_REGIONS_OCC 16          // resident region-growing warps per SM the default build of k_lsd_regions targets
 
 int lsd_alloc(pslam_ctx* c) {
     if (c->lsd) return PSLAM_OK;
@@ -160,8 +161,13 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, LSD_ORDER_SMEM));
     PSLAM_LAUNCH(c, "lsd_order", k_lsd_order<<<nframes, LSD_ORDER_THREADS, LSD_ORDER_SMEM, st>>>(g, B.d_scaled, B.d_smax, B.d_order, B.d_norder));
     PSLAM_CUDA(c, cudaMemsetAsync(B.d_used, 0, (size_t)nframes * npx, st));
-    PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<<<nframes, 32, 0, st>>>(g, nframes, B.d_rec, B.d_smax, B.d_used, B.d_reg, B.d_order, B.d_norder, B.d_cands, B.d_ncand,
-                                                                        B.d_status));
+    {
+        static const int occ = [] { const char* e = std::getenv("PSLAM_LSD_OCC"); const int v = e ? std::atoi(e) : LSD_REGIONS_OCC; return v == 16 || v == 20 || v == 24 || v == 32 ? v : LSD_REGIONS_OCC; }();
+#define LSD_REGIONS_LAUNCH(V) PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<V><<<nframes, 32, 0, st>>>(g, nframes, B.d_rec, B.d_smax, B.d_used, B.d_reg, B.d_order, B.d_norder, \
+                                                                                                B.d_cands, B.d_ncand, B.d_status))
+        if (occ == 16) LSD_REGIONS_LAUNCH(16); else if (occ == 20) LSD_REGIONS_LAUNCH(20); else if (occ == 24) LSD_REGIONS_LAUNCH(24); else LSD_REGIONS_LAUNCH(32);
+#undef LSD_REGIONS_LAUNCH
+    }
     if (refine >= 2) {
         // grid.x covers the candidate capacity; warps beyond a frame's candidate count exit at once
         const dim3 gv((g.cand_cap + 63) / 64, nframes);

@@ -129,6 +129,29 @@ def render_sequence(seed: int, n: int, width: int = 640, height: int = 480, **kw
     return g, d
 
 
+def _render_job(job):
+    seed, i, n, width, height = job
+    g, d, _, _ = render_frame(seed, i, width, height, n_frames=max(n, 64))
+    return i, g, d
+
+
+def render_sequence_parallel(seed: int, n: int, width: int = 640, height: int = 480, workers: int = 0):
+    """render_sequence over a pool of spawned worker processes (the frames are independent; ~0.4 s of numpy each).  Same bytes as render_sequence."""
+    import multiprocessing as mp
+    import os
+    if workers <= 0:
+        workers = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    workers = max(1, min(workers, n))
+    if workers == 1:
+        return render_sequence(seed, n, width, height)
+    g = np.empty((n, height, width), np.uint8)
+    d = np.empty((n, height, width), np.uint16)
+    with mp.get_context("spawn").Pool(workers) as pool:
+        for i, gi, di in pool.imap_unordered(_render_job, [(seed, i, n, width, height) for i in range(n)], chunksize=max(1, n // (4 * workers))):
+            g[i], d[i] = gi, di
+    return g, d
+
+
 def polygon_image(seed: int, width: int = 640, height: int = 480, n_poly: int = 40) -> np.ndarray:
     """Config-1 style image: random filled convex-ish polygons + value noise + blur (numpy only)."""
     rng = np.random.Generator(np.random.Philox(key=int(seed)))
