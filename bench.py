@@ -42,8 +42,8 @@ DEFAULT_WAVE = 1776                                            # 148 SMs x 12 re
 SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "4"))         # ORB / PEAC / pose library calls per step (LSD takes the whole step in one call:
                                                                # its one-warp-per-frame kernel needs 32 frames per SM in flight, PEAC clustering fits 12)
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
-LSD_SUBS = int(os.environ.get("PSLAM_LSD_SUBS", "3"))          # LSD calls per step: 4 x 1776 = 3 x 2368 frames, i.e. every LSD call is exactly one wave of its
-                                                               # one-warp-per-frame kernel (16 resident CTAs per SM x 148), every PEAC call one wave of the clustering kernel (12 x 148)
+LSD_SUBS = int(os.environ.get("PSLAM_LSD_SUBS", "2"))          # LSD calls per step: 4 x 1776 = 2 x 3552 frames, i.e. every LSD call is exactly one wave of its
+                                                               # one-warp-per-frame kernel (24 resident CTAs per SM x 148), every PEAC call one wave of the clustering kernel (12 x 148)
 DISTINCT_FRAMES = int(os.environ.get("PSLAM_DISTINCT_FRAMES", "256"))   # distinct frames of the replayed sequence (rendered on the host cores by a process pool)
                                                                          # and distinct pose problems; the step's frames cycle through them
 
@@ -52,6 +52,7 @@ ALGO_BYTES = {
     "orb_resize_level": 926546 + 850812,      # read levels 0-6 once, write levels 1-7 (borderless)
     "orb_fast_cells": 950532 + 30000 * 4,     # read every level once, write <= 30k packed candidates
     "orb_blur_level": 2 * 950532,             # read + write every level once
+    "orb_blur_tma": 2 * 950532,               # same work, all levels in one TMA-staged launch
     "orb_quadtree": 30000 * 4 * 2,
     "orb_orient_describe": 1000 * (709 + 512 + 60),
     "peac_blocks": 614400 + 3072 * (17 * 8 + 5),       # read depth once, write per-block sums + PCA
@@ -65,8 +66,10 @@ ALGO_BYTES = {
     "pose_optimization": 1046 * 104 + 1046 * 24 + 2048,   # edge records read once, residuals + flags written (per problem)
     "lsd_blur_scale": 307200 + 196608,                 # read the frame once, write the 512x384 scaled image
     "lsd_gradient": 196608 + 196608 * 16,              # read the scaled image, write one 16-byte record per pixel
-    "lsd_regions": 196608 * 16 + 2 * 60000 * 4 + 2 * 120000 * 4 + 2 * 196608 + 2500 * 96,   # records once, seed order W+R, region FIFO W+R, used map, candidates
+    "lsd_regions": 196608 * 16 + 60000 * 4 + 2 * 120000 * 4 + 2 * 196608 + 2500 * 96,   # records once, seed order read, region FIFO W+R, used map, candidates
     "lsd_validate": 2500 * (96 + 8) + 2500 * 100 * 16, # candidate rectangles + the records under each rectangle once
+    "lsd_improve": 500 * (96 + 8) + 500 * 25 * 100 * 16,   # queued candidates: up to 25 more rectangle variants each
+    "lsd_order": 2 * 196608 + 60000 * 4,               # the scaled image twice, the seed order once
     "lsd_emit": 2500 * 104 + 800 * 40,
     "lsd_keylines": 800 * 16 + 40 * (68 + 24),
 }

@@ -202,6 +202,31 @@ int pslam_search_by_projection_map(pslam_ctx* ctx, const pslam_frame_view* frame
 int pslam_search_by_projection_last(pslam_ctx* ctx, const pslam_frame_view* cur, const pslam_last_frame* last, const pslam_map_points* map,
                                     float th, int mono, int check_orientation, int32_t* matches_io);
 
+/* ---- Device-resident tracking chain (BASELINE.json config 3) ------------------------------------
+ * Replaces the per-frame part of  void Tracking::Track()  src/Tracking.cc:239-304  for a replayed sequence against a fixed map snapshot:
+ *   Frame::Frame (ORB + ComputeStereoFromRGBD, src/Frame.cc:90-110, 603-621)                          batched over the sequence
+ *   bool Tracking::TrackWithMotionModel()   src/Tracking.cc:1739-1859   pose prediction, SearchByProjection(cur, last), PoseOptimization, outlier sweep
+ *   bool Tracking::TrackLocalMap()          src/Tracking.cc:1954-2046   SearchLocalPoints (isInFrustum + SearchByProjection(F, map)), PoseOptimization
+ *   mVelocity update                        src/Tracking.cc:270-278
+ * The map snapshot (pslam_track_set_map: the arrays of pslam_map_points, copied once) and every intermediate product stay in HBM; nothing is read back
+ * between the stages of a frame or between frames.  Frame 0 starts from Tcw0 and runs the local-map stage only; frame 1 predicts with the last pose,
+ * later frames with mVelocity when use_motion_model is set.  Tcw_out [nframes][16] float row-major; stats [nframes][4] = {matches, inliers} of the
+ * motion-model stage and of the local-map stage.  Not modelled: UpdateLastFrame's temporary RGB-D points, key-frame insertion, line / plane edges. */
+typedef struct pslam_track_params {
+    float fx, fy, cx, cy, bf;           /* Frame::fx .. mbf */
+    float depth_factor;                 /* metres per raw depth unit (1 / DepthMapFactor) */
+    float min_x, max_x, min_y, max_y;   /* mnMinX .. mnMaxY */
+    float th_last;                      /* window of SearchByProjection(cur, last): 15 for RGB-D (src/Tracking.cc:1757-1764) */
+    float th_map;                       /* th of SearchByProjection(F, local map): 3 (src/Tracking.cc:2321-2328) */
+    float nnratio_map;                  /* ORBmatcher(0.8) of SearchLocalPoints */
+    int32_t use_motion_model;           /* 0: always predict with the last pose */
+} pslam_track_params;
+int pslam_track_set_map(pslam_ctx* ctx, const pslam_map_points* map);
+int pslam_track_sequence_dev(pslam_ctx* ctx, const uint8_t* d_gray, const uint16_t* d_depth, int nframes, const pslam_track_params* params, const float* Tcw0,
+                             float* Tcw_out, int32_t* stats /* may be NULL */);
+int pslam_track_sequence(pslam_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int nframes, const pslam_track_params* params, const float* Tcw0,
+                         float* Tcw_out, int32_t* stats /* may be NULL */);
+
 /* ---- Plane association -------------------------------------------------------------------------
  * Replaces  int PlaneMatcher::SearchMapByCoefficients(Frame& pF, const vector<MapPlane*>& vpMapPlanes)   src/PlaneMatcher.cpp:10-67
  * (with Frame::ComputePlaneWorldCoeff, src/Frame.cc:815-820).  frame_coef: mvPlaneCoefficients [n_frame][4]; map_coef: GetWorldPos()

@@ -81,6 +81,7 @@ void pslam_destroy(pslam_ctx* c) {
     lba_free(c);
     lsd_free(c);
     search_free(c);
+    track_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

@@ -20,6 +20,7 @@ struct LsdBuffers {
     uint8_t* d_scaled = nullptr; LsdRec* d_rec = nullptr; int32_t* d_smax = nullptr;
     uint8_t* d_used = nullptr; uint32_t* d_reg = nullptr; uint32_t* d_order = nullptr; int32_t* d_norder = nullptr;
     double* d_cands = nullptr; double* d_cand_nfa = nullptr; int32_t* d_ncand = nullptr;
+    uint32_t* d_fail = nullptr; int32_t* d_nfail = nullptr;      // candidates whose first NFA evaluation fails (queue of k_lsd_improve)
     float4* d_segs = nullptr; double* d_wpn = nullptr; int32_t* d_nsegs = nullptr; int32_t* d_status = nullptr;
     LsdKeyLine* d_kl = nullptr; double* d_lf = nullptr; int32_t* d_nkl = nullptr;
     std::vector<int32_t> h_n, h_status;
@@ -42,7 +43,7 @@ static float host_fast_atan2_deg(float y, float x) {                            
 }
 
 static const int LSD_SEG_CAP = 4096;
-#define LSD_REGIONS_OCC 16          // resident region-growing warps per SM the default build of k_lsd_regions targets
+#define LSD_REGIONS_OCC 24          // resident region-growing warps per SM the default build of k_lsd_regions targets
 
 int lsd_alloc(pslam_ctx* c) {
     if (c->lsd) return PSLAM_OK;
@@ -115,6 +116,7 @@ int lsd_alloc(pslam_ctx* c) {
     LA(B.d_ix, g.W * 2); LA(B.d_ax, g.W * 2); LA(B.d_iy, g.H * 2); LA(B.d_ay, g.H * 2); LA(B.d_lut, lut.size() * sizeof(float2)); LA(B.d_lgamma, LSD_LGAMMA_N * 8);
     LA(B.d_gray, nb * g.w * g.h); LA(B.d_scaled, nb * npx); LA(B.d_rec, nb * npx * sizeof(LsdRec)); LA(B.d_smax, nb * 4);
     LA(B.d_used, nb * npx); LA(B.d_reg, nb * npx * 4); LA(B.d_order, nb * npx * 4); LA(B.d_norder, nb * 4);
+    LA(B.d_fail, nb * g.cand_cap * 4); LA(B.d_nfail, nb * 4);
     LA(B.d_cands, nb * g.cand_cap * 12 * 8); LA(B.d_cand_nfa, nb * g.cand_cap * 8); LA(B.d_ncand, nb * 4);
     LA(B.d_segs, nb * g.seg_cap * sizeof(float4)); LA(B.d_wpn, nb * g.seg_cap * 3 * 8); LA(B.d_nsegs, nb * 4); LA(B.d_status, nb * 4);
 #undef LA
@@ -136,7 +138,7 @@ void lsd_free(pslam_ctx* c) {
     LsdBuffers& B = *c->lsd;
     for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_rec,
                     (void*)B.d_smax, (void*)B.d_used, (void*)B.d_reg, (void*)B.d_order, (void*)B.d_norder, (void*)B.d_segs, (void*)B.d_wpn,
-                    (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl})
+                    (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_fail, (void*)B.d_nfail, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl})
         if (p) cudaFree(p);
     delete c->lsd;
     c->lsd = nullptr;
@@ -171,7 +173,9 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     if (refine >= 2) {
         // grid.x covers the candidate capacity; warps beyond a frame's candidate count exit at once
         const dim3 gv((g.cand_cap + 63) / 64, nframes);
-        PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 64, 0, st>>>(g, B.d_rec, B.d_cands, B.d_ncand, B.d_cand_nfa));
+        PSLAM_CUDA(c, cudaMemsetAsync(B.d_nfail, 0, (size_t)nframes * 4, st));
+        PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 64, 0, st>>>(g, B.d_rec, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_fail, B.d_nfail));
+        PSLAM_LAUNCH(c, "lsd_improve", k_lsd_improve<<<gv, 64, 0, st>>>(g, B.d_rec, B.d_cands, B.d_cand_nfa, B.d_fail, B.d_nfail));
     }
     PSLAM_LAUNCH(c, "lsd_emit", k_lsd_emit<<<nframes, 256, 0, st>>>(g, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_segs, B.d_wpn, B.d_nsegs, B.d_status));
     PSLAM_CUDA(c, cudaGetLastError());

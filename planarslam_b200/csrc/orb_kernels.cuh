@@ -13,6 +13,7 @@
 
 #include "orb_common.h"
 #include "pslam_internal.h"
+#include "tma_util.cuh"
 
 namespace pslam {
 
@@ -448,6 +449,85 @@ __global__ void __launch_bounds__(256) k_blur_level(const uint8_t* __restrict__ 
             const uint32_t acc = 18u * (hz[r][c] + hz[r + 6][c]) + 34u * (hz[r + 1][c] + hz[r + 5][c]) +
                                  48u * (hz[r + 2][c] + hz[r + 4][c]) + 56u * hz[r + 3][c];
             D[(size_t)y * dst_pitch + x] = (uint8_t)min(255u, (acc + 32768u) >> 16);
+        }
+    }
+}
+
+// K4a (TMA): the same blur, every level of every frame in ONE launch.  A CTA owns a 128 x 64 output tile; its 144 x 70 source box
+// (3-pixel halo, 4-byte aligned columns) is fetched by one cp.async.bulk.tensor copy into shared memory (zero fill outside the image),
+// the REFLECT_101 halo of border tiles is rebuilt in shared memory from the interior, and each thread slides a 7-row window down a
+// 4-pixel-wide, 16-row strip: horizontal taps by two __dp4a per pixel on byte windows cut from three aligned words, vertical taps on
+// the 8.8 sums held in registers, one 32-bit store per row.  Arithmetic identical to k_blur_level (8.8 -> 16.16, round half up).
+__device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int lane, uint32_t hv[4]) {
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row) + lane;
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const uint32_t c0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), c1 = 48u | (34u << 8) | (18u << 16);
+    hv[0] = __dp4a(__funnelshift_r(w0, w1, 8), c0, __dp4a(__funnelshift_r(w1, w2, 8), c1, 0u));
+    hv[1] = __dp4a(__funnelshift_r(w0, w1, 16), c0, __dp4a(__funnelshift_r(w1, w2, 16), c1, 0u));
+    hv[2] = __dp4a(__funnelshift_r(w0, w1, 24), c0, __dp4a(__funnelshift_r(w1, w2, 24), c1, 0u));
+    hv[3] = __dp4a(w1, c0, __dp4a(w2, c1, 0u));
+}
+
+__global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTmaParams P, uint8_t* __restrict__ blur, size_t blur_frame_bytes) {
+    __shared__ __align__(128) uint8_t tile[BT_BOX_H][BT_BOX_W];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x, lane = tid & 31, strip = tid >> 5, frame = blockIdx.y;
+    int level = 0;
+    while (level + 1 < P.nlevels && (int)blockIdx.x >= P.tile_base[level + 1]) ++level;
+    const int t = blockIdx.x - P.tile_base[level];
+    const int ty = t / P.tiles_x[level], tx = t - ty * P.tiles_x[level];
+    const int x0 = tx * BT_W, y0 = ty * BT_H, w = P.w[level], h = P.h[level];
+    if (tid == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&bar, BT_BOX_W * BT_BOX_H);
+        tma_load_3d(&tile[0][0], &P.map[level], x0 - 4, y0 - 3, frame, &bar);     // smem (r, c) <-> image (y0 - 3 + r, x0 - 4 + c)
+    }
+    mbar_wait(&bar, 0);
+    // REFLECT_101 halo of border tiles: rows first (whole rows, halo columns included), then columns (all rows): the reflection is separable
+    if (y0 == 0 || y0 + BT_H + 3 > h) {
+        for (int i = tid; i < 6 * (BT_BOX_W / 4); i += 128) {
+            const int k = i / (BT_BOX_W / 4), cw = i - k * (BT_BOX_W / 4);
+            const int Y = k < 3 ? k - 3 : h + (k - 3);                             // rows -3..-1 and h..h+2
+            const int r = Y - (y0 - 3);
+            if (r < 0 || r >= BT_BOX_H) continue;
+            const int rs = (Y < 0 ? -Y : 2 * (h - 1) - Y) - (y0 - 3);
+            if (rs < 0 || rs >= BT_BOX_H) continue;
+            reinterpret_cast<uint32_t*>(&tile[r][0])[cw] = reinterpret_cast<const uint32_t*>(&tile[rs][0])[cw];
+        }
+        __syncthreads();
+    }
+    if (x0 == 0 || x0 + BT_W + 3 > w) {
+        for (int i = tid; i < 6 * BT_BOX_H; i += 128) {
+            const int r = i / 6, k = i - r * 6;
+            const int X = k < 3 ? k - 3 : w + (k - 3);
+            const int c = X - (x0 - 4);
+            if (c < 0 || c >= BT_BOX_W) continue;
+            const int cs = (X < 0 ? -X : 2 * (w - 1) - X) - (x0 - 4);
+            if (cs < 0 || cs >= BT_BOX_W) continue;
+            tile[r][c] = tile[r][cs];
+        }
+        __syncthreads();
+    }
+    const int x = x0 + 4 * lane, ys = y0 + 16 * strip;
+    if (x >= w || ys >= h) return;
+    uint8_t* D = blur + (size_t)frame * blur_frame_bytes + P.dst_off[level];
+    const int pitch = P.dst_pitch[level];
+    uint32_t hw[7][4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) blur_hrow(&tile[16 * strip + k][0], lane, hw[k]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        blur_hrow(&tile[16 * strip + j + 6][0], lane, hw[(j + 6) % 7]);
+        if (ys + j < h) {
+            uint32_t out = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t acc = 18u * (hw[j % 7][q] + hw[(j + 6) % 7][q]) + 34u * (hw[(j + 1) % 7][q] + hw[(j + 5) % 7][q]) +
+                                     48u * (hw[(j + 2) % 7][q] + hw[(j + 4) % 7][q]) + 56u * hw[(j + 3) % 7][q];
+                out |= min(255u, (acc + 32768u) >> 16) << (8 * q);
+            }
+            *reinterpret_cast<uint32_t*>(D + (size_t)(ys + j) * pitch + x) = out;
         }
     }
 }

@@ -184,7 +184,31 @@ int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint
     // K3: quadtree, one warp per (level, frame)
     PSLAM_LAUNCH(c, "orb_quadtree", k_quadtree<<<dim3(g.nlevels, nframes), 32, 0, st>>>(g, c->d_slots, c->d_cell_cnt, c->d_cand, c->d_cand_cnt,
                  c->d_nodes, c->d_links, c->d_work, c->d_lvl_kp, c->d_lvl_cnt, c->d_status));
-    // K4a: blur every level
+    // K4a: blur every level.  TMA path: one launch for all levels; the tensor maps of levels 1.. point into the context's pyramid buffer, level 0's
+    // into the caller's frames (re-encoded when the pointer or the frame count changes).  Images whose rows are not 16-byte multiples cannot be
+    // described by a tensor map and take the per-level kernel.
+    bool tma_ok = (g.width % 16) == 0 && ((uintptr_t)d_gray % 16) == 0 && std::getenv("PSLAM_NO_TMA") == nullptr;
+    if (tma_ok) {
+        BlurTmaParams& P = c->blur_tma;
+        if (c->blur_tma_src != d_gray || c->blur_tma_n != nframes) {
+            int base = 0;
+            for (int l = 0; l < g.nlevels && tma_ok; ++l) {
+                const LevelGeom& v = g.lv[l];
+                P.tiles_x[l] = (v.w + BT_W - 1) / BT_W;
+                P.tile_base[l] = base;
+                base += P.tiles_x[l] * ((v.h + BT_H - 1) / BT_H);
+                P.w[l] = v.w; P.h[l] = v.h; P.dst_pitch[l] = v.blur_pitch; P.dst_off[l] = v.blur_off;
+                tma_ok = l == 0 ? tma_encode_3d(&P.map[0], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, d_gray, v.w, v.h, nframes, (size_t)g.width, frame_px, BT_BOX_W, BT_BOX_H)
+                                : tma_encode_3d(&P.map[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c->d_pyr + v.pyr_off, v.w, v.h, c->cfg.max_batch, (size_t)v.pitch,
+                                                (size_t)g.pyr_bytes, BT_BOX_W, BT_BOX_H);
+            }
+            P.tile_base[g.nlevels] = base; P.nlevels = g.nlevels;
+            c->blur_tma_src = tma_ok ? d_gray : nullptr; c->blur_tma_n = nframes;
+        }
+    }
+    if (tma_ok) {
+        PSLAM_LAUNCH(c, "orb_blur_tma", k_blur_tma<<<dim3(c->blur_tma.tile_base[g.nlevels], nframes), 128, 0, st>>>(c->blur_tma, c->d_blur, (size_t)c->blur_frame_bytes));
+    } else
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& v = g.lv[l];
         const uint8_t* src = (l == 0) ? d_gray : c->d_pyr + v.pyr_off;

@@ -55,7 +55,7 @@ struct PoseOutDev {
 struct PoseCam { double fx, fy, cx, cy, bf; };
 
 // residual of one edge at pose T (computeError of the six edge classes)
-__device__ __noinline__ void pose_edge_error(const PoseEdgeDev& e, const dSE3& T, const PoseCam& K, double err[3]) {
+static __device__ __noinline__ void pose_edge_error(const PoseEdgeDev& e, const dSE3& T, const PoseCam& K, double err[3]) {
     if (e.kind <= PK_LINE || (e.kind >= PK_MONO_T && e.kind <= PK_LINE_T)) {
         const bool tonly = e.kind >= PK_MONO_T;                                   // mapTrans: Xc + t (se3quat.h:221)
         const dV3 p = tonly ? dv(e.a[0], e.a[1], e.a[2]) + T.t : qrot(T.q, dv(e.a[0], e.a[1], e.a[2])) + T.t;
@@ -96,7 +96,7 @@ __device__ __noinline__ void pose_edge_error(const PoseEdgeDev& e, const dSE3& T
 
 __device__ __forceinline__ int pose_edge_dim(int kind) { return kind == PK_MONO || kind == PK_MONO_T || kind == PK_PAR || kind == PK_VER ? 2 : 3; }
 
-__device__ __noinline__ void pose_edge_jacobian(const PoseEdgeDev& e, const dSE3& T, const PoseCam& K, double J[3][6]) {
+static __device__ __noinline__ void pose_edge_jacobian(const PoseEdgeDev& e, const dSE3& T, const PoseCam& K, double J[3][6]) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -159,7 +159,7 @@ __device__ __forceinline__ void huber(double e2, double delta, double& rho0, dou
     else { const double s = sqrt(e2); rho0 = 2 * s * delta - dsqr; rho1 = delta / s; }
 }
 
-__device__ __noinline__ bool solve6(const double H[6][6], const double b[6], double x[6]) {
+static __device__ __noinline__ bool solve6(const double H[6][6], const double b[6], double x[6]) {
     double L[6][6], D[6], y[6];
     for (int j = 0; j < 6; ++j) {
         double d = H[j][j];
@@ -202,7 +202,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_part /*[POS
 }
 
 // errors of the active edges at pose Tq, and the robust chi2 (computeActiveErrors + activeRobustChi2)
-__device__ __noinline__ double pose_active_chi(const PoseEdgeDev* E, int ne, const uint8_t* level, double* err, const dSE3& Tq, const PoseCam& K,
+static __device__ __noinline__ double pose_active_chi(const PoseEdgeDev* E, int ne, const uint8_t* level, double* err, const dSE3& Tq, const PoseCam& K,
                                                bool robust, double* s_part, double* s_red) {
     double acc[1] = {0};
     for (int i = threadIdx.x; i < ne; i += POSE_THREADS) {
@@ -221,7 +221,7 @@ __device__ __noinline__ double pose_active_chi(const PoseEdgeDev* E, int ne, con
     return s_red[0];
 }
 
-__global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const PoseHeaderDev* __restrict__ headers, const PoseEdgeDev* __restrict__ edges,
+static __global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const PoseHeaderDev* __restrict__ headers, const PoseEdgeDev* __restrict__ edges,
                                                                     double* __restrict__ err_all, uint8_t* __restrict__ level_all,
                                                                     uint8_t* __restrict__ f_pt, uint8_t* __restrict__ f_line, uint8_t* __restrict__ f_plane,
                                                                     uint8_t* __restrict__ f_par, uint8_t* __restrict__ f_ver, PoseOutDev* __restrict__ outs) {

@@ -1,5 +1,6 @@
 // Internal declarations shared by the translation units of libpslam_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -46,6 +47,19 @@ struct OrbGeom {
     int umax[16];
 };
 
+// TMA-staged Gaussian blur of the ORB path (orb_kernels.cuh k_blur_tma): tile / box geometry and the kernel parameter block
+#define BT_W 128
+#define BT_H 64
+#define BT_BOX_W 144
+#define BT_BOX_H 70
+struct BlurTmaParams {
+    CUtensorMap map[PSLAM_MAX_LEVELS];
+    int tile_base[PSLAM_MAX_LEVELS + 1];    // first tile of each level in blockIdx.x
+    int tiles_x[PSLAM_MAX_LEVELS];
+    int w[PSLAM_MAX_LEVELS], h[PSLAM_MAX_LEVELS], dst_pitch[PSLAM_MAX_LEVELS], dst_off[PSLAM_MAX_LEVELS];
+    int nlevels;
+};
+
 // PEAC parameters and sizes (compiled-in defaults of the reference: AHCPlaneFitter.hpp:154-158, AHCParamSet.hpp:68-76)
 struct PeacGeom {
     int w, h, nbw, nbh, nblk, win;
@@ -64,6 +78,7 @@ struct PoseBuffers;
 struct SearchBuffers;
 struct LbaBuffers;
 struct LsdBuffers;
+struct TrackBuffers;
 
 }  // namespace pslam
 
@@ -88,6 +103,8 @@ struct pslam_ctx {
     uint8_t* d_pyr = nullptr;         // levels 1.. of every frame
     uint8_t* d_blur = nullptr;        // blurred levels 0.. of every frame (same layout incl. level 0)
     int blur_frame_bytes = 0;
+    pslam::BlurTmaParams blur_tma;    // tensor maps of the TMA-staged blur (orb_pipeline.cu); valid for (blur_tma_src, blur_tma_n)
+    const uint8_t* blur_tma_src = nullptr; int blur_tma_n = 0;
     int16_t* d_xofs = nullptr; int16_t* d_xa = nullptr;   // resize tables: source column, (alpha0, alpha1) pairs
     int16_t* d_yofs = nullptr; int16_t* d_ya = nullptr;
     uint32_t* d_slots = nullptr;      // per-cell candidate slots (packed x | y<<11 | score<<22)
@@ -119,6 +136,7 @@ struct pslam_ctx {
     pslam::SearchBuffers* search = nullptr;      // projection-search staging (search_kernels.cu)
     pslam::LbaBuffers* lba = nullptr;            // local bundle adjustment staging (lba_pipeline.cu)
     pslam::LsdBuffers* lsd = nullptr;            // line-segment detector buffers (lsd_pipeline.cu)
+    pslam::TrackBuffers* track = nullptr;        // device-resident tracking chain (track_chain.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
     int32_t* h_status = nullptr;
@@ -138,6 +156,7 @@ void pose_free(pslam_ctx* c);
 void search_free(pslam_ctx* c);
 void lba_free(pslam_ctx* c);
 void lsd_free(pslam_ctx* c);
+void track_free(pslam_ctx* c);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

@@ -26,12 +26,16 @@ for seed in (0, 7):
             length = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
             segs = segs[np.argsort(-length, kind="stable")[:40]]
         lsd[f"seed{seed}_refine{refine}"] = segs.astype(np.float32)
-# the 40 longest LSD_REFINE_ADV segments (what ExtractLineSegment keeps) of the 17 LSD test frames
+# what ExtractLineSegment keeps of LSD_REFINE_ADV on the 17 LSD test frames: LSDDetector clamps the end points into the image (x >= cols -> cols - 1, < 0 -> 0),
+# KeyLine.response = clamped length / max(cols, rows), the 40 largest responses are kept (ties: detection order)
 adv_frames = [synth.render_frame(seed=s, frame=3 * s)[0] for s in range(16)] + [synth.polygon_image(11)]
 for k, g in enumerate(adv_frames):
-    segs = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(g)[0].reshape(-1, 4)
-    length = np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1])
-    lsd[f"adv_top40_{k}"] = segs[np.argsort(-length, kind="stable")[:40]].astype(np.float32)
+    segs = cv2.createLineSegmentDetector(cv2.LSD_REFINE_ADV).detect(g)[0].reshape(-1, 4).astype(np.float32)
+    h, w = g.shape
+    segs[:, [0, 2]] = np.where(segs[:, [0, 2]] < 0, np.float32(0), np.where(segs[:, [0, 2]] >= w, np.float32(w - 1), segs[:, [0, 2]]))
+    segs[:, [1, 3]] = np.where(segs[:, [1, 3]] < 0, np.float32(0), np.where(segs[:, [1, 3]] >= h, np.float32(h - 1), segs[:, [1, 3]]))
+    length = np.sqrt((segs[:, 0] - segs[:, 2]).astype(np.float64) ** 2 + (segs[:, 1] - segs[:, 3]).astype(np.float64) ** 2).astype(np.float32)
+    lsd[f"adv_top40_{k}"] = segs[np.argsort(-(length / np.float32(max(w, h))), kind="stable")[:40]]
 np.savez_compressed(os.path.join(out, "lsd_cv2_4_13.npz"), **lsd)
 
 # ---- 8-bit primitives on a seeded random image ----
