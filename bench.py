@@ -66,9 +66,9 @@ ALGO_BYTES = {
     "pose_optimization": 1046 * 104 + 1046 * 24 + 2048,   # edge records read once, residuals + flags written (per problem)
     "lsd_blur_scale": 307200 + 196608,                 # read the frame once, write the 512x384 scaled image
     "lsd_gradient": 196608 + 196608 * 16,              # read the scaled image, write one 16-byte record per pixel
-    "lsd_regions": 196608 * 16 + 60000 * 4 + 2 * 120000 * 4 + 2 * 196608 + 2500 * 96,   # records once, seed order read, region FIFO W+R, used map, candidates
-    "lsd_validate": 2500 * (96 + 8) + 2500 * 100 * 16, # candidate rectangles + the records under each rectangle once
-    "lsd_improve": 500 * (96 + 8) + 500 * 25 * 100 * 16,   # queued candidates: up to 25 more rectangle variants each
+    "lsd_regions": 196608 * 4 + 120000 * (4 + 8 + 4) + 60000 * 4 + 2 * 120000 * 4 + 2500 * 96,   # angle plane once, used-bit write + cos/sin + gradient of region pixels, seed order, region FIFO W+R, candidates
+    "lsd_validate": 2500 * (96 + 8) + 2500 * 100 * 4,  # candidate rectangles + the angle words under each rectangle once
+    "lsd_improve": 500 * (96 + 8) + 500 * 25 * 100 * 4,   # queued candidates: up to 25 more rectangle variants each
     "lsd_order": 2 * 196608 + 60000 * 4,               # the scaled image twice, the seed order once
     "lsd_emit": 2500 * 104 + 800 * 40,
     "lsd_keylines": 800 * 16 + 40 * (68 + 24),

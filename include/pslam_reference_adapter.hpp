@@ -1,0 +1,329 @@
+// pslam_reference_adapter.hpp - drop-in replacements WITH THE REFERENCE'S OWN SIGNATURES (Frame*, Frame&, std::vector<MapPoint*>, MapPlane* ...)
+// on top of the C ABI (include/pslam_abi.h).  Header-only; compile it inside the PlanarSLAM tree after the reference's own headers:
+//
+//     #include "Frame.h"  "MapPoint.h"  "MapPlane.h"  "MapLine.h"  "Config.h"          (the reference's)
+//     #include "pslam_reference_adapter.hpp"
+//     ...
+//     int nInliers = pslam_adapter::ref::Optimizer::PoseOptimization(&mCurrentFrame);                       // was Optimizer::PoseOptimization   (include/Optimizer.h:38)
+//     pslam_adapter::ref::ORBmatcher matcher(0.8);  matcher.SearchByProjection(mCurrentFrame, mvpLocalMapPoints, th);    // include/ORBmatcher.h:43
+//
+// Each entry point gathers what the reference function reads from the object graph - under the same mutexes the reference takes -, calls the C ABI
+// (one context per calling thread, created on first use), and writes back exactly what the reference function writes (mvpMapPoints, mvbOutlier...,
+// mTcw through Frame::SetPose).  Return values are the reference's.
+//
+//   static int  Optimizer::PoseOptimization(Frame*)                                   include/Optimizer.h:38   src/Optimizer.cc:550-1275
+//   static int  Optimizer::TranslationOptimization(Frame*)                            include/Optimizer.h:40   src/Optimizer.cc:2995-3737
+//   int ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float th)    include/ORBmatcher.h:43  src/ORBmatcher.cc:46-130
+//   int ORBmatcher::SearchByProjection(Frame&, const Frame&, float th, bool bMono)    include/ORBmatcher.h:47  src/ORBmatcher.cc:1396-1535
+//   int PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)       include/PlaneMatcher.h:18 src/PlaneMatcher.cpp:10-67
+//   void ORBextractor::operator()(cv::InputArray, cv::InputArray, vector<cv::KeyPoint>&, cv::OutputArray)   include/ORBextractor.h:59-61
+//
+// Two reference members read here are protected in the reference (MapPoint::mfMaxDistance / mfMinDistance: the getters return them scaled by 1.2 / 0.8
+// and a float division does not undo a float multiplication): add `friend struct pslam_adapter::ref::Access;` to MapPoint, or two raw getters - see
+// INTEGRATION.md.  tests/ builds this header against the reference's headers with the stand-in OpenCV / Eigen of oracle/ref/shims
+// (oracle/ref/adapter_driver.cc) and compares every entry point with the reference function on the same objects (tests/test_reference_adapter_gpu.py).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <unordered_map>
+#include <vector>
+
+#include "pslam_abi.h"
+
+namespace pslam_adapter {
+namespace ref {
+
+using Planar_SLAM::Frame;
+using Planar_SLAM::MapLine;
+using Planar_SLAM::MapPlane;
+using Planar_SLAM::MapPoint;
+
+struct Access {          // the two protected MapPoint members (see the header comment)
+    static float max_distance(MapPoint* p) { return p->mfMaxDistance; }
+    static float min_distance(MapPoint* p) { return p->mfMinDistance; }
+};
+
+// one context per calling thread (the reference calls its matchers / optimiser from the tracking thread and from three SearchLocal* threads)
+inline pslam_ctx* context(int width = 640, int height = 480) {
+    struct Holder {
+        pslam_ctx* c = nullptr; int w = 0, h = 0;
+        ~Holder() { if (c) pslam_destroy(c); }
+    };
+    thread_local Holder H;
+    if (!H.c || H.w != width || H.h != height) {
+        if (H.c) pslam_destroy(H.c);
+        pslam_config cfg;
+        pslam_default_config(&cfg, width, height, 1);
+        if (pslam_create(&cfg, &H.c) != PSLAM_OK) { H.c = nullptr; throw std::runtime_error("pslam_create failed: no sm_100 GPU"); }
+        H.w = width; H.h = height;
+    }
+    return H.c;
+}
+
+struct Optimizer {
+    static int PoseOptimization(Frame* pFrame) { return run(pFrame, false); }
+    static int TranslationOptimization(Frame* pFrame) { return run(pFrame, true); }
+
+private:
+    static int run(Frame* pFrame, bool translation_only) {
+        pslam_pose_problem P;
+        std::memset(&P, 0, sizeof P);
+        P.fx = pFrame->fx; P.fy = pFrame->fy; P.cx = pFrame->cx; P.cy = pFrame->cy; P.bf = pFrame->mbf;
+        const int N = pFrame->N;
+        std::vector<float> Xw, obs, inv_sigma2;
+        std::vector<int> pt_index;
+        {
+            std::unique_lock<std::mutex> lock(MapPoint::mGlobalMutex);
+            for (int i = 0; i < N; ++i) {
+                MapPoint* pMP = pFrame->mvpMapPoints[i];
+                if (!pMP) continue;
+                pFrame->mvbOutlier[i] = false;
+                const cv::KeyPoint& kpUn = pFrame->mvKeysUn[i];
+                const cv::Mat X = pMP->GetWorldPos();
+                for (int k = 0; k < 3; ++k) Xw.push_back(X.at<float>(k));
+                obs.push_back(kpUn.pt.x); obs.push_back(kpUn.pt.y); obs.push_back(pFrame->mvuRight[i] < 0 ? -1.0f : pFrame->mvuRight[i]);
+                inv_sigma2.push_back(pFrame->mvInvLevelSigma2[kpUn.octave]);
+                pt_index.push_back(i);
+            }
+        }
+        const int NL = pFrame->NL;
+        std::vector<double> line_Xw, line_obs;
+        std::vector<int> line_index;
+        {
+            std::unique_lock<std::mutex> lock(MapLine::mGlobalMutex);
+            for (int i = 0; i < NL; ++i) {
+                MapLine* pML = pFrame->mvpMapLines[i];
+                if (!pML) continue;
+                pFrame->mvbLineOutlier[i] = false;
+                for (int k = 0; k < 6; ++k) line_Xw.push_back(pML->mWorldPos(k));
+                for (int k = 0; k < 3; ++k) line_obs.push_back(pFrame->mvKeyLineFunctions[i](k));
+                line_index.push_back(i);
+            }
+        }
+        const int M = pFrame->mnPlaneNum;
+        std::vector<float> meas[3], mapc[3];
+        std::vector<int> plane_index[3];
+        {
+            std::unique_lock<std::mutex> lock(MapPlane::mGlobalMutex);
+            for (int fam = 0; fam < (translation_only ? 1 : 3); ++fam) {          // TranslationOptimization adds plane edges only (src/Optimizer.cc:3215-3220)
+                std::vector<MapPlane*>& held = fam == 0 ? pFrame->mvpMapPlanes : fam == 1 ? pFrame->mvpParallelPlanes : pFrame->mvpVerticalPlanes;
+                std::vector<bool>& flags = fam == 0 ? pFrame->mvbPlaneOutlier : fam == 1 ? pFrame->mvbParPlaneOutlier : pFrame->mvbVerPlaneOutlier;
+                for (int i = 0; i < M; ++i) {
+                    MapPlane* pMP = held[i];
+                    if (!pMP) continue;
+                    flags[i] = false;
+                    const cv::Mat w = pMP->GetWorldPos();
+                    for (int k = 0; k < 4; ++k) { meas[fam].push_back(pFrame->mvPlaneCoefficients[i].at<float>(k)); mapc[fam].push_back(w.at<float>(k)); }
+                    plane_index[fam].push_back(i);
+                }
+            }
+        }
+        P.n_points = (int)pt_index.size(); P.Xw = Xw.data(); P.obs = obs.data(); P.inv_sigma2 = inv_sigma2.data();
+        P.n_lines = (int)line_index.size(); P.line_Xw = line_Xw.data(); P.line_obs = line_obs.data();
+        P.n_planes = (int)plane_index[0].size(); P.n_par = (int)plane_index[1].size(); P.n_ver = (int)plane_index[2].size();
+        P.plane_meas = meas[0].data(); P.plane_map = mapc[0].data(); P.par_meas = meas[1].data(); P.par_map = mapc[1].data();
+        P.ver_meas = meas[2].data(); P.ver_map = mapc[2].data();
+        P.angle_info = Planar_SLAM::Config::Get<double>("Plane.AngleInfo"); P.dist_info = Planar_SLAM::Config::Get<double>("Plane.DistanceInfo");
+        P.par_info = Planar_SLAM::Config::Get<double>("Plane.ParallelInfo"); P.ver_info = Planar_SLAM::Config::Get<double>("Plane.VerticalInfo");
+        P.plane_chi = Planar_SLAM::Config::Get<double>("Plane.Chi"); P.vp_chi = Planar_SLAM::Config::Get<double>("Plane.VPChi");
+        float T[16];
+        for (int i = 0; i < 16; ++i) T[i] = pFrame->mTcw.at<float>(i / 4, i % 4);
+        std::vector<uint8_t> o_pt(P.n_points + 1), o_line(P.n_lines + 1), o_pl(P.n_planes + 1), o_par(P.n_par + 1), o_ver(P.n_ver + 1);
+        pslam_ctx* c = context();
+        const int rc = translation_only ? pslam_translation_optimization(c, &P, T, o_pt.data(), o_line.data(), o_pl.data())
+                                        : pslam_pose_optimization(c, &P, T, o_pt.data(), o_line.data(), o_pl.data(), o_par.data(), o_ver.data());
+        if (rc < 0) throw std::runtime_error(pslam_last_error(c));
+        const int n_initial = translation_only ? P.n_points : P.n_points + P.n_lines + P.n_planes + P.n_par + P.n_ver;
+        if (n_initial < 3) return 0;                                              // the reference returns before touching the flags or the pose
+        for (int k = 0; k < P.n_points; ++k) pFrame->mvbOutlier[pt_index[k]] = o_pt[k] != 0;
+        for (int k = 0; k < P.n_lines; ++k) pFrame->mvbLineOutlier[line_index[k]] = o_line[k] != 0;
+        for (int k = 0; k < P.n_planes; ++k) pFrame->mvbPlaneOutlier[plane_index[0][k]] = o_pl[k] != 0;
+        for (int k = 0; k < P.n_par; ++k) pFrame->mvbParPlaneOutlier[plane_index[1][k]] = o_par[k] != 0;
+        for (int k = 0; k < P.n_ver; ++k) pFrame->mvbVerPlaneOutlier[plane_index[2][k]] = o_ver[k] != 0;
+        cv::Mat pose(4, 4, CV_32F);
+        for (int i = 0; i < 16; ++i) pose.at<float>(i / 4, i % 4) = T[i];
+        pFrame->SetPose(pose);
+        return rc;
+    }
+};
+
+// gathers the arrays of pslam_frame_view from a Frame (mvKeysUn, mvuRight, mDescriptors, mTcw, statics, scale tables)
+struct FrameArrays {
+    std::vector<pslam_keypoint> keys; std::vector<uint8_t> desc; pslam_frame_view v;
+    explicit FrameArrays(const Frame& F) {
+        const int n = F.N;
+        keys.resize(n); desc.resize((size_t)n * 32);
+        for (int i = 0; i < n; ++i) {
+            const cv::KeyPoint& k = F.mvKeysUn[i];
+            keys[i].x = k.pt.x; keys[i].y = k.pt.y; keys[i].size = k.size; keys[i].angle = k.angle; keys[i].response = k.response; keys[i].octave = k.octave;
+            keys[i].class_id = k.class_id;
+            std::memcpy(&desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+        }
+        std::memset(&v, 0, sizeof v);
+        v.n = n; v.keys_un = keys.data(); v.u_right = F.mvuRight.data(); v.desc = desc.data();
+        for (int i = 0; i < 16; ++i) v.Tcw[i] = F.mTcw.at<float>(i / 4, i % 4);
+        v.fx = Frame::fx; v.fy = Frame::fy; v.cx = Frame::cx; v.cy = Frame::cy; v.bf = F.mbf;
+        v.min_x = Frame::mnMinX; v.max_x = Frame::mnMaxX; v.min_y = Frame::mnMinY; v.max_y = Frame::mnMaxY;
+        v.n_levels = F.mnScaleLevels; v.scale_factors = F.mvScaleFactors.data(); v.log_scale_factor = F.mfLogScaleFactor;
+    }
+};
+
+struct MapArrays {       // pslam_map_points over a list of distinct MapPoint*
+    std::vector<float> pos, normal, maxd, mind; std::vector<uint8_t> desc, skip, has_obs; pslam_map_points v;
+    std::unordered_map<MapPoint*, int> index; std::vector<MapPoint*> pts;
+    int add(MapPoint* p, bool skipped) {
+        auto it = index.find(p);
+        if (it != index.end()) return it->second;
+        const int id = (int)pts.size();
+        index[p] = id; pts.push_back(p);
+        const cv::Mat X = p->GetWorldPos(), Nv = p->GetNormal(), D = p->GetDescriptor();
+        for (int k = 0; k < 3; ++k) { pos.push_back(X.at<float>(k)); normal.push_back(Nv.empty() ? 0.f : Nv.at<float>(k)); }
+        maxd.push_back(Access::max_distance(p)); mind.push_back(Access::min_distance(p));
+        desc.resize(desc.size() + 32);
+        if (!D.empty()) std::memcpy(&desc[desc.size() - 32], D.ptr(0), 32);
+        skip.push_back(skipped ? 1 : 0); has_obs.push_back(p->Observations() > 0 ? 1 : 0);
+        return id;
+    }
+    const pslam_map_points* view() {
+        v.n = (int)pts.size(); v.pos = pos.data(); v.normal = normal.data(); v.max_distance = maxd.data(); v.min_distance = mind.data();
+        v.desc = desc.data(); v.skip = skip.data(); v.has_obs = has_obs.data();
+        return &v;
+    }
+};
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+    // Search matches between Frame keypoints and projected MapPoints (the caller ran Frame::isInFrustum on them: mbTrackInView)
+    int SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th = 3) {
+        // the kernel walks the map arrays in index order = the order of vpMapPoints; points the frame already holds are appended (skipped: they only
+        // take part as "this key point is taken", src/ORBmatcher.cc:83-85)
+        MapArrays L;
+        std::vector<int32_t> matches(F.N, -1);
+        for (MapPoint* p : vpMapPoints) L.add(p, !p->mbTrackInView || p->isBad());
+        for (int i = 0; i < F.N; ++i) matches[i] = F.mvpMapPoints[i] ? L.add(F.mvpMapPoints[i], true) : -1;
+        FrameArrays A(F);
+        pslam_ctx* c = context();
+        const int n = pslam_search_by_projection_map(c, &A.v, L.view(), th, mfNNratio, matches.data(), nullptr);
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int i = 0; i < F.N; ++i) F.mvpMapPoints[i] = matches[i] >= 0 ? L.pts[matches[i]] : static_cast<MapPoint*>(NULL);
+        return n;
+    }
+
+    // Project MapPoints tracked in the last frame into the current frame and search matches (motion-model tracking)
+    int SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+        MapArrays M;
+        std::vector<int32_t> last_mp(LastFrame.N, -1), matches(CurrentFrame.N, -1);
+        std::vector<uint8_t> last_out(LastFrame.N, 0);
+        std::vector<pslam_keypoint> last_keys(LastFrame.N);
+        for (int i = 0; i < LastFrame.N; ++i) {
+            if (LastFrame.mvpMapPoints[i]) last_mp[i] = M.add(LastFrame.mvpMapPoints[i], false);
+            last_out[i] = LastFrame.mvbOutlier[i] ? 1 : 0;
+            const cv::KeyPoint& k = LastFrame.mvKeys[i];
+            last_keys[i].x = k.pt.x; last_keys[i].y = k.pt.y; last_keys[i].size = k.size; last_keys[i].angle = k.angle; last_keys[i].response = k.response;
+            last_keys[i].octave = k.octave; last_keys[i].class_id = k.class_id;
+        }
+        for (int i = 0; i < CurrentFrame.N; ++i) if (CurrentFrame.mvpMapPoints[i]) matches[i] = M.add(CurrentFrame.mvpMapPoints[i], false);
+        pslam_last_frame Lf;
+        std::memset(&Lf, 0, sizeof Lf);
+        Lf.n = LastFrame.N; Lf.keys = last_keys.data(); Lf.map_point = last_mp.data(); Lf.outlier = last_out.data();
+        for (int i = 0; i < 16; ++i) Lf.Tcw[i] = LastFrame.mTcw.at<float>(i / 4, i % 4);
+        FrameArrays A(CurrentFrame);
+        pslam_ctx* c = context();
+        const int n = pslam_search_by_projection_last(c, &A.v, &Lf, M.view(), th, bMono ? 1 : 0, mbCheckOrientation ? 1 : 0, matches.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int i = 0; i < CurrentFrame.N; ++i) CurrentFrame.mvpMapPoints[i] = matches[i] >= 0 ? M.pts[matches[i]] : static_cast<MapPoint*>(NULL);
+        return n;
+    }
+
+private:
+    float mfNNratio; bool mbCheckOrientation;
+};
+
+class PlaneMatcher {
+public:
+    PlaneMatcher(float dTh = 0.1, float aTh = 0.86, float verTh = 0.08716, float parTh = 0.9962) : dTh(dTh), aTh(aTh), verTh(verTh), parTh(parTh) {}
+    int SearchMapByCoefficients(Frame& pF, const std::vector<MapPlane*>& vpMapPlanes) {
+        pF.mbNewPlane = false;
+        const int nf = pF.mnPlaneNum, nm = (int)vpMapPlanes.size();
+        std::vector<float> fc((size_t)nf * 4), mc((size_t)nm * 4), pts;
+        std::vector<uint8_t> bad(nm);
+        std::vector<int32_t> off(nm + 1, 0);
+        for (int i = 0; i < nf; ++i) for (int k = 0; k < 4; ++k) fc[4 * i + k] = pF.mvPlaneCoefficients[i].at<float>(k);
+        for (int j = 0; j < nm; ++j) {
+            MapPlane* p = vpMapPlanes[j];
+            bad[j] = p->isBad() ? 1 : 0;
+            const cv::Mat w = p->GetWorldPos();
+            for (int k = 0; k < 4; ++k) mc[4 * j + k] = w.at<float>(k);
+            for (const auto& q : p->mvPlanePoints->points) { pts.push_back(q.x); pts.push_back(q.y); pts.push_back(q.z); }
+            off[j + 1] = (int32_t)(pts.size() / 3);
+        }
+        float T[16];
+        for (int i = 0; i < 16; ++i) T[i] = pF.mTcw.at<float>(i / 4, i % 4);
+        std::vector<int32_t> m(nf + 1, -1), v(nf + 1, -1), pr(nf + 1, -1);
+        pslam_ctx* c = context();
+        const int n = pslam_plane_match(c, T, nf, fc.data(), nm, mc.data(), bad.data(), off.data(), pts.empty() ? fc.data() : pts.data(), dTh, aTh, verTh, parTh,
+                                        m.data(), v.data(), pr.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int i = 0; i < nf; ++i) {                 // the reference only overwrites a slot when it finds a candidate
+            if (m[i] >= 0) pF.mvpMapPlanes[i] = vpMapPlanes[m[i]];
+            if (v[i] >= 0) pF.mvpVerticalPlanes[i] = vpMapPlanes[v[i]];
+            if (pr[i] >= 0) pF.mvpParallelPlanes[i] = vpMapPlanes[pr[i]];
+        }
+        return n;
+    }
+
+private:
+    float dTh, aTh, verTh, parTh;
+};
+
+// Planar_SLAM::ORBextractor with cv types: same constructor, getters and call operator (mask ignored like the reference, empty image -> silent return)
+class ORBextractor {
+public:
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+        : nfeatures(nfeatures), scaleFactor(scaleFactor), nlevels(nlevels), iniThFAST(iniThFAST), minThFAST(minThFAST) {}
+    ~ORBextractor() { if (ctx) pslam_destroy(ctx); }
+    ORBextractor(const ORBextractor&) = delete;
+    ORBextractor& operator=(const ORBextractor&) = delete;
+
+    void operator()(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& _keypoints, cv::OutputArray _descriptors) {
+        if (_image.empty()) return;
+        cv::Mat image = _image.getMat();
+        if (image.type() != CV_8UC1) throw std::invalid_argument("ORBextractor: CV_8UC1 expected");            // the reference asserts (src/ORBextractor.cc:1050)
+        if (!ctx || w != image.cols || h != image.rows) {
+            if (ctx) pslam_destroy(ctx);
+            pslam_config cfg;
+            pslam_default_config(&cfg, image.cols, image.rows, 1);
+            cfg.nfeatures = nfeatures; cfg.scale_factor = scaleFactor; cfg.nlevels = nlevels; cfg.ini_th_fast = iniThFAST; cfg.min_th_fast = minThFAST;
+            if (pslam_create(&cfg, &ctx) != PSLAM_OK) { ctx = nullptr; throw std::runtime_error("pslam_create failed: no sm_100 GPU"); }
+            w = image.cols; h = image.rows;
+        }
+        const int cap = pslam_orb_max_keypoints(ctx);
+        std::vector<pslam_keypoint> kps(cap);
+        std::vector<uint8_t> desc((size_t)cap * 32);
+        int32_t n = 0;
+        if (pslam_orb_extract(ctx, image.ptr(0), (int)image.step, kps.data(), desc.data(), cap, &n) != PSLAM_OK) throw std::runtime_error(pslam_last_error(ctx));
+        _keypoints.resize(n);
+        for (int i = 0; i < n; ++i) {
+            cv::KeyPoint& k = _keypoints[i];
+            k.pt.x = kps[i].x; k.pt.y = kps[i].y; k.size = kps[i].size; k.angle = kps[i].angle; k.response = kps[i].response; k.octave = kps[i].octave;
+            k.class_id = kps[i].class_id;
+        }
+        if (n == 0) { _descriptors.release(); return; }
+        _descriptors.create(n, 32, CV_8U);
+        cv::Mat d = _descriptors.getMat();
+        for (int i = 0; i < n; ++i) std::memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
+    }
+    int inline GetLevels() { return nlevels; }
+    float inline GetScaleFactor() { return scaleFactor; }
+
+private:
+    int nfeatures; float scaleFactor; int nlevels, iniThFAST, minThFAST;
+    pslam_ctx* ctx = nullptr; int w = 0, h = 0;
+};
+
+}  // namespace ref
+}  // namespace pslam_adapter

@@ -43,16 +43,31 @@
 #undef protected
 #include "pslam_abi.h"
 
+// Which implementation the entry points below exercise.  Default: the reference's own classes (libmatch_ref.so, ref_* symbols).  oracle/ref/adapter_driver.cc
+// includes this file with the product's reference-typed adapter (include/pslam_reference_adapter.hpp) in their place (libadapter_ref.so, adp_* symbols): the
+// same object graphs, the same read-back, only the function under test differs.
+#ifdef PSLAM_ADAPTER_BUILD
+#include "pslam_reference_adapter.hpp"
+#endif
+#ifndef DRV
+#define DRV(name) ref_##name
+#define DRV_ORBMATCHER ORBmatcher
+#define DRV_PLANEMATCHER PlaneMatcher
+#define DRV_OPTIMIZER Optimizer
+#endif
+
 using namespace Planar_SLAM;
 
 // src/LSDextractor.cpp wraps OpenCV-contrib's LSDDetector / BinaryDescriptor classes, which are not in this image; the only caller is Frame's image
 // constructor (Frame.cc:170-176), which no pinned path runs.  Defined here so that Frame.cc links.
+#ifndef PSLAM_ADAPTER_BUILD
 namespace Planar_SLAM {
 void LineSegment::ExtractLineSegment(const cv::Mat&, std::vector<cv::line_descriptor::KeyLine>&, cv::Mat&, std::vector<Eigen::Vector3d>&, float, int) {
     std::fprintf(stderr, "oracle/ref/match_driver.cc: LineSegment::ExtractLineSegment is a link-only stand-in\n");
     std::abort();
 }
 }  // namespace Planar_SLAM
+#endif
 
 namespace {
 
@@ -145,7 +160,7 @@ DBoW2::FeatureVector feat_vec(int n_nodes, const int32_t* node_id, const int32_t
 }  // namespace
 
 // Tracking::SearchLocalPoints + ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)   src/ORBmatcher.cc:46-130
-extern "C" int ref_search_by_projection_map(const pslam_frame_view* fv, const pslam_map_points* m, float th, float nnratio, int32_t* matches_io, uint8_t* in_view) {
+extern "C" int DRV(search_by_projection_map)(const pslam_frame_view* fv, const pslam_map_points* m, float th, float nnratio, int32_t* matches_io, uint8_t* in_view) {
     World w;
     w.add(*m);
     Frame F;
@@ -156,7 +171,7 @@ extern "C" int ref_search_by_projection_map(const pslam_frame_view* fv, const ps
         if (m->skip[i]) { pMP->mbTrackInView = false; continue; }
         F.isInFrustum(pMP, 0.5);
     }
-    ORBmatcher matcher(nnratio);
+    DRV_ORBMATCHER matcher(nnratio);
     const int n = matcher.SearchByProjection(F, w.pts, th);
     read_back(F, w, matches_io);
     if (in_view) for (int i = 0; i < m->n; ++i) in_view[i] = w.pts[i]->mbTrackInView ? 1 : 0;
@@ -164,7 +179,7 @@ extern "C" int ref_search_by_projection_map(const pslam_frame_view* fv, const ps
 }
 
 // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)   src/ORBmatcher.cc:1396-1535
-extern "C" int ref_search_by_projection_last(const pslam_frame_view* cur, const pslam_last_frame* last, const pslam_map_points* m, float th, int mono,
+extern "C" int DRV(search_by_projection_last)(const pslam_frame_view* cur, const pslam_last_frame* last, const pslam_map_points* m, float th, int mono,
                                              int check_orientation, int32_t* matches_io) {
     World w;
     w.add(*m);
@@ -181,12 +196,13 @@ extern "C" int ref_search_by_projection_last(const pslam_frame_view* cur, const 
     L.mvbOutlier.assign(last->n, false);
     for (int i = 0; i < last->n; ++i) { if (last->map_point[i] >= 0) L.mvpMapPoints[i] = w.pts[last->map_point[i]]; L.mvbOutlier[i] = last->outlier[i] != 0; }
     L.SetPose(mat44(last->Tcw));
-    ORBmatcher matcher(0.9, check_orientation != 0);
+    DRV_ORBMATCHER matcher(0.9, check_orientation != 0);
     const int n = matcher.SearchByProjection(C, L, th, mono != 0);
     read_back(C, w, matches_io);
     return n;
 }
 
+#ifndef PSLAM_ADAPTER_BUILD
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)   src/ORBmatcher.cc:160-292
 extern "C" int ref_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_mp, int kf_nodes, const int32_t* kf_node_id,
                                  const int32_t* kf_node_off, const int32_t* kf_node_feat, int n_f, const uint8_t* f_desc, const float* f_angle, int f_nodes,
@@ -283,8 +299,10 @@ extern "C" int ref_line_search_by_projection(int nf, const float* pt, const floa
     return n;
 }
 
+#endif  // !PSLAM_ADAPTER_BUILD
+
 // PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)   src/PlaneMatcher.cpp:10-82 (Frame::ComputePlaneWorldCoeff src/Frame.cc:815-820)
-extern "C" int ref_plane_match(const float* Tcw, int n_frame, const float* frame_coef, int n_map, const float* map_coef, const uint8_t* map_bad, const int32_t* pts_off,
+extern "C" int DRV(plane_match)(const float* Tcw, int n_frame, const float* frame_coef, int n_map, const float* map_coef, const uint8_t* map_bad, const int32_t* pts_off,
                                const float* pts, float dTh, float aTh, float verTh, float parTh, int32_t* match, int32_t* ver, int32_t* par) {
     World w;
     Frame F;
@@ -308,7 +326,7 @@ extern "C" int ref_plane_match(const float* Tcw, int n_frame, const float* frame
         for (int q = pts_off[j]; q < pts_off[j + 1]; ++q) { pcl::PointXYZRGB pt; pt.x = pts[3 * q]; pt.y = pts[3 * q + 1]; pt.z = pts[3 * q + 2]; p->mvPlanePoints->points.push_back(pt); }
         planes[j] = p; index[p] = j;
     }
-    PlaneMatcher matcher(dTh, aTh, verTh, parTh);
+    DRV_PLANEMATCHER matcher(dTh, aTh, verTh, parTh);
     const int n = matcher.SearchMapByCoefficients(F, planes);
     for (int i = 0; i < n_frame; ++i) {
         match[i] = F.mvpMapPlanes[i] ? index.at(F.mvpMapPlanes[i]) : -1;
@@ -331,7 +349,7 @@ static void set_plane_settings(double angle_info, double dist_info, double par_i
     Config::SetParameterFile("pslam-settings-table");
 }
 
-extern "C" int ref_full_pose_optimization(const pslam_pose_problem* P, const float* Tcw_in, int translation_only, float* Tcw_out, uint8_t* o_pt, uint8_t* o_line,
+extern "C" int DRV(full_pose_optimization)(const pslam_pose_problem* P, const float* Tcw_in, int translation_only, float* Tcw_out, uint8_t* o_pt, uint8_t* o_line,
                                           uint8_t* o_plane, uint8_t* o_par, uint8_t* o_ver) {
     set_plane_settings(P->angle_info, P->dist_info, P->par_info, P->ver_info, P->plane_chi, P->vp_chi);
     World w;
@@ -373,7 +391,7 @@ extern "C" int ref_full_pose_optimization(const pslam_pose_problem* P, const flo
         (is_plane ? F.mvpMapPlanes : is_par ? F.mvpParallelPlanes : F.mvpVerticalPlanes)[i] = planes.back();
     }
     F.SetPose(mat44(Tcw_in));
-    const int n = translation_only ? Optimizer::TranslationOptimization(&F) : Optimizer::PoseOptimization(&F);
+    const int n = translation_only ? DRV_OPTIMIZER::TranslationOptimization(&F) : DRV_OPTIMIZER::PoseOptimization(&F);
     for (int i = 0; i < 16; ++i) Tcw_out[i] = F.mTcw.at<float>(i / 4, i % 4);
     for (int i = 0; i < F.N; ++i) o_pt[i] = F.mvbOutlier[i] ? 1 : 0;
     for (int i = 0; i < F.NL; ++i) o_line[i] = F.mvbLineOutlier[i] ? 1 : 0;
@@ -385,6 +403,7 @@ extern "C" int ref_full_pose_optimization(const pslam_pose_problem* P, const flo
     return n;
 }
 
+#ifndef PSLAM_ADAPTER_BUILD
 // Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*) src/Optimizer.cc:1853-2678 called as it is on a KeyFrame / MapPoint / MapLine / MapPlane graph
 // built from a pslam_lba_problem.  The current key frame is the last one; its covisible list holds every non-fixed key frame plus key frame 0 (which the
 // reference fixes through mnId == 0); the other fixed key frames are left for the function to discover through the observations.  Observation j of a
@@ -534,3 +553,4 @@ extern "C" void ref_full_lines3d_frame(const void* keylines, int n_lines, const 
     F.isLineGood(imGray, imDepth, K);
     for (int i = 0; i < n_lines; ++i) { depth_line[i] = F.mvDepthLine[i]; for (int c = 0; c < 6; ++c) lines3d[6 * i + c] = F.mvLines3D[i](c); }
 }
+#endif  // !PSLAM_ADAPTER_BUILD

@@ -17,8 +17,8 @@ struct LsdBuffers {
     int16_t *d_ix = nullptr, *d_ax = nullptr, *d_iy = nullptr, *d_ay = nullptr;
     float2* d_lut = nullptr; double* d_lgamma = nullptr;
     uint8_t* d_gray = nullptr;        // staging for the host-pointer entry points
-    uint8_t* d_scaled = nullptr; LsdRec* d_rec = nullptr; int32_t* d_smax = nullptr;
-    uint8_t* d_used = nullptr; uint32_t* d_reg = nullptr; uint32_t* d_order = nullptr; int32_t* d_norder = nullptr;
+    uint8_t* d_scaled = nullptr; uint32_t* d_ang = nullptr; float2* d_cs = nullptr; uint32_t* d_gxy = nullptr; int32_t* d_smax = nullptr;
+    uint32_t* d_reg = nullptr; uint32_t* d_order = nullptr; int32_t* d_norder = nullptr;
     double* d_cands = nullptr; double* d_cand_nfa = nullptr; int32_t* d_ncand = nullptr;
     uint32_t* d_fail = nullptr; int32_t* d_nfail = nullptr;      // candidates whose first NFA evaluation fails (queue of k_lsd_improve)
     float4* d_segs = nullptr; double* d_wpn = nullptr; int32_t* d_nsegs = nullptr; int32_t* d_status = nullptr;
@@ -114,8 +114,8 @@ int lsd_alloc(pslam_ctx* c) {
     const size_t npx = (size_t)g.W * g.H, nb = (size_t)B.max_batch;
 #define LA(ptr, bytes) do { const int rc_ = check_cuda(c, cudaMalloc((void**)&(ptr), (bytes)), "cudaMalloc(lsd)"); if (rc_ != PSLAM_OK) { c->lsd = Bp; lsd_free(c); return rc_; } } while (0)
     LA(B.d_ix, g.W * 2); LA(B.d_ax, g.W * 2); LA(B.d_iy, g.H * 2); LA(B.d_ay, g.H * 2); LA(B.d_lut, lut.size() * sizeof(float2)); LA(B.d_lgamma, LSD_LGAMMA_N * 8);
-    LA(B.d_gray, nb * g.w * g.h); LA(B.d_scaled, nb * npx); LA(B.d_rec, nb * npx * sizeof(LsdRec)); LA(B.d_smax, nb * 4);
-    LA(B.d_used, nb * npx); LA(B.d_reg, nb * npx * 4); LA(B.d_order, nb * npx * 4); LA(B.d_norder, nb * 4);
+    LA(B.d_gray, nb * g.w * g.h); LA(B.d_scaled, nb * npx); LA(B.d_ang, nb * npx * 4); LA(B.d_cs, nb * npx * 8); LA(B.d_gxy, nb * npx * 4); LA(B.d_smax, nb * 4);
+    LA(B.d_reg, nb * npx * 4); LA(B.d_order, nb * npx * 4); LA(B.d_norder, nb * 4);
     LA(B.d_fail, nb * g.cand_cap * 4); LA(B.d_nfail, nb * 4);
     LA(B.d_cands, nb * g.cand_cap * 12 * 8); LA(B.d_cand_nfa, nb * g.cand_cap * 8); LA(B.d_ncand, nb * 4);
     LA(B.d_segs, nb * g.seg_cap * sizeof(float4)); LA(B.d_wpn, nb * g.seg_cap * 3 * 8); LA(B.d_nsegs, nb * 4); LA(B.d_status, nb * 4);
@@ -136,8 +136,8 @@ int lsd_alloc(pslam_ctx* c) {
 void lsd_free(pslam_ctx* c) {
     if (!c->lsd) return;
     LsdBuffers& B = *c->lsd;
-    for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_rec,
-                    (void*)B.d_smax, (void*)B.d_used, (void*)B.d_reg, (void*)B.d_order, (void*)B.d_norder, (void*)B.d_segs, (void*)B.d_wpn,
+    for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_ang, (void*)B.d_cs, (void*)B.d_gxy,
+                    (void*)B.d_smax, (void*)B.d_reg, (void*)B.d_order, (void*)B.d_norder, (void*)B.d_segs, (void*)B.d_wpn,
                     (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_fail, (void*)B.d_nfail, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl})
         if (p) cudaFree(p);
     delete c->lsd;
@@ -159,13 +159,12 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     const dim3 gb((g.W + LSD_TW - 1) / LSD_TW, (g.H + LSD_TH - 1) / LSD_TH, nframes);
     PSLAM_LAUNCH(c, "lsd_blur_scale", k_lsd_blur_scale<<<gb, 256, 0, st>>>(g, d_gray, B.d_ix, B.d_ax, B.d_iy, B.d_ay, B.d_scaled));
     const dim3 gg((g.W + 63) / 64, (g.H + 3) / 4, nframes);
-    PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient<<<gg, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_rec, B.d_smax));
+    PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient<<<gg, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_ang, B.d_cs, B.d_gxy, B.d_smax));
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, LSD_ORDER_SMEM));
     PSLAM_LAUNCH(c, "lsd_order", k_lsd_order<<<nframes, LSD_ORDER_THREADS, LSD_ORDER_SMEM, st>>>(g, B.d_scaled, B.d_smax, B.d_order, B.d_norder));
-    PSLAM_CUDA(c, cudaMemsetAsync(B.d_used, 0, (size_t)nframes * npx, st));
     {
         static const int occ = [] { const char* e = std::getenv("PSLAM_LSD_OCC"); const int v = e ? std::atoi(e) : LSD_REGIONS_OCC; return v == 16 || v == 20 || v == 24 || v == 32 ? v : LSD_REGIONS_OCC; }();
-#define LSD_REGIONS_LAUNCH(V) PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<V><<<nframes, 32, 0, st>>>(g, nframes, B.d_rec, B.d_smax, B.d_used, B.d_reg, B.d_order, B.d_norder, \
+#define LSD_REGIONS_LAUNCH(V) PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<V><<<nframes, 32, 0, st>>>(g, nframes, B.d_ang, B.d_cs, B.d_gxy, B.d_smax, B.d_reg, B.d_order, B.d_norder, \
                                                                                                 B.d_cands, B.d_ncand, B.d_status))
         if (occ == 16) LSD_REGIONS_LAUNCH(16); else if (occ == 20) LSD_REGIONS_LAUNCH(20); else if (occ == 24) LSD_REGIONS_LAUNCH(24); else LSD_REGIONS_LAUNCH(32);
 #undef LSD_REGIONS_LAUNCH
@@ -174,8 +173,8 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
         // grid.x covers the candidate capacity; warps beyond a frame's candidate count exit at once
         const dim3 gv((g.cand_cap + 63) / 64, nframes);
         PSLAM_CUDA(c, cudaMemsetAsync(B.d_nfail, 0, (size_t)nframes * 4, st));
-        PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 64, 0, st>>>(g, B.d_rec, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_fail, B.d_nfail));
-        PSLAM_LAUNCH(c, "lsd_improve", k_lsd_improve<<<gv, 64, 0, st>>>(g, B.d_rec, B.d_cands, B.d_cand_nfa, B.d_fail, B.d_nfail));
+        PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 64, 0, st>>>(g, B.d_ang, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_fail, B.d_nfail));
+        PSLAM_LAUNCH(c, "lsd_improve", k_lsd_improve<<<gv, 64, 0, st>>>(g, B.d_ang, B.d_cands, B.d_cand_nfa, B.d_fail, B.d_nfail));
     }
     PSLAM_LAUNCH(c, "lsd_emit", k_lsd_emit<<<nframes, 256, 0, st>>>(g, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_segs, B.d_wpn, B.d_nsegs, B.d_status));
     PSLAM_CUDA(c, cudaGetLastError());
@@ -298,11 +297,11 @@ int pslam_lsd_debug_stage(pslam_ctx* c, int frame, int32_t* dims, uint8_t* scale
     if (dims) { dims[0] = g.W; dims[1] = g.H; }
     if (scaled) PSLAM_CUDA(c, cudaMemcpy(scaled, B.d_scaled + (size_t)frame * npx, npx, cudaMemcpyDeviceToHost));
     if (modgrad || angles) {
-        std::vector<LsdRec> rec(npx);
-        PSLAM_CUDA(c, cudaMemcpy(rec.data(), B.d_rec + (size_t)frame * npx, npx * sizeof(LsdRec), cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> gxy(npx);
+        PSLAM_CUDA(c, cudaMemcpy(gxy.data(), B.d_gxy + (size_t)frame * npx, npx * 4, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < npx; ++i) {
             // same formulas as the device helpers (sqrt and the float polynomial are exactly rounded operations)
-            const int gx = rec[i].gx, gy = rec[i].gy;                 // (rec[i].deg < 0 <=> nrm <= rho, checked by the stage test)
+            const int gx = (int16_t)(gxy[i] & 0xffff), gy = (int16_t)(gxy[i] >> 16);
             const double nrm = std::sqrt((double)(gx * gx + gy * gy) / 4.0);
             if (modgrad) modgrad[i] = nrm;
             if (angles) angles[i] = nrm > g.rho ? (double)host_fast_atan2_deg((float)gx, (float)(-gy)) * LSD_DEG2RAD : -1024.0;

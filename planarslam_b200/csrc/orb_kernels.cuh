@@ -468,7 +468,11 @@ __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int l
     hv[3] = __dp4a(w1, c0, __dp4a(w2, c1, 0u));
 }
 
-__global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTmaParams P, uint8_t* __restrict__ blur, size_t blur_frame_bytes) {
+// The tensor maps are read by the copy engine from `maps`: device global memory (the context's copy, default) or - MAPS_IN_PARAM - the kernel's own
+// __grid_constant__ parameter block.
+template <bool MAPS_IN_PARAM>
+__global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTmaParams P, const CUtensorMap* __restrict__ maps, uint8_t* __restrict__ blur,
+                                                  size_t blur_frame_bytes) {
     __shared__ __align__(128) uint8_t tile[BT_BOX_H][BT_BOX_W];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, strip = tid >> 5, frame = blockIdx.y;
@@ -481,7 +485,7 @@ __global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTm
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, BT_BOX_W * BT_BOX_H);
-        tma_load_3d(&tile[0][0], &P.map[level], x0 - 4, y0 - 3, frame, &bar);     // smem (r, c) <-> image (y0 - 3 + r, x0 - 4 + c)
+        tma_load_3d(&tile[0][0], MAPS_IN_PARAM ? &P.map[level] : maps + level, x0 - 4, y0 - 3, frame, &bar);     // smem (r, c) <-> image (y0 - 3 + r, x0 - 4 + c)
     }
     mbar_wait(&bar, 0);
     // REFLECT_101 halo of border tiles: rows first (whole rows, halo columns included), then columns (all rows): the reflection is separable

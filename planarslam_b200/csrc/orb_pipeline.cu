@@ -151,7 +151,7 @@ int orb_alloc(pslam_ctx* c) {
 }
 
 void orb_free(pslam_ctx* c) {
-    cudaFree(c->d_gray); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_xofs); cudaFree(c->d_xa); cudaFree(c->d_yofs);
+    cudaFree(c->d_gray); cudaFree(c->d_pyr); cudaFree(c->d_blur); cudaFree(c->d_blur_maps); c->d_blur_maps = nullptr; cudaFree(c->d_xofs); cudaFree(c->d_xa); cudaFree(c->d_yofs);
     cudaFree(c->d_ya); cudaFree(c->d_slots); cudaFree(c->d_cell_cnt); cudaFree(c->d_cand); cudaFree(c->d_cand_cnt);
     cudaFree(c->d_nodes); cudaFree(c->d_links); cudaFree(c->d_work); cudaFree(c->d_lvl_kp); cudaFree(c->d_lvl_cnt);
     cudaFree(c->d_kps); cudaFree(c->d_desc); cudaFree(c->d_n);
@@ -204,10 +204,17 @@ int orb_run_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, pslam_keypoint
             }
             P.tile_base[g.nlevels] = base; P.nlevels = g.nlevels;
             c->blur_tma_src = tma_ok ? d_gray : nullptr; c->blur_tma_n = nframes;
+            if (tma_ok) {
+                if (!c->d_blur_maps) PSLAM_CUDA(c, cudaMalloc((void**)&c->d_blur_maps, sizeof P.map));
+                PSLAM_CUDA(c, cudaMemcpyAsync(c->d_blur_maps, P.map, sizeof P.map, cudaMemcpyHostToDevice, st));      // P.map lives in the context: stable until the next re-encode
+            }
         }
     }
     if (tma_ok) {
-        PSLAM_LAUNCH(c, "orb_blur_tma", k_blur_tma<<<dim3(c->blur_tma.tile_base[g.nlevels], nframes), 128, 0, st>>>(c->blur_tma, c->d_blur, (size_t)c->blur_frame_bytes));
+        static const bool in_param = [] { const char* e = std::getenv("PSLAM_TMA_MAPS"); return e && !std::strcmp(e, "param"); }();
+        const dim3 grid(c->blur_tma.tile_base[g.nlevels], nframes);
+        if (in_param) PSLAM_LAUNCH(c, "orb_blur_tma", k_blur_tma<true><<<grid, 128, 0, st>>>(c->blur_tma, c->d_blur_maps, c->d_blur, (size_t)c->blur_frame_bytes));
+        else PSLAM_LAUNCH(c, "orb_blur_tma", k_blur_tma<false><<<grid, 128, 0, st>>>(c->blur_tma, c->d_blur_maps, c->d_blur, (size_t)c->blur_frame_bytes));
     } else
     for (int l = 0; l < g.nlevels; ++l) {
         const LevelGeom& v = g.lv[l];

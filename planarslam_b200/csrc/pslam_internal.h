@@ -105,6 +105,7 @@ struct pslam_ctx {
     int blur_frame_bytes = 0;
     pslam::BlurTmaParams blur_tma;    // tensor maps of the TMA-staged blur (orb_pipeline.cu); valid for (blur_tma_src, blur_tma_n)
     const uint8_t* blur_tma_src = nullptr; int blur_tma_n = 0;
+    CUtensorMap* d_blur_maps = nullptr;      // device copy of blur_tma.map (what the copy engine reads)
     int16_t* d_xofs = nullptr; int16_t* d_xa = nullptr;   // resize tables: source column, (alpha0, alpha1) pairs
     int16_t* d_yofs = nullptr; int16_t* d_ya = nullptr;
     uint32_t* d_slots = nullptr;      // per-cell candidate slots (packed x | y<<11 | score<<22)

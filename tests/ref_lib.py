@@ -268,26 +268,47 @@ def match_lib():
     return _match
 
 
-def ref_search_by_projection_map(fv: dict, m: dict, th: float, nnratio: float, matches0: np.ndarray):
-    """Tracking::SearchLocalPoints' frustum loop + ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) by the reference's own code.
-    Same arguments and returns as oracle_lib.search_by_projection_map."""
+_adapter = None
+
+
+def adapter_lib():
+    """oracle/_ref/libadapter_ref.so: the entry points of match_driver.cc with the product's reference-typed adapter (include/pslam_reference_adapter.hpp) in place
+    of the reference's functions (adp_* symbols; oracle/ref/adapter_driver.cc).  Needs libmatch_ref.so and the CUDA library."""
+    global _adapter
+    if _adapter is None and match_lib() is not None:
+        path = os.path.join(REF_DIR, "libadapter_ref.so")
+        if not os.path.exists(path) and os.path.isdir("/root/reference/src"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "adapter"], check=True, stdout=subprocess.DEVNULL)
+        _adapter = C.CDLL(path) if os.path.exists(path) else None
+    return _adapter
+
+
+def _impl(impl):
+    return (match_lib(), "ref_") if impl == "ref" else (adapter_lib(), "adp_")
+
+
+def ref_search_by_projection_map(fv: dict, m: dict, th: float, nnratio: float, matches0: np.ndarray, impl: str = "ref"):
+    """Tracking::SearchLocalPoints' frustum loop + ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th) by the reference's own code
+    (impl="adp": by the product's adapter class of the same signature, on the same objects).  Same arguments and returns as oracle_lib.search_by_projection_map."""
     import oracle_lib
-    L = match_lib()
-    L.ref_search_by_projection_map.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "search_by_projection_map")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
     matches = np.ascontiguousarray(matches0, np.int32).copy()
     in_view = np.zeros(max(m["n"], 1), np.uint8)
-    n = L.ref_search_by_projection_map(C.byref(oracle_lib.frame_view_struct(fv)), C.byref(oracle_lib.map_points_struct(m)), th, nnratio, matches.ctypes.data,
+    n = fn(C.byref(oracle_lib.frame_view_struct(fv)), C.byref(oracle_lib.map_points_struct(m)), th, nnratio, matches.ctypes.data,
                                        in_view.ctypes.data)
     return n, matches, in_view[:m["n"]]
 
 
-def ref_search_by_projection_last(fv: dict, lf: dict, m: dict, th: float, mono: bool, check_ori: bool, matches0: np.ndarray):
-    """ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) by the reference's own code."""
+def ref_search_by_projection_last(fv: dict, lf: dict, m: dict, th: float, mono: bool, check_ori: bool, matches0: np.ndarray, impl: str = "ref"):
+    """ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) by the reference's own code (impl="adp": the product's adapter)."""
     import oracle_lib
-    L = match_lib()
-    L.ref_search_by_projection_last.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "search_by_projection_last")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]
     matches = np.ascontiguousarray(matches0, np.int32).copy()
-    n = L.ref_search_by_projection_last(C.byref(oracle_lib.frame_view_struct(fv)), C.byref(oracle_lib.last_frame_struct(lf)), C.byref(oracle_lib.map_points_struct(m)),
+    n = fn(C.byref(oracle_lib.frame_view_struct(fv)), C.byref(oracle_lib.last_frame_struct(lf)), C.byref(oracle_lib.map_points_struct(m)),
                                         th, int(mono), int(check_ori), matches.ctypes.data)
     return n, matches
 
@@ -339,29 +360,31 @@ def ref_line_search_by_projection(frame: dict, map_lines: dict, th: float, nnrat
     return n, assigned[:nf]
 
 
-def ref_plane_match(T, fc, mc, bad, off, pts, dTh, aTh, verTh, parTh):
-    """PlaneMatcher::SearchMapByCoefficients by the reference's own code.  Returns (nmatches, match, vertical, parallel)."""
-    L = match_lib()
-    L.ref_plane_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 3
+def ref_plane_match(T, fc, mc, bad, off, pts, dTh, aTh, verTh, parTh, impl: str = "ref"):
+    """PlaneMatcher::SearchMapByCoefficients by the reference's own code (impl="adp": the product's adapter).  Returns (nmatches, match, vertical, parallel)."""
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "plane_match")
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p] * 3
     T, fc, mc = np.ascontiguousarray(T, np.float32), np.ascontiguousarray(fc, np.float32), np.ascontiguousarray(mc, np.float32)
     bad, off, pts = np.ascontiguousarray(bad, np.uint8), np.ascontiguousarray(off, np.int32), np.ascontiguousarray(pts, np.float32)
     om, ov, op = [np.zeros(max(len(fc), 1), np.int32) for _ in range(3)]
-    n = L.ref_plane_match(T.ctypes.data, len(fc), fc.ctypes.data, len(mc), mc.ctypes.data, bad.ctypes.data, off.ctypes.data, pts.ctypes.data, dTh, aTh, verTh, parTh,
+    n = fn(T.ctypes.data, len(fc), fc.ctypes.data, len(mc), mc.ctypes.data, bad.ctypes.data, off.ctypes.data, pts.ctypes.data, dTh, aTh, verTh, parTh,
                           om.ctypes.data, ov.ctypes.data, op.ctypes.data)
     return n, om[:len(fc)], ov[:len(fc)], op[:len(fc)]
 
 
-def ref_full_pose_optimization(p: dict, translation_only: bool = False):
+def ref_full_pose_optimization(p: dict, translation_only: bool = False, impl: str = "ref"):
     """Optimizer::PoseOptimization(Frame*) / TranslationOptimization(Frame*) THEMSELVES (src/Optimizer.cc compiled unmodified into libmatch_ref.so) on a
     Frame built from a planarslam_b200.synth_pose problem.  Returns dict(Tcw float32 4x4 - the reference writes the pose back as float -, n_inliers, outlier_*)."""
     import oracle_lib
-    L = match_lib()
-    L.ref_full_pose_optimization.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+    lib, pre = _impl(impl)                     # impl="adp": pslam_adapter::ref::Optimizer::PoseOptimization(Frame*) on the same Frame
+    fn = getattr(lib, pre + "full_pose_optimization")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
     s = oracle_lib.pose_problem_struct(p)
     T0 = np.ascontiguousarray(p["Tcw0"], np.float32)
     T = np.zeros((4, 4), np.float32)
     o = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes, s.n_par, s.n_ver)]
-    n = L.ref_full_pose_optimization(C.byref(s), T0.ctypes.data, int(translation_only), T.ctypes.data, *[a.ctypes.data for a in o])
+    n = fn(C.byref(s), T0.ctypes.data, int(translation_only), T.ctypes.data, *[a.ctypes.data for a in o])
     return dict(Tcw=T, n_inliers=n, outlier_pt=o[0][:s.n_points], outlier_line=o[1][:s.n_lines], outlier_plane=o[2][:s.n_planes],
                 outlier_par=o[3][:s.n_par], outlier_ver=o[4][:s.n_ver])
 

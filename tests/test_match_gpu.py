@@ -18,7 +18,8 @@ def _oracle(q, t):
     L.orc_bf_knn2(q.ctypes.data, nq, t.ctypes.data, len(t), idx.ctypes.data, dist.ctypes.data)
     d1 = np.ascontiguousarray(dist[:nq, 0])
     keep = np.zeros(max(nq, 1), np.int32)
-    n = L.orc_match_gate(d1.ctypes.data, nq, keep.ctypes.data)
+    # an empty train set yields no DMatch at all (cv::BFMatcher::match, src/ORBmatcher.cc:1346-1366): MatchORBPoints keeps nothing
+    n = L.orc_match_gate(d1.ctypes.data, nq, keep.ctypes.data) if len(t) else 0
     return idx[:nq], dist[:nq], keep[:n]
 
 
