@@ -227,6 +227,23 @@ int pslam_track_sequence_dev(pslam_ctx* ctx, const uint8_t* d_gray, const uint16
 int pslam_track_sequence(pslam_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int nframes, const pslam_track_params* params, const float* Tcw0,
                          float* Tcw_out, int32_t* stats /* may be NULL */);
 
+/* ---- Key-frame descriptor exchange over NVLink peer memory, fused with the Hamming matcher -------------------
+ * The one exchange step of the multi-GPU layout: every rank (one process per GPU) publishes the ORB block of a key frame - descriptors [n][32], key points
+ * [n] (28 B), count - into a record in ITS OWN HBM; peers map the records through CUDA IPC (NVLink / NVSwitch P2P) and pslam_exchange_match_dev finds, for
+ * every query descriptor, the two nearest rows over the concatenation rank 0 | rank 1 | ... by reading the peers' records in place: the CTA working on peer
+ * p starts as soon as p's epoch flag lands, no gathered copy is built.  Same result as pslam_hamming_knn2_batch on the concatenated set (cv::BFMatcher::knnMatch
+ * k = 2 - the matcher behind KeyFrameDatabase::DetectLoopCandidates / LoopClosing::ComputeSim3's candidates, src/KeyFrameDatabase.cc:76-197, src/LoopClosing.cc:231-400).
+ *   create   allocates `slots` records of capacity cap_kp on the context's device and returns its CUDA IPC handle (PSLAM_IPC_HANDLE_BYTES bytes)
+ *   attach   handles = the handles of all ranks in rank order (exchanged by the caller, e.g. torch.distributed.all_gather); world = 1 needs no handles
+ *   publish  enqueues the copy + release of `epoch` (> 0) on the context's stream; a slot may be re-published once every rank has matched the old epoch
+ *   match    enqueues the fused wait + match; idx [capq][2] = row in the concatenation (-1: none), dist [capq][2] (256: none)
+ * Errors: PSLAM_E_NCCL when a peer record cannot be mapped (no P2P path). */
+#define PSLAM_IPC_HANDLE_BYTES 64
+int pslam_exchange_create(pslam_ctx* ctx, int cap_kp, int slots, void* ipc_handle_out);
+int pslam_exchange_attach(pslam_ctx* ctx, int world, int rank, const void* handles /* [world][PSLAM_IPC_HANDLE_BYTES] */);
+int pslam_exchange_publish_dev(pslam_ctx* ctx, int slot, const uint8_t* d_desc, const pslam_keypoint* d_kps /* may be NULL */, const int32_t* d_n, uint32_t epoch);
+int pslam_exchange_match_dev(pslam_ctx* ctx, int slot, uint32_t epoch, const uint8_t* d_qdesc, const int32_t* d_nq, int capq, int32_t* d_idx, int32_t* d_dist);
+
 /* ---- Plane association -------------------------------------------------------------------------
  * Replaces  int PlaneMatcher::SearchMapByCoefficients(Frame& pF, const vector<MapPlane*>& vpMapPlanes)   src/PlaneMatcher.cpp:10-67
  * (with Frame::ComputePlaneWorldCoeff, src/Frame.cc:815-820).  frame_coef: mvPlaneCoefficients [n_frame][4]; map_coef: GetWorldPos()
@@ -359,6 +376,14 @@ int pslam_lsd_set_rect_enumeration(pslam_ctx* ctx, int mode);
 /* cv::LineSegmentDetector::detect on nframes frames: segs [nframes][cap][4] float (x1 y1 x2 y2), wpn [nframes][cap][3] double
  * (width, precision, log-NFA; -1 unless refine == 2), n [nframes].  PSLAM_E_CAPACITY when a frame has more than cap segments. */
 int pslam_lsd_detect_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int refine, float* segs, double* wpn, int cap, int32_t* n);
+/* The whole  void LineSegment::ExtractLineSegment(const Mat& img, vector<KeyLine>&, Mat& ldesc, vector<Vector3d>& lineFunctions, ...)
+ * include/LSDextractor.h:349, src/LSDextractor.cpp:13-39: detector, keep-max_lines filter, LBD descriptors (BinaryDescriptor::compute: desc [nframes][max_lines][32] =
+ * the rows of ldesc / Frame::mLdesc; lbd72 [nframes][max_lines][72] optional, the float LBD vectors), line functions.  The LBD logic follows the published
+ * algorithm (upstream source absent: parity unpinned, see oracle/lbd.h); its OpenCV primitives are pinned to cv2 4.13. */
+int pslam_lines_extract_describe_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int max_lines, pslam_keyline* kl, double* line_functions, uint8_t* desc,
+                                       float* lbd72 /* may be NULL */, int32_t* n);
+int pslam_lines_extract_describe_batch_dev(pslam_ctx* ctx, const uint8_t* d_gray, int nframes, int max_lines, pslam_keyline* d_kl, double* d_line_functions,
+                                           uint8_t* d_desc, int32_t* d_n);
 /* ExtractLineSegment without descriptors: kl [nframes][max_lines], line_functions [nframes][max_lines][3], n [nframes]. */
 int pslam_lines_extract_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int max_lines, pslam_keyline* kl, double* line_functions,
                               int32_t* n);

@@ -99,3 +99,13 @@ extern "C" void orc_lines_in_frustum(const float* frame, int n, const double* po
     F.log_scale_factor = frame[24];
     oracle::lines_in_frustum(F, n, pos, normal, max_distance, min_distance, cos_limit, in_view, proj, level, view_cos);
 }
+
+#include "lbd.h"
+extern "C" {
+void orc_gaussian_blur_5x5_s1(const uint8_t* img, int w, int h, int stride, uint8_t* dst) { oracle::gaussian_blur_5x5_s1_u8(oracle::Img8{img, w, h, stride}, dst); }
+void orc_sobel3_s16(const uint8_t* img, int w, int h, int16_t* dx, int16_t* dy) { oracle::sobel3_s16(img, w, h, dx, dy); }
+// keylines: KeyLine[n] (68 bytes each); lbd72: float[n][72] or null; desc: uint8[n][32]
+void orc_lbd_compute(const uint8_t* img, int w, int h, int stride, const void* keylines, int n, float* lbd72, uint8_t* desc) {
+    oracle::lbd_compute(oracle::Img8{img, w, h, stride}, (const oracle::KeyLine*)keylines, n, lbd72, desc);
+}
+}

@@ -82,6 +82,7 @@ void pslam_destroy(pslam_ctx* c) {
     lsd_free(c);
     search_free(c);
     track_free(c);
+    exchange_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }

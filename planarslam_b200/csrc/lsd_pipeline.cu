@@ -8,6 +8,7 @@
 #include <string>
 
 #include "lsd_kernels.cuh"
+#include "lbd_kernels.cuh"
 
 namespace pslam {
 
@@ -23,6 +24,7 @@ struct LsdBuffers {
     uint32_t* d_fail = nullptr; int32_t* d_nfail = nullptr;      // candidates whose first NFA evaluation fails (queue of k_lsd_improve)
     float4* d_segs = nullptr; double* d_wpn = nullptr; int32_t* d_nsegs = nullptr; int32_t* d_status = nullptr;
     LsdKeyLine* d_kl = nullptr; double* d_lf = nullptr; int32_t* d_nkl = nullptr;
+    int16_t *d_dx = nullptr, *d_dy = nullptr; float *d_glocal = nullptr, *d_gglobal = nullptr; uint8_t* d_ldesc = nullptr; float* d_lbd72 = nullptr;   // LBD (lbd_kernels.cuh)
     std::vector<int32_t> h_n, h_status;
 };
 
@@ -138,7 +140,8 @@ void lsd_free(pslam_ctx* c) {
     LsdBuffers& B = *c->lsd;
     for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_ang, (void*)B.d_cs, (void*)B.d_gxy,
                     (void*)B.d_smax, (void*)B.d_reg, (void*)B.d_order, (void*)B.d_norder, (void*)B.d_segs, (void*)B.d_wpn,
-                    (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_fail, (void*)B.d_nfail, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl})
+                    (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_fail, (void*)B.d_nfail, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl, (void*)B.d_dx, (void*)B.d_dy, (void*)B.d_glocal, (void*)B.d_gglobal,
+                    (void*)B.d_ldesc, (void*)B.d_lbd72})
         if (p) cudaFree(p);
     delete c->lsd;
     c->lsd = nullptr;
@@ -248,11 +251,61 @@ static int lsd_ensure_kl(pslam_ctx* c, int max_lines) {
     if (B.d_kl) cudaFree(B.d_kl);
     if (B.d_lf) cudaFree(B.d_lf);
     if (B.d_nkl) cudaFree(B.d_nkl);
-    B.d_kl = nullptr; B.d_lf = nullptr; B.d_nkl = nullptr; B.max_lines_cap = 0;
+    if (B.d_ldesc) cudaFree(B.d_ldesc);
+    if (B.d_lbd72) cudaFree(B.d_lbd72);
+    B.d_kl = nullptr; B.d_lf = nullptr; B.d_nkl = nullptr; B.d_ldesc = nullptr; B.d_lbd72 = nullptr; B.max_lines_cap = 0;
     PSLAM_CUDA(c, cudaMalloc((void**)&B.d_kl, (size_t)B.max_batch * max_lines * sizeof(LsdKeyLine)));
     PSLAM_CUDA(c, cudaMalloc((void**)&B.d_lf, (size_t)B.max_batch * max_lines * 24));
     PSLAM_CUDA(c, cudaMalloc((void**)&B.d_nkl, (size_t)B.max_batch * 4));
+    PSLAM_CUDA(c, cudaMalloc((void**)&B.d_ldesc, (size_t)B.max_batch * max_lines * 32));
+    PSLAM_CUDA(c, cudaMalloc((void**)&B.d_lbd72, (size_t)B.max_batch * max_lines * 72 * 4));
     B.max_lines_cap = max_lines;
+    return PSLAM_OK;
+}
+
+// BinaryDescriptor::compute on the key lines the detector left on the device (src/LSDextractor.cpp:28)
+static int lbd_describe_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int max_lines, const LsdKeyLine* d_kl, const int32_t* d_n, uint8_t* d_desc, float* d_lbd72) {
+    LsdBuffers& B = *c->lsd;
+    const LsdGeom& g = B.g;
+    cudaStream_t st = c->stream;
+    if (!B.d_dx) {
+        const size_t bytes = (size_t)B.max_batch * g.w * g.h * sizeof(int16_t);
+        PSLAM_CUDA(c, cudaMalloc((void**)&B.d_dx, bytes)); PSLAM_CUDA(c, cudaMalloc((void**)&B.d_dy, bytes));
+        PSLAM_CUDA(c, cudaMalloc((void**)&B.d_glocal, LBD_WIDTH * 3 * 4)); PSLAM_CUDA(c, cudaMalloc((void**)&B.d_gglobal, LBD_HEIGHT * 4));
+        float gl[LBD_WIDTH * 3], gg[LBD_HEIGHT];               // the two Gaussian windows, evaluated with the host libm like upstream (integer-division sigmas)
+        { const double u = (double)((LBD_WIDTH * 3 - 1) / 2), sigma = (double)((LBD_WIDTH * 2 + 1) / 2), inv = -1 / (2 * sigma * sigma);
+          for (int i = 0; i < LBD_WIDTH * 3; ++i) { const double d = i - u; gl[i] = (float)std::exp(d * d * inv); } }
+        { const double u = (double)((LBD_HEIGHT - 1) / 2), sigma = u, inv = -1 / (2 * sigma * sigma);
+          for (int i = 0; i < LBD_HEIGHT; ++i) { const double d = i - u; gg[i] = (float)std::exp(d * d * inv); } }
+        PSLAM_CUDA(c, cudaMemcpy(B.d_glocal, gl, sizeof gl, cudaMemcpyHostToDevice));
+        PSLAM_CUDA(c, cudaMemcpy(B.d_gglobal, gg, sizeof gg, cudaMemcpyHostToDevice));
+    }
+    const dim3 gb((g.w + LBD_TW - 1) / LBD_TW, (g.h + LBD_TH - 1) / LBD_TH, nframes);
+    PSLAM_LAUNCH(c, "lbd_gradients", k_lbd_gradients<<<gb, 256, 0, st>>>(d_gray, g.w, g.h, B.d_dx, B.d_dy));
+    PSLAM_LAUNCH(c, "lbd_lines", k_lbd_lines<<<dim3(max_lines, nframes), 64, 0, st>>>(B.d_dx, B.d_dy, g.w, g.h, d_kl, d_n, max_lines, B.d_glocal, B.d_gglobal, d_desc, d_lbd72));
+    PSLAM_CUDA(c, cudaGetLastError());
+    return PSLAM_OK;
+}
+
+int pslam_lines_extract_describe_batch_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int max_lines, pslam_keyline* d_kl, double* d_lf, uint8_t* d_desc, int32_t* d_n) {
+    if (!c) return PSLAM_E_INVALID;
+    if (!d_desc) return set_error(c, PSLAM_E_INVALID, "null descriptor buffer");
+    int rc = pslam_lines_extract_batch_dev(c, d_gray, nframes, max_lines, d_kl, d_lf, d_n);
+    if (rc != PSLAM_OK) return rc;
+    return lbd_describe_dev(c, d_gray, nframes, max_lines, (const LsdKeyLine*)d_kl, d_n, d_desc, nullptr);
+}
+
+int pslam_lines_extract_describe_batch(pslam_ctx* c, const uint8_t* gray, int nframes, int max_lines, pslam_keyline* kl, double* lf, uint8_t* desc, float* lbd72, int32_t* n) {
+    if (!c) return PSLAM_E_INVALID;
+    if (!desc) return set_error(c, PSLAM_E_INVALID, "null descriptor buffer");
+    int rc = pslam_lines_extract_batch(c, gray, nframes, max_lines, kl, lf, n);       // uploads the frames into the context's staging buffer and leaves the key lines there
+    if (rc != PSLAM_OK) return rc;
+    LsdBuffers& B = *c->lsd;
+    if ((rc = lbd_describe_dev(c, B.d_gray, nframes, max_lines, B.d_kl, B.d_nkl, B.d_ldesc, B.d_lbd72)) != PSLAM_OK) return rc;
+    cudaStream_t st = c->stream;
+    PSLAM_CUDA(c, cudaMemcpyAsync(desc, B.d_ldesc, (size_t)nframes * max_lines * 32, cudaMemcpyDeviceToHost, st));
+    if (lbd72) PSLAM_CUDA(c, cudaMemcpyAsync(lbd72, B.d_lbd72, (size_t)nframes * max_lines * 72 * 4, cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaStreamSynchronize(st));
     return PSLAM_OK;
 }
 

@@ -48,6 +48,20 @@ class LineSegment:
         out = [(kl[i, :cnt[i]].copy(), lf[i, :cnt[i]].copy()) for i in range(n)]
         return out[0] if g.ndim == 2 else out
 
+    # ExtractLineSegment with the LBD descriptors (ldesc / Frame::mLdesc): (keylines, line functions, desc uint8 [n][32], lbd float32 [n][72]) per frame
+    def ExtractLineSegmentWithDescriptors(self, gray: np.ndarray, max_lines: int = 40):
+        g = np.ascontiguousarray(gray, np.uint8)
+        frames = g[None] if g.ndim == 2 else g
+        n = len(frames)
+        L = self.ctx.L
+        L.pslam_lines_extract_describe_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        kl, lf, cnt = np.zeros((n, max_lines), KEYLINE_DTYPE), np.zeros((n, max_lines, 3)), np.zeros(n, np.int32)
+        desc, lbd = np.zeros((n, max_lines, 32), np.uint8), np.zeros((n, max_lines, 72), np.float32)
+        self.ctx.check(L.pslam_lines_extract_describe_batch(self.ctx.h, frames.ctypes.data, n, max_lines, kl.ctypes.data, lf.ctypes.data, desc.ctypes.data,
+                                                            lbd.ctypes.data, cnt.ctypes.data))
+        out = [(kl[i, :cnt[i]].copy(), lf[i, :cnt[i]].copy(), desc[i, :cnt[i]].copy(), lbd[i, :cnt[i]].copy()) for i in range(n)]
+        return out[0] if g.ndim == 2 else out
+
     def debug_stage(self, frame: int = 0):
         dims = np.zeros(2, np.int32)
         self.ctx.check(self.ctx.L.pslam_lsd_debug_stage(self.ctx.h, frame, dims.ctypes.data, None, None, None, None, None))

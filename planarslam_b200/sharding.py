@@ -64,3 +64,48 @@ class KeyframeDescriptorExchange:
     @staticmethod
     def to_global(rank: int, local: int, offs: np.ndarray) -> int:
         return int(offs[rank] + local)
+
+
+class PeerDescriptorExchange:
+    """The exchange step on hardware (include/pslam_abi.h pslam_exchange_*): every rank publishes key-frame ORB blocks into records in its own HBM, the peers map
+    them through CUDA IPC (NVLink / NVSwitch P2P), and `match` runs the fused wait-on-flag + Hamming k = 2 kernel that reads the peers' records in place.
+    torch.distributed only carries the 64-byte IPC handles (once) and the epoch barriers that guard slot reuse."""
+
+    def __init__(self, ctx, cap: int, slots: int = 1, group=None):
+        import ctypes as C
+        import torch
+        self.C, self.torch, self.ctx, self.cap, self.slots, self.group = C, torch, ctx, int(cap), int(slots), group
+        L = ctx.L
+        L.pslam_exchange_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pslam_exchange_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pslam_exchange_publish_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.pslam_exchange_match_dev.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        handle = np.zeros(64, np.uint8)
+        ctx.check(L.pslam_exchange_create(ctx.h, self.cap, self.slots, handle.ctypes.data))
+        import torch.distributed as dist
+        self.dist = dist if dist.is_available() and dist.is_initialized() else None
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        handles = handle[None]
+        if self.world > 1:
+            dev = torch.device("cuda", ctx.cfg.device)
+            mine = torch.from_numpy(handle).to(dev)
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+            self.dist.all_gather_into_tensor(allh, mine, group=group)
+            handles = allh.cpu().numpy().reshape(self.world, 64)
+        handles = np.ascontiguousarray(handles)
+        ctx.check(L.pslam_exchange_attach(ctx.h, self.world, self.rank, handles.ctypes.data))
+
+    def publish(self, slot: int, d_desc, d_n, epoch: int, d_kps=None):
+        """d_desc [cap, 32] uint8 and d_n int32 [1] device tensors (the ORB output of a key frame); enqueued on the context's stream."""
+        self.ctx.check(self.ctx.L.pslam_exchange_publish_dev(self.ctx.h, slot, d_desc.data_ptr(), d_kps.data_ptr() if d_kps is not None else None, d_n.data_ptr(), epoch))
+
+    def match(self, slot: int, epoch: int, d_q, d_nq, d_idx, d_dist):
+        """k = 2 nearest rows of every query over the concatenation of all ranks' records of `slot` (waits inside the kernel for each peer's epoch flag)."""
+        self.ctx.check(self.ctx.L.pslam_exchange_match_dev(self.ctx.h, slot, epoch, d_q.data_ptr(), d_nq.data_ptr(), int(d_q.shape[0]), d_idx.data_ptr(), d_dist.data_ptr()))
+
+    def barrier(self):
+        """Call before re-publishing a slot: every rank must have finished matching the old epoch."""
+        self.torch.cuda.synchronize()
+        if self.dist and self.world > 1:
+            self.dist.barrier(group=self.group)

@@ -458,3 +458,29 @@ def compute_stereo_from_rgbd(keys_xy, keys_un_xy, depth, bf: float):
     ur, dz = np.zeros(n, np.float32), np.zeros(n, np.float32)
     L.orc_compute_stereo_from_rgbd(n, k.ctypes.data, ku.ctypes.data, d.ctypes.data, d.shape[1], bf, ur.ctypes.data, dz.ctypes.data)
     return ur, dz
+
+
+def lbd_compute(gray: np.ndarray, keylines: np.ndarray):
+    """Oracle BinaryDescriptor::compute (oracle/lbd.cc; descriptor logic parity-unpinned, see oracle/lbd.h).  Returns (lbd float32 [n][72], desc uint8 [n][32])."""
+    L = lib()
+    L.orc_lbd_compute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_lbd_compute.restype = None
+    g = np.ascontiguousarray(gray, np.uint8)
+    kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+    n = len(kl)
+    f, d = np.zeros((max(n, 1), 72), np.float32), np.zeros((max(n, 1), 32), np.uint8)
+    L.orc_lbd_compute(g.ctypes.data, g.shape[1], g.shape[0], g.strides[0], kl.ctypes.data, n, f.ctypes.data, d.ctypes.data)
+    return f[:n], d[:n]
+
+
+def lbd_prims(gray: np.ndarray):
+    """(GaussianBlur 5x5 s=1, Sobel dx, Sobel dy of the blurred image) as the LBD oracle computes them."""
+    L = lib()
+    L.orc_gaussian_blur_5x5_s1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.orc_sobel3_s16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    g = np.ascontiguousarray(gray, np.uint8)
+    h, w = g.shape
+    b, dx, dy = np.zeros((h, w), np.uint8), np.zeros((h, w), np.int16), np.zeros((h, w), np.int16)
+    L.orc_gaussian_blur_5x5_s1(g.ctypes.data, w, h, g.strides[0], b.ctypes.data)
+    L.orc_sobel3_s16(b.ctypes.data, w, h, dx.ctypes.data, dy.ctypes.data)
+    return b, dx, dy
