@@ -453,13 +453,13 @@ __global__ void __launch_bounds__(256) k_blur_level(const uint8_t* __restrict__ 
     }
 }
 
-// K4a (TMA): the same blur, every level of every frame in ONE launch.  A CTA owns a 128 x 64 output tile; its 144 x 70 source box
-// (3-pixel halo, 4-byte aligned columns) is fetched by one cp.async.bulk.tensor copy into shared memory (zero fill outside the image),
+// K4a (TMA): the same blur, every level of every frame in ONE launch.  A CTA owns a 128 x 64 output tile; its 160 x 70 source box
+// (3-pixel halo; starting 16 columns left of the tile so that the box start is 16-byte aligned) is fetched by one cp.async.bulk.tensor copy into shared memory (zero fill outside the image),
 // the REFLECT_101 halo of border tiles is rebuilt in shared memory from the interior, and each thread slides a 7-row window down a
 // 4-pixel-wide, 16-row strip: horizontal taps by two __dp4a per pixel on byte windows cut from three aligned words, vertical taps on
 // the 8.8 sums held in registers, one 32-bit store per row.  Arithmetic identical to k_blur_level (8.8 -> 16.16, round half up).
 __device__ __forceinline__ void blur_hrow(const uint8_t* __restrict__ row, int lane, uint32_t hv[4]) {
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row) + lane;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(row) + lane + (BT_X_PAD - 4) / 4;        // bytes x - 4 .. x + 7 of the row, x = x0 + 4 lane
     const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
     const uint32_t c0 = 18u | (34u << 8) | (48u << 16) | (56u << 24), c1 = 48u | (34u << 8) | (18u << 16);
     hv[0] = __dp4a(__funnelshift_r(w0, w1, 8), c0, __dp4a(__funnelshift_r(w1, w2, 8), c1, 0u));
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTm
     __syncthreads();
     if (tid == 0) {
         mbar_expect_tx(&bar, BT_BOX_W * BT_BOX_H);
-        tma_load_3d(&tile[0][0], MAPS_IN_PARAM ? &P.map[level] : maps + level, x0 - 4, y0 - 3, frame, &bar);     // smem (r, c) <-> image (y0 - 3 + r, x0 - 4 + c)
+        tma_load_3d(&tile[0][0], MAPS_IN_PARAM ? &P.map[level] : maps + level, x0 - BT_X_PAD, y0 - 3, frame, &bar);     // smem (r, c) <-> image (y0 - 3 + r, x0 - 16 + c)
     }
     mbar_wait(&bar, 0);
     // REFLECT_101 halo of border tiles: rows first (whole rows, halo columns included), then columns (all rows): the reflection is separable
@@ -505,9 +505,9 @@ __global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTm
         for (int i = tid; i < 6 * BT_BOX_H; i += 128) {
             const int r = i / 6, k = i - r * 6;
             const int X = k < 3 ? k - 3 : w + (k - 3);
-            const int c = X - (x0 - 4);
+            const int c = X - (x0 - BT_X_PAD);
             if (c < 0 || c >= BT_BOX_W) continue;
-            const int cs = (X < 0 ? -X : 2 * (w - 1) - X) - (x0 - 4);
+            const int cs = (X < 0 ? -X : 2 * (w - 1) - X) - (x0 - BT_X_PAD);
             if (cs < 0 || cs >= BT_BOX_W) continue;
             tile[r][c] = tile[r][cs];
         }
