@@ -137,6 +137,26 @@ int pslam_peac_run_batch(pslam_ctx* ctx, const uint16_t* depth, int nframes, int
 int pslam_peac_run_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes,
                              int32_t* d_nplanes, int32_t* d_member_idx, int32_t* d_member_off);
 
+/* ---- Plane post-processing of Frame::ComputePlanes (src/Frame.cc:647-753) + Frame::MaxPointDistanceFromPlane (:755-813) ----------------------
+ * What turns the PEAC result into  mvPlanePoints / mvPlaneCoefficients  and  vSurfaceNormal:
+ *   per PEAC plane: pcl::VoxelGrid(0.1) of its member points -> reject the plane when a voxel centroid is farther than dist_th (Plane.DistanceThreshold) from
+ *   (n, -n . c) -> pcl::SACSegmentation plane RANSAC + least-squares refit, sign of d kept (MaxPointDistanceFromPlane) -> coefficients + voxel cloud;
+ *   pcl::IntegralImageNormalEstimation(AVERAGE_3D_GRADIENT, 0.05, 10) on the 3x sub-sampled cloud, every 2nd row / column -> surface normals.
+ * PCL is not part of the reference tree: the three algorithms are restated (oracle/planepost.cc, parity unpinned upstream; voxel centroids are an order-free
+ * fixed-point mean - PCL's float sum runs in the unspecified order std::sort leaves).
+ * Outputs per frame: n_kept; src [maxp] = PEAC plane index of every kept plane (PEAC order); coef [maxp][4] float = mvPlaneCoefficients; pt_off [maxp + 1] +
+ * pts [cap_pts][3] = mvPlanePoints concatenated; normals8 [pslam_surface_normals_count()][8] = SurfaceNormal {normal xyz (NaN where PCL leaves NaN), cameraPosition
+ * xyz, FramePosition xy}.  maxp = pslam_peac_max_planes(); at most pslam_planes_post_max_points() voxels per plane (PSLAM_E_CAPACITY beyond). */
+int pslam_surface_normals_count(const pslam_ctx* ctx);
+int pslam_planes_post_max_points(const pslam_ctx* ctx);
+int pslam_planes_post_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, const pslam_plane* d_planes, const int32_t* d_nplanes, const int32_t* d_member_idx,
+                                const int32_t* d_member_off, float dist_th, int32_t* d_n_kept, int32_t* d_src, float* d_coef, int32_t* d_pt_off, float* d_pts, int cap_pts,
+                                int32_t* d_status);
+int pslam_surface_normals_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, float* d_normals8);
+/* PEAC + post-processing + normals on host depth images (the whole Frame::ComputePlanes); normals8 may be NULL */
+int pslam_compute_planes_batch(pslam_ctx* ctx, const uint16_t* depth, int nframes, float dist_th, int32_t* n_kept, int32_t* src, float* coef, int32_t* pt_off, float* pts,
+                               int cap_pts, float* normals8);
+
 /* Stage outputs of the most recent PEAC call (host buffers; synchronises): per 10x10 block the nine running sums
  * (sx sy sz sxx syy szz sxy syz sxz), {center[3], normal[3], mse, curvature}, point count and the "node kept" flag;
  * the eroded block -> coarse plane map and the number of coarse planes before the last merge. */

@@ -74,3 +74,28 @@ int orc_heap_selftest(const double* keys, int n, const int* ops, int nops) {
     return bad;
 }
 }
+
+#include "planepost.h"
+extern "C" {
+// Frame::ComputePlanes post-processing on the PEAC result `p`: returns the number of kept planes; src [n], coef [n][4], npts [n], pts (concatenated xyz, capacity
+// cap_pts points), stats [n][2] = RANSAC inliers / iterations
+int orc_planes_post(void* p, const uint16_t* depth, int w, int h, float fx, float fy, float cx, float cy, float scale, double dist_th, int32_t* src, float* coef,
+                    int32_t* npts, float* pts, int cap_pts, int32_t* stats) {
+    std::vector<oracle::PostPlane> out;
+    oracle::compute_planes_post(depth, w, h, oracle::PlanePostParams{fx, fy, cx, cy, scale, dist_th}, *(PeacResult*)p, out);
+    int tot = 0;
+    for (size_t i = 0; i < out.size(); ++i) {
+        src[i] = out[i].src; std::memcpy(coef + 4 * i, out[i].coef, 16); npts[i] = (int)out[i].points.size() / 3; stats[2 * i] = out[i].n_inliers; stats[2 * i + 1] = out[i].n_iterations;
+        for (size_t k = 0; k < out[i].points.size() / 3 && tot < cap_pts; ++k, ++tot) std::memcpy(pts + 3 * (size_t)tot, &out[i].points[3 * k], 12);
+    }
+    return (int)out.size();
+}
+// vSurfaceNormal: out [n][8] = normal xyz, camera position xyz, frame position xy; returns n
+int orc_surface_normals(const uint16_t* depth, int w, int h, float fx, float fy, float cx, float cy, float scale, float* out8, int cap) {
+    std::vector<oracle::SurfaceNormal> v;
+    oracle::surface_normals(depth, w, h, oracle::PlanePostParams{fx, fy, cx, cy, scale, 0.0}, v);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) std::memcpy(out8 + 8 * i, &v[i], 32);
+    return (int)v.size();
+}
+uint32_t orc_pcl_rng(int n) { oracle::PclRng r; uint32_t v = 0; for (int i = 0; i < n; ++i) v = r.next_u32(); return v; }
+}

@@ -82,6 +82,7 @@ struct LbaBuffers;
 struct LsdBuffers;
 struct TrackBuffers;
 struct ExchangeBuffers;
+struct PlanePostBuffers;
 
 }  // namespace pslam
 
@@ -141,6 +142,7 @@ struct pslam_ctx {
     pslam::LbaBuffers* lba = nullptr;            // local bundle adjustment staging (lba_pipeline.cu)
     pslam::LsdBuffers* lsd = nullptr;            // line-segment detector buffers (lsd_pipeline.cu)
     pslam::TrackBuffers* track = nullptr;        // device-resident tracking chain (track_chain.cu)
+    pslam::PlanePostBuffers* planepost = nullptr; // Frame::ComputePlanes post-processing + surface normals (planepost_kernels.cu)
     pslam::ExchangeBuffers* exchange = nullptr;  // key-frame descriptor exchange over peer memory (exchange_kernels.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
@@ -163,6 +165,7 @@ void lba_free(pslam_ctx* c);
 void lsd_free(pslam_ctx* c);
 void track_free(pslam_ctx* c);
 void exchange_free(pslam_ctx* c);
+void planepost_free(pslam_ctx* c);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

@@ -97,3 +97,26 @@ class PlaneDetection:
         nc = C.c_int32()
         ctx.check(ctx.L.pslam_peac_debug_coarse(ctx.h, frame, bm.ctypes.data, C.byref(nc)))
         return bm, nc.value
+
+
+def ComputePlanes(ctx: Context, depth: np.ndarray, dist_th: float = 0.05, normals: bool = True):
+    """void Frame::ComputePlanes(...) (src/Frame.cc:647-753) for a batch of depth images [B,H,W] uint16: PEAC + voxel grid + distance check + RANSAC refit +
+    integral-image surface normals (include/pslam_abi.h pslam_compute_planes_batch).  The context must carry the camera (fx, fy, cx, cy, depth_scale).
+    Returns per frame dict(src int32 [n], coef float32 [n][4] = mvPlaneCoefficients, points = list of float32 [k][3] = mvPlanePoints, normals float32 [m][8])."""
+    import ctypes as C
+    d = np.ascontiguousarray(depth, np.uint16)
+    B = len(d)
+    L = ctx.L
+    L.pslam_compute_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    maxp, cap, nsn = int(L.pslam_peac_max_planes(ctx.h)), 16384, int(L.pslam_surface_normals_count(ctx.h))
+    nk, src, coef = np.zeros(B, np.int32), np.zeros((B, maxp), np.int32), np.zeros((B, maxp, 4), np.float32)
+    off, pts = np.zeros((B, maxp + 1), np.int32), np.zeros((B, cap, 3), np.float32)
+    sn = np.zeros((B, nsn, 8), np.float32) if normals else None
+    ctx.check(L.pslam_compute_planes_batch(ctx.h, d.ctypes.data, B, dist_th, nk.ctypes.data, src.ctypes.data, coef.ctypes.data, off.ctypes.data, pts.ctypes.data, cap,
+                                           sn.ctypes.data if normals else None))
+    out = []
+    for f in range(B):
+        n = int(nk[f])
+        out.append(dict(src=src[f, :n].copy(), coef=coef[f, :n].copy(), points=[pts[f, off[f, k]:off[f, k + 1]].copy() for k in range(n)],
+                        normals=sn[f].copy() if normals else None))
+    return out

@@ -484,3 +484,37 @@ def lbd_prims(gray: np.ndarray):
     L.orc_gaussian_blur_5x5_s1(g.ctypes.data, w, h, g.strides[0], b.ctypes.data)
     L.orc_sobel3_s16(b.ctypes.data, w, h, dx.ctypes.data, dy.ctypes.data)
     return b, dx, dy
+
+
+def planes_post(depth: np.ndarray, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 / 5000.0), dist_th: float = 0.05):
+    """Oracle Frame::ComputePlanes post-processing (PEAC -> VoxelGrid 0.1 -> MaxPointDistanceFromPlane check -> RANSAC refit; oracle/planepost.cc, parity
+    unpinned).  Returns a list of dict(src, coef float32 [4], points float32 [n][3], n_inliers, n_iterations)."""
+    L = lib()
+    depth = np.ascontiguousarray(depth, np.uint16)
+    h, w = depth.shape
+    r = C.c_void_p(L.orc_peac_run(depth.ctypes.data, w, h, K[0], K[1], K[2], K[3], float(np.float32(scale))))
+    L.orc_planes_post.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_double] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
+    cap = 128
+    src, coef, npts, stats = np.zeros(cap, np.int32), np.zeros((cap, 4), np.float32), np.zeros(cap, np.int32), np.zeros((cap, 2), np.int32)
+    pts = np.zeros((200000, 3), np.float32)
+    n = L.orc_planes_post(r, depth.ctypes.data, w, h, K[0], K[1], K[2], K[3], float(np.float32(scale)), dist_th, src.ctypes.data, coef.ctypes.data, npts.ctypes.data,
+                          pts.ctypes.data, len(pts), stats.ctypes.data)
+    L.orc_peac_free(r)
+    out, o = [], 0
+    for i in range(n):
+        out.append(dict(src=int(src[i]), coef=coef[i].copy(), points=pts[o:o + npts[i]].copy(), n_inliers=int(stats[i, 0]), n_iterations=int(stats[i, 1])))
+        o += int(npts[i])
+    return out
+
+
+def surface_normals(depth: np.ndarray, K=(535.4, 539.2, 320.1, 247.6), scale=np.float32(1.0 / 5000.0)):
+    """Oracle vSurfaceNormal of Frame::ComputePlanes (IntegralImageNormalEstimation AVERAGE_3D_GRADIENT restated; parity unpinned): float32 [n][8] =
+    normal xyz (NaN at the borders / depth edges), camera position xyz, frame position xy."""
+    L = lib()
+    L.orc_surface_normals.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_float] * 5 + [C.c_void_p, C.c_int]
+    depth = np.ascontiguousarray(depth, np.uint16)
+    h, w = depth.shape
+    cap = ((h + 2) // 3) * ((w + 2) // 3)
+    out = np.zeros((cap, 8), np.float32)
+    n = L.orc_surface_normals(depth.ctypes.data, w, h, K[0], K[1], K[2], K[3], float(np.float32(scale)), out.ctypes.data, cap)
+    return out[:n].copy()
