@@ -72,8 +72,23 @@ ALGO_BYTES = {
     "lsd_order": 2 * 196608 + 60000 * 4,               # the scaled image twice, the seed order once
     "lsd_emit": 2500 * 104 + 800 * 40,
     "lsd_keylines": 800 * 16 + 40 * (68 + 24),
+    # chained extras
+    "stereo_from_rgbd": 1000 * (28 + 2 + 8),           # key points + one depth sample each, uRight / depth out
+    "hamming_knn2": 2 * 1000 * 32 + 1000 * 16,         # both descriptor sets once, two (index, distance) pairs per query
+    "match_gate": 1000 * 12,
+    "lbd_gradients": 307200 + 2 * 614400,              # the frame once, two int16 gradient planes
+    "lbd_lines": 40 * 63 * 120 * 4 + 40 * 32,          # ~120 gradient samples on each of the 63 rows of a line's support region, 32 descriptor bytes
+    "lines3d": 40 * (68 + 96) + 2040 * 2,              # key lines in, 3-D lines out, <= 51 depth samples per line
+    "planes_post": 2 * 280000 * (4 + 2),               # member index + depth sample of every plane pixel, twice (bounding box, voxel pass)
+    "planes_compact": 3 * 700 * 12 * 2,
+    "sn_points": 34240 * (2 + 12), "sn_chamfer": 34240 * (12 + 1 + 4 * 3), "sn_gradients": 34240 * (12 + 24), "sn_integral": 34240 * 24 + 34615 * 48,
+    "sn_normals": 34240 * (12 + 4 + 12) + 8 * 34615 * 24 // 4, "sn_gather": 8480 * (24 + 32 + 12),
+    "track_manhattan": 8480 * 12 * 4 + 8480,           # the normals four times (cones, then one pass per axis), masks out
 }
 STAGES = [s for s in os.environ.get("PSLAM_STAGES", "orb,lsd,peac,pose").split(",") if s]
+# the rest of the per-frame front end, chained on the stage that feeds it: ComputeStereoFromRGBD + MatchORBPoints after ORB, LBD descriptors + isLineGood after LSD,
+# Frame::ComputePlanes' post-processing (voxel grid / RANSAC refit / surface normals) + TrackManhattanFrame after PEAC
+EXTRAS = os.environ.get("PSLAM_EXTRAS", "1") != "0"
 
 
 def _peaks():
@@ -336,7 +351,9 @@ def workload_config():
                         "line functions; LBD descriptors not built) + PEAC planes + PoseOptimization (1000 point + 40 line (80 edges) + 6 plane "
                         "edges per frame)",
             "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "distinct_frames": DISTINCT_FRAMES, "l2": "inputs_larger_than_l2",
-            "stages": STAGES, "streams": len(STAGES)}
+            "stages": STAGES, "streams": len(STAGES),
+            "extras": ("ComputeStereoFromRGBD + MatchORBPoints (consecutive frames) after ORB; LBD descriptors + isLineGood after LSD; ComputePlanes post-processing "
+                       "(VoxelGrid, RANSAC refit, surface normals) + TrackManhattanFrame (surface normals only) after PEAC") if EXTRAS else "off"}
 
 
 def main():
@@ -420,7 +437,7 @@ def main():
     d_labels = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
     d_planes = torch.empty((SUB_BATCH, maxp, PLANE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     d_npl = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
-    d_midx = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
+    d_members = torch.empty((SUB_BATCH, H * W), dtype=torch.int32, device=dev)
     d_moff = torch.empty((SUB_BATCH, maxp + 1), dtype=torch.int32, device=dev)
     d_kl = torch.empty((FRAMES_PER_STEP, MAX_LINES, KEYLINE_DTYPE.itemsize), dtype=torch.uint8, device=dev)
     d_lf = torch.empty((FRAMES_PER_STEP, MAX_LINES, 3), dtype=torch.float64, device=dev)
@@ -448,21 +465,81 @@ def main():
     pose_h2d = sum(sum(p[k].nbytes for k in ("Xw", "obs", "inv_sigma2", "line_Xw", "line_obs", "plane_meas", "plane_map", "par_meas",
                                               "par_map", "ver_meas", "ver_map")) + 64 for p in probs)
 
+    # ---- buffers of the chained extras ----
+    h_ur, h_dz = pinned((SUB_BATCH, cap), np.float32), pinned((SUB_BATCH, cap), np.float32)
+    h_ldesc = pinned((FRAMES_PER_STEP, MAX_LINES, 32), np.uint8)
+    h_l3d = pinned((FRAMES_PER_STEP, MAX_LINES, 96), np.uint8)
+    h_seed, h_drawn = pinned((FRAMES_PER_STEP,), np.uint32), pinned((FRAMES_PER_STEP,), np.int32)
+    h_seed[:] = 1
+    h_pp_n, h_pp_src, h_pp_coef = pinned((SUB_BATCH,), np.int32), pinned((SUB_BATCH, maxp), np.int32), pinned((SUB_BATCH, maxp, 4), np.float32)
+    h_pp_off, h_pp_pts = pinned((SUB_BATCH, maxp + 1), np.int32), pinned((SUB_BATCH, 4096, 3), np.float32)
+    h_sn8 = pinned((SUB_BATCH, int(L.pslam_surface_normals_count(c_peac.h)), 8), np.float32)
+    L.pslam_compute_stereo_from_rgbd_batch.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.pslam_compute_planes_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    L.pslam_lines_extract_describe_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+    L.pslam_lines3d_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5
+    from planarslam_b200.lines import LINE3D_DTYPE
+    from planarslam_b200.manhattan import MANHATTAN_RESULT_DTYPE
+    DEPTH_FACTOR, BF, DIST_TH = float(np.float32(1.0 / 5000.0)), 40.0, 0.05
+    cam4 = (C.c_float * 4)(535.4, 539.2, 320.1, 247.6)
+    n_sn = int(L.pslam_surface_normals_count(c_peac.h))
+    PP_CAP = 4096
+    d_ur = torch.empty((SUB_BATCH, cap), dtype=torch.float32, device=dev); d_dz = torch.empty_like(d_ur)
+    d_midx = torch.empty((SUB_BATCH, cap, 2), dtype=torch.int32, device=dev); d_mdist = torch.empty_like(d_midx)
+    d_good = torch.empty((SUB_BATCH, cap), dtype=torch.int32, device=dev); d_ngood = torch.zeros(SUB_BATCH, dtype=torch.int32, device=dev)
+    d_ldesc = torch.empty((FRAMES_PER_STEP, MAX_LINES, 32), dtype=torch.uint8, device=dev)
+    d_l3d = torch.empty((FRAMES_PER_STEP, MAX_LINES, LINE3D_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_seed = torch.ones(FRAMES_PER_STEP, dtype=torch.int32, device=dev); d_drawn = torch.zeros(FRAMES_PER_STEP, dtype=torch.int32, device=dev)
+    d_pp_n = torch.zeros(SUB_BATCH, dtype=torch.int32, device=dev); d_pp_src = torch.empty((SUB_BATCH, maxp), dtype=torch.int32, device=dev)
+    d_pp_coef = torch.empty((SUB_BATCH, maxp, 4), dtype=torch.float32, device=dev); d_pp_off = torch.empty((SUB_BATCH, maxp + 1), dtype=torch.int32, device=dev)
+    d_pp_pts = torch.empty((SUB_BATCH, PP_CAP, 3), dtype=torch.float32, device=dev); d_pp_status = torch.zeros(SUB_BATCH, dtype=torch.int32, device=dev)
+    d_sn8 = torch.empty((SUB_BATCH, n_sn, 8), dtype=torch.float32, device=dev); d_sn3 = torch.empty((SUB_BATCH, n_sn, 3), dtype=torch.float32, device=dev)
+    d_nsn = torch.full((SUB_BATCH,), n_sn, dtype=torch.int32, device=dev); d_ndirs = torch.zeros(SUB_BATCH, dtype=torch.int32, device=dev)
+    d_dirs = torch.zeros((SUB_BATCH, 1, 3), dtype=torch.float64, device=dev)
+    d_Rlast = torch.eye(3, dtype=torch.float32, device=dev).repeat(SUB_BATCH, 1, 1).contiguous()
+    d_mres = torch.empty((SUB_BATCH, MANHATTAN_RESULT_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    d_nmask = torch.empty((SUB_BATCH, n_sn), dtype=torch.uint8, device=dev); d_dmask = torch.empty((SUB_BATCH, 1), dtype=torch.uint8, device=dev)
+    L.pslam_compute_stereo_from_rgbd_batch_dev.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    L.pslam_lines_extract_describe_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4
+    L.pslam_lines3d_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float] + [C.c_void_p] * 5
+    L.pslam_planes_post_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    L.pslam_surface_normals_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.pslam_track_manhattan_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
     def dev_orb(o):
         c_orb.check(L.pslam_orb_extract_batch_dev(c_orb.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps.data_ptr(), d_desc.data_ptr(), cap,
                                                   d_n[o:].data_ptr()))
+        if EXTRAS:
+            c_orb.check(L.pslam_compute_stereo_from_rgbd_batch_dev(c_orb.h, d_kps.data_ptr(), d_kps.data_ptr(), d_n[o:].data_ptr(), cap, d_depth[o].data_ptr(), SUB_BATCH,
+                                                                   DEPTH_FACTOR, BF, d_ur.data_ptr(), d_dz.data_ptr()))
+            # MatchORBPoints of every frame against its predecessor in the sub-batch (cv::BFMatcher 1-NN + the 2 x min-distance gate)
+            c_orb.check(L.pslam_hamming_knn2_batch_dev(c_orb.h, d_desc[1:].data_ptr(), d_n[o + 1:].data_ptr(), cap, d_desc.data_ptr(), d_n[o:].data_ptr(), cap,
+                                                       SUB_BATCH - 1, d_midx.data_ptr(), d_mdist.data_ptr(), d_good.data_ptr(), d_ngood.data_ptr()))
 
     def dev_peac(o):
         c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
-                                                d_npl[o:].data_ptr(), d_midx.data_ptr(), d_moff.data_ptr()))
+                                                d_npl[o:].data_ptr(), d_members.data_ptr(), d_moff.data_ptr()))
+        if EXTRAS:
+            c_peac.check(L.pslam_planes_post_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_planes.data_ptr(), d_npl[o:].data_ptr(), d_members.data_ptr(),
+                                                       d_moff.data_ptr(), DIST_TH, d_pp_n.data_ptr(), d_pp_src.data_ptr(), d_pp_coef.data_ptr(), d_pp_off.data_ptr(),
+                                                       d_pp_pts.data_ptr(), PP_CAP, d_pp_status.data_ptr()))
+            c_peac.check(L.pslam_surface_normals_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_sn8.data_ptr(), d_sn3.data_ptr()))
+            c_peac.check(L.pslam_track_manhattan_batch_dev(c_peac.h, d_Rlast.data_ptr(), d_sn3.data_ptr(), d_nsn.data_ptr(), n_sn, d_dirs.data_ptr(), d_ndirs.data_ptr(), 1,
+                                                           SUB_BATCH, d_mres.data_ptr(), d_nmask.data_ptr(), d_dmask.data_ptr()))
 
     LSD_BATCH = (FRAMES_PER_STEP + LSD_SUBS - 1) // LSD_SUBS
 
     def dev_lsd(j=None):
         for q in (range(LSD_SUBS) if j is None else [j]):
             o, n = q * LSD_BATCH, min(LSD_BATCH, FRAMES_PER_STEP - q * LSD_BATCH)
-            c_lsd.check(L.pslam_lines_extract_batch_dev(c_lsd.h, d_gray[o].data_ptr(), n, MAX_LINES, d_kl[o].data_ptr(), d_lf[o].data_ptr(),
-                                                        d_nkl[o:].data_ptr()))
+            if EXTRAS:
+                c_lsd.check(L.pslam_lines_extract_describe_batch_dev(c_lsd.h, d_gray[o].data_ptr(), n, MAX_LINES, d_kl[o].data_ptr(), d_lf[o].data_ptr(),
+                                                                     d_ldesc[o].data_ptr(), d_nkl[o:].data_ptr()))
+                c_lsd.check(L.pslam_lines3d_batch_dev(c_lsd.h, d_kl[o].data_ptr(), d_nkl[o:].data_ptr(), MAX_LINES, d_depth[o].data_ptr(), n, DEPTH_FACTOR, cam4,
+                                                      d_seed[o:].data_ptr(), None, d_l3d[o].data_ptr(), d_drawn[o:].data_ptr()))
+            else:
+                c_lsd.check(L.pslam_lines_extract_batch_dev(c_lsd.h, d_gray[o].data_ptr(), n, MAX_LINES, d_kl[o].data_ptr(), d_lf[o].data_ptr(),
+                                                            d_nkl[o:].data_ptr()))
 
     def steps_dev(nsteps):
         """nsteps passes over the batch.  The three stage families are independent per frame, so each runs its own
@@ -498,12 +575,19 @@ def main():
             for s in range(SUBS_PER_STEP):
                 c_orb.check(L.pslam_orb_extract_batch(c_orb.h, h_gray[s * SUB_BATCH].data_ptr(), SUB_BATCH, h_kps.ctypes.data, h_desc.ctypes.data,
                                                       cap, h_n.ctypes.data))
+                if EXTRAS:      # Frame::ComputeStereoFromRGBD on the key points just returned (host buffers in, host buffers out)
+                    c_orb.check(L.pslam_compute_stereo_from_rgbd_batch(c_orb.h, h_kps.ctypes.data, h_kps.ctypes.data, h_n.ctypes.data, cap, h_depth[s * SUB_BATCH].data_ptr(),
+                                                                       SUB_BATCH, DEPTH_FACTOR, BF, h_ur.ctypes.data, h_dz.ctypes.data))
 
         def e_peac():
             torch.cuda.set_device(local_rank)
             for s in range(SUBS_PER_STEP):
-                c_peac.check(L.pslam_peac_run_batch(c_peac.h, h_depth[s * SUB_BATCH].data_ptr(), SUB_BATCH, h_labels.ctypes.data,
-                                                    h_planes.ctypes.data, h_npl.ctypes.data, None, None))
+                if EXTRAS:      # the whole Frame::ComputePlanes: PEAC + post-processing + surface normals -> mvPlaneCoefficients, mvPlanePoints, vSurfaceNormal
+                    c_peac.check(L.pslam_compute_planes_batch(c_peac.h, h_depth[s * SUB_BATCH].data_ptr(), SUB_BATCH, DIST_TH, h_pp_n.ctypes.data, h_pp_src.ctypes.data,
+                                                              h_pp_coef.ctypes.data, h_pp_off.ctypes.data, h_pp_pts.ctypes.data, PP_CAP, h_sn8.ctypes.data))
+                else:
+                    c_peac.check(L.pslam_peac_run_batch(c_peac.h, h_depth[s * SUB_BATCH].data_ptr(), SUB_BATCH, h_labels.ctypes.data,
+                                                        h_planes.ctypes.data, h_npl.ctypes.data, None, None))
 
         def e_pose():
             torch.cuda.set_device(local_rank)
@@ -513,8 +597,14 @@ def main():
             torch.cuda.set_device(local_rank)
             for q in range(LSD_SUBS):
                 o, n = q * LSD_BATCH, min(LSD_BATCH, FRAMES_PER_STEP - q * LSD_BATCH)
-                c_lsd.check(L.pslam_lines_extract_batch(c_lsd.h, h_gray[o].data_ptr(), n, MAX_LINES, h_kl[o:].ctypes.data, h_lf[o:].ctypes.data,
-                                                        h_nkl[o:].ctypes.data))
+                if EXTRAS:      # the whole ExtractLineSegment (with LBD descriptors), then Frame::isLineGood on the key lines just returned
+                    c_lsd.check(L.pslam_lines_extract_describe_batch(c_lsd.h, h_gray[o].data_ptr(), n, MAX_LINES, h_kl[o:].ctypes.data, h_lf[o:].ctypes.data,
+                                                                     h_ldesc[o:].ctypes.data, None, h_nkl[o:].ctypes.data))
+                    c_lsd.check(L.pslam_lines3d_batch(c_lsd.h, h_kl[o:].ctypes.data, h_nkl[o:].ctypes.data, MAX_LINES, h_depth[o].data_ptr(), n, DEPTH_FACTOR, cam4,
+                                                      h_seed[o:].ctypes.data, None, h_l3d[o:].ctypes.data, h_drawn[o:].ctypes.data))
+                else:
+                    c_lsd.check(L.pslam_lines_extract_batch(c_lsd.h, h_gray[o].data_ptr(), n, MAX_LINES, h_kl[o:].ctypes.data, h_lf[o:].ctypes.data,
+                                                            h_nkl[o:].ctypes.data))
         fns = [fn for nm, fn in (("peac", e_peac), ("lsd", e_lsd), ("orb", e_orb), ("pose", e_pose)) if nm in STAGES]
         for f in [pool.submit(fn) for fn in fns]:
             f.result()
@@ -560,8 +650,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
     h2d = FRAMES_PER_STEP * (("orb" in STAGES) * W * H + ("lsd" in STAGES) * W * H + ("peac" in STAGES) * 2 * W * H) + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
+    if EXTRAS:          # stereo: key points + depth again; isLineGood: key lines + depth again (every host-pointer call uploads what it reads)
+        h2d += FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 28 + 2 * W * H) + ("lsd" in STAGES) * (MAX_LINES * 68 + 2 * W * H))
     d2h = FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 60 + 8) + ("peac" in STAGES) * (4 * W * H + maxp * PLANE_DTYPE.itemsize + 4) +
                              ("pose" in STAGES) * (64 + 1046 + 4) + ("lsd" in STAGES) * (MAX_LINES * (68 + 24) + 4))
+    if EXTRAS:
+        d2h += FRAMES_PER_STEP * (("orb" in STAGES) * cap * 8 + ("lsd" in STAGES) * MAX_LINES * (32 + 96) +
+                                  ("peac" in STAGES) * (maxp * 28 + 4096 * 12 + int(L.pslam_surface_normals_count(c_peac.h)) * 32 - 4 * W * H - maxp * PLANE_DTYPE.itemsize))
 
     # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
     # one stage family at a time, so a launch's duration is not inflated by kernels of the other two streams

@@ -152,7 +152,9 @@ int pslam_planes_post_max_points(const pslam_ctx* ctx);
 int pslam_planes_post_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, const pslam_plane* d_planes, const int32_t* d_nplanes, const int32_t* d_member_idx,
                                 const int32_t* d_member_off, float dist_th, int32_t* d_n_kept, int32_t* d_src, float* d_coef, int32_t* d_pt_off, float* d_pts, int cap_pts,
                                 int32_t* d_status);
-int pslam_surface_normals_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, float* d_normals8);
+/* d_normals3 (optional): the normals alone, [nframes][pslam_surface_normals_count()][3] - the layout pslam_track_manhattan_batch_dev reads (NaN normals stay NaN and fail
+ * every cone test there, like in the reference) */
+int pslam_surface_normals_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, float* d_normals8, float* d_normals3);
 /* PEAC + post-processing + normals on host depth images (the whole Frame::ComputePlanes); normals8 may be NULL */
 int pslam_compute_planes_batch(pslam_ctx* ctx, const uint16_t* depth, int nframes, float dist_th, int32_t* n_kept, int32_t* src, float* coef, int32_t* pt_off, float* pts,
                                int cap_pts, float* normals8);

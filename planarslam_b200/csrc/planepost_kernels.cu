@@ -485,7 +485,7 @@ __global__ void k_sn_normals(int W3, int H3, const float* __restrict__ cloud_all
     for (int k = 0; k < 3; ++k) nrm_all[((size_t)frame * NP + i) * 3 + k] = out[k];
 }
 // vSurfaceNormal: odd rows and columns of the sub-sampled grid -> [n][8] = normal, camera position, frame position
-__global__ void k_sn_gather(int W3, int H3, const float* __restrict__ cloud_all, const float* __restrict__ nrm_all, float* __restrict__ out8, int n_out) {
+__global__ void k_sn_gather(int W3, int H3, const float* __restrict__ cloud_all, const float* __restrict__ nrm_all, float* __restrict__ out8, float* __restrict__ out3, int n_out) {
     const int frame = blockIdx.y, o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_out) return;
     const int cols = W3 / 2, r = o / cols, c = o - r * cols, m = 2 * r + 1, n = 2 * c + 1;
@@ -493,6 +493,7 @@ __global__ void k_sn_gather(int W3, int H3, const float* __restrict__ cloud_all,
     float* d = out8 + ((size_t)frame * n_out + o) * 8;
     for (int k = 0; k < 3; ++k) { d[k] = nrm_all[((size_t)frame * NP + idx) * 3 + k]; d[3 + k] = cloud_all[((size_t)frame * NP + idx) * 3 + k]; }
     d[6] = (float)(n * 3); d[7] = (float)(m * 3);
+    if (out3) for (int k = 0; k < 3; ++k) out3[((size_t)frame * n_out + o) * 3 + k] = d[k];      // the normals alone, the layout pslam_track_manhattan_batch_dev reads
 }
 
 void planepost_free(pslam_ctx* c) {
@@ -556,7 +557,7 @@ int pslam_planes_post_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int nfram
     return PSLAM_OK;
 }
 
-int pslam_surface_normals_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, float* d_normals8) {
+int pslam_surface_normals_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, float* d_normals8, float* d_normals3) {
     if (!c) return PSLAM_E_INVALID;
     if (!d_depth || !d_normals8 || nframes < 1 || nframes > c->cfg.max_batch) return set_error(c, PSLAM_E_INVALID, "surface normals: null pointer or nframes outside [1, max_batch]");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
@@ -572,7 +573,7 @@ int pslam_surface_normals_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int n
     PSLAM_LAUNCH(c, "sn_gradients", k_sn_gradients<<<gp, 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_gx, B.d_gy));
     PSLAM_LAUNCH(c, "sn_integral", k_sn_integral<<<(nframes * 6 + 63) / 64, 64, 0, st>>>(nframes, B.w3, B.h3, B.d_gx, B.d_gy, B.d_ix, B.d_iy));
     PSLAM_LAUNCH(c, "sn_normals", k_sn_normals<<<gp, 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_dist, B.d_ix, B.d_iy, B.d_nrm));
-    PSLAM_LAUNCH(c, "sn_gather", k_sn_gather<<<dim3((n_out + 255) / 256, nframes), 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_nrm, d_normals8, n_out));
+    PSLAM_LAUNCH(c, "sn_gather", k_sn_gather<<<dim3((n_out + 255) / 256, nframes), 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_nrm, d_normals8, d_normals3, n_out));
     PSLAM_CUDA(c, cudaGetLastError());
     return PSLAM_OK;
 }
@@ -600,7 +601,7 @@ int pslam_compute_planes_batch(pslam_ctx* c, const uint16_t* depth, int nframes,
         rc = pslam_planes_post_batch_dev(c, (const uint16_t*)(d + off[0]), nframes, (const pslam_plane*)(d + off[2]), (const int32_t*)(d + off[3]), (const int32_t*)(d + off[4]),
                                          (const int32_t*)(d + off[5]), dist_th, (int32_t*)(d + off[6]), (int32_t*)(d + off[7]), (float*)(d + off[8]), (int32_t*)(d + off[9]),
                                          (float*)(d + off[10]), cap_pts, (int32_t*)(d + off[11]));
-    if (rc == PSLAM_OK && normals8) rc = pslam_surface_normals_batch_dev(c, (const uint16_t*)(d + off[0]), nframes, (float*)(d + off[12]));
+    if (rc == PSLAM_OK && normals8) rc = pslam_surface_normals_batch_dev(c, (const uint16_t*)(d + off[0]), nframes, (float*)(d + off[12]), nullptr);
     if (rc != PSLAM_OK) { cudaStreamSynchronize(st); cudaFree(d); return rc; }
     std::vector<int32_t> status(nframes);
     cudaMemcpyAsync(n_kept, d + off[6], sz[6], cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(src, d + off[7], sz[7], cudaMemcpyDeviceToHost, st);
