@@ -83,6 +83,7 @@ ALGO_BYTES = {
     "planes_compact": 3 * 700 * 12 * 2,
     "sn_points": 34240 * (2 + 12), "sn_chamfer": 34240 * (12 + 1 + 4 * 3), "sn_gradients": 34240 * (12 + 24), "sn_integral": 34240 * 24 + 34615 * 48,
     "sn_normals": 34240 * (12 + 4 + 12) + 8 * 34615 * 24 // 4, "sn_gather": 8480 * (24 + 32 + 12),
+    "exchange_publish": 2 * 1000 * (32 + 28), "exchange_match": 2 * 1000 * 32 + 1000 * 16,     # per key frame and peer record (8 key frames per step, not per frame)
     "track_manhattan": 8480 * 12 * 4 + 8480,           # the normals four times (cones, then one pass per axis), masks out
 }
 STAGES = [s for s in os.environ.get("PSLAM_STAGES", "orb,lsd,peac,pose").split(",") if s]
@@ -175,22 +176,92 @@ def _cpu_stage_fns(stages):
         except Exception:
             lsd_cv = None
 
-    def f_lsd(i):
-        if lsd_cv is None:
-            return oracle_lib.extract_line_segments(gray[i % n], 40)
-        segs = lsd_cv.detect(gray[i % n])[0]                       # + ExtractLineSegment's keep-40 (src/LSDextractor.cpp:18-26)
-        if segs is not None:
-            segs = segs.reshape(-1, 4)
-            segs[np.argsort(-np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1]), kind="stable")[:40]]
+    from planarslam_b200.lines import KEYLINE_DTYPE
+    extras = EXTRAS
+    cam = (535.4, 539.2, 320.1, 247.6)
+    depth_m = [(depth[k].astype(np.float32) * np.float32(1.0 / 5000.0)) for k in range(n)] if extras else None     # imDepth.convertTo(CV_32F, mDepthMapFactor): the caller's job
+    bf = None
+    if use_ref and extras:
+        try:
+            import cv2
+            bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+        except Exception:
+            bf = None
+    prev_desc = {}
 
-    fns = {"orb": (lambda i: ref_lib.ref_orb_extract(gray[i % n], monotonic_alloc=False)) if ref_orb else (lambda i: oracle_lib.orb_extract(gray[i % n])),
-           "lsd": f_lsd,
-           "peac": (lambda i: ref_lib.ref_peac_time(depth[i % n])) if ref_peac else (lambda i: oracle_lib.PeacOracle(depth[i % n])),
+    def keylines_of(segs):
+        """KeyLines of ExtractLineSegment (LSDDetector::detect fields used downstream) from cv2's segments: 40 longest, end points clamped into the image."""
+        kl = np.zeros(len(segs), KEYLINE_DTYPE)
+        if len(segs):
+            sx, sy = np.clip(segs[:, 0], 0, W - 1), np.clip(segs[:, 1], 0, H - 1)
+            ex, ey = np.clip(segs[:, 2], 0, W - 1), np.clip(segs[:, 3], 0, H - 1)
+            kl["startPointX"], kl["startPointY"], kl["endPointX"], kl["endPointY"] = sx, sy, ex, ey
+            kl["sPointInOctaveX"], kl["sPointInOctaveY"], kl["ePointInOctaveX"], kl["ePointInOctaveY"] = sx, sy, ex, ey
+            kl["lineLength"] = np.hypot(ex - sx, ey - sy)
+            kl["angle"] = np.arctan2(ey - sy, ex - sx)
+            kl["pt"][:, 0], kl["pt"][:, 1] = (sx + ex) / 2, (sy + ey) / 2
+            kl["size"] = np.abs(ex - sx) * np.abs(ey - sy)
+            kl["class_id"] = np.arange(len(segs))
+            kl["numOfPixels"] = np.maximum(np.abs(ex - sx), np.abs(ey - sy)).astype(np.int32) + 1
+        return kl
+
+    def f_lsd(i):
+        g = gray[i % n]
+        if lsd_cv is None:
+            kl = oracle_lib.extract_line_segments(g, 40)
+            kl = kl[0] if isinstance(kl, tuple) else kl
+        else:
+            segs = lsd_cv.detect(g)[0]                       # + ExtractLineSegment's keep-40 (src/LSDextractor.cpp:18-26)
+            segs = segs.reshape(-1, 4) if segs is not None else np.zeros((0, 4), np.float32)
+            segs = segs[np.argsort(-np.hypot(segs[:, 2] - segs[:, 0], segs[:, 3] - segs[:, 1]), kind="stable")[:40]]
+            kl = keylines_of(segs) if extras else None
+        if extras:
+            oracle_lib.lbd_compute(g, kl)                                                      # BinaryDescriptor::compute (port: opencv_contrib is not in this image)
+            (ref_lib.ref_full_lines3d_frame if ref_match else oracle_lib.lines3d_frame)(kl, depth_m[i % n], cam, 1)        # Frame::isLineGood
+
+    def f_orb(i):
+        g = gray[i % n]
+        r = ref_lib.ref_orb_extract(g, monotonic_alloc=False) if ref_orb else oracle_lib.orb_extract(g)
+        if extras:
+            kps, desc = r[0], r[1]
+            xy = np.ascontiguousarray(np.stack([kps["x"], kps["y"]], 1), np.float32)
+            (ref_lib.ref_full_compute_stereo_from_rgbd if ref_match else oracle_lib.compute_stereo_from_rgbd)(xy, xy, depth_m[i % n], 40.0)
+            last = prev_desc.get("d")
+            if last is not None and len(last) and len(desc):                                   # MatchORBPoints against the previous frame of this worker
+                if bf is not None:
+                    m = bf.match(np.ascontiguousarray(desc), last)
+                    dmin = min((x.distance for x in m), default=0.0)
+                    [x for x in m if x.distance <= max(2 * dmin, 30.0)]
+                else:
+                    xor = np.bitwise_xor(np.ascontiguousarray(desc)[:, None, :], last[None, :, :])
+                    np.unpackbits(xor, axis=2).sum(2).argmin(1)
+            prev_desc["d"] = np.ascontiguousarray(desc)
+
+    R_eye = np.eye(3, dtype=np.float32)
+    ref_track = ref_lib.track_lib() if (use_ref and extras) else None
+
+    def f_peac(i):
+        d = depth[i % n]
+        if not extras:
+            return ref_lib.ref_peac_time(d) if ref_peac else oracle_lib.PeacOracle(d)
+        # Frame::ComputePlanes: PEAC + the per-plane post-processing + surface normals, then TrackManhattanFrame on the normals.  The post-processing consumes
+        # the PEAC result in memory, so the whole function runs in the port here (one PEAC pass, not the compiled reference's plus the port's)
+        oracle_lib.planes_post(d)
+        sn = oracle_lib.surface_normals(d)
+        nr = np.ascontiguousarray(sn[:, :3])
+        (ref_lib.ref_track_manhattan_frame if ref_track else oracle_lib.track_manhattan_frame)(R_eye, nr, np.zeros((0, 3)))
+
+    fns = {"orb": f_orb, "lsd": f_lsd, "peac": f_peac,
            "pose": (lambda i: ref_lib.ref_full_pose_optimization(probs[i % n], False)) if ref_match else (lambda i: oracle_lib.pose_optimization(probs[i % n]))}
     units = {"orb": "reference src/ORBextractor.cc (OpenCV primitives inside it: scalar restatements)" if ref_orb else "port",
              "lsd": "upstream cv2 LineSegmentDetector (1 thread)" if lsd_cv is not None else "port",
-             "peac": "reference src/PlaneExtractor.cpp + include/peac" if ref_peac else "port",
+             "peac": ("reference src/PlaneExtractor.cpp + include/peac" if ref_peac else "port") if not extras else
+                     "port of the whole Frame::ComputePlanes (PEAC + VoxelGrid / RANSAC refit + surface normals; PCL is not in this image)",
              "pose": "reference src/Optimizer.cc PoseOptimization(Frame*) + Thirdparty/g2o" if ref_match else "port"}
+    if extras:
+        units["orb"] += " + Frame::ComputeStereoFromRGBD (compiled src/Frame.cc) + cv2.BFMatcher (MatchORBPoints)" if (ref_match and bf is not None) else " + stereo / matching ports"
+        units["lsd"] += " + LBD port + Frame::isLineGood (compiled src/Frame.cc)" if ref_match else " + LBD / isLineGood ports"
+        units["peac"] += " + Tracking::TrackManhattanFrame (compiled src/Tracking.cc)" if ref_track else " + Manhattan port"
     return {k: v for k, v in fns.items() if k in stages}, {k: v for k, v in units.items() if k in stages}
 
 
@@ -506,6 +577,18 @@ def main():
     L.pslam_surface_normals_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.pslam_track_manhattan_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
 
+    # key-frame exchange: every step, each rank publishes the ORB blocks of KF of its frames into records in its own HBM and matches
+    # them against the records of ALL ranks read in place over NVLink (one fused wait-on-flag + Hamming k = 2 kernel per key frame); two slot sets alternate
+    # by epoch parity, so a slot is rewritten only after every peer has matched it (publish(e + 2) is stream-ordered after this rank's match(e + 1), which
+    # waited for every peer's publish(e + 1), itself stream-ordered after that peer's match(e))
+    KF = int(os.environ.get("PSLAM_KEYFRAMES_PER_STEP", "8"))
+    xch, xch_epoch = None, [0]
+    if EXTRAS and "orb" in STAGES and KF > 0:
+        from planarslam_b200.sharding import PeerDescriptorExchange
+        xch = PeerDescriptorExchange(c_orb, cap, slots=2 * KF)
+        d_xidx = torch.empty((KF, cap, 2), dtype=torch.int32, device=dev); d_xdist = torch.empty_like(d_xidx)
+        kf_stride = max(SUB_BATCH // KF, 1)
+
     def dev_orb(o):
         c_orb.check(L.pslam_orb_extract_batch_dev(c_orb.h, d_gray[o].data_ptr(), SUB_BATCH, d_kps.data_ptr(), d_desc.data_ptr(), cap,
                                                   d_n[o:].data_ptr()))
@@ -515,6 +598,15 @@ def main():
             # MatchORBPoints of every frame against its predecessor in the sub-batch (cv::BFMatcher 1-NN + the 2 x min-distance gate)
             c_orb.check(L.pslam_hamming_knn2_batch_dev(c_orb.h, d_desc[1:].data_ptr(), d_n[o + 1:].data_ptr(), cap, d_desc.data_ptr(), d_n[o:].data_ptr(), cap,
                                                        SUB_BATCH - 1, d_midx.data_ptr(), d_mdist.data_ptr(), d_good.data_ptr(), d_ngood.data_ptr()))
+            if xch is not None and o == 0:
+                xch_epoch[0] += 1
+                e, base = xch_epoch[0], (xch_epoch[0] & 1) * KF
+                for k in range(KF):
+                    f = min(k * kf_stride, SUB_BATCH - 1)
+                    xch.publish(base + k, d_desc[f], d_n[f:f + 1], e, d_kps[f])
+                for k in range(KF):
+                    f = min(k * kf_stride, SUB_BATCH - 1)
+                    xch.match(base + k, e, d_desc[f], d_n[f:f + 1], d_xidx[k], d_xdist[k])
 
     def dev_peac(o):
         c_peac.check(L.pslam_peac_run_batch_dev(c_peac.h, d_depth[o].data_ptr(), SUB_BATCH, d_labels.data_ptr(), d_planes.data_ptr(),
@@ -676,6 +768,8 @@ def main():
     for name, (n, tot_ms) in rep.items():
         frames_per_launch = FRAMES_PER_STEP / n
         bytes_per_launch = ALGO_BYTES.get(name, 0) * frames_per_launch
+        if name.startswith("exchange_"):           # one key frame per launch (the matcher reads one record per rank)
+            bytes_per_launch = ALGO_BYTES[name] * (world if name == "exchange_match" else 1)
         per_kernel[name] = {"launches": n, "ms_total": round(tot_ms, 4), "share": None, "algo_bytes_per_launch": int(bytes_per_launch),
                             "achieved_gbs": round(bytes_per_launch / (tot_ms / n * 1e-3) / 1e9, 2)}
     tot = sum(v["ms_total"] for v in per_kernel.values()) or 1.0
@@ -730,6 +824,15 @@ def main():
         except Exception as ex:
             aux["new_kernels"] = {"error": repr(ex)}
 
+    xch_info = None
+    if xch is not None:
+        n_to = C.c_int32(0)
+        L.pslam_exchange_timeouts.argtypes = [C.c_void_p, C.c_void_p]
+        c_orb.check(L.pslam_exchange_timeouts(c_orb.h, C.byref(n_to)))
+        if n_to.value:
+            raise RuntimeError(f"key-frame exchange: {n_to.value} matcher CTAs timed out waiting for a peer")
+        xch_info = {"key_frames_per_rank_per_step": KF, "records_read_per_match": world, "transport": "CUDA IPC peer memory (NVLink P2P), fused with the Hamming k=2 matcher",
+                    "epochs": xch_epoch[0], "nearest_distance_median": float(d_xdist[:, :500, 0].float().median().item())}
     if rank == 0:
         modes = cpu_modes(gray[:CPU_SAMPLE_FRAMES], depth[:CPU_SAMPLE_FRAMES], seconds=float(os.environ.get("PSLAM_CPU_SECONDS", "8")))
         best = modes["frame_parallel_all_cores"]
@@ -744,7 +847,7 @@ def main():
                                  "sample": f"{' + '.join(STAGES)}: {best['frames']} frames in {best['seconds']} s, one pinned process per host core "
                                            f"({modes['host_cores']}), -O3 -march=x86-64-v3 (oracle/Makefile fast); modes = BASELINE.md section 3"},
                 "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP,
-                "keylines_per_frame": float(d_nkl.sum().item()) / FRAMES_PER_STEP if "lsd" in STAGES else None, "aux": aux}
+                "keylines_per_frame": float(d_nkl.sum().item()) / FRAMES_PER_STEP if "lsd" in STAGES else None, "exchange": xch_info, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

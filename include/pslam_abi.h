@@ -265,6 +265,9 @@ int pslam_exchange_create(pslam_ctx* ctx, int cap_kp, int slots, void* ipc_handl
 int pslam_exchange_attach(pslam_ctx* ctx, int world, int rank, const void* handles /* [world][PSLAM_IPC_HANDLE_BYTES] */);
 int pslam_exchange_publish_dev(pslam_ctx* ctx, int slot, const uint8_t* d_desc, const pslam_keypoint* d_kps /* may be NULL */, const int32_t* d_n, uint32_t epoch);
 int pslam_exchange_match_dev(pslam_ctx* ctx, int slot, uint32_t epoch, const uint8_t* d_qdesc, const int32_t* d_nq, int capq, int32_t* d_idx, int32_t* d_dist);
+/* A matcher CTA that waits more than 20 s for a peer's epoch flag treats that peer's record as empty and counts the wait; this returns the count since create
+ * (synchronises the context's stream).  Non-zero means a peer died or the epochs / slots of the ranks are out of step. */
+int pslam_exchange_timeouts(pslam_ctx* ctx, int32_t* n_out);
 
 /* ---- Plane association -------------------------------------------------------------------------
  * Replaces  int PlaneMatcher::SearchMapByCoefficients(Frame& pF, const vector<MapPlane*>& vpMapPlanes)   src/PlaneMatcher.cpp:10-67

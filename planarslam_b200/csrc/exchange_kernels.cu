@@ -33,6 +33,7 @@ struct ExchangeBuffers {
     bool opened[XCH_MAX_WORLD] = {false};
     uint32_t* d_part = nullptr;                     // [XCH_MAX_WORLD][capq][2] per-peer best keys
     int32_t* d_ticket = nullptr;                    // per query tile
+    int32_t* d_timeouts = nullptr;                  // CTAs that gave up waiting for a peer's epoch flag (pslam_exchange_timeouts)
     int capq = 0;
 };
 
@@ -43,6 +44,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define XCH_WAIT_NS 20000000000ull      // a peer that has not published after 20 s is treated as absent (its rows are skipped, the wait is counted)
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // record layout inside a slot
@@ -73,7 +80,7 @@ __global__ void __launch_bounds__(256) k_exchange_publish(uint8_t* __restrict__ 
 
 __global__ void __launch_bounds__(XCH_WARPS * 32) k_exchange_match(ExchangePeers P, int world, int cap, size_t slot_off, uint32_t epoch, const uint8_t* __restrict__ q,
                                                                    const int32_t* __restrict__ nq_dev, int capq, uint32_t* __restrict__ part,
-                                                                   int32_t* __restrict__ ticket, int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
+                                                                   int32_t* __restrict__ ticket, int32_t* __restrict__ timeouts, int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
     __shared__ uint4 tile[XCH_TILE][2];
     __shared__ int s_nt, s_last;
     const int p = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -82,8 +89,13 @@ __global__ void __launch_bounds__(XCH_WARPS * 32) k_exchange_match(ExchangePeers
     const bool active = qi < nQ;
     const uint8_t* slot = P.block[p] + slot_off;
     if (threadIdx.x == 0) {
-        while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(slot)) != epoch) __nanosleep(200);     // peer p has published this epoch
-        s_nt = min(max(reinterpret_cast<const volatile int32_t*>(slot)[1], 0), cap);
+        const uint64_t t0 = global_timer_ns();
+        bool there = true;
+        while (ld_acquire_sys(reinterpret_cast<const uint32_t*>(slot)) != epoch) {                     // peer p has published this epoch
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > XCH_WAIT_NS) { there = false; atomicAdd(timeouts, 1); break; }
+        }
+        s_nt = there ? min(max(reinterpret_cast<const volatile int32_t*>(slot)[1], 0), cap) : 0;
     }
     __syncthreads();
     const int nT = s_nt;
@@ -149,7 +161,7 @@ void exchange_free(pslam_ctx* c) {
     if (!c->exchange) return;
     ExchangeBuffers& B = *c->exchange;
     for (int r = 0; r < B.world; ++r) if (B.opened[r] && B.peer[r]) cudaIpcCloseMemHandle(B.peer[r]);
-    cudaFree(B.local); cudaFree(B.d_part); cudaFree(B.d_ticket);
+    cudaFree(B.local); cudaFree(B.d_part); cudaFree(B.d_ticket); cudaFree(B.d_timeouts);
     delete c->exchange;
     c->exchange = nullptr;
 }
@@ -170,6 +182,8 @@ int pslam_exchange_create(pslam_ctx* c, int cap_kp, int slots, void* ipc_handle_
     B.cap = cap_kp; B.slots = slots; B.slot_bytes = xch_slot_bytes(cap_kp);
     PSLAM_CUDA(c, cudaMalloc((void**)&B.local, B.slot_bytes * slots));
     PSLAM_CUDA(c, cudaMemset(B.local, 0, B.slot_bytes * slots));
+    PSLAM_CUDA(c, cudaMalloc((void**)&B.d_timeouts, 4));
+    PSLAM_CUDA(c, cudaMemset(B.d_timeouts, 0, 4));
     B.peer[0] = B.local; B.world = 1; B.rank = 0;
     cudaIpcMemHandle_t h;
     PSLAM_CUDA(c, cudaIpcGetMemHandle(&h, B.local));
@@ -224,8 +238,17 @@ int pslam_exchange_match_dev(pslam_ctx* c, int slot, uint32_t epoch, const uint8
     ExchangePeers P;
     for (int r = 0; r < XCH_MAX_WORLD; ++r) P.block[r] = r < B.world ? B.peer[r] : nullptr;
     PSLAM_LAUNCH(c, "exchange_match", k_exchange_match<<<dim3(tiles, B.world), XCH_WARPS * 32, 0, c->stream>>>(P, B.world, B.cap, (size_t)slot * B.slot_bytes, epoch,
-                 d_qdesc, d_nq, capq, B.d_part, B.d_ticket, d_idx, d_dist));
+                 d_qdesc, d_nq, capq, B.d_part, B.d_ticket, B.d_timeouts, d_idx, d_dist));
     PSLAM_CUDA(c, cudaGetLastError());
+    return PSLAM_OK;
+}
+
+int pslam_exchange_timeouts(pslam_ctx* c, int32_t* n_out) {
+    if (!c) return PSLAM_E_INVALID;
+    if (!c->exchange || !n_out) return set_error(c, PSLAM_E_INVALID, "exchange timeouts: create first / null pointer");
+    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    PSLAM_CUDA(c, cudaStreamSynchronize(c->stream));
+    PSLAM_CUDA(c, cudaMemcpy(n_out, c->exchange->d_timeouts, 4, cudaMemcpyDeviceToHost));
     return PSLAM_OK;
 }
 

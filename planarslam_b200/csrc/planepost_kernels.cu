@@ -7,9 +7,9 @@
 //                    RANSAC (mt19937(12345) sample shuffling, <= 50 iterations, inlier counts by the whole CTA) and the float least-squares refit through the
 //                    closed-form eigen33, sign kept like the reference
 //   k_planes_compact one thread block per frame: the planes that survive, in PEAC order, with their voxel clouds packed
-//   k_sn_*           surface normals of the 3x sub-sampled organised cloud: points + depth-change map (parallel), the two chamfer passes (one thread per frame:
-//                    raster-order dependence), 3-D gradients (parallel), integral images in double (one thread per frame and component: the recurrence fixes
-//                    the rounding), normals from rectangle sums (parallel), odd rows / columns gathered into vSurfaceNormal
+//   k_sn_*           surface normals of the 3x sub-sampled organised cloud: points + depth-change map (parallel), the two chamfer passes (one warp per frame: the lanes
+//                    evaluate the terms from the neighbouring row, lane 0 walks the in-row chain of rounded additions), 3-D gradients + integral images in
+//                    double (one warp per frame: rows of gradients built by all lanes, the recurrence walked by one lane per image and component), normals from rectangle sums (parallel), odd rows / columns gathered into vSurfaceNormal
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -33,7 +33,7 @@ struct PlanePostBuffers {
     // per (frame, plane) working records
     float* d_coef = nullptr; int32_t* d_valid = nullptr; int32_t* d_npts = nullptr; float* d_pts = nullptr; int32_t* d_stats = nullptr;     // [B][maxp][...]
     // surface normals scratch
-    float* d_cloud = nullptr; uint8_t* d_change = nullptr; float* d_dist = nullptr; float *d_gx = nullptr, *d_gy = nullptr; double *d_ix = nullptr, *d_iy = nullptr;
+    float* d_cloud = nullptr; float* d_dist = nullptr; double *d_ix = nullptr, *d_iy = nullptr;
     float* d_nrm = nullptr;
 };
 
@@ -47,6 +47,8 @@ __device__ __forceinline__ void pp_vertex(const uint16_t* __restrict__ depth, in
     z = (float)zz;
 }
 __device__ __forceinline__ float pp_dot4(const float c[4], float x, float y, float z) { return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c[0], x), __fmul_rn(c[1], y)), __fmul_rn(c[2], z)), c[3]); }
+
+__device__ uint32_t g_pp_mt[624];    // boost::mt19937(12345) after the first regeneration: identical for every plane, computed once on the host
 
 struct PPRng {                    // boost::mt19937(12345) >> 1, as pcl::SampleConsensusModel::rnd() draws it
     uint32_t* mt; int idx;
@@ -138,7 +140,6 @@ __global__ void __launch_bounds__(PP_THREADS) k_planes_post(const uint16_t* __re
     float* s_px = reinterpret_cast<float*>(s_cnt + PP_SLOTS);                                     // [3][PP_SLOTS] sorted centroids
     uint32_t* s_ord = reinterpret_cast<uint32_t*>(s_px + 3 * PP_SLOTS);                           // [PP_SLOTS] sort keys (voxel index << 11 | slot) / shuffled indices
     uint32_t* s_mt = s_ord + PP_SLOTS;                                                            // [624]
-    __shared__ float s_mn[3], s_mx[3], s_red[PP_THREADS / 32][6];
     __shared__ int s_i[8];
     __shared__ float s_model[4];
     const int pl = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -148,44 +149,46 @@ __global__ void __launch_bounds__(PP_THREADS) k_planes_post(const uint16_t* __re
     const int32_t* moff = moff_all + (size_t)frame * (maxp + 1);
     const int32_t* midx = midx_all + (size_t)frame * w * h + moff[pl];
     const int nm = moff[pl + 1] - moff[pl];
-    // ---- bounding box ----
-    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    for (int i = tid; i < nm; i += PP_THREADS) {
-        float x, y, z;
-        pp_vertex(depth, w, K, midx[i], x, y, z);
-        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z); mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
-    }
-    for (int k = 0; k < 3; ++k)
-        for (int o = 16; o; o >>= 1) { mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o)); mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o)); }
-    if (lane == 0) for (int k = 0; k < 3; ++k) { s_red[wid][k] = mn[k]; s_red[wid][3 + k] = mx[k]; }
     for (int i = tid; i < PP_SLOTS; i += PP_THREADS) { s_key[i] = PP_EMPTY; s_cnt[i] = 0; s_sum[i] = 0; s_sum[PP_SLOTS + i] = 0; s_sum[2 * PP_SLOTS + i] = 0; }
+    for (int i = tid; i < 624; i += PP_THREADS) s_mt[i] = g_pp_mt[i];
     if (tid == 0) { s_i[0] = 0; s_i[1] = 0; }
     __syncthreads();
-    if (tid < 3) { float a = FLT_MAX, b = -FLT_MAX; for (int q = 0; q < PP_THREADS / 32; ++q) { a = fminf(a, s_red[q][tid]); b = fmaxf(b, s_red[q][3 + tid]); } s_mn[tid] = a; s_mx[tid] = b; }
-    __syncthreads();
+    // ---- voxel accumulation (leaf 0.1 m, order-free fixed-point sums) ----
+    // pcl::VoxelGrid numbers a voxel i0 + i1 * div0 + i2 * div0 * div1 with i* = floor(coordinate * 10) - floor(minimum * 10): ascending index = lexicographic
+    // (i2, i1, i0), which the packed absolute key (iz, iy, ix) below orders identically - so no bounding-box pass is needed.  The members of a plane are in pixel
+    // order and neighbouring pixels mostly share a voxel: every thread walks a contiguous run of members and only touches the table when the voxel changes.
     const float inv = 10.0f;                                      // 1.0f / 0.1f rounds to 10.0f
-    int min_b[3], div_b[3];
-    for (int k = 0; k < 3; ++k) { min_b[k] = (int)floorf(__fmul_rn(s_mn[k], inv)); div_b[k] = (int)floorf(__fmul_rn(s_mx[k], inv)) - min_b[k] + 1; }
-    const int mul1 = div_b[0], mul2 = div_b[0] * div_b[1];
-    // ---- voxel accumulation (order-free fixed-point sums) ----
-    for (int i = tid; i < nm; i += PP_THREADS) {
-        float x, y, z;
-        pp_vertex(depth, w, K, midx[i], x, y, z);
-        const int i0 = (int)__fsub_rn(floorf(__fmul_rn(x, inv)), (float)min_b[0]), i1 = (int)__fsub_rn(floorf(__fmul_rn(y, inv)), (float)min_b[1]),
-                  i2 = (int)__fsub_rn(floorf(__fmul_rn(z, inv)), (float)min_b[2]);
-        const uint32_t key = (uint32_t)(i0 + i1 * mul1 + i2 * mul2);
-        uint32_t slot = (key * 2654435761u) >> 21;                 // 11 bits
-        bool placed = false;
-        for (int probe = 0; probe < PP_SLOTS; ++probe) {
-            const uint32_t cur = atomicCAS(&s_key[slot], PP_EMPTY, key);
-            if (cur == PP_EMPTY || cur == key) { placed = true; break; }
-            slot = (slot + 1) & (PP_SLOTS - 1);
+    {
+        const int chunk = (nm + PP_THREADS - 1) / PP_THREADS;
+        const int i_end = min(nm, (tid + 1) * chunk);
+        uint32_t run_key = PP_EMPTY, run_cnt = 0;
+        long long rx = 0, ry = 0, rz = 0;
+        auto flush = [&]() {
+            if (run_key == PP_EMPTY) return;
+            uint32_t slot = (run_key * 2654435761u) >> 21;         // 11 bits
+            bool placed = false;
+            for (int probe = 0; probe < PP_SLOTS; ++probe) {
+                const uint32_t cur = atomicCAS(&s_key[slot], PP_EMPTY, run_key);
+                if (cur == PP_EMPTY || cur == run_key) { placed = true; break; }
+                slot = (slot + 1) & (PP_SLOTS - 1);
+            }
+            if (!placed) { atomicOr(&s_i[1], 1); return; }
+            atomicAdd(&s_cnt[slot], run_cnt);
+            atomicAdd(&s_sum[slot], (unsigned long long)rx);
+            atomicAdd(&s_sum[PP_SLOTS + slot], (unsigned long long)ry);
+            atomicAdd(&s_sum[2 * PP_SLOTS + slot], (unsigned long long)rz);
+        };
+        for (int i = tid * chunk; i < i_end; ++i) {
+            float x, y, z;
+            pp_vertex(depth, w, K, midx[i], x, y, z);
+            const int i0 = (int)floorf(__fmul_rn(x, inv)) + 512, i1 = (int)floorf(__fmul_rn(y, inv)) + 512, i2 = (int)floorf(__fmul_rn(z, inv));
+            if ((unsigned)i0 > 1023u || (unsigned)i1 > 1023u || (unsigned)i2 >= 4095u) { atomicOr(&s_i[1], 1); continue; }      // > 51 m sideways / 409 m deep: capacity flag
+            const uint32_t key = ((uint32_t)i2 << 20) | ((uint32_t)i1 << 10) | (uint32_t)i0;
+            if (key != run_key) { flush(); run_key = key; run_cnt = 0; rx = ry = rz = 0; }
+            ++run_cnt;
+            rx += llrint((double)x * 1048576.0); ry += llrint((double)y * 1048576.0); rz += llrint((double)z * 1048576.0);
         }
-        if (!placed) { atomicOr(&s_i[1], 1); continue; }
-        atomicAdd(&s_cnt[slot], 1u);
-        atomicAdd(&s_sum[slot], (unsigned long long)llrint((double)x * 1048576.0));
-        atomicAdd(&s_sum[PP_SLOTS + slot], (unsigned long long)llrint((double)y * 1048576.0));
-        atomicAdd(&s_sum[2 * PP_SLOTS + slot], (unsigned long long)llrint((double)z * 1048576.0));
+        flush();
     }
     __syncthreads();
     // ---- order the occupied voxels by index: bitonic sort of (key, slot) pairs; empty slots sort last ----
@@ -224,8 +227,7 @@ __global__ void __launch_bounds__(PP_THREADS) k_planes_post(const uint16_t* __re
     // ---- RANSAC (pcl::RandomSampleConsensus on SampleConsensusModelPlane) ----
     uint32_t* shuffled = s_ord;                                   // the sort order is no longer needed
     for (int i = tid; i < N; i += PP_THREADS) shuffled[i] = (uint32_t)i;
-    PPRng rng; rng.mt = s_mt; rng.idx = 624;
-    if (tid == 0) rng.seed(12345u);
+    PPRng rng; rng.mt = s_mt; rng.idx = 0;                       // s_mt: mt19937(12345) after its first twist (copied from g_pp_mt above)
     __syncthreads();
     int best_count = -INT_MAX, iterations = 0;
     double k = 1.0;
@@ -377,74 +379,131 @@ __global__ void k_sn_points(const uint16_t* __restrict__ depth_all, int w, int h
     float* p = cloud + ((size_t)frame * W3 * H3 + i) * 3;
     p[2] = d; p[0] = __fdiv_rn(__fmul_rn(__fsub_rn((float)n, K.cx), d), K.fx); p[1] = __fdiv_rn(__fmul_rn(__fsub_rn((float)m, K.cy), d), K.fy);
 }
-// depth-change map + both chamfer passes: one thread per frame (raster-order dependence); dist has one guard element before and after the image
-__global__ void k_sn_chamfer(int nframes, int W3, int H3, const float* __restrict__ cloud_all, uint8_t* __restrict__ change_all, float* __restrict__ dist_all) {
-    const int frame = blockIdx.x * blockDim.x + threadIdx.x;
-    if (frame >= nframes) return;
-    const size_t NP = (size_t)W3 * H3;
-    const float* pts = cloud_all + (size_t)frame * NP * 3;
-    uint8_t* change = change_all + (size_t)frame * NP;
-    float* dist = dist_all + (size_t)frame * (NP + 2);
-    float* dm = dist + 1;
-    for (size_t i = 0; i < NP; ++i) change[i] = 255;
-    for (int ri = 0; ri < H3 - 1; ++ri)
-        for (int ci = 0; ci < W3 - 1; ++ci) {
-            const size_t idx = (size_t)ri * W3 + ci;
-            const float dep = pts[idx * 3 + 2], depR = pts[(idx + 1) * 3 + 2], depD = pts[(idx + W3) * 3 + 2];
-            const float tol = __fmul_rn(__fmul_rn(0.05f, __fadd_rn(fabsf(dep), 1.0f)), 2.0f);
-            if (fabsf(__fsub_rn(dep, depR)) > tol || !isfinite(dep) || !isfinite(depR)) { change[idx] = 0; change[idx + 1] = 0; }
-            if (fabsf(__fsub_rn(dep, depD)) > tol || !isfinite(dep) || !isfinite(depD)) { change[idx] = 0; change[idx + W3] = 0; }
-        }
-    const float far = (float)(W3 + H3);
-    for (size_t i = 0; i < NP; ++i) dm[i] = change[i] == 0 ? 0.0f : far;
-    dist[0] = far; dist[NP + 1] = far;
-    for (int ri = 1; ri < H3; ++ri) {
-        float* prev = dm + (size_t)(ri - 1) * W3; float* cur = dm + (size_t)ri * W3;
-        for (int ci = 1; ci < W3; ++ci) {
-            const float upLeft = __fadd_rn(prev[ci - 1], 1.4f), up = __fadd_rn(prev[ci], 1.0f), upRight = __fadd_rn(prev[ci + 1], 1.4f), left = __fadd_rn(cur[ci - 1], 1.0f);
-            const float mv = fminf(fminf(upLeft, up), fminf(left, upRight));
-            if (mv < cur[ci]) cur[ci] = mv;
-        }
-    }
-    for (int ri = H3 - 2; ri >= 0; --ri) {
-        float* next = dm + (size_t)(ri + 1) * W3; float* cur = dm + (size_t)ri * W3;
-        for (int ci = W3 - 2; ci >= 0; --ci) {
-            const float lowerLeft = __fadd_rn(next[ci - 1], 1.4f), lower = __fadd_rn(next[ci], 1.0f), lowerRight = __fadd_rn(next[ci + 1], 1.4f), right = __fadd_rn(cur[ci + 1], 1.0f);
-            const float mv = fminf(fminf(lowerLeft, lower), fminf(right, lowerRight));
-            if (mv < cur[ci]) cur[ci] = mv;
-        }
-    }
+// depth-change map -> initial distance map (0 at a depth change, W3 + H3 elsewhere): one thread per point.  The reference loop visits (ri, ci) with ri < H3 - 1,
+// ci < W3 - 1 and clears the visited point and its right / lower neighbour when the depth step exceeds the tolerance: a point is cleared by its own two tests, by
+// the right-test of its left neighbour or by the down-test of its upper neighbour.  dist has one guard element before and after the image.
+__device__ __forceinline__ bool sn_step(float dep, float other) {
+    const float tol = __fmul_rn(__fmul_rn(0.05f, __fadd_rn(fabsf(dep), 1.0f)), 2.0f);
+    return fabsf(__fsub_rn(dep, other)) > tol || !isfinite(dep) || !isfinite(other);
 }
-__global__ void k_sn_gradients(int W3, int H3, const float* __restrict__ cloud_all, float* __restrict__ gx_all, float* __restrict__ gy_all) {
+__global__ void k_sn_change(int W3, int H3, const float* __restrict__ cloud_all, float* __restrict__ dist_all) {
     const int frame = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W3 * H3) return;
-    const int r = i / W3, c = i - r * W3;
     const size_t NP = (size_t)W3 * H3;
+    if (i >= W3 * H3) return;
     const float* pts = cloud_all + (size_t)frame * NP * 3;
-    float gx[3] = {0, 0, 0}, gy[3] = {0, 0, 0};
-    if (r >= 1 && r < H3 - 1 && c >= 1 && c < W3 - 1)
-        for (int k = 0; k < 3; ++k) { gx[k] = __fsub_rn(pts[((size_t)i + 1) * 3 + k], pts[((size_t)i - 1) * 3 + k]); gy[k] = __fsub_rn(pts[((size_t)i + W3) * 3 + k], pts[((size_t)i - W3) * 3 + k]); }
-    for (int k = 0; k < 3; ++k) { gx_all[((size_t)frame * NP + i) * 3 + k] = gx[k]; gy_all[((size_t)frame * NP + i) * 3 + k] = gy[k]; }
+    float* dist = dist_all + (size_t)frame * (NP + 2);
+    const int r = i / W3, c = i - r * W3;
+    const float dep = pts[(size_t)i * 3 + 2];
+    bool cleared = false;
+    if (r < H3 - 1 && c < W3 - 1) cleared = sn_step(dep, pts[((size_t)i + 1) * 3 + 2]) || sn_step(dep, pts[((size_t)i + W3) * 3 + 2]);
+    if (!cleared && c >= 1 && r < H3 - 1) cleared = sn_step(pts[((size_t)i - 1) * 3 + 2], dep);
+    if (!cleared && r >= 1 && c < W3 - 1) cleared = sn_step(pts[((size_t)i - W3) * 3 + 2], dep);
+    const float far = (float)(W3 + H3);
+    dist[1 + i] = cleared ? 0.0f : far;
+    if (i == 0) { dist[0] = far; dist[NP + 1] = far; }
 }
-// integral images in double: thread (frame, image, component); I[r+1][c+1] = I[r][c+1] + I[r+1][c] - I[r][c] (+ element when the 3-vector is finite)
-__global__ void k_sn_integral(int nframes, int W3, int H3, const float* __restrict__ gx_all, const float* __restrict__ gy_all, double* __restrict__ ix_all, double* __restrict__ iy_all) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nframes * 6) return;
-    const int frame = t / 6, which = (t % 6) / 3, k = t % 3;
-    const size_t NP = (size_t)W3 * H3, NI = (size_t)(W3 + 1) * (H3 + 1);
-    const float* src = (which ? gy_all : gx_all) + (size_t)frame * NP * 3;
-    double* I = (which ? iy_all : ix_all) + (size_t)frame * NI * 3;
-    for (int c = 0; c <= W3; ++c) I[(size_t)c * 3 + k] = 0.0;
-    for (int r = 0; r < H3; ++r) {
-        I[((size_t)(r + 1) * (W3 + 1)) * 3 + k] = 0.0;
-        double left = 0.0;                                            // I[r + 1][c]
-        for (int c = 0; c < W3; ++c) {
-            double v = __dsub_rn(__dadd_rn(I[((size_t)r * (W3 + 1) + c + 1) * 3 + k], left), I[((size_t)r * (W3 + 1) + c) * 3 + k]);
-            const float* e = src + ((size_t)r * W3 + c) * 3;
-            if (isfinite(e[0]) && isfinite(e[1]) && isfinite(e[2])) v = __dadd_rn(v, (double)e[k]);
-            I[((size_t)(r + 1) * (W3 + 1) + c + 1) * 3 + k] = v;
-            left = v;
+// The two chamfer passes (1.0 / 1.4 weights, float): one warp per frame.  Each row's three terms from the neighbouring row are evaluated by all lanes; what
+// remains is d[c] = min(m[c], d[c -+ 1] + 1.0f) along the row, a chain of rounded float additions that lane 0 walks in order (the rounding of x + 1.0f + 1.0f ...
+// is not that of x + n, so the chain is kept).  Like the reference loop, the forward pass reads prev[W3] = cur[0] and the backward pass next[-1] = cur[W3 - 1].
+#define SN_WARPS 4
+__global__ void __launch_bounds__(SN_WARPS * 32) k_sn_chamfer(int nframes, int W3, int H3, float* __restrict__ dist_all) {
+    extern __shared__ __align__(16) unsigned char sn_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.x * SN_WARPS + wid;
+    if (frame >= nframes) return;
+    const int RS = W3 + 2;                                             // row stride in shared memory: element c lives at [c + 1]
+    float* rowA = reinterpret_cast<float*>(sn_smem) + (size_t)wid * 3 * RS;
+    float* rowB = rowA + RS;
+    float* m = rowB + RS;
+    const size_t NP = (size_t)W3 * H3;
+    float* dm = dist_all + (size_t)frame * (NP + 2) + 1;
+    float* prev = rowA; float* cur = rowB;
+    for (int c = lane; c < W3; c += 32) prev[c + 1] = dm[c];
+    for (int ri = 1; ri < H3; ++ri) {
+        float* g = dm + (size_t)ri * W3;
+        for (int c = lane; c < W3; c += 32) cur[c + 1] = g[c];
+        __syncwarp();
+        if (lane == 0) prev[W3 + 1] = cur[1];
+        __syncwarp();
+        for (int c = 1 + lane; c < W3; c += 32)
+            m[c] = fminf(fminf(cur[c + 1], __fadd_rn(prev[c], 1.4f)), fminf(__fadd_rn(prev[c + 1], 1.0f), __fadd_rn(prev[c + 2], 1.4f)));
+        __syncwarp();
+        if (lane == 0) {
+            float d = cur[1];
+#pragma unroll 8
+            for (int c = 1; c < W3; ++c) { d = fminf(m[c], __fadd_rn(d, 1.0f)); cur[c + 1] = d; }
         }
+        __syncwarp();
+        for (int c = lane; c < W3; c += 32) g[c] = cur[c + 1];
+        float* t = prev; prev = cur; cur = t;
+    }
+    // backward: `prev` holds the last row (its final values)
+    float* next = prev;
+    for (int ri = H3 - 2; ri >= 0; --ri) {
+        float* g = dm + (size_t)ri * W3;
+        for (int c = lane; c < W3; c += 32) cur[c + 1] = g[c];
+        __syncwarp();
+        if (lane == 0) next[0] = cur[W3];
+        __syncwarp();
+        for (int c = lane; c < W3 - 1; c += 32)
+            m[c] = fminf(fminf(cur[c + 1], __fadd_rn(next[c], 1.4f)), fminf(__fadd_rn(next[c + 1], 1.0f), __fadd_rn(next[c + 2], 1.4f)));
+        __syncwarp();
+        if (lane == 0) {
+            float d = cur[W3];
+#pragma unroll 8
+            for (int c = W3 - 2; c >= 0; --c) { d = fminf(m[c], __fadd_rn(d, 1.0f)); cur[c + 1] = d; }
+        }
+        __syncwarp();
+        for (int c = lane; c < W3; c += 32) g[c] = cur[c + 1];
+        float* t = next; next = cur; cur = t;
+    }
+}
+// 3-D gradients (central differences of the organised cloud, zero on the image border) and their integral images in double, one warp per frame: all lanes
+// build row r of the six gradient components in shared memory; lanes 0..5 (image x / y, component) then walk the recurrence
+//     I[r+1][c+1] = (I[r][c+1] + I[r+1][c]) - I[r][c]  (+ element when the 3-vector is finite)
+// along the row in place over the previous row (the rounding of every step is the reference's), and all lanes store the finished row.
+__global__ void __launch_bounds__(SN_WARPS * 32) k_sn_integral(int nframes, int W3, int H3, const float* __restrict__ cloud_all, double* __restrict__ ix_all, double* __restrict__ iy_all) {
+    extern __shared__ __align__(16) unsigned char sn_smem[];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, frame = blockIdx.x * SN_WARPS + wid;
+    if (frame >= nframes) return;
+    const int RI = (W3 + 1) * 3, RE = W3 * 3;
+    const size_t per_warp = (size_t)2 * RI * sizeof(double) + (size_t)2 * RE * sizeof(float);
+    double* buf = reinterpret_cast<double*>(sn_smem + (size_t)wid * ((per_warp + 15) & ~(size_t)15));     // [2][RI]
+    float* e = reinterpret_cast<float*>(buf + 2 * RI);                                                    // [2][RE]
+    const size_t NP = (size_t)W3 * H3, NI = (size_t)(W3 + 1) * (H3 + 1);
+    const float* pts = cloud_all + (size_t)frame * NP * 3;
+    double* IX = ix_all + (size_t)frame * NI * 3;
+    double* IY = iy_all + (size_t)frame * NI * 3;
+    for (int i = lane; i < 2 * RI; i += 32) buf[i] = 0.0;
+    for (int i = lane; i < RI; i += 32) { IX[i] = 0.0; IY[i] = 0.0; }
+    __syncwarp();
+    for (int r = 0; r < H3; ++r) {
+        const bool inner_r = r >= 1 && r < H3 - 1;
+        const float* row = pts + (size_t)r * W3 * 3;
+        for (int i = lane; i < RE; i += 32) {
+            float gx = 0.0f, gy = 0.0f;
+            if (inner_r && i >= 3 && i < RE - 3) { gx = __fsub_rn(row[i + 3], row[i - 3]); gy = __fsub_rn(row[i + RE], row[i - RE]); }
+            e[i] = gx; e[RE + i] = gy;
+        }
+        __syncwarp();
+        if (lane < 6) {
+            const int which = lane / 3, k = lane - which * 3;
+            double* b = buf + which * RI;
+            const float* ev = e + which * RE;
+            double left = 0.0, pc = b[k];                                 // I[r][0] (= 0)
+            b[k] = 0.0;                                                   // I[r + 1][0]
+            for (int c = 0; c < W3; ++c) {
+                const double pc1 = b[(c + 1) * 3 + k];
+                double v = __dsub_rn(__dadd_rn(pc1, left), pc);
+                const float e0 = ev[c * 3], e1 = ev[c * 3 + 1], e2 = ev[c * 3 + 2];
+                if (isfinite(e0) && isfinite(e1) && isfinite(e2)) v = __dadd_rn(v, (double)ev[c * 3 + k]);
+                b[(c + 1) * 3 + k] = v;
+                left = v; pc = pc1;
+            }
+        }
+        __syncwarp();
+        double* ox = IX + (size_t)(r + 1) * RI; double* oy = IY + (size_t)(r + 1) * RI;
+        for (int i = lane; i < RI; i += 32) { ox[i] = buf[i]; oy[i] = buf[RI + i]; }
+        __syncwarp();
     }
 }
 __global__ void k_sn_normals(int W3, int H3, const float* __restrict__ cloud_all, const float* __restrict__ dist_all, const double* __restrict__ ix_all,
@@ -499,8 +558,7 @@ __global__ void k_sn_gather(int W3, int H3, const float* __restrict__ cloud_all,
 void planepost_free(pslam_ctx* c) {
     if (!c->planepost) return;
     PlanePostBuffers& B = *c->planepost;
-    for (void* p : {(void*)B.d_coef, (void*)B.d_valid, (void*)B.d_npts, (void*)B.d_pts, (void*)B.d_stats, (void*)B.d_cloud, (void*)B.d_change, (void*)B.d_dist, (void*)B.d_gx,
-                    (void*)B.d_gy, (void*)B.d_ix, (void*)B.d_iy, (void*)B.d_nrm})
+    for (void* p : {(void*)B.d_coef, (void*)B.d_valid, (void*)B.d_npts, (void*)B.d_pts, (void*)B.d_stats, (void*)B.d_cloud, (void*)B.d_dist, (void*)B.d_ix, (void*)B.d_iy, (void*)B.d_nrm})
         if (p) cudaFree(p);
     delete c->planepost;
     c->planepost = nullptr;
@@ -514,11 +572,22 @@ static int planepost_alloc(pslam_ctx* c) {
     B.max_batch = c->cfg.max_batch; B.maxp = pslam_peac_max_planes(c);
     if (B.maxp > PP_MAX_PLANES) { planepost_free(c); return set_error(c, PSLAM_E_INVALID, "plane capacity above the post-processing limit"); }
     B.w3 = (c->cfg.width + 2) / 3; B.h3 = (c->cfg.height + 2) / 3;
+    {   // mt19937(12345) seeded and regenerated once (what the first draw of every RANSAC run sees)
+        uint32_t mt[624];
+        mt[0] = 12345u;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        for (int i = 0; i < 624; ++i) {
+            const uint32_t y = (mt[i] & 0x80000000u) | (mt[(i + 1) % 624] & 0x7fffffffu);
+            mt[i] = mt[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        const int rc_ = check_cuda(c, cudaMemcpyToSymbol(g_pp_mt, mt, sizeof mt), "cudaMemcpyToSymbol(mt19937)");
+        if (rc_ != PSLAM_OK) { planepost_free(c); return rc_; }
+    }
     const size_t nb = B.max_batch, np = (size_t)B.w3 * B.h3, ni = (size_t)(B.w3 + 1) * (B.h3 + 1);
 #define PA(ptr, bytes) do { const int rc_ = check_cuda(c, cudaMalloc((void**)&(ptr), (bytes)), "cudaMalloc(planepost)"); if (rc_ != PSLAM_OK) { planepost_free(c); return rc_; } } while (0)
     PA(B.d_coef, nb * B.maxp * 16); PA(B.d_valid, nb * B.maxp * 4); PA(B.d_npts, nb * B.maxp * 4); PA(B.d_stats, nb * B.maxp * 8);
     PA(B.d_pts, nb * B.maxp * (size_t)PP_SLOTS * 12);
-    PA(B.d_cloud, nb * np * 12); PA(B.d_change, nb * np); PA(B.d_dist, nb * (np + 2) * 4); PA(B.d_gx, nb * np * 12); PA(B.d_gy, nb * np * 12);
+    PA(B.d_cloud, nb * np * 12); PA(B.d_dist, nb * (np + 2) * 4);
     PA(B.d_ix, nb * ni * 24); PA(B.d_iy, nb * ni * 24); PA(B.d_nrm, nb * np * 12);
 #undef PA
     return PSLAM_OK;
@@ -569,9 +638,18 @@ int pslam_surface_normals_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int n
     const int np = B.w3 * B.h3, n_out = pslam_surface_normals_count(c);
     const dim3 gp((np + 255) / 256, nframes);
     PSLAM_LAUNCH(c, "sn_points", k_sn_points<<<gp, 256, 0, st>>>(d_depth, c->cfg.width, c->cfg.height, B.w3, B.h3, K, B.d_cloud));
-    PSLAM_LAUNCH(c, "sn_chamfer", k_sn_chamfer<<<(nframes + 31) / 32, 32, 0, st>>>(nframes, B.w3, B.h3, B.d_cloud, B.d_change, B.d_dist));
-    PSLAM_LAUNCH(c, "sn_gradients", k_sn_gradients<<<gp, 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_gx, B.d_gy));
-    PSLAM_LAUNCH(c, "sn_integral", k_sn_integral<<<(nframes * 6 + 63) / 64, 64, 0, st>>>(nframes, B.w3, B.h3, B.d_gx, B.d_gy, B.d_ix, B.d_iy));
+    const size_t smem_ch = (size_t)SN_WARPS * 3 * (B.w3 + 2) * sizeof(float);
+    const size_t smem_ii = (size_t)SN_WARPS * (((size_t)2 * (B.w3 + 1) * 3 * sizeof(double) + (size_t)2 * B.w3 * 3 * sizeof(float) + 15) & ~(size_t)15);
+    if (smem_ch > 227 * 1024 || smem_ii > 227 * 1024) return set_error(c, PSLAM_E_INVALID, "surface normals: image too wide for the row buffers");
+    static bool attr_set = false;
+    if (!attr_set) {
+        PSLAM_CUDA(c, cudaFuncSetAttribute(k_sn_chamfer, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PSLAM_CUDA(c, cudaFuncSetAttribute(k_sn_integral, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    PSLAM_LAUNCH(c, "sn_change", k_sn_change<<<gp, 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_dist));
+    PSLAM_LAUNCH(c, "sn_chamfer", k_sn_chamfer<<<(nframes + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem_ch, st>>>(nframes, B.w3, B.h3, B.d_dist));
+    PSLAM_LAUNCH(c, "sn_integral", k_sn_integral<<<(nframes + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem_ii, st>>>(nframes, B.w3, B.h3, B.d_cloud, B.d_ix, B.d_iy));
     PSLAM_LAUNCH(c, "sn_normals", k_sn_normals<<<gp, 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_dist, B.d_ix, B.d_iy, B.d_nrm));
     PSLAM_LAUNCH(c, "sn_gather", k_sn_gather<<<dim3((n_out + 255) / 256, nframes), 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_nrm, d_normals8, d_normals3, n_out));
     PSLAM_CUDA(c, cudaGetLastError());
