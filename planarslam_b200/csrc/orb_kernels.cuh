@@ -564,6 +564,10 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+#define OD_R 18                       // the pattern's largest radius is 18.38: a rotated, rounded coordinate stays within +-18.  Key points are >= 19 pixels from
+                                      // the level border, so the staged rows (and the word-aligned overshoot of <= 3 bytes either side) stay inside the level
+#define OD_ROWS (2 * OD_R + 1)
+#define OD_WORDS 10                   // 37 bytes + up to 3 bytes of misalignment = 40
 __global__ void __launch_bounds__(256) k_orient_describe(OrbGeom g, const uint8_t* __restrict__ gray, const uint8_t* __restrict__ pyr,
                                                          const uint8_t* __restrict__ blur, int blur_frame_bytes,
                                                          const uint32_t* __restrict__ lvl_kp, const int32_t* __restrict__ lvl_cnt,
@@ -591,24 +595,42 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbGeom g, const uint8_
     const uint8_t* img = level_ptr(g, gray, pyr, frame, level, pitch);
     const uint8_t* c = img + (size_t)y * pitch + x;
 
-    // IC_Angle: lane r sums row v = r - 15 of the radius-15 disc
+    // IC_Angle over the radius-15 disc: lane = column u = lane - 15, rows walked in order, so that every load instruction of the warp reads 31 consecutive
+    // bytes (one or two sectors) instead of one byte from each of 31 rows; integer moments, so the summation order is free
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int v = lane - 15, d = g.umax[v < 0 ? -v : v];
-        const uint8_t* rowp = c + v * pitch;
-        int s = 0;
-        for (int u = -d; u <= d; ++u) { const int val = rowp[u]; m10 += u * val; s += val; }
-        m01 = v * s;
+    {
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        int col = 0;
+        if (lane < 31) {
+#pragma unroll
+            for (int v = -15; v <= 15; ++v) {
+                const int val = (au <= g.umax[v < 0 ? -v : v]) ? (int)c[v * pitch + u] : 0;
+                col += val; m01 += v * val;
+            }
+        }
+        m10 = u * col;
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
     const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    // steered BRIEF on the blurred level: lane i produces descriptor byte i
+    // steered BRIEF on the blurred level: the 37 x 37 patch around the key point (the rotated pattern stays within +-18) is staged in shared memory with
+    // coalesced word loads, then lane i gathers its 16 samples from there and produces descriptor byte i
     const float ar = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.f));
     const float a = (float)cos((double)ar), b = (float)sin((double)ar);
     const int bp = L.blur_pitch;
     const uint8_t* bc = blur + (size_t)frame * blur_frame_bytes + L.blur_off + (size_t)y * bp + x;
+    __shared__ uint32_t s_patch[8][OD_ROWS * OD_WORDS];
+    uint32_t* sp = s_patch[threadIdx.x >> 5];
+    const uintptr_t left = reinterpret_cast<uintptr_t>(bc - OD_R);
+    const int sh = (int)(left & 3);                                    // the patch row starts sh bytes into its first word; bp is a multiple of 4
+    const uint8_t* base = bc - OD_R - sh - (size_t)OD_R * bp;           // word-aligned start of the top row
+    for (int i = lane; i < OD_ROWS * OD_WORDS; i += 32) {
+        const int r = i / OD_WORDS, wd = i - r * OD_WORDS;
+        sp[i] = *reinterpret_cast<const uint32_t*>(base + (size_t)r * bp + 4 * wd);
+    }
+    __syncwarp();
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(sp) + OD_R * (OD_WORDS * 4) + OD_R + sh;      // the key point inside the staged patch
     const int8_t* pat = c_pattern + lane * 32;
     int val = 0;
 #pragma unroll
@@ -619,7 +641,7 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbGeom g, const uint8_
             const float px = (float)pat[4 * k + 2 * e], py = (float)pat[4 * k + 2 * e + 1];
             const int yy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int xx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            t[e] = bc[yy * bp + xx];
+            t[e] = sb[yy * (OD_WORDS * 4) + xx];
         }
         val |= (t[0] < t[1]) << k;
     }

@@ -178,8 +178,9 @@ static __device__ __noinline__ bool solve6(const double H[6][6], const double b[
     return true;
 }
 
-#define POSE_THREADS 256
+#define POSE_THREADS 256                 // upper bound of the block size (single problems, track_chain.cu); batches launch PSLAM_POSE_THREADS (pose_pipeline.cu)
 #define POSE_WARPS (POSE_THREADS / 32)
+#define POSE_NT ((int)blockDim.x)
 
 // deterministic block reduction of NV doubles held per thread: result broadcast in out[] (shared)
 template <int NV>
@@ -195,7 +196,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_part /*[POS
     __syncthreads();
     if (threadIdx.x < NV) {
         double t = 0;
-        for (int w = 0; w < POSE_WARPS; ++w) t += s_part[w * NV + threadIdx.x];
+        for (int w = 0; w < (POSE_NT >> 5); ++w) t += s_part[w * NV + threadIdx.x];
         s_out[threadIdx.x] = t;
     }
     __syncthreads();
@@ -205,7 +206,7 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double* s_part /*[POS
 static __device__ __noinline__ double pose_active_chi(const PoseEdgeDev* E, int ne, const uint8_t* level, double* err, const dSE3& Tq, const PoseCam& K,
                                                bool robust, double* s_part, double* s_red) {
     double acc[1] = {0};
-    for (int i = threadIdx.x; i < ne; i += POSE_THREADS) {
+    for (int i = threadIdx.x; i < ne; i += POSE_NT) {
         if (level[i]) continue;
         const PoseEdgeDev& e = E[i];
         double e3[3];
@@ -249,14 +250,14 @@ static __global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const
         T0.t = dv(hd.Tcw0[3], hd.Tcw0[7], hd.Tcw0[11]);
     }
     PoseOutDev& out = outs[prob];
-    for (int i = tid; i < 12; i += POSE_THREADS) out.trace_i[i] = -1;
-    for (int i = tid; i < 8; i += POSE_THREADS) out.trace_d[i] = 0;
-    for (int i = tid; i < hd.n_pt; i += POSE_THREADS) fl[0][i] = 0;
-    for (int i = tid; i < hd.n_line; i += POSE_THREADS) fl[1][i] = 0;
-    for (int i = tid; i < hd.n_plane; i += POSE_THREADS) fl[2][i] = 0;
-    for (int i = tid; i < hd.n_par; i += POSE_THREADS) fl[3][i] = 0;
-    for (int i = tid; i < hd.n_ver; i += POSE_THREADS) fl[4][i] = 0;
-    for (int i = tid; i < ne; i += POSE_THREADS) {
+    for (int i = tid; i < 12; i += POSE_NT) out.trace_i[i] = -1;
+    for (int i = tid; i < 8; i += POSE_NT) out.trace_d[i] = 0;
+    for (int i = tid; i < hd.n_pt; i += POSE_NT) fl[0][i] = 0;
+    for (int i = tid; i < hd.n_line; i += POSE_NT) fl[1][i] = 0;
+    for (int i = tid; i < hd.n_plane; i += POSE_NT) fl[2][i] = 0;
+    for (int i = tid; i < hd.n_par; i += POSE_NT) fl[3][i] = 0;
+    for (int i = tid; i < hd.n_ver; i += POSE_NT) fl[4][i] = 0;
+    for (int i = tid; i < ne; i += POSE_NT) {
         level[i] = 0;
         double e3[3] = {0, 0, 0};
         if (pk_is_plane(E[i].kind)) pose_edge_error(E[i], T0, K, e3);      // computeError() while the graph is built (:896,:935,:975,:3300)
@@ -301,7 +302,7 @@ static __global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const
             double acc[27];
 #pragma unroll
             for (int k = 0; k < 27; ++k) acc[k] = 0;
-            for (int i = tid; i < ne; i += POSE_THREADS) {
+            for (int i = tid; i < ne; i += POSE_NT) {
                 if (level[i]) continue;
                 const PoseEdgeDev& e = E[i];
                 double J[3][6];
@@ -375,7 +376,7 @@ static __global__ void __launch_bounds__(POSE_THREADS) k_pose_optimization(const
         }
         // ---- classify every edge against its chi-square threshold (:1006-1259) ----
         double nb[1] = {0};
-        for (int i = tid; i < ne; i += POSE_THREADS) {
+        for (int i = tid; i < ne; i += POSE_NT) {
             const PoseEdgeDev& e = E[i];
             if (pk_is_point(e.kind)) {
                 uint8_t& f = fl[0][e.idx];

@@ -140,7 +140,10 @@ int pose_pack_upload(pslam_ctx* c, const pslam_pose_problem* probs, int n, const
 int pose_run_packed(pslam_ctx* c) {
     if (!c->pose || c->pose->n_prob < 1) return set_error(c, PSLAM_E_INVALID, "no packed pose problems");
     PoseBuffers& B = *c->pose;
-    PSLAM_LAUNCH(c, "pose_optimization", k_pose_optimization<<<B.n_prob, POSE_THREADS, 0, c->stream>>>(B.d_hdr, B.d_edges, B.d_err, B.d_level, B.d_flags[0],
+    // a batch is throughput-bound: the kernel's serial stretches (6x6 solve, barriers between the reductions) leave an SM idle unless several problems share
+    // it, and the register count allows 65536 / (regs x threads) of them - so a batch runs narrow CTAs (PSLAM_POSE_THREADS: 64, 128 or 256)
+    static const int nt = [] { const char* e = getenv("PSLAM_POSE_THREADS"); const int v = e ? atoi(e) : 64; return (v == 64 || v == 128 || v == 256) ? v : 64; }();
+    PSLAM_LAUNCH(c, "pose_optimization", k_pose_optimization<<<B.n_prob, nt, 0, c->stream>>>(B.d_hdr, B.d_edges, B.d_err, B.d_level, B.d_flags[0],
                  B.d_flags[1], B.d_flags[2], B.d_flags[3], B.d_flags[4], B.d_out));
     PSLAM_CUDA(c, cudaGetLastError());
     return PSLAM_OK;
