@@ -33,12 +33,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-W, H = 640, 480
+# BASELINE.json configs: the default is configs[1] (640x480, 1000 ORB features), the configuration the metric is quoted on.  PSLAM_CONFIG=5 runs configs[4]
+# (1280x960, 2000 features, frame-sharded with the peer-memory descriptor exchange) with the same step structure; it reports metric rgbd_frames_per_sec_1280x960.
+CONFIG = os.environ.get("PSLAM_CONFIG", "2")
+W, H = (1280, 960) if CONFIG == "5" else (640, 480)
+NFEATURES = 2000 if CONFIG == "5" else 1000
+AREA = (W * H) // (640 * 480)                                   # frames of config 5 carry 4x the pixels: per-frame byte counts and batch sizes scale with it
+K_CAM = tuple(k * W / 640.0 for k in (535.4, 539.2, 320.1, 247.6))
 # Frames per library call (context max_batch).  The serial-order kernels run one warp per frame, so throughput scales with
 # frames in flight; the default is one full wave of the clustering kernel (pslam_peac_wave_frames: SMs x resident CTAs/SM,
 # 1776 on a 148-SM B200), set in main().  1776 frames = 1.6 GB of gray+depth input >> 126 MB L2.
 SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "0"))
-DEFAULT_WAVE = 1776                                            # 148 SMs x 12 resident clustering CTAs
+DEFAULT_WAVE = 1776 // AREA                                    # 148 SMs x 12 resident clustering CTAs (a quarter of a wave at 1280x960: device memory per frame is 4x)
 SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "4"))         # ORB / PEAC / pose library calls per step (LSD takes the whole step in one call:
                                                                # its one-warp-per-frame kernel needs 32 frames per SM in flight, PEAC clustering fits 12)
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
@@ -178,7 +184,7 @@ def _cpu_stage_fns(stages):
 
     from planarslam_b200.lines import KEYLINE_DTYPE
     extras = EXTRAS
-    cam = (535.4, 539.2, 320.1, 247.6)
+    cam = K_CAM
     depth_m = [(depth[k].astype(np.float32) * np.float32(1.0 / 5000.0)) for k in range(n)] if extras else None     # imDepth.convertTo(CV_32F, mDepthMapFactor): the caller's job
     bf = None
     if use_ref and extras:
@@ -221,7 +227,7 @@ def _cpu_stage_fns(stages):
 
     def f_orb(i):
         g = gray[i % n]
-        r = ref_lib.ref_orb_extract(g, monotonic_alloc=False) if ref_orb else oracle_lib.orb_extract(g)
+        r = ref_lib.ref_orb_extract(g, nfeatures=NFEATURES, monotonic_alloc=False) if ref_orb else oracle_lib.orb_extract(g, nfeatures=NFEATURES)
         if extras:
             kps, desc = r[0], r[1]
             xy = np.ascontiguousarray(np.stack([kps["x"], kps["y"]], 1), np.float32)
@@ -243,11 +249,11 @@ def _cpu_stage_fns(stages):
     def f_peac(i):
         d = depth[i % n]
         if not extras:
-            return ref_lib.ref_peac_time(d) if ref_peac else oracle_lib.PeacOracle(d)
+            return ref_lib.ref_peac_time(d, K=K_CAM) if ref_peac else oracle_lib.PeacOracle(d, K=K_CAM)
         # Frame::ComputePlanes: PEAC + the per-plane post-processing + surface normals, then TrackManhattanFrame on the normals.  The post-processing consumes
         # the PEAC result in memory, so the whole function runs in the port here (one PEAC pass, not the compiled reference's plus the port's)
-        oracle_lib.planes_post(d)
-        sn = oracle_lib.surface_normals(d)
+        oracle_lib.planes_post(d, K=K_CAM)
+        sn = oracle_lib.surface_normals(d, K=K_CAM)
         nr = np.ascontiguousarray(sn[:, :3])
         (ref_lib.ref_track_manhattan_frame if ref_track else oracle_lib.track_manhattan_frame)(R_eye, nr, np.zeros((0, 3)))
 
@@ -408,7 +414,7 @@ def run_reference(args, rank, world):
     v = tot_n / tot_t
     cfg = workload_config()
     cfg["reference_step"] = f"{per_worker} frames on each of {cores} pinned worker processes ({FRAMES_PER_STEP} frames per step, {CPU_SAMPLE_FRAMES} distinct)"
-    line = {"impl": "reference", "metric": "rgbd_frames_per_sec_640x480", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": f"rgbd_frames_per_sec_{W}x{H}", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "reference", "units": units,
@@ -418,8 +424,8 @@ def run_reference(args, rank, world):
 
 
 def workload_config():
-    return {"workload": "640x480 synthetic RGB-D sequence: ORB (1000 feats, 8 levels) + LSD line segments (REFINE_ADV, 40 longest -> KeyLines + "
-                        "line functions; LBD descriptors not built) + PEAC planes + PoseOptimization (1000 point + 40 line (80 edges) + 6 plane "
+    return {"workload": f"{W}x{H} synthetic RGB-D sequence: ORB ({NFEATURES} feats, 8 levels) + LSD line segments (REFINE_ADV, 40 longest -> KeyLines + "
+                        "line functions) + PEAC planes + PoseOptimization (1000 point + 40 line (80 edges) + 6 plane "
                         "edges per frame)",
             "frames_per_step": FRAMES_PER_STEP, "sub_batch": SUB_BATCH, "distinct_frames": DISTINCT_FRAMES, "l2": "inputs_larger_than_l2",
             "stages": STAGES, "streams": len(STAGES),
@@ -460,7 +466,7 @@ def main():
     global SUB_BATCH, FRAMES_PER_STEP
     if SUB_BATCH <= 0:
         probe = Context(W, H, 1, device=local_rank)
-        SUB_BATCH = int(probe.L.pslam_peac_wave_frames(probe.h)) or DEFAULT_WAVE
+        SUB_BATCH = (int(probe.L.pslam_peac_wave_frames(probe.h)) or 1776) // AREA
         del probe
     FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
     assert LSD_SUBS <= SUBS_PER_STEP
@@ -480,7 +486,7 @@ def main():
     # ORB, PEAC, pose.  The PEAC chain (one warp per frame, latency-bound) is the critical path: high priority, so its CTAs
     # are placed first and the bulk-parallel ORB / pose kernels fill the remaining issue slots.
     streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)]
-    ctxs = [Context(W, H, SUB_BATCH, device=local_rank) for _ in range(3)] + [Context(W, H, (FRAMES_PER_STEP + LSD_SUBS - 1) // LSD_SUBS, device=local_rank)]   # one context per stage family
+    ctxs = [Context(W, H, SUB_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(3)] + [Context(W, H, (FRAMES_PER_STEP + LSD_SUBS - 1) // LSD_SUBS, device=local_rank)]   # one context per stage family
     # PSLAM_LSD_STREAM=peac puts the two latency-bound one-warp-per-frame chains (PEAC, LSD) on one stream: their CTAs compete for
     # the same register file, and running them back to back avoids half-resident waves of both
     mode = os.environ.get("PSLAM_LSD_STREAM", "peac")
@@ -552,7 +558,7 @@ def main():
     from planarslam_b200.lines import LINE3D_DTYPE
     from planarslam_b200.manhattan import MANHATTAN_RESULT_DTYPE
     DEPTH_FACTOR, BF, DIST_TH = float(np.float32(1.0 / 5000.0)), 40.0, 0.05
-    cam4 = (C.c_float * 4)(535.4, 539.2, 320.1, 247.6)
+    cam4 = (C.c_float * 4)(*K_CAM)
     n_sn = int(L.pslam_surface_normals_count(c_peac.h))
     PP_CAP = 4096
     d_ur = torch.empty((SUB_BATCH, cap), dtype=torch.float32, device=dev); d_dz = torch.empty_like(d_ur)
@@ -767,7 +773,7 @@ def main():
     per_kernel = {}
     for name, (n, tot_ms) in rep.items():
         frames_per_launch = FRAMES_PER_STEP / n
-        bytes_per_launch = ALGO_BYTES.get(name, 0) * frames_per_launch
+        bytes_per_launch = ALGO_BYTES.get(name, 0) * AREA * frames_per_launch
         if name.startswith("exchange_"):           # one key frame per launch (the matcher reads one record per rank)
             bytes_per_launch = ALGO_BYTES[name] * (world if name == "exchange_match" else 1)
         per_kernel[name] = {"launches": n, "ms_total": round(tot_ms, 4), "share": None, "algo_bytes_per_launch": int(bytes_per_launch),
@@ -836,7 +842,7 @@ def main():
     if rank == 0:
         modes = cpu_modes(gray[:CPU_SAMPLE_FRAMES], depth[:CPU_SAMPLE_FRAMES], seconds=float(os.environ.get("PSLAM_CPU_SECONDS", "8")))
         best = modes["frame_parallel_all_cores"]
-        line = {"metric": "rgbd_frames_per_sec_640x480", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        line = {"metric": f"rgbd_frames_per_sec_{W}x{H}", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(),
                 "clocks": sampler.summary(), "gpu_launches": int(launches),

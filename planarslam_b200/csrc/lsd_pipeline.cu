@@ -56,7 +56,9 @@ int lsd_alloc(pslam_ctx* c) {
     const double SCALE = 0.8, ANG_TH = 22.5, QUANT = 2.0;
     g.W = lsd_cv_round(g.w * SCALE); g.H = lsd_cv_round(g.h * SCALE);
     if (g.W < 8 || g.H < 8 || g.W > 32767 || g.H > 32767) { delete Bp; return set_error(c, PSLAM_E_INVALID, "image size unsupported by the line-segment detector"); }
-    g.refine = 2; g.seg_cap = LSD_SEG_CAP; g.cand_cap = LSD_SEG_CAP;
+    g.refine = 2;
+    // candidate / segment capacity per frame: 4096 at 640x480 (a textured frame yields a few hundred), scaled with the image area above that
+    g.seg_cap = g.cand_cap = std::max(LSD_SEG_CAP, (int)(((long long)LSD_SEG_CAP * g.w * g.h / (640 * 480) + 1023) / 1024 * 1024));
     {   // default enumeration of the NFA validation = OpenCV 4.x rect_nfa (the variant the oracle pins to cv2 4.13); PSLAM_LSD_RECT_ENUM=published
         // or pslam_lsd_set_rect_enumeration(ctx, 0) select the published LSD iterator
         const char* e = std::getenv("PSLAM_LSD_RECT_ENUM");
@@ -164,6 +166,10 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     const dim3 gg((g.W + 63) / 64, (g.H + 3) / 4, nframes);
     PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient<<<gg, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_ang, B.d_cs, B.d_gxy, B.d_smax));
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, LSD_ORDER_SMEM));
+    if ((size_t)B.g.seg_cap * sizeof(float) > 48 * 1024) {
+        if ((size_t)B.g.seg_cap * sizeof(float) > 227 * 1024) return set_error(c, PSLAM_E_INVALID, "image too large for the key-line ranking buffer");
+        PSLAM_CUDA(c, cudaFuncSetAttribute(k_lsd_keylines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(B.g.seg_cap * sizeof(float))));
+    }
     PSLAM_LAUNCH(c, "lsd_order", k_lsd_order<<<nframes, LSD_ORDER_THREADS, LSD_ORDER_SMEM, st>>>(g, B.d_scaled, B.d_smax, B.d_order, B.d_norder));
     {
         static const int occ = [] { const char* e = std::getenv("PSLAM_LSD_OCC"); const int v = e ? std::atoi(e) : LSD_REGIONS_OCC; return v == 16 || v == 20 || v == 24 || v == 32 ? v : LSD_REGIONS_OCC; }();
@@ -198,7 +204,10 @@ using namespace pslam;
 
 extern "C" {
 
-int pslam_lsd_max_segments(const pslam_ctx* c) { return c ? LSD_SEG_CAP : 0; }
+int pslam_lsd_max_segments(const pslam_ctx* c) {
+    if (!c) return 0;
+    return std::max(LSD_SEG_CAP, (int)(((long long)LSD_SEG_CAP * c->cfg.width * c->cfg.height / (640 * 480) + 1023) / 1024 * 1024));
+}
 
 int pslam_lsd_set_rect_enumeration(pslam_ctx* c, int mode) {
     if (!c) return PSLAM_E_INVALID;

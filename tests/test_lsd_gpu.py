@@ -93,3 +93,27 @@ def test_lsd_published_enumeration_matches_oracle():
     ls.set_rect_enumeration(1)
     segs1 = ls.detect(g[:1], 2)[0][0]
     assert np.array_equal(segs1, oracle_lib.lsd_detect(g[0], 2, rect_enum=1)[0])
+
+
+@pytest.mark.parametrize("size", [(1280, 960), (320, 240), (752, 480)])
+def test_lsd_other_image_sizes(size):
+    """BASELINE.json config 5 (1280x960) and two more sizes: segments, KeyLines and LBD descriptors against the oracle (capacities scale with the image area)."""
+    from planarslam_b200.lines import LineSegment
+    w, h = size
+    g = np.stack([synth.render_frame(seed=5, frame=2, width=w, height=h)[0], synth.render_frame(seed=6, frame=9, width=w, height=h)[0]])
+    ls = LineSegment(width=w, height=h, max_batch=2)
+    res = ls.detect(g, 2)
+    for f in range(2):
+        segs, width, prec, nfa = res[f]
+        osegs, owidth, oprec, onfa = oracle_lib.lsd_detect(g[f], 2, cap=65536)
+        assert len(segs) == len(osegs) > 20, (f, len(segs), len(osegs))
+        assert np.array_equal(segs, osegs), f
+        assert np.array_equal(width, owidth) and np.array_equal(prec, oprec), f
+    kres = ls.ExtractLineSegment(g, 40)
+    for f in range(2):
+        kl, lf = kres[f]
+        okl, olf = oracle_lib.extract_line_segments(g[f], 40)
+        assert len(kl) == len(okl)
+        for name in ("startPointX", "startPointY", "endPointX", "endPointY", "lineLength", "response", "class_id"):
+            assert np.array_equal(kl[name], okl[name]), (f, name)
+        assert np.array_equal(lf, olf)
