@@ -102,10 +102,77 @@ __device__ __forceinline__ int fast_score(const uint8_t (*win)[FAST_WIN_MAX + 4]
     return s >= min_th ? s : 0;
 }
 
+// Two horizontally adjacent pixels at once in packed 16-bit lanes (DPX three-input min / max on u16x2, native on sm_90+): every difference is kept biased,
+// d' = centre - circle + 256 in [1, 511] and e' = 512 - d', so plain 32-bit subtraction never borrows across the lanes.  The score is the one fast_score()
+// returns (the largest threshold at which a 9-arc exists, or 0 below min_th); the compass-point test is evaluated for the pair and the whole warp skips the
+// arc search when no lane passes it.  win row r holds image bytes from column xa0; X = column of the left pixel inside the window row.
+__device__ __forceinline__ uint32_t fast_pair(uint32_t w, int k) {            // bytes k, k+1 of a word as u16x2 (k = 0..2)
+    return __byte_perm(w, 0u, k == 0 ? 0x4140u : k == 1 ? 0x4241u : 0x4342u);
+}
+__device__ __forceinline__ void fast_score_pair(const uint8_t (*win)[FAST_WIN_MAX + 4], int X, int y, int min_th, int& s0, int& s1) {
+    const int base = (X - 3) & ~3, sh = 8 * ((X - 3) & 3);
+    uint32_t lo[7], hi[7];                                                     // row y - 3 + r: bytes of columns X-3 .. X+4
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(&win[y - 3 + r][base]);
+        const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
+        lo[r] = __funnelshift_r(w0, w1, sh); hi[r] = __funnelshift_r(w1, w2, sh);
+    }
+    // byte offset of dx inside the 8-byte row: dx + 3
+    const uint32_t VB = (fast_pair(__funnelshift_r(lo[3], hi[3], 24), 0)) + 0x01000100u;      // (centre + 256) per lane; centre = bytes 3, 4
+    uint32_t D[16];
+    D[0]  = VB - fast_pair(__funnelshift_r(lo[6], hi[6], 24), 0);      // ( 0, +3)
+    D[1]  = VB - fast_pair(hi[6], 0);                                  // (+1, +3)
+    D[2]  = VB - fast_pair(hi[5], 1);                                  // (+2, +2)
+    D[3]  = VB - fast_pair(hi[4], 2);                                  // (+3, +1)
+    D[4]  = VB - fast_pair(hi[3], 2);                                  // (+3,  0)
+    D[5]  = VB - fast_pair(hi[2], 2);                                  // (+3, -1)
+    D[6]  = VB - fast_pair(hi[1], 1);                                  // (+2, -2)
+    D[7]  = VB - fast_pair(hi[0], 0);                                  // (+1, -3)
+    D[8]  = VB - fast_pair(__funnelshift_r(lo[0], hi[0], 24), 0);      // ( 0, -3)
+    D[9]  = VB - fast_pair(lo[0], 2);                                  // (-1, -3)
+    D[10] = VB - fast_pair(lo[1], 1);                                  // (-2, -2)
+    D[11] = VB - fast_pair(lo[2], 0);                                  // (-3, -1)
+    D[12] = VB - fast_pair(lo[3], 0);                                  // (-3,  0)
+    D[13] = VB - fast_pair(lo[4], 0);                                  // (-3, +1)
+    D[14] = VB - fast_pair(lo[5], 1);                                  // (-2, +2)
+    D[15] = VB - fast_pair(lo[6], 2);                                  // (-1, +3)
+    {   // any 9-arc of the 16-circle contains at least two of the four compass points: second smallest / second largest of d'[0, 4, 8, 12]
+        const uint32_t a = __vimin3_u16x2(D[0], D[4], D[4]), b = __vimax3_u16x2(D[0], D[4], D[4]);
+        const uint32_t c = __vimin3_u16x2(D[8], D[12], D[12]), d = __vimax3_u16x2(D[8], D[12], D[12]);
+        const uint32_t t1 = __vimax3_u16x2(a, c, c), t2 = __vimin3_u16x2(b, d, d);
+        const uint32_t s2 = __vimin3_u16x2(t1, t2, t2), l2 = __vimax3_u16x2(t1, t2, t2);
+        const int brt = 256 - min_th, drk = 256 + min_th;                      // circle > centre + th  <=>  d' < 256 - th
+        const bool pass = (int)(s2 & 0xffffu) < brt || (int)(s2 >> 16) < brt || (int)(l2 & 0xffffu) > drk || (int)(l2 >> 16) > drk;
+        if (!__any_sync(__activemask(), pass)) { s0 = 0; s1 = 0; return; }
+    }
+    uint32_t best = 0;
+    uint32_t m3[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m3[i] = __vimin3_u16x2(D[i], D[(i + 1) & 15], D[(i + 2) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const uint32_t q0 = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]), q1 = __vimin3_u16x2(m3[i + 1], m3[(i + 4) & 15], m3[(i + 7) & 15]);
+        best = __vimax3_u16x2(best, q0, q1);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) D[i] = 0x02000200u - D[i];                    // e' = circle - centre + 256
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m3[i] = __vimin3_u16x2(D[i], D[(i + 1) & 15], D[(i + 2) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const uint32_t q0 = __vimin3_u16x2(m3[i], m3[(i + 3) & 15], m3[(i + 6) & 15]), q1 = __vimin3_u16x2(m3[i + 1], m3[(i + 4) & 15], m3[(i + 7) & 15]);
+        best = __vimax3_u16x2(best, q0, q1);
+    }
+    const int b0 = (int)(best & 0xffffu) - 257, b1 = (int)(best >> 16) - 257;
+    s0 = b0 >= min_th ? b0 : 0;
+    s1 = b1 >= min_th ? b1 : 0;
+}
+
 __global__ void __launch_bounds__(128) k_fast_cells(const uint8_t* __restrict__ gray, const uint8_t* __restrict__ pyr,
                                                     OrbGeom g, uint32_t* __restrict__ slots, int32_t* __restrict__ cell_cnt,
                                                     int32_t* __restrict__ status) {
-    __shared__ __align__(16) uint8_t win[FAST_WIN_MAX][FAST_WIN_MAX + 4];
+    __shared__ __align__(16) uint8_t win[FAST_WIN_MAX + 1][FAST_WIN_MAX + 4];      // one spare row: the pair scorer reads whole words past a row's last pixel
     __shared__ uint8_t sc[FAST_WIN_MAX][FAST_WIN_MAX + 4];
     __shared__ int s_tot20, s_warp[4];
 
@@ -140,10 +207,18 @@ __global__ void __launch_bounds__(128) k_fast_cells(const uint8_t* __restrict__ 
     __syncthreads();
 
     const int wi = ww - 6, hi = wh - 6, P = wi * hi;
-    for (int p = threadIdx.x; p < P; p += 128) {
-        const int y = p / wi, x = p - y * wi;
-        const int s = fast_score(win, x + 3 + ox, y + 3, g.min_th);
-        sc[y + 3][x + 3] = (uint8_t)s;
+    {
+        const int wi2 = (wi + 1) >> 1, P2 = wi2 * hi;
+        for (int p0 = 0; p0 < P2; p0 += 128) {                // warp-uniform trip count: fast_score_pair votes across the warp
+            const int p = p0 + threadIdx.x;
+            if (p < P2) {
+                const int y = p / wi2, x = 2 * (p - y * wi2);
+                int sa, sb;
+                fast_score_pair(win, x + 3 + ox, y + 3, g.min_th, sa, sb);
+                sc[y + 3][x + 3] = (uint8_t)sa;
+                if (x + 1 < wi) sc[y + 3][x + 4] = (uint8_t)sb;
+            }
+        }
     }
     __syncthreads();
 
@@ -539,7 +614,7 @@ __global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTm
 // ------------------------------------------------------------------------------------------------------
 // K4b: intensity-centroid angle (IC_Angle) + steered BRIEF (computeOrbDescriptor) + final keypoint record.
 // One warp per keypoint slot; 8 warps per CTA. grid (ceil(total_kp / 8), frames).
-__device__ __constant__ int8_t c_pattern[1024] = {
+__device__ __align__(16) const int8_t g_pattern[1024] = {
 #include "orb_pattern.inc"
 };
 
@@ -631,14 +706,21 @@ __global__ void __launch_bounds__(256) k_orient_describe(OrbGeom g, const uint8_
     }
     __syncwarp();
     const uint8_t* sb = reinterpret_cast<const uint8_t*>(sp) + OD_R * (OD_WORDS * 4) + OD_R + sh;      // the key point inside the staged patch
-    const int8_t* pat = c_pattern + lane * 32;
+    // lane i owns pattern bytes [32 i, 32 i + 32): eight words read once from global memory (a per-lane index into __constant__ memory would be serialised
+    // 32 ways by the constant cache - that was this kernel's limiter)
+    uint32_t pw[8];
+    {
+        const uint4* pp = reinterpret_cast<const uint4*>(g_pattern) + lane * 2;
+        const uint4 p0 = __ldg(pp), p1 = __ldg(pp + 1);
+        pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w; pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+    }
     int val = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         int t[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const float px = (float)pat[4 * k + 2 * e], py = (float)pat[4 * k + 2 * e + 1];
+            const float px = (float)(int)(int8_t)(pw[k] >> (16 * e)), py = (float)(int)(int8_t)(pw[k] >> (16 * e + 8));
             const int yy = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
             const int xx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
             t[e] = sb[yy * (OD_WORDS * 4) + xx];
