@@ -44,11 +44,11 @@ K_CAM = tuple(k * W / 640.0 for k in (535.4, 539.2, 320.1, 247.6))
 # frames in flight; the default is one full wave of the clustering kernel (pslam_peac_wave_frames: SMs x resident CTAs/SM,
 # 1776 on a 148-SM B200), set in main().  1776 frames = 1.6 GB of gray+depth input >> 126 MB L2.
 SUB_BATCH = int(os.environ.get("PSLAM_SUB_BATCH", "0"))
-DEFAULT_WAVE = 1776 // AREA                                    # 148 SMs x 12 resident clustering CTAs (a quarter of a wave at 1280x960: device memory per frame is 4x)
+DEFAULT_WAVE = 1776 // min(AREA, 2)                                    # 148 SMs x 12 resident clustering CTAs (a quarter of a wave at 1280x960: device memory per frame is 4x)
 SUBS_PER_STEP = int(os.environ.get("PSLAM_SUBS", "4"))         # ORB / PEAC / pose library calls per step (LSD takes the whole step in one call:
                                                                # its one-warp-per-frame kernel needs 32 frames per SM in flight, PEAC clustering fits 12)
 FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
-LSD_SUBS = int(os.environ.get("PSLAM_LSD_SUBS", "2"))          # LSD calls per step: 4 x 1776 = 2 x 3552 frames, i.e. every LSD call is exactly one wave of its
+LSD_SUBS = int(os.environ.get("PSLAM_LSD_SUBS", "2" if AREA == 1 else "4"))          # LSD calls per step: 4 x 1776 = 2 x 3552 frames, i.e. every LSD call is exactly one wave of its
                                                                # one-warp-per-frame kernel (24 resident CTAs per SM x 148), every PEAC call one wave of the clustering kernel (12 x 148)
 DISTINCT_FRAMES = int(os.environ.get("PSLAM_DISTINCT_FRAMES", "256"))   # distinct frames of the replayed sequence (rendered on the host cores by a process pool)
                                                                          # and distinct pose problems; the step's frames cycle through them
@@ -466,7 +466,7 @@ def main():
     global SUB_BATCH, FRAMES_PER_STEP
     if SUB_BATCH <= 0:
         probe = Context(W, H, 1, device=local_rank)
-        SUB_BATCH = (int(probe.L.pslam_peac_wave_frames(probe.h)) or 1776) // AREA
+        SUB_BATCH = (int(probe.L.pslam_peac_wave_frames(probe.h)) or 1776) // min(AREA, 2)          # config 5: half a wave per call (device memory per frame is 4x)
         del probe
     FRAMES_PER_STEP = SUB_BATCH * SUBS_PER_STEP
     assert LSD_SUBS <= SUBS_PER_STEP
@@ -734,28 +734,6 @@ def main():
     ms_max = float(t.item())
     value = world * FRAMES_PER_STEP * args.steps / (ms_max / 1e3)
 
-    # ---- end to end through the host-pointer ABI ----
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(2, args.steps // 3)
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
-    h2d = FRAMES_PER_STEP * (("orb" in STAGES) * W * H + ("lsd" in STAGES) * W * H + ("peac" in STAGES) * 2 * W * H) + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
-    if EXTRAS:          # stereo: key points + depth again; isLineGood: key lines + depth again (every host-pointer call uploads what it reads)
-        h2d += FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 28 + 2 * W * H) + ("lsd" in STAGES) * (MAX_LINES * 68 + 2 * W * H))
-    d2h = FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 60 + 8) + ("peac" in STAGES) * (4 * W * H + maxp * PLANE_DTYPE.itemsize + 4) +
-                             ("pose" in STAGES) * (64 + 1046 + 4) + ("lsd" in STAGES) * (MAX_LINES * (68 + 24) + 4))
-    if EXTRAS:
-        d2h += FRAMES_PER_STEP * (("orb" in STAGES) * cap * 8 + ("lsd" in STAGES) * MAX_LINES * (32 + 96) +
-                                  ("peac" in STAGES) * (maxp * 28 + 4096 * 12 + int(L.pslam_surface_normals_count(c_peac.h)) * 32 - 4 * W * H - maxp * PLANE_DTYPE.itemsize))
-
     # ---- per-kernel roofline pass (event-bracketed launches, same workload, outside the timed regions) ----
     # one stage family at a time, so a launch's duration is not inflated by kernels of the other two streams
     rep = {}
@@ -838,7 +816,65 @@ def main():
         if n_to.value:
             raise RuntimeError(f"key-frame exchange: {n_to.value} matcher CTAs timed out waiting for a peer")
         xch_info = {"key_frames_per_rank_per_step": KF, "records_read_per_match": world, "transport": "CUDA IPC peer memory (NVLink P2P), fused with the Hamming k=2 matcher",
-                    "epochs": xch_epoch[0], "nearest_distance_median": float(d_xdist[:, :500, 0].float().median().item())}
+                    "epochs": xch_epoch[0], "second_nearest_distance_median": float(d_xdist[:, :500, 1].float().median().item())}
+    # ---- end to end through the host-pointer ABI ----
+    n_keylines = float(d_nkl.sum().item()) if "lsd" in STAGES else None
+    frame_e2e = EXTRAS and all(k in STAGES for k in ("orb", "lsd", "peac"))
+    if frame_e2e:
+        # The call a replay driver makes per batch is the Frame constructor's compute, pslam_frame_construct_batch: host frames in (uploaded once), every Frame
+        # product out.  Two contexts on two host threads take alternate sub-batches, so one batch's copies overlap the other's kernels; PoseOptimization runs on
+        # a third thread as before.  The device-resident leg's contexts and buffers are released first (two full-family contexts take ~110 GB).
+        barrier()
+        xch = None
+        del d_gray, d_depth, d_kps, d_desc, d_labels, d_planes, d_members, d_moff, d_kl, d_lf, d_ur, d_dz, d_midx, d_mdist, d_good, d_ldesc, d_l3d, d_pp_coef, d_pp_pts
+        del d_sn8, d_sn3, d_nmask
+        for c in (c_orb, c_peac, c_lsd):
+            c.close()
+        torch.cuda.empty_cache()
+        from planarslam_b200.frame import ConstructFrames, FrameOutputs
+        fctx = [Context(W, H, SUB_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(2)]
+        fout = [FrameOutputs(c, SUB_BATCH, MAX_LINES, PP_CAP, normals=True, pinned=True) for c in fctx]
+
+        def e_frames(t):
+            torch.cuda.set_device(local_rank)
+            for sb in range(t, SUBS_PER_STEP, 2):
+                ConstructFrames(fctx[t], h_gray[sb * SUB_BATCH].data_ptr(), h_depth[sb * SUB_BATCH].data_ptr(), fout[t], DEPTH_FACTOR, BF, DIST_TH, 1, nframes=SUB_BATCH)
+
+        def e_pose2():
+            torch.cuda.set_device(local_rank)
+            for _ in range(SUBS_PER_STEP):
+                opt.PoseOptimizationBatch(probs)
+
+        def step_e2e():
+            jobs = [pool.submit(e_frames, 0), pool.submit(e_frames, 1)] + ([pool.submit(e_pose2)] if "pose" in STAGES else [])
+            for f in jobs:
+                f.result()
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, args.steps // 3)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
+    if frame_e2e:
+        h2d = FRAMES_PER_STEP * 3 * W * H + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
+        d2h = SUBS_PER_STEP * fout[0].nbytes() + ("pose" in STAGES) * FRAMES_PER_STEP * (64 + 1046 + 4)
+        e2e_call = "pslam_frame_construct_batch (Frame constructor: one upload of gray + depth per frame) on two contexts / host threads + pslam_pose_optimization_batch"
+    else:
+        h2d = FRAMES_PER_STEP * (("orb" in STAGES) * W * H + ("lsd" in STAGES) * W * H + ("peac" in STAGES) * 2 * W * H) + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
+        d2h = FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 60 + 8) + ("peac" in STAGES) * (4 * W * H + maxp * PLANE_DTYPE.itemsize + 4) +
+                                 ("pose" in STAGES) * (64 + 1046 + 4) + ("lsd" in STAGES) * (MAX_LINES * (68 + 24) + 4))
+        if EXTRAS:          # stereo: key points + depth again; isLineGood: key lines + depth again (every host-pointer call uploads what it reads)
+            h2d += FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 28 + 2 * W * H) + ("lsd" in STAGES) * (MAX_LINES * 68 + 2 * W * H))
+            d2h += FRAMES_PER_STEP * (("orb" in STAGES) * cap * 8 + ("lsd" in STAGES) * MAX_LINES * (32 + 96) +
+                                      ("peac" in STAGES) * (maxp * 28 + 4096 * 12 + n_sn * 32 - 4 * W * H - maxp * PLANE_DTYPE.itemsize))
+        e2e_call = "per-function host-pointer entry points, one host thread per stage family"
+
     if rank == 0:
         modes = cpu_modes(gray[:CPU_SAMPLE_FRAMES], depth[:CPU_SAMPLE_FRAMES], seconds=float(os.environ.get("PSLAM_CPU_SECONDS", "8")))
         best = modes["frame_parallel_all_cores"]
@@ -846,14 +882,14 @@ def main():
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic", "config": workload_config(),
                 "clocks": sampler.summary(), "gpu_launches": int(launches),
-                "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "call": e2e_call},
                 "roofline": roofline,
                 "cpu_baseline": {"value": best["frames_per_sec"], "unit": "frames/s", "cores": best["threads"], "kind": "reference",
                                  "units": {k: CPU_UNITS.get(k) for k in STAGES}, "modes": modes,
                                  "sample": f"{' + '.join(STAGES)}: {best['frames']} frames in {best['seconds']} s, one pinned process per host core "
                                            f"({modes['host_cores']}), -O3 -march=x86-64-v3 (oracle/Makefile fast); modes = BASELINE.md section 3"},
                 "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP,
-                "keylines_per_frame": float(d_nkl.sum().item()) / FRAMES_PER_STEP if "lsd" in STAGES else None, "exchange": xch_info, "aux": aux}
+                "keylines_per_frame": n_keylines / FRAMES_PER_STEP if n_keylines is not None else None, "exchange": xch_info, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

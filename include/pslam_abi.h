@@ -530,6 +530,29 @@ int pslam_bow_transform(pslam_ctx* ctx, int n_nodes, int L, const uint8_t* voc_d
                         const int32_t* voc_word_id, const double* voc_weight, const uint8_t* features, int n, int levelsup, int32_t* word_id,
                         double* word_val, int32_t* node_id, int32_t* node_off, int32_t* node_feat, int32_t* counts);
 
+/* ---- The RGB-D Frame constructor's compute in one call ----------------------------------------------------
+ * Replaces the work of  Frame::Frame(imRGB, imGray, imDepth, ...)   src/Frame.cc:55-140 : the three extractor threads it starts (:90-95)
+ *   ExtractORB (:181-186)  then  ComputeStereoFromRGBD (:603-621)            -> mvKeys (= mvKeysUn: no distortion model on this path), mDescriptors, mvuRight, mvDepth
+ *   ExtractLSD (:170-179): ExtractLineSegment + LBD, isLineGood (:189-267)   -> mvKeylinesUn, mvKeyLineFunctions, mLdesc, mvLines3D / mvDepthLine
+ *   ComputePlanes (:647-753)                                                 -> mvPlaneCoefficients, mvPlanePoints, vSurfaceNormal
+ * for nframes frames.  gray uint8 [nframes][h][w] and depth uint16 [nframes][h][w] are host buffers and are uploaded ONCE (the per-function host-pointer
+ * entry points above upload the depth frame three times and the gray frame twice); all outputs are host buffers:
+ *   keys [nframes][capk], desc [nframes][capk][32], n_keys [nframes], u_right / depth_kp [nframes][capk]      capk = pslam_orb_max_keypoints()
+ *   keylines [nframes][max_lines], line_functions [nframes][max_lines][3], line_desc [nframes][max_lines][32], lines3d [nframes][max_lines], n_lines [nframes],
+ *   n_rand_drawn [nframes] (may be NULL; see pslam_lines3d_batch: every frame's rand() stream starts from line_seed)
+ *   n_planes [nframes], plane_src / plane_coef [nframes][maxp] ([4]), plane_pt_off [nframes][maxp + 1], plane_pts [nframes][cap_plane_pts][3]   maxp = pslam_peac_max_planes()
+ *   surface_normals8 [nframes][pslam_surface_normals_count()][8] (may be NULL: the normals are then not computed)
+ * Pinned (page-locked) buffers make the copies asynchronous to the host; two contexts driven from two host threads overlap one batch's copies with the
+ * other's kernels.  Device staging belongs to the context and only grows.  PSLAM_E_CAPACITY like the per-function calls. */
+typedef struct pslam_frame_outputs {
+    pslam_keypoint* keys; uint8_t* desc; int32_t* n_keys; float* u_right; float* depth_kp;
+    pslam_keyline* keylines; double* line_functions; uint8_t* line_desc; struct pslam_line3d* lines3d; int32_t* n_lines; int32_t* n_rand_drawn;
+    int32_t* n_planes; int32_t* plane_src; float* plane_coef; int32_t* plane_pt_off; float* plane_pts; int32_t cap_plane_pts;
+    float* surface_normals8;
+} pslam_frame_outputs;
+int pslam_frame_construct_batch(pslam_ctx* ctx, const uint8_t* gray, const uint16_t* depth, int nframes, float depth_factor, float bf, float plane_dist_th,
+                                int max_lines, uint32_t line_seed, const pslam_frame_outputs* out);
+
 #ifdef __cplusplus
 }
 #endif

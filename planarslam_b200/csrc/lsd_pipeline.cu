@@ -191,6 +191,12 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     return PSLAM_OK;
 }
 
+int lsd_status_fetch_async(pslam_ctx* c, int nframes, int32_t* h_pinned) {      // capacity flags of the most recent detection (frame_pipeline.cu)
+    if (!c->lsd) return set_error(c, PSLAM_E_INVALID, "no line detection has run");
+    PSLAM_CUDA(c, cudaMemcpyAsync(h_pinned, c->lsd->d_status, (size_t)nframes * 4, cudaMemcpyDeviceToHost, c->stream));
+    return PSLAM_OK;
+}
+
 int lsd_keylines_dev(pslam_ctx* c, int nframes, int max_lines, LsdKeyLine* d_kl, double* d_lf, int32_t* d_n) {
     LsdBuffers& B = *c->lsd;
     PSLAM_LAUNCH(c, "lsd_keylines", k_lsd_keylines<<<nframes, 128, B.g.seg_cap * sizeof(float), c->stream>>>(B.g, max_lines, B.d_segs, B.d_nsegs, d_kl, d_lf, d_n));

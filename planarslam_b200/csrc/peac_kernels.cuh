@@ -391,20 +391,29 @@ struct PeacPlaneRec {
 };
 
 // K-P2: graph edges + coarse clustering + eroded block map. grid (frames), block 32.
-__global__ void __launch_bounds__(32) k_peac_cluster(PeacGeom g, const double* __restrict__ blk_st, const double* __restrict__ blk_geo,
+// OCC = resident CTAs per SM the build targets.  12 is what 168 registers and 18 KB of shared memory (float heap keys + u16 heap) allow; the variants above it
+// cap the registers at 65536 / (32 OCC) and keep only the 6 KB heap in shared memory (keys in global memory, L1-resident): the kernel is bound by the latency of
+// its dependent FP64 chains at ~3 warps per scheduler, so more resident frames trade a little per-frame speed for throughput (PSLAM_PEAC_OCC, measured in DESIGN.md).
+template <int OCC>
+__global__ void __launch_bounds__(32, OCC) k_peac_cluster(PeacGeom g, const double* __restrict__ blk_st, const double* __restrict__ blk_geo,
                                                      const int32_t* __restrict__ blk_n, const uint8_t* __restrict__ blk_valid,
                                                      double* node_st, double* node_geo, int32_t* node_n, int32_t* node_rid, int32_t* node_cid,
                                                      uint8_t* node_alive, uint32_t* adj, int16_t* wlo_all, int16_t* whi_all, int32_t* nb_list, int32_t* ds_parent,
                                                      int32_t* ds_size, PeacPlaneRec* planes, int32_t* n_planes, int32_t* blk_map,
-                                                     int32_t* next_cid_out, int32_t* status) {
+                                                     int32_t* next_cid_out, int32_t* status, float* keyf_all) {
     const int frame = blockIdx.x, lane = threadIdx.x;
     const size_t fo = (size_t)frame * g.nblk;
     AhcState S;
     S.nslots = g.nblk; S.words = g.adj_words;
     S.st = node_st + fo * 9; S.geo = node_geo + fo * 8; S.N = node_n + fo; S.rid = node_rid + fo; S.cid = node_cid + fo;
     extern __shared__ __align__(16) unsigned char cluster_smem[];
-    S.keyf = reinterpret_cast<float*>(cluster_smem);                               // [nblk]
-    S.heap = reinterpret_cast<uint16_t*>(cluster_smem + (size_t)g.nblk * sizeof(float));   // [nblk]
+    if (OCC > 12) {
+        S.keyf = keyf_all + fo;                                                        // [nblk] in global memory
+        S.heap = reinterpret_cast<uint16_t*>(cluster_smem);                            // [nblk]
+    } else {
+        S.keyf = reinterpret_cast<float*>(cluster_smem);                               // [nblk]
+        S.heap = reinterpret_cast<uint16_t*>(cluster_smem + (size_t)g.nblk * sizeof(float));   // [nblk]
+    }
     S.alive = node_alive + fo; S.adj = adj + fo * g.adj_words; S.nb_list = nb_list + fo;
     S.wlo = wlo_all + fo; S.whi = whi_all + fo;
     S.ds_parent = ds_parent + fo; S.ds_size = ds_size + fo;

@@ -51,7 +51,7 @@ int peac_alloc(pslam_ctx* c) {
     A(dmalloc(c, &c->d_blk_st, B * nb * 9)); A(dmalloc(c, &c->d_blk_geo, B * nb * 8)); A(dmalloc(c, &c->d_blk_n, B * nb)); A(dmalloc(c, &c->d_blk_valid, B * nb));
     A(dmalloc(c, &c->d_node_st, B * nb * 9)); A(dmalloc(c, &c->d_node_geo, B * nb * 8)); A(dmalloc(c, &c->d_node_n, B * nb));
     A(dmalloc(c, &c->d_node_rid, B * nb)); A(dmalloc(c, &c->d_node_cid, B * nb)); A(dmalloc(c, &c->d_node_alive, B * nb));
-    A(dmalloc(c, &c->d_adj, B * nb * g.adj_words)); A(dmalloc(c, &c->d_wlo, B * nb)); A(dmalloc(c, &c->d_whi, B * nb)); A(dmalloc(c, &c->d_nb_list, B * nb));
+    A(dmalloc(c, &c->d_adj, B * nb * g.adj_words)); A(dmalloc(c, &c->d_wlo, B * nb)); A(dmalloc(c, &c->d_whi, B * nb)); A(dmalloc(c, &c->d_nb_list, B * nb)); A(dmalloc(c, &c->d_keyf, B * nb));
     A(dmalloc(c, &c->d_ds_parent, B * nb)); A(dmalloc(c, &c->d_ds_size, B * nb));
     A(dmalloc(c, &c->d_coarse, B * PEAC_MAX_PLANES)); A(dmalloc(c, &c->d_ncoarse, B)); A(dmalloc(c, &c->d_next_cid, B)); A(dmalloc(c, &c->d_blk_map, B * nb));
     A(dmalloc(c, &c->d_dist, B * px)); A(dmalloc(c, &c->d_queue, B * g.queue_cap)); A(dmalloc(c, &c->d_qlen, B));
@@ -69,10 +69,19 @@ int peac_alloc(pslam_ctx* c) {
 void peac_free(pslam_ctx* c) {
     cudaFree(c->d_depth); cudaFree(c->d_blk_st); cudaFree(c->d_blk_geo); cudaFree(c->d_blk_n); cudaFree(c->d_blk_valid);
     cudaFree(c->d_node_st); cudaFree(c->d_node_geo); cudaFree(c->d_node_n); cudaFree(c->d_node_rid); cudaFree(c->d_node_cid);
-    cudaFree(c->d_node_alive); cudaFree(c->d_adj); cudaFree(c->d_wlo); cudaFree(c->d_whi); cudaFree(c->d_nb_list); cudaFree(c->d_ds_parent); cudaFree(c->d_ds_size);
+    cudaFree(c->d_node_alive); cudaFree(c->d_adj); cudaFree(c->d_wlo); cudaFree(c->d_whi); cudaFree(c->d_nb_list); cudaFree(c->d_keyf); cudaFree(c->d_ds_parent); cudaFree(c->d_ds_size);
     cudaFree(c->d_coarse); cudaFree(c->d_ncoarse); cudaFree(c->d_next_cid); cudaFree(c->d_blk_map); cudaFree(c->d_dist); cudaFree(c->d_queue);
     cudaFree(c->d_qlen); cudaFree(c->d_pl_adj); cudaFree(c->d_final); cudaFree(c->d_scratch); cudaFree(c->d_final_map); cudaFree(c->d_labels); cudaFree(c->d_planes);
     cudaFree(c->d_nplanes); cudaFree(c->d_midx); cudaFree(c->d_moff); cudaFreeHost(c->h_depth);
+}
+
+// resident-CTA target of the clustering kernel (see k_peac_cluster): PSLAM_PEAC_OCC = 12 (default), 16 or 20
+static int peac_cluster_occ() {
+    static const int occ = [] { const char* e = std::getenv("PSLAM_PEAC_OCC"); const int v = e ? std::atoi(e) : 12; return (v == 16 || v == 20) ? v : 12; }();
+    return occ;
+}
+static size_t peac_cluster_smem(const PeacGeom& g, int occ) {
+    return (size_t)g.nblk * (occ > 12 ? sizeof(uint16_t) : sizeof(float) + sizeof(uint16_t));      // u16 heap (+ float heap keys)
 }
 
 int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_labels, pslam_plane* d_planes, int32_t* d_nplanes,
@@ -87,12 +96,16 @@ int peac_run_dev(pslam_ctx* c, const uint16_t* d_depth, int nframes, int32_t* d_
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_adj, 0, (size_t)nframes * g.nblk * g.adj_words * sizeof(uint32_t), st));
     PSLAM_CUDA(c, cudaMemsetAsync(c->d_pl_adj, 0, (size_t)nframes * PEAC_MAX_PLANES * PEAC_PL_WORDS * sizeof(uint32_t), st));
     PSLAM_LAUNCH(c, "peac_blocks", k_peac_blocks<<<dim3((g.nblk + 127) / 128, nframes), 128, 0, st>>>(g, d_depth, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid));
-    const size_t cluster_smem = (size_t)g.nblk * (sizeof(float) + sizeof(uint16_t));     // float heap keys + u16 heap
-    PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem));
-    PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    PSLAM_LAUNCH(c, "peac_cluster", k_peac_cluster<<<nframes, 32, cluster_smem, st>>>(g, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid, c->d_node_st, c->d_node_geo,
-                 c->d_node_n, c->d_node_rid, c->d_node_cid, c->d_node_alive, c->d_adj, c->d_wlo, c->d_whi, c->d_nb_list, c->d_ds_parent, c->d_ds_size, c->d_coarse,
-                 c->d_ncoarse, c->d_blk_map, c->d_next_cid, c->d_status));
+    const int occ = peac_cluster_occ();
+    const size_t cluster_smem = peac_cluster_smem(g, occ);
+#define PEAC_CLUSTER(V) do { \
+        PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem)); \
+        PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_cluster<V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+        PSLAM_LAUNCH(c, "peac_cluster", k_peac_cluster<V><<<nframes, 32, cluster_smem, st>>>(g, c->d_blk_st, c->d_blk_geo, c->d_blk_n, c->d_blk_valid, c->d_node_st, \
+                     c->d_node_geo, c->d_node_n, c->d_node_rid, c->d_node_cid, c->d_node_alive, c->d_adj, c->d_wlo, c->d_whi, c->d_nb_list, c->d_ds_parent, c->d_ds_size, \
+                     c->d_coarse, c->d_ncoarse, c->d_blk_map, c->d_next_cid, c->d_status, c->d_keyf)); } while (0)
+    if (occ == 16) PEAC_CLUSTER(16); else if (occ == 20) PEAC_CLUSTER(20); else PEAC_CLUSTER(12);
+#undef PEAC_CLUSTER
     PSLAM_LAUNCH(c, "peac_seed", k_peac_seed<<<nframes, 256, 0, st>>>(g, c->d_blk_map, d_labels, c->d_dist, c->d_queue, c->d_qlen));
     const size_t flood_smem = PEAC_MAX_PLANES * sizeof(FloodPlane) + (size_t)g.nblk;
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_peac_flood, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)flood_smem));
@@ -121,12 +134,16 @@ int pslam_peac_num_blocks(const pslam_ctx* c) { return c ? c->pgeom.nblk : 0; }
 
 int pslam_peac_wave_frames(const pslam_ctx* c) {
     if (!c) return 0;
-    const size_t cluster_smem = (size_t)c->pgeom.nblk * (sizeof(float) + sizeof(uint16_t));
+    const int occ = peac_cluster_occ();
+    const size_t cluster_smem = peac_cluster_smem(c->pgeom, occ);
     int per_sm = 0, sms = 0, dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem) != cudaSuccess) return 0;
-    cudaFuncSetAttribute(k_peac_cluster, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_peac_cluster, 32, cluster_smem) != cudaSuccess) return 0;
+#define PEAC_OCCUPANCY(V) do { \
+        if (cudaFuncSetAttribute(k_peac_cluster<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster_smem) != cudaSuccess) return 0; \
+        cudaFuncSetAttribute(k_peac_cluster<V>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_peac_cluster<V>, 32, cluster_smem) != cudaSuccess) return 0; } while (0)
+    if (occ == 16) PEAC_OCCUPANCY(16); else if (occ == 20) PEAC_OCCUPANCY(20); else PEAC_OCCUPANCY(12);
+#undef PEAC_OCCUPANCY
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
     return per_sm * sms;
 }

@@ -83,6 +83,7 @@ struct LsdBuffers;
 struct TrackBuffers;
 struct ExchangeBuffers;
 struct PlanePostBuffers;
+struct FrameBuffers;
 
 }  // namespace pslam
 
@@ -131,7 +132,7 @@ struct pslam_ctx {
     double* d_blk_st = nullptr; double* d_blk_geo = nullptr; int32_t* d_blk_n = nullptr; uint8_t* d_blk_valid = nullptr;
     double* d_node_st = nullptr; double* d_node_geo = nullptr; int32_t* d_node_n = nullptr; int32_t* d_node_rid = nullptr;
     int32_t* d_node_cid = nullptr; uint8_t* d_node_alive = nullptr; uint32_t* d_adj = nullptr; int16_t* d_wlo = nullptr; int16_t* d_whi = nullptr;
-    int32_t* d_nb_list = nullptr; int32_t* d_ds_parent = nullptr; int32_t* d_ds_size = nullptr;
+    int32_t* d_nb_list = nullptr; float* d_keyf = nullptr; int32_t* d_ds_parent = nullptr; int32_t* d_ds_size = nullptr;
     pslam::PeacPlaneRec* d_coarse = nullptr; int32_t* d_ncoarse = nullptr; int32_t* d_next_cid = nullptr; int32_t* d_blk_map = nullptr;
     float* d_dist = nullptr; uint32_t* d_queue = nullptr; int32_t* d_qlen = nullptr; uint32_t* d_pl_adj = nullptr;
     pslam::PeacPlaneRec* d_final = nullptr; int32_t* d_scratch = nullptr; int32_t* d_final_map = nullptr;
@@ -143,6 +144,7 @@ struct pslam_ctx {
     pslam::LsdBuffers* lsd = nullptr;            // line-segment detector buffers (lsd_pipeline.cu)
     pslam::TrackBuffers* track = nullptr;        // device-resident tracking chain (track_chain.cu)
     pslam::PlanePostBuffers* planepost = nullptr; // Frame::ComputePlanes post-processing + surface normals (planepost_kernels.cu)
+    pslam::FrameBuffers* frame = nullptr;        // staging of pslam_frame_construct_batch (frame_pipeline.cu)
     pslam::ExchangeBuffers* exchange = nullptr;  // key-frame descriptor exchange over peer memory (exchange_kernels.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
@@ -166,6 +168,8 @@ void lsd_free(pslam_ctx* c);
 void track_free(pslam_ctx* c);
 void exchange_free(pslam_ctx* c);
 void planepost_free(pslam_ctx* c);
+void frame_free(pslam_ctx* c);
+int lsd_status_fetch_async(pslam_ctx* c, int nframes, int32_t* h_pinned);
 // PEAC pipeline (peac_pipeline.cu)
 int peac_build_geometry(pslam_ctx* c);
 int peac_alloc(pslam_ctx* c);

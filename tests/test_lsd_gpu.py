@@ -101,7 +101,8 @@ def test_lsd_other_image_sizes(size):
     from planarslam_b200.lines import LineSegment
     w, h = size
     g = np.stack([synth.render_frame(seed=5, frame=2, width=w, height=h)[0], synth.render_frame(seed=6, frame=9, width=w, height=h)[0]])
-    ls = LineSegment(width=w, height=h, max_batch=2)
+    from planarslam_b200._lib import Context
+    ls = LineSegment(ctx=Context(w, h, 2, nlevels=4 if w < 640 else 8))          # (the context also builds the ORB pyramid geometry: 8 levels need >= 640 columns)
     res = ls.detect(g, 2)
     for f in range(2):
         segs, width, prec, nfa = res[f]
