@@ -1,27 +1,27 @@
 #!/bin/bash
-# 2 GPUs: peer-memory key-frame exchange check (fused matcher vs NCCL all_gather + single-GPU matcher), bench at N=2 for both arms, config 5 at N=2
+# frame-constructor call (parity + e2e), PEAC clustering occupancy variants, LSD at other sizes, full GPU suite
 set -u
 OUT=gpurun_out/r2_call10
 mkdir -p $OUT
 export PSLAM_AUX_NEW=0 PSLAM_CPU_SECONDS=0.5
-N=${PSLAM_NGPUS:-2}
-nvidia-smi topo -m > $OUT/topo.txt 2>&1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/exchange_check.py > $OUT/exchange_check.json 2> $OUT/exchange_check.err; echo "exchange check rc=$?" >> $OUT/summary.txt
-cat $OUT/exchange_check.json; tail -3 $OUT/exchange_check.err
-PSLAM_CONFIG=5 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/exchange_check.py > $OUT/exchange_check_config5.json 2> $OUT/exchange_check_config5.err; echo "exchange check config5 rc=$?" >> $OUT/summary.txt
-cat $OUT/exchange_check_config5.json
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 3 --warmup 3 > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; echo "bench N=$N rc=$?" >> $OUT/summary.txt
-tail -3 $OUT/bench_n$N.err
-PSLAM_CONFIG=5 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus $N --steps 2 --warmup 3 > $OUT/bench_config5_n$N.json 2> $OUT/bench_config5_n$N.err; echo "bench config5 N=$N rc=$?" >> $OUT/summary.txt
-tail -3 $OUT/bench_config5_n$N.err
+timeout 600 python -m pytest -q -m gpu -x tests/test_frame_construct_gpu.py tests/test_lsd_gpu.py tests/test_peac_gpu.py > $OUT/pytest_new.log 2>&1; echo "pytest new rc=$?" >> $OUT/summary.txt
+tail -8 $OUT/pytest_new.log
+for occ in 12 16 20; do
+  PSLAM_PEAC_OCC=$occ PSLAM_STAGES=peac PSLAM_EXTRAS=0 timeout 300 python bench.py --steps 3 --warmup 3 > $OUT/bench_peac_occ$occ.json 2> $OUT/bench_peac_occ$occ.err; echo "peac occ $occ rc=$?" >> $OUT/summary.txt
+done
+PSLAM_PEAC_OCC=16 timeout 300 python -m pytest -q -m gpu -x tests/test_peac_gpu.py > $OUT/pytest_peac16.log 2>&1; echo "pytest peac occ16 rc=$?" >> $OUT/summary.txt
+timeout 900 python bench.py --steps 3 --warmup 3 > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench default rc=$?" >> $OUT/summary.txt
+tail -5 $OUT/bench_default.err
+timeout 1500 python -m pytest -q -m gpu tests > $OUT/pytest_all.log 2>&1; echo "pytest all rc=$?" >> $OUT/summary.txt
+tail -5 $OUT/pytest_all.log
 cat $OUT/summary.txt; python - <<'PY'
 import json, glob
 for f in sorted(glob.glob("gpurun_out/r2_call10/bench_*.json")):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
         pk=d["roofline"]["per_kernel"]
-        print(f.split("/")[-1], d["metric"], "n_gpus", d["n_gpus"], "value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "ms/step", round(d["ms_per_step"],1), d.get("exchange"))
-        print("   ", {k:round(v["ms_total"],2) for k,v in pk.items() if k.startswith("exchange")})
+        print(f.split("/")[-1], d["metric"], "frames/step", d["config"]["frames_per_step"], "value", round(d["value"],1), "e2e", round(d["e2e"]["value"],1), "ms/step", round(d["ms_per_step"],1), "cpu", d["cpu_baseline"]["value"])
+        print("   ", {k:round(v["ms_total"],1) for k,v in pk.items() if v["ms_total"]>2})
     except Exception as e:
         print(f, "failed", e)
 PY
