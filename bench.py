@@ -4,18 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" = one pass of the hot path over 7104 synthetic 640x480 RGB-D frames (seeded "room corner" sequence,
-planarslam_b200/synth.py): four library calls of 1776 frames for ORB / PEAC / PoseOptimization and three of 2368 for LSD, so that
-every call of a one-warp-per-frame kernel is exactly one resident wave.  Frames are independent units, so ranks shard them with no data-path
-collective (weak scaling: every rank processes FRAMES_PER_STEP frames per step).
+A "step" = one pass of the hot path over 7104 frames of a 256-frame synthetic 640x480 RGB-D sequence ("room corner", planarslam_b200/synth.py): four library
+calls of 1776 frames for ORB / PEAC / PoseOptimization and two of 3552 for LSD, so that every call of a one-warp-per-frame kernel is exactly one resident wave.
+With PSLAM_EXTRAS=1 (default) the extractors are followed by what the Frame constructor and Tracking run on their output: ComputeStereoFromRGBD, MatchORBPoints
+against the previous frame, the key-frame exchange, LBD descriptors, isLineGood, the ComputePlanes post-processing, surface normals, TrackManhattanFrame.
+Frames are independent units, so ranks shard them with no data-path collective (weak scaling: every rank processes FRAMES_PER_STEP frames per step); the
+key-frame exchange is the one step that reads peer memory.  PSLAM_CONFIG=5 runs BASELINE.json's 1280x960 configuration.
 
-Prints ONE JSON line on rank 0 (see DESIGN.md §measurement for every field):
+Prints ONE JSON line on rank 0 (see DESIGN.md section 7 for every field):
   value      frames/s, inputs already resident in HBM, CUDA events on the launching stream, max over ranks
-  e2e        frames/s through the host-pointer C-ABI call (pinned H2D of the frames + D2H of keypoints,
-             descriptors, plane labels inside the timed region)
-  roofline   dominant kernel: algorithmic bytes per launch / its mean launch time (event-bracketed, measured live
-             in a separate pass of the same workload) vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle (a restatement of the reference, NOT the original binary) timed on host cores
+  e2e        frames/s through the host-pointer C ABI (pslam_frame_construct_batch + pslam_pose_optimization_batch): pinned H2D of the frames and D2H of
+             every Frame product inside the timed region
+  roofline   dominant kernel: algorithmic bytes per launch / its mean launch time (event-bracketed, measured live in a separate pass of the same
+             workload) vs MEASURED_PEAKS.json hbm_gbs; per_kernel lists every kernel family
+  cpu_baseline  the CPU path on the host cores: the reference's own code compiled here wherever it compiles, cv2 for the OpenCV calls, the oracle port for
+             the rest (cpu_baseline.units says which); --impl reference prints the same thing as its own line
 """
 from __future__ import annotations
 
@@ -793,6 +796,35 @@ def main():
         aux["lba_config"] = "20 key frames (1 fixed), 5000 point + 100 line (200 edges) + 30 plane-type edges, 296 problems per launch"
     except Exception as ex:                      # auxiliary only: never fail the headline
         aux["lba_error"] = repr(ex)
+    # ---- auxiliary: BASELINE.json config 3, the device-resident tracking chain on ONE sequence (frame t+1 needs the pose of frame t: a latency number) ----
+    if rank == 0:
+        try:
+            from planarslam_b200 import synth, synth_map
+            from planarslam_b200.orb import ORBextractor
+            from planarslam_b200.tracking import Tracker
+            nseq = 64
+            fr = [synth.render_frame(2, f)[:2] for f in range(nseq)]
+            ex = ORBextractor(1000, 1.2, 8, 20, 7)
+            parts = []
+            for f in range(0, nseq, 8):
+                k, de = ex(fr[f][0])
+                parts.append(synth_map.map_from_frame(synth_map.frame_arrays(k, de, fr[f][1]), synth_map.true_pose(f)))
+            m = {key: np.concatenate([q[key] for q in parts]) for key in ("pos", "normal", "max_distance", "min_distance", "desc", "skip", "has_obs")}
+            tctx = Context(640, 480, max_batch=nseq, device=local_rank)
+            tr = Tracker(tctx)
+            tr.set_map(m)
+            sg, sd, T0 = np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr]), synth_map.true_pose(0).astype(np.float32)
+            tr.track(sg, sd, T0)
+            t0 = time.perf_counter()
+            poses, stats = tr.track(sg, sd, T0)
+            dt = time.perf_counter() - t0
+            err = max(synth_pose.pose_error(poses[t], synth_map.true_pose(t))[0] for t in range(nseq))
+            aux["tracking_chain"] = {"frames_per_sec_single_sequence": round(nseq / dt, 1), "frames": nseq, "map_points": int(len(m["skip"])),
+                                     "max_rotation_error_vs_ground_truth_rad": float(err), "min_inliers": int(stats[:, 3].min()),
+                                     "what": "ORB -> stereo -> motion model -> SearchByProjection(last) -> PoseOptimization -> SearchByProjection(map) -> PoseOptimization, host frames in"}
+            tctx.close()
+        except Exception as ex_:
+            aux["tracking_chain"] = {"error": repr(ex_)}
     # ---- auxiliary: Frame::isLineGood and Tracking::TrackManhattanFrame (kernels added after the round-1 GPU budget was spent): run in a
     # child process so that a fault there cannot touch this process' CUDA context; it reports throughput and whether the results match
     # the signatures computed on the CPU at commit time (tests/golden/aux_new_kernels_expected.json) ----

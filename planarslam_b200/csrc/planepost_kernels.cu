@@ -46,6 +46,13 @@ __device__ __forceinline__ void pp_vertex(const uint16_t* __restrict__ depth, in
     y = (float)(((double)i - (double)K.cy) * zz / (double)K.fy);
     z = (float)zz;
 }
+__device__ __forceinline__ void pp_vertex_d(uint16_t dval, int w, const PPCam& K, int pix, float& x, float& y, float& z) {      // pp_vertex with the depth sample already loaded
+    const int i = pix / w, j = pix - i * w;
+    const double zz = (double)dval * (double)K.scale;
+    x = (float)(((double)j - (double)K.cx) * zz / (double)K.fx);
+    y = (float)(((double)i - (double)K.cy) * zz / (double)K.fy);
+    z = (float)zz;
+}
 __device__ __forceinline__ float pp_dot4(const float c[4], float x, float y, float z) { return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(c[0], x), __fmul_rn(c[1], y)), __fmul_rn(c[2], z)), c[3]); }
 
 __device__ uint32_t g_pp_mt[624];    // boost::mt19937(12345) after the first regeneration: identical for every plane, computed once on the host
@@ -178,15 +185,25 @@ __global__ void __launch_bounds__(PP_THREADS) k_planes_post(const uint16_t* __re
             atomicAdd(&s_sum[PP_SLOTS + slot], (unsigned long long)ry);
             atomicAdd(&s_sum[2 * PP_SLOTS + slot], (unsigned long long)rz);
         };
-        for (int i = tid * chunk; i < i_end; ++i) {
+        // four members per trip: their index and depth loads are issued together (the walk was bound by the latency of one dependent load pair per member)
+        for (int ib = tid * chunk; ib < i_end; ib += 4) {
+          int pixv[4]; uint16_t dv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) pixv[u] = ib + u < i_end ? midx[ib + u] : -1;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dv[u] = pixv[u] >= 0 ? depth[pixv[u]] : (uint16_t)0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (pixv[u] < 0) continue;
             float x, y, z;
-            pp_vertex(depth, w, K, midx[i], x, y, z);
+            pp_vertex_d(dv[u], w, K, pixv[u], x, y, z);
             const int i0 = (int)floorf(__fmul_rn(x, inv)) + 512, i1 = (int)floorf(__fmul_rn(y, inv)) + 512, i2 = (int)floorf(__fmul_rn(z, inv));
             if ((unsigned)i0 > 1023u || (unsigned)i1 > 1023u || (unsigned)i2 >= 4095u) { atomicOr(&s_i[1], 1); continue; }      // > 51 m sideways / 409 m deep: capacity flag
             const uint32_t key = ((uint32_t)i2 << 20) | ((uint32_t)i1 << 10) | (uint32_t)i0;
             if (key != run_key) { flush(); run_key = key; run_cnt = 0; rx = ry = rz = 0; }
             ++run_cnt;
             rx += llrint((double)x * 1048576.0); ry += llrint((double)y * 1048576.0); rz += llrint((double)z * 1048576.0);
+          }
         }
         flush();
     }
