@@ -658,12 +658,9 @@ int pslam_surface_normals_batch_dev(pslam_ctx* c, const uint16_t* d_depth, int n
     const size_t smem_ch = (size_t)SN_WARPS * 3 * (B.w3 + 2) * sizeof(float);
     const size_t smem_ii = (size_t)SN_WARPS * (((size_t)2 * (B.w3 + 1) * 3 * sizeof(double) + (size_t)2 * B.w3 * 3 * sizeof(float) + 15) & ~(size_t)15);
     if (smem_ch > 227 * 1024 || smem_ii > 227 * 1024) return set_error(c, PSLAM_E_INVALID, "surface normals: image too wide for the row buffers");
-    static bool attr_set = false;
-    if (!attr_set) {
-        PSLAM_CUDA(c, cudaFuncSetAttribute(k_sn_chamfer, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        PSLAM_CUDA(c, cudaFuncSetAttribute(k_sn_integral, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    // (the attribute is per device and contexts may live on several devices of one process: set it on every call, it is a cheap driver query)
+    if (smem_ch > 48 * 1024) PSLAM_CUDA(c, cudaFuncSetAttribute(k_sn_chamfer, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ch));
+    if (smem_ii > 48 * 1024) PSLAM_CUDA(c, cudaFuncSetAttribute(k_sn_integral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ii));
     PSLAM_LAUNCH(c, "sn_change", k_sn_change<<<gp, 256, 0, st>>>(B.w3, B.h3, B.d_cloud, B.d_dist));
     PSLAM_LAUNCH(c, "sn_chamfer", k_sn_chamfer<<<(nframes + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem_ch, st>>>(nframes, B.w3, B.h3, B.d_dist));
     PSLAM_LAUNCH(c, "sn_integral", k_sn_integral<<<(nframes + SN_WARPS - 1) / SN_WARPS, SN_WARPS * 32, smem_ii, st>>>(nframes, B.w3, B.h3, B.d_cloud, B.d_ix, B.d_iy));
