@@ -475,6 +475,9 @@ def main():
     assert LSD_SUBS <= SUBS_PER_STEP
 
     gray, depth = make_frames(world=world)
+    if world > 1:          # every rank replays the sequence from a different position, so that the key frames the ranks exchange differ
+        shift = rank * (len(gray) // world)
+        gray, depth = np.roll(gray, -shift, axis=0), np.roll(depth, -shift, axis=0)
     # the step's frames are built once, directly in page-locked host memory (the buffers the end-to-end leg hands to the ABI): the DISTINCT_FRAMES
     # frames of the rendered sequence, repeated in order until the step is full
     h_gray = torch.empty((FRAMES_PER_STEP, H, W), dtype=torch.uint8).pin_memory()
@@ -763,10 +766,11 @@ def main():
     for v in per_kernel.values():
         v["share"] = round(v["ms_total"] / tot, 4)
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_total"])
-    # DRAM bytes per frame of the dominant kernels from the committed `ncu --set full` capture (profiles/r1_ncu_full_summary.csv,
-    # dram__bytes_read.sum + dram__bytes_write.sum at 296 frames per launch), scaled to this run's frames per launch
-    NCU_DRAM_BYTES_PER_FRAME = {"lsd_regions": (7.700881e9 + 0.565746e9) / 296, "peac_cluster": (0.603116e9 + 0.338629e9) / 296,
-                                "peac_flood": (4.953115e9 + 1.131992e9) / 296}
+    # DRAM bytes per frame of the dominant kernels from the committed round-2 `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum of one
+    # launch / its frames: profiles/r2_ncu_full_lsd_kernels.csv at 3552 frames, profiles/r2_ncu_full_peac_kernels.csv at 1776; k_peac_flood from
+    # profiles/r1_ncu_full_summary.csv at 296 - its round-2 capture returned no DRAM counters), scaled to this run's frames per launch
+    NCU_DRAM_BYTES_PER_FRAME = {"lsd_regions": (99.155276e9 + 9.574393e9) / 3552, "peac_cluster": (8.573231e9 + 3.334866e9) / 1776,
+                                "peac_flood": (4.953115e9 + 1.131992e9) / 296, "lsd_improve": (3.480971e9 + 1.401838e9) / 3552}
     traffic = NCU_DRAM_BYTES_PER_FRAME.get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": round(per_kernel[dom]["achieved_gbs"] / peak, 6),

@@ -194,25 +194,26 @@ __global__ void __launch_bounds__(128) k_fast_cells(const uint8_t* __restrict__ 
     int pitch;
     const uint8_t* img = level_ptr(g, gray, pyr, frame, level, pitch);
 
-    // stage the window: aligned 32-bit loads; smem column 0 corresponds to image column (x0 & ~3)
+    // stage the window: aligned 32-bit loads; smem column 0 corresponds to image column (x0 & ~3).  One warp per row, one lane per word (no index division)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int xa0 = x0 & ~3, ox = x0 - xa0;
-    const int words = ((x1 + 3) >> 2) - (xa0 >> 2);
-    for (int i = threadIdx.x; i < wh * words; i += 128) {
-        const int r = i / words, wq = i - r * words;
-        const uint32_t v = *reinterpret_cast<const uint32_t*>(img + (size_t)(y0 + r) * pitch + xa0 + 4 * wq);
-        *reinterpret_cast<uint32_t*>(&win[r][4 * wq]) = v;
+    const int words = ((x1 + 3) >> 2) - (xa0 >> 2);                  // <= 19
+    for (int r = wid; r < wh; r += 4) {
+        if (lane < words) *reinterpret_cast<uint32_t*>(&win[r][4 * lane]) = *reinterpret_cast<const uint32_t*>(img + (size_t)(y0 + r) * pitch + xa0 + 4 * lane);
+        if (lane < (FAST_WIN_MAX + 4) / 4) *reinterpret_cast<uint32_t*>(&sc[r][4 * lane]) = 0u;
     }
-    for (int i = threadIdx.x; i < FAST_WIN_MAX * (FAST_WIN_MAX + 4) / 4; i += 128) reinterpret_cast<uint32_t*>(&sc[0][0])[i] = 0;
     if (threadIdx.x == 0) s_tot20 = 0;
     __syncthreads();
 
     const int wi = ww - 6, hi = wh - 6, P = wi * hi;
     {
-        const int wi2 = (wi + 1) >> 1, P2 = wi2 * hi;
-        for (int p0 = 0; p0 < P2; p0 += 128) {                // warp-uniform trip count: fast_score_pair votes across the warp
-            const int p = p0 + threadIdx.x;
-            if (p < P2) {
-                const int y = p / wi2, x = 2 * (p - y * wi2);
+        // pixel pairs: a warp iteration covers 32 >> lg rows of (1 << lg) pairs each (lg chosen so that a row of pairs fits), warps interleave
+        const int wi2 = (wi + 1) >> 1;
+        const int lg = wi2 <= 8 ? 3 : wi2 <= 16 ? 4 : 5;
+        const int rows_per_it = 32 >> lg, x2 = lane & ((1 << lg) - 1), yl = lane >> lg;
+        for (int yb = wid * rows_per_it; yb < hi; yb += 4 * rows_per_it) {          // warp-uniform trip count: fast_score_pair votes across the warp
+            const int y = yb + yl, x = 2 * x2;
+            if (x2 < wi2 && y < hi) {
                 int sa, sb;
                 fast_score_pair(win, x + 3 + ox, y + 3, g.min_th, sa, sb);
                 sc[y + 3][x + 3] = (uint8_t)sa;
@@ -226,15 +227,19 @@ __global__ void __launch_bounds__(128) k_fast_cells(const uint8_t* __restrict__ 
     const int chunk = (P + 127) / 128;      // <= 32 for windows up to 68x68
     const int pbeg = threadIdx.x * chunk, pend = min(P, pbeg + chunk);
     uint32_t m_max = 0, m_ini = 0;
-    for (int p = pbeg; p < pend; ++p) {
-        const int y = p / wi + 3, x = p - (p / wi) * wi + 3;
-        const int s = sc[y][x];
-        if (s == 0) continue;
-        const bool is_max = s > sc[y - 1][x - 1] && s > sc[y - 1][x] && s > sc[y - 1][x + 1] && s > sc[y][x - 1] &&
-                            s > sc[y][x + 1] && s > sc[y + 1][x - 1] && s > sc[y + 1][x] && s > sc[y + 1][x + 1];
-        if (is_max) {
-            m_max |= 1u << (p - pbeg);
-            if (s >= g.ini_th) m_ini |= 1u << (p - pbeg);
+    {
+        int y = pbeg / wi, x = pbeg - y * wi;                        // one division per thread, then the walk wraps by comparison
+        for (int p = pbeg; p < pend; ++p) {
+            const int s = sc[y + 3][x + 3];
+            if (s != 0) {
+                const uint8_t* r0 = &sc[y + 2][x + 2]; const uint8_t* r1 = &sc[y + 3][x + 2]; const uint8_t* r2 = &sc[y + 4][x + 2];
+                const bool is_max = s > r0[0] && s > r0[1] && s > r0[2] && s > r1[0] && s > r1[2] && s > r2[0] && s > r2[1] && s > r2[2];
+                if (is_max) {
+                    m_max |= 1u << (p - pbeg);
+                    if (s >= g.ini_th) m_ini |= 1u << (p - pbeg);
+                }
+            }
+            if (++x == wi) { x = 0; ++y; }
         }
     }
     if (m_ini) atomicAdd(&s_tot20, __popc(m_ini));
@@ -242,7 +247,6 @@ __global__ void __launch_bounds__(128) k_fast_cells(const uint8_t* __restrict__ 
     const uint32_t sel = s_tot20 > 0 ? m_ini : m_max;
     const int cnt = __popc(sel);
     // block exclusive scan of cnt
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }

@@ -141,8 +141,8 @@ int pose_run_packed(pslam_ctx* c) {
     if (!c->pose || c->pose->n_prob < 1) return set_error(c, PSLAM_E_INVALID, "no packed pose problems");
     PoseBuffers& B = *c->pose;
     // a batch is throughput-bound: the kernel's serial stretches (6x6 solve, barriers between the reductions) leave an SM idle unless several problems share
-    // it, and the register count allows 65536 / (regs x threads) of them - so a batch runs narrow CTAs (PSLAM_POSE_THREADS: 64, 128 or 256)
-    static const int nt = [] { const char* e = getenv("PSLAM_POSE_THREADS"); const int v = e ? atoi(e) : 64; return (v == 64 || v == 128 || v == 256) ? v : 64; }();
+    // it, and the register count allows 65536 / (regs x threads) of them - so a batch runs narrow CTAs (PSLAM_POSE_THREADS: 32, 64, 128 or 256)
+    static const int nt = [] { const char* e = getenv("PSLAM_POSE_THREADS"); const int v = e ? atoi(e) : 64; return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 64; }();
     PSLAM_LAUNCH(c, "pose_optimization", k_pose_optimization<<<B.n_prob, nt, 0, c->stream>>>(B.d_hdr, B.d_edges, B.d_err, B.d_level, B.d_flags[0],
                  B.d_flags[1], B.d_flags[2], B.d_flags[3], B.d_flags[4], B.d_out));
     PSLAM_CUDA(c, cudaGetLastError());
