@@ -183,7 +183,7 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
         const dim3 gv((g.cand_cap + 63) / 64, nframes);
         PSLAM_CUDA(c, cudaMemsetAsync(B.d_nfail, 0, (size_t)nframes * 4, st));
         PSLAM_LAUNCH(c, "lsd_validate", k_lsd_validate<<<gv, 64, 0, st>>>(g, B.d_ang, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_fail, B.d_nfail));
-        PSLAM_LAUNCH(c, "lsd_improve", k_lsd_improve<<<dim3(LSD_IMPROVE_CTAS, nframes), LSD_IMPROVE_WARPS * 32, 0, st>>>(g, B.d_ang, B.d_cands, B.d_cand_nfa, B.d_fail, B.d_nfail));
+        PSLAM_LAUNCH(c, "lsd_improve", k_lsd_improve<<<gv, 64, 0, st>>>(g, B.d_ang, B.d_cands, B.d_cand_nfa, B.d_fail, B.d_nfail));
     }
     PSLAM_LAUNCH(c, "lsd_emit", k_lsd_emit<<<nframes, 256, 0, st>>>(g, B.d_cands, B.d_ncand, B.d_cand_nfa, B.d_segs, B.d_wpn, B.d_nsegs, B.d_status));
     PSLAM_CUDA(c, cudaGetLastError());

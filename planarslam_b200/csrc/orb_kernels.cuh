@@ -603,13 +603,14 @@ __global__ void __launch_bounds__(128) k_blur_tma(const __grid_constant__ BlurTm
     for (int j = 0; j < 16; ++j) {
         blur_hrow(&tile[16 * strip + j + 6][0], lane, hw[(j + 6) % 7]);
         if (ys + j < h) {
-            uint32_t out = 0;
+            // acc + 32768 <= 255 * 65536 + 32768 (the taps sum to 256 in both passes), so bits 16..23 are the rounded pixel and no clamp is needed:
+            // the four result bytes are gathered with three byte permutes instead of shift / or chains
+            uint32_t r[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t acc = 18u * (hw[j % 7][q] + hw[(j + 6) % 7][q]) + 34u * (hw[(j + 1) % 7][q] + hw[(j + 5) % 7][q]) +
-                                     48u * (hw[(j + 2) % 7][q] + hw[(j + 4) % 7][q]) + 56u * hw[(j + 3) % 7][q];
-                out |= min(255u, (acc + 32768u) >> 16) << (8 * q);
-            }
+            for (int q = 0; q < 4; ++q)
+                r[q] = 18u * (hw[j % 7][q] + hw[(j + 6) % 7][q]) + 34u * (hw[(j + 1) % 7][q] + hw[(j + 5) % 7][q]) +
+                       48u * (hw[(j + 2) % 7][q] + hw[(j + 4) % 7][q]) + 56u * hw[(j + 3) % 7][q] + 32768u;
+            const uint32_t out = __byte_perm(__byte_perm(r[0], r[1], 0x0062), __byte_perm(r[2], r[3], 0x0062), 0x5410);
             *reinterpret_cast<uint32_t*>(D + (size_t)(ys + j) * pitch + x) = out;
         }
     }
