@@ -163,8 +163,13 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     PSLAM_CUDA(c, cudaMemsetAsync(B.d_smax, 0, (size_t)nframes * 4, st));
     const dim3 gb((g.W + LSD_TW - 1) / LSD_TW, (g.H + LSD_TH - 1) / LSD_TH, nframes);
     PSLAM_LAUNCH(c, "lsd_blur_scale", k_lsd_blur_scale<<<gb, 256, 0, st>>>(g, d_gray, B.d_ix, B.d_ax, B.d_iy, B.d_ay, B.d_scaled));
-    const dim3 gg((g.W + 63) / 64, (g.H + 3) / 4, nframes);
-    PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient<<<gg, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_ang, B.d_cs, B.d_gxy, B.d_smax));
+    if ((g.W & 3) == 0 && !std::getenv("PSLAM_LSD_GRADIENT1")) {        // four pixels per thread when a row is a whole number of words (buffers are 256-byte aligned)
+        const dim3 gg4(((g.W >> 2) + 63) / 64, (g.H + 3) / 4, nframes);
+        PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient4<<<gg4, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_ang, B.d_cs, B.d_gxy, B.d_smax));
+    } else {
+        const dim3 gg((g.W + 63) / 64, (g.H + 3) / 4, nframes);
+        PSLAM_LAUNCH(c, "lsd_gradient", k_lsd_gradient<<<gg, 256, 0, st>>>(g, B.d_scaled, B.d_lut, B.d_ang, B.d_cs, B.d_gxy, B.d_smax));
+    }
     PSLAM_CUDA(c, cudaFuncSetAttribute(k_lsd_order, cudaFuncAttributeMaxDynamicSharedMemorySize, LSD_ORDER_SMEM));
     if ((size_t)B.g.seg_cap * sizeof(float) > 48 * 1024) {
         if ((size_t)B.g.seg_cap * sizeof(float) > 227 * 1024) return set_error(c, PSLAM_E_INVALID, "image too large for the key-line ranking buffer");

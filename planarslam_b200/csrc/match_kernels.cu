@@ -21,48 +21,63 @@ namespace pslam {
 #define MATCH_TILE 256
 #define MATCH_WARPS 8
 
+// Every warp keeps MATCH_NQ query rows in registers: a 32-byte train row read from shared memory serves four distances (the kernel with one query per warp was
+// bound by its two 16-byte shared loads per distance).
+#define MATCH_NQ 4
 __global__ void __launch_bounds__(MATCH_WARPS * 32) k_hamming_knn2(const uint8_t* __restrict__ q, const int32_t* __restrict__ nq, int capq,
                                                                   const uint8_t* __restrict__ t, const int32_t* __restrict__ nt, int capt,
                                                                   int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
     __shared__ uint4 tile[MATCH_TILE][2];
     const int frame = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int nQ = min(nq[frame], capq), nT = min(nt[frame], capt);
-    const int qi = blockIdx.x * MATCH_WARPS + wid;
-    const bool active = qi < nQ;
-    uint32_t qw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (active) {
-        const uint4* qp = reinterpret_cast<const uint4*>(q + ((size_t)frame * capq + qi) * 32);
-        const uint4 a = qp[0], b = qp[1];
-        qw[0] = a.x; qw[1] = a.y; qw[2] = a.z; qw[3] = a.w; qw[4] = b.x; qw[5] = b.y; qw[6] = b.z; qw[7] = b.w;
+    const int q0 = (blockIdx.x * MATCH_WARPS + wid) * MATCH_NQ;
+    uint32_t qw[MATCH_NQ][8];
+#pragma unroll
+    for (int u = 0; u < MATCH_NQ; ++u) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) qw[u][k] = 0;
+        if (q0 + u < nQ) {
+            const uint4* qp = reinterpret_cast<const uint4*>(q + ((size_t)frame * capq + q0 + u) * 32);
+            const uint4 a = qp[0], b = qp[1];
+            qw[u][0] = a.x; qw[u][1] = a.y; qw[u][2] = a.z; qw[u][3] = a.w; qw[u][4] = b.x; qw[u][5] = b.y; qw[u][6] = b.z; qw[u][7] = b.w;
+        }
     }
     const uint32_t NONE = 0xffffffffu;
-    uint32_t k0 = NONE, k1 = NONE;
+    uint32_t k0[MATCH_NQ], k1[MATCH_NQ];
+#pragma unroll
+    for (int u = 0; u < MATCH_NQ; ++u) { k0[u] = NONE; k1[u] = NONE; }
     const uint4* tp = reinterpret_cast<const uint4*>(t + (size_t)frame * capt * 32);
     for (int base = 0; base < nT; base += MATCH_TILE) {
         const int cnt = min(MATCH_TILE, nT - base);
         __syncthreads();
         for (int i = threadIdx.x; i < cnt * 2; i += MATCH_WARPS * 32) tile[i >> 1][i & 1] = tp[(size_t)(base + (i >> 1)) * 2 + (i & 1)];
         __syncthreads();
-        if (active)
+        if (q0 < nQ)
             for (int j = lane; j < cnt; j += 32) {
                 const uint4 a = tile[j][0], b = tile[j][1];
-                const int d = __popc(qw[0] ^ a.x) + __popc(qw[1] ^ a.y) + __popc(qw[2] ^ a.z) + __popc(qw[3] ^ a.w) +
-                              __popc(qw[4] ^ b.x) + __popc(qw[5] ^ b.y) + __popc(qw[6] ^ b.z) + __popc(qw[7] ^ b.w);
-                const uint32_t key = ((uint32_t)d << 16) | (uint32_t)(base + j);
-                if (key < k0) { k1 = k0; k0 = key; } else if (key < k1) k1 = key;
+#pragma unroll
+                for (int u = 0; u < MATCH_NQ; ++u) {
+                    const int d = __popc(qw[u][0] ^ a.x) + __popc(qw[u][1] ^ a.y) + __popc(qw[u][2] ^ a.z) + __popc(qw[u][3] ^ a.w) +
+                                  __popc(qw[u][4] ^ b.x) + __popc(qw[u][5] ^ b.y) + __popc(qw[u][6] ^ b.z) + __popc(qw[u][7] ^ b.w);
+                    const uint32_t key = ((uint32_t)d << 16) | (uint32_t)(base + j);
+                    if (key < k0[u]) { k1[u] = k0[u]; k0[u] = key; } else if (key < k1[u]) k1[u] = key;
+                }
             }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
-        const uint32_t lo = min(k0, o0), hi = max(k0, o0);
-        k1 = min(hi, min(k1, o1));
-        k0 = lo;
-    }
-    if (active && lane == 0) {
-        const size_t o = ((size_t)frame * capq + qi) * 2;
-        idx[o] = k0 == NONE ? -1 : (int)(k0 & 0xffff); dist[o] = k0 == NONE ? 256 : (int)(k0 >> 16);
-        idx[o + 1] = k1 == NONE ? -1 : (int)(k1 & 0xffff); dist[o + 1] = k1 == NONE ? 256 : (int)(k1 >> 16);
+    for (int u = 0; u < MATCH_NQ; ++u) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0[u], o), o1 = __shfl_xor_sync(0xffffffffu, k1[u], o);
+            const uint32_t lo = min(k0[u], o0), hi = max(k0[u], o0);
+            k1[u] = min(hi, min(k1[u], o1));
+            k0[u] = lo;
+        }
+        if (q0 + u < nQ && lane == 0) {
+            const size_t o = ((size_t)frame * capq + q0 + u) * 2;
+            idx[o] = k0[u] == NONE ? -1 : (int)(k0[u] & 0xffff); dist[o] = k0[u] == NONE ? 256 : (int)(k0[u] >> 16);
+            idx[o + 1] = k1[u] == NONE ? -1 : (int)(k1[u] & 0xffff); dist[o + 1] = k1[u] == NONE ? 256 : (int)(k1[u] >> 16);
+        }
     }
 }
 
@@ -104,7 +119,7 @@ int pslam_hamming_knn2_batch_dev(pslam_ctx* c, const uint8_t* d_q, const int32_t
     if (!d_q || !d_nq || !d_t || !d_nt || !d_idx || !d_dist || nframes < 1 || capq < 1 || capt < 1 || capt > 65535)
         return set_error(c, PSLAM_E_INVALID, "null pointer, nframes < 1 or capacity outside [1, 65535]");
     PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
-    PSLAM_LAUNCH(c, "hamming_knn2", k_hamming_knn2<<<dim3((capq + MATCH_WARPS - 1) / MATCH_WARPS, nframes), MATCH_WARPS * 32, 0, c->stream>>>(
+    PSLAM_LAUNCH(c, "hamming_knn2", k_hamming_knn2<<<dim3((capq + MATCH_WARPS * MATCH_NQ - 1) / (MATCH_WARPS * MATCH_NQ), nframes), MATCH_WARPS * 32, 0, c->stream>>>(
                      d_q, d_nq, capq, d_t, d_nt, capt, d_idx, d_dist));
     if (d_good && d_ngood) PSLAM_LAUNCH(c, "match_gate", k_match_gate<<<nframes, 256, 0, c->stream>>>(d_nq, capq, d_idx, d_dist, d_good, d_ngood));
     PSLAM_CUDA(c, cudaGetLastError());
