@@ -520,6 +520,40 @@ int pslam_search_by_bow(pslam_ctx* ctx, int n_kf, const uint8_t* kf_desc, const 
                         const float* f_angle, int f_nodes, const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat,
                         float nnratio, int check_orientation, int32_t* match);
 
+/* Replaces  int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12)
+ *           include/ORBmatcher.h:56, src/ORBmatcher.cc:526-659 - the loop-closure matcher (LoopClosing::ComputeSim3, src/LoopClosing.cc:258), the consumer
+ *           of the key-frame descriptor exchange.
+ * Same array layout as pslam_search_by_bow, both sides with map-point flags (has_mp[i] = vpMapPoints[i] && !isBad()); the distance gate is the
+ * strict bestDist1 < TH_LOW of this overload.  match12[i1] = feature of key frame 2 whose map point the call stores into vpMatches12[i1] (-1: NULL).
+ * Returns nmatches (>= 0) or a negative pslam_status. */
+int pslam_search_by_bow_kf(pslam_ctx* ctx, int n1, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int nodes1, const int32_t* node_id1,
+                           const int32_t* node_off1, const int32_t* node_feat1, int n2, const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2,
+                           int nodes2, const int32_t* node_id2, const int32_t* node_off2, const int32_t* node_feat2, float nnratio, int check_orientation,
+                           int32_t* match12);
+
+/* The key-frame database of KeyFrameDatabase (include/KeyFrameDatabase.h:43-75) as the candidate searches read it: the BowVectors of the key frames in the
+ * order KeyFrameDatabase::add saw them (src/KeyFrameDatabase.cc:38-44; an erased key frame is simply left out), CSR with strictly ascending word ids per
+ * key frame (std::map order).  Uploaded once and kept in HBM by the context; a second call replaces it, n_kf = 0 releases it. */
+int pslam_bow_database_set(pslam_ctx* ctx, int n_kf, const int32_t* kf_off, const int32_t* kf_word, const double* kf_val);
+
+/* Replaces  std::vector<KeyFrame*> KeyFrameDatabase::DetectLoopCandidates(KeyFrame* pKF, float minScore)
+ *           include/KeyFrameDatabase.h:58, src/KeyFrameDatabase.cc:76-197 with DBoW2's L1 score (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-68).
+ * Query = pKF->mBowVec (n_q words ascending + values).  covis[k][covis_stride] = KeyFrame::GetBestCovisibilityKeyFrames(10) of database key frame k as
+ * database indices, -1 ends a row; connected[k] != 0: key frame k is in pKF->GetConnectedKeyFrames() (NULL: none).  candidates (capacity n_kf) receives
+ * vpLoopCandidates as database indices in the reference's order.  Optional outputs, n_kf entries each: common_words[k] = mnLoopWords after the call,
+ * score[k] = mLoopScore where the reference evaluates it (entries of other key frames are left untouched).
+ * Not reproduced: a query key frame with mnId 0 finds nothing in the reference (mnLoopQuery starts at 0); LoopClosing never queries that key frame.
+ * Returns the number of candidates (>= 0) or a negative pslam_status. */
+int pslam_detect_loop_candidates(pslam_ctx* ctx, int n_q, const int32_t* q_word, const double* q_val, const int32_t* covis, int covis_stride,
+                                 const uint8_t* connected, float min_score, int32_t* candidates, int32_t* common_words, float* score);
+
+/* Replaces  std::vector<KeyFrame*> KeyFrameDatabase::DetectRelocalizationCandidates(Frame* F)   include/KeyFrameDatabase.h:61, src/KeyFrameDatabase.cc:199-305.
+ * reloc_score_io[k] = KeyFrame::mRelocScore of database key frame k: the reference adds a covisible neighbour's mRelocScore whenever that neighbour shares a
+ * word with the frame, also when it did not evaluate the score for this frame - the value an earlier query left (the constructor does not initialise it;
+ * pass zeros for a fresh database).  Updated in place like the reference updates the key frames. */
+int pslam_detect_relocalization_candidates(pslam_ctx* ctx, int n_q, const int32_t* q_word, const double* q_val, const int32_t* covis, int covis_stride,
+                                           float* reloc_score_io, int32_t* candidates, int32_t* common_words);
+
 /* Replaces  DBoW2::TemplatedVocabulary<FORB::TDescriptor, FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
  *           Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1125-1252, called by Frame::ComputeBoW / KeyFrame::ComputeBoW
  *           (src/KeyFrame.cc:66-76: mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4); TF_IDF weights, L1 norm).

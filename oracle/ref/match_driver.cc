@@ -39,6 +39,8 @@
 #include "PlaneMatcher.h"
 #include "Optimizer.h"
 #include "Config.h"
+#include "KeyFrameDatabase.h"
+#include "ORBVocabulary.h"
 #undef private
 #undef protected
 #include "pslam_abi.h"
@@ -235,6 +237,115 @@ extern "C" int ref_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* 
     for (int i = 0; i < n_f; ++i) match[i] = vpMapPointMatches[i] ? w.index.at(vpMapPointMatches[i]) : -1;     // index of the key-frame feature whose map point was taken
     delete pKF;
     return n;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)   src/ORBmatcher.cc:526-659 (the loop-closure matcher, LoopClosing::ComputeSim3 :258)
+extern "C" int ref_search_by_bow_kf(int n1, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int nodes1, const int32_t* node_id1, const int32_t* node_off1,
+                                    const int32_t* node_feat1, int n2, const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2, int nodes2,
+                                    const int32_t* node_id2, const int32_t* node_off2, const int32_t* node_feat2, float nnratio, int check_orientation, int32_t* match12) {
+    World w;
+    const float zero3[3] = {0, 0, 0};
+    std::unordered_map<MapPoint*, int> index2;
+    auto make_kf = [&](int n, const uint8_t* desc, const float* angle, const uint8_t* has_mp, int nodes, const int32_t* id, const int32_t* off, const int32_t* feat,
+                       std::unordered_map<MapPoint*, int>* index) {
+        Frame F;
+        F.N = n;
+        F.mvKeysUn.resize(n);
+        for (int i = 0; i < n; ++i) { F.mvKeysUn[i].angle = angle[i]; F.mvKeysUn[i].octave = 0; }
+        F.mvKeys = F.mvKeysUn;
+        F.mDescriptors = cv::Mat(n, 32, CV_8U);
+        for (int i = 0; i < n; ++i) std::memcpy(F.mDescriptors.ptr(i), desc + 32 * (size_t)i, 32);
+        F.mvpMapPoints.assign(n, static_cast<MapPoint*>(NULL));
+        F.mvbOutlier.assign(n, false);
+        F.SetPose(cv::Mat::eye(4, 4, CV_32F));
+        F.mFeatVec = feat_vec(nodes, id, off, feat);
+        for (int i = 0; i < n; ++i)
+            if (has_mp[i]) { MapPoint* p = w.make_point(zero3, zero3, 0, 0, nullptr, true); w.pts.push_back(p); F.mvpMapPoints[i] = p; if (index) (*index)[p] = i; }
+        return new KeyFrame(F, &w.map, static_cast<KeyFrameDatabase*>(NULL));
+    };
+    KeyFrame* k1 = make_kf(n1, desc1, angle1, has_mp1, nodes1, node_id1, node_off1, node_feat1, nullptr);
+    KeyFrame* k2 = make_kf(n2, desc2, angle2, has_mp2, nodes2, node_id2, node_off2, node_feat2, &index2);
+    ORBmatcher matcher(nnratio, check_orientation != 0);
+    std::vector<MapPoint*> vpMatches12;
+    const int n = matcher.SearchByBoW(k1, k2, vpMatches12);
+    for (int i = 0; i < n1; ++i) match12[i] = vpMatches12[i] ? index2.at(vpMatches12[i]) : -1;
+    delete k1; delete k2;
+    return n;
+}
+
+// KeyFrameDatabase::DetectLoopCandidates / DetectRelocalizationCandidates   src/KeyFrameDatabase.cc:76-305 with DBoW2's L1 score (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp)
+namespace {
+DBoW2::BowVector bow_vec(const int32_t* word, const double* val, int n) {
+    DBoW2::BowVector v;
+    for (int i = 0; i < n; ++i) v.insert(std::make_pair((DBoW2::WordId)word[i], (DBoW2::WordValue)val[i]));
+    return v;
+}
+struct LoopWorld {
+    World w;
+    ORBVocabulary voc;                   // default: TF_IDF weighting, L1_NORM scoring (the reference's ORBvoc.txt header says the same)
+    KeyFrameDatabase db;
+    std::vector<KeyFrame*> kfs;
+    std::unordered_map<KeyFrame*, int> index;
+    LoopWorld(int n_kf, const int32_t* off, const int32_t* word, const double* val, const int32_t* covis, int covis_stride, int32_t max_query_word) : db(voc) {
+        int32_t max_word = max_query_word;
+        for (int i = 0; i < off[n_kf]; ++i) max_word = std::max(max_word, word[i]);
+        db.mvInvertedFile.clear();
+        db.mvInvertedFile.resize((size_t)max_word + 1);
+        for (int k = 0; k < n_kf; ++k) {
+            Frame F;
+            F.N = 0;
+            F.SetPose(cv::Mat::eye(4, 4, CV_32F));
+            F.mBowVec = bow_vec(word + off[k], val + off[k], off[k + 1] - off[k]);
+            KeyFrame* kf = new KeyFrame(F, &w.map, &db);
+            index[kf] = k;
+            kfs.push_back(kf);
+            db.add(kf);
+        }
+        for (int k = 0; k < n_kf && covis; ++k)
+            for (int j = 0; j < covis_stride; ++j) {
+                const int k2 = covis[(size_t)k * covis_stride + j];
+                if (k2 < 0) break;
+                kfs[k]->mvpOrderedConnectedKeyFrames.push_back(kfs[k2]);
+            }
+    }
+    ~LoopWorld() { for (KeyFrame* k : kfs) delete k; }
+};
+}  // namespace
+
+extern "C" int ref_detect_loop_candidates(const int32_t* q_word, const double* q_val, int n_q, int n_kf, const int32_t* off, const int32_t* word, const double* val,
+                                          const int32_t* covis, int covis_stride, const uint8_t* connected, float min_score, int32_t* cand, int32_t* common_words,
+                                          float* score) {
+    LoopWorld L(n_kf, off, word, val, covis, covis_stride, n_q ? q_word[n_q - 1] : 0);
+    Frame F;
+    F.N = 0;
+    F.SetPose(cv::Mat::eye(4, 4, CV_32F));
+    F.mBowVec = bow_vec(q_word, q_val, n_q);
+    KeyFrame* q = new KeyFrame(F, &L.w.map, &L.db);
+    for (int k = 0; k < n_kf; ++k) {
+        if (connected && connected[k]) q->mConnectedKeyFrameWeights[L.kfs[k]] = 1;
+        L.kfs[k]->mLoopScore = score[k];           // uninitialised in the reference's constructor: the caller's sentinel shows where it was evaluated
+    }
+    const std::vector<KeyFrame*> r = L.db.DetectLoopCandidates(q, min_score);
+    for (size_t i = 0; i < r.size(); ++i) cand[i] = L.index.at(r[i]);
+    for (int k = 0; k < n_kf; ++k) { common_words[k] = L.kfs[k]->mnLoopWords; score[k] = L.kfs[k]->mLoopScore; }
+    delete q;
+    return (int)r.size();
+}
+
+extern "C" int ref_detect_relocalization_candidates(const int32_t* q_word, const double* q_val, int n_q, int n_kf, const int32_t* off, const int32_t* word,
+                                                    const double* val, const int32_t* covis, int covis_stride, float* reloc_score_io, int32_t* cand,
+                                                    int32_t* common_words) {
+    LoopWorld L(n_kf, off, word, val, covis, covis_stride, n_q ? q_word[n_q - 1] : 0);
+    Frame F;
+    F.N = 0;
+    F.SetPose(cv::Mat::eye(4, 4, CV_32F));
+    F.mBowVec = bow_vec(q_word, q_val, n_q);
+    F.mnId = 1000000;                              // mnRelocQuery starts at 0: a frame id of 0 would list nothing
+    for (int k = 0; k < n_kf; ++k) L.kfs[k]->mRelocScore = reloc_score_io[k];
+    const std::vector<KeyFrame*> r = L.db.DetectRelocalizationCandidates(&F);
+    for (size_t i = 0; i < r.size(); ++i) cand[i] = L.index.at(r[i]);
+    for (int k = 0; k < n_kf; ++k) { common_words[k] = L.kfs[k]->mnRelocWords; reloc_score_io[k] = L.kfs[k]->mRelocScore; }
+    return (int)r.size();
 }
 
 // Frame::isInFrustum(MapLine*, viewingCosLimit)   src/Frame.cc:369-437 (with MapLine::PredictScale / Get{Min,Max}DistanceInvariance, src/MapLine.cpp:364-390)

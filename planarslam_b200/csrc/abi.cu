@@ -84,6 +84,7 @@ void pslam_destroy(pslam_ctx* c) {
     track_free(c);
     exchange_free(c);
     planepost_free(c);
+    bowdb_free(c);
     frame_free(c);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;

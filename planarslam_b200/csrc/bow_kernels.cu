@@ -3,10 +3,19 @@
 // common node walks the key-frame features of the node in order (an earlier match takes its frame feature away from later
 // ones), the lanes evaluate the 256-bit Hamming distances to the node's frame features, a warp top-2 gives the reference's
 // best / second-best, and a second kernel applies the rotation-histogram filter (ComputeThreeMaxima, :1666-1707).
+// The same kernels serve ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (:526-659, the loop-closure matcher): both sides carry map-point
+// flags there and the distance gate is strict (bestDist1 < TH_LOW instead of <=).
+//
+// Loop-closure / relocalisation candidates (KeyFrameDatabase::DetectLoopCandidates / DetectRelocalizationCandidates, src/KeyFrameDatabase.cc:76-305): the
+// database's BowVectors live in HBM as CSR (pslam_bow_database_set); k_bow_db_scores runs one warp per key frame - lanes look the key frame's words up in the
+// query (binary search), count the shared words, and fold the DBoW2 L1 terms (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp:23-68) in ascending word order, the
+// order the reference's merge loop adds them in, so the double sum (and the float it is stored as) is bit-identical.  The list logic that follows (common-word
+// gate, covisibility accumulation, 0.75 x best) touches a few dozen key frames and runs on the host over the downloaded per-key-frame triples.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "pslam_internal.h"
@@ -26,7 +35,8 @@ __device__ __forceinline__ void bow_top2(uint32_t& k0, uint32_t& k1) {
 __global__ void __launch_bounds__(128) k_bow_nodes(int n_pairs, const int2* __restrict__ pairs, const uint8_t* __restrict__ kf_desc, const float* __restrict__ kf_angle,
                                                    const uint8_t* __restrict__ kf_has_mp, const int32_t* __restrict__ kf_off, const int32_t* __restrict__ kf_feat,
                                                    const uint8_t* __restrict__ f_desc, const float* __restrict__ f_angle, const int32_t* __restrict__ f_off,
-                                                   const int32_t* __restrict__ f_feat, float nnratio, int check_ori, int32_t* __restrict__ match,
+                                                   const int32_t* __restrict__ f_feat, const uint8_t* __restrict__ f_has_mp, int th_low, float nnratio, int check_ori,
+                                                   int32_t* __restrict__ match,
                                                    int8_t* __restrict__ bin_of, int32_t* __restrict__ hist, int32_t* __restrict__ nmatches) {
     const int lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= n_pairs) return;
@@ -43,7 +53,7 @@ __global__ void __launch_bounds__(128) k_bow_nodes(int n_pairs, const int2* __re
         uint32_t k0 = NONE, k1 = NONE;
         for (int p = lane; p < nfn; p += 32) {
             const int jf = f_feat[f0 + p];
-            if (match[jf] >= 0) continue;
+            if (match[jf] >= 0 || (f_has_mp && !f_has_mp[jf])) continue;
             int d = 0;
 #pragma unroll
             for (int t = 0; t < 8; ++t) d += __popc(dk[t] ^ reinterpret_cast<const uint32_t*>(f_desc)[8 * jf + t]);
@@ -53,7 +63,7 @@ __global__ void __launch_bounds__(128) k_bow_nodes(int n_pairs, const int2* __re
         bow_top2(k0, k1);
         if (k0 == NONE) continue;
         const int bestDist1 = (int)(k0 >> 16), bestDist2 = k1 == NONE ? 256 : (int)(k1 >> 16);
-        if (bestDist1 <= 50 && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
+        if (bestDist1 <= th_low && (float)bestDist1 < __fmul_rn(nnratio, (float)bestDist2)) {
             const int jf = f_feat[f0 + (k0 & 0xffff)];
             if (lane == 0) {
                 match[jf] = ik;
@@ -97,6 +107,162 @@ __global__ void __launch_bounds__(256) k_bow_orientation(int nf, int32_t* __rest
     if (removed) atomicSub(nmatches, removed);
 }
 
+struct BowDbBuffers {
+    int n_kf = 0, total = 0;
+    int32_t* d_off = nullptr; int32_t* d_word = nullptr; double* d_val = nullptr;
+    int32_t* d_common = nullptr; int32_t* d_first = nullptr; float* d_score = nullptr;
+    int32_t* d_qword = nullptr; double* d_qval = nullptr; int q_cap = 0;
+    std::vector<int32_t> h_common, h_first; std::vector<float> h_score;
+};
+
+void bowdb_free(pslam_ctx* c) {
+    if (!c->bowdb) return;
+    BowDbBuffers& B = *c->bowdb;
+    cudaFree(B.d_off); cudaFree(B.d_word); cudaFree(B.d_val); cudaFree(B.d_common); cudaFree(B.d_first); cudaFree(B.d_score); cudaFree(B.d_qword); cudaFree(B.d_qval);
+    delete c->bowdb;
+    c->bowdb = nullptr;
+}
+
+// One warp per key frame of the database.  Query and key-frame words are ascending, so the shared words come out in the order of the reference's merge loop.
+__global__ void __launch_bounds__(128) k_bow_db_scores(int n_kf, const int32_t* __restrict__ off, const int32_t* __restrict__ word, const double* __restrict__ val, int n_q,
+                                                       const int32_t* __restrict__ q_word, const double* __restrict__ q_val, int32_t* __restrict__ common,
+                                                       int32_t* __restrict__ first, float* __restrict__ score) {
+    const int lane = threadIdx.x & 31, k = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (k >= n_kf) return;
+    const int b = off[k], e = off[k + 1];
+    int n_common = 0, first_q = -1;
+    double sum = 0.0;
+    for (int base = b; base < e; base += 32) {
+        const int i = base + lane;
+        int qi = -1;
+        double term = 0.0;
+        if (i < e) {
+            const int32_t w = word[i];
+            int lo = 0, hi = n_q;                      // lower_bound of w in the query's words
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (q_word[mid] < w) lo = mid + 1; else hi = mid; }
+            if (lo < n_q && q_word[lo] == w) {
+                qi = lo;
+                const double vi = q_val[lo], wi = val[i];
+                term = (fabs(vi - wi) - fabs(vi)) - fabs(wi);
+            }
+        }
+        unsigned hits = __ballot_sync(0xffffffffu, qi >= 0);
+        if (hits && first_q < 0) first_q = __shfl_sync(0xffffffffu, qi, __ffs(hits) - 1);
+        n_common += __popc(hits);
+        while (hits) {                                 // ordered fold: every lane adds the same terms in ascending word order
+            const int src = __ffs(hits) - 1;
+            sum += __shfl_sync(0xffffffffu, term, src);
+            hits &= hits - 1;
+        }
+    }
+    if (lane == 0) { common[k] = n_common; first[k] = first_q; score[k] = (float)(-sum / 2.0); }
+}
+
+namespace {
+
+struct BowSideArgs { int n; const uint8_t* desc; const float* angle; const uint8_t* has_mp; int nodes; const int32_t* node_id; const int32_t* node_off; const int32_t* node_feat; };
+
+// match2[j2] = feature of side 1 matched to feature j2 of side 2 (-1 none); side 1 is walked in feature-vector order like the reference's outer loop
+int bow_search_impl(pslam_ctx* c, const BowSideArgs& A, const BowSideArgs& Bs, int th_low, float nnratio, int check_orientation, int32_t* match2) {
+    const int nkf = A.n, nf = Bs.n, kf_nodes = A.nodes, f_nodes = Bs.nodes;
+    if (nkf < 0 || nf < 0 || kf_nodes < 0 || f_nodes < 0 || (nf && !match2) || (nkf && (!A.desc || !A.angle || !A.has_mp)) || (nf && (!Bs.desc || !Bs.angle)) ||
+        (kf_nodes && (!A.node_id || !A.node_off || !A.node_feat)) || (f_nodes && (!Bs.node_id || !Bs.node_off || !Bs.node_feat)))
+        return set_error(c, PSLAM_E_INVALID, "bad SearchByBoW arrays");
+    for (int i = 0; i < nf; ++i) match2[i] = -1;
+    // merge-join of the two (ascending) node-id lists, like the reference's two map iterators
+    std::vector<int2> pairs;
+    for (int a = 0, b = 0; a < kf_nodes && b < f_nodes;) {
+        if (A.node_id[a] == Bs.node_id[b]) { pairs.push_back(make_int2(a, b)); ++a; ++b; }
+        else if (A.node_id[a] < Bs.node_id[b]) a = (int)(std::lower_bound(A.node_id, A.node_id + kf_nodes, Bs.node_id[b]) - A.node_id);
+        else b = (int)(std::lower_bound(Bs.node_id, Bs.node_id + f_nodes, A.node_id[a]) - Bs.node_id);
+    }
+    if (pairs.empty() || nf == 0 || nkf == 0) return 0;
+    const int nkfeat = A.node_off[kf_nodes], nffeat = Bs.node_off[f_nodes];
+    for (int i = 0; i < nkfeat; ++i) if (A.node_feat[i] < 0 || A.node_feat[i] >= nkf) return set_error(c, PSLAM_E_INVALID, "key-frame feature index out of range");
+    for (int i = 0; i < nffeat; ++i) if (Bs.node_feat[i] < 0 || Bs.node_feat[i] >= nf) return set_error(c, PSLAM_E_INVALID, "frame feature index out of range");
+    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t st = c->stream;
+    const size_t sz[] = {pairs.size() * 8, (size_t)nkf * 32, (size_t)nkf * 4, (size_t)nkf, (size_t)(kf_nodes + 1) * 4, (size_t)nkfeat * 4, (size_t)nf * 32,
+                         (size_t)nf * 4, (size_t)(f_nodes + 1) * 4, (size_t)nffeat * 4, (size_t)nf * 4, Bs.has_mp ? (size_t)nf : 0, (size_t)nf, 31 * 4};
+    const void* src[] = {pairs.data(), A.desc, A.angle, A.has_mp, A.node_off, A.node_feat, Bs.desc, Bs.angle, Bs.node_off, Bs.node_feat, match2, Bs.has_mp, nullptr, nullptr};
+    size_t off[15]; off[0] = 0;
+    for (int i = 0; i < 14; ++i) off[i + 1] = (off[i] + sz[i] + 15) & ~(size_t)15;
+    uint8_t* d = nullptr;
+    PSLAM_CUDA(c, cudaMalloc((void**)&d, off[14]));
+    cudaError_t e = cudaMemsetAsync(d + off[13], 0, 31 * 4, st);
+    for (int i = 0; i < 12 && e == cudaSuccess; ++i) if (sz[i]) e = cudaMemcpyAsync(d + off[i], src[i], sz[i], cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { cudaFree(d); return check_cuda(c, e, "SearchByBoW upload"); }
+    int32_t* d_hist = (int32_t*)(d + off[13]);
+    PSLAM_LAUNCH(c, "bow_nodes", k_bow_nodes<<<((int)pairs.size() + 3) / 4, 128, 0, st>>>((int)pairs.size(), (const int2*)(d + off[0]), d + off[1], (const float*)(d + off[2]),
+                 d + off[3], (const int32_t*)(d + off[4]), (const int32_t*)(d + off[5]), d + off[6], (const float*)(d + off[7]), (const int32_t*)(d + off[8]),
+                 (const int32_t*)(d + off[9]), Bs.has_mp ? d + off[11] : nullptr, th_low, nnratio, check_orientation, (int32_t*)(d + off[10]), (int8_t*)(d + off[12]),
+                 d_hist, d_hist + 30));
+    if (check_orientation)
+        PSLAM_LAUNCH(c, "bow_orientation", k_bow_orientation<<<1, 256, 0, st>>>(nf, (int32_t*)(d + off[10]), (const int8_t*)(d + off[12]), d_hist, d_hist + 30));
+    int32_t n = 0;
+    e = cudaMemcpyAsync(match2, d + off[10], (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_hist + 30, 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return check_cuda(c, e, "SearchByBoW");
+    return n;
+}
+
+// shared words + L1 scores of every database key frame against one query BowVector, downloaded into the buffers' host vectors
+int bowdb_score(pslam_ctx* c, int n_q, const int32_t* q_word, const double* q_val) {
+    if (!c->bowdb || !c->bowdb->n_kf) return set_error(c, PSLAM_E_INVALID, "no key-frame database (pslam_bow_database_set)");
+    if (n_q < 0 || (n_q && (!q_word || !q_val))) return set_error(c, PSLAM_E_INVALID, "bad query BowVector");
+    for (int i = 1; i < n_q; ++i) if (q_word[i] <= q_word[i - 1]) return set_error(c, PSLAM_E_INVALID, "query words must be strictly ascending (std::map order)");
+    BowDbBuffers& B = *c->bowdb;
+    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    cudaStream_t st = c->stream;
+    if (n_q > B.q_cap) {
+        cudaFree(B.d_qword); cudaFree(B.d_qval); B.d_qword = nullptr; B.d_qval = nullptr; B.q_cap = 0;
+        const int cap = std::max(n_q * 3 / 2, 1024);
+        PSLAM_CUDA(c, cudaMalloc((void**)&B.d_qword, (size_t)cap * 4));
+        PSLAM_CUDA(c, cudaMalloc((void**)&B.d_qval, (size_t)cap * 8));
+        B.q_cap = cap;
+    }
+    if (n_q) {
+        PSLAM_CUDA(c, cudaMemcpyAsync(B.d_qword, q_word, (size_t)n_q * 4, cudaMemcpyHostToDevice, st));
+        PSLAM_CUDA(c, cudaMemcpyAsync(B.d_qval, q_val, (size_t)n_q * 8, cudaMemcpyHostToDevice, st));
+    }
+    PSLAM_LAUNCH(c, "bow_db_scores", k_bow_db_scores<<<(B.n_kf + 3) / 4, 128, 0, st>>>(B.n_kf, B.d_off, B.d_word, B.d_val, n_q, B.d_qword, B.d_qval, B.d_common, B.d_first,
+                                                                                      B.d_score));
+    PSLAM_CUDA(c, cudaGetLastError());
+    PSLAM_CUDA(c, cudaMemcpyAsync(B.h_common.data(), B.d_common, (size_t)B.n_kf * 4, cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(B.h_first.data(), B.d_first, (size_t)B.n_kf * 4, cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaMemcpyAsync(B.h_score.data(), B.d_score, (size_t)B.n_kf * 4, cudaMemcpyDeviceToHost, st));
+    PSLAM_CUDA(c, cudaStreamSynchronize(st));
+    return PSLAM_OK;
+}
+
+// lKFsSharingWords: key frames in the order the scan of the inverted file meets them - query words ascending, each word's list in database order
+void sharing_order(const BowDbBuffers& B, const uint8_t* connected, std::vector<int>& listed) {
+    listed.clear();
+    for (int k = 0; k < B.n_kf; ++k)
+        if (B.h_first[k] >= 0 && !(connected && connected[k])) listed.push_back(k);
+    std::stable_sort(listed.begin(), listed.end(), [&](int a, int b) { return B.h_first[a] < B.h_first[b]; });
+}
+
+int covis_check(pslam_ctx* c, const BowDbBuffers& B, const int32_t* covis, int covis_stride) {
+    if (covis_stride < 0 || (covis_stride && !covis)) return set_error(c, PSLAM_E_INVALID, "bad covisibility table");
+    for (size_t i = 0; i < (size_t)B.n_kf * covis_stride; ++i)
+        if (covis[i] >= B.n_kf) return set_error(c, PSLAM_E_INVALID, "covisibility index out of range");
+    return PSLAM_OK;
+}
+
+// the tail both detectors share (src/KeyFrameDatabase.cc:176-196 / :284-304): keep accumulated scores above 0.75 x best, first occurrence of each key frame
+int retain(const std::vector<std::pair<float, int>>& acc, float best_acc, int n_kf, int32_t* candidates) {
+    const float min_retain = 0.75f * best_acc;
+    std::vector<char> added(n_kf, 0);
+    int n = 0;
+    for (const auto& a : acc)
+        if (a.first > min_retain && !added[a.second]) { candidates[n++] = a.second; added[a.second] = 1; }
+    return n;
+}
+
+}  // namespace
 }  // namespace pslam
 
 using namespace pslam;
@@ -106,44 +272,139 @@ extern "C" int pslam_search_by_bow(pslam_ctx* c, int nkf, const uint8_t* kf_desc
                                    const float* f_angle, int f_nodes, const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat,
                                    float nnratio, int check_orientation, int32_t* match) {
     if (!c) return PSLAM_E_INVALID;
-    if (nkf < 0 || nf < 0 || kf_nodes < 0 || f_nodes < 0 || (nf && !match) || (nkf && (!kf_desc || !kf_angle || !kf_has_mp)) || (nf && (!f_desc || !f_angle)) ||
-        (kf_nodes && (!kf_node_id || !kf_node_off || !kf_node_feat)) || (f_nodes && (!f_node_id || !f_node_off || !f_node_feat)))
-        return set_error(c, PSLAM_E_INVALID, "bad SearchByBoW arrays");
-    for (int i = 0; i < nf; ++i) match[i] = -1;
-    // merge-join of the two (ascending) node-id lists, like the reference's two map iterators
-    std::vector<int2> pairs;
-    for (int a = 0, b = 0; a < kf_nodes && b < f_nodes;) {
-        if (kf_node_id[a] == f_node_id[b]) { pairs.push_back(make_int2(a, b)); ++a; ++b; }
-        else if (kf_node_id[a] < f_node_id[b]) a = (int)(std::lower_bound(kf_node_id, kf_node_id + kf_nodes, f_node_id[b]) - kf_node_id);
-        else b = (int)(std::lower_bound(f_node_id, f_node_id + f_nodes, kf_node_id[a]) - f_node_id);
-    }
-    if (pairs.empty() || nf == 0 || nkf == 0) return 0;
-    const int nkfeat = kf_node_off[kf_nodes], nffeat = f_node_off[f_nodes];
-    for (int i = 0; i < nkfeat; ++i) if (kf_node_feat[i] < 0 || kf_node_feat[i] >= nkf) return set_error(c, PSLAM_E_INVALID, "key-frame feature index out of range");
-    for (int i = 0; i < nffeat; ++i) if (f_node_feat[i] < 0 || f_node_feat[i] >= nf) return set_error(c, PSLAM_E_INVALID, "frame feature index out of range");
-    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
-    cudaStream_t st = c->stream;
-    const size_t sz[] = {pairs.size() * 8, (size_t)nkf * 32, (size_t)nkf * 4, (size_t)nkf, (size_t)(kf_nodes + 1) * 4, (size_t)nkfeat * 4, (size_t)nf * 32,
-                         (size_t)nf * 4, (size_t)(f_nodes + 1) * 4, (size_t)nffeat * 4, (size_t)nf * 4, (size_t)nf, 31 * 4};
-    const void* src[] = {pairs.data(), kf_desc, kf_angle, kf_has_mp, kf_node_off, kf_node_feat, f_desc, f_angle, f_node_off, f_node_feat, match, nullptr, nullptr};
-    size_t off[14]; off[0] = 0;
-    for (int i = 0; i < 13; ++i) off[i + 1] = (off[i] + sz[i] + 15) & ~(size_t)15;
-    uint8_t* d = nullptr;
-    PSLAM_CUDA(c, cudaMalloc((void**)&d, off[13]));
-    cudaError_t e = cudaMemsetAsync(d + off[12], 0, 31 * 4, st);
-    for (int i = 0; i < 11 && e == cudaSuccess; ++i) if (sz[i]) e = cudaMemcpyAsync(d + off[i], src[i], sz[i], cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) { cudaFree(d); return check_cuda(c, e, "SearchByBoW upload"); }
-    int32_t* d_hist = (int32_t*)(d + off[12]);
-    PSLAM_LAUNCH(c, "bow_nodes", k_bow_nodes<<<((int)pairs.size() + 3) / 4, 128, 0, st>>>((int)pairs.size(), (const int2*)(d + off[0]), d + off[1], (const float*)(d + off[2]),
-                 d + off[3], (const int32_t*)(d + off[4]), (const int32_t*)(d + off[5]), d + off[6], (const float*)(d + off[7]), (const int32_t*)(d + off[8]),
-                 (const int32_t*)(d + off[9]), nnratio, check_orientation, (int32_t*)(d + off[10]), (int8_t*)(d + off[11]), d_hist, d_hist + 30));
-    if (check_orientation)
-        PSLAM_LAUNCH(c, "bow_orientation", k_bow_orientation<<<1, 256, 0, st>>>(nf, (int32_t*)(d + off[10]), (const int8_t*)(d + off[11]), d_hist, d_hist + 30));
-    int32_t n = 0;
-    e = cudaMemcpyAsync(match, d + off[10], (size_t)nf * 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&n, d_hist + 30, 4, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d);
-    if (e != cudaSuccess) return check_cuda(c, e, "SearchByBoW");
+    const BowSideArgs A{nkf, kf_desc, kf_angle, kf_has_mp, kf_nodes, kf_node_id, kf_node_off, kf_node_feat};
+    const BowSideArgs B{nf, f_desc, f_angle, nullptr, f_nodes, f_node_id, f_node_off, f_node_feat};
+    return bow_search_impl(c, A, B, 50, nnratio, check_orientation, match);          // bestDist1 <= TH_LOW (src/ORBmatcher.cc:236)
+}
+
+extern "C" int pslam_search_by_bow_kf(pslam_ctx* c, int n1, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int nodes1, const int32_t* node_id1,
+                                      const int32_t* node_off1, const int32_t* node_feat1, int n2, const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2,
+                                      int nodes2, const int32_t* node_id2, const int32_t* node_off2, const int32_t* node_feat2, float nnratio, int check_orientation,
+                                      int32_t* match12) {
+    if (!c) return PSLAM_E_INVALID;
+    if (n1 < 0 || n2 < 0 || (n1 && !match12) || (n2 && !has_mp2)) return set_error(c, PSLAM_E_INVALID, "bad SearchByBoW(KeyFrame, KeyFrame) arrays");
+    const BowSideArgs A{n1, desc1, angle1, has_mp1, nodes1, node_id1, node_off1, node_feat1};
+    const BowSideArgs B{n2, desc2, angle2, has_mp2, nodes2, node_id2, node_off2, node_feat2};
+    std::vector<int32_t> match2((size_t)std::max(n2, 1), -1);
+    const int n = bow_search_impl(c, A, B, 49, nnratio, check_orientation, match2.data());     // bestDist1 < TH_LOW (src/ORBmatcher.cc:598)
+    for (int i = 0; i < n1; ++i) match12[i] = -1;
+    if (n < 0) return n;
+    for (int j = 0; j < n2; ++j) if (match2[j] >= 0) match12[match2[j]] = j;                   // vpMatches12[idx1] = vpMapPoints2[bestIdx2]
     return n;
+}
+
+extern "C" int pslam_bow_database_set(pslam_ctx* c, int n_kf, const int32_t* kf_off, const int32_t* kf_word, const double* kf_val) {
+    if (!c) return PSLAM_E_INVALID;
+    if (n_kf < 0 || (n_kf && (!kf_off || kf_off[0] != 0))) return set_error(c, PSLAM_E_INVALID, "bad key-frame database offsets");
+    for (int k = 0; k < n_kf; ++k) {
+        if (kf_off[k + 1] < kf_off[k]) return set_error(c, PSLAM_E_INVALID, "key-frame database offsets must not decrease");
+        for (int i = kf_off[k] + 1; i < kf_off[k + 1]; ++i)
+            if (kf_word[i] <= kf_word[i - 1]) return set_error(c, PSLAM_E_INVALID, "BowVector words must be strictly ascending (std::map order)");
+    }
+    bowdb_free(c);
+    if (n_kf == 0) return PSLAM_OK;
+    const int total = kf_off[n_kf];
+    if (total && (!kf_word || !kf_val)) return set_error(c, PSLAM_E_INVALID, "bad key-frame database arrays");
+    PSLAM_CUDA(c, cudaSetDevice(c->cfg.device));
+    c->bowdb = new BowDbBuffers();
+    BowDbBuffers& B = *c->bowdb;
+    B.n_kf = n_kf; B.total = total;
+    cudaError_t e = cudaMalloc((void**)&B.d_off, (size_t)(n_kf + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B.d_word, (size_t)std::max(total, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B.d_val, (size_t)std::max(total, 1) * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B.d_common, (size_t)n_kf * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B.d_first, (size_t)n_kf * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B.d_score, (size_t)n_kf * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(B.d_off, kf_off, (size_t)(n_kf + 1) * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(B.d_word, kf_word, (size_t)total * 4, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(B.d_val, kf_val, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { bowdb_free(c); return check_cuda(c, e, "key-frame database upload"); }
+    B.h_common.resize(n_kf); B.h_first.resize(n_kf); B.h_score.resize(n_kf);
+    return PSLAM_OK;
+}
+
+extern "C" int pslam_detect_loop_candidates(pslam_ctx* c, int n_q, const int32_t* q_word, const double* q_val, const int32_t* covis, int covis_stride,
+                                            const uint8_t* connected, float min_score, int32_t* candidates, int32_t* common_words, float* score) {
+    if (!c) return PSLAM_E_INVALID;
+    if (!candidates) return set_error(c, PSLAM_E_INVALID, "candidates is NULL");
+    int rc = bowdb_score(c, n_q, q_word, q_val);
+    if (rc != PSLAM_OK) return rc;
+    const BowDbBuffers& B = *c->bowdb;
+    if ((rc = covis_check(c, B, covis, covis_stride)) != PSLAM_OK) return rc;
+    std::vector<int> listed;
+    sharing_order(B, connected, listed);
+    for (int k = 0; k < B.n_kf; ++k) {
+        // a connected key frame's counter restarts at every shared word (its mnLoopQuery is never set, src/KeyFrameDatabase.cc:93-103)
+        if (common_words) common_words[k] = (connected && connected[k] && B.h_common[k] > 0) ? 1 : B.h_common[k];
+    }
+    if (listed.empty()) return 0;
+    int max_common = 0;
+    for (int k : listed) max_common = std::max(max_common, B.h_common[k]);
+    const int min_common = (int)(max_common * 0.8f);
+    std::vector<char> scored(B.n_kf, 0);                       // mnLoopQuery == query && mnLoopWords > minCommonWords
+    std::vector<std::pair<float, int>> above;
+    for (int k : listed) {
+        if (B.h_common[k] <= min_common) continue;
+        scored[k] = 1;
+        if (score) score[k] = B.h_score[k];
+        if (B.h_score[k] >= min_score) above.emplace_back(B.h_score[k], k);
+    }
+    if (above.empty()) return 0;
+    std::vector<std::pair<float, int>> acc;
+    float best_acc = min_score;
+    for (const auto& sm : above) {
+        float best = sm.first, sum = sm.first;
+        int best_kf = sm.second;
+        for (int j = 0; j < covis_stride; ++j) {
+            const int k2 = covis[(size_t)sm.second * covis_stride + j];
+            if (k2 < 0) break;
+            if (!scored[k2]) continue;
+            sum += B.h_score[k2];
+            if (B.h_score[k2] > best) { best_kf = k2; best = B.h_score[k2]; }
+        }
+        acc.emplace_back(sum, best_kf);
+        if (sum > best_acc) best_acc = sum;
+    }
+    return retain(acc, best_acc, B.n_kf, candidates);
+}
+
+extern "C" int pslam_detect_relocalization_candidates(pslam_ctx* c, int n_q, const int32_t* q_word, const double* q_val, const int32_t* covis, int covis_stride,
+                                                      float* reloc_score_io, int32_t* candidates, int32_t* common_words) {
+    if (!c) return PSLAM_E_INVALID;
+    if (!candidates || !reloc_score_io) return set_error(c, PSLAM_E_INVALID, "candidates / reloc_score_io is NULL");
+    int rc = bowdb_score(c, n_q, q_word, q_val);
+    if (rc != PSLAM_OK) return rc;
+    const BowDbBuffers& B = *c->bowdb;
+    if ((rc = covis_check(c, B, covis, covis_stride)) != PSLAM_OK) return rc;
+    std::vector<int> listed;
+    sharing_order(B, nullptr, listed);
+    if (common_words) for (int k = 0; k < B.n_kf; ++k) common_words[k] = B.h_common[k];
+    if (listed.empty()) return 0;
+    int max_common = 0;
+    for (int k : listed) max_common = std::max(max_common, B.h_common[k]);
+    const int min_common = (int)(max_common * 0.8f);
+    std::vector<std::pair<float, int>> evaluated;
+    for (int k : listed) {
+        if (B.h_common[k] <= min_common) continue;
+        reloc_score_io[k] = B.h_score[k];
+        evaluated.emplace_back(B.h_score[k], k);
+    }
+    if (evaluated.empty()) return 0;
+    std::vector<std::pair<float, int>> acc;
+    float best_acc = 0;
+    for (const auto& sm : evaluated) {
+        float best = sm.first, sum = sm.first;
+        int best_kf = sm.second;
+        for (int j = 0; j < covis_stride; ++j) {
+            const int k2 = covis[(size_t)sm.second * covis_stride + j];
+            if (k2 < 0) break;
+            if (B.h_first[k2] < 0) continue;                  // mnRelocQuery != F->mnId: shares no word with the frame
+            sum += reloc_score_io[k2];                        // also a score left by an earlier query (the reference reads mRelocScore unconditionally)
+            if (reloc_score_io[k2] > best) { best_kf = k2; best = reloc_score_io[k2]; }
+        }
+        acc.emplace_back(sum, best_kf);
+        if (sum > best_acc) best_acc = sum;
+    }
+    return retain(acc, best_acc, B.n_kf, candidates);
 }

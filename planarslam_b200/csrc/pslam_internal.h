@@ -83,6 +83,7 @@ struct LsdBuffers;
 struct TrackBuffers;
 struct ExchangeBuffers;
 struct PlanePostBuffers;
+struct BowDbBuffers;
 struct FrameBuffers;
 
 }  // namespace pslam
@@ -145,6 +146,7 @@ struct pslam_ctx {
     pslam::TrackBuffers* track = nullptr;        // device-resident tracking chain (track_chain.cu)
     pslam::PlanePostBuffers* planepost = nullptr; // Frame::ComputePlanes post-processing + surface normals (planepost_kernels.cu)
     pslam::FrameBuffers* frame = nullptr;        // staging of pslam_frame_construct_batch (frame_pipeline.cu)
+    pslam::BowDbBuffers* bowdb = nullptr;        // key-frame database BowVectors for loop / relocalisation candidates (bow_kernels.cu)
     pslam::ExchangeBuffers* exchange = nullptr;  // key-frame descriptor exchange over peer memory (exchange_kernels.cu)
     // pinned host staging
     uint8_t* h_gray = nullptr; pslam_keypoint* h_kps = nullptr; uint8_t* h_desc = nullptr; int32_t* h_n = nullptr;
@@ -168,6 +170,7 @@ void lsd_free(pslam_ctx* c);
 void track_free(pslam_ctx* c);
 void exchange_free(pslam_ctx* c);
 void planepost_free(pslam_ctx* c);
+void bowdb_free(pslam_ctx* c);
 void frame_free(pslam_ctx* c);
 int lsd_status_fetch_async(pslam_ctx* c, int nframes, int32_t* h_pinned);
 // PEAC pipeline (peac_pipeline.cu)

@@ -131,3 +131,52 @@ def make_line_frustum(seed: int, n: int = 400):
     max_d = (dist * rng.uniform(0.7, 2.5, n)).astype(np.float32)
     min_d = (max_d / np.float32(1.2 ** 7)).astype(np.float32)
     return frame, pos, nrm, max_d, min_d
+
+
+def make_bow_database(seed: int, n_kf: int = 400, n_words: int = 5000, words_per_kf: int = 300, n_similar: int = 40, covis: int = 10):
+    """A key-frame database for KeyFrameDatabase::DetectLoopCandidates / DetectRelocalizationCandidates: a query BowVector, `n_kf` key-frame BowVectors in the
+    order KeyFrameDatabase::add saw them (CSR: off, word ascending, val L1-normalised like DBoW2's TF_IDF + L1_NORM transform), of which `n_similar` share a
+    varying fraction of the query's words (a revisited place: consecutive runs, so that covisibility groups accumulate), the covisibility table
+    GetBestCovisibilityKeyFrames(10) as database indices (-1 ends a row) and the flags of the key frames connected to the query (never candidates)."""
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 7919 + 5))
+    idf = rng.uniform(0.5, 8.0, n_words)
+
+    def bow(words, counts):
+        words = np.asarray(words)
+        order = np.argsort(words)
+        v = counts[order] * idf[words[order]]
+        return words[order].astype(np.int32), (v / v.sum()).astype(np.float64)
+    qw = rng.choice(n_words, words_per_kf, replace=False)
+    qc = rng.integers(1, 4, words_per_kf).astype(np.float64)
+    q_word, q_val = bow(qw, qc)
+    similar_start = int(rng.integers(0, max(n_kf - n_similar, 1)))
+    off, words, vals = [0], [], []
+    for k in range(n_kf):
+        m = int(rng.integers(words_per_kf // 2, words_per_kf * 3 // 2))
+        if similar_start <= k < similar_start + n_similar:
+            frac = 0.25 + 0.6 * np.exp(-0.5 * ((k - similar_start - n_similar / 2) / (n_similar / 5)) ** 2) * rng.uniform(0.7, 1.0)
+            keep = qw[rng.random(words_per_kf) < frac]
+            rest = np.setdiff1d(rng.choice(n_words, m, replace=False), qw)[: max(m - len(keep), 0)]
+            w = np.concatenate([keep, rest])
+        else:
+            w = rng.choice(n_words, m, replace=False)
+        wi, vi = bow(w, rng.integers(1, 4, len(w)).astype(np.float64))
+        words.append(wi); vals.append(vi); off.append(off[-1] + len(wi))
+    table = np.full((n_kf, covis), -1, np.int32)
+    for k in range(n_kf):            # temporal neighbours, nearest first, a few rows shorter than 10 and a few empty
+        nb = [j for d in range(1, covis) for j in (k - d, k + d) if 0 <= j < n_kf][: int(rng.integers(0, covis + 1))]
+        table[k, :len(nb)] = nb
+    connected = np.zeros(n_kf, np.uint8)
+    connected[rng.integers(0, n_kf, 5)] = 1
+    if n_similar:
+        connected[similar_start + int(rng.integers(0, n_similar))] = 1        # one of the similar key frames is a covisible neighbour of the query
+    return dict(q_word=q_word, q_val=q_val, off=np.asarray(off, np.int32), word=np.concatenate(words).astype(np.int32), val=np.concatenate(vals),
+                covis=table, connected=connected)
+
+
+def make_bow_kf_pair(seed: int, **kw):
+    """Two key frames for ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...): make_bow_pair plus map-point flags on the second side."""
+    kf1, kf2 = make_bow_pair(seed, **kw)
+    rng = np.random.Generator(np.random.Philox(key=int(seed) * 613 + 1))
+    kf2["has_mp"] = (rng.random(len(kf2["angle"])) < 0.85).astype(np.uint8)
+    return kf1, kf2

@@ -518,3 +518,51 @@ def surface_normals(depth: np.ndarray, K=(535.4, 539.2, 320.1, 247.6), scale=np.
     out = np.zeros((cap, 8), np.float32)
     n = L.orc_surface_normals(depth.ctypes.data, w, h, K[0], K[1], K[2], K[3], float(np.float32(scale)), out.ctypes.data, cap)
     return out[:n].copy()
+
+
+def _db_args(db):
+    d = {k: np.ascontiguousarray(v) for k, v in db.items()}
+    n_kf = len(d["off"]) - 1
+    covis = d.get("covis")
+    return d, n_kf, (covis.ctypes.data if covis is not None else None), (covis.shape[1] if covis is not None else 0)
+
+
+def detect_loop_candidates(db: dict, min_score: float, sentinel: float = -1.0):
+    """Oracle KeyFrameDatabase::DetectLoopCandidates.  db: planarslam_b200.synth_lines.make_bow_database layout.  Returns (candidates, common_words, score);
+    score[k] == sentinel where the reference does not evaluate it."""
+    L = lib()
+    L.orc_detect_loop_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 3
+    d, n_kf, covis, stride = _db_args(db)
+    cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.full(max(n_kf, 1), sentinel, np.float32)
+    n = L.orc_detect_loop_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+                                     d["val"].ctypes.data, covis, stride, d["connected"].ctypes.data if "connected" in d else None, min_score,
+                                     cand.ctypes.data, words.ctypes.data, score.ctypes.data)
+    return cand[:n].copy(), words[:n_kf], score[:n_kf]
+
+
+def detect_relocalization_candidates(db: dict, reloc_score: np.ndarray):
+    """Oracle KeyFrameDatabase::DetectRelocalizationCandidates.  reloc_score = KeyFrame::mRelocScore before the call.  Returns (candidates, common_words, mRelocScore after)."""
+    L = lib()
+    L.orc_detect_relocalization_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
+    d, n_kf, covis, stride = _db_args(db)
+    cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.ascontiguousarray(reloc_score, np.float32).copy()
+    n = L.orc_detect_relocalization_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+                                               d["val"].ctypes.data, covis, stride, score.ctypes.data, cand.ctypes.data, words.ctypes.data)
+    return cand[:n].copy(), words[:n_kf], score
+
+
+def _bow_kf_call(fn, kf1, kf2, nnratio, check_orientation):
+    fn.argtypes = ([C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] * 2) + [C.c_float, C.c_int, C.c_void_p]
+    a = {k: np.ascontiguousarray(v) for k, v in kf1.items()}
+    b = {k: np.ascontiguousarray(v) for k, v in kf2.items()}
+    n1 = len(a["angle"])
+    match = np.full(max(n1, 1), -1, np.int32)
+    side = lambda s: (len(s["angle"]), s["desc"].ctypes.data, s["angle"].ctypes.data, s["has_mp"].ctypes.data, len(s["node_id"]), s["node_id"].ctypes.data,
+                      s["node_off"].ctypes.data, s["node_feat"].ctypes.data)
+    n = fn(*side(a), *side(b), nnratio, 1 if check_orientation else 0, match.ctypes.data)
+    return n, match[:n1]
+
+
+def search_by_bow_kf(kf1: dict, kf2: dict, nnratio: float = 0.75, check_orientation: bool = True):
+    """Oracle ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&).  Returns (nmatches, match12 [n1]: feature of key frame 2 or -1)."""
+    return _bow_kf_call(lib().orc_search_by_bow_kf, kf1, kf2, nnratio, check_orientation)

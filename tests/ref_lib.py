@@ -450,3 +450,33 @@ def ref_track_manhattan_frame(R_last, normals, dirs):
     rc = L.ref_track_manhattan_frame(R.ctypes.data, nr.ctypes.data, len(nr), dr.ctypes.data, len(dr), out.ctypes.data)
     assert rc == 33, rc
     return out
+
+
+def ref_detect_loop_candidates(db: dict, min_score: float, sentinel: float = -1.0):
+    """KeyFrameDatabase::DetectLoopCandidates by the reference's own code (src/KeyFrameDatabase.cc + DBoW2 L1 scoring).  Same layout as oracle_lib.detect_loop_candidates."""
+    L = match_lib()
+    L.ref_detect_loop_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 3
+    import oracle_lib
+    d, n_kf, covis, stride = oracle_lib._db_args(db)
+    cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.full(max(n_kf, 1), sentinel, np.float32)
+    n = L.ref_detect_loop_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+                                     d["val"].ctypes.data, covis, stride, d["connected"].ctypes.data if "connected" in d else None, min_score,
+                                     cand.ctypes.data, words.ctypes.data, score.ctypes.data)
+    return cand[:n].copy(), words[:n_kf], score[:n_kf]
+
+
+def ref_detect_relocalization_candidates(db: dict, reloc_score: np.ndarray):
+    L = match_lib()
+    L.ref_detect_relocalization_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
+    import oracle_lib
+    d, n_kf, covis, stride = oracle_lib._db_args(db)
+    cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.ascontiguousarray(reloc_score, np.float32).copy()
+    n = L.ref_detect_relocalization_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+                                               d["val"].ctypes.data, covis, stride, score.ctypes.data, cand.ctypes.data, words.ctypes.data)
+    return cand[:n].copy(), words[:n_kf], score
+
+
+def ref_search_by_bow_kf(kf1: dict, kf2: dict, nnratio: float = 0.75, check_orientation: bool = True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) by the reference's own code."""
+    import oracle_lib
+    return oracle_lib._bow_kf_call(match_lib().ref_search_by_bow_kf, kf1, kf2, nnratio, check_orientation)

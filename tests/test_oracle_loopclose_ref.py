@@ -1,0 +1,57 @@
+"""CPU: the loop-closure / relocalisation candidate oracle (oracle/loopclose.cc) pinned against THE REFERENCE'S OWN code: src/KeyFrameDatabase.cc
+(DetectLoopCandidates :76-197, DetectRelocalizationCandidates :199-305), DBoW2's L1 scoring (Thirdparty/DBoW2/DBoW2/ScoringObject.cpp) and
+src/ORBmatcher.cc (SearchByBoW(KeyFrame*, KeyFrame*, ...) :526-659), compiled unmodified into oracle/_ref/libmatch_ref.so; the driver only builds KeyFrame
+objects (BowVectors, covisibility lists, map points) from the plain arrays."""
+import numpy as np
+import pytest
+
+import oracle_lib
+import ref_lib
+from planarslam_b200 import synth_lines
+
+pytestmark = pytest.mark.skipif(ref_lib.match_lib() is None, reason="oracle/_ref/libmatch_ref.so not built and no /root/reference to build it from")
+
+CASES = [dict(seed=0), dict(seed=1, n_kf=150, n_similar=25), dict(seed=2, n_kf=600, n_words=3000, words_per_kf=500, n_similar=80),
+         dict(seed=3, n_kf=60, n_similar=0), dict(seed=4, n_kf=40, n_words=400, words_per_kf=120, n_similar=10), dict(seed=5, n_kf=1, n_similar=1),
+         dict(seed=6, n_kf=300, n_words=100000, words_per_kf=900, n_similar=30)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"seed{c['seed']}")
+def test_detect_loop_candidates_identical_to_compiled_reference(case):
+    db = synth_lines.make_bow_database(**case)
+    some = 0
+    for min_score in (0.0, 0.01, 0.03, 0.08):
+        c, w, s = oracle_lib.detect_loop_candidates(db, min_score)
+        rc, rw, rs = ref_lib.ref_detect_loop_candidates(db, min_score)
+        assert np.array_equal(c, rc), (min_score, c, rc)
+        assert np.array_equal(w, rw)
+        assert np.array_equal(s, rs)            # float scores bit-identical (and evaluated for the same key frames: the sentinel elsewhere)
+        some += len(c)
+    if case.get("n_similar", 40) >= 10:
+        assert some > 0
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"seed{c['seed']}")
+def test_detect_relocalization_candidates_identical_to_compiled_reference(case):
+    db = synth_lines.make_bow_database(**case)
+    n_kf = len(db["off"]) - 1
+    rng = np.random.default_rng(case["seed"])
+    for stale in (np.zeros(n_kf, np.float32), rng.uniform(0, 0.05, n_kf).astype(np.float32)):     # mRelocScore left by earlier queries
+        c, w, s = oracle_lib.detect_relocalization_candidates(db, stale)
+        rc, rw, rs = ref_lib.ref_detect_relocalization_candidates(db, stale)
+        assert np.array_equal(c, rc), (c, rc)
+        assert np.array_equal(w, rw)
+        assert np.array_equal(s, rs)
+
+
+def test_search_by_bow_kf_identical_to_compiled_reference():
+    total = 0
+    for seed in range(5):
+        kf1, kf2 = synth_lines.make_bow_kf_pair(seed, **(dict(n_kf=400, n_f=380, n_nodes=90) if seed < 3 else {}))
+        for ratio, ori in ((0.75, True), (0.75, False), (0.9, True), (0.6, True)):
+            n, m = oracle_lib.search_by_bow_kf(kf1, kf2, ratio, ori)
+            rn, rm = ref_lib.ref_search_by_bow_kf(kf1, kf2, ratio, ori)
+            assert n == rn and np.array_equal(m, rm)
+            assert n == int((m >= 0).sum())
+            total += n
+    assert total > 1000
