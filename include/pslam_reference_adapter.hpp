@@ -15,7 +15,12 @@
 //   static int  Optimizer::TranslationOptimization(Frame*)                            include/Optimizer.h:40   src/Optimizer.cc:2995-3737
 //   int ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float th)    include/ORBmatcher.h:43  src/ORBmatcher.cc:46-130
 //   int ORBmatcher::SearchByProjection(Frame&, const Frame&, float th, bool bMono)    include/ORBmatcher.h:47  src/ORBmatcher.cc:1396-1535
+//   int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)                include/ORBmatcher.h:53  src/ORBmatcher.cc:160-292
+//   int ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)             include/ORBmatcher.h:56  src/ORBmatcher.cc:526-659
+//   int LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, float th)     include/LSDmatcher.h:24  src/LSDmatcher.cpp:141-211
 //   int PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)       include/PlaneMatcher.h:18 src/PlaneMatcher.cpp:10-67
+//   KeyFrameDatabase::add / erase / clear / DetectLoopCandidates(KeyFrame*, float) / DetectRelocalizationCandidates(Frame*)
+//                                                                                     include/KeyFrameDatabase.h:43-75  src/KeyFrameDatabase.cc:38-305
 //   void ORBextractor::operator()(cv::InputArray, cv::InputArray, vector<cv::KeyPoint>&, cv::OutputArray)   include/ORBextractor.h:59-61
 //
 // Two reference members read here are protected in the reference (MapPoint::mfMaxDistance / mfMinDistance: the getters return them scaled by 1.2 / 0.8
@@ -24,8 +29,10 @@
 // (oracle/ref/adapter_driver.cc) and compares every entry point with the reference function on the same objects (tests/test_reference_adapter_gpu.py).
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
+#include <set>
 #include <stdexcept>
 #include <unordered_map>
 #include <vector>
@@ -36,6 +43,7 @@ namespace pslam_adapter {
 namespace ref {
 
 using Planar_SLAM::Frame;
+using Planar_SLAM::KeyFrame;
 using Planar_SLAM::MapLine;
 using Planar_SLAM::MapPlane;
 using Planar_SLAM::MapPoint;
@@ -239,8 +247,188 @@ public:
         return n;
     }
 
+    // Search matches between MapPoints in a KeyFrame and ORB in a Frame, brute force constrained to the same vocabulary node (relocalisation, tracking
+    // with the reference key frame)
+    int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+        const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+        vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+        BowSide A(pKF->mDescriptors, pKF->mvKeysUn, pKF->mFeatVec, &vpMapPointsKF), B(F.mDescriptors, F.mvKeys, F.mFeatVec, nullptr);
+        std::vector<int32_t> match((size_t)std::max(F.N, 1), -1);
+        pslam_ctx* c = context();
+        const int n = pslam_search_by_bow(c, A.n, A.desc.data(), A.angle.data(), A.has_mp.data(), (int)A.node_id.size(), A.node_id.data(), A.node_off.data(),
+                                          A.node_feat.data(), B.n, B.desc.data(), B.angle.data(), (int)B.node_id.size(), B.node_id.data(), B.node_off.data(),
+                                          B.node_feat.data(), mfNNratio, mbCheckOrientation ? 1 : 0, match.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int j = 0; j < F.N; ++j) if (match[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[match[j]];
+        return n;
+    }
+
+    // Matching between two key frames for loop detection (LoopClosing::ComputeSim3): the consumer of the key-frame exchange
+    int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+        const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+        vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+        BowSide A(pKF1->mDescriptors, pKF1->mvKeysUn, pKF1->mFeatVec, &vpMapPoints1), B(pKF2->mDescriptors, pKF2->mvKeysUn, pKF2->mFeatVec, &vpMapPoints2);
+        std::vector<int32_t> match12((size_t)std::max(A.n, 1), -1);
+        pslam_ctx* c = context();
+        const int n = pslam_search_by_bow_kf(c, A.n, A.desc.data(), A.angle.data(), A.has_mp.data(), (int)A.node_id.size(), A.node_id.data(), A.node_off.data(),
+                                             A.node_feat.data(), B.n, B.desc.data(), B.angle.data(), B.has_mp.data(), (int)B.node_id.size(), B.node_id.data(),
+                                             B.node_off.data(), B.node_feat.data(), mfNNratio, mbCheckOrientation ? 1 : 0, match12.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int i = 0; i < A.n; ++i) if (match12[i] >= 0) vpMatches12[i] = vpMapPoints2[match12[i]];
+        return n;
+    }
+
+private:
+    struct BowSide {          // descriptors, key-point angles, map-point flags and the DBoW2 FeatureVector (std::map<NodeId, vector<unsigned>>) as CSR
+        int n; std::vector<uint8_t> desc, has_mp; std::vector<float> angle; std::vector<int32_t> node_id, node_off, node_feat;
+        BowSide(const cv::Mat& D, const std::vector<cv::KeyPoint>& keys, const DBoW2::FeatureVector& fv, const std::vector<MapPoint*>* mps) : n((int)keys.size()) {
+            desc.resize((size_t)std::max(n, 1) * 32); has_mp.assign((size_t)std::max(n, 1), 1); angle.resize((size_t)std::max(n, 1));
+            for (int i = 0; i < n; ++i) {
+                std::memcpy(&desc[32 * (size_t)i], D.ptr(i), 32);
+                angle[i] = keys[i].angle;
+                if (mps) { MapPoint* p = (*mps)[i]; has_mp[i] = (p && !p->isBad()) ? 1 : 0; }
+            }
+            node_off.push_back(0);
+            for (const auto& kv : fv) {
+                node_id.push_back((int32_t)kv.first);
+                for (unsigned f : kv.second) node_feat.push_back((int32_t)f);
+                node_off.push_back((int32_t)node_feat.size());
+            }
+        }
+    };
+    float mfNNratio; bool mbCheckOrientation;
+};
+
+class LSDmatcher {
+public:
+    LSDmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+    // Search matches between Frame key lines and projected MapLines (the caller ran Frame::isInFrustum(MapLine*) on them: mbTrackInView, mTrackProj*)
+    int SearchByProjection(Frame& F, const std::vector<MapLine*>& vpMapLines, const float th = 3) {
+        const int nf = F.NL, nm = (int)vpMapLines.size();
+        std::vector<float> pt((size_t)std::max(nf, 1) * 2), angle((size_t)std::max(nf, 1)), view_cos((size_t)std::max(nm, 1)), proj((size_t)std::max(nm, 1) * 4);
+        std::vector<int32_t> octave((size_t)std::max(nf, 1)), level((size_t)std::max(nm, 1)), assigned((size_t)std::max(nf, 1), -1);
+        std::vector<uint8_t> desc((size_t)std::max(nf, 1) * 32), has_obs((size_t)std::max(nf, 1)), skip((size_t)std::max(nm, 1), 1), mdesc((size_t)std::max(nm, 1) * 32),
+            m_has_obs((size_t)std::max(nm, 1));
+        for (int i = 0; i < nf; ++i) {
+            const auto& k = F.mvKeylinesUn[i];
+            pt[2 * i] = k.pt.x; pt[2 * i + 1] = k.pt.y; angle[i] = k.angle; octave[i] = k.octave;
+            std::memcpy(&desc[32 * (size_t)i], F.mLdesc.ptr(i), 32);
+            has_obs[i] = (F.mvpMapLines[i] && F.mvpMapLines[i]->Observations() > 0) ? 1 : 0;
+        }
+        for (int j = 0; j < nm; ++j) {
+            MapLine* p = vpMapLines[j];
+            if (!p || p->isBad() || !p->mbTrackInView) continue;
+            skip[j] = 0;
+            level[j] = p->mnTrackScaleLevel; view_cos[j] = p->mTrackViewCos;
+            proj[4 * j] = p->mTrackProjX1; proj[4 * j + 1] = p->mTrackProjY1; proj[4 * j + 2] = p->mTrackProjX2; proj[4 * j + 3] = p->mTrackProjY2;
+            const cv::Mat d = p->GetDescriptor();
+            std::memcpy(&mdesc[32 * (size_t)j], d.ptr(0), 32);
+            m_has_obs[j] = p->Observations() > 0 ? 1 : 0;
+        }
+        pslam_ctx* c = context();
+        const int n = pslam_line_search_by_projection(c, nf, pt.data(), angle.data(), octave.data(), desc.data(), has_obs.data(), F.mvScaleFactors.data(),
+                                                      (int)F.mvScaleFactors.size(), nm, skip.data(), level.data(), view_cos.data(), proj.data(), mdesc.data(),
+                                                      m_has_obs.data(), th, mfNNratio, assigned.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int i = 0; i < nf; ++i) if (assigned[i] >= 0) F.mvpMapLines[i] = vpMapLines[assigned[i]];
+        return n;
+    }
+
 private:
     float mfNNratio; bool mbCheckOrientation;
+};
+
+// The candidate searches of Planar_SLAM::KeyFrameDatabase.  The reference keeps only the inverted file; this class keeps the key frames in insertion order
+// (the order every inverted-file list has) and mirrors their BowVectors into HBM when the set changed since the last query.  mnLoopQuery / mnLoopWords /
+// mLoopScore (mnReloc*) of the key frames are written like the reference writes them, so code that reads them afterwards (LoopClosing) sees the same values.
+class KeyFrameDatabase {
+public:
+    void add(KeyFrame* pKF) { std::unique_lock<std::mutex> lock(mMutex); mvKeyFrames.push_back(pKF); mbDirty = true; }
+    void erase(KeyFrame* pKF) {
+        std::unique_lock<std::mutex> lock(mMutex);
+        auto it = std::find(mvKeyFrames.begin(), mvKeyFrames.end(), pKF);
+        if (it != mvKeyFrames.end()) { mvKeyFrames.erase(it); mbDirty = true; }
+    }
+    void clear() { std::unique_lock<std::mutex> lock(mMutex); mvKeyFrames.clear(); mbDirty = true; }
+
+    std::vector<KeyFrame*> DetectLoopCandidates(KeyFrame* pKF, float minScore) {
+        std::unique_lock<std::mutex> lock(mMutex);
+        const int n_kf = (int)mvKeyFrames.size();
+        if (!n_kf) return std::vector<KeyFrame*>();
+        pslam_ctx* c = context();
+        upload(c);
+        const std::set<KeyFrame*> spConnected = pKF->GetConnectedKeyFrames();
+        std::vector<uint8_t> connected(n_kf);
+        for (int k = 0; k < n_kf; ++k) connected[k] = spConnected.count(mvKeyFrames[k]) ? 1 : 0;
+        Query q(pKF->mBowVec);
+        std::vector<int32_t> covis = covisibility(), cand(n_kf), words(n_kf);
+        const float unset = -2.f;
+        std::vector<float> score(n_kf, unset);
+        const int n = pslam_detect_loop_candidates(c, (int)q.word.size(), q.word.data(), q.val.data(), covis.data(), 10, connected.data(), minScore, cand.data(),
+                                                   words.data(), score.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int k = 0; k < n_kf; ++k) {
+            KeyFrame* kf = mvKeyFrames[k];
+            if (words[k] > 0) { kf->mnLoopWords = words[k]; if (!connected[k]) kf->mnLoopQuery = pKF->mnId; }
+            if (score[k] != unset) kf->mLoopScore = score[k];
+        }
+        std::vector<KeyFrame*> r(n);
+        for (int i = 0; i < n; ++i) r[i] = mvKeyFrames[cand[i]];
+        return r;
+    }
+
+    std::vector<KeyFrame*> DetectRelocalizationCandidates(Frame* F) {
+        std::unique_lock<std::mutex> lock(mMutex);
+        const int n_kf = (int)mvKeyFrames.size();
+        if (!n_kf) return std::vector<KeyFrame*>();
+        pslam_ctx* c = context();
+        upload(c);
+        Query q(F->mBowVec);
+        std::vector<int32_t> covis = covisibility(), cand(n_kf), words(n_kf);
+        std::vector<float> score(n_kf);
+        for (int k = 0; k < n_kf; ++k) score[k] = mvKeyFrames[k]->mRelocScore;
+        const int n = pslam_detect_relocalization_candidates(c, (int)q.word.size(), q.word.data(), q.val.data(), covis.data(), 10, score.data(), cand.data(), words.data());
+        if (n < 0) throw std::runtime_error(pslam_last_error(c));
+        for (int k = 0; k < n_kf; ++k) {
+            KeyFrame* kf = mvKeyFrames[k];
+            if (words[k] > 0) { kf->mnRelocWords = words[k]; kf->mnRelocQuery = F->mnId; }
+            kf->mRelocScore = score[k];
+        }
+        std::vector<KeyFrame*> r(n);
+        for (int i = 0; i < n; ++i) r[i] = mvKeyFrames[cand[i]];
+        return r;
+    }
+
+private:
+    struct Query {
+        std::vector<int32_t> word; std::vector<double> val;
+        explicit Query(const DBoW2::BowVector& v) { for (const auto& kv : v) { word.push_back((int32_t)kv.first); val.push_back(kv.second); } }
+    };
+    void upload(pslam_ctx* c) {
+        if (!mbDirty && c == mpUploadedTo) return;
+        std::vector<int32_t> off(1, 0), word; std::vector<double> val;
+        for (KeyFrame* kf : mvKeyFrames) {
+            for (const auto& kv : kf->mBowVec) { word.push_back((int32_t)kv.first); val.push_back(kv.second); }
+            off.push_back((int32_t)word.size());
+        }
+        if (pslam_bow_database_set(c, (int)mvKeyFrames.size(), off.data(), word.data(), val.data()) != PSLAM_OK) throw std::runtime_error(pslam_last_error(c));
+        mbDirty = false; mpUploadedTo = c;
+    }
+    std::vector<int32_t> covisibility() {          // KeyFrame::GetBestCovisibilityKeyFrames(10) as database indices; neighbours outside the database cannot
+        std::unordered_map<KeyFrame*, int> index;  // carry this query's id and are left out, like the reference's mnLoopQuery / mnRelocQuery test skips them
+        for (size_t k = 0; k < mvKeyFrames.size(); ++k) index[mvKeyFrames[k]] = (int)k;
+        std::vector<int32_t> t(mvKeyFrames.size() * 10, -1);
+        for (size_t k = 0; k < mvKeyFrames.size(); ++k) {
+            int j = 0;
+            for (KeyFrame* nb : mvKeyFrames[k]->GetBestCovisibilityKeyFrames(10)) {
+                auto it = index.find(nb);
+                if (it != index.end()) t[k * 10 + j++] = it->second;
+            }
+        }
+        return t;
+    }
+    std::vector<KeyFrame*> mvKeyFrames; bool mbDirty = true; pslam_ctx* mpUploadedTo = nullptr; std::mutex mMutex;
 };
 
 class PlaneMatcher {

@@ -54,6 +54,7 @@
 #ifndef DRV
 #define DRV(name) ref_##name
 #define DRV_ORBMATCHER ORBmatcher
+#define DRV_LSDMATCHER LSDmatcher
 #define DRV_PLANEMATCHER PlaneMatcher
 #define DRV_OPTIMIZER Optimizer
 #endif
@@ -204,9 +205,8 @@ extern "C" int DRV(search_by_projection_last)(const pslam_frame_view* cur, const
     return n;
 }
 
-#ifndef PSLAM_ADAPTER_BUILD
 // ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)   src/ORBmatcher.cc:160-292
-extern "C" int ref_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_mp, int kf_nodes, const int32_t* kf_node_id,
+extern "C" int DRV(search_by_bow)(int n_kf, const uint8_t* kf_desc, const float* kf_angle, const uint8_t* kf_has_mp, int kf_nodes, const int32_t* kf_node_id,
                                  const int32_t* kf_node_off, const int32_t* kf_node_feat, int n_f, const uint8_t* f_desc, const float* f_angle, int f_nodes,
                                  const int32_t* f_node_id, const int32_t* f_node_off, const int32_t* f_node_feat, float nnratio, int check_orientation, int32_t* match) {
     World w;
@@ -231,7 +231,7 @@ extern "C" int ref_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* 
     Frame F;
     basic(F, n_f, f_desc, f_angle);
     F.mFeatVec = feat_vec(f_nodes, f_node_id, f_node_off, f_node_feat);
-    ORBmatcher matcher(nnratio, check_orientation != 0);
+    DRV_ORBMATCHER matcher(nnratio, check_orientation != 0);
     std::vector<MapPoint*> vpMapPointMatches;
     const int n = matcher.SearchByBoW(pKF, F, vpMapPointMatches);
     for (int i = 0; i < n_f; ++i) match[i] = vpMapPointMatches[i] ? w.index.at(vpMapPointMatches[i]) : -1;     // index of the key-frame feature whose map point was taken
@@ -240,7 +240,7 @@ extern "C" int ref_search_by_bow(int n_kf, const uint8_t* kf_desc, const float* 
 }
 
 // ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)   src/ORBmatcher.cc:526-659 (the loop-closure matcher, LoopClosing::ComputeSim3 :258)
-extern "C" int ref_search_by_bow_kf(int n1, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int nodes1, const int32_t* node_id1, const int32_t* node_off1,
+extern "C" int DRV(search_by_bow_kf)(int n1, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int nodes1, const int32_t* node_id1, const int32_t* node_off1,
                                     const int32_t* node_feat1, int n2, const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2, int nodes2,
                                     const int32_t* node_id2, const int32_t* node_off2, const int32_t* node_feat2, float nnratio, int check_orientation, int32_t* match12) {
     World w;
@@ -265,7 +265,7 @@ extern "C" int ref_search_by_bow_kf(int n1, const uint8_t* desc1, const float* a
     };
     KeyFrame* k1 = make_kf(n1, desc1, angle1, has_mp1, nodes1, node_id1, node_off1, node_feat1, nullptr);
     KeyFrame* k2 = make_kf(n2, desc2, angle2, has_mp2, nodes2, node_id2, node_off2, node_feat2, &index2);
-    ORBmatcher matcher(nnratio, check_orientation != 0);
+    DRV_ORBMATCHER matcher(nnratio, check_orientation != 0);
     std::vector<MapPoint*> vpMatches12;
     const int n = matcher.SearchByBoW(k1, k2, vpMatches12);
     for (int i = 0; i < n1; ++i) match12[i] = vpMatches12[i] ? index2.at(vpMatches12[i]) : -1;
@@ -282,21 +282,35 @@ DBoW2::BowVector bow_vec(const int32_t* word, const double* val, int n) {
 }
 struct LoopWorld {
     World w;
+#ifdef PSLAM_ADAPTER_BUILD
+    pslam_adapter::ref::KeyFrameDatabase db;
+    KeyFrameDatabase* ref_db() { return static_cast<KeyFrameDatabase*>(NULL); }
+#else
     ORBVocabulary voc;                   // default: TF_IDF weighting, L1_NORM scoring (the reference's ORBvoc.txt header says the same)
     KeyFrameDatabase db;
+    KeyFrameDatabase* ref_db() { return &db; }
+#endif
     std::vector<KeyFrame*> kfs;
     std::unordered_map<KeyFrame*, int> index;
-    LoopWorld(int n_kf, const int32_t* off, const int32_t* word, const double* val, const int32_t* covis, int covis_stride, int32_t max_query_word) : db(voc) {
+    LoopWorld(int n_kf, const int32_t* off, const int32_t* word, const double* val, const int32_t* covis, int covis_stride, int32_t max_query_word)
+#ifndef PSLAM_ADAPTER_BUILD
+        : db(voc)
+#endif
+    {
+#ifndef PSLAM_ADAPTER_BUILD
         int32_t max_word = max_query_word;
         for (int i = 0; i < off[n_kf]; ++i) max_word = std::max(max_word, word[i]);
         db.mvInvertedFile.clear();
         db.mvInvertedFile.resize((size_t)max_word + 1);
+#else
+        (void)max_query_word;
+#endif
         for (int k = 0; k < n_kf; ++k) {
             Frame F;
             F.N = 0;
             F.SetPose(cv::Mat::eye(4, 4, CV_32F));
             F.mBowVec = bow_vec(word + off[k], val + off[k], off[k + 1] - off[k]);
-            KeyFrame* kf = new KeyFrame(F, &w.map, &db);
+            KeyFrame* kf = new KeyFrame(F, &w.map, ref_db());
             index[kf] = k;
             kfs.push_back(kf);
             db.add(kf);
@@ -312,7 +326,7 @@ struct LoopWorld {
 };
 }  // namespace
 
-extern "C" int ref_detect_loop_candidates(const int32_t* q_word, const double* q_val, int n_q, int n_kf, const int32_t* off, const int32_t* word, const double* val,
+extern "C" int DRV(detect_loop_candidates)(const int32_t* q_word, const double* q_val, int n_q, int n_kf, const int32_t* off, const int32_t* word, const double* val,
                                           const int32_t* covis, int covis_stride, const uint8_t* connected, float min_score, int32_t* cand, int32_t* common_words,
                                           float* score) {
     LoopWorld L(n_kf, off, word, val, covis, covis_stride, n_q ? q_word[n_q - 1] : 0);
@@ -320,7 +334,7 @@ extern "C" int ref_detect_loop_candidates(const int32_t* q_word, const double* q
     F.N = 0;
     F.SetPose(cv::Mat::eye(4, 4, CV_32F));
     F.mBowVec = bow_vec(q_word, q_val, n_q);
-    KeyFrame* q = new KeyFrame(F, &L.w.map, &L.db);
+    KeyFrame* q = new KeyFrame(F, &L.w.map, L.ref_db());
     for (int k = 0; k < n_kf; ++k) {
         if (connected && connected[k]) q->mConnectedKeyFrameWeights[L.kfs[k]] = 1;
         L.kfs[k]->mLoopScore = score[k];           // uninitialised in the reference's constructor: the caller's sentinel shows where it was evaluated
@@ -332,7 +346,7 @@ extern "C" int ref_detect_loop_candidates(const int32_t* q_word, const double* q
     return (int)r.size();
 }
 
-extern "C" int ref_detect_relocalization_candidates(const int32_t* q_word, const double* q_val, int n_q, int n_kf, const int32_t* off, const int32_t* word,
+extern "C" int DRV(detect_relocalization_candidates)(const int32_t* q_word, const double* q_val, int n_q, int n_kf, const int32_t* off, const int32_t* word,
                                                     const double* val, const int32_t* covis, int covis_stride, float* reloc_score_io, int32_t* cand,
                                                     int32_t* common_words) {
     LoopWorld L(n_kf, off, word, val, covis, covis_stride, n_q ? q_word[n_q - 1] : 0);
@@ -348,6 +362,7 @@ extern "C" int ref_detect_relocalization_candidates(const int32_t* q_word, const
     return (int)r.size();
 }
 
+#ifndef PSLAM_ADAPTER_BUILD
 // Frame::isInFrustum(MapLine*, viewingCosLimit)   src/Frame.cc:369-437 (with MapLine::PredictScale / Get{Min,Max}DistanceInvariance, src/MapLine.cpp:364-390)
 // fv: Tcw[16], fx, fy, cx, cy, min_x, max_x, min_y, max_y, log_scale_factor
 extern "C" void ref_lines_in_frustum(const float* fv, int n, const double* pos, const double* normal, const float* max_distance, const float* min_distance,
@@ -374,7 +389,9 @@ extern "C" void ref_lines_in_frustum(const float* fv, int n, const double* pos, 
 }
 
 // LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, th)   src/LSDmatcher.cpp:141-211 (Frame::GetLinesInArea src/Frame.cc:491-523)
-extern "C" int ref_line_search_by_projection(int nf, const float* pt, const float* angle, const int32_t* octave, const uint8_t* desc, const uint8_t* has_obs,
+#endif  // !PSLAM_ADAPTER_BUILD
+
+extern "C" int DRV(line_search_by_projection)(int nf, const float* pt, const float* angle, const int32_t* octave, const uint8_t* desc, const uint8_t* has_obs,
                                              const float* scale_factors, int n_levels, int nm, const uint8_t* skip, const int32_t* level, const float* view_cos,
                                              const float* proj, const uint8_t* mdesc, const uint8_t* m_has_obs, float th, float nnratio, int32_t* assigned) {
     World w;
@@ -403,14 +420,12 @@ extern "C" int ref_line_search_by_projection(int nf, const float* pt, const floa
         p->nObs = m_has_obs[j] ? 1 : 0;
         vpMapLines[j] = p; index[p] = j; own.push_back(p);
     }
-    LSDmatcher matcher(nnratio);
+    DRV_LSDMATCHER matcher(nnratio);
     const int n = matcher.SearchByProjection(F, vpMapLines, th);
     for (int i = 0; i < nf; ++i) assigned[i] = (F.mvpMapLines[i] && F.mvpMapLines[i] != held[i]) ? index.at(F.mvpMapLines[i]) : -1;
     for (MapLine* p : own) delete p;
     return n;
 }
-
-#endif  // !PSLAM_ADAPTER_BUILD
 
 // PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)   src/PlaneMatcher.cpp:10-82 (Frame::ComputePlaneWorldCoeff src/Frame.cc:815-820)
 extern "C" int DRV(plane_match)(const float* Tcw, int n_frame, const float* frame_coef, int n_map, const float* map_coef, const uint8_t* map_bad, const int32_t* pts_off,

@@ -18,6 +18,7 @@
 #include <utility>
 #include <vector>
 
+#include "bowdb_select.h"
 #include "pslam_internal.h"
 
 namespace pslam {
@@ -237,31 +238,6 @@ int bowdb_score(pslam_ctx* c, int n_q, const int32_t* q_word, const double* q_va
     return PSLAM_OK;
 }
 
-// lKFsSharingWords: key frames in the order the scan of the inverted file meets them - query words ascending, each word's list in database order
-void sharing_order(const BowDbBuffers& B, const uint8_t* connected, std::vector<int>& listed) {
-    listed.clear();
-    for (int k = 0; k < B.n_kf; ++k)
-        if (B.h_first[k] >= 0 && !(connected && connected[k])) listed.push_back(k);
-    std::stable_sort(listed.begin(), listed.end(), [&](int a, int b) { return B.h_first[a] < B.h_first[b]; });
-}
-
-int covis_check(pslam_ctx* c, const BowDbBuffers& B, const int32_t* covis, int covis_stride) {
-    if (covis_stride < 0 || (covis_stride && !covis)) return set_error(c, PSLAM_E_INVALID, "bad covisibility table");
-    for (size_t i = 0; i < (size_t)B.n_kf * covis_stride; ++i)
-        if (covis[i] >= B.n_kf) return set_error(c, PSLAM_E_INVALID, "covisibility index out of range");
-    return PSLAM_OK;
-}
-
-// the tail both detectors share (src/KeyFrameDatabase.cc:176-196 / :284-304): keep accumulated scores above 0.75 x best, first occurrence of each key frame
-int retain(const std::vector<std::pair<float, int>>& acc, float best_acc, int n_kf, int32_t* candidates) {
-    const float min_retain = 0.75f * best_acc;
-    std::vector<char> added(n_kf, 0);
-    int n = 0;
-    for (const auto& a : acc)
-        if (a.first > min_retain && !added[a.second]) { candidates[n++] = a.second; added[a.second] = 1; }
-    return n;
-}
-
 }  // namespace
 }  // namespace pslam
 
@@ -331,42 +307,8 @@ extern "C" int pslam_detect_loop_candidates(pslam_ctx* c, int n_q, const int32_t
     int rc = bowdb_score(c, n_q, q_word, q_val);
     if (rc != PSLAM_OK) return rc;
     const BowDbBuffers& B = *c->bowdb;
-    if ((rc = covis_check(c, B, covis, covis_stride)) != PSLAM_OK) return rc;
-    std::vector<int> listed;
-    sharing_order(B, connected, listed);
-    for (int k = 0; k < B.n_kf; ++k) {
-        // a connected key frame's counter restarts at every shared word (its mnLoopQuery is never set, src/KeyFrameDatabase.cc:93-103)
-        if (common_words) common_words[k] = (connected && connected[k] && B.h_common[k] > 0) ? 1 : B.h_common[k];
-    }
-    if (listed.empty()) return 0;
-    int max_common = 0;
-    for (int k : listed) max_common = std::max(max_common, B.h_common[k]);
-    const int min_common = (int)(max_common * 0.8f);
-    std::vector<char> scored(B.n_kf, 0);                       // mnLoopQuery == query && mnLoopWords > minCommonWords
-    std::vector<std::pair<float, int>> above;
-    for (int k : listed) {
-        if (B.h_common[k] <= min_common) continue;
-        scored[k] = 1;
-        if (score) score[k] = B.h_score[k];
-        if (B.h_score[k] >= min_score) above.emplace_back(B.h_score[k], k);
-    }
-    if (above.empty()) return 0;
-    std::vector<std::pair<float, int>> acc;
-    float best_acc = min_score;
-    for (const auto& sm : above) {
-        float best = sm.first, sum = sm.first;
-        int best_kf = sm.second;
-        for (int j = 0; j < covis_stride; ++j) {
-            const int k2 = covis[(size_t)sm.second * covis_stride + j];
-            if (k2 < 0) break;
-            if (!scored[k2]) continue;
-            sum += B.h_score[k2];
-            if (B.h_score[k2] > best) { best_kf = k2; best = B.h_score[k2]; }
-        }
-        acc.emplace_back(sum, best_kf);
-        if (sum > best_acc) best_acc = sum;
-    }
-    return retain(acc, best_acc, B.n_kf, candidates);
+    if (!bowdb_covis_ok(B.n_kf, covis, covis_stride)) return set_error(c, PSLAM_E_INVALID, "bad covisibility table");
+    return bowdb_select_loop(B.n_kf, B.h_common.data(), B.h_first.data(), B.h_score.data(), covis, covis_stride, connected, min_score, candidates, common_words, score);
 }
 
 extern "C" int pslam_detect_relocalization_candidates(pslam_ctx* c, int n_q, const int32_t* q_word, const double* q_val, const int32_t* covis, int covis_stride,
@@ -376,35 +318,6 @@ extern "C" int pslam_detect_relocalization_candidates(pslam_ctx* c, int n_q, con
     int rc = bowdb_score(c, n_q, q_word, q_val);
     if (rc != PSLAM_OK) return rc;
     const BowDbBuffers& B = *c->bowdb;
-    if ((rc = covis_check(c, B, covis, covis_stride)) != PSLAM_OK) return rc;
-    std::vector<int> listed;
-    sharing_order(B, nullptr, listed);
-    if (common_words) for (int k = 0; k < B.n_kf; ++k) common_words[k] = B.h_common[k];
-    if (listed.empty()) return 0;
-    int max_common = 0;
-    for (int k : listed) max_common = std::max(max_common, B.h_common[k]);
-    const int min_common = (int)(max_common * 0.8f);
-    std::vector<std::pair<float, int>> evaluated;
-    for (int k : listed) {
-        if (B.h_common[k] <= min_common) continue;
-        reloc_score_io[k] = B.h_score[k];
-        evaluated.emplace_back(B.h_score[k], k);
-    }
-    if (evaluated.empty()) return 0;
-    std::vector<std::pair<float, int>> acc;
-    float best_acc = 0;
-    for (const auto& sm : evaluated) {
-        float best = sm.first, sum = sm.first;
-        int best_kf = sm.second;
-        for (int j = 0; j < covis_stride; ++j) {
-            const int k2 = covis[(size_t)sm.second * covis_stride + j];
-            if (k2 < 0) break;
-            if (B.h_first[k2] < 0) continue;                  // mnRelocQuery != F->mnId: shares no word with the frame
-            sum += reloc_score_io[k2];                        // also a score left by an earlier query (the reference reads mRelocScore unconditionally)
-            if (reloc_score_io[k2] > best) { best_kf = k2; best = reloc_score_io[k2]; }
-        }
-        acc.emplace_back(sum, best_kf);
-        if (sum > best_acc) best_acc = sum;
-    }
-    return retain(acc, best_acc, B.n_kf, candidates);
+    if (!bowdb_covis_ok(B.n_kf, covis, covis_stride)) return set_error(c, PSLAM_E_INVALID, "bad covisibility table");
+    return bowdb_select_reloc(B.n_kf, B.h_common.data(), B.h_first.data(), B.h_score.data(), covis, covis_stride, reloc_score_io, candidates, common_words);
 }

@@ -188,3 +188,59 @@ def lines_in_frustum(ctx: Context, frame: dict, pos, normal, max_distance, min_d
     if rc < 0:
         ctx.check(rc)
     return rc, o
+
+
+def search_by_bow_kf(ctx: Context, kf1: dict, kf2: dict, nnratio: float = 0.75, check_orientation: bool = True):
+    """ORBmatcher(nnratio, checkOri).SearchByBoW(pKF1, pKF2, vpMatches12) - the loop-closure matcher (src/ORBmatcher.cc:526-659).  kf1 / kf2: desc [n][32] u8,
+    angle [n] f32 (mvKeysUn), has_mp [n] u8, node_id, node_off, node_feat i32.  Returns (nmatches, match12 [n1]: feature of key frame 2 or -1)."""
+    a = {k: np.ascontiguousarray(v) for k, v in kf1.items()}
+    b = {k: np.ascontiguousarray(v) for k, v in kf2.items()}
+    n1 = len(a["angle"])
+    match = np.full(max(n1, 1), -1, np.int32)
+    fn = ctx.L.pslam_search_by_bow_kf
+    fn.argtypes = [C.c_void_p] + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p] * 2 + [C.c_float, C.c_int, C.c_void_p]
+    side = lambda s: (len(s["angle"]), s["desc"].ctypes.data, s["angle"].ctypes.data, s["has_mp"].ctypes.data, len(s["node_id"]), s["node_id"].ctypes.data,
+                      s["node_off"].ctypes.data, s["node_feat"].ctypes.data)
+    n = fn(ctx.h, *side(a), *side(b), nnratio, 1 if check_orientation else 0, match.ctypes.data)
+    if n < 0:
+        ctx.check(n)
+    return n, match[:n1]
+
+
+class KeyFrameDatabase:
+    """The candidate searches of Planar_SLAM::KeyFrameDatabase (include/KeyFrameDatabase.h) over a database whose BowVectors are resident in HBM.
+    db: off [n_kf + 1], word, val (CSR, key frames in KeyFrameDatabase::add order), covis [n_kf][<= 10] (GetBestCovisibilityKeyFrames(10), -1 padded)."""
+
+    def __init__(self, ctx: Context, off, word, val, covis=None):
+        self.ctx = ctx
+        self.off, self.word, self.val = np.ascontiguousarray(off, np.int32), np.ascontiguousarray(word, np.int32), np.ascontiguousarray(val, np.float64)
+        self.n_kf = len(self.off) - 1
+        self.covis = np.ascontiguousarray(covis, np.int32) if covis is not None else np.full((max(self.n_kf, 1), 1), -1, np.int32)
+        L = ctx.L
+        L.pslam_bow_database_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pslam_detect_loop_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 3
+        L.pslam_detect_relocalization_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 3
+        ctx.check(L.pslam_bow_database_set(ctx.h, self.n_kf, self.off.ctypes.data, self.word.ctypes.data, self.val.ctypes.data))
+
+    def DetectLoopCandidates(self, q_word, q_val, min_score: float, connected=None, sentinel: float = -1.0):
+        """Returns (candidates, mnLoopWords [n_kf], mLoopScore [n_kf]; `sentinel` where the reference does not evaluate the score)."""
+        qw, qv = np.ascontiguousarray(q_word, np.int32), np.ascontiguousarray(q_val, np.float64)
+        cand, words = np.zeros(max(self.n_kf, 1), np.int32), np.zeros(max(self.n_kf, 1), np.int32)
+        score = np.full(max(self.n_kf, 1), sentinel, np.float32)
+        con = np.ascontiguousarray(connected, np.uint8) if connected is not None else None
+        n = self.ctx.L.pslam_detect_loop_candidates(self.ctx.h, len(qw), qw.ctypes.data, qv.ctypes.data, self.covis.ctypes.data, self.covis.shape[1],
+                                                    con.ctypes.data if con is not None else None, min_score, cand.ctypes.data, words.ctypes.data, score.ctypes.data)
+        if n < 0:
+            self.ctx.check(n)
+        return cand[:n].copy(), words[:self.n_kf], score[:self.n_kf]
+
+    def DetectRelocalizationCandidates(self, q_word, q_val, reloc_score):
+        """reloc_score: KeyFrame::mRelocScore of every database key frame before the call.  Returns (candidates, mnRelocWords, mRelocScore after)."""
+        qw, qv = np.ascontiguousarray(q_word, np.int32), np.ascontiguousarray(q_val, np.float64)
+        cand, words = np.zeros(max(self.n_kf, 1), np.int32), np.zeros(max(self.n_kf, 1), np.int32)
+        score = np.ascontiguousarray(reloc_score, np.float32).copy()
+        n = self.ctx.L.pslam_detect_relocalization_candidates(self.ctx.h, len(qw), qw.ctypes.data, qv.ctypes.data, self.covis.ctypes.data, self.covis.shape[1],
+                                                              score.ctypes.data, cand.ctypes.data, words.ctypes.data)
+        if n < 0:
+            self.ctx.check(n)
+        return cand[:n].copy(), words[:self.n_kf], score

@@ -313,16 +313,18 @@ def ref_search_by_projection_last(fv: dict, lf: dict, m: dict, th: float, mono: 
     return n, matches
 
 
-def ref_search_by_bow(kf: dict, frame: dict, nnratio: float = 0.7, check_orientation: bool = True):
-    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) by the reference's own code.  Same layout as oracle_lib.search_by_bow."""
-    L = match_lib()
-    L.ref_search_by_bow.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+def ref_search_by_bow(kf: dict, frame: dict, nnratio: float = 0.7, check_orientation: bool = True, impl: str = "ref"):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) by the reference's own code (impl="adp": the product's adapter).  Same layout as
+    oracle_lib.search_by_bow."""
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "search_by_bow")
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]
     k = {a: np.ascontiguousarray(b) for a, b in kf.items()}
     f = {a: np.ascontiguousarray(b) for a, b in frame.items()}
     nf = len(f["angle"])
     match = np.full(max(nf, 1), -1, np.int32)
-    n = L.ref_search_by_bow(len(k["angle"]), k["desc"].ctypes.data, k["angle"].ctypes.data, k["has_mp"].ctypes.data, len(k["node_id"]), k["node_id"].ctypes.data,
+    n = fn(len(k["angle"]), k["desc"].ctypes.data, k["angle"].ctypes.data, k["has_mp"].ctypes.data, len(k["node_id"]), k["node_id"].ctypes.data,
                             k["node_off"].ctypes.data, k["node_feat"].ctypes.data, nf, f["desc"].ctypes.data, f["angle"].ctypes.data, len(f["node_id"]),
                             f["node_id"].ctypes.data, f["node_off"].ctypes.data, f["node_feat"].ctypes.data, nnratio, 1 if check_orientation else 0,
                             match.ctypes.data)
@@ -345,15 +347,17 @@ def ref_lines_in_frustum(frame: dict, pos, normal, max_distance, min_distance, c
     return o
 
 
-def ref_line_search_by_projection(frame: dict, map_lines: dict, th: float, nnratio: float):
-    """LSDmatcher::SearchByProjection(Frame&, vector<MapLine*>&, th) by the reference's own code.  Same layout as oracle_lib.line_search_by_projection."""
-    L = match_lib()
-    L.ref_line_search_by_projection.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p]
+def ref_line_search_by_projection(frame: dict, map_lines: dict, th: float, nnratio: float, impl: str = "ref"):
+    """LSDmatcher::SearchByProjection(Frame&, vector<MapLine*>&, th) by the reference's own code (impl="adp": the product's adapter).  Same layout as
+    oracle_lib.line_search_by_projection."""
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "line_search_by_projection")
+    fn.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_float, C.c_float, C.c_void_p]
     f = {k: np.ascontiguousarray(v) for k, v in frame.items()}
     m = {k: np.ascontiguousarray(v) for k, v in map_lines.items()}
     nf, nm = len(f["angle"]), len(m["level"])
     assigned = np.full(max(nf, 1), -1, np.int32)
-    n = L.ref_line_search_by_projection(nf, f["pt"].ctypes.data, f["angle"].ctypes.data, f["octave"].ctypes.data, f["desc"].ctypes.data,
+    n = fn(nf, f["pt"].ctypes.data, f["angle"].ctypes.data, f["octave"].ctypes.data, f["desc"].ctypes.data,
                                         f["has_obs"].ctypes.data, f["scale_factors"].ctypes.data, len(f["scale_factors"]), nm, m["skip"].ctypes.data,
                                         m["level"].ctypes.data, m["view_cos"].ctypes.data, m["proj"].ctypes.data, m["desc"].ctypes.data,
                                         m["has_obs"].ctypes.data, th, nnratio, assigned.ctypes.data)
@@ -452,31 +456,34 @@ def ref_track_manhattan_frame(R_last, normals, dirs):
     return out
 
 
-def ref_detect_loop_candidates(db: dict, min_score: float, sentinel: float = -1.0):
+def ref_detect_loop_candidates(db: dict, min_score: float, sentinel: float = -1.0, impl: str = "ref"):
     """KeyFrameDatabase::DetectLoopCandidates by the reference's own code (src/KeyFrameDatabase.cc + DBoW2 L1 scoring).  Same layout as oracle_lib.detect_loop_candidates."""
-    L = match_lib()
-    L.ref_detect_loop_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 3
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "detect_loop_candidates")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_float] + [C.c_void_p] * 3
     import oracle_lib
     d, n_kf, covis, stride = oracle_lib._db_args(db)
     cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.full(max(n_kf, 1), sentinel, np.float32)
-    n = L.ref_detect_loop_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+    n = fn(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
                                      d["val"].ctypes.data, covis, stride, d["connected"].ctypes.data if "connected" in d else None, min_score,
                                      cand.ctypes.data, words.ctypes.data, score.ctypes.data)
     return cand[:n].copy(), words[:n_kf], score[:n_kf]
 
 
-def ref_detect_relocalization_candidates(db: dict, reloc_score: np.ndarray):
-    L = match_lib()
-    L.ref_detect_relocalization_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
+def ref_detect_relocalization_candidates(db: dict, reloc_score: np.ndarray, impl: str = "ref"):
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "detect_relocalization_candidates")
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 3
     import oracle_lib
     d, n_kf, covis, stride = oracle_lib._db_args(db)
     cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.ascontiguousarray(reloc_score, np.float32).copy()
-    n = L.ref_detect_relocalization_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+    n = fn(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
                                                d["val"].ctypes.data, covis, stride, score.ctypes.data, cand.ctypes.data, words.ctypes.data)
     return cand[:n].copy(), words[:n_kf], score
 
 
-def ref_search_by_bow_kf(kf1: dict, kf2: dict, nnratio: float = 0.75, check_orientation: bool = True):
-    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) by the reference's own code."""
+def ref_search_by_bow_kf(kf1: dict, kf2: dict, nnratio: float = 0.75, check_orientation: bool = True, impl: str = "ref"):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) by the reference's own code (impl="adp": the product's adapter)."""
     import oracle_lib
-    return oracle_lib._bow_kf_call(match_lib().ref_search_by_bow_kf, kf1, kf2, nnratio, check_orientation)
+    lib, pre = _impl(impl)
+    return oracle_lib._bow_kf_call(getattr(lib, pre + "search_by_bow_kf"), kf1, kf2, nnratio, check_orientation)

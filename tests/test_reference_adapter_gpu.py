@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import ref_lib
-from planarslam_b200 import synth_pose
+from planarslam_b200 import synth_lines, synth_pose
 from test_oracle_match_ref import PLANE_TH, last_case, map_case
 from test_oracle_planematch import _scenario as plane_scenario
 
@@ -61,3 +61,51 @@ def test_optimizer_pose_and_translation_adapters():
                 assert np.array_equal(a[k], r[k]), (translation_only, kw, k)
             da, dt = synth_pose.pose_error(a["Tcw"], r["Tcw"])
             assert da < 5e-6 and dt < 2e-5, (translation_only, kw, da, dt)
+
+
+def test_orbmatcher_search_by_bow_adapters():
+    tot = 0
+    for seed in range(3):
+        kf, f = synth_lines.make_bow_pair(seed, n_kf=400, n_f=380, n_nodes=90)
+        for ratio, ori in ((0.7, True), (0.9, False)):
+            rn, rm = ref_lib.ref_search_by_bow(kf, f, ratio, ori)
+            an, am = ref_lib.ref_search_by_bow(kf, f, ratio, ori, impl="adp")
+            assert an == rn and np.array_equal(am, rm), (seed, ratio, ori)
+            tot += an
+        kf1, kf2 = synth_lines.make_bow_kf_pair(seed, n_kf=400, n_f=380, n_nodes=90)
+        for ratio, ori in ((0.75, True), (0.9, False)):
+            rn, rm = ref_lib.ref_search_by_bow_kf(kf1, kf2, ratio, ori)
+            an, am = ref_lib.ref_search_by_bow_kf(kf1, kf2, ratio, ori, impl="adp")
+            assert an == rn and np.array_equal(am, rm), (seed, ratio, ori)
+            tot += an
+    assert tot > 800
+
+
+def test_lsdmatcher_search_by_projection_adapter():
+    tot = 0
+    for seed in range(6):
+        frame, mp = synth_lines.make_line_search(seed, n_frame=40 + 4 * seed, n_map=120 + 30 * seed)
+        for th, nnr in ((3.0, 0.8), (1.0, 0.8), (5.0, 0.6)):
+            rn, ra = ref_lib.ref_line_search_by_projection(frame, mp, th, nnr)
+            an, aa = ref_lib.ref_line_search_by_projection(frame, mp, th, nnr, impl="adp")
+            assert an == rn and np.array_equal(aa, ra), (seed, th, nnr)
+            tot += an
+    assert tot > 50
+
+
+def test_keyframe_database_adapter():
+    from test_oracle_loopclose_ref import CASES
+    found = 0
+    for case in CASES:
+        db = synth_lines.make_bow_database(**case)
+        n_kf = len(db["off"]) - 1
+        for min_score in (0.0, 0.03):
+            rc, rw, rs = ref_lib.ref_detect_loop_candidates(db, min_score)
+            ac, aw, as_ = ref_lib.ref_detect_loop_candidates(db, min_score, impl="adp")       # reads mnLoopWords / mLoopScore back from the KeyFrame objects
+            assert np.array_equal(ac, rc) and np.array_equal(aw, rw) and np.array_equal(as_, rs), (case, min_score)
+            found += len(rc)
+        stale = np.random.default_rng(case["seed"]).uniform(0, 0.05, n_kf).astype(np.float32)
+        rc, rw, rs = ref_lib.ref_detect_relocalization_candidates(db, stale)
+        ac, aw, as_ = ref_lib.ref_detect_relocalization_candidates(db, stale, impl="adp")
+        assert np.array_equal(ac, rc) and np.array_equal(aw, rw) and np.array_equal(as_, rs), case
+    assert found > 5
