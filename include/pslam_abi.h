@@ -521,7 +521,7 @@ int pslam_search_by_bow(pslam_ctx* ctx, int n_kf, const uint8_t* kf_desc, const 
                         float nnratio, int check_orientation, int32_t* match);
 
 /* Replaces  int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12)
- *           include/ORBmatcher.h:56, src/ORBmatcher.cc:526-659 - the loop-closure matcher (LoopClosing::ComputeSim3, src/LoopClosing.cc:258), the consumer
+ *           include/ORBmatcher.h:56, src/ORBmatcher.cc:526-659 - the loop-closure matcher (LoopClosing::ComputeSim3, src/LoopClosing.cc:265), the consumer
  *           of the key-frame descriptor exchange.
  * Same array layout as pslam_search_by_bow, both sides with map-point flags (has_mp[i] = vpMapPoints[i] && !isBad()); the distance gate is the
  * strict bestDist1 < TH_LOW of this overload.  match12[i1] = feature of key frame 2 whose map point the call stores into vpMatches12[i1] (-1: NULL).

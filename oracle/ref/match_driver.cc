@@ -239,7 +239,7 @@ extern "C" int DRV(search_by_bow)(int n_kf, const uint8_t* kf_desc, const float*
     return n;
 }
 
-// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)   src/ORBmatcher.cc:526-659 (the loop-closure matcher, LoopClosing::ComputeSim3 :258)
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)   src/ORBmatcher.cc:526-659 (the loop-closure matcher, LoopClosing::ComputeSim3 :265)
 extern "C" int DRV(search_by_bow_kf)(int n1, const uint8_t* desc1, const float* angle1, const uint8_t* has_mp1, int nodes1, const int32_t* node_id1, const int32_t* node_off1,
                                     const int32_t* node_feat1, int n2, const uint8_t* desc2, const float* angle2, const uint8_t* has_mp2, int nodes2,
                                     const int32_t* node_id2, const int32_t* node_off2, const int32_t* node_feat2, float nnratio, int check_orientation, int32_t* match12) {
