@@ -495,7 +495,8 @@ def main():
     ctxs = [Context(W, H, SUB_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(3)] + [Context(W, H, (FRAMES_PER_STEP + LSD_SUBS - 1) // LSD_SUBS, device=local_rank)]   # one context per stage family
     # PSLAM_LSD_STREAM=peac puts the two latency-bound one-warp-per-frame chains (PEAC, LSD) on one stream: their CTAs compete for
     # the same register file, and running them back to back avoids half-resident waves of both
-    mode = os.environ.get("PSLAM_LSD_STREAM", "peac")
+    # (config 5: a call holds a quarter of the frames the one-warp-per-frame kernels could keep resident, so the two chains overlap on separate streams)
+    mode = os.environ.get("PSLAM_LSD_STREAM", "peac" if AREA == 1 else "own")
     if mode == "peac":
         streams[3] = streams[1]
     elif mode == "one":
