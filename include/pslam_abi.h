@@ -155,6 +155,17 @@ int pslam_planes_post_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nfr
 /* d_normals3 (optional): the normals alone, [nframes][pslam_surface_normals_count()][3] - the layout pslam_track_manhattan_batch_dev reads (NaN normals stay NaN and fail
  * every cone test there, like in the reference) */
 int pslam_surface_normals_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, float* d_normals8, float* d_normals3);
+/* Replaces  void MapPlane::UpdateCoefficientsAndPoints()  and  (const Frame& pF, int id)      include/MapPlane.h, src/MapPlane.cc:298-365
+ * (SURVEY.md 8 f4): per map plane ("job") the clouds of its observations - KeyFrame::mvPlanePoints[id] with T = Converter::toMatrix4d(GetPoseInverse());
+ * for the second overload the frame's cloud with T = toSE3Quat(mTcw).inverse() plus the plane's current cloud with the identity - are transformed like
+ * pcl::transformPointCloud (double 4x4, row-major here, on float points), concatenated and reduced by pcl::VoxelGrid (leaf 0.1 m).  out_pts [n_jobs][cap][3]
+ * receives the new MapPlane::mvPlanePoints (voxel centroids in ascending voxel index), n_out [n_jobs] their counts.  Clouds as CSR: job_cloud_off [n_jobs + 1]
+ * into the cloud list, cloud_pt_off [n_clouds + 1] into pts (xyz), T [n_clouds][16].  The reference's SACSegmentation call after the filter writes into
+ * locals that are never read and is not reproduced.  PSLAM_E_CAPACITY when a plane occupies more than cap (<= pslam_map_plane_max_points()) voxels. */
+int pslam_map_plane_max_points(const pslam_ctx* ctx);
+int pslam_map_plane_update_batch(pslam_ctx* ctx, int n_jobs, const int32_t* job_cloud_off, const int32_t* cloud_pt_off, const float* pts, const double* T,
+                                 int cap, float* out_pts, int32_t* n_out);
+
 /* PEAC + post-processing + normals on host depth images (the whole Frame::ComputePlanes); normals8 may be NULL */
 int pslam_compute_planes_batch(pslam_ctx* ctx, const uint16_t* depth, int nframes, float dist_th, int32_t* n_kept, int32_t* src, float* coef, int32_t* pt_off, float* pts,
                                int cap_pts, float* normals8);

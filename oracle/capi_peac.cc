@@ -97,5 +97,15 @@ int orc_surface_normals(const uint16_t* depth, int w, int h, float fx, float fy,
     for (size_t i = 0; i < v.size() && (int)i < cap; ++i) std::memcpy(out8 + 8 * i, &v[i], 32);
     return (int)v.size();
 }
+// MapPlane::UpdateCoefficientsAndPoints: clouds as CSR (cloud_off [n_clouds + 1] in points, pts xyz), T [n_clouds][16]; returns the number of voxel centroids
+int orc_map_plane_update(int n_clouds, const int32_t* cloud_off, const float* pts, const double* T, float* out, int cap) {
+    std::vector<std::vector<float>> clouds(n_clouds);
+    std::vector<const double*> Ts(n_clouds);
+    for (int c = 0; c < n_clouds; ++c) { clouds[c].assign(pts + 3 * (size_t)cloud_off[c], pts + 3 * (size_t)cloud_off[c + 1]); Ts[c] = T + 16 * (size_t)c; }
+    std::vector<float> o;
+    oracle::map_plane_update(clouds, Ts, o);
+    for (size_t i = 0; i < o.size() && (int)(i / 3) < cap; ++i) out[i] = o[i];
+    return (int)o.size() / 3;
+}
 uint32_t orc_pcl_rng(int n) { oracle::PclRng r; uint32_t v = 0; for (int i = 0; i < n; ++i) v = r.next_u32(); return v; }
 }

@@ -235,6 +235,24 @@ void compute_planes_post(const uint16_t* depth, int w, int /*h*/, const PlanePos
     }
 }
 
+void map_plane_update(const std::vector<std::vector<float>>& clouds, const std::vector<const double*>& T, std::vector<float>& out_points) {
+    std::vector<P3> combined, coarse;
+    for (size_t c = 0; c < clouds.size(); ++c) {
+        const double* t = T[c];
+        for (size_t i = 0; i + 2 < clouds[c].size(); i += 3) {
+            const double x = clouds[c][i], y = clouds[c][i + 1], z = clouds[c][i + 2];
+            P3 p;                       // pcl::transformPointCloud<PointT, double>: rows of the matrix times (x, y, z, 1) in double, stored as float
+            p.x = (float)(((t[0] * x + t[1] * y) + t[2] * z) + t[3]);
+            p.y = (float)(((t[4] * x + t[5] * y) + t[6] * z) + t[7]);
+            p.z = (float)(((t[8] * x + t[9] * y) + t[10] * z) + t[11]);
+            combined.push_back(p);
+        }
+    }
+    voxel_grid(combined, coarse);
+    out_points.clear();
+    for (const P3& p : coarse) { out_points.push_back(p.x); out_points.push_back(p.y); out_points.push_back(p.z); }
+}
+
 void surface_normals(const uint16_t* depth, int w, int h, const PlanePostParams& prm, std::vector<SurfaceNormal>& out) {
     out.clear();
     const int W = (int)std::ceil(w / 3.0), H = (int)std::ceil(h / 3.0);

@@ -33,6 +33,12 @@ struct SurfaceNormal { float normal[3]; float cam[3]; float frame_xy[2]; };
 // vSurfaceNormal: every 2nd row / column (odd ones) of the normals of the 3x sub-sampled organised cloud; NaN normals at the borders are kept like the reference
 void surface_normals(const uint16_t* depth, int w, int h, const PlanePostParams& prm, std::vector<SurfaceNormal>& out);
 
+// MapPlane::UpdateCoefficientsAndPoints() / (const Frame&, int id)   src/MapPlane.cc:298-365: the plane clouds of the observations brought into one frame by
+// pcl::transformPointCloud (double 4x4 applied to float points, result rounded to float), concatenated and passed through the same VoxelGrid (leaf 0.1 m);
+// the result becomes MapPlane::mvPlanePoints.  (The SACSegmentation call that follows in the reference writes into locals that are never read.)
+// clouds: xyz triples; T: one row-major 4x4 per cloud.  PARITY UNPINNED like the rest of this file (PCL absent).
+void map_plane_update(const std::vector<std::vector<float>>& clouds, const std::vector<const double*>& T, std::vector<float>& out_points);
+
 // boost::mt19937(12345) through boost::uniform_int<>(0, INT_MAX) as pcl::SampleConsensusModel::rnd() draws it
 struct PclRng {
     uint32_t mt[624]; int idx;

@@ -120,3 +120,27 @@ def ComputePlanes(ctx: Context, depth: np.ndarray, dist_th: float = 0.05, normal
         out.append(dict(src=src[f, :n].copy(), coef=coef[f, :n].copy(), points=[pts[f, off[f, k]:off[f, k + 1]].copy() for k in range(n)],
                         normals=sn[f].copy() if normals else None))
     return out
+
+
+def UpdateMapPlanePoints(ctx: Context, jobs, cap: int | None = None):
+    """void MapPlane::UpdateCoefficientsAndPoints() / (const Frame&, int id) (src/MapPlane.cc:298-365) for a batch of map planes.  jobs: one list per map plane of
+    (points float32 [k][3], T float64 [4][4]) pairs - the observations' KeyFrame::mvPlanePoints[id] with the key frame's inverse pose (for the second overload
+    the frame's cloud with its inverse pose and the plane's current cloud with the identity).  Returns the new mvPlanePoints per map plane (float32 [n][3],
+    voxel centroids of the 0.1 m grid in ascending voxel index)."""
+    import ctypes as C
+    L = ctx.L
+    L.pslam_map_plane_update_batch.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
+    cap = int(cap or L.pslam_map_plane_max_points(ctx.h))
+    job_off, cloud_off, pts, Ts = [0], [0], [], []
+    for clouds in jobs:
+        for p, T in clouds:
+            p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+            pts.append(p); Ts.append(np.ascontiguousarray(T, np.float64).reshape(16)); cloud_off.append(cloud_off[-1] + len(p))
+        job_off.append(len(Ts))
+    job_off, cloud_off = np.asarray(job_off, np.int32), np.asarray(cloud_off, np.int32)
+    P = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, 3), np.float32))
+    T = np.ascontiguousarray(np.stack(Ts) if Ts else np.zeros((0, 16)))
+    out, n = np.zeros((max(len(jobs), 1), cap, 3), np.float32), np.zeros(max(len(jobs), 1), np.int32)
+    ctx.check(L.pslam_map_plane_update_batch(ctx.h, len(jobs), job_off.ctypes.data, cloud_off.ctypes.data, P.ctypes.data, T.ctypes.data, cap, out.ctypes.data,
+                                             n.ctypes.data))
+    return [out[j, :n[j]].copy() for j in range(len(jobs))]

@@ -566,3 +566,20 @@ def _bow_kf_call(fn, kf1, kf2, nnratio, check_orientation):
 def search_by_bow_kf(kf1: dict, kf2: dict, nnratio: float = 0.75, check_orientation: bool = True):
     """Oracle ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&).  Returns (nmatches, match12 [n1]: feature of key frame 2 or -1)."""
     return _bow_kf_call(lib().orc_search_by_bow_kf, kf1, kf2, nnratio, check_orientation)
+
+
+def map_plane_update(clouds):
+    """Oracle MapPlane::UpdateCoefficientsAndPoints (oracle/planepost.cc map_plane_update, parity unpinned): clouds = [(points float32 [k][3], T float64 [4][4])].
+    Returns the voxel centroids float32 [n][3]."""
+    L = lib()
+    L.orc_map_plane_update.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_int]
+    off, pts, Ts = [0], [], []
+    for p, T in clouds:
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+        pts.append(p); Ts.append(np.ascontiguousarray(T, np.float64).reshape(16)); off.append(off[-1] + len(p))
+    off = np.asarray(off, np.int32)
+    P = np.ascontiguousarray(np.concatenate(pts) if pts else np.zeros((0, 3), np.float32))
+    T = np.ascontiguousarray(np.stack(Ts) if Ts else np.zeros((0, 16)))
+    out = np.zeros((max(len(P), 1), 3), np.float32)
+    n = L.orc_map_plane_update(len(clouds), off.ctypes.data, P.ctypes.data, T.ctypes.data, out.ctypes.data, len(out))
+    return out[:n].copy()
