@@ -13,6 +13,7 @@
 //
 //   static int  Optimizer::PoseOptimization(Frame*)                                   include/Optimizer.h:38   src/Optimizer.cc:550-1275
 //   static int  Optimizer::TranslationOptimization(Frame*)                            include/Optimizer.h:40   src/Optimizer.cc:2995-3737
+//   static void Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*)              include/Optimizer.h:34   src/Optimizer.cc:1853-2678
 //   int ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, float th)    include/ORBmatcher.h:43  src/ORBmatcher.cc:46-130
 //   int ORBmatcher::SearchByProjection(Frame&, const Frame&, float th, bool bMono)    include/ORBmatcher.h:47  src/ORBmatcher.cc:1396-1535
 //   int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)                include/ORBmatcher.h:53  src/ORBmatcher.cc:160-292
@@ -31,6 +32,8 @@
 #include <cmath>
 #include <algorithm>
 #include <cstring>
+#include <list>
+#include <map>
 #include <mutex>
 #include <set>
 #include <stdexcept>
@@ -73,6 +76,185 @@ inline pslam_ctx* context(int width = 640, int height = 480) {
 struct Optimizer {
     static int PoseOptimization(Frame* pFrame) { return run(pFrame, false); }
     static int TranslationOptimization(Frame* pFrame) { return run(pFrame, true); }
+
+    // Local bundle adjustment around pKF (include/Optimizer.h:34, src/Optimizer.cc:1853-2678).  The walk that selects the local / fixed key frames and the local
+    // points, lines and planes is the reference's (same marker fields mnBALocalForKF / mnBAFixedForKF, same list orders); the graph it would hand to g2o goes to
+    // pslam_local_bundle_adjustment as plain arrays; erasures, poses and landmark positions are written back under pMap->mMutexMapUpdate like the reference does.
+    // pbStopFlag is only honoured before the optimisation starts (a result that depends on when another thread raises the flag cannot be reproduced).
+    static void LocalBundleAdjustment(KeyFrame* pKF, bool* pbStopFlag, Planar_SLAM::Map* pMap) {
+        std::list<KeyFrame*> lLocalKeyFrames;
+        lLocalKeyFrames.push_back(pKF);
+        pKF->mnBALocalForKF = pKF->mnId;
+        for (KeyFrame* pKFi : pKF->GetVectorCovisibleKeyFrames()) {
+            pKFi->mnBALocalForKF = pKF->mnId;
+            if (!pKFi->isBad()) lLocalKeyFrames.push_back(pKFi);
+        }
+        std::list<MapPoint*> lLocalMapPoints;
+        std::list<MapLine*> lLocalMapLines;
+        std::list<MapPlane*> lLocalMapPlanes;
+        for (KeyFrame* k : lLocalKeyFrames)
+            for (MapPoint* pMP : k->GetMapPointMatches())
+                if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) { lLocalMapPoints.push_back(pMP); pMP->mnBALocalForKF = pKF->mnId; }
+        for (KeyFrame* k : lLocalKeyFrames)
+            for (MapLine* pML : k->GetMapLineMatches())
+                if (pML && !pML->isBad() && pML->mnBALocalForKF != pKF->mnId) { lLocalMapLines.push_back(pML); pML->mnBALocalForKF = pKF->mnId; }
+        for (KeyFrame* k : lLocalKeyFrames)
+            for (MapPlane* pMP : k->GetMapPlaneMatches())
+                if (pMP && !pMP->isBad() && pMP->mnBALocalForKF != pKF->mnId) { lLocalMapPlanes.push_back(pMP); pMP->mnBALocalForKF = pKF->mnId; }
+        std::list<KeyFrame*> lFixedCameras;
+        auto fix = [&](const std::map<KeyFrame*, size_t>& observations) {
+            for (const auto& o : observations) {
+                KeyFrame* pKFi = o.first;
+                if (pKFi->mnBALocalForKF != pKF->mnId && pKFi->mnBAFixedForKF != pKF->mnId) {
+                    pKFi->mnBAFixedForKF = pKF->mnId;
+                    if (!pKFi->isBad()) lFixedCameras.push_back(pKFi);
+                }
+            }
+        };
+        for (MapPoint* p : lLocalMapPoints) fix(p->GetObservations());
+        for (MapLine* l : lLocalMapLines) fix(l->GetObservations());
+        for (MapPlane* q : lLocalMapPlanes) fix(q->GetObservations());
+        if (pbStopFlag && *pbStopFlag) return;
+
+        // vertices in g2o's order (ascending id): key frames by mnId, then points, line end points and planes by mnId
+        std::vector<KeyFrame*> kfs(lLocalKeyFrames.begin(), lLocalKeyFrames.end());
+        const size_t n_local = kfs.size();
+        kfs.insert(kfs.end(), lFixedCameras.begin(), lFixedCameras.end());
+        std::vector<uint8_t> is_fixed_cam(kfs.size(), 0);
+        for (size_t i = n_local; i < kfs.size(); ++i) is_fixed_cam[i] = 1;
+        std::vector<int> kf_order(kfs.size());
+        for (size_t i = 0; i < kfs.size(); ++i) kf_order[i] = (int)i;
+        std::sort(kf_order.begin(), kf_order.end(), [&](int a, int b) { return kfs[a]->mnId < kfs[b]->mnId; });
+        std::unordered_map<KeyFrame*, int> kf_index;
+        std::vector<KeyFrame*> kf_sorted(kfs.size());
+        std::vector<float> kf_Tcw(kfs.size() * 16), kf_K(kfs.size() * 5);
+        std::vector<uint8_t> kf_fixed(kfs.size());
+        unsigned long maxKFid = 0;
+        for (size_t r = 0; r < kfs.size(); ++r) {
+            KeyFrame* k = kfs[kf_order[r]];
+            kf_sorted[r] = k; kf_index[k] = (int)r;
+            kf_fixed[r] = (is_fixed_cam[kf_order[r]] || k->mnId == 0) ? 1 : 0;
+            const cv::Mat T = k->GetPose();
+            for (int i = 0; i < 16; ++i) kf_Tcw[r * 16 + i] = T.at<float>(i / 4, i % 4);
+            kf_K[r * 5] = k->fx; kf_K[r * 5 + 1] = k->fy; kf_K[r * 5 + 2] = k->cx; kf_K[r * 5 + 3] = k->cy; kf_K[r * 5 + 4] = k->mbf;
+            if (k->mnId > maxKFid) maxKFid = k->mnId;
+        }
+        auto by_id = [](auto& v) { std::stable_sort(v.begin(), v.end(), [](auto* a, auto* b) { return a->mnId < b->mnId; }); };
+        std::vector<MapPoint*> pts(lLocalMapPoints.begin(), lLocalMapPoints.end());
+        std::vector<MapLine*> lines(lLocalMapLines.begin(), lLocalMapLines.end());
+        std::vector<MapPlane*> planes(lLocalMapPlanes.begin(), lLocalMapPlanes.end());
+        by_id(pts); by_id(lines); by_id(planes);
+        std::unordered_map<MapPoint*, int> pt_index; std::unordered_map<MapLine*, int> line_index; std::unordered_map<MapPlane*, int> plane_index;
+        std::vector<float> pt_Xw(pts.size() * 3 + 3), plane_Xw(planes.size() * 4 + 4);
+        std::vector<double> line_Xw(lines.size() * 6 + 6);
+        for (size_t i = 0; i < pts.size(); ++i) { pt_index[pts[i]] = (int)i; const cv::Mat X = pts[i]->GetWorldPos(); for (int c = 0; c < 3; ++c) pt_Xw[i * 3 + c] = X.at<float>(c); }
+        for (size_t i = 0; i < lines.size(); ++i) { line_index[lines[i]] = (int)i; const auto X = lines[i]->GetWorldPos(); for (int c = 0; c < 6; ++c) line_Xw[i * 6 + c] = X(c); }
+        for (size_t i = 0; i < planes.size(); ++i) { plane_index[planes[i]] = (int)i; const cv::Mat X = planes[i]->GetWorldPos(); for (int c = 0; c < 4; ++c) plane_Xw[i * 4 + c] = X.at<float>(c); }
+
+        // edges in creation order: the local lists as the reference walks them, every landmark's observations in its std::map order
+        struct PtObs { KeyFrame* kf; MapPoint* p; };
+        struct LineObs { KeyFrame* kf; MapLine* l; };
+        struct PlaneObs { KeyFrame* kf; MapPlane* q; };
+        std::vector<PtObs> pt_obs; std::vector<LineObs> line_obs; std::vector<PlaneObs> plane_obs[3];
+        std::vector<int32_t> po_kf, po_pt, lo_kf, lo_line, plo_kf[3], plo_plane[3];
+        std::vector<float> po_uvr, po_is2, plo_meas[3];
+        std::vector<double> lo_l;
+        for (MapPoint* pMP : lLocalMapPoints)
+            for (const auto& o : pMP->GetObservations()) {
+                KeyFrame* pKFi = o.first;
+                if (pKFi->isBad()) continue;
+                const auto it = kf_index.find(pKFi);
+                if (it == kf_index.end()) continue;                         // (cannot happen: every observer is local or was made a fixed camera above)
+                const cv::KeyPoint& kpUn = pKFi->mvKeysUn[o.second];
+                po_kf.push_back(it->second); po_pt.push_back(pt_index[pMP]);
+                po_uvr.push_back(kpUn.pt.x); po_uvr.push_back(kpUn.pt.y); po_uvr.push_back(pKFi->mvuRight[o.second] < 0 ? -1.0f : pKFi->mvuRight[o.second]);
+                po_is2.push_back(pKFi->mvInvLevelSigma2[kpUn.octave]);
+                pt_obs.push_back(PtObs{pKFi, pMP});
+            }
+        const int cur = kf_index[pKF];
+        for (MapLine* pML : lLocalMapLines)
+            for (const auto& o : pML->GetObservations()) {
+                KeyFrame* pKFi = o.first;
+                if (pKFi->isBad()) continue;
+                const Eigen::Vector3d lineObs = pKF->mvKeyLineFunctions[o.second];   // the reference reads the CURRENT key frame's line function and hangs both
+                lo_kf.push_back(cur); lo_line.push_back(line_index[pML]);            // end-point edges on the current key frame (src/Optimizer.cc:2169-2201)
+                for (int c = 0; c < 3; ++c) lo_l.push_back(lineObs(c));
+                line_obs.push_back(LineObs{pKFi, pML});
+            }
+        for (MapPlane* pMP : lLocalMapPlanes)
+            for (int fam = 0; fam < 3; ++fam) {                             // [0] EdgePlane, [1] EdgeVerticalPlane, [2] EdgeParallelPlane
+                const std::map<KeyFrame*, size_t> observations = fam == 0 ? pMP->GetObservations() : fam == 1 ? pMP->GetVerObservations() : pMP->GetParObservations();
+                for (const auto& o : observations) {
+                    KeyFrame* k = o.first;
+                    if (k->isBad() || k->mnId > maxKFid) continue;
+                    const auto it = kf_index.find(k);
+                    if (it == kf_index.end()) continue;                     // no vertex with that id in the reference's graph either (it would dereference NULL)
+                    plo_kf[fam].push_back(it->second); plo_plane[fam].push_back(plane_index[pMP]);
+                    for (int c = 0; c < 4; ++c) plo_meas[fam].push_back(k->mvPlaneCoefficients[o.second].at<float>(c));
+                    plane_obs[fam].push_back(PlaneObs{k, pMP});
+                }
+            }
+
+        pslam_lba_problem P;
+        std::memset(&P, 0, sizeof P);
+        P.n_kf = (int)kfs.size(); P.kf_Tcw = kf_Tcw.data(); P.kf_fixed = kf_fixed.data(); P.kf_K = kf_K.data();
+        P.n_points = (int)pts.size(); P.pt_Xw = pt_Xw.data();
+        P.n_pt_obs = (int)pt_obs.size(); P.pt_obs_kf = po_kf.data(); P.pt_obs_pt = po_pt.data(); P.pt_obs_uvr = po_uvr.data(); P.pt_obs_inv_sigma2 = po_is2.data();
+        P.n_lines = (int)lines.size(); P.line_Xw = line_Xw.data();
+        P.n_line_obs = (int)line_obs.size(); P.line_obs_kf = lo_kf.data(); P.line_obs_line = lo_line.data(); P.line_obs_l = lo_l.data();
+        P.n_planes = (int)planes.size(); P.plane_Xw = plane_Xw.data();
+        for (int fam = 0; fam < 3; ++fam) {
+            P.n_plane_obs[fam] = (int)plane_obs[fam].size(); P.plane_obs_kf[fam] = plo_kf[fam].data(); P.plane_obs_plane[fam] = plo_plane[fam].data();
+            P.plane_obs_meas[fam] = plo_meas[fam].data();
+        }
+        P.angle_info = Planar_SLAM::Config::Get<double>("Plane.AngleInfo"); P.dist_info = Planar_SLAM::Config::Get<double>("Plane.DistanceInfo");
+        P.plane_chi = Planar_SLAM::Config::Get<double>("Plane.Chi"); P.vp_chi = Planar_SLAM::Config::Get<double>("Plane.VPChi");
+        std::vector<float> r_T(kfs.size() * 16), r_pt(pts.size() * 3 + 3), r_pl(planes.size() * 4 + 4);
+        std::vector<double> r_line(lines.size() * 6 + 6);
+        std::vector<uint8_t> e_pt(pt_obs.size() + 1), e_line(line_obs.size() + 1), e_pl[3];
+        pslam_lba_result R;
+        std::memset(&R, 0, sizeof R);
+        R.kf_Tcw = r_T.data(); R.pt_Xw = r_pt.data(); R.line_Xw = r_line.data(); R.plane_Xw = r_pl.data(); R.erase_pt = e_pt.data(); R.erase_line = e_line.data();
+        for (int fam = 0; fam < 3; ++fam) { e_pl[fam].assign(plane_obs[fam].size() + 1, 0); R.erase_plane[fam] = e_pl[fam].data(); }
+        pslam_ctx* c = context();
+        if (pslam_local_bundle_adjustment(c, &P, &R) != PSLAM_OK) throw std::runtime_error(pslam_last_error(c));
+
+        std::unique_lock<std::mutex> lock(pMap->mMutexMapUpdate);
+        // vToErase lists monocular edges before stereo ones (:2462-2490); a (key frame, point) pair occurs once, so only the order of the cascades differs
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t j = 0; j < pt_obs.size(); ++j) {
+                if (!e_pt[j] || (po_uvr[3 * j + 2] < 0) != (pass == 0)) continue;
+                pt_obs[j].kf->EraseMapPointMatch(pt_obs[j].p); pt_obs[j].p->EraseObservation(pt_obs[j].kf);
+            }
+        for (size_t j = 0; j < line_obs.size(); ++j) if (e_line[j]) { line_obs[j].kf->EraseMapLineMatch(line_obs[j].l); line_obs[j].l->EraseObservation(line_obs[j].kf); }
+        for (size_t j = 0; j < plane_obs[0].size(); ++j) if (e_pl[0][j]) { plane_obs[0][j].kf->EraseMapPlaneMatch(plane_obs[0][j].q); plane_obs[0][j].q->EraseObservation(plane_obs[0][j].kf); }
+        for (size_t j = 0; j < plane_obs[1].size(); ++j) if (e_pl[1][j]) { plane_obs[1][j].kf->EraseMapVerticalPlaneMatch(plane_obs[1][j].q); plane_obs[1][j].q->EraseVerObservation(plane_obs[1][j].kf); }
+        for (size_t j = 0; j < plane_obs[2].size(); ++j) if (e_pl[2][j]) { plane_obs[2][j].kf->EraseMapParallelPlaneMatch(plane_obs[2][j].q); plane_obs[2][j].q->EraseParObservation(plane_obs[2][j].kf); }
+        for (KeyFrame* k : lLocalKeyFrames) {
+            cv::Mat T(4, 4, CV_32F);
+            const float* t = &r_T[(size_t)kf_index[k] * 16];
+            for (int i = 0; i < 16; ++i) T.at<float>(i / 4, i % 4) = t[i];
+            k->SetPose(T);
+        }
+        for (MapPoint* pMP : lLocalMapPoints) {
+            cv::Mat X(3, 1, CV_32F);
+            for (int c2 = 0; c2 < 3; ++c2) X.at<float>(c2) = r_pt[(size_t)pt_index[pMP] * 3 + c2];
+            pMP->SetWorldPos(X);
+            pMP->UpdateNormalAndDepth();
+        }
+        for (MapLine* pML : lLocalMapLines) {
+            Planar_SLAM::Vector6d LinePos;
+            for (int c2 = 0; c2 < 6; ++c2) LinePos(c2) = r_line[(size_t)line_index[pML] * 6 + c2];
+            pML->SetWorldPos(LinePos);
+            pML->UpdateAverageDir();
+        }
+        for (MapPlane* pMP : lLocalMapPlanes) {
+            cv::Mat X(4, 1, CV_32F);
+            for (int c2 = 0; c2 < 4; ++c2) X.at<float>(c2) = r_pl[(size_t)plane_index[pMP] * 4 + c2];
+            pMP->SetWorldPos(X);
+            pMP->UpdateCoefficientsAndPoints();
+        }
+    }
 
 private:
     static int run(Frame* pFrame, bool translation_only) {

@@ -529,13 +529,12 @@ extern "C" int DRV(full_pose_optimization)(const pslam_pose_problem* P, const fl
     return n;
 }
 
-#ifndef PSLAM_ADAPTER_BUILD
 // Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*) src/Optimizer.cc:1853-2678 called as it is on a KeyFrame / MapPoint / MapLine / MapPlane graph
 // built from a pslam_lba_problem.  The current key frame is the last one; its covisible list holds every non-fixed key frame plus key frame 0 (which the
 // reference fixes through mnId == 0); the other fixed key frames are left for the function to discover through the observations.  Observation j of a
 // family sits in feature slot j of its key frame.  Read back: the poses / positions the function wrote (float, Converter::toCvMat), which slots it cleared
 // (erase_*: the observation was erased, or its landmark went bad - *_bad tells which) - everything in between is the reference's code.
-extern "C" int ref_full_local_bundle_adjustment(const pslam_lba_problem* P, pslam_lba_result* R, uint8_t* pt_bad, uint8_t* line_bad, uint8_t* plane_bad) {
+extern "C" int DRV(full_local_bundle_adjustment)(const pslam_lba_problem* P, pslam_lba_result* R, uint8_t* pt_bad, uint8_t* line_bad, uint8_t* plane_bad) {
     set_plane_settings(P->angle_info, P->dist_info, 0, 0, P->plane_chi, P->vp_chi);
     World w;
     w.anchor->mnId = 1000000;
@@ -619,7 +618,7 @@ extern "C" int ref_full_local_bundle_adjustment(const pslam_lba_problem* P, psla
             else { kf->mvpParallelPlanes[slot] = q; q->AddParObservation(kf, slot); }
         }
     bool stop = false;
-    Optimizer::LocalBundleAdjustment(kfs[cur], &stop, &w.map);
+    DRV_OPTIMIZER::LocalBundleAdjustment(kfs[cur], &stop, &w.map);
     for (int k = 0; k < P->n_kf; ++k) {
         cv::Mat T = kfs[k]->GetPose();
         for (int i = 0; i < 16; ++i) { R->kf_Tcw[16 * k + i] = T.at<float>(i / 4, i % 4); R->kf_Tcw_d[16 * k + i] = T.at<float>(i / 4, i % 4); }
@@ -652,6 +651,7 @@ extern "C" int ref_full_local_bundle_adjustment(const pslam_lba_problem* P, psla
     return 0;
 }
 
+#ifndef PSLAM_ADAPTER_BUILD
 // Frame::ComputeStereoFromRGBD(imDepth) src/Frame.cc:603-621 and Frame::isLineGood(imGray, imDepth, K) src/Frame.cc:189-267 called as they are (with the
 // reference's src/LineExtractor.cpp and libc rand()) on a Frame holding the key points / key lines.
 extern "C" void ref_full_compute_stereo_from_rgbd(int n, const float* keys_xy, const float* keys_un_xy, const float* depth, int w, int h, float bf, float* u_right, float* z) {

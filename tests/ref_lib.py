@@ -393,17 +393,18 @@ def ref_full_pose_optimization(p: dict, translation_only: bool = False, impl: st
                 outlier_par=o[3][:s.n_par], outlier_ver=o[4][:s.n_ver])
 
 
-def ref_full_local_bundle_adjustment(p: dict) -> dict:
+def ref_full_local_bundle_adjustment(p: dict, impl: str = "ref") -> dict:
     """Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*) ITSELF (src/Optimizer.cc compiled unmodified into libmatch_ref.so) on a key-frame / landmark graph
     built from a planarslam_b200.synth_lba problem.  Keys of oracle_lib.local_bundle_adjustment (positions as the reference wrote them back: float) plus
     pt_bad / line_bad / plane_bad (landmarks the erasures turned bad: all their slots are cleared, not only the erased observation's)."""
     from planarslam_b200 import lba as _lba
-    L = match_lib()
-    L.ref_full_local_bundle_adjustment.argtypes = [C.c_void_p] * 5
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "full_local_bundle_adjustment")          # impl="adp": pslam_adapter::ref::Optimizer::LocalBundleAdjustment on the same object graph
+    fn.argtypes = [C.c_void_p] * 5
     s = _lba.problem_struct(p)
     r, o = _lba.result_struct(s)
     bad = [np.zeros(max(n, 1), np.uint8) for n in (s.n_points, s.n_lines, s.n_planes)]
-    rc = L.ref_full_local_bundle_adjustment(C.byref(s), C.byref(r), *[b.ctypes.data for b in bad])
+    rc = fn(C.byref(s), C.byref(r), *[b.ctypes.data for b in bad])
     assert rc == 0, rc
     out = _lba.finish(r, o)
     out["pt_bad"], out["line_bad"], out["plane_bad"] = bad[0][:s.n_points], bad[1][:s.n_lines], bad[2][:s.n_planes]

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import ref_lib
-from planarslam_b200 import synth_lines, synth_pose
+from planarslam_b200 import synth_lba, synth_lines, synth_pose
 from test_oracle_match_ref import PLANE_TH, last_case, map_case
 from test_oracle_planematch import _scenario as plane_scenario
 
@@ -109,3 +109,32 @@ def test_keyframe_database_adapter():
         ac, aw, as_ = ref_lib.ref_detect_relocalization_candidates(db, stale, impl="adp")
         assert np.array_equal(ac, rc) and np.array_equal(aw, rw) and np.array_equal(as_, rs), case
     assert found > 5
+
+
+def test_optimizer_local_bundle_adjustment_adapter():
+    """Optimizer::LocalBundleAdjustment(KeyFrame*, bool*, Map*) of the reference and of the adapter on the same KeyFrame / MapPoint / MapLine / MapPlane graph: the
+    slots each clears (erased observations and the bad-landmark cascade they trigger through the reference's own EraseObservation) must be identical, poses and
+    landmark positions agree like the C ABI does with the reference (tests/test_cuda_vs_reference_functions_gpu.py)."""
+    from test_oracle_lba_ref import SMALL
+    small = dict(SMALL, line_kf_quirk=True)
+    cases = [dict(seed=s, **small) for s in (1, 10)] + [dict(seed=2, n_kf=8, n_points=300, n_pt_obs=900, n_lines=0, n_line_obs=0, n_plane_obs=(0, 0, 0))]
+    hard = [dict(seed=20, **small, line_norm3=False, outlier_frac=0.2, plane_outlier_frac=0.25)]
+    n_cleared = 0
+    for kw in cases + hard:
+        p = synth_lba.restrict_to_local_planes(synth_lba.make_lba_problem(**kw))
+        r = ref_lib.ref_full_local_bundle_adjustment(p)
+        a = ref_lib.ref_full_local_bundle_adjustment(p, impl="adp")
+        for k in ("pt_bad", "line_bad", "plane_bad", "erase_pt"):
+            assert np.array_equal(a[k], r[k]), (kw, k)
+        if len(p["line_obs_line"]):
+            assert np.array_equal(a["erase_line"], r["erase_line"]), kw
+        for t in range(3):
+            if len(p["plane_obs_plane"][t]):
+                assert np.array_equal(a["erase_plane"][t], r["erase_plane"][t]), (kw, t)
+        tol = (2e-5, 5e-5) if kw in hard else (1e-6, 1e-6)
+        for k in range(len(a["kf_Tcw_d"])):
+            da, dt = synth_pose.pose_error(a["kf_Tcw_d"][k], r["kf_Tcw_d"][k])
+            assert da < tol[0] and dt < tol[1], (kw, k, da, dt)
+        assert np.median(np.abs(a["pt_Xw_d"] - r["pt_Xw_d"]).max(1)) < (2e-5 if kw in hard else 5e-6), kw
+        n_cleared += int(r["erase_pt"].sum())
+    assert n_cleared > 50
