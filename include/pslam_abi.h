@@ -441,7 +441,7 @@ int pslam_lsd_debug_stage(pslam_ctx* ctx, int frame, int32_t* dims /* W, H */, u
  * rand(): the reference draws from the process-wide libc stream; here each frame has its own glibc-compatible stream, started
  * with srand(seed[f]) and advanced by skip[f] draws (skip may be NULL).  n_drawn[f] returns the number of rand() calls the frame
  * made, so a caller that wants the reference's single stream passes seed = its srand seed, skip = draws made so far, and adds
- * n_drawn.  depth: raw uint16 [nframes][height][width]; metres = (float)raw * depth_factor (imDepth.convertTo(CV_32F, factor)).
+ * n_drawn (large skips cost O(log skip): the generator's recurrence x^31 = x^28 + 1 is jumped, not stepped).  depth: raw uint16 [nframes][height][width]; metres = (float)raw * depth_factor (imDepth.convertTo(CV_32F, factor)).
  * cam: fx, fy, cx, cy (float, as Frame::fx ... are). */
 typedef struct pslam_line3d {
     double A[3], B[3];       /* mvLines3D[i]; zero unless valid */

@@ -29,6 +29,7 @@ struct L3dKeyLine {                      // cv::line_descriptor::KeyLine, 68 byt
 struct L3dPoint { double pos[3]; double DU[9]; };
 
 struct L3dRand { int32_t state[31]; int f, b; int32_t drawn; };
+#define L3D_JUMP_ABOVE 4096        // draws to discard above which l3d_srand jumps ahead instead of stepping
 
 L3D_HD inline int32_t l3d_rand(L3dRand& g) {                 // glibc random_r, TYPE_3
     const uint32_t val = (uint32_t)g.state[g.f] + (uint32_t)g.state[g.b];
@@ -49,7 +50,42 @@ L3D_HD inline void l3d_srand(L3dRand& g, uint32_t seed, int skip) {       // gli
         g.state[i] = word;
     }
     g.f = 3; g.b = 0; g.drawn = 0;
-    for (int i = 0; i < 310 + skip; ++i) (void)l3d_rand(g);
+    const long long D = 310LL + (skip > 0 ? skip : 0);            // glibc discards 310 draws after seeding
+    if (D <= L3D_JUMP_ABOVE) {
+        for (int i = 0; i < (int)D; ++i) (void)l3d_rand(g);
+    } else {
+        // Jump ahead in O(log D): draw k adds state[k % 31] to state[(k + 3) % 31], so with t_0..t_30 = (s_3 .. s_30, s_0, s_1, s_2) every later value obeys
+        // t_{k+31} = t_k + t_{k+28} (mod 2^32): a linear recurrence with characteristic polynomial x^31 = x^28 + 1.  With p = x^D mod that polynomial,
+        // t_{D+j} = sum_i p_i t_{i+j}; after D draws the value t_{k+31} sits in state[(3 + k) % 31] for k = D - 31 .. D - 1.  (A replay driver passes the number
+        // of draws its sequence has made so far: the loop above would cost that many steps in the one thread that owns the frame.)
+        uint32_t t[61];
+        for (int i = 0; i < 28; ++i) t[i] = (uint32_t)g.state[i + 3];
+        for (int i = 0; i < 3; ++i) t[28 + i] = (uint32_t)g.state[i];
+        for (int i = 31; i < 61; ++i) t[i] = t[i - 31] + t[i - 3];
+        uint32_t p[31], q[61];
+        for (int i = 0; i < 31; ++i) p[i] = 0;
+        p[0] = 1;
+        int top = 62;
+        while (top > 0 && !((D >> (top - 1)) & 1)) --top;
+        for (int bit = top - 1; bit >= 0; --bit) {
+            for (int i = 0; i < 61; ++i) q[i] = 0;               // q = p * p
+            for (int i = 0; i < 31; ++i) { const uint32_t a = p[i]; if (a) for (int j = 0; j < 31; ++j) q[i + j] += a * p[j]; }
+            for (int d = 60; d >= 31; --d) { const uint32_t c = q[d]; q[d - 3] += c; q[d - 31] += c; }        // x^d = x^(d-3) + x^(d-31)
+            if ((D >> bit) & 1) {                                 // ... * x: the coefficient pushed to x^31 comes back as x^28 + 1
+                const uint32_t c = q[30];
+                for (int i = 30; i > 0; --i) q[i] = q[i - 1];
+                q[0] = c; q[28] += c;
+            }
+            for (int i = 0; i < 31; ++i) p[i] = q[i];
+        }
+        for (int j = 0; j < 31; ++j) {
+            uint32_t v = 0;
+            for (int i = 0; i < 31; ++i) v += p[i] * t[i + j];
+            const long long k = D - 31 + j;                       // t_{D+j} = t_{k+31}
+            g.state[(int)((3 + k) % 31)] = (int32_t)v;
+        }
+        g.f = (int)((3 + D) % 31); g.b = (int)(D % 31);
+    }
     g.drawn = 0;
 }
 

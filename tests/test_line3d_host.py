@@ -45,6 +45,11 @@ def test_body_rand_matches_oracle(host_lib):
         out = np.zeros(500, np.int32)
         host_lib.host_glibc_rand(seed, skip, 500, out.ctypes.data)
         assert np.array_equal(out, oracle_lib.glibc_rand(seed, 500 + skip)[skip:]), (seed, skip)
+    # the jump-ahead path of l3d_srand (more than L3D_JUMP_ABOVE = 4096 discarded draws: x^D modulo x^31 - x^28 - 1) against the stepping oracle
+    for seed, skip in ((1, 3787), (1, 3786), (1, 3785), (1, 4097), (7, 5000), (1, 65536), (123456789, 1000003), (2 ** 31 + 5, 3141592)):
+        out = np.zeros(200, np.int32)
+        host_lib.host_glibc_rand(seed, skip, 200, out.ctypes.data)
+        assert np.array_equal(out, oracle_lib.glibc_rand(seed, 200 + skip)[skip:]), (seed, skip)
 
 
 def test_body_matches_oracle_on_synthetic_frames(host_lib):
