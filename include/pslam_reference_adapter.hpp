@@ -19,6 +19,7 @@
 //   int ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)                include/ORBmatcher.h:53  src/ORBmatcher.cc:160-292
 //   int ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)             include/ORBmatcher.h:56  src/ORBmatcher.cc:526-659
 //   int LSDmatcher::SearchByProjection(Frame&, const vector<MapLine*>&, float th)     include/LSDmatcher.h:24  src/LSDmatcher.cpp:141-211
+//   int LSDmatcher::SearchByDescriptor(KeyFrame*, Frame&, vector<MapLine*>&)          include/LSDmatcher.h:21  src/LSDmatcher.cpp:242-279
 //   int PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)       include/PlaneMatcher.h:18 src/PlaneMatcher.cpp:10-67
 //   KeyFrameDatabase::add / erase / clear / DetectLoopCandidates(KeyFrame*, float) / DetectRelocalizationCandidates(Frame*)
 //                                                                                     include/KeyFrameDatabase.h:43-75  src/KeyFrameDatabase.cc:38-305
@@ -515,6 +516,33 @@ public:
         if (n < 0) throw std::runtime_error(pslam_last_error(c));
         for (int i = 0; i < nf; ++i) if (assigned[i] >= 0) F.mvpMapLines[i] = vpMapLines[assigned[i]];
         return n;
+    }
+
+    // Matching of the key frame's map lines to the frame's key lines by LBD descriptor: cv::BFMatcher(NORM_HAMMING).knnMatch(k = 2) + the 1 / 1.5 ratio test
+    // (include/LSDmatcher.h:21, src/LSDmatcher.cpp:242-279; the thresholds lineDescriptorMAD computes there are never read)
+    int SearchByDescriptor(KeyFrame* pKF, Frame& currentF, std::vector<MapLine*>& vpMapLineMatches) {
+        const std::vector<MapLine*> vpMapLinesKF = pKF->GetMapLineMatches();
+        vpMapLineMatches = std::vector<MapLine*>(currentF.NL, static_cast<MapLine*>(NULL));
+        const cv::Mat& ldesc1 = pKF->mLineDescriptors;
+        const cv::Mat& ldesc2 = currentF.mLdesc;
+        const int nq = ldesc1.rows, nt = ldesc2.rows;
+        if (nq == 0 || nt < 2) return 0;                                  // (the reference indexes lmatches[i][1]: it needs two frame lines)
+        std::vector<uint8_t> q((size_t)nq * 32), t((size_t)nt * 32);
+        for (int i = 0; i < nq; ++i) std::memcpy(&q[32 * (size_t)i], ldesc1.ptr(i), 32);
+        for (int i = 0; i < nt; ++i) std::memcpy(&t[32 * (size_t)i], ldesc2.ptr(i), 32);
+        std::vector<int32_t> idx2((size_t)nq * 2), dist2((size_t)nq * 2);
+        pslam_ctx* c = context();
+        if (pslam_hamming_knn2(c, q.data(), nq, t.data(), nt, idx2.data(), dist2.data(), nullptr, nullptr) != PSLAM_OK) throw std::runtime_error(pslam_last_error(c));
+        const float minRatio = 1.0f / 1.5f;
+        int nmatches = 0;
+        for (int i = 0; i < nq; ++i) {
+            const double dist_12 = (float)dist2[2 * i] / (float)dist2[2 * i + 1];
+            if (dist_12 < minRatio) {
+                MapLine* mapLine = i < (int)vpMapLinesKF.size() ? vpMapLinesKF[i] : static_cast<MapLine*>(NULL);
+                if (mapLine) { vpMapLineMatches[idx2[2 * i]] = mapLine; nmatches++; }
+            }
+        }
+        return nmatches;
     }
 
 private:

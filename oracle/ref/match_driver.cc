@@ -427,6 +427,36 @@ extern "C" int DRV(line_search_by_projection)(int nf, const float* pt, const flo
     return n;
 }
 
+// LSDmatcher::SearchByDescriptor(KeyFrame*, Frame&, vector<MapLine*>&)   src/LSDmatcher.cpp:242-279: kf_desc [n_kf][32] = the key frame's mLineDescriptors, kf_has_ml[i] = it
+// holds a map line for key line i, f_desc [n_f][32] = the frame's mLdesc; match[j] = key line of the key frame whose map line is stored into vpMapLineMatches[j] (-1: NULL)
+extern "C" int DRV(line_search_by_descriptor)(int n_kf, const uint8_t* kf_desc, const uint8_t* kf_has_ml, int n_f, const uint8_t* f_desc, int32_t* match) {
+    World w;
+    Vector6d zero6 = Vector6d::Zero();
+    Frame K;
+    K.N = 0; K.NL = n_kf;
+    K.mvKeylinesUn.resize(n_kf); K.mvKeyLineFunctions.assign(n_kf, Eigen::Vector3d(0, 0, 1));
+    K.mLdesc = cv::Mat(n_kf, 32, CV_8U);
+    for (int i = 0; i < n_kf; ++i) std::memcpy(K.mLdesc.ptr(i), kf_desc + 32 * (size_t)i, 32);
+    K.mvpMapLines.assign(n_kf, static_cast<MapLine*>(NULL));
+    K.SetPose(cv::Mat::eye(4, 4, CV_32F));
+    std::vector<MapLine*> own;
+    std::unordered_map<MapLine*, int> index;
+    for (int i = 0; i < n_kf; ++i)
+        if (kf_has_ml[i]) { MapLine* p = new MapLine(zero6, w.anchor, &w.map); own.push_back(p); index[p] = i; K.mvpMapLines[i] = p; }
+    KeyFrame* pKF = new KeyFrame(K, &w.map, static_cast<KeyFrameDatabase*>(NULL));
+    Frame F;
+    F.NL = n_f;
+    F.mLdesc = cv::Mat(n_f, 32, CV_8U);
+    for (int i = 0; i < n_f; ++i) std::memcpy(F.mLdesc.ptr(i), f_desc + 32 * (size_t)i, 32);
+    DRV_LSDMATCHER matcher;
+    std::vector<MapLine*> vpMapLineMatches;
+    const int n = matcher.SearchByDescriptor(pKF, F, vpMapLineMatches);
+    for (int j = 0; j < n_f; ++j) match[j] = vpMapLineMatches[j] ? index.at(vpMapLineMatches[j]) : -1;
+    delete pKF;
+    for (MapLine* p : own) delete p;
+    return n;
+}
+
 // PlaneMatcher::SearchMapByCoefficients(Frame&, const vector<MapPlane*>&)   src/PlaneMatcher.cpp:10-82 (Frame::ComputePlaneWorldCoeff src/Frame.cc:815-820)
 extern "C" int DRV(plane_match)(const float* Tcw, int n_frame, const float* frame_coef, int n_map, const float* map_coef, const uint8_t* map_bad, const int32_t* pts_off,
                                const float* pts, float dTh, float aTh, float verTh, float parTh, int32_t* match, int32_t* ver, int32_t* par) {

@@ -488,3 +488,15 @@ def ref_search_by_bow_kf(kf1: dict, kf2: dict, nnratio: float = 0.75, check_orie
     import oracle_lib
     lib, pre = _impl(impl)
     return oracle_lib._bow_kf_call(getattr(lib, pre + "search_by_bow_kf"), kf1, kf2, nnratio, check_orientation)
+
+
+def ref_line_search_by_descriptor(kf_desc, kf_has_ml, f_desc, impl: str = "ref"):
+    """LSDmatcher::SearchByDescriptor(KeyFrame*, Frame&, vector<MapLine*>&) by the reference's own code (impl="adp": the product's adapter).  Returns (nmatches,
+    match [n_f]: key line of the key frame whose map line the call stores into vpMapLineMatches[j], -1 NULL)."""
+    lib, pre = _impl(impl)
+    fn = getattr(lib, pre + "line_search_by_descriptor")
+    fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    q, h, t = np.ascontiguousarray(kf_desc, np.uint8), np.ascontiguousarray(kf_has_ml, np.uint8), np.ascontiguousarray(f_desc, np.uint8)
+    match = np.full(max(len(t), 1), -1, np.int32)
+    n = fn(len(q), q.ctypes.data, h.ctypes.data, len(t), t.ctypes.data, match.ctypes.data)
+    return n, match[:len(t)]

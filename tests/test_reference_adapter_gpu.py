@@ -138,3 +138,22 @@ def test_optimizer_local_bundle_adjustment_adapter():
         assert np.median(np.abs(a["pt_Xw_d"] - r["pt_Xw_d"]).max(1)) < (2e-5 if kw in hard else 5e-6), kw
         n_cleared += int(r["erase_pt"].sum())
     assert n_cleared > 50
+
+
+def test_lsdmatcher_search_by_descriptor_adapter():
+    tot = 0
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        n_kf, n_f = 40 - seed, 40 - 2 * seed
+        kf_desc = rng.integers(0, 256, (n_kf, 32), dtype=np.uint8)
+        f_desc = rng.integers(0, 256, (n_f, 32), dtype=np.uint8)
+        src = rng.permutation(n_kf)[:n_f * 2 // 3]                          # two thirds of the frame lines re-observe a key-frame line (a few flipped bits)
+        flips = np.packbits(rng.random((len(src), 256)) < 0.05, axis=1)
+        f_desc[:len(src)] = kf_desc[src] ^ flips
+        f_desc[-1] = f_desc[0]                                              # a duplicate: equal best and second-best distances for its source
+        has_ml = (rng.random(n_kf) < 0.8).astype(np.uint8)
+        rn, rm = ref_lib.ref_line_search_by_descriptor(kf_desc, has_ml, f_desc)
+        an, am = ref_lib.ref_line_search_by_descriptor(kf_desc, has_ml, f_desc, impl="adp")
+        assert an == rn and np.array_equal(am, rm), seed
+        tot += rn
+    assert tot > 60
