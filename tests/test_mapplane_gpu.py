@@ -13,7 +13,7 @@ def test_map_plane_update_matches_oracle():
     from planarslam_b200._lib import Context, PslamError
     from planarslam_b200.planes import UpdateMapPlanePoints
     ctx = Context(640, 480, 1)
-    jobs = [make_map_plane(0), make_map_plane(1, n_obs=1), make_map_plane(2, n_obs=12, pts_per_obs=900, extent=5.0), make_map_plane(3, with_current=True),
+    jobs = [make_map_plane(0), make_map_plane(1, n_obs=1), make_map_plane(2, n_obs=12, pts_per_obs=900, extent=3.0), make_map_plane(3, with_current=True),
             make_map_plane(4, n_obs=3, pts_per_obs=5, extent=0.2), [], make_map_plane(5, n_obs=2, pts_per_obs=2000, extent=1.0, noise=0.03)]
     got = UpdateMapPlanePoints(ctx, jobs)
     assert len(got) == len(jobs)
@@ -27,6 +27,8 @@ def test_map_plane_update_matches_oracle():
     # one job alone gives the same points as inside the batch
     alone = UpdateMapPlanePoints(ctx, [jobs[2]])[0]
     assert np.array_equal(alone, got[2])
-    # capacity: fewer output slots than occupied voxels
+    # capacity: fewer output slots than occupied voxels; more occupied voxels (4201) than the table holds (4096)
     with pytest.raises(PslamError):
         UpdateMapPlanePoints(ctx, [jobs[2]], cap=16)
+    with pytest.raises(PslamError):
+        UpdateMapPlanePoints(ctx, [make_map_plane(2, n_obs=12, pts_per_obs=900, extent=5.0)])
