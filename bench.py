@@ -670,7 +670,7 @@ def main():
             main.wait_event(e)
 
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(4)
+    pool = ThreadPoolExecutor(9)
 
     def step_e2e():
         # the three stage families are independent per frame; a replay driver calls the (blocking, host-pointer) ABI
@@ -840,13 +840,19 @@ def main():
             c.close()
         torch.cuda.empty_cache()
         from planarslam_b200.frame import ConstructFrames, FrameOutputs
-        fctx = [Context(W, H, SUB_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(2)]
-        fout = [FrameOutputs(c, SUB_BATCH, MAX_LINES, PP_CAP, normals=True, pinned=True) for c in fctx]
+        # PSLAM_E2E_CONTEXTS contexts (default 4) of 2 * SUB_BATCH / contexts frames each - the device memory of two full sub-batches either way.  With two contexts a
+        # copy phase of one leaves the other's half-wave kernels alone on the GPU; with four, two or three batches are always computing while one copies.
+        E2E_CTX = max(2, int(os.environ.get("PSLAM_E2E_CONTEXTS", "4")))
+        E2E_BATCH = max(1, 2 * SUB_BATCH // E2E_CTX)
+        E2E_CALLS = (FRAMES_PER_STEP + E2E_BATCH - 1) // E2E_BATCH
+        fctx = [Context(W, H, E2E_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(E2E_CTX)]
+        fout = [FrameOutputs(c, E2E_BATCH, MAX_LINES, PP_CAP, normals=True, pinned=True) for c in fctx]
 
         def e_frames(t):
             torch.cuda.set_device(local_rank)
-            for sb in range(t, SUBS_PER_STEP, 2):
-                ConstructFrames(fctx[t], h_gray[sb * SUB_BATCH].data_ptr(), h_depth[sb * SUB_BATCH].data_ptr(), fout[t], DEPTH_FACTOR, BF, DIST_TH, 1, nframes=SUB_BATCH)
+            for sb in range(t, E2E_CALLS, E2E_CTX):
+                o = sb * E2E_BATCH
+                ConstructFrames(fctx[t], h_gray[o].data_ptr(), h_depth[o].data_ptr(), fout[t], DEPTH_FACTOR, BF, DIST_TH, 1, nframes=min(E2E_BATCH, FRAMES_PER_STEP - o))
 
         def e_pose2():
             torch.cuda.set_device(local_rank)
@@ -854,7 +860,7 @@ def main():
                 opt.PoseOptimizationBatch(probs)
 
         def step_e2e():
-            jobs = [pool.submit(e_frames, 0), pool.submit(e_frames, 1)] + ([pool.submit(e_pose2)] if "pose" in STAGES else [])
+            jobs = [pool.submit(e_frames, t) for t in range(E2E_CTX)] + ([pool.submit(e_pose2)] if "pose" in STAGES else [])
             for f in jobs:
                 f.result()
     step_e2e()
@@ -871,8 +877,9 @@ def main():
     e2e_val = world * FRAMES_PER_STEP * e2e_steps / float(t.item())
     if frame_e2e:
         h2d = FRAMES_PER_STEP * 3 * W * H + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
-        d2h = SUBS_PER_STEP * fout[0].nbytes() + ("pose" in STAGES) * FRAMES_PER_STEP * (64 + 1046 + 4)
-        e2e_call = "pslam_frame_construct_batch (Frame constructor: one upload of gray + depth per frame) on two contexts / host threads + pslam_pose_optimization_batch"
+        d2h = E2E_CALLS * fout[0].nbytes() + ("pose" in STAGES) * FRAMES_PER_STEP * (64 + 1046 + 4)
+        e2e_call = (f"pslam_frame_construct_batch (Frame constructor: one upload of gray + depth per frame) on {E2E_CTX} contexts / host threads, {E2E_BATCH} frames per call "
+                    "+ pslam_pose_optimization_batch")
     else:
         h2d = FRAMES_PER_STEP * (("orb" in STAGES) * W * H + ("lsd" in STAGES) * W * H + ("peac" in STAGES) * 2 * W * H) + ("pose" in STAGES) * SUBS_PER_STEP * pose_h2d
         d2h = FRAMES_PER_STEP * (("orb" in STAGES) * (cap * 60 + 8) + ("peac" in STAGES) * (4 * W * H + maxp * PLANE_DTYPE.itemsize + 4) +

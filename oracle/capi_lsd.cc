@@ -109,3 +109,9 @@ void orc_lbd_compute(const uint8_t* img, int w, int h, int stride, const void* k
     oracle::lbd_compute(oracle::Img8{img, w, h, stride}, (const oracle::KeyLine*)keylines, n, lbd72, desc);
 }
 }
+
+#include "detmath.h"
+// oracle::det_sincos (detmath.h) on an array: what the product's lsd_detsincos.h must reproduce bit for bit
+extern "C" void orc_det_sincos(const double* x, int n, double* s, double* c) {
+    for (int i = 0; i < n; ++i) oracle::det_sincos(x[i], s[i], c[i]);
+}

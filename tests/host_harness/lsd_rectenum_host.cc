@@ -22,3 +22,9 @@ extern "C" int host_lsd_cv4_spans(const double* rect, int W, int H, int32_t* row
     }
     return m;
 }
+
+// planarslam_b200/csrc/lsd_detsincos.h (the deterministic sincos the device code and the host-built seed table share), compiled for the host
+#include "lsd_detsincos.h"
+extern "C" void host_lsd_sincos(const double* x, int n, double* s, double* c) {
+    for (int i = 0; i < n; ++i) lsd_sincos_body(x[i], s[i], c[i]);
+}

@@ -75,3 +75,23 @@ def test_rectenum_counts_match_cv2_on_known_rectangle(host_lib):
     a = _spans(host_lib.host_lsd_cv4_spans, r, 512, 384)
     assert int((a[:, 2] - a[:, 1] + 1).sum()) == 24
     assert a[0, 0] == 191 and a[-1, 0] == 199                                 # row 200 (ceil of the bottom corner) is visited but empty
+
+
+def test_detsincos_header_matches_oracle(host_lib):
+    """planarslam_b200/csrc/lsd_detsincos.h compiled for the host == oracle/detmath.h bit for bit: the seed (cos, sin) table of k_lsd_regions is built from it on
+    the host, the rectangle axes use it on the device.  Inputs: every angle the detector can produce for a gradient (degrees as float, times pi / 180) plus
+    rectangle-axis angles up to 3 pi."""
+    import ctypes as C
+    import oracle_lib
+    host_lib.host_lsd_sincos.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L = oracle_lib.lib()
+    L.orc_det_sincos.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    deg = np.concatenate([rng.uniform(0, 360, 200000).astype(np.float32), np.arange(0, 360, 0.25, dtype=np.float32)])
+    x = np.concatenate([deg.astype(np.float64) * 0.0174532925199432957692, rng.uniform(-3 * np.pi, 3 * np.pi, 100000), [0.0, np.pi / 2, np.pi, 2 * np.pi, -np.pi / 2]])
+    x = np.ascontiguousarray(x)
+    hs, hc, os_, oc = (np.zeros(len(x)) for _ in range(4))
+    host_lib.host_lsd_sincos(x.ctypes.data, len(x), hs.ctypes.data, hc.ctypes.data)
+    L.orc_det_sincos(x.ctypes.data, len(x), os_.ctypes.data, oc.ctypes.data)
+    assert np.array_equal(hs.view(np.uint64), os_.view(np.uint64)) and np.array_equal(hc.view(np.uint64), oc.view(np.uint64))
+    assert np.abs(hs - np.sin(x)).max() < 3e-16 and np.abs(hc - np.cos(x)).max() < 3e-16
