@@ -512,6 +512,8 @@ def main():
     cap = c_orb.L.pslam_orb_max_keypoints(c_orb.h)
     maxp = c_peac.L.pslam_peac_max_planes(c_peac.h)
     L = c_orb.L
+    L.pslam_lsd_fast_division_active.argtypes = [C.c_void_p]
+    lsd_fast_div = int(L.pslam_lsd_fast_division_active(c_lsd.h)) if "lsd" in STAGES else None
 
     d_gray = h_gray.to(dev)                                            # [FRAMES_PER_STEP, H, W] resident in HBM
     d_depth = h_depth.to(dev)
@@ -937,7 +939,8 @@ def main():
                                  "sample": f"{' + '.join(STAGES)}: {best['frames']} frames in {best['seconds']} s, one pinned process per host core "
                                            f"({modes['host_cores']}), -O3 -march=x86-64-v3 (oracle/Makefile fast); modes = BASELINE.md section 3"},
                 "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP,
-                "keylines_per_frame": n_keylines / FRAMES_PER_STEP if n_keylines is not None else None, "exchange": xch_info, "aux": aux}
+                "keylines_per_frame": n_keylines / FRAMES_PER_STEP if n_keylines is not None else None, "exchange": xch_info,
+                "lsd_fast_division_verified_on_device": lsd_fast_div, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
