@@ -618,9 +618,13 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
     bool overflow = false;
 
     struct Touch { int c, x, y, plid; float cdist; bool have, ok; };
-    // stage A for queue entry e and this lane's neighbour slot.  Neighbour order of getValid4Neighbor (:393-405): left,
-    // right, up, down, skipping the ones outside the image.
-    auto stage_a = [&](uint32_t e) -> Touch {
+    // stage A in three parts, so that the two dependent global loads of a touch - its queue entry, then the depth sample of the neighbour that entry names -
+    // are issued a whole step before their values are needed (ncu: 40 % of the kernel's stall samples sat on those two loads when stage A was one function):
+    //   a_geom   neighbour pixel of queue entry e for this lane's slot (order of getValid4Neighbor :393-405: left, right, up, down, skipping the ones outside the
+    //            image); pixels inside a kept block are skipped by every touch and never change: dropped here, before the conflict test
+    //   (load)   the neighbour's depth sample
+    //   a_math   distance to the plane and the inlier test
+    auto a_geom = [&](uint32_t e) -> Touch {
         Touch t;
         const int sx = e & 0xfff, sy = (e >> 12) & 0xfff;
         t.plid = e >> 24; t.c = -1; t.x = 0; t.y = 0; t.cdist = -1.f; t.ok = false; t.have = false;
@@ -630,51 +634,55 @@ __global__ void __launch_bounds__(32) k_peac_flood(PeacGeom g, const uint16_t* _
         if (sy > 0) { if (n == 0 && !t.have) { t.x = sx; t.y = sy - 1; t.have = true; } --n; }
         if (sy < g.h - 1) { if (n == 0 && !t.have) { t.x = sx; t.y = sy + 1; t.have = true; } --n; }
         if (t.have) {
-            // pixels inside a kept block are skipped by every touch and never change: drop them before the conflict test
             const int by = (t.y * g.win_magic) >> 16, bx = (t.x * g.win_magic) >> 16;
             if (by < g.nbh && bx < g.nbw && sbm[by * g.nbw + bx] >= 0) t.have = false;
         }
-        if (t.have) {
-            t.c = t.y * g.w + t.x;
-            const int dv = D[t.c];
-            if (dv != 0) {
-                const FloodPlane& pr = sP[t.plid];
-                const double z = (double)dv * scale;
-                const double x = ((double)t.x - cx) * z / fx, y = ((double)t.y - cy) * z / fy;
-                const double sd = pr.n[0] * (x - pr.c[0]) + pr.n[1] * (y - pr.c[1]) + pr.n[2] * (z - pr.c[2]);
-                t.cdist = (float)fabs(sd);
-                t.ok = (double)t.cdist * (double)t.cdist < pr.th;
-            }
-        }
+        if (t.have) t.c = t.y * g.w + t.x;
         return t;
+    };
+    auto a_math = [&](Touch& t, int dv) {
+        if (t.have && dv != 0) {
+            const FloodPlane& pr = sP[t.plid];
+            const double z = (double)dv * scale;
+            const double x = ((double)t.x - cx) * z / fx, y = ((double)t.y - cy) * z / fy;
+            const double sd = pr.n[0] * (x - pr.c[0]) + pr.n[1] * (y - pr.c[1]) + pr.n[2] * (z - pr.c[2]);
+            t.cdist = (float)fabs(sd);
+            t.ok = (double)t.cdist * (double)t.cdist < pr.th;
+        }
     };
 
     Touch nxt;
     nxt.c = -1; nxt.x = nxt.y = nxt.plid = 0; nxt.cdist = -1.f; nxt.have = nxt.ok = false;
-    bool next_ready = false;                            // nxt = stage A of q[head + item_in_group] of the coming step
+    int nxt_dv = 0;                                     // depth sample of nxt's pixel, requested during the previous step
+    uint32_t e_far = 0;                                 // queue entry head + 16 + item_in_group, requested during the previous step
+    bool next_ready = false, far_ready = false;         // nxt / e_far belong to the coming step (warp-uniform)
     for (int head = 0; head < tail;) {
         const int group = min(8, tail - head);          // items consumed by this step (a partial group must not skip later pushes)
         const int k = head + item_in_group;
         Touch t = nxt;
-        if (!next_ready) {
+        if (next_ready) a_math(t, nxt_dv);
+        else {
             t.have = false; t.c = -1;
-            if (item_in_group < group) t = stage_a(q[k]);
+            if (item_in_group < group) { t = a_geom(q[k]); a_math(t, t.have ? (int)D[t.c] : 0); }
         }
         // pixel state for this step (mutable: always loaded after the previous step's stores)
         int tr = 0;
         float old = 0.f;
         if (t.have) { tr = lab[t.c]; old = dm[t.c]; }
-        // stage A of the next step for entries that already exist (entries never change once written), plus an L1
-        // prefetch of the two mutable lines it will read
-        next_ready = false;
-        if (group == 8 && head + 16 <= tail) {          // the whole next group is already queued (warp-uniform)
-            nxt = stage_a(q[k + 8]);
-            next_ready = true;
+        // the next step's neighbour and its depth request, for entries that already exist (entries never change once written), plus an L1 prefetch of the two
+        // mutable lines it will read; and the queue entries of the step after it
+        const bool whole_next = group == 8 && head + 16 <= tail;            // the whole next group is already queued (warp-uniform)
+        if (whole_next) {
+            nxt = a_geom(far_ready ? e_far : q[k + 8]);
+            nxt_dv = nxt.have ? (int)D[nxt.c] : 0;
             if (nxt.have) {
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(lab + nxt.c));
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(dm + nxt.c));
             }
         }
+        next_ready = whole_next;
+        far_ready = group == 8 && head + 24 <= tail;                         // then the next step is a whole group with a whole successor: it takes e_far
+        if (far_ready) e_far = q[k + 16];
         // ---- stage B: lanes that address the same pixel apply their touches in lane order (:444-473) ----
         const uint32_t peers = __match_any_sync(full, t.have ? t.c : -1 - lane);
         const int rank = __popc(peers & lt_mask);
