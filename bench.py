@@ -512,8 +512,6 @@ def main():
     cap = c_orb.L.pslam_orb_max_keypoints(c_orb.h)
     maxp = c_peac.L.pslam_peac_max_planes(c_peac.h)
     L = c_orb.L
-    L.pslam_lsd_fast_division_active.argtypes = [C.c_void_p]
-    lsd_fast_div = int(L.pslam_lsd_fast_division_active(c_lsd.h)) if "lsd" in STAGES else None
 
     d_gray = h_gray.to(dev)                                            # [FRAMES_PER_STEP, H, W] resident in HBM
     d_depth = h_depth.to(dev)
@@ -842,9 +840,10 @@ def main():
             c.close()
         torch.cuda.empty_cache()
         from planarslam_b200.frame import ConstructFrames, FrameOutputs
-        # PSLAM_E2E_CONTEXTS contexts (default 4) of 2 * SUB_BATCH / contexts frames each - the device memory of two full sub-batches either way.  With two contexts a
-        # copy phase of one leaves the other's half-wave kernels alone on the GPU; with four, two or three batches are always computing while one copies.
-        E2E_CTX = max(2, int(os.environ.get("PSLAM_E2E_CONTEXTS", "4")))
+        # PSLAM_E2E_CONTEXTS contexts (default 2) of 2 * SUB_BATCH / contexts frames each - the device memory of two full sub-batches either way.  Measured on B200
+        # (profiles/r2_exp_e2e_*contexts.json): two contexts of 1776 frames 5.2 k frames/s, four of 888 frames 4.6 k - smaller calls leave the one-warp-per-frame
+        # kernels with quarter-wave launches.
+        E2E_CTX = max(2, int(os.environ.get("PSLAM_E2E_CONTEXTS", "2")))
         E2E_BATCH = max(1, 2 * SUB_BATCH // E2E_CTX)
         E2E_CALLS = (FRAMES_PER_STEP + E2E_BATCH - 1) // E2E_BATCH
         fctx = [Context(W, H, E2E_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(E2E_CTX)]
@@ -939,8 +938,7 @@ def main():
                                  "sample": f"{' + '.join(STAGES)}: {best['frames']} frames in {best['seconds']} s, one pinned process per host core "
                                            f"({modes['host_cores']}), -O3 -march=x86-64-v3 (oracle/Makefile fast); modes = BASELINE.md section 3"},
                 "keypoints_per_frame": n_found / FRAMES_PER_STEP, "planes_per_frame": n_planes_found / FRAMES_PER_STEP,
-                "keylines_per_frame": n_keylines / FRAMES_PER_STEP if n_keylines is not None else None, "exchange": xch_info,
-                "lsd_fast_division_verified_on_device": lsd_fast_div, "aux": aux}
+                "keylines_per_frame": n_keylines / FRAMES_PER_STEP if n_keylines is not None else None, "exchange": xch_info, "aux": aux}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

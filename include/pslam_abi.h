@@ -409,9 +409,6 @@ int pslam_lsd_max_segments(const pslam_ctx* ctx);     /* segment capacity per fr
  * cv2 4.13 in the oracle), 0 = the published LSD rectangle iterator.  The environment variable
  * PSLAM_LSD_RECT_ENUM=published selects 0 as the default of a new context. */
 int pslam_lsd_set_rect_enumeration(pslam_ctx* ctx, int mode);
-/* 1 when the region-growing kernel evaluates cv::fastAtan2's division with its short exact sequence: a context enables it only after the sequence reproduced
- * the IEEE division bit for bit on a sweep of its operand domain on the context's device (PSLAM_LSD_FAST_DIV=0 forces the IEEE division).  0 otherwise. */
-int pslam_lsd_fast_division_active(pslam_ctx* ctx);
 /* cv::LineSegmentDetector::detect on nframes frames: segs [nframes][cap][4] float (x1 y1 x2 y2), wpn [nframes][cap][3] double
  * (width, precision, log-NFA; -1 unless refine == 2), n [nframes].  PSLAM_E_CAPACITY when a frame has more than cap segments. */
 int pslam_lsd_detect_batch(pslam_ctx* ctx, const uint8_t* gray, int nframes, int refine, float* segs, double* wpn, int cap, int32_t* n);

@@ -16,7 +16,7 @@ struct LsdBuffers {
     LsdGeom g;
     int max_batch = 0, last_n = 0, max_lines_cap = 0;
     int16_t *d_ix = nullptr, *d_ax = nullptr, *d_iy = nullptr, *d_ay = nullptr;
-    float2* d_lut = nullptr; float2* d_seed_lut = nullptr; double* d_lgamma = nullptr;
+    float2* d_lut = nullptr; double* d_lgamma = nullptr;
     uint8_t* d_gray = nullptr;        // staging for the host-pointer entry points
     uint8_t* d_scaled = nullptr; uint32_t* d_ang = nullptr; float2* d_cs = nullptr; uint32_t* d_gxy = nullptr; int32_t* d_smax = nullptr;
     uint32_t* d_reg = nullptr; uint32_t* d_order = nullptr; int32_t* d_norder = nullptr;
@@ -97,16 +97,12 @@ int lsd_alloc(pslam_ctx* c) {
         if (std::min(iy[Y1] + 1, g.h - 1) - iy[Y0] + 5 > LSD_SH) { delete Bp; return set_error(c, PSLAM_E_INVALID, "LSD tile bound (height)"); }
     }
     // cosf / sinf of the level-line angle for every possible gradient: the float sums of region_grow use libm's float routines
-    std::vector<float2> lut((size_t)1021 * 1021), seed_lut((size_t)1021 * 1021);
+    std::vector<float2> lut((size_t)1021 * 1021);
     for (int gx = -510; gx <= 510; ++gx)
         for (int gy = -510; gy <= 510; ++gy) {
             const double ang = (double)host_fast_atan2_deg((float)gx, (float)(-gy)) * LSD_DEG2RAD;
             const float af = (float)ang;
             lut[(size_t)(gx + 510) * 1021 + (gy + 510)] = make_float2(std::cos(af), std::sin(af));
-            // the first point of a region enters the sums as float(cos(angle)), float(sin(angle)) of the DOUBLE angle (deterministic sincos, lsd_detsincos.h)
-            double sn, cs;
-            lsd_sincos_body(ang, sn, cs);
-            seed_lut[(size_t)(gx + 510) * 1021 + (gy + 510)] = make_float2((float)cs, (float)sn);
         }
     // log_gamma(i), i = 0 .. LSD_LGAMMA_N - 1, with the reference's two approximations (lsd.cpp log_gamma_lanczos / _windschitl)
     std::vector<double> lgam(LSD_LGAMMA_N, 0.0);
@@ -122,7 +118,7 @@ int lsd_alloc(pslam_ctx* c) {
     }
     const size_t npx = (size_t)g.W * g.H, nb = (size_t)B.max_batch;
 #define LA(ptr, bytes) do { const int rc_ = check_cuda(c, cudaMalloc((void**)&(ptr), (bytes)), "cudaMalloc(lsd)"); if (rc_ != PSLAM_OK) { c->lsd = Bp; lsd_free(c); return rc_; } } while (0)
-    LA(B.d_ix, g.W * 2); LA(B.d_ax, g.W * 2); LA(B.d_iy, g.H * 2); LA(B.d_ay, g.H * 2); LA(B.d_lut, lut.size() * sizeof(float2)); LA(B.d_seed_lut, seed_lut.size() * sizeof(float2)); LA(B.d_lgamma, LSD_LGAMMA_N * 8);
+    LA(B.d_ix, g.W * 2); LA(B.d_ax, g.W * 2); LA(B.d_iy, g.H * 2); LA(B.d_ay, g.H * 2); LA(B.d_lut, lut.size() * sizeof(float2)); LA(B.d_lgamma, LSD_LGAMMA_N * 8);
     LA(B.d_gray, nb * g.w * g.h); LA(B.d_scaled, nb * npx); LA(B.d_ang, nb * npx * 4); LA(B.d_cs, nb * npx * 8); LA(B.d_gxy, nb * npx * 4); LA(B.d_smax, nb * 4);
     LA(B.d_reg, nb * npx * 4); LA(B.d_order, nb * npx * 4); LA(B.d_norder, nb * 4);
     LA(B.d_fail, nb * g.cand_cap * 4); LA(B.d_nfail, nb * 4);
@@ -135,21 +131,8 @@ int lsd_alloc(pslam_ctx* c) {
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_iy, iy.data(), g.H * 2, cudaMemcpyHostToDevice, st));
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_ay, ay.data(), g.H * 2, cudaMemcpyHostToDevice, st));
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_lut, lut.data(), lut.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
-    PSLAM_CUDA(c, cudaMemcpyAsync(B.d_seed_lut, seed_lut.data(), seed_lut.size() * sizeof(float2), cudaMemcpyHostToDevice, st));
     PSLAM_CUDA(c, cudaMemcpyAsync(B.d_lgamma, lgam.data(), LSD_LGAMMA_N * 8, cudaMemcpyHostToDevice, st));
     g.lgamma_tab = B.d_lgamma;
-    {   // the region kernel's division shortcut is only used after it reproduced __fdiv_rn on a sweep of its domain on THIS device (PSLAM_LSD_FAST_DIV=0 disables it)
-        const char* fd = std::getenv("PSLAM_LSD_FAST_DIV");
-        g.fast_div = 0;
-        if (!(fd && !std::strcmp(fd, "0"))) {
-            PSLAM_CUDA(c, cudaMemsetAsync(B.d_status, 0, 4, st));
-            k_lsd_fdiv_check<<<148 * 4, 256, 0, st>>>(64, B.d_status);
-            int32_t bad = -1;
-            PSLAM_CUDA(c, cudaMemcpyAsync(&bad, B.d_status, 4, cudaMemcpyDeviceToHost, st));
-            PSLAM_CUDA(c, cudaStreamSynchronize(st));
-            g.fast_div = bad == 0 ? 1 : 0;
-        }
-    }
     PSLAM_CUDA(c, cudaStreamSynchronize(st));
     c->lsd = Bp;
     return PSLAM_OK;
@@ -158,7 +141,7 @@ int lsd_alloc(pslam_ctx* c) {
 void lsd_free(pslam_ctx* c) {
     if (!c->lsd) return;
     LsdBuffers& B = *c->lsd;
-    for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_seed_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_ang, (void*)B.d_cs, (void*)B.d_gxy,
+    for (void* p : {(void*)B.d_ix, (void*)B.d_ax, (void*)B.d_iy, (void*)B.d_ay, (void*)B.d_lut, (void*)B.d_lgamma, (void*)B.d_gray, (void*)B.d_scaled, (void*)B.d_ang, (void*)B.d_cs, (void*)B.d_gxy,
                     (void*)B.d_smax, (void*)B.d_reg, (void*)B.d_order, (void*)B.d_norder, (void*)B.d_segs, (void*)B.d_wpn,
                     (void*)B.d_nsegs, (void*)B.d_status, (void*)B.d_cands, (void*)B.d_cand_nfa, (void*)B.d_ncand, (void*)B.d_fail, (void*)B.d_nfail, (void*)B.d_kl, (void*)B.d_lf, (void*)B.d_nkl, (void*)B.d_dx, (void*)B.d_dy, (void*)B.d_glocal, (void*)B.d_gglobal,
                     (void*)B.d_ldesc, (void*)B.d_lbd72})
@@ -196,7 +179,7 @@ int lsd_detect_dev(pslam_ctx* c, const uint8_t* d_gray, int nframes, int refine)
     PSLAM_LAUNCH(c, "lsd_order", k_lsd_order<<<nframes, LSD_ORDER_THREADS, LSD_ORDER_SMEM, st>>>(g, B.d_scaled, B.d_smax, B.d_order, B.d_norder));
     {
         static const int occ = [] { const char* e = std::getenv("PSLAM_LSD_OCC"); const int v = e ? std::atoi(e) : LSD_REGIONS_OCC; return v == 16 || v == 20 || v == 24 || v == 32 ? v : LSD_REGIONS_OCC; }();
-#define LSD_REGIONS_LAUNCH(V) PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<V><<<nframes, 32, 0, st>>>(g, nframes, B.d_ang, B.d_cs, B.d_gxy, B.d_seed_lut, B.d_smax, B.d_reg, B.d_order, B.d_norder, \
+#define LSD_REGIONS_LAUNCH(V) PSLAM_LAUNCH(c, "lsd_regions", k_lsd_regions<V><<<nframes, 32, 0, st>>>(g, nframes, B.d_ang, B.d_cs, B.d_gxy, B.d_smax, B.d_reg, B.d_order, B.d_norder, \
                                                                                                 B.d_cands, B.d_ncand, B.d_status))
         if (occ == 16) LSD_REGIONS_LAUNCH(16); else if (occ == 20) LSD_REGIONS_LAUNCH(20); else if (occ == 24) LSD_REGIONS_LAUNCH(24); else LSD_REGIONS_LAUNCH(32);
 #undef LSD_REGIONS_LAUNCH
@@ -245,13 +228,6 @@ int pslam_lsd_set_rect_enumeration(pslam_ctx* c, int mode) {
     if (rc != PSLAM_OK) return rc;
     c->lsd->g.rect_enum = mode;
     return PSLAM_OK;
-}
-
-int pslam_lsd_fast_division_active(pslam_ctx* c) {
-    if (!c) return PSLAM_E_INVALID;
-    const int rc = lsd_alloc(c);
-    if (rc != PSLAM_OK) return rc;
-    return c->lsd->g.fast_div;
 }
 
 static int lsd_upload(pslam_ctx* c, const uint8_t* gray, int nframes) {
