@@ -855,10 +855,22 @@ def main():
                 o = sb * E2E_BATCH
                 ConstructFrames(fctx[t], h_gray[o].data_ptr(), h_depth[o].data_ptr(), fout[t], DEPTH_FACTOR, BF, DIST_TH, 1, nframes=min(E2E_BATCH, FRAMES_PER_STEP - o))
 
+        # PoseOptimization through the host-pointer batch call of the C ABI: the problem descriptors (plain structs pointing at the host arrays) are built once -
+        # the call itself packs the edge records from the host arrays, uploads them, optimises and returns poses / outlier flags / inlier counts every time
+        from planarslam_b200.optimizer import _to_struct
+        from planarslam_b200._lib import PoseProblem
+        pose_arr = (PoseProblem * len(probs))(*[_to_struct(p_) for p_ in probs])
+        pose_T0 = np.ascontiguousarray(np.stack([p_["Tcw0"] for p_ in probs]), np.float32)
+        pose_T = np.empty_like(pose_T0)
+        pose_flags = [np.zeros(max(sum(len(p_[k]) for p_ in probs), 1), np.uint8) for k in ("Xw", "line_Xw", "plane_meas", "par_meas", "ver_meas")]
+        pose_ninl = np.zeros(len(probs), np.int32)
+        L.pslam_pose_optimization_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7
+
         def e_pose2():
             torch.cuda.set_device(local_rank)
             for _ in range(SUBS_PER_STEP):
-                opt.PoseOptimizationBatch(probs)
+                np.copyto(pose_T, pose_T0)
+                c_pose.check(L.pslam_pose_optimization_batch(c_pose.h, pose_arr, len(probs), pose_T.ctypes.data, *[f_.ctypes.data for f_ in pose_flags], pose_ninl.ctypes.data))
 
         def step_e2e():
             jobs = [pool.submit(e_frames, t) for t in range(E2E_CTX)] + ([pool.submit(e_pose2)] if "pose" in STAGES else [])
