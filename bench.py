@@ -844,7 +844,7 @@ def main():
         # (profiles/r2_exp_e2e_*contexts.json): two contexts of 1776 frames 5.2 k frames/s, four of 888 frames 4.6 k - smaller calls leave the one-warp-per-frame
         # kernels with quarter-wave launches.
         E2E_CTX = max(2, int(os.environ.get("PSLAM_E2E_CONTEXTS", "2")))
-        E2E_BATCH = max(1, 2 * SUB_BATCH // E2E_CTX)
+        E2E_BATCH = max(1, 2 * min(SUB_BATCH, int(os.environ.get("PSLAM_E2E_WAVE", str(DEFAULT_WAVE)))) // E2E_CTX)      # (two contexts of one clustering wave each: ~110 GB)
         E2E_CALLS = (FRAMES_PER_STEP + E2E_BATCH - 1) // E2E_BATCH
         fctx = [Context(W, H, E2E_BATCH, device=local_rank, nfeatures=NFEATURES) for _ in range(E2E_CTX)]
         fout = [FrameOutputs(c, E2E_BATCH, MAX_LINES, PP_CAP, normals=True, pinned=True) for c in fctx]
