@@ -9,7 +9,6 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 
 tail -2 $OUT/smoke.log
 ( time timeout 600 python bench.py --steps 4 --warmup 3 ) > $OUT/bench_default.json 2> $OUT/bench_default.err; echo "bench default rc=$?" >> $OUT/summary.txt
 tail -3 $OUT/bench_default.err
-( time timeout 300 python bench.py --impl reference --steps 2 --warmup 1 ) > $OUT/bench_reference.json 2> $OUT/bench_reference.err; echo "bench reference rc=$?" >> $OUT/summary.txt
 PSLAM_AUX_NEW=0 PSLAM_CPU_SECONDS=0.5 timeout 420 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_ncu.csv python bench.py --steps 1 --warmup 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?" >> $OUT/summary.txt
 ( time PSLAM_AUX_NEW=0 PSLAM_CPU_SECONDS=0.5 PSLAM_CONFIG=5 timeout 420 python bench.py --steps 2 --warmup 3 ) > $OUT/bench_config5.json 2> $OUT/bench_config5.err; echo "bench config5 rc=$?" >> $OUT/summary.txt
 ( time PSLAM_AUX_NEW=0 PSLAM_CPU_SECONDS=0.5 timeout 420 ncu --set full --clock-control none -k regex:"k_lsd_regions|k_peac_flood" -c 2 -f -o $OUT/top2 python bench.py --steps 1 --warmup 1 ) > $OUT/ncu_top2.log 2>&1; echo "ncu top2 rc=$?" >> $OUT/summary.txt
