@@ -770,7 +770,8 @@ def main():
     # DRAM bytes per frame of the dominant kernels from the committed round-2 `ncu --set full` captures (dram__bytes_read.sum + dram__bytes_write.sum of one
     # launch / its frames: profiles/r2_ncu_full_lsd_kernels.csv at 3552 frames, profiles/r2_ncu_full_peac_kernels.csv at 1776; k_peac_flood from
     # profiles/r1_ncu_full_summary.csv at 296 - its round-2 capture returned no DRAM counters), scaled to this run's frames per launch
-    NCU_DRAM_BYTES_PER_FRAME = {"lsd_regions": (99.155276e9 + 9.574393e9) / 3552, "peac_cluster": (8.573231e9 + 3.334866e9) / 1776,
+    # (k_lsd_regions re-captured after its last change at the benchmark launch size: 99.141 + 9.583 GB per 3552 frames, profiles/r2_final_ncu_full_lsd_regions_peac_flood.csv)
+    NCU_DRAM_BYTES_PER_FRAME = {"lsd_regions": (99.140878e9 + 9.582504e9) / 3552, "peac_cluster": (8.573231e9 + 3.334866e9) / 1776,
                                 "peac_flood": (4.953115e9 + 1.131992e9) / 296, "lsd_improve": (3.480971e9 + 1.401838e9) / 3552}
     traffic = NCU_DRAM_BYTES_PER_FRAME.get(dom)
     roofline = {"kernel": dom, "bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
