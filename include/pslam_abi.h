@@ -156,7 +156,7 @@ int pslam_planes_post_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nfr
  * every cone test there, like in the reference) */
 int pslam_surface_normals_batch_dev(pslam_ctx* ctx, const uint16_t* d_depth, int nframes, float* d_normals8, float* d_normals3);
 /* Replaces  void MapPlane::UpdateCoefficientsAndPoints()  and  (const Frame& pF, int id)      include/MapPlane.h, src/MapPlane.cc:298-365
- * (SURVEY.md 8 f4): per map plane ("job") the clouds of its observations - KeyFrame::mvPlanePoints[id] with T = Converter::toMatrix4d(GetPoseInverse());
+ * (called from src/Optimizer.cc:541, 2676, 2989, src/Tracking.cc:300, 1207, 2270): per map plane ("job") the clouds of its observations - KeyFrame::mvPlanePoints[id] with T = Converter::toMatrix4d(GetPoseInverse());
  * for the second overload the frame's cloud with T = toSE3Quat(mTcw).inverse() plus the plane's current cloud with the identity - are transformed like
  * pcl::transformPointCloud (double 4x4, row-major here, on float points), concatenated and reduced by pcl::VoxelGrid (leaf 0.1 m).  out_pts [n_jobs][cap][3]
  * receives the new MapPlane::mvPlanePoints (voxel centroids in ascending voxel index), n_out [n_jobs] their counts.  Clouds as CSR: job_cloud_off [n_jobs + 1]
