@@ -45,3 +45,16 @@ def test_selection_logic_matches_oracle(host_lib, case):
                                                            words.ctypes.data)
         oc, ow, os_ = oracle_lib.detect_relocalization_candidates(db, stale)
         assert n == len(oc) and np.array_equal(cand[:n], oc) and np.array_equal(words[:n_kf], ow) and np.array_equal(score, os_)
+
+
+def test_selection_logic_edge_cases(host_lib):
+    from test_oracle_loopclose_ref import _edge_databases
+    for name, db in _edge_databases():
+        d, n_kf, covis, stride = oracle_lib._db_args(db)
+        for min_score in (0.0, 0.02, 0.9):
+            cand, words, score = np.zeros(max(n_kf, 1), np.int32), np.zeros(max(n_kf, 1), np.int32), np.full(max(n_kf, 1), -1.0, np.float32)
+            n = host_lib.host_detect_loop_candidates(d["q_word"].ctypes.data, d["q_val"].ctypes.data, len(d["q_word"]), n_kf, d["off"].ctypes.data, d["word"].ctypes.data,
+                                                     d["val"].ctypes.data, covis, stride, d["connected"].ctypes.data, min_score, cand.ctypes.data, words.ctypes.data,
+                                                     score.ctypes.data)
+            oc, ow, os_ = oracle_lib.detect_loop_candidates(db, min_score)
+            assert n == len(oc) and np.array_equal(cand[:n], oc) and np.array_equal(words[:n_kf], ow) and np.array_equal(score[:n_kf], os_), (name, min_score)

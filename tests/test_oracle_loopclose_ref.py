@@ -55,3 +55,32 @@ def test_search_by_bow_kf_identical_to_compiled_reference():
             assert n == int((m >= 0).sum())
             total += n
     assert total > 1000
+
+
+def _edge_databases():
+    base = synth_lines.make_bow_database(seed=9, n_kf=50, n_words=600, words_per_kf=150, n_similar=12)
+    yield "all connected", dict(base, connected=np.ones(50, np.uint8))
+    empty_q = dict(base, q_word=np.zeros(0, np.int32), q_val=np.zeros(0))
+    yield "empty query", empty_q
+    off = base["off"].copy()
+    cut = off[21] - off[20]                       # key frame 20 loses all its words
+    word = np.concatenate([base["word"][:off[20]], base["word"][off[21]:]])
+    val = np.concatenate([base["val"][:off[20]], base["val"][off[21]:]])
+    off2 = off.copy(); off2[21:] -= cut
+    yield "key frame without words", dict(base, off=off2, word=word, val=val)
+    covis = base["covis"].copy(); covis[:, :] = -1
+    yield "no covisibility", dict(base, covis=covis)
+    covis = base["covis"].copy(); covis[:, 0] = 25
+    yield "everyone's best neighbour is key frame 25", dict(base, covis=covis)
+
+
+def test_candidate_edge_cases_identical_to_compiled_reference():
+    for name, db in _edge_databases():
+        for min_score in (0.0, 0.02, 0.9):
+            c, w, s = oracle_lib.detect_loop_candidates(db, min_score)
+            rc, rw, rs = ref_lib.ref_detect_loop_candidates(db, min_score)
+            assert np.array_equal(c, rc) and np.array_equal(w, rw) and np.array_equal(s, rs), (name, min_score)
+        n_kf = len(db["off"]) - 1
+        c, w, s = oracle_lib.detect_relocalization_candidates(db, np.full(n_kf, 0.01, np.float32))
+        rc, rw, rs = ref_lib.ref_detect_relocalization_candidates(db, np.full(n_kf, 0.01, np.float32))
+        assert np.array_equal(c, rc) and np.array_equal(w, rw) and np.array_equal(s, rs), name
