@@ -387,14 +387,15 @@ int pslam_lba_run_packed(pslam_ctx* ctx);
 int pslam_lba_fetch(pslam_ctx* ctx, pslam_lba_result* res /* [n] */);
 
 /* ---- Line segments ---------------------------------------------------------------------------------
- * Replaces the detector half of
+ * Replaces
  *     void LineSegment::ExtractLineSegment(const cv::Mat& img, std::vector<KeyLine>& keylines, cv::Mat& ldesc,
  *                                          std::vector<Eigen::Vector3d>& keylineFunctions, float scale, int numOctaves)
  *     include/LSDextractor.h:349, src/LSDextractor.cpp:13-39  (called from Frame::ExtractLSD, src/Frame.cc:170-179)
  * i.e. LSDDetector::detect (opencv_contrib line_descriptor, one octave) = cv::LineSegmentDetector(LSD_REFINE_ADV) on the
  * input image, the KeyLine records built from the segments, the reference's "sort by response, keep 40, renumber class_id"
  * filter (:18-26) and the line functions sp x ep / |sp x ep| (:30-38).  The LBD descriptors (BinaryDescriptor::compute, :28)
- * are NOT produced: no upstream implementation is obtainable here to pin them against.
+ * come from pslam_lines_extract_describe_batch below (restated from the published algorithm: no upstream implementation is
+ * obtainable here to pin them against); the *_extract_* entry points without "describe" stop before them.
  * pslam_keyline has the memory layout of cv::line_descriptor::KeyLine (17 four-byte fields, 68 bytes).
  * refine: 0 = LSD_REFINE_NONE, 1 = LSD_REFINE_STD, 2 = LSD_REFINE_ADV (what the reference runs). */
 typedef struct pslam_keyline {

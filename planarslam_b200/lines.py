@@ -2,7 +2,8 @@
 
     LineSegment(ctx).ExtractLineSegment(gray) -> (keylines structured array, line functions [n][3])
 
-The LBD descriptors of the reference's ExtractLineSegment are not produced (no pinnable upstream implementation here).
+ExtractLineSegmentWithDescriptors adds the LBD descriptors (pslam_lines_extract_describe_batch; restated from the published algorithm - no pinnable upstream
+implementation here).
 """
 from __future__ import annotations
 
