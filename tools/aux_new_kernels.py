@@ -76,7 +76,7 @@ def main():
     TrackManhattanFrame(ctx, Rb, nb, dbm)
     dt = time.perf_counter() - t0
     out["manhattan"]["frames_per_sec_host_buffers"] = round(BATCH / dt, 1)
-    out["note"] = f"host-buffer calls (copies and packing included), {BATCH} frames per call; kernels are one-thread-per-frame first versions"
+    out["note"] = f"host-buffer calls (copies and packing included), {BATCH} frames per call; warp-per-frame kernels (k_lines3d_warp, k_track_manhattan_warp)"
     print(json.dumps(out))
 
 
