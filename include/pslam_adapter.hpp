@@ -1,9 +1,9 @@
 // pslam_adapter.hpp — header-only C++ adapter that re-creates the reference's class interfaces on top of the C ABI
 // (include/pslam_abi.h), so Frame / Tracking can switch to the B200 path without changing their call sites.
 //
-// The OpenCV/Eigen-typed overloads (cv::InputArray, std::vector<cv::KeyPoint>, cv::Mat K, ...) are compiled only when
-// PSLAM_WITH_OPENCV is defined (OpenCV headers are not installed in the authoring image); the plain-pointer overloads
-// below carry the same names and argument order and are what tests/test_adapter_compiles.py builds.
+// This header carries the reference's method names and argument order over plain pointers / std::vector (no OpenCV, Eigen or PCL needed;
+// tests/test_adapter_compiles.py builds it).  The calls WITH the reference's own argument types (Frame*, KeyFrame*, cv::InputArray,
+// std::vector<MapPoint*> ...) are in include/pslam_reference_adapter.hpp, which is compiled inside the PlanarSLAM tree.
 //
 //   Planar_SLAM::ORBextractor::operator()      include/ORBextractor.h:59-61   -> pslam_orb_extract
 //   ORBextractor getters                       include/ORBextractor.h:63-83   -> pslam_orb_get_scale_tables
