@@ -35,18 +35,29 @@ class KeyframeDescriptorExchange:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
 
-    def gather(self, desc, count: int):
+    def gather(self, desc, count, sync_counts: bool = True):
+        """count: a Python int, or a one-element integer tensor on desc's device (then nothing crosses to the host on the way in).  With sync_counts=False the
+        per-rank counts come back as an int64 tensor on the device as well: the call is then free of host round trips (the block and the gathered buffer are
+        allocated once and reused, so the returned views are valid until the next call; this is the NCCL comparison path - the product exchange is
+        PeerDescriptorExchange below)."""
         import torch
         if desc.shape != (self.cap, 32) or desc.dtype != torch.uint8:
             raise ValueError("desc must be a [cap, 32] uint8 tensor")
-        block = torch.zeros(self.cap * 32 + 8, dtype=torch.uint8, device=desc.device)
-        block[: self.cap * 32] = desc.reshape(-1)
-        block[self.cap * 32:] = torch.tensor([count], dtype=torch.int64).view(torch.uint8).to(desc.device)
-        out = torch.empty(self.world * block.numel(), dtype=torch.uint8, device=desc.device)
+        n = self.cap * 32
+        if getattr(self, "_block", None) is None or self._block.device != desc.device:
+            self._block = torch.zeros(n + 8, dtype=torch.uint8, device=desc.device)
+            self._out = torch.empty(self.world * (n + 8), dtype=torch.uint8, device=desc.device)
+        block, out = self._block, self._out
+        block[:n] = desc.reshape(-1)
+        if torch.is_tensor(count):
+            block[n:] = count.reshape(1).to(torch.int64).view(torch.uint8)
+        else:
+            block[n:] = torch.tensor([int(count)], dtype=torch.int64).view(torch.uint8).to(desc.device)
         self.dist.all_gather_into_tensor(out, block, group=self.group)
-        out = out.view(self.world, -1)
-        counts = out[:, self.cap * 32:].contiguous().view(torch.int64).reshape(self.world).cpu().numpy()
-        return out[:, : self.cap * 32].reshape(self.world, self.cap, 32), counts
+        rows = out.view(self.world, -1)
+        counts = rows[:, n:].contiguous().view(torch.int64).reshape(self.world)
+        gathered = rows[:, :n].reshape(self.world, self.cap, 32)
+        return gathered, (counts.cpu().numpy() if sync_counts else counts)
 
     @staticmethod
     def compact(gathered, counts):
